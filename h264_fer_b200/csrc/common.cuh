@@ -1,0 +1,133 @@
+// fh264_b200 — shared device-side definitions.
+// Data layout in HBM (per sequence): planar u8 pictures (stride == width), 16 quarter-pel luma
+// planes, 80 uint16 box-sum feature planes, a 64x64-tile index of plane-0 positions sorted by (K0>>7, K1>>6),
+// per-partition phase-A lists, per-MB motion records and the ABI result records.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/fh264_b200.h"
+
+#define FH_TILE 64              // spatial tile of the stage-2 index
+#define FH_TILE_SHIFT 6
+#define FH_CELLS 16384          // (K0>>7) * 128 + (K1>>6)
+#define FH_TSTART_PITCH 16386   // uint16 per tile: 16384 cell starts + total + pad
+#define FH_S3_MAX 33            // list slots evaluated in stages 2/3 (moestimation.cpp:498,511)
+#define FH_S1_MAX 17            // list slots evaluated in stage 1 (moestimation.cpp:460)
+#define FH_S2_SMEM_CAP 2048     // stage-2 survivors held in shared memory per partition
+#define FH_MAX_WINDOW 64
+#define FH_COST_EMPTY 100000000 // stages 2/3 ignore list slots with cost >= 1e8 (moestimation.cpp:499,512)
+
+// status word indices (uint32 per sequence)
+#define ST_FLAGS 0
+#define ST_S2CURSOR 1
+#define ST_COUNTS 2   // ..6
+#define ST_SAD_LO 8
+#define ST_SAD_HI 9
+#define ST_TICKET 10
+#define ST_FLAGS_NEXT 11   // flags raised by phase R for the NEXT picture's reference
+#define ST_WORDS 16
+#define FLAG_UB_INPUT 1u
+#define FLAG_CAPACITY 2u
+
+struct Geo {
+    int W, H, Wmb, Hmb, nmb, nparts, tilesx, tilesy, ntiles;
+    int WH;
+};
+
+struct __align__(16) TileEntry { uint16_t x, y, k0, k1, k2, k3, k4, pad; };
+
+struct __align__(16) MbMotion {       // phase B output per macroblock (48 bytes)
+    int16_t mb_type, num_parts;
+    int16_t mv[4][2];
+    int16_t mvd[4][2];
+    uint16_t sad[4];
+    int16_t maxdiff, pad;
+};
+
+struct S3Entry { int16_t mvx, mvy; uint16_t sad, pad; };           // stage-3 list slot, list order
+struct PartA { uint16_t suma[5]; uint16_t n3; uint32_t s2_off; uint32_t n2; };   // per 8x8 partition
+
+static_assert(sizeof(fh264_mb_result) == 832, "ABI record size");
+static_assert(sizeof(MbMotion) == 48, "MbMotion size");
+
+struct SeqDev {
+    uint8_t *cur[3];        // `frame`: source picture (Y, Cb, Cr)
+    uint8_t *ref[3];        // `dpb`: previous reconstruction
+    uint8_t *rec[3];        // reconstruction of the picture being coded (swapped with ref afterwards)
+    uint8_t *planes;        // refFrameInterpolated[f].L, f-major, WH each (+16 bytes slack at the end)
+    uint16_t *kar;          // refFrameKar[k][f]: plane (f*5+k), WH each
+    TileEntry *tent;        // ntiles * 4096 entries
+    uint16_t *tstart;       // ntiles * FH_TSTART_PITCH
+    PartA *parta;           // nparts
+    S3Entry *s3;            // nparts * 33
+    uint2 *s2pool;          // stage-2 candidates in arrival order: {dx | dy<<16, feat | sad<<18}
+    uint32_t s2pool_size;
+    MbMotion *motion;       // nmb
+    uint32_t *done;         // nmb: epoch of the picture whose motion record is final
+    fh264_mb_result *results;
+    uint32_t *status;       // ST_WORDS
+};
+
+__device__ __forceinline__ int iabs_(int a) { return a < 0 ? -a : a; }
+__device__ __forceinline__ int clampi_(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ int clip255_(int v) { return min(max(v, 0), 255); }
+// mocomp.cpp:39-40,47
+__device__ __forceinline__ int tap6_(int a, int b, int c, int d, int e, int f) { return clip255_((a - 5 * b + 20 * c + 20 * d - 5 * e + f + 16) >> 5); }
+__device__ __forceinline__ int mid_(int a, int b) { return (a + b + 1) >> 1; }
+
+// 8 consecutive bytes starting at an arbitrary address, as two little-endian words (reads up to 3 bytes past).
+__device__ __forceinline__ uint2 load8_unaligned(const uint8_t *p)
+{
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+
+// satdLuma8x8MVs (moestimation.cpp:175-195), one row: |cur row - plane row| with the reference's clamping rule
+// (block origin clamped to the picture as a whole, then each index clamped at the right/bottom edge only).
+__device__ __forceinline__ int sad_row8(uint2 cur, const uint8_t *plane, int W, int H, int x0, int y)
+{
+    y = min(y, H - 1);
+    const uint8_t *p = plane + (size_t)y * W + x0;
+    uint2 r;
+    if (x0 + 8 <= W) {
+        r = load8_unaligned(p);
+    } else {
+        uint32_t b[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) b[i] = plane[(size_t)y * W + min(x0 + i, W - 1)];
+        r.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        r.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+    }
+    return __vsadu4(cur.x, r.x) + __vsadu4(cur.y, r.y);
+}
+
+// Feature distance (moestimation.cpp:267-276).
+__device__ __forceinline__ int feat_dist(const int s[5], int K0, int K1, int K2, int K3, int K4)
+{
+    int d = iabs_(s[0] - K0);
+    d += iabs_(s[1] - K1) + iabs_(s[0] - s[1] - K0 + K1);
+    d += iabs_(s[2] - K2) + iabs_(s[0] - s[2] - K0 + K2);
+    d += iabs_(s[3] - K3) + iabs_(s[0] - s[3] - K0 + K3);
+    d += iabs_(s[4] - K4) + iabs_(s[0] - s[4] - K0 + K4);
+    return d;
+}
+
+// suma[0..4] of one 8x8 source block held as 8 rows of two words (moestimation.cpp:440-451):
+// all, rows 0-3, columns 0-3, rows {0,1,4,5}, columns {0,1,4,5}.
+__device__ __forceinline__ void block_sums(const uint2 rows[8], int s[5])
+{
+    s[0] = s[1] = s[2] = s[3] = s[4] = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int lo = __vsadu4(rows[r].x, 0), hi = __vsadu4(rows[r].y, 0);
+        int c01 = __vsadu4(rows[r].x & 0x0000ffffu, 0) + __vsadu4(rows[r].y & 0x0000ffffu, 0);
+        s[0] += lo + hi;
+        if (r < 4) s[1] += lo + hi;
+        s[2] += lo;
+        if ((r & 3) < 2) s[3] += lo + hi;
+        s[4] += c01;
+    }
+}

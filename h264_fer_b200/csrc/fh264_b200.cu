@@ -1,0 +1,432 @@
+// fh264_b200 — C-ABI shim (include/fh264_b200.h) over the sm_100a kernels. One translation unit.
+// Session = one GPU + `batch` sequences advancing in lockstep; all work is enqueued on one CUDA stream.
+// There is deliberately NO CPU fallback: without a usable sm_100 device every entry point fails loudly.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "phase_r.cuh"
+#include "phase_a.cuh"
+#include "phase_b.cuh"
+#include "phase_c.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_err = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(FH264_E_CUDA, #call, e_); } while (0)
+#define CKL() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(FH264_E_CUDA, "kernel launch", e_); } while (0)
+
+struct fh264_session {
+    Geo g;
+    int batch, device;
+    cudaStream_t stream;
+    bool own_stream;
+    std::vector<SeqDev> h;          // host mirror of the device SeqDev array
+    SeqDev *d_seqs;
+    int *d_wf_order;
+    uint32_t *d_ticket;
+    uint32_t epoch;
+    std::vector<char> has_ref;
+    uint32_t *h_status;             // pinned: batch * ST_WORDS, snapshot after phase C of the last encode
+    uint32_t *h_sad;                // pinned: ST_WORDS scratch for scene_sad
+    cudaEvent_t ev[5];
+    bool timed;
+    std::vector<void *> allocs;
+    // scratch for the stand-alone entry points
+    uint8_t *d_scr[3]; int16_t *d_scr16[2]; size_t scr_mbs;
+};
+
+__global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
+{
+    uint32_t *st = seqs[seq0 + threadIdx.x].status;
+    st[ST_FLAGS] = st[ST_FLAGS_NEXT];
+    st[ST_S2CURSOR] = 0;
+    for (int i = 0; i < 5; i++) st[ST_COUNTS + i] = 0;
+    if (threadIdx.x == 0) *ticket = 0;
+}
+__global__ void k_begin_ref(SeqDev *seqs, int seq0) { seqs[seq0 + threadIdx.x].status[ST_FLAGS_NEXT] = 0; }
+__global__ void k_swap_ref(SeqDev *seqs, int seq0)
+{
+    SeqDev &S = seqs[seq0 + threadIdx.x];
+    for (int c = 0; c < 3; c++) { uint8_t *t = S.ref[c]; S.ref[c] = S.rec[c]; S.rec[c] = t; }
+}
+
+template <typename T>
+static cudaError_t dalloc(fh264_session *s, T **p, size_t count)
+{
+    void *v = nullptr;
+    cudaError_t e = cudaMalloc(&v, count * sizeof(T) + 256);
+    if (e == cudaSuccess) { s->allocs.push_back(v); e = cudaMemset(v, 0, count * sizeof(T) + 256); }
+    *p = (T *)v;
+    return e;
+}
+
+extern "C" int fh264_abi_version(void) { return FH264_ABI_VERSION; }
+extern "C" const char *fh264_last_error(void) { return g_err.c_str(); }
+
+extern "C" int fh264_close(fh264_session *s)
+{
+    if (!s) return FH264_OK;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    for (void *p : s->allocs) cudaFree(p);
+    for (int i = 0; i < 3; i++) if (s->d_scr[i]) cudaFree(s->d_scr[i]);
+    for (int i = 0; i < 2; i++) if (s->d_scr16[i]) cudaFree(s->d_scr16[i]);
+    if (s->h_status) cudaFreeHost(s->h_status);
+    if (s->h_sad) cudaFreeHost(s->h_sad);
+    for (int i = 0; i < 5; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return FH264_OK;
+}
+
+extern "C" int fh264_open(int width, int height, int batch, int device, fh264_session **out)
+{
+    if (!out) return fail(FH264_E_ARG, "out is null");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || (width & 15) || (height & 15)) return fail(FH264_E_ARG, "width/height must be positive multiples of 16");
+    if ((width >> 4) * (height >> 4) > 10000) return fail(FH264_E_ARG, "more than 10000 macroblocks (reference limit, h264_globals.cpp:180)");
+    if (width > 65535 || height > 65535) return fail(FH264_E_ARG, "picture dimension exceeds 65535");
+    if (batch < 1 || batch > 1024) return fail(FH264_E_ARG, "batch must be in 1..1024");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FH264_E_NO_DEVICE, "no CUDA device: fh264_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(FH264_E_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(FH264_E_NO_DEVICE, "device is not sm_100 (B200): kernels are built for sm_100a only");
+    CK(cudaSetDevice(device));
+
+    fh264_session *s = new fh264_session();
+    s->batch = batch; s->device = device; s->epoch = 0; s->timed = false; s->own_stream = true;
+    s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->scr_mbs = 0;
+    for (int i = 0; i < 5; i++) s->ev[i] = nullptr;
+    for (int i = 0; i < 3; i++) s->d_scr[i] = nullptr;
+    s->d_scr16[0] = s->d_scr16[1] = nullptr;
+    Geo &g = s->g;
+    g.W = width; g.H = height; g.Wmb = width >> 4; g.Hmb = height >> 4; g.nmb = g.Wmb * g.Hmb; g.nparts = g.nmb * 4;
+    g.tilesx = (width + FH_TILE - 1) / FH_TILE; g.tilesy = (height + FH_TILE - 1) / FH_TILE; g.ntiles = g.tilesx * g.tilesy;
+    g.WH = width * height;
+    s->has_ref.assign(batch, 0);
+    s->h.resize(batch);
+#define OPEN_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(FH264_E_CUDA, #call, e_); fh264_close(s); return FH264_E_CUDA; } } while (0)
+    OPEN_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 5; i++) OPEN_CK(cudaEventCreate(&s->ev[i]));
+    OPEN_CK(cudaHostAlloc((void **)&s->h_status, sizeof(uint32_t) * ST_WORDS * batch, cudaHostAllocDefault));
+    OPEN_CK(cudaHostAlloc((void **)&s->h_sad, sizeof(uint32_t) * ST_WORDS, cudaHostAllocDefault));
+    memset(s->h_status, 0, sizeof(uint32_t) * ST_WORDS * batch);
+    const size_t WH = (size_t)g.WH, CWH = WH / 4;
+    fh264_mb_result *results = nullptr;
+    OPEN_CK(dalloc(s, &results, (size_t)batch * g.nmb));
+    for (int b = 0; b < batch; b++) {
+        SeqDev &S = s->h[b];
+        for (int c = 0; c < 3; c++) {
+            OPEN_CK(dalloc(s, &S.cur[c], c ? CWH : WH));
+            OPEN_CK(dalloc(s, &S.ref[c], c ? CWH : WH));
+            OPEN_CK(dalloc(s, &S.rec[c], c ? CWH : WH));
+        }
+        OPEN_CK(dalloc(s, &S.planes, 16 * WH));
+        OPEN_CK(dalloc(s, &S.kar, 80 * WH));
+        OPEN_CK(dalloc(s, &S.tent, (size_t)g.ntiles * FH_TILE * FH_TILE));
+        OPEN_CK(dalloc(s, &S.tstart, (size_t)g.ntiles * FH_TSTART_PITCH));
+        OPEN_CK(dalloc(s, &S.parta, (size_t)g.nparts));
+        OPEN_CK(dalloc(s, &S.s3, (size_t)g.nparts * FH_S3_MAX));
+        S.s2pool_size = (uint32_t)std::min<size_t>((size_t)g.nparts * 320, 0x7fffffffu);
+        OPEN_CK(dalloc(s, &S.s2pool, (size_t)S.s2pool_size));
+        OPEN_CK(dalloc(s, &S.motion, (size_t)g.nmb));
+        OPEN_CK(dalloc(s, &S.done, (size_t)g.nmb));
+        OPEN_CK(dalloc(s, &S.status, (size_t)ST_WORDS));
+        S.results = results + (size_t)b * g.nmb;
+    }
+    OPEN_CK(dalloc(s, &s->d_seqs, (size_t)batch));
+    OPEN_CK(cudaMemcpy(s->d_seqs, s->h.data(), sizeof(SeqDev) * batch, cudaMemcpyHostToDevice));
+    // anti-diagonal (x + 2y) visiting order of the wavefront
+    std::vector<int> order(g.nmb);
+    for (int i = 0; i < g.nmb; i++) order[i] = i;
+    const int Wmb = g.Wmb;
+    std::stable_sort(order.begin(), order.end(), [Wmb](int a, int b) { return (a % Wmb) + 2 * (a / Wmb) < (b % Wmb) + 2 * (b / Wmb); });
+    OPEN_CK(dalloc(s, &s->d_wf_order, (size_t)g.nmb));
+    OPEN_CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.nmb, cudaMemcpyHostToDevice));
+    OPEN_CK(dalloc(s, &s->d_ticket, (size_t)4));
+    OPEN_CK(cudaFuncSetAttribute(k_tile_index, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_CELLS * 4));
+    OPEN_CK(cudaDeviceSynchronize());
+    *out = s;
+    return FH264_OK;
+}
+
+extern "C" int fh264_set_stream(fh264_session *s, void *cuda_stream)
+{
+    if (!s) return fail(FH264_E_ARG, "null session");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
+    if (cuda_stream) s->stream = (cudaStream_t)cuda_stream;
+    else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
+    return FH264_OK;
+}
+
+extern "C" int fh264_sync(fh264_session *s)
+{
+    if (!s) return fail(FH264_E_ARG, "null session");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    return FH264_OK;
+}
+
+extern "C" void *fh264_host_alloc(size_t bytes) { void *p = nullptr; return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+extern "C" void fh264_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+static int check_seq(fh264_session *s, int seq0, int nseq)
+{
+    if (!s) return fail(FH264_E_ARG, "null session");
+    if (seq0 < 0 || nseq < 1 || seq0 + nseq > s->batch) return fail(FH264_E_ARG, "sequence range outside the session batch");
+    return FH264_OK;
+}
+
+extern "C" int fh264_upload_source(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!y || !cb || !cr) return fail(FH264_E_ARG, "null plane");
+    CK(cudaSetDevice(s->device));
+    const size_t WH = (size_t)s->g.WH;
+    CK(cudaMemcpyAsync(s->h[seq].cur[0], y, WH, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->h[seq].cur[1], cb, WH / 4, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->h[seq].cur[2], cr, WH / 4, cudaMemcpyHostToDevice, s->stream));
+    return FH264_OK;
+}
+
+// Phase R on the current dpb of sequences [seq0, seq0+nseq).
+static int launch_phase_r(fh264_session *s, int seq0, int nseq)
+{
+    const Geo &g = s->g;
+    k_begin_ref<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0);
+    dim3 gi((g.W + IT_W - 1) / IT_W, (g.H + IT_H - 1) / IT_H, nseq);
+    k_interp<<<gi, 256, 0, s->stream>>>(s->d_seqs, seq0, g);
+    dim3 gf((g.W + FT_W - 1) / FT_W, (g.H + FT_H - 1) / FT_H, 16 * nseq);
+    k_features<<<gf, 256, 0, s->stream>>>(s->d_seqs, seq0, g);
+    dim3 gt(g.ntiles, nseq);
+    k_tile_index<<<gt, 256, FH_CELLS * 4, s->stream>>>(s->d_seqs, seq0, g);
+    CKL();
+    return FH264_OK;
+}
+
+extern "C" int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!y || !cb || !cr) return fail(FH264_E_ARG, "null plane");
+    CK(cudaSetDevice(s->device));
+    const size_t WH = (size_t)s->g.WH;
+    CK(cudaMemcpyAsync(s->h[seq].ref[0], y, WH, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->h[seq].ref[1], cb, WH / 4, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->h[seq].ref[2], cr, WH / 4, cudaMemcpyHostToDevice, s->stream));
+    rc = launch_phase_r(s, seq, 1); if (rc) return rc;
+    s->has_ref[seq] = 1;
+    return FH264_OK;
+}
+
+extern "C" int fh264_scene_sad(fh264_session *s, int seq, uint64_t *sad)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!sad) return fail(FH264_E_ARG, "null output");
+    if (!s->has_ref[seq]) return fail(FH264_E_STATE, "scene_sad before any reference picture (dpb.L == NULL => IDR, ref_frames.cpp:191)");
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemsetAsync(s->h[seq].status + ST_SAD_LO, 0, 8, s->stream));
+    dim3 gs(148 * 2, 1);
+    k_scene_sad<<<gs, 256, 0, s->stream>>>(s->d_seqs, seq, s->g);
+    CKL();
+    CK(cudaMemcpyAsync(s->h_sad, s->h[seq].status, sizeof(uint32_t) * ST_WORDS, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *sad = (uint64_t)s->h_sad[ST_SAD_LO] | ((uint64_t)s->h_sad[ST_SAD_HI] << 32);
+    return FH264_OK;
+}
+
+extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const fh264_params *p, fh264_mb_result *results)
+{
+    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
+    if (!p) return fail(FH264_E_ARG, "null params");
+    if (p->qp < 0 || p->qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
+    if (p->window < 0 || p->window > FH_MAX_WINDOW) return fail(FH264_E_UNSUPPORTED, "WindowSize above 64 is not supported");
+    if (p->maxdiff_set < -1) return fail(FH264_E_ARG, "maxdiff_set below -1");
+    for (int b = seq0; b < seq0 + nseq; b++)
+        if (!s->has_ref[b]) return fail(FH264_E_STATE, "encode_p before any reference picture (upload_recon first)");
+    CK(cudaSetDevice(s->device));
+    const Geo &g = s->g;
+    fh264_params prm = *p;
+    prm.basic = prm.basic ? 1 : 0;
+    s->epoch++;
+    cudaStream_t st = s->stream;
+    CK(cudaEventRecord(s->ev[0], st));
+    k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, s->d_ticket);
+    if (!prm.basic) {
+        dim3 ga(g.nparts, nseq);
+        k_stage3<<<ga, PA_NT, 0, st>>>(s->d_seqs, seq0, g, prm);
+        k_stage2<<<ga, PA_NT, 0, st>>>(s->d_seqs, seq0, g, prm);
+    }
+    CK(cudaEventRecord(s->ev[1], st));
+    k_phase_b<<<(unsigned)(g.nmb * nseq), PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
+    CK(cudaEventRecord(s->ev[2], st));
+    dim3 gc((g.nmb + 3) / 4, nseq);
+    k_phase_c<<<gc, 128, 0, st>>>(s->d_seqs, seq0, g, prm);
+    CKL();
+    CK(cudaEventRecord(s->ev[3], st));
+    for (int b = seq0; b < seq0 + nseq; b++)
+        CK(cudaMemcpyAsync(s->h_status + (size_t)b * ST_WORDS, s->h[b].status, sizeof(uint32_t) * ST_WORDS, cudaMemcpyDeviceToHost, st));
+    if (results)
+        CK(cudaMemcpyAsync(results, s->h[seq0].results, sizeof(fh264_mb_result) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, st));
+    // dpb := reconstruction (frameDeepCopy, ref_frames.cpp:17-35) by pointer swap, then phase R for the next picture
+    k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
+    for (int b = seq0; b < seq0 + nseq; b++)
+        for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
+    rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
+    CK(cudaEventRecord(s->ev[4], st));
+    s->timed = true;
+    return FH264_OK;
+}
+
+extern "C" int fh264_encode_p(fh264_session *s, int seq0, int nseq, const fh264_params *p, fh264_mb_result *results)
+{
+    int rc = fh264_encode_p_async(s, seq0, nseq, p, results); if (rc) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    for (int b = seq0; b < seq0 + nseq; b++) { rc = fh264_picture_status(s, b); if (rc) return rc; }
+    return FH264_OK;
+}
+
+extern "C" int fh264_picture_status(fh264_session *s, int seq)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    const uint32_t f = s->h_status[(size_t)seq * ST_WORDS + ST_FLAGS];
+    if (f & FLAG_UB_INPUT) return fail(FH264_E_UB_INPUT, "reference picture has an 8x8 window sum of 0 or >= 16203: undefined in the reference (moestimation.cpp:153-158,477-480)");
+    if (f & FLAG_CAPACITY) return fail(FH264_E_CAPACITY, "stage-2 candidate capacity exceeded (flat content)");
+    return FH264_OK;
+}
+
+extern "C" int fh264_mode_counts(fh264_session *s, int seq, int32_t counts[5])
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!counts) return fail(FH264_E_ARG, "null output");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    // device counters: [0] skip, [1] 16x16, [2] 16x8, [3] 8x16, [4] 8x8 == brojTipova order
+    for (int i = 0; i < 5; i++) counts[i] = (int32_t)s->h_status[(size_t)seq * ST_WORDS + ST_COUNTS + i];
+    return FH264_OK;
+}
+
+extern "C" int fh264_download_recon(fh264_session *s, int seq, uint8_t *y, uint8_t *cb, uint8_t *cr)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!y || !cb || !cr) return fail(FH264_E_ARG, "null plane");
+    if (!s->has_ref[seq]) return fail(FH264_E_STATE, "no reference picture yet");
+    CK(cudaSetDevice(s->device));
+    const size_t WH = (size_t)s->g.WH;
+    CK(cudaMemcpyAsync(y, s->h[seq].ref[0], WH, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(cb, s->h[seq].ref[1], WH / 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(cr, s->h[seq].ref[2], WH / 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FH264_OK;
+}
+
+extern "C" int fh264_last_timings(fh264_session *s, float ms[5])
+{
+    if (!s || !ms) return fail(FH264_E_ARG, "null argument");
+    if (!s->timed) return fail(FH264_E_STATE, "no encode_p issued yet");
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventSynchronize(s->ev[4]));
+    for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms[i], s->ev[i], s->ev[i + 1]));
+    CK(cudaEventElapsedTime(&ms[4], s->ev[0], s->ev[4]));
+    return FH264_OK;
+}
+
+static int ensure_scratch(fh264_session *s, size_t nmbs)
+{
+    if (nmbs <= s->scr_mbs) return FH264_OK;
+    CK(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < 3; i++) if (s->d_scr[i]) { cudaFree(s->d_scr[i]); s->d_scr[i] = nullptr; }
+    for (int i = 0; i < 2; i++) if (s->d_scr16[i]) { cudaFree(s->d_scr16[i]); s->d_scr16[i] = nullptr; }
+    for (int i = 0; i < 3; i++) CK(cudaMalloc((void **)&s->d_scr[i], nmbs * 384));
+    for (int i = 0; i < 2; i++) CK(cudaMalloc((void **)&s->d_scr16[i], nmbs * 384 * 2));
+    s->scr_mbs = nmbs;
+    return FH264_OK;
+}
+
+extern "C" int fh264_tq_macroblocks(fh264_session *s, int n, const uint8_t *src384, const uint8_t *pred384, int qp, int16_t *levels384, uint8_t *recon384)
+{
+    if (!s || !src384 || !pred384 || !levels384 || !recon384 || n < 1) return fail(FH264_E_ARG, "bad argument");
+    if (qp < 0 || qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_scratch(s, (size_t)n); if (rc) return rc;
+    cudaStream_t st = s->stream;
+    CK(cudaMemcpyAsync(s->d_scr[0], src384, (size_t)n * 384, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_scr[1], pred384, (size_t)n * 384, cudaMemcpyHostToDevice, st));
+    k_tq_only<<<(n + 3) / 4, 128, 0, st>>>(s->d_scr[0], s->d_scr[1], n, qp, s->d_scr16[0], s->d_scr[2]);
+    CKL();
+    CK(cudaMemcpyAsync(levels384, s->d_scr16[0], (size_t)n * 384 * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(recon384, s->d_scr[2], (size_t)n * 384, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FH264_OK;
+}
+
+extern "C" int fh264_tq_luma_intra16(fh264_session *s, int n, const uint8_t *src256, const uint8_t *pred256, int qp, int16_t *dc16, int16_t *ac16x15, uint8_t *recon256)
+{
+    if (!s || !src256 || !pred256 || !dc16 || !ac16x15 || !recon256 || n < 1) return fail(FH264_E_ARG, "bad argument");
+    if (qp < 0 || qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
+    CK(cudaSetDevice(s->device));
+    int rc = ensure_scratch(s, (size_t)n); if (rc) return rc;
+    cudaStream_t st = s->stream;
+    CK(cudaMemcpyAsync(s->d_scr[0], src256, (size_t)n * 256, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_scr[1], pred256, (size_t)n * 256, cudaMemcpyHostToDevice, st));
+    k_tq_intra16<<<(n + 3) / 4, 128, 0, st>>>(s->d_scr[0], s->d_scr[1], n, qp, s->d_scr16[0], s->d_scr16[1], s->d_scr[2]);
+    CKL();
+    CK(cudaMemcpyAsync(dc16, s->d_scr16[0], (size_t)n * 16 * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ac16x15, s->d_scr16[1], (size_t)n * 240 * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(recon256, s->d_scr[2], (size_t)n * 256, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FH264_OK;
+}
+
+extern "C" int fh264_motion_compensate(fh264_session *s, int seq, const int16_t *qmv, uint8_t *pred384)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!qmv || !pred384) return fail(FH264_E_ARG, "null argument");
+    if (!s->has_ref[seq]) return fail(FH264_E_STATE, "no reference picture yet");
+    CK(cudaSetDevice(s->device));
+    const int n = s->g.nmb;
+    rc = ensure_scratch(s, (size_t)n); if (rc) return rc;
+    cudaStream_t st = s->stream;
+    CK(cudaMemcpyAsync(s->d_scr16[0], qmv, (size_t)n * 8 * 2, cudaMemcpyHostToDevice, st));
+    k_mc_only<<<(n + 3) / 4, 128, 0, st>>>(s->d_seqs, seq, s->g, s->d_scr16[0], s->d_scr[2]);
+    CKL();
+    CK(cudaMemcpyAsync(pred384, s->d_scr[2], (size_t)n * 384, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FH264_OK;
+}
+
+extern "C" int fh264_debug_plane(fh264_session *s, int seq, int f, uint8_t *out)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!out || f < 0 || f > 15) return fail(FH264_E_ARG, "bad argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemcpyAsync(out, s->h[seq].planes + (size_t)f * s->g.WH, (size_t)s->g.WH, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FH264_OK;
+}
+
+extern "C" int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!out || f < 0 || f > 15 || k < 0 || k > 4) return fail(FH264_E_ARG, "bad argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemcpyAsync(out, s->h[seq].kar + (size_t)(f * 5 + k) * s->g.WH, (size_t)s->g.WH * 2, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FH264_OK;
+}

@@ -1,0 +1,52 @@
+"""Host-side mirror of the reference's per-picture driver for the P path (fer_h264.cpp:55-79 NastaviEncode,
+ref_frames.cpp:185-234 selectNALUnitType, rbsp_encoding.cpp:139-323 RBSP_encode slice branch).
+
+Intra (IDR) pictures are NOT coded here: as in the integration build the reference's host code
+codes them and hands the reconstruction to the device (``intra_coder`` callback -> ``fh264_upload_recon``)."""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+from .native import Session
+
+NAL_NON_IDR, NAL_IDR = 1, 5
+
+
+class SequenceEncoder:
+    """Drives one sequence of a Session with the reference's frame-type rule and parameters
+    (Starter::PostaviParametre, fer_h264.cpp:169-178)."""
+
+    def __init__(self, session: Session, seq: int, qp=28, window=16, maxdiff_set=3, basic=0, intra_every=1000,
+                 intra_coder: Optional[Callable] = None):
+        self.s, self.seq = session, seq
+        self.qp, self.window, self.maxdiff_set, self.basic, self.intra_every = qp, window, maxdiff_set, basic, intra_every
+        self.intra_coder = intra_coder
+        self.curr_frame_count = 0        # currFrameCount (fer_h264.cpp:188,196)
+        self.have_dpb = False            # dpb.L != NULL (ref_frames.cpp:191)
+        self.nmb = session.nmb
+
+    def select_nal_unit_type(self) -> int:
+        """selectNALUnitType (ref_frames.cpp:185-234); the source picture must already be uploaded."""
+        if not self.have_dpb or self.curr_frame_count % self.intra_every == 0:
+            return NAL_IDR
+        sad = self.s.scene_sad(self.seq)
+        return NAL_IDR if sad > (self.nmb << 12) else NAL_NON_IDR
+
+    def encode_picture(self, y, cb, cr):
+        """One picture. Returns (nal_unit_type, records or None). For IDR the intra_coder callback must return the
+        reconstruction (Y, Cb, Cr) of the host-coded picture."""
+        self.s.upload_source(self.seq, y, cb, cr)
+        nal = self.select_nal_unit_type()
+        rec = None
+        if nal == NAL_IDR:
+            if self.intra_coder is None:
+                raise RuntimeError("IDR picture: an intra_coder (the reference host path) is required")
+            ry, rcb, rcr = self.intra_coder(y, cb, cr)
+            self.s.upload_recon(self.seq, ry, rcb, rcr)
+            self.have_dpb = True
+        else:
+            rec = self.s.encode_p(self.qp, self.window, self.maxdiff_set, self.basic, seq0=self.seq, nseq=1)[0]
+        self.curr_frame_count += 1
+        return nal, rec

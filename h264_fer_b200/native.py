@@ -1,0 +1,250 @@
+"""ctypes binding of include/fh264_b200.h (the drop-in C ABI). No torch types cross this boundary."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+P_L0_16x16, P_L0_L0_16x8, P_L0_L0_8x16, P_8x8ref0, P_SKIP = 0, 1, 2, 4, 31
+
+# struct fh264_mb_result (832 bytes)
+MB_RESULT_DTYPE = np.dtype([("mb_type", "<i2"), ("num_parts", "<i2"), ("mv", "<i2", (4, 2)), ("mvd", "<i2", (4, 2)),
+                            ("sad", "<u2", (4,)), ("luma", "<i2", (16, 16)), ("chroma_dc", "<i2", (2, 4)),
+                            ("chroma_ac", "<i2", (2, 4, 15)), ("reserved", "<i2", (10,))])
+assert MB_RESULT_DTYPE.itemsize == 832
+
+ERRORS = {-1: "FH264_E_ARG", -2: "FH264_E_CUDA", -3: "FH264_E_NO_DEVICE", -4: "FH264_E_STATE", -5: "FH264_E_UB_INPUT",
+          -6: "FH264_E_CAPACITY", -7: "FH264_E_UNSUPPORTED"}
+
+EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version", "fh264_set_stream", "fh264_sync",
+           "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_recon", "fh264_scene_sad",
+           "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
+           "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
+           "fh264_debug_feature", "fh264_last_timings"]
+
+
+class Fh264Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "FH264_E_?"), code, msg))
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("qp", C.c_int32), ("window", C.c_int32), ("maxdiff_set", C.c_int32), ("basic", C.c_int32)]
+
+
+def lib_path() -> str:
+    return os.path.join(HERE, "libfh264_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the in-tree CUDA library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.isfile(p):
+        raise Fh264Error(-3, "CUDA library %s is missing: run `python -m h264_fer_b200.build` (no CPU fallback exists)" % p)
+    L = C.CDLL(p)
+    vp, i32, u8p = C.c_void_p, C.c_int, C.c_void_p
+    L.fh264_open.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
+    L.fh264_close.argtypes = [vp]
+    L.fh264_last_error.restype = C.c_char_p
+    L.fh264_set_stream.argtypes = [vp, vp]
+    L.fh264_sync.argtypes = [vp]
+    L.fh264_host_alloc.restype = vp
+    L.fh264_host_alloc.argtypes = [C.c_size_t]
+    L.fh264_host_free.argtypes = [vp]
+    L.fh264_upload_source.argtypes = [vp, i32, u8p, u8p, u8p]
+    L.fh264_upload_recon.argtypes = [vp, i32, u8p, u8p, u8p]
+    L.fh264_scene_sad.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
+    L.fh264_encode_p.argtypes = [vp, i32, i32, C.POINTER(Params), vp]
+    L.fh264_encode_p_async.argtypes = [vp, i32, i32, C.POINTER(Params), vp]
+    L.fh264_picture_status.argtypes = [vp, i32]
+    L.fh264_download_recon.argtypes = [vp, i32, u8p, u8p, u8p]
+    L.fh264_mode_counts.argtypes = [vp, i32, C.POINTER(C.c_int32)]
+    L.fh264_tq_macroblocks.argtypes = [vp, i32, u8p, u8p, i32, vp, u8p]
+    L.fh264_tq_luma_intra16.argtypes = [vp, i32, u8p, u8p, i32, vp, vp, u8p]
+    L.fh264_motion_compensate.argtypes = [vp, i32, vp, u8p]
+    L.fh264_debug_plane.argtypes = [vp, i32, i32, u8p]
+    L.fh264_debug_feature.argtypes = [vp, i32, i32, i32, vp]
+    L.fh264_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
+    for name in EXPORTS:
+        getattr(L, name)
+    _lib = L
+    return L
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (fh264_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        L = load_library()
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(shape)) * self.dtype.itemsize
+        self.ptr = L.fh264_host_alloc(max(self.nbytes, 16))
+        if not self.ptr:
+            raise Fh264Error(-2, "cudaHostAlloc failed")
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            load_library().fh264_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Session:
+    """One GPU, ``batch`` sequences in lockstep. Thin 1:1 wrapper over the C ABI."""
+
+    def __init__(self, width, height, batch=1, device=0):
+        self.L = load_library()
+        self.w, self.h, self.batch, self.device = int(width), int(height), int(batch), int(device)
+        self.nmb = (self.w >> 4) * (self.h >> 4)
+        h = C.c_void_p()
+        self._ck(self.L.fh264_open(self.w, self.h, self.batch, self.device, C.byref(h)))
+        self.handle = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise Fh264Error(rc, (self.L.fh264_last_error() or b"").decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.L.fh264_close(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- stream / sync
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.fh264_set_stream(self.handle, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._ck(self.L.fh264_sync(self.handle))
+
+    # -- pictures
+    def upload_source(self, seq, y, cb, cr):
+        y, cb, cr = _u8(y), _u8(cb), _u8(cr)
+        assert y.size == self.w * self.h and cb.size == y.size // 4 and cr.size == y.size // 4
+        self._keep = (y, cb, cr)
+        self._ck(self.L.fh264_upload_source(self.handle, seq, _ptr(y), _ptr(cb), _ptr(cr)))
+
+    def upload_recon(self, seq, y, cb, cr):
+        y, cb, cr = _u8(y), _u8(cb), _u8(cr)
+        assert y.size == self.w * self.h and cb.size == y.size // 4 and cr.size == y.size // 4
+        self._ck(self.L.fh264_upload_recon(self.handle, seq, _ptr(y), _ptr(cb), _ptr(cr)))
+        self.sync()
+
+    def scene_sad(self, seq) -> int:
+        v = C.c_uint64()
+        self._ck(self.L.fh264_scene_sad(self.handle, seq, C.byref(v)))
+        return int(v.value)
+
+    def encode_p(self, qp, window, maxdiff_set, basic=0, seq0=0, nseq=None, out=None, sync=True):
+        """Returns a structured array [nseq, nmb] of MB_RESULT_DTYPE (a view of `out` if given)."""
+        nseq = self.batch - seq0 if nseq is None else nseq
+        prm = Params(int(qp), int(window), int(maxdiff_set), int(basic))
+        if out is None:
+            out = np.zeros((nseq, self.nmb), dtype=MB_RESULT_DTYPE)
+        fn = self.L.fh264_encode_p if sync else self.L.fh264_encode_p_async
+        self._ck(fn(self.handle, seq0, nseq, C.byref(prm), _ptr(out)))
+        return out
+
+    def picture_status(self, seq):
+        self._ck(self.L.fh264_picture_status(self.handle, seq))
+
+    def download_recon(self, seq):
+        y = np.zeros((self.h, self.w), np.uint8)
+        cb = np.zeros((self.h // 2, self.w // 2), np.uint8)
+        cr = np.zeros((self.h // 2, self.w // 2), np.uint8)
+        self._ck(self.L.fh264_download_recon(self.handle, seq, _ptr(y), _ptr(cb), _ptr(cr)))
+        return y, cb, cr
+
+    def mode_counts(self, seq):
+        c = (C.c_int32 * 5)()
+        self._ck(self.L.fh264_mode_counts(self.handle, seq, c))
+        return list(c)
+
+    def last_timings(self):
+        t = (C.c_float * 5)()
+        self._ck(self.L.fh264_last_timings(self.handle, t))
+        return dict(zip(("phase_a_ms", "phase_b_ms", "phase_c_ms", "phase_r_ms", "total_ms"), [float(x) for x in t]))
+
+    # -- building blocks
+    def tq_macroblocks(self, src384, pred384, qp):
+        src384, pred384 = _u8(src384).reshape(-1, 384), _u8(pred384).reshape(-1, 384)
+        n = src384.shape[0]
+        lv = np.zeros((n, 384), np.int16)
+        rc = np.zeros((n, 384), np.uint8)
+        self._ck(self.L.fh264_tq_macroblocks(self.handle, n, _ptr(src384), _ptr(pred384), int(qp), _ptr(lv), _ptr(rc)))
+        return lv, rc
+
+    def tq_luma_intra16(self, src256, pred256, qp):
+        src256, pred256 = _u8(src256).reshape(-1, 256), _u8(pred256).reshape(-1, 256)
+        n = src256.shape[0]
+        dc = np.zeros((n, 16), np.int16)
+        ac = np.zeros((n, 16, 15), np.int16)
+        rc = np.zeros((n, 256), np.uint8)
+        self._ck(self.L.fh264_tq_luma_intra16(self.handle, n, _ptr(src256), _ptr(pred256), int(qp), _ptr(dc), _ptr(ac), _ptr(rc)))
+        return dc, ac, rc
+
+    def motion_compensate(self, seq, qmv):
+        qmv = np.ascontiguousarray(qmv, dtype=np.int16).reshape(self.nmb, 4, 2)
+        out = np.zeros((self.nmb, 384), np.uint8)
+        self._ck(self.L.fh264_motion_compensate(self.handle, seq, _ptr(qmv), _ptr(out)))
+        return out
+
+    def debug_plane(self, seq, f):
+        out = np.zeros((self.h, self.w), np.uint8)
+        self._ck(self.L.fh264_debug_plane(self.handle, seq, f, _ptr(out)))
+        return out
+
+    def debug_feature(self, seq, k, f):
+        out = np.zeros((self.h, self.w), np.uint16)
+        self._ck(self.L.fh264_debug_feature(self.handle, seq, k, f, _ptr(out)))
+        return out
+
+
+def records_to_ints(rec: np.ndarray) -> np.ndarray:
+    """[nmb] MB_RESULT_DTYPE -> [nmb, 405] int32 in the layout of the oracle / reference dump records:
+    mb_type, mv[4][2], mvd[4][2], sad[4], luma[16][16], cdc[2][4], cac[2][4][15]."""
+    n = rec.shape[0]
+    out = np.zeros((n, 405), np.int32)
+    out[:, 0] = rec["mb_type"]
+    out[:, 1:9] = rec["mv"].reshape(n, 8)
+    out[:, 9:17] = rec["mvd"].reshape(n, 8)
+    out[:, 17:21] = rec["sad"]
+    out[:, 21:277] = rec["luma"].reshape(n, 256)
+    out[:, 277:285] = rec["chroma_dc"].reshape(n, 8)
+    out[:, 285:405] = rec["chroma_ac"].reshape(n, 120)
+    return out

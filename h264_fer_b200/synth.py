@@ -24,9 +24,9 @@ def _box5(a: np.ndarray) -> np.ndarray:
 class SynthClip:
     """Frame generator: ``clip.frame(t) -> (Y, Cb, Cr)`` uint8 arrays of the *input* size (before crop)."""
 
-    def __init__(self, width: int, height: int, seed: int, pan=(2, 1), noise=1.0):
+    def __init__(self, width: int, height: int, seed: int, pan=(2, 1), noise=1.0, square=True):
         self.w, self.h, self.seed = int(width), int(height), int(seed)
-        self.pan, self.noise = pan, float(noise)
+        self.pan, self.noise, self.square = pan, float(noise), bool(square)
         rng = np.random.default_rng(seed)
         gh, gw = self.h // 8 + 40, self.w // 8 + 40
         grid = rng.integers(40, 200, size=(gh, gw), dtype=np.int32)
@@ -42,7 +42,8 @@ class SynthClip:
         # moving inverted square
         sx = (16 + 5 * t) % max(1, w - 32)
         sy = (h // 3 + 3 * t) % max(1, h - 32)
-        y[sy:sy + 32, sx:sx + 32] = 255.0 - y[sy:sy + 32, sx:sx + 32]
+        if self.square:
+            y[sy:sy + 32, sx:sx + 32] = 255.0 - y[sy:sy + 32, sx:sx + 32]
         if self.noise > 0:
             rng = np.random.default_rng([self.seed, 7919, t])
             y = y + self.noise * rng.standard_normal(size=y.shape)

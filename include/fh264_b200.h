@@ -1,0 +1,154 @@
+/*
+ * fh264_b200 — C ABI of the B200 (sm_100a) implementation of the P-picture hot path of zoltanmaric/h264-fer.
+ *
+ * This is the drop-in boundary: plain C, opaque handle, plain pointers and sizes, int status codes.
+ * Each entry point names the reference interface it stands in for (paths relative to the reference's
+ * fer_h264/fer_h264/). The reference communicates through process globals (h264_globals.h:99-193,
+ * residual.h:6-15, mode_pred.h:19-22); INTEGRATION.md shows the C++ shim that copies fh264_mb_result
+ * records into those globals so the unchanged host CAVLC/NAL code emits the bitstream.
+ *
+ * A session owns one GPU and `batch` independent sequences that advance in lockstep (one picture of every
+ * sequence per call), because the reference itself is one-sequence-per-process (function-local statics,
+ * fer_h264.cpp:55-79) and a single 1080p picture cannot fill a B200's wavefront-limited phase.
+ *
+ * Per picture and sequence, in the order the reference's RBSP_encode()/encode() issue them:
+ *   fh264_upload_source   <- ReadFromY4M() filling `frame`                         (fileIO.cpp:258-345)
+ *   fh264_scene_sad       <- selectNALUnitType()'s luma |frame-dpb| sum             (ref_frames.cpp:185-234)
+ *   fh264_encode_p        <- the P-slice MB loop: interEncoding() + quantizationTransform()/
+ *                            transformDecodingP_Skip() for every MB                (rbsp_encoding.cpp:175-192),
+ *                            then modificationProcess()/frameDeepCopy() and
+ *                            FillInterpolatedRefFrame() for the next picture       (rbsp_encoding.cpp:317-322)
+ *   fh264_upload_recon    <- after a host-coded I picture: frame -> dpb, then FillInterpolatedRefFrame()
+ * All arithmetic is integer; results are bit-exact with the reference CPU path.
+ */
+#ifndef FH264_B200_H
+#define FH264_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FH264_ABI_VERSION 1
+
+/* status codes (the reference has none: void functions + assert, openCL_functions.cpp:60-139) */
+enum {
+    FH264_OK = 0,
+    FH264_E_ARG = -1,          /* bad argument (null pointer, size not a multiple of 16, > 10000 MBs, ...) */
+    FH264_E_CUDA = -2,         /* CUDA runtime error, see fh264_last_error() */
+    FH264_E_NO_DEVICE = -3,    /* no usable sm_100 device: the library never falls back to a CPU path */
+    FH264_E_STATE = -4,        /* call order violated (e.g. encode_p before any reference picture) */
+    FH264_E_UB_INPUT = -5,     /* reference-undefined input: an 8x8 reference window sums to 0 or >= 16203
+                                  (moestimation.cpp:153-158,477-480) */
+    FH264_E_CAPACITY = -6,     /* stage-2 candidate pool exhausted (flat content); see DESIGN.md */
+    FH264_E_UNSUPPORTED = -7   /* parameter outside the supported range (WindowSize > 64) */
+};
+
+/* mb_type values as the reference stores them in mb_type_array[] (h264_globals.h:24-28,58) */
+enum { FH264_P_L0_16x16 = 0, FH264_P_L0_L0_16x8 = 1, FH264_P_L0_L0_8x16 = 2, FH264_P_8x8ref0 = 4, FH264_P_SKIP = 31 };
+
+/* Encoder parameters = Starter::PostaviParametre (fer_h264.cpp:169-178), the subset the P path reads. */
+typedef struct fh264_params {
+    int32_t qp;           /* _qParameter == QPy (headers_and_parameter_sets.cpp:186-189), 0..51 */
+    int32_t window;       /* WindowSize: stage 3 scans +-window/2, stages 1/3b +-window/16 (moestimation.cpp:458,509-510) */
+    int32_t maxdiff_set;  /* MAXDIFF_SET; -1 = adaptive per macroblock (moestimation.cpp:407-419) */
+    int32_t basic;        /* BasicInterEncoding: 1 = stage 1 only (moestimation.cpp:470) */
+} fh264_params;
+
+/* One macroblock's outputs = the globals interEncoding()/quantizationTransform() leave behind:
+ * mb_type, mvL0x/mvL0y[CurrMbAddr][q][0] (quadrant MVs, quarter-pel), mvd_l0[part][0][], the 8x8 SADs the
+ * search measured for the chosen MVs (satdLuma8x8MVs, moestimation.cpp:175-195), LumaLevel[16][16]
+ * (z-order 4x4 blocks, zigzag), ChromaDCLevel[2][4], ChromaACLevel[2][4][0..14]. 832 bytes (13 x 64). */
+typedef struct fh264_mb_result {
+    int16_t mb_type;
+    int16_t num_parts;          /* NumMbPart(mb_type): 1, 2 or 4; 0 for P_Skip */
+    int16_t mv[4][2];           /* per 8x8 quadrant: {x, y} */
+    int16_t mvd[4][2];          /* per partition (first num_parts valid, rest 0) */
+    uint16_t sad[4];            /* per 8x8 quadrant; 0 for P_Skip */
+    int16_t luma[16][16];
+    int16_t chroma_dc[2][4];
+    int16_t chroma_ac[2][4][15];
+    int16_t reserved[10];
+} fh264_mb_result;
+
+typedef struct fh264_session fh264_session;
+
+/* Lifecycle seam. Replaces InitCL()/AllocateFrameBuffersCL()/InitializeInterpolatedRefFrame()/AllocateMemory()
+ * (openCL_functions.cpp:52,142; moestimation.cpp:29; mode_pred.cpp:22). width/height are the CODED luma size
+ * (multiples of 16, <= 10000 MBs as h264_globals.cpp:180). device = CUDA ordinal. */
+int fh264_open(int width, int height, int batch, int device, fh264_session **out);
+int fh264_close(fh264_session *s);                                   /* CloseCL() openCL_functions.cpp:162 */
+const char *fh264_last_error(void);
+int fh264_abi_version(void);
+
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*), or NULL for the session's own stream. */
+int fh264_set_stream(fh264_session *s, void *cuda_stream);
+int fh264_sync(fh264_session *s);
+
+/* Pinned host staging for the asynchronous calls (cudaHostAlloc / cudaFreeHost). */
+void *fh264_host_alloc(size_t bytes);
+void fh264_host_free(void *p);
+
+/* `frame` := source picture of sequence `seq` (planar 4:2:0, row-major, stride == width). Asynchronous on the
+ * session stream; the host buffers must stay valid until the next fh264_sync()/synchronous call. */
+int fh264_upload_source(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
+
+/* dpb := reconstruction of a picture coded elsewhere (host I picture), then phase R on it
+ * (frameDeepCopy ref_frames.cpp:17-35 + FillInterpolatedRefFrame moestimation.cpp:74-173). */
+int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
+
+/* Sum over luma of |frame - dpb| for sequence seq (selectNALUnitType ref_frames.cpp:210-224; the reference's
+ * OpenCL AbsDiff kernel h264_kernels.cl:1-5 + host sum). Synchronous (returns the value). */
+int fh264_scene_sad(fh264_session *s, int seq, uint64_t *sad);
+
+/* Code one P picture of sequences [seq0, seq0+nseq): motion search, mode decision, motion compensation,
+ * pixel snapping, transform/quant/reconstruction for every MB; then dpb := reconstruction and phase R for the
+ * next picture. results: nseq * (width/16*height/16) records (host memory, pinned preferred), MB raster order
+ * per sequence; may be NULL (results stay on the device; see fh264_download_results). Synchronous. */
+int fh264_encode_p(fh264_session *s, int seq0, int nseq, const fh264_params *p, fh264_mb_result *results);
+
+/* Asynchronous variant: enqueues everything (including the D2H of results if non-NULL) and returns. */
+int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const fh264_params *p, fh264_mb_result *results);
+
+/* Status of the last encode_p of sequence seq (FH264_OK, FH264_E_UB_INPUT, FH264_E_CAPACITY); synchronous. */
+int fh264_picture_status(fh264_session *s, int seq);
+
+/* Current dpb (== `frame` after RBSP_encode) of sequence seq. Tests / decoder-side use. Synchronous. */
+int fh264_download_recon(fh264_session *s, int seq, uint8_t *y, uint8_t *cb, uint8_t *cr);
+
+/* brojTipova[5] of the last coded P picture (moestimation.cpp:422,529-551): #P_Skip,#16x16,#16x8,#8x16,#8x8. */
+int fh264_mode_counts(fh264_session *s, int seq, int32_t counts[5]);
+
+/* ---- stand-alone building blocks (unit tests, and the I-picture helper named by the north star) -------- */
+
+/* Fused per-macroblock residual -> 4x4 transform -> quant -> zigzag -> dequant -> inverse -> clip for n inter
+ * macroblocks given source and prediction (384 bytes each: 16x16 Y, 8x8 Cb, 8x8 Cr). Host pointers.
+ * quantizationTransform(...,true) quantizationTransform.cpp:349-485 + inttransform.cpp:133-154,237-321. */
+int fh264_tq_macroblocks(fh264_session *s, int n, const uint8_t *src384, const uint8_t *pred384, int qp,
+                         int16_t *levels384, uint8_t *recon384);
+
+/* Intra16x16 luma variant with the 4x4 Hadamard of the 16 DCs (quantizationTransform.cpp:105-152,227-260;
+ * scaleTransform.cpp:154-189,344-376; inttransform.cpp:157-208). n macroblocks, 256 bytes each. */
+int fh264_tq_luma_intra16(fh264_session *s, int n, const uint8_t *src256, const uint8_t *pred256, int qp,
+                          int16_t *dc16, int16_t *ac16x15, uint8_t *recon256);
+
+/* Motion compensation of a whole picture of sequence seq from per-MB quadrant MVs (mocomp.cpp:152-208):
+ * qmv = nmb*4*2 int16 (host), pred384 = nmb*384 bytes (host). */
+int fh264_motion_compensate(fh264_session *s, int seq, const int16_t *qmv, uint8_t *pred384);
+
+/* Phase-R products of sequence seq's current dpb (host copies; tests): plane f (W*H bytes), feature k of plane f
+ * (W*H uint16). */
+int fh264_debug_plane(fh264_session *s, int seq, int f, uint8_t *out);
+int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out);
+
+/* Device time of the phases of the last fh264_encode_p call, milliseconds, measured with CUDA events on the
+ * session stream: [0] phase A (predictor-independent search), [1] phase B (wavefront), [2] phase C (MC + TQ +
+ * reconstruction), [3] phase R (reference preparation for the next picture), [4] total. */
+int fh264_last_timings(fh264_session *s, float ms[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FH264_B200_H */

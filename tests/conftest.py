@@ -1,0 +1,65 @@
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+class Golden:
+    """A committed fixture produced by tests/golden/make_golden.py from the compiled reference."""
+
+    def __init__(self, path):
+        self.name = os.path.splitext(os.path.basename(path))[0]
+        z = np.load(path)
+        self.w_in, self.h_in, self.seed, self.frames, self.qp, self.window, self.maxdiff, self.basic = [int(v) for v in z["params"]]
+        self.types = [int(t) for t in z["types"]]
+        self.w, self.h = z["RECY_0"].shape[1], z["RECY_0"].shape[0]
+        self.z = z
+
+    def src(self, n):
+        return self.z["SRCY_%d" % n], self.z["SRCU_%d" % n], self.z["SRCV_%d" % n]
+
+    def rec(self, n):
+        return self.z["RECY_%d" % n], self.z["RECU_%d" % n], self.z["RECV_%d" % n]
+
+    def mbrec(self, n):
+        return self.z["mbrec_%d" % n].astype(np.int32)
+
+    def tqio(self, n):
+        return self.z["tqio_%d" % n]
+
+    def counts(self, n):
+        return [int(c) for c in self.z["counts_%d" % n]]
+
+    def p_pictures(self):
+        return [n for n, t in enumerate(self.types) if t == 1]
+
+
+def golden_paths():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+@pytest.fixture(params=golden_paths(), ids=lambda p: os.path.splitext(os.path.basename(p))[0])
+def golden(request):
+    return Golden(request.param)
+
+
+@pytest.fixture(scope="session")
+def gpu_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False

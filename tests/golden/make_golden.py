@@ -1,0 +1,55 @@
+"""Generates the committed golden vectors from the UNMODIFIED reference (oracle/_ref/ref_encoder, built from
+/root/reference by `make -C oracle ref`). Run in the build container only:  python tests/golden/make_golden.py
+
+Each fixture (npz) holds, for a short synthetic clip: the cropped source pictures, the reference's reconstruction
+of every picture, picture types, and for every P picture the per-macroblock records
+(mb_type, mv[4][2], mvd[4][2], sad[4], 384 levels) plus the .264 md5 — everything the GPU path must reproduce."""
+import hashlib
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from h264_fer_b200 import synth  # noqa: E402
+from oracle import refdump  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (width, height, seed, frames, qp, window, maxdiff, basic, noise, square)
+    "qcif_w16_qp28": (176, 144, 1, 4, 28, 16, 3, 0, 1.0, True),
+    "cif_crop_w32_qp20_adaptive": (200, 120, 11, 4, 20, 32, -1, 0, 0.0, True),
+    "small_basic_qp33": (128, 96, 12, 3, 33, 16, 2, 1, 0.5, False),
+}
+
+
+def main():
+    assert refdump.have_ref_encoder(), "build oracle/_ref/ref_encoder first (make -C oracle ref)"
+    for name, (w, h, seed, frames, qp, window, maxdiff, basic, noise, square) in CASES.items():
+        tmp = tempfile.mkdtemp()
+        y4m = os.path.join(tmp, "in.y4m")
+        synth.write_y4m(y4m, w, h, seed, frames, noise=noise, square=square)
+        summ, dump, out264 = refdump.run_reference(y4m, frames, qp=qp, basic=basic, window=window, maxdiff=maxdiff,
+                                                   dumpmask=refdump.D_MBREC | refdump.D_RECON | refdump.D_SOURCE | refdump.D_TQIO)
+        pics = refdump.parse_dump(dump)
+        arrays = dict(params=np.array([w, h, seed, frames, qp, window, maxdiff, basic], np.int32),
+                      noise=np.array([noise]), square=np.array([int(square)]), types=np.array([p["nal_type"] for p in pics], np.int32),
+                      bitstream_md5=np.frombuffer(hashlib.md5(open(out264, "rb").read()).digest(), np.uint8),
+                      y4m_md5=np.frombuffer(hashlib.md5(open(y4m, "rb").read()).digest(), np.uint8))
+        for n, p in enumerate(pics):
+            for t in ("SRCY", "SRCU", "SRCV", "RECY", "RECU", "RECV"):
+                arrays["%s_%d" % (t, n)] = p[t]
+            if "mbrec" in p:
+                arrays["mbrec_%d" % n] = p["mbrec"].astype(np.int16)
+                arrays["tqio_%d" % n] = p["tqio"]
+                arrays["counts_%d" % n] = np.array(p["counts"], np.int32)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **arrays)
+        print(name, summ["types"], os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

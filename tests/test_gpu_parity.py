@@ -1,0 +1,216 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the oracle on seeded inputs and against the
+committed golden vectors from the unmodified reference. Bit-exact everywhere (integer/byte arithmetic)."""
+import numpy as np
+import pytest
+
+import h264_fer_b200 as fh
+from h264_fer_b200 import synth
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _loaded_native():
+    import os
+    maps = open("/proc/self/maps").read()
+    return "libfh264_b200.so" in maps
+
+
+def test_native_library_is_what_runs():
+    s = fh.Session(64, 48)
+    s.close()
+    assert _loaded_native()
+
+
+@pytest.mark.parametrize("w,h,seed", [(176, 144, 1), (208, 112, 2), (64, 48, 3)])
+def test_phase_r_planes_and_features(w, h, seed):
+    y, cb, cr = synth.SynthClip(w, h, seed).frame(0)
+    o = port.Oracle(w, h)
+    o.phase_r(y)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, y, cb, cr)
+        for f in range(16):
+            assert np.array_equal(s.debug_plane(0, f), o.plane(f)), "plane %d" % f
+            for k in range(5):
+                assert np.array_equal(s.debug_feature(0, k, f), o.kar(k, f)), "feature %d plane %d" % (k, f)
+
+
+def test_phase_r_random_noise_edges():
+    rng = np.random.default_rng(5)
+    w, h = 80, 64
+    y = rng.integers(16, 236, (h, w), dtype=np.uint8)
+    c = rng.integers(16, 240, (h // 2, w // 2), dtype=np.uint8)
+    o = port.Oracle(w, h)
+    o.phase_r(y)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, y, c, c)
+        for f in range(16):
+            assert np.array_equal(s.debug_plane(0, f), o.plane(f))
+            assert np.array_equal(s.debug_feature(0, 0, f), o.kar(0, f))
+            assert np.array_equal(s.debug_feature(0, 4, f), o.kar(4, f))
+
+
+@pytest.mark.parametrize("qp", [0, 12, 23, 24, 28, 37, 51])
+def test_fused_tq_against_oracle(qp):
+    rng = np.random.default_rng(qp)
+    n = 300
+    src = rng.integers(0, 256, (n, 384), dtype=np.uint8)
+    pred = np.clip(src.astype(int) + rng.integers(-40, 41, (n, 384)), 0, 255).astype(np.uint8)
+    pred[:20] = src[:20]                       # zero residual
+    pred[20:40] = rng.integers(0, 256, (20, 384), dtype=np.uint8)   # large residual
+    with fh.Session(64, 48) as s:
+        lv, rc = s.tq_macroblocks(src, pred, qp)
+    for i in range(n):
+        elv, erc = port.tq_mb(src[i], pred[i], qp)
+        assert np.array_equal(lv[i].astype(np.int32), elv), (qp, i)
+        assert np.array_equal(rc[i], erc), (qp, i)
+
+
+@pytest.mark.parametrize("qp", [10, 28, 36, 44])
+def test_intra16_luma_dc_path_against_oracle(qp):
+    rng = np.random.default_rng(100 + qp)
+    n = 64
+    src = rng.integers(0, 256, (n, 256), dtype=np.uint8)
+    pred = np.clip(src.astype(int) + rng.integers(-30, 31, (n, 256)), 0, 255).astype(np.uint8)
+    with fh.Session(64, 48) as s:
+        dc, ac, rc = s.tq_luma_intra16(src, pred, qp)
+    for i in range(n):
+        edc, eac, erc = port.tq_luma_intra16(src[i], pred[i], qp)
+        assert np.array_equal(dc[i].astype(np.int32), edc) and np.array_equal(ac[i].astype(np.int32), eac) and np.array_equal(rc[i], erc), (qp, i)
+
+
+def test_fused_tq_against_golden_tqio(golden):
+    with fh.Session(64, 48) as s:
+        for n in golden.p_pictures():
+            io, want = golden.tqio(n), golden.mbrec(n)
+            sel = np.where(want[:, 0] != 31)[0]
+            lv, rc = s.tq_macroblocks(io[sel, :384], io[sel, 384:], golden.qp)
+            assert np.array_equal(lv.astype(np.int32), want[sel, 21:])
+
+
+def test_motion_compensation_including_picture_edges():
+    w, h = 96, 80
+    y, cb, cr = synth.SynthClip(w, h, 9).frame(0)
+    rng = np.random.default_rng(1)
+    nmb = (w // 16) * (h // 16)
+    qmv = rng.integers(-80, 81, (nmb, 4, 2)).astype(np.int32)     # quarter-pel, up to 20 px: many cross the border
+    qmv[0] = [[-400, -400]] * 4
+    qmv[1] = [[3, 3], [2, 2], [1, 3], [3, 1]]
+    o = port.Oracle(w, h)
+    o.phase_r(y)
+    want = o.mc_picture((y, cb, cr), qmv.reshape(nmb, 8))
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, y, cb, cr)
+        got = s.motion_compensate(0, qmv)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:5]
+
+
+def test_scene_sad():
+    w, h = 176, 144
+    c = synth.SynthClip(w, h, 4)
+    (y0, u0, v0), (y1, u1, v1) = c.frame(0), c.frame(1)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, y0, u0, v0)
+        s.upload_source(0, y1, u1, v1)
+        assert s.scene_sad(0) == port.scene_sad(y1, y0)
+        s.upload_source(0, y0, u0, v0)
+        assert s.scene_sad(0) == 0
+
+
+def _check_picture(s, seq, golden, n, got_rec):
+    want = golden.mbrec(n)
+    got = fh.records_to_ints(got_rec)
+    if not np.array_equal(got, want):
+        d = np.argwhere(got != want)
+        raise AssertionError("%s picture %d: %d record fields differ, first %s got %s want %s" % (
+            golden.name, n, len(d), d[:6].tolist(), [int(got[a, b]) for a, b in d[:6]], [int(want[a, b]) for a, b in d[:6]]))
+    ry, ru, rv = s.download_recon(seq)
+    ey, eu, ev = golden.rec(n)
+    assert np.array_equal(ry, ey) and np.array_equal(ru, eu) and np.array_equal(rv, ev), "%s picture %d recon" % (golden.name, n)
+
+
+def test_encode_p_matches_reference_golden(golden):
+    """Whole P pictures: MVs, mvds, SADs, mb_types, quantised levels and the reconstruction, against vectors dumped from
+    the unmodified reference; I pictures are taken from the reference's reconstruction (host path)."""
+    with fh.Session(golden.w, golden.h) as s:
+        for n, t in enumerate(golden.types):
+            if t == 5:
+                s.upload_recon(0, *golden.rec(n))
+                continue
+            s.upload_source(0, *golden.src(n))
+            rec = s.encode_p(golden.qp, golden.window, golden.maxdiff, golden.basic)[0]
+            _check_picture(s, 0, golden, n, rec)
+            counts = s.mode_counts(0)
+            want_counts = golden.counts(n)
+            if not golden.basic:        # with BasicInterEncoding the reference double-counts (moestimation.cpp:326,353,422)
+                assert counts == want_counts, (counts, want_counts)
+
+
+def test_encode_p_against_oracle_on_seeded_clip():
+    """Chained P pictures (each predicts from the GPU's own reconstruction) against the oracle, WindowSize 32."""
+    w, h, qp, window, maxdiff = 208, 160, 26, 32, 3
+    clip = synth.SynthClip(w, h, 31)
+    o = port.Oracle(w, h)
+    ref = clip.frame(0)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, *ref)
+        for t in range(1, 4):
+            cur = clip.frame(t)
+            assert not o.phase_r(ref[0])
+            erec, erecon = o.encode_p(cur, ref, qp, window, maxdiff)
+            s.upload_source(0, *cur)
+            assert s.scene_sad(0) == port.scene_sad(cur[0], ref[0])
+            got = fh.records_to_ints(s.encode_p(qp, window, maxdiff)[0])
+            assert np.array_equal(got, erec), np.argwhere(got != erec)[:6]
+            ry, ru, rv = s.download_recon(0)
+            assert np.array_equal(ry, erecon[0]) and np.array_equal(ru, erecon[1]) and np.array_equal(rv, erecon[2])
+            ref = erecon
+
+
+def test_batch_of_sequences_equals_single_sequence_runs():
+    """Sequences of a batch are independent: a batch-of-3 call equals three batch-of-1 sessions."""
+    w, h, qp, window, maxdiff = 112, 96, 28, 16, -1
+    clips = [synth.SynthClip(w, h, 40 + i, square=False) for i in range(3)]
+    singles = []
+    for c in clips:
+        with fh.Session(w, h) as s:
+            s.upload_recon(0, *c.frame(0))
+            s.upload_source(0, *c.frame(1))
+            singles.append((s.encode_p(qp, window, maxdiff)[0].copy(), s.download_recon(0)))
+    with fh.Session(w, h, batch=3) as s:
+        for i, c in enumerate(clips):
+            s.upload_recon(i, *c.frame(0))
+            s.upload_source(i, *c.frame(1))
+        out = s.encode_p(qp, window, maxdiff)
+        for i in range(3):
+            assert out[i].tobytes() == singles[i][0].tobytes()
+            for a, b in zip(s.download_recon(i), singles[i][1]):
+                assert np.array_equal(a, b)
+
+
+def test_error_paths():
+    with fh.Session(64, 48) as s:
+        with pytest.raises(fh.Fh264Error) as e:
+            s.encode_p(28, 16, 3)
+        assert e.value.code == -4          # no reference picture yet
+        y = np.full((48, 64), 120, np.uint8); c = np.full((24, 32), 128, np.uint8)
+        s.upload_recon(0, y, c, c)
+        s.upload_source(0, y, c, c)
+        with pytest.raises(fh.Fh264Error) as e:
+            s.encode_p(28, 128, 3)
+        assert e.value.code == -7          # WindowSize > 64
+        with pytest.raises(fh.Fh264Error) as e:
+            s.encode_p(77, 16, 3)
+        assert e.value.code == -1
+
+
+def test_reference_undefined_input_is_reported_not_emulated():
+    """An all-zero reference has 8x8 sums of 0: the reference's counting sort is undefined there (moestimation.cpp:153-158)."""
+    w, h = 64, 48
+    z = np.zeros((h, w), np.uint8); c = np.full((h // 2, w // 2), 128, np.uint8)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, z, c, c)
+        s.upload_source(0, z, c, c)
+        with pytest.raises(fh.Fh264Error) as e:
+            s.encode_p(28, 16, 3)
+        assert e.value.code == -5

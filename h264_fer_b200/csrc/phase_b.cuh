@@ -155,13 +155,13 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
         int mvpx, mvpy;
         predict_mv_(nc, (pi & 1) * 8, (pi >> 1) * 8, 8, 0, curq, mvpx, mvpy);
         const int genx = mvpx >> 2, geny = mvpy >> 2;
-        const PartA pa = S.parta[part];
+        PartA pa = S.parta[part];
+        if (prm.basic) { pa.n2 = 0; pa.n3 = 0; pa.s2_off = 0; }
         int s[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) s[k] = pa.suma[k];
         uint2 rows[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) rows[r] = *(const uint2 *)&cur[(pi >> 1) * 8 + r][(pi & 1) * 8];
+        block_sums(rows, s);          // suma[0..4] (:440-451); phase A is skipped with BasicInterEncoding
         if (tid == 0) { best = ~0ull; n_valid1 = 0; }
         __syncthreads();
 

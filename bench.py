@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric: 1080p frames/s of the P-picture ME + transform/quant/reconstruction path.
+
+Workload at N GPUs (config 5 of BASELINE.json, sharded as SURVEY.md §8e "batch of independent sequences"): every
+GPU codes `--seqs` independent synthetic 1080p sequences (coded 1920x1072, IPPP, QP 28, WindowSize 32 = +-16 search,
+MAXDIFF 3) in lockstep; one STEP = one P picture of every sequence on the GPU: scene-change SAD (a12), phases A/B/C
+(a3-a10), dpb swap (a11), phase R (a2). Weak scaling: per-GPU work fixed, no data-path collective.
+
+  value  : pictures/s with the source pictures already resident in HBM (device-to-device into `frame`)
+  e2e    : the same through the C ABI with HOST buffers: pinned H2D of every source picture and D2H of every
+           macroblock record (832 B/MB) inside the timed region
+  --impl reference : the unmodified reference encoder (oracle/_ref/ref_encoder, compiled from /root/reference in the
+           build container) on the box's host cores, one single-threaded process per sequence.
+
+The oracle / reference binary is used here ONLY as the timed CPU baseline, never by the measured GPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 1920, 1080            # input size; coded 1920x1072 after the reference's crop (fileIO.cpp:242-243)
+QP, WINDOW, MAXDIFF = 28, 32, 3
+CLIP_LEN = 6                          # distinct pictures per sequence, played ping-pong so motion stays continuous
+ALG_BYTES_PER_MB = 1984               # 384 src + 384 ref + 384 recon + 768 levels + 64 metadata
+ALG_INTOPS_PER_MB = 0.43e6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def pingpong(t, n):
+    """0,1,..,n-1,n-2,..,1,0,1,.. : consecutive pictures always differ by exactly one pan step."""
+    period = 2 * (n - 1)
+    k = t % period
+    return k if k < n else period - k
+
+
+def make_clips(nseq, first_seed):
+    from h264_fer_b200 import synth
+    clips = []
+    for i in range(nseq):
+        c = synth.SynthClip(WIDTH, HEIGHT, first_seed + i)
+        frames = []
+        for t in range(CLIP_LEN):
+            y, cb, cr = c.frame(t)
+            frames.append((synth.crop16(y), synth.crop16(cb, chroma=True), synth.crop16(cr, chroma=True)))
+        clips.append(frames)
+    return clips
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference_processes(nproc, pictures, first_seed, tmpdir):
+    """nproc single-threaded reference encoders in parallel, each coding 1 I + (pictures-1) P pictures of its own 1080p
+    clip. Returns per-process summaries (hot-path seconds per picture)."""
+    from h264_fer_b200 import synth
+    from oracle import refdump
+    procs = []
+    for i in range(nproc):
+        y4m = os.path.join(tmpdir, "seq%d.y4m" % i)
+        synth.write_y4m(y4m, WIDTH, HEIGHT, first_seed + i, pictures)
+        cmd = [refdump.REF_ENCODER, y4m, os.path.join(tmpdir, "seq%d.264" % i), "-", str(pictures), str(QP), "0", str(WINDOW),
+               str(MAXDIFF), "1000", "0"]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, cwd=tmpdir))
+    outs = []
+    for p in procs:
+        out, _ = p.communicate()
+        line = [l for l in out.decode().splitlines() if l.startswith("{")][-1]
+        outs.append(json.loads(line))
+    return outs
+
+
+def hot_seconds(summary, pic):
+    return summary["t_select"][pic] + summary["t_inter"][pic] + summary["t_tq"][pic] + summary["t_fill"][pic]
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import refdump
+    cores = os.cpu_count() or 1
+    nseq_total = args.seqs * args.gpus
+    nproc = max(1, min(cores, nseq_total))
+    steps = max(1, min(args.steps, 4))
+    warm = 1 if args.warmup > 0 else 0
+    line = {"impl": "reference", "metric": "1080p P-picture frames/s, ME + transform/quant/reconstruction hot path", "unit": "frames/s",
+            "n_gpus": args.gpus, "higher_is_better": True, "scaling": "weak", "dtype": "u8/int32", "data": "synthetic", "vs_baseline": None,
+            "config": workload_config(args, nseq_total)}
+    if not refdump.have_ref_encoder():
+        # the port (oracle/fh264_oracle.c) is the fallback CPU implementation of the path
+        from oracle import port
+        clips = make_clips(1, 100)
+        o = port.Oracle(WIDTH, clips[0][0][0].shape[0])
+        ref = clips[0][0]
+        ts = []
+        for t in range(1, warm + steps + 1):
+            t0 = time.perf_counter()
+            o.phase_r(ref[0])
+            _, ref = o.encode_p(clips[0][pingpong(t, CLIP_LEN)], ref, QP, WINDOW, MAXDIFF)
+            ts.append(time.perf_counter() - t0)
+        sec = sum(ts[warm:])
+        value = steps / sec
+        line.update(value=value, steps=steps, warmup=warm, ms_per_step=1000 * sec / steps,
+                    cpu_baseline={"value": value, "unit": "frames/s", "cores": 1, "kind": "port",
+                                  "sample": "%d 1080p P pictures of 1 sequence, oracle port, 1 thread" % steps},
+                    e2e={"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line))
+        return 0
+    tmp = tempfile.mkdtemp(prefix="fh264_refarm_")
+    outs = run_reference_processes(nproc, 1 + warm + steps, 100, tmp)
+    # one step = one P picture of every running process; hot-path time only, slowest process per step
+    per_step = [max(hot_seconds(o, 1 + warm + k) for o in outs) for k in range(steps)]
+    sec = sum(per_step)
+    value = nproc * steps / sec
+    line.update(value=value, steps=steps, warmup=warm, ms_per_step=1000 * sec / steps,
+                cpu_baseline={"value": value, "unit": "frames/s", "cores": nproc, "kind": "reference",
+                              "sample": "%d concurrent single-threaded reference processes (of %d host cores), each 1 I + %d P 1080p pictures; "
+                                        "timed: %d P pictures per process, hot-path calls only (interEncoding, quantizationTransform, "
+                                        "transformDecodingP_Skip, FillInterpolatedRefFrame, selectNALUnitType)" % (nproc, cores, warm + steps, steps)},
+                e2e={"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, nseq_total):
+    return {"workload": "BASELINE.json config 5 sharding: %d independent synthetic 1080p sequences per GPU (%d total), coded 1920x1072, "
+                        "IPPP, 1 step = 1 P picture of every sequence" % (args.seqs, nseq_total),
+            "qp": QP, "window": WINDOW, "maxdiff_set": MAXDIFF, "basic": 0, "seqs_per_gpu": args.seqs, "clip": "%d-picture ping-pong" % CLIP_LEN,
+            "first_picture": "source picture 0 uploaded as the reconstruction (I pictures are host work, out of scope)",
+            "l2": "per-step working set (>330 MB of reference planes/features per sequence) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seqs", type=int, default=8, help="independent sequences per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import h264_fer_b200 as fh
+    from h264_fer_b200.native import PinnedArray
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, Wu = args.seqs, args.steps, max(args.warmup, 3)
+    clips = make_clips(B, 100 + rank * B)
+    H = clips[0][0][0].shape[0]
+    nmb = (WIDTH // 16) * (H // 16)
+    ysz, csz = WIDTH * H, WIDTH * H // 4
+
+    # host (pinned) and device-resident copies of every source picture
+    pinned = [[PinnedArray((ysz + 2 * csz,), np.uint8) for _ in range(CLIP_LEN)] for _ in range(B)]
+    for b in range(B):
+        for t in range(CLIP_LEN):
+            a = pinned[b][t].array
+            a[:ysz] = clips[b][t][0].ravel(); a[ysz:ysz + csz] = clips[b][t][1].ravel(); a[ysz + csz:] = clips[b][t][2].ravel()
+    dev = [[torch.from_numpy(pinned[b][t].array.copy()).cuda() for t in range(CLIP_LEN)] for b in range(B)]
+    results = PinnedArray((B, nmb), fh.MB_RESULT_DTYPE)
+
+    s = fh.Session(WIDTH, H, batch=B, device=local)
+    stream = torch.cuda.current_stream()
+    s.set_stream(stream.cuda_stream)
+    idr_decisions = 0
+
+    def reset():
+        for b in range(B):
+            s.upload_recon(b, *clips[b][0])
+        s.sync()
+
+    def step(t, host):
+        nonlocal idr_decisions
+        k = pingpong(t, CLIP_LEN)
+        for b in range(B):
+            if host:
+                p = pinned[b][k].ptr
+                s.upload_source_ptrs(b, p, p + ysz, p + ysz + csz, device=False)
+            else:
+                p = dev[b][k].data_ptr()
+                s.upload_source_ptrs(b, p, p + ysz, p + ysz + csz, device=True)
+        sads = s.scene_sad_batch()                                   # selectNALUnitType's measure (ref_frames.cpp:210-224)
+        idr_decisions += sum(1 for v in sads if v > (nmb << 12))
+        s.encode_p(QP, WINDOW, MAXDIFF, 0, out=results.array, sync=False, download=host)
+
+    def timed(host):
+        reset()
+        t = 1
+        for _ in range(Wu):
+            step(t, host); t += 1
+        s.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            step(t, host); t += 1
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        for b in range(B):
+            s.picture_status(b)
+        return ms, clocks
+
+    ms_dev, clocks = timed(host=False)
+    ms_e2e, clocks_e2e = timed(host=True)
+
+    # per-kernel device times (CUDA events inside the library, on the launching stream), a few instrumented steps
+    reset()
+    acc, nsamp, t = {}, 0, 1
+    for i in range(3 + 4):
+        step(t, False); t += 1
+        tm = s.last_timings()
+        if i >= 3:
+            for k_, v in tm.items():
+                acc[k_] = acc.get(k_, 0.0) + v
+            nsamp += 1
+    tm = {k_: v / nsamp for k_, v in acc.items()}
+    counts = [s.mode_counts(b) for b in range(B)]
+
+    if rank == 0:
+        hbm_peak, peak_src, sm_max = peaks()
+        frames_per_step = B * world
+        value = frames_per_step * K / (ms_dev / 1000.0)
+        e2e_value = frames_per_step * K / (ms_e2e / 1000.0)
+        kernels = {"k_stage3": tm["k_stage3_ms"], "k_stage2": tm["k_stage2_ms"], "k_phase_b": tm["phase_b_ms"], "k_phase_c": tm["phase_c_ms"],
+                   "k_interp": tm["k_interp_ms"], "k_features": tm["k_features_ms"], "k_tile_index": tm["k_tile_index_ms"]}
+        dom = max(kernels, key=kernels.get)
+        alg_bytes = ALG_BYTES_PER_MB * nmb * B            # one launch processes B pictures
+        achieved = alg_bytes / (kernels[dom] / 1000.0) / 1e9
+        # phase C alone is the HBM-bound kernel of the path: report it too
+        c_achieved = alg_bytes / (tm["phase_c_ms"] / 1000.0) / 1e9
+        int_ops = ALG_INTOPS_PER_MB * nmb * B
+        step_ms = tm["total_ms"]
+        line = {
+            "metric": "1080p P-picture frames/s, ME + transform/quant/reconstruction hot path", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": K, "warmup": Wu, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic", "config": workload_config(args, B * world),
+            "macroblocks_per_s": value * nmb,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * (ysz + 2 * csz), "d2h_bytes_per_step": B * nmb * 832 + B * 8,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": 13 * K,
+            "clocks": clocks, "clocks_e2e": clocks_e2e,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "algorithmic bytes = 1984 B/MB x %d MB x %d pictures per launch / live CUDA-event duration of the dominant kernel; "
+                                 "the ME kernels are integer-pipe bound, see int_roofline" % (nmb, B)},
+            "roofline_phase_c": {"bound": "hbm", "kernel": "k_phase_c", "achieved": c_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": c_achieved / hbm_peak},
+            "int_roofline": {"ops_per_mb": ALG_INTOPS_PER_MB, "achieved_tops": int_ops / (step_ms / 1000.0) / 1e12,
+                             "peak_tops_nominal": 148 * 128 * sm_max * 1e6 / 1e12,
+                             "frac": (int_ops / (step_ms / 1000.0) / 1e12) / (148 * 128 * sm_max * 1e6 / 1e12),
+                             "note": "SURVEY.md §8d: 0.43 M int32-lane ops per MB over the whole step; peak = 148 SMs x 128 lanes x max SM clock"},
+            "kernel_ms_per_step": kernels, "phase_ms_per_step": {k_: tm[k_] for k_ in ("phase_a_ms", "phase_b_ms", "phase_c_ms", "copy_phase_r_ms", "total_ms")},
+            "idr_decisions": idr_decisions, "mode_counts_last_picture_seq0": counts[0],
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline():
+    """Reference (or port) on ONE host core, bounded sample: 1 I + 1 P 1080p picture; hot-path time of the P picture."""
+    from oracle import refdump
+    try:
+        if refdump.have_ref_encoder():
+            tmp = tempfile.mkdtemp(prefix="fh264_cpubase_")
+            o = run_reference_processes(1, 2, 100, tmp)[0]
+            sec = hot_seconds(o, 1)
+            return {"value": 1.0 / sec, "unit": "frames/s", "cores": 1, "kind": "reference",
+                    "sample": "unmodified reference, 1 thread: 1 I + 1 P 1080p picture (seed 100), timed = hot-path calls of the P picture "
+                              "(%.2f s; whole picture %.2f s)" % (sec, o["t_picture"][1])}
+        from oracle import port
+        clips = make_clips(1, 100)
+        o = port.Oracle(WIDTH, clips[0][0][0].shape[0])
+        t0 = time.perf_counter()
+        o.phase_r(clips[0][0][0])
+        o.encode_p(clips[0][1], clips[0][0], QP, WINDOW, MAXDIFF)
+        sec = time.perf_counter() - t0
+        return {"value": 1.0 / sec, "unit": "frames/s", "cores": 1, "kind": "port", "sample": "oracle port, 1 thread, 1 P 1080p picture (%.2f s)" % sec}
+    except Exception as e:  # the baseline is reported, never required
+        return {"value": None, "unit": "frames/s", "cores": 1, "kind": "reference", "sample": "failed: %r" % (e,)}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

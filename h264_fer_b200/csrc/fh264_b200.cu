@@ -38,8 +38,10 @@ struct fh264_session {
     uint32_t epoch;
     std::vector<char> has_ref;
     uint32_t *h_status;             // pinned: batch * ST_WORDS, snapshot after phase C of the last encode
-    uint32_t *h_sad;                // pinned: ST_WORDS scratch for scene_sad
+    uint64_t *h_sad;                // pinned: batch scene SADs
+    unsigned long long *d_sadout;
     cudaEvent_t ev[5];
+    cudaEvent_t evk[4];             // after stage3, after interp, after features (per-kernel split of phases A and R)
     bool timed;
     std::vector<void *> allocs;
     // scratch for the stand-alone entry points
@@ -55,6 +57,12 @@ __global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
     if (threadIdx.x == 0) *ticket = 0;
 }
 __global__ void k_begin_ref(SeqDev *seqs, int seq0) { seqs[seq0 + threadIdx.x].status[ST_FLAGS_NEXT] = 0; }
+__global__ void k_zero_sad(SeqDev *seqs, int seq0) { uint32_t *st = seqs[seq0 + threadIdx.x].status; st[ST_SAD_LO] = 0; st[ST_SAD_HI] = 0; }
+__global__ void k_gather_sad(SeqDev *seqs, int seq0, unsigned long long *out)
+{
+    const uint32_t *st = seqs[seq0 + threadIdx.x].status;
+    out[threadIdx.x] = (unsigned long long)st[ST_SAD_LO] | ((unsigned long long)st[ST_SAD_HI] << 32);
+}
 __global__ void k_swap_ref(SeqDev *seqs, int seq0)
 {
     SeqDev &S = seqs[seq0 + threadIdx.x];
@@ -85,6 +93,7 @@ extern "C" int fh264_close(fh264_session *s)
     if (s->h_status) cudaFreeHost(s->h_status);
     if (s->h_sad) cudaFreeHost(s->h_sad);
     for (int i = 0; i < 5; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (int i = 0; i < 4; i++) if (s->evk[i]) cudaEventDestroy(s->evk[i]);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return FH264_OK;
@@ -108,8 +117,9 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
 
     fh264_session *s = new fh264_session();
     s->batch = batch; s->device = device; s->epoch = 0; s->timed = false; s->own_stream = true;
-    s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->scr_mbs = 0;
+    s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->d_sadout = nullptr; s->scr_mbs = 0;
     for (int i = 0; i < 5; i++) s->ev[i] = nullptr;
+    for (int i = 0; i < 4; i++) s->evk[i] = nullptr;
     for (int i = 0; i < 3; i++) s->d_scr[i] = nullptr;
     s->d_scr16[0] = s->d_scr16[1] = nullptr;
     Geo &g = s->g;
@@ -121,8 +131,10 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
 #define OPEN_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(FH264_E_CUDA, #call, e_); fh264_close(s); return FH264_E_CUDA; } } while (0)
     OPEN_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 5; i++) OPEN_CK(cudaEventCreate(&s->ev[i]));
+    for (int i = 0; i < 4; i++) OPEN_CK(cudaEventCreate(&s->evk[i]));
     OPEN_CK(cudaHostAlloc((void **)&s->h_status, sizeof(uint32_t) * ST_WORDS * batch, cudaHostAllocDefault));
-    OPEN_CK(cudaHostAlloc((void **)&s->h_sad, sizeof(uint32_t) * ST_WORDS, cudaHostAllocDefault));
+    OPEN_CK(cudaHostAlloc((void **)&s->h_sad, sizeof(uint64_t) * batch, cudaHostAllocDefault));
+    OPEN_CK(dalloc(s, &s->d_sadout, (size_t)batch));
     memset(s->h_status, 0, sizeof(uint32_t) * ST_WORDS * batch);
     const size_t WH = (size_t)g.WH, CWH = WH / 4;
     fh264_mb_result *results = nullptr;
@@ -210,9 +222,12 @@ static int launch_phase_r(fh264_session *s, int seq0, int nseq)
     const Geo &g = s->g;
     k_begin_ref<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0);
     dim3 gi((g.W + IT_W - 1) / IT_W, (g.H + IT_H - 1) / IT_H, nseq);
+    cudaEventRecord(s->evk[1], s->stream);
     k_interp<<<gi, 256, 0, s->stream>>>(s->d_seqs, seq0, g);
+    cudaEventRecord(s->evk[2], s->stream);
     dim3 gf((g.W + FT_W - 1) / FT_W, (g.H + FT_H - 1) / FT_H, 16 * nseq);
     k_features<<<gf, 256, 0, s->stream>>>(s->d_seqs, seq0, g);
+    cudaEventRecord(s->evk[3], s->stream);
     dim3 gt(g.ntiles, nseq);
     k_tile_index<<<gt, 256, FH_CELLS * 4, s->stream>>>(s->d_seqs, seq0, g);
     CKL();
@@ -233,19 +248,35 @@ extern "C" int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, c
     return FH264_OK;
 }
 
-extern "C" int fh264_scene_sad(fh264_session *s, int seq, uint64_t *sad)
+extern "C" int fh264_scene_sad_batch(fh264_session *s, int seq0, int nseq, uint64_t *sads)
+{
+    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
+    if (!sads) return fail(FH264_E_ARG, "null output");
+    for (int b = seq0; b < seq0 + nseq; b++)
+        if (!s->has_ref[b]) return fail(FH264_E_STATE, "scene_sad before any reference picture (dpb.L == NULL => IDR, ref_frames.cpp:191)");
+    CK(cudaSetDevice(s->device));
+    k_zero_sad<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0);
+    dim3 gs(nseq >= 8 ? 74 : 296, nseq);
+    k_scene_sad<<<gs, 256, 0, s->stream>>>(s->d_seqs, seq0, s->g);
+    k_gather_sad<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0, s->d_sadout);
+    CKL();
+    CK(cudaMemcpyAsync(s->h_sad, s->d_sadout, sizeof(uint64_t) * nseq, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    memcpy(sads, s->h_sad, sizeof(uint64_t) * nseq);
+    return FH264_OK;
+}
+
+extern "C" int fh264_scene_sad(fh264_session *s, int seq, uint64_t *sad) { return fh264_scene_sad_batch(s, seq, 1, sad); }
+
+extern "C" int fh264_upload_source_device(fh264_session *s, int seq, const void *dy, const void *dcb, const void *dcr)
 {
     int rc = check_seq(s, seq, 1); if (rc) return rc;
-    if (!sad) return fail(FH264_E_ARG, "null output");
-    if (!s->has_ref[seq]) return fail(FH264_E_STATE, "scene_sad before any reference picture (dpb.L == NULL => IDR, ref_frames.cpp:191)");
+    if (!dy || !dcb || !dcr) return fail(FH264_E_ARG, "null plane");
     CK(cudaSetDevice(s->device));
-    CK(cudaMemsetAsync(s->h[seq].status + ST_SAD_LO, 0, 8, s->stream));
-    dim3 gs(148 * 2, 1);
-    k_scene_sad<<<gs, 256, 0, s->stream>>>(s->d_seqs, seq, s->g);
-    CKL();
-    CK(cudaMemcpyAsync(s->h_sad, s->h[seq].status, sizeof(uint32_t) * ST_WORDS, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    *sad = (uint64_t)s->h_sad[ST_SAD_LO] | ((uint64_t)s->h_sad[ST_SAD_HI] << 32);
+    const size_t WH = (size_t)s->g.WH;
+    CK(cudaMemcpyAsync(s->h[seq].cur[0], dy, WH, cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->h[seq].cur[1], dcb, WH / 4, cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->h[seq].cur[2], dcr, WH / 4, cudaMemcpyDeviceToDevice, s->stream));
     return FH264_OK;
 }
 
@@ -266,9 +297,11 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     cudaStream_t st = s->stream;
     CK(cudaEventRecord(s->ev[0], st));
     k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, s->d_ticket);
+    if (prm.basic) CK(cudaEventRecord(s->evk[0], st));
     if (!prm.basic) {
         dim3 ga(g.nparts, nseq);
         k_stage3<<<ga, PA_NT, 0, st>>>(s->d_seqs, seq0, g, prm);
+        CK(cudaEventRecord(s->evk[0], st));
         k_stage2<<<ga, PA_NT, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
     CK(cudaEventRecord(s->ev[1], st));
@@ -336,7 +369,7 @@ extern "C" int fh264_download_recon(fh264_session *s, int seq, uint8_t *y, uint8
     return FH264_OK;
 }
 
-extern "C" int fh264_last_timings(fh264_session *s, float ms[5])
+extern "C" int fh264_last_timings(fh264_session *s, float ms[10])
 {
     if (!s || !ms) return fail(FH264_E_ARG, "null argument");
     if (!s->timed) return fail(FH264_E_STATE, "no encode_p issued yet");
@@ -344,6 +377,11 @@ extern "C" int fh264_last_timings(fh264_session *s, float ms[5])
     CK(cudaEventSynchronize(s->ev[4]));
     for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms[i], s->ev[i], s->ev[i + 1]));
     CK(cudaEventElapsedTime(&ms[4], s->ev[0], s->ev[4]));
+    CK(cudaEventElapsedTime(&ms[5], s->ev[0], s->evk[0]));      // k_stage3 (+ k_begin_picture)
+    CK(cudaEventElapsedTime(&ms[6], s->evk[0], s->ev[1]));      // k_stage2
+    CK(cudaEventElapsedTime(&ms[7], s->evk[1], s->evk[2]));     // k_interp
+    CK(cudaEventElapsedTime(&ms[8], s->evk[2], s->evk[3]));     // k_features
+    CK(cudaEventElapsedTime(&ms[9], s->evk[3], s->ev[4]));      // k_tile_index
     return FH264_OK;
 }
 

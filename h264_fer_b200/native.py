@@ -19,7 +19,7 @@ ERRORS = {-1: "FH264_E_ARG", -2: "FH264_E_CUDA", -3: "FH264_E_NO_DEVICE", -4: "F
           -6: "FH264_E_CAPACITY", -7: "FH264_E_UNSUPPORTED"}
 
 EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version", "fh264_set_stream", "fh264_sync",
-           "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_recon", "fh264_scene_sad",
+           "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
            "fh264_debug_feature", "fh264_last_timings"]
@@ -63,6 +63,8 @@ def load_library():
     L.fh264_upload_source.argtypes = [vp, i32, u8p, u8p, u8p]
     L.fh264_upload_recon.argtypes = [vp, i32, u8p, u8p, u8p]
     L.fh264_scene_sad.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
+    L.fh264_scene_sad_batch.argtypes = [vp, i32, i32, C.POINTER(C.c_uint64)]
+    L.fh264_upload_source_device.argtypes = [vp, i32, vp, vp, vp]
     L.fh264_encode_p.argtypes = [vp, i32, i32, C.POINTER(Params), vp]
     L.fh264_encode_p_async.argtypes = [vp, i32, i32, C.POINTER(Params), vp]
     L.fh264_picture_status.argtypes = [vp, i32]
@@ -159,6 +161,17 @@ class Session:
         self._keep = (y, cb, cr)
         self._ck(self.L.fh264_upload_source(self.handle, seq, _ptr(y), _ptr(cb), _ptr(cr)))
 
+    def upload_source_ptrs(self, seq, py, pcb, pcr, device=False):
+        """Raw-pointer variant (pinned host memory, or device memory with device=True); asynchronous."""
+        fn = self.L.fh264_upload_source_device if device else self.L.fh264_upload_source
+        self._ck(fn(self.handle, seq, C.c_void_p(py), C.c_void_p(pcb), C.c_void_p(pcr)))
+
+    def scene_sad_batch(self, seq0=0, nseq=None):
+        nseq = self.batch - seq0 if nseq is None else nseq
+        v = (C.c_uint64 * nseq)()
+        self._ck(self.L.fh264_scene_sad_batch(self.handle, seq0, nseq, v))
+        return [int(x) for x in v]
+
     def upload_recon(self, seq, y, cb, cr):
         y, cb, cr = _u8(y), _u8(cb), _u8(cr)
         assert y.size == self.w * self.h and cb.size == y.size // 4 and cr.size == y.size // 4
@@ -170,15 +183,16 @@ class Session:
         self._ck(self.L.fh264_scene_sad(self.handle, seq, C.byref(v)))
         return int(v.value)
 
-    def encode_p(self, qp, window, maxdiff_set, basic=0, seq0=0, nseq=None, out=None, sync=True):
-        """Returns a structured array [nseq, nmb] of MB_RESULT_DTYPE (a view of `out` if given)."""
+    def encode_p(self, qp, window, maxdiff_set, basic=0, seq0=0, nseq=None, out=None, sync=True, download=True):
+        """Returns a structured array [nseq, nmb] of MB_RESULT_DTYPE (a view of `out` if given); with download=False the
+        records stay on the device (NULL results pointer) and None is returned."""
         nseq = self.batch - seq0 if nseq is None else nseq
         prm = Params(int(qp), int(window), int(maxdiff_set), int(basic))
-        if out is None:
+        if download and out is None:
             out = np.zeros((nseq, self.nmb), dtype=MB_RESULT_DTYPE)
         fn = self.L.fh264_encode_p if sync else self.L.fh264_encode_p_async
-        self._ck(fn(self.handle, seq0, nseq, C.byref(prm), _ptr(out)))
-        return out
+        self._ck(fn(self.handle, seq0, nseq, C.byref(prm), _ptr(out) if download else None))
+        return out if download else None
 
     def picture_status(self, seq):
         self._ck(self.L.fh264_picture_status(self.handle, seq))
@@ -196,9 +210,11 @@ class Session:
         return list(c)
 
     def last_timings(self):
-        t = (C.c_float * 5)()
+        t = (C.c_float * 10)()
         self._ck(self.L.fh264_last_timings(self.handle, t))
-        return dict(zip(("phase_a_ms", "phase_b_ms", "phase_c_ms", "phase_r_ms", "total_ms"), [float(x) for x in t]))
+        names = ("phase_a_ms", "phase_b_ms", "phase_c_ms", "copy_phase_r_ms", "total_ms", "k_stage3_ms", "k_stage2_ms",
+                 "k_interp_ms", "k_features_ms", "k_tile_index_ms")
+        return dict(zip(names, [float(x) for x in t]))
 
     # -- building blocks
     def tq_macroblocks(self, src384, pred384, qp):

@@ -95,6 +95,9 @@ void fh264_host_free(void *p);
  * session stream; the host buffers must stay valid until the next fh264_sync()/synchronous call. */
 int fh264_upload_source(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
 
+/* Same, from planes already resident in device memory (device pointers; device-to-device copy on the stream). */
+int fh264_upload_source_device(fh264_session *s, int seq, const void *dy, const void *dcb, const void *dcr);
+
 /* dpb := reconstruction of a picture coded elsewhere (host I picture), then phase R on it
  * (frameDeepCopy ref_frames.cpp:17-35 + FillInterpolatedRefFrame moestimation.cpp:74-173). */
 int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
@@ -102,6 +105,8 @@ int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, const uint8_
 /* Sum over luma of |frame - dpb| for sequence seq (selectNALUnitType ref_frames.cpp:210-224; the reference's
  * OpenCL AbsDiff kernel h264_kernels.cl:1-5 + host sum). Synchronous (returns the value). */
 int fh264_scene_sad(fh264_session *s, int seq, uint64_t *sad);
+/* The same for sequences [seq0, seq0+nseq) with one launch and one synchronisation. */
+int fh264_scene_sad_batch(fh264_session *s, int seq0, int nseq, uint64_t *sads);
 
 /* Code one P picture of sequences [seq0, seq0+nseq): motion search, mode decision, motion compensation,
  * pixel snapping, transform/quant/reconstruction for every MB; then dpb := reconstruction and phase R for the
@@ -143,10 +148,11 @@ int fh264_motion_compensate(fh264_session *s, int seq, const int16_t *qmv, uint8
 int fh264_debug_plane(fh264_session *s, int seq, int f, uint8_t *out);
 int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out);
 
-/* Device time of the phases of the last fh264_encode_p call, milliseconds, measured with CUDA events on the
- * session stream: [0] phase A (predictor-independent search), [1] phase B (wavefront), [2] phase C (MC + TQ +
- * reconstruction), [3] phase R (reference preparation for the next picture), [4] total. */
-int fh264_last_timings(fh264_session *s, float ms[5]);
+/* Device time of the last fh264_encode_p call, milliseconds, from CUDA events on the session stream:
+ * [0] phase A (predictor-independent search), [1] phase B (wavefront), [2] phase C (MC + TQ + reconstruction),
+ * [3] result copies + phase R (reference preparation for the next picture), [4] total; per kernel:
+ * [5] k_stage3, [6] k_stage2, [7] k_interp, [8] k_features, [9] k_tile_index. */
+int fh264_last_timings(fh264_session *s, float ms[10]);
 
 #ifdef __cplusplus
 }

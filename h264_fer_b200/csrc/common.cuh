@@ -1,6 +1,6 @@
 // fh264_b200 — shared device-side definitions.
 // Data layout in HBM (per sequence): planar u8 pictures (stride == width), 16 quarter-pel luma
-// planes, 80 uint16 box-sum feature planes, a 64x64-tile index of plane-0 positions sorted by (K0>>7, K1>>6),
+// planes, 16 planes of packed box-sum features (16 B per position), a 64x64-tile index of plane-0 positions sorted by (K0>>7, K1>>6),
 // per-partition phase-A lists, per-MB motion records and the ABI result records.
 #pragma once
 #include <cuda_runtime.h>
@@ -55,7 +55,7 @@ struct SeqDev {
     uint8_t *ref[3];        // `dpb`: previous reconstruction
     uint8_t *rec[3];        // reconstruction of the picture being coded (swapped with ref afterwards)
     uint8_t *planes;        // refFrameInterpolated[f].L, f-major, WH each (+16 bytes slack at the end)
-    uint16_t *kar;          // refFrameKar[k][f]: plane (f*5+k), WH each
+    uint4 *kar;             // refFrameKar[0..4][f] packed per position: [f][y][x] = {K0|K1<<16, K2|K3<<16, K4, 0}
     TileEntry *tent;        // ntiles * 4096 entries
     uint16_t *tstart;       // ntiles * FH_TSTART_PITCH
     PartA *parta;           // nparts
@@ -85,24 +85,22 @@ __device__ __forceinline__ uint2 load8_unaligned(const uint8_t *p)
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
 
-// satdLuma8x8MVs (moestimation.cpp:175-195), one row: |cur row - plane row| with the reference's clamping rule
+// satdLuma8x8MVs (moestimation.cpp:175-195), one row of the reference block with the reference's clamping rule
 // (block origin clamped to the picture as a whole, then each index clamped at the right/bottom edge only).
-__device__ __forceinline__ int sad_row8(uint2 cur, const uint8_t *plane, int W, int H, int x0, int y)
+__device__ __forceinline__ uint2 load_row8(const uint8_t *plane, int W, int H, int x0, int y)
 {
     y = min(y, H - 1);
-    const uint8_t *p = plane + (size_t)y * W + x0;
-    uint2 r;
-    if (x0 + 8 <= W) {
-        r = load8_unaligned(p);
-    } else {
-        uint32_t b[8];
+    if (x0 + 8 <= W) return load8_unaligned(plane + (size_t)y * W + x0);
+    uint32_t b[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) b[i] = plane[(size_t)y * W + min(x0 + i, W - 1)];
-        r.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-        r.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-    }
-    return __vsadu4(cur.x, r.x) + __vsadu4(cur.y, r.y);
+    for (int i = 0; i < 8; i++) b[i] = plane[(size_t)y * W + min(x0 + i, W - 1)];
+    return make_uint2(b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24), b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
 }
+__device__ __forceinline__ int sad8(uint2 a, uint2 b) { return __vsadu4(a.x, b.x) + __vsadu4(a.y, b.y); }
+__device__ __forceinline__ int sad_row8(uint2 cur, const uint8_t *plane, int W, int H, int x0, int y) { return sad8(cur, load_row8(plane, W, H, x0, y)); }
+
+// n / d for 0 <= n < 65536 / d with inv = 65536 / d + 1 (window geometry: d <= 129)
+__device__ __forceinline__ int fdiv_(int n, int inv) { return (int)(((unsigned)n * (unsigned)inv) >> 16); }
 
 // Feature distance (moestimation.cpp:267-276).
 __device__ __forceinline__ int feat_dist(const int s[5], int K0, int K1, int K2, int K3, int K4)

@@ -147,7 +147,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
             OPEN_CK(dalloc(s, &S.rec[c], c ? CWH : WH));
         }
         OPEN_CK(dalloc(s, &S.planes, 16 * WH));
-        OPEN_CK(dalloc(s, &S.kar, 80 * WH));
+        OPEN_CK(dalloc(s, &S.kar, 16 * WH));
         OPEN_CK(dalloc(s, &S.tent, (size_t)g.ntiles * FH_TILE * FH_TILE));
         OPEN_CK(dalloc(s, &S.tstart, (size_t)g.ntiles * FH_TSTART_PITCH));
         OPEN_CK(dalloc(s, &S.parta, (size_t)g.nparts));
@@ -170,6 +170,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     OPEN_CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.nmb, cudaMemcpyHostToDevice));
     OPEN_CK(dalloc(s, &s->d_ticket, (size_t)4));
     OPEN_CK(cudaFuncSetAttribute(k_tile_index, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_CELLS * 4));
+    OPEN_CK(cudaFuncSetAttribute(k_stage3, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     OPEN_CK(cudaDeviceSynchronize());
     *out = s;
     return FH264_OK;
@@ -299,10 +300,14 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, s->d_ticket);
     if (prm.basic) CK(cudaEventRecord(s->evk[0], st));
     if (!prm.basic) {
-        dim3 ga(g.nparts, nseq);
-        k_stage3<<<ga, PA_NT, 0, st>>>(s->d_seqs, seq0, g, prm);
+        const int g3 = prm.window / 2, g1 = prm.window / 16;
+        const int n3 = (2 * g3 + 1) * (2 * g3 + 1) + (2 * g1 + 1) * (2 * g1 + 1) * 16;
+        const int npad = (n3 + 31) & ~31;
+        const size_t smem3 = 4 * sizeof(S3Warp) + (size_t)4 * npad * sizeof(uint32_t);
+        dim3 g3d(g.nparts / 4, nseq), g2d(g.nparts / 2, nseq);
+        k_stage3<<<g3d, 128, smem3, st>>>(s->d_seqs, seq0, g, prm, npad);
         CK(cudaEventRecord(s->evk[0], st));
-        k_stage2<<<ga, PA_NT, 0, st>>>(s->d_seqs, seq0, g, prm);
+        k_stage2<<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
     CK(cudaEventRecord(s->ev[1], st));
     k_phase_b<<<(unsigned)(g.nmb * nseq), PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
@@ -459,12 +464,24 @@ extern "C" int fh264_debug_plane(fh264_session *s, int seq, int f, uint8_t *out)
     return FH264_OK;
 }
 
+__global__ void k_unpack_feature(const uint4 *__restrict__ kar, int n, int k, uint16_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 v = kar[i];
+    out[i] = (uint16_t)(k == 0 ? v.x & 0xffff : k == 1 ? v.x >> 16 : k == 2 ? v.y & 0xffff : k == 3 ? v.y >> 16 : v.z);
+}
+
 extern "C" int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out)
 {
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     if (!out || f < 0 || f > 15 || k < 0 || k > 4) return fail(FH264_E_ARG, "bad argument");
     CK(cudaSetDevice(s->device));
-    CK(cudaMemcpyAsync(out, s->h[seq].kar + (size_t)(f * 5 + k) * s->g.WH, (size_t)s->g.WH * 2, cudaMemcpyDeviceToHost, s->stream));
+    const int n = s->g.WH;
+    rc = ensure_scratch(s, (size_t)(n * 2 + 767) / 768); if (rc) return rc;
+    k_unpack_feature<<<(n + 255) / 256, 256, 0, s->stream>>>(s->h[seq].kar + (size_t)f * n, n, k, (uint16_t *)s->d_scr16[0]);
+    CKL();
+    CK(cudaMemcpyAsync(out, s->d_scr16[0], (size_t)n * 2, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return FH264_OK;
 }

@@ -4,13 +4,11 @@
 //   k_stage2  the stage-2 candidate SET (moestimation.cpp:470-497): positions whose 8x8 sum is within +-j_stop of
 //             the block's, gated by Manhattan distance and the two half-sums, in the reference's arrival order,
 //             with feature distance and SAD. Only the multiplier (|dx-genx|+|dy-geny|+4) is left to phase B.
-// One CTA (128 threads) per partition.
+// One WARP per partition (no block barriers).
 #pragma once
 #include "common.cuh"
-#include "select.cuh"
+#include "warp_select.cuh"
 
-#define PA_NT 128
-#define S3_COST_CAP 5632      // (64+1)^2 + (2*4+1)^2*16 = 5521 candidates at WindowSize 64
 #define COST_INVALID 0xffffffffu
 
 __device__ __forceinline__ void part_origin(const Geo &g, int part, int &xP, int &yP)
@@ -20,97 +18,144 @@ __device__ __forceinline__ void part_origin(const Geo &g, int part, int &xP, int
     yP = (mb / g.Wmb) * 16 + (pi >> 1) * 8;
 }
 
-__device__ __forceinline__ int feat_at(const uint16_t *__restrict__ kar, const Geo &g, const int s[5], int f, int x, int y)
+__device__ __forceinline__ int feat_of(const int s[5], const uint4 v)
 {
-    const uint16_t *K = kar + (size_t)f * 5 * g.WH + (size_t)y * g.W + x;
-    return feat_dist(s, __ldg(K), __ldg(K + g.WH), __ldg(K + 2 * (size_t)g.WH), __ldg(K + 3 * (size_t)g.WH), __ldg(K + 4 * (size_t)g.WH));
+    return feat_dist(s, (int)(v.x & 0xffff), (int)(v.x >> 16), (int)(v.y & 0xffff), (int)(v.y >> 16), (int)v.z);
 }
 
-__global__ void __launch_bounds__(PA_NT) k_stage3(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
+// Loads the 8x8 source block of a partition (8 rows of two words) into every lane's registers.
+__device__ __forceinline__ void load_cur8x8(const uint8_t *__restrict__ cur, const Geo &g, int xP, int yP, uint2 rows[8])
 {
-    __shared__ uint32_t cost[S3_COST_CAP];
-    __shared__ uint2 currow[8];
-    __shared__ SelectScratch sc;
-    __shared__ uint32_t mem_idx[FH_S3_MAX], mem_sad[FH_S3_MAX];
-    __shared__ int n_mem, n_valid;
+#pragma unroll
+    for (int r = 0; r < 8; r++) rows[r] = __ldg((const uint2 *)(cur + (size_t)(yP + r) * g.W + xP));
+}
+__device__ __forceinline__ uint2 pick_row(const uint2 rows[8], int r)
+{
+    uint2 cr = rows[0];
+#pragma unroll
+    for (int q = 1; q < 8; q++) if (r == q) cr = rows[q];
+    return cr;
+}
+
+// arrival index of the stage-3 list -> displacement and fraction
+__device__ __forceinline__ void s3_decode(int i, int n3a, int w3, int g3, int w1, int g1, int &dx, int &dy, int &f)
+{
+    if (i < n3a) { const int c = i / w3; dx = c - g3; dy = i - c * w3 - g3; f = 0; }
+    else { const int t = i - n3a, pos = t >> 4, c = pos / w1; f = t & 15; dx = c - g1; dy = pos - c * w1 - g1; }
+}
+
+struct S3Warp { WarpSelScratch ws; uint16_t members[FH_S3_MAX + 1]; uint16_t msad[FH_S3_MAX + 1]; };
+
+__global__ void __launch_bounds__(128, 4) k_stage3(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    S3Warp *sw = (S3Warp *)smem_raw + warp;
+    uint32_t *cost = (uint32_t *)(smem_raw + 4 * sizeof(S3Warp)) + (size_t)warp * npad;
     const SeqDev &S = seqs[seq0 + blockIdx.y];
-    const int part = blockIdx.x, tid = threadIdx.x;
+    const int part = blockIdx.x * 4 + warp;
     int xP, yP;
     part_origin(g, part, xP, yP);
-    if (tid < 8) currow[tid] = *(const uint2 *)(S.cur[0] + (size_t)(yP + tid) * g.W + xP);
-    if (tid == 0) { n_mem = 0; n_valid = 0; }
-    __syncthreads();
+    uint2 rows[8];
+    load_cur8x8(S.cur[0], g, xP, yP, rows);
     int s[5];
-    { uint2 rows[8];
-#pragma unroll
-      for (int r = 0; r < 8; r++) rows[r] = currow[r];
-      block_sums(rows, s); }
+    block_sums(rows, s);
+    const int W = g.W, H = g.H;
     const int g3 = prm.window / 2, g1 = prm.window / 16;
     const int w3 = 2 * g3 + 1, w1 = 2 * g1 + 1;
     const int n3a = w3 * w3, n3b = w1 * w1 * 16, N = n3a + n3b;
-    int valid = 0;
-    // first call: MEstimation(g = window/2, frac 0) — threads walk row-major (coalesced), arrival index is x-major
-    for (int t = tid; t < n3a; t += PA_NT) {
-        const int r = t / w3, c = t - r * w3, dx = c - g3, dy = r - g3;
-        const int rx = xP + dx, ry = yP + dy;
-        uint32_t cst = COST_INVALID;
-        if (rx >= 0 && rx < g.W && ry >= 0 && ry < g.H) { cst = (uint32_t)((iabs_(dx) + iabs_(dy) + 4) * feat_at(S.kar, g, s, 0, rx, ry)); valid++; }
-        cost[c * w3 + r] = cst;
-    }
-    // second call: MEstimation(g = window/16, all 16 fractions); arrival = (dx, dy, frac)
-    for (int t = tid; t < n3b; t += PA_NT) {
-        const int f = t & 15, pos = t >> 4, dx = pos / w1 - g1, dy = pos % w1 - g1;
-        const int rx = xP + dx, ry = yP + dy;
-        uint32_t cst = COST_INVALID;
-        if (rx >= 0 && rx < g.W && ry >= 0 && ry < g.H) { cst = (uint32_t)((iabs_(dx) + iabs_(dy) + 4) * feat_at(S.kar, g, s, f, rx, ry)); valid++; }
-        cost[n3a + t] = cst;
-    }
-    if (valid) atomicAdd(&n_valid, valid);
-    __syncthreads();
-    const int K = min(FH_S3_MAX, n_valid);
-    if (K > 0) {
-        int lt, lt2;
-        const uint32_t T = block_kth_smallest<uint32_t, PA_NT>(N, K, 24, [&](int i) { return cost[i]; }, &sc, &lt);
-        // ties at the threshold enter in arrival order: the (K - lt) smallest indices among cost == T
-        const uint32_t Ti = block_kth_smallest<uint32_t, PA_NT>(N, K - lt, 13, [&](int i) { return cost[i] == T ? (uint32_t)i : COST_INVALID; }, &sc, &lt2);
-        for (int i = tid; i < N; i += PA_NT) {
-            const uint32_t c = cost[i];
-            if (c < T || (c == T && (uint32_t)i <= Ti)) mem_idx[atomicAdd(&n_mem, 1)] = (uint32_t)i;
+    const uint4 *__restrict__ K0p = S.kar;
+    // first call: MEstimation(g = window/2, frac 0); arrival index = (dx + g3) * w3 + (dy + g3).
+    // Full 32-column chunks: lane = column (coalesced 16-byte loads), 8 rows in flight.
+    const int ncf = w3 & ~31;
+    for (int cb = 0; cb < ncf; cb += 32) {
+        const int c = cb + lane, dx = c - g3, rx = xP + dx;
+        const bool xok = rx >= 0 && rx < W;
+        const int adx = iabs_(dx) + 4;
+        for (int r0 = 0; r0 < w3; r0 += 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int ry = yP + r0 + u - g3;
+                v[u] = make_uint4(0, 0, 0, 1u);
+                if (xok && r0 + u < w3 && ry >= 0 && ry < H) v[u] = __ldg(K0p + (size_t)ry * W + rx);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int r = r0 + u;
+                if (r < w3) cost[c * w3 + r] = v[u].w ? COST_INVALID : (uint32_t)((adx + iabs_(r - g3)) * feat_of(s, v[u]));
+            }
         }
     }
-    __syncthreads();
-    const int nm = n_mem;
-    // SADs of the members (satdLuma8x8MVs): 4 threads per member, 2 rows each
-    for (int base = 0; base < nm; base += PA_NT / 4) {
-        const int m = base + (tid >> 2);
-        int sad = 0;
-        if (m < nm) {
-            const int i = (int)mem_idx[m];
-            int dx, dy, f;
-            if (i < n3a) { dx = i / w3 - g3; dy = i % w3 - g3; f = 0; }
-            else { const int t = i - n3a; f = t & 15; dx = (t >> 4) / w1 - g1; dy = (t >> 4) % w1 - g1; }
-            const uint8_t *pl = S.planes + (size_t)f * g.WH;
-            const int r0 = (tid & 3) * 2;
-            sad = sad_row8(currow[r0], pl, g.W, g.H, xP + dx, yP + dy + r0) + sad_row8(currow[r0 + 1], pl, g.W, g.H, xP + dx, yP + dy + r0 + 1);
+    // leftover columns: lane = row
+    for (int c = ncf; c < w3; c++) {
+        const int dx = c - g3, rx = xP + dx;
+        const bool xok = rx >= 0 && rx < W;
+        for (int r = lane; r < w3; r += 32) {
+            const int ry = yP + r - g3;
+            uint32_t cst = COST_INVALID;
+            if (xok && ry >= 0 && ry < H) cst = (uint32_t)((iabs_(dx) + iabs_(r - g3) + 4) * feat_of(s, __ldg(K0p + (size_t)ry * W + rx)));
+            cost[c * w3 + r] = cst;
         }
-        sad += __shfl_xor_sync(0xffffffffu, sad, 1);
-        sad += __shfl_xor_sync(0xffffffffu, sad, 2);
-        if (m < nm && (tid & 3) == 0) mem_sad[m] = (uint32_t)sad;
     }
-    __syncthreads();
-    // list order = (cost, arrival index); rank by counting among <= 33 members
-    if (tid < nm) {
-        const uint32_t i = mem_idx[tid], c = cost[i];
-        int rank = 0;
-        for (int k = 0; k < nm; k++) { const uint32_t ik = mem_idx[k], ck = cost[ik]; rank += (ck < c) || (ck == c && ik < i); }
+    // second call: MEstimation(g = window/16, all 16 fractions); arrival = ((dx+g1)*w1 + (dy+g1))*16 + frac.
+    // lane -> (fraction = lane & 15, position parity = lane >> 4); 8 loads in flight
+    {
+        const int f = lane & 15, npos = w1 * w1, inv1 = 65536 / w1 + 1;
+        const uint4 *__restrict__ Kf = S.kar + (size_t)f * g.WH;
+        for (int p0 = 0; p0 < npos; p0 += 16) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), rx = xP + cx - g1, ry = yP + pos - cx * w1 - g1;
+                v[u] = make_uint4(0, 0, 0, 1u);
+                if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) v[u] = __ldg(Kf + (size_t)ry * W + rx);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), dx = cx - g1, dy = pos - cx * w1 - g1;
+                if (pos < npos) cost[n3a + pos * 16 + f] = v[u].w ? COST_INVALID : (uint32_t)((iabs_(dx) + iabs_(dy) + 4) * feat_of(s, v[u]));
+            }
+        }
+    }
+    __syncwarp();
+    // the 33 smallest by (cost, arrival index), in list order
+    const int nm = warp_select_smallest(N, FH_S3_MAX, [&](int i) -> u64 { const uint32_t c = cost[i]; return c == COST_INVALID ? KEY_NONE : (((u64)c << 16) | (u64)i); },
+                                        &sw->ws, sw->members);
+    // SADs of the members (satdLuma8x8MVs): 8 lanes per member, one row each; 3 rounds of loads in flight
+    const int r = lane & 7;
+    const uint2 cr = pick_row(rows, r);
+    for (int base = 0; base < nm; base += 12) {
+        uint2 rr[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int m = base + u * 4 + (lane >> 3);
+            rr[u] = make_uint2(0, 0);
+            if (m < nm) {
+                int dx, dy, f;
+                s3_decode((int)sw->members[m], n3a, w3, g3, w1, g1, dx, dy, f);
+                rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, xP + dx, yP + dy + r);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int m = base + u * 4 + (lane >> 3);
+            int sad = m < nm ? sad8(cr, rr[u]) : 0;
+            sad += __shfl_xor_sync(0xffffffffu, sad, 1);
+            sad += __shfl_xor_sync(0xffffffffu, sad, 2);
+            sad += __shfl_xor_sync(0xffffffffu, sad, 4);
+            if (m < nm && r == 0) sw->msad[m] = (uint16_t)sad;
+        }
+    }
+    __syncwarp();
+    for (int m = lane; m < nm; m += 32) {
         int dx, dy, f;
-        if ((int)i < n3a) { dx = (int)i / w3 - g3; dy = (int)i % w3 - g3; f = 0; }
-        else { const int t = (int)i - n3a; f = t & 15; dx = (t >> 4) / w1 - g1; dy = (t >> 4) % w1 - g1; }
+        s3_decode((int)sw->members[m], n3a, w3, g3, w1, g1, dx, dy, f);
         S3Entry e;
-        e.mvx = (int16_t)((dx << 2) | (f & 3)); e.mvy = (int16_t)((dy << 2) | (f >> 2)); e.sad = (uint16_t)mem_sad[tid]; e.pad = 0;
-        S.s3[(size_t)part * FH_S3_MAX + rank] = e;
+        e.mvx = (int16_t)((dx << 2) | (f & 3)); e.mvy = (int16_t)((dy << 2) | (f >> 2)); e.sad = sw->msad[m]; e.pad = 0;
+        S.s3[(size_t)part * FH_S3_MAX + m] = e;
     }
-    if (tid == 0) {
+    if (lane == 0) {
         PartA *pa = &S.parta[part];
 #pragma unroll
         for (int k = 0; k < 5; k++) pa->suma[k] = (uint16_t)s[k];
@@ -118,124 +163,195 @@ __global__ void __launch_bounds__(PA_NT) k_stage3(const SeqDev *__restrict__ seq
     }
 }
 
-__global__ void __launch_bounds__(PA_NT) k_stage2(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
+#define S2_WARP_CAP 1024      // gated survivors held per partition; beyond: FH264_E_CAPACITY
+#define S2_BINS 384           // (j, side) bins: 2*j + side, j <= 180
+struct S2Warp {
+    uint32_t akey[S2_WARP_CAP];      // arrival key: j<<21 | side<<20 | (dx+279)<<10 | (dy+279)
+    uint32_t afeat[S2_WARP_CAP];     // feature distance (18 bits) | SAD << 18
+    uint16_t order[S2_WARP_CAP];     // survivor index by output slot
+    uint32_t bins[S2_BINS];          // counts, then exclusive starts, then scatter cursors
+    int n_surv;
+};
+
+__global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
 {
-    __shared__ uint32_t akey[FH_S2_SMEM_CAP];    // arrival key: j<<21 | side<<20 | (dx+279)<<10 | (dy+279)
-    __shared__ uint32_t afeat[FH_S2_SMEM_CAP];
-    __shared__ uint16_t asad[FH_S2_SMEM_CAP];
-    __shared__ uint32_t jcount[192];
-    __shared__ uint2 currow[8];
-    __shared__ int n_surv, j_stop_s, n2_s, cnt0_s;
-    __shared__ uint32_t pool_off;
+    __shared__ S2Warp sm[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    S2Warp *w = &sm[warp];
     const SeqDev &S = seqs[seq0 + blockIdx.y];
-    const int part = blockIdx.x, tid = threadIdx.x;
+    const int part = blockIdx.x * 2 + warp;
     int xP, yP;
     part_origin(g, part, xP, yP);
-    if (tid < 8) currow[tid] = *(const uint2 *)(S.cur[0] + (size_t)(yP + tid) * g.W + xP);
-    for (int i = tid; i < 192; i += PA_NT) jcount[i] = 0;
-    if (tid == 0) n_surv = 0;
-    __syncthreads();
+    uint2 rows[8];
+    load_cur8x8(S.cur[0], g, xP, yP, rows);
     int s[5];
-    { uint2 rows[8];
-#pragma unroll
-      for (int r = 0; r < 8; r++) rows[r] = currow[r];
-      block_sums(rows, s); }
+    block_sums(rows, s);
+    for (int i = lane; i < S2_BINS; i += 32) w->bins[i] = 0;
+    if (lane == 0) w->n_surv = 0;
+    __syncwarp();
     // tiles intersecting the bounding box of the diamond |dx|+|dy| < 280 (moestimation.cpp:481)
     const int tx0 = max(0, xP - 279) >> FH_TILE_SHIFT, tx1 = min(g.W - 1, xP + 279) >> FH_TILE_SHIFT;
     const int ty0 = max(0, yP - 279) >> FH_TILE_SHIFT, ty1 = min(g.H - 1, yP + 279) >> FH_TILE_SHIFT;
     const int ntx = tx1 - tx0 + 1, nty = ty1 - ty0 + 1;
     const int qlo = max(0, s[0] - 180) >> 7, qhi = min(16383, s[0] + 180) >> 7, nq = qhi - qlo + 1;
     const int k1lo = max(0, s[1] - 99) >> 6, k1hi = min(8191, s[1] + 99) >> 6;
-    const int items = ntx * nty * nq;
-    for (int it = tid; it < items; it += PA_NT) {
-        const int q = qlo + it % nq, tt = it / nq;
-        const int tx = tx0 + tt % ntx, ty = ty0 + tt / ntx;
-        // closest point of the tile rectangle to the block origin
+    const int ntiles = ntx * nty, inv_ntx = 65536 / ntx + 1;
+    for (int tt = lane; tt < ntiles; tt += 32) {
+        const int tyy = fdiv_(tt, inv_ntx), tx = tx0 + tt - tyy * ntx, ty = ty0 + tyy;
         const int rx0 = tx << FH_TILE_SHIFT, ry0 = ty << FH_TILE_SHIFT;
         const int ddx = max(0, max(rx0 - xP, xP - (rx0 + FH_TILE - 1))), ddy = max(0, max(ry0 - yP, yP - (ry0 + FH_TILE - 1)));
         if (ddx + ddy >= 280) continue;
         const int tile = ty * g.tilesx + tx;
         const uint16_t *ts = S.tstart + (size_t)tile * FH_TSTART_PITCH;
-        const int e0 = __ldg(&ts[q * 128 + k1lo]), e1 = __ldg(&ts[q * 128 + k1hi + 1]);
         const uint4 *te = (const uint4 *)(S.tent + (size_t)tile * (FH_TILE * FH_TILE));
-        for (int e = e0; e < e1; e++) {
-            const uint4 v = __ldg(&te[e]);
-            const int x = v.x & 0xffff, y = v.x >> 16, k0 = v.y & 0xffff, k1 = v.y >> 16, k2 = v.z & 0xffff, k3 = v.z >> 16, k4 = v.w & 0xffff;
-            const int j = iabs_(k0 - s[0]), dx = x - xP, dy = y - yP;
-            if (j <= 180 && iabs_(dx) + iabs_(dy) < 280 && iabs_(k1 - s[1]) < 100 && iabs_(k2 - s[2]) < 100) {
-                atomicAdd(&jcount[j], j == 0 ? 2u : 1u);       // both sides visit bucket s0 when j == 0 (:476,486)
-                const int pos = atomicAdd(&n_surv, 1);
-                if (pos < FH_S2_SMEM_CAP) {
-                    akey[pos] = ((uint32_t)j << 21) | ((uint32_t)(k0 > s[0]) << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
-                    afeat[pos] = (uint32_t)feat_dist(s, k0, k1, k2, k3, k4);
+        // cell ranges of the (at most 4) K0 rows, fetched together
+        int e0[4], e1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            e0[q] = e1[q] = 0;
+            if (q < nq) { e0[q] = __ldg(&ts[(qlo + q) * 128 + k1lo]); e1[q] = __ldg(&ts[(qlo + q) * 128 + k1hi + 1]); }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            for (int eb = e0[q]; eb < e1[q]; eb += 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = eb + u < e1[q] ? __ldg(&te[eb + u]) : make_uint4(0, 0xffffu, 0, 0);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int x = v[u].x & 0xffff, y = v[u].x >> 16, k0 = v[u].y & 0xffff, k1 = v[u].y >> 16, k2 = v[u].z & 0xffff;
+                    const int j = iabs_(k0 - s[0]), dx = x - xP, dy = y - yP;
+                    if (eb + u < e1[q] && j <= 180 && iabs_(dx) + iabs_(dy) < 280 && iabs_(k1 - s[1]) < 100 && iabs_(k2 - s[2]) < 100) {
+                        const int side = k0 > s[0];
+                        atomicAdd(&w->bins[2 * j + side], 1u);
+                        const int pos = atomicAdd(&w->n_surv, 1);
+                        if (pos < S2_WARP_CAP) {
+                            w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
+                            w->afeat[pos] = (uint32_t)feat_dist(s, k0, k1, k2, (int)(v[u].z >> 16), (int)(v[u].w & 0xffff));
+                        }
+                    }
                 }
             }
         }
     }
-    __syncthreads();
-    // j_stop: first j at which the running gated count exceeds 128 (:496), else 180
-    if (tid < 32) {
-        uint32_t c[6], local = 0;
+    __syncwarp();
+    // j_stop: first j at which the running gated count exceeds 128 (:496), else 180. Bucket s0 is visited by both
+    // sides (:476,486), so its entries count twice. Lane l owns j = 6l .. 6l+5 (bins 12l .. 12l+11).
+    uint32_t cb[12], cj[6], local = 0;
 #pragma unroll
-        for (int i = 0; i < 6; i++) { c[i] = jcount[tid * 6 + i]; local += c[i]; }
-        uint32_t incl = local;
-        for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
-        uint32_t run = incl - local;
-        int first = 1 << 20;
+    for (int i = 0; i < 12; i++) cb[i] = w->bins[lane * 12 + i];
 #pragma unroll
-        for (int i = 0; i < 6; i++) { run += c[i]; if (run > 128 && first == (1 << 20)) first = tid * 6 + i; }
-        for (int d = 16; d; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
-        const int js = min(first, 180);
-        // candidates kept: all gated entries with j <= j_stop
-        uint32_t upto = 0;
+    for (int i = 0; i < 6; i++) { cj[i] = cb[2 * i] + cb[2 * i + 1]; if (lane == 0 && i == 0) cj[i] *= 2; local += cj[i]; }
+    uint32_t incl = local;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const uint32_t excl = incl - local;
+    uint32_t run = excl;
+    int first = 1 << 20;
 #pragma unroll
-        for (int i = 0; i < 6; i++) if (tid * 6 + i <= js) upto += c[i];
-        for (int d = 16; d; d >>= 1) upto += __shfl_xor_sync(0xffffffffu, upto, d);
-        if (tid == 0) { j_stop_s = js; n2_s = (int)upto; cnt0_s = (int)(jcount[0] >> 1); }
-    }
-    __syncthreads();
-    const int ns = n_surv, js = j_stop_s, cnt0 = cnt0_s;
-    int n2 = n2_s;
-    if (tid == 0) {
-        uint32_t off = 0;
-        if (ns > FH_S2_SMEM_CAP || n2 > 1023) { atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); n2 = 0; }
+    for (int i = 0; i < 6; i++) { run += cj[i]; if (run > 128 && first == (1 << 20)) first = lane * 6 + i; }
+    first = __reduce_min_sync(0xffffffffu, first);
+    const int js = min(first, 180);
+    uint32_t upto = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) if (lane * 6 + i <= js) upto += cj[i];
+    int n2 = (int)__reduce_add_sync(0xffffffffu, upto);
+    const int cnt0 = (int)__shfl_sync(0xffffffffu, cb[0], 0), ns = w->n_surv;
+    uint32_t off = 0;
+    if (lane == 0) {
+        if (ns > S2_WARP_CAP || n2 > 1023) { atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); n2 = 0; }
         else if (n2 > 0) {
             off = atomicAdd(&S.status[ST_S2CURSOR], (uint32_t)n2);
             if (off + (uint32_t)n2 > S.s2pool_size) { atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); n2 = 0; }
         }
-        pool_off = off; n2_s = n2;
         PartA *pa = &S.parta[part];
         pa->s2_off = off; pa->n2 = (uint32_t)n2;
     }
-    __syncthreads();
-    n2 = n2_s;
+    n2 = __shfl_sync(0xffffffffu, n2, 0);
+    off = __shfl_sync(0xffffffffu, off, 0);
     if (n2 == 0) return;
-    // SAD at integer displacement (fraction 0 => plane 0): 4 threads per survivor
-    const uint8_t *pl = S.planes;
-    for (int base = 0; base < ns; base += PA_NT / 4) {
-        const int m = base + (tid >> 2);
-        int sad = 0;
-        const bool live = m < ns && (int)(akey[m < ns ? m : 0] >> 21) <= js;
-        if (live) {
-            const uint32_t k = akey[m];
-            const int dx = (int)((k >> 10) & 1023) - 279, dy = (int)(k & 1023) - 279, r0 = (tid & 3) * 2;
-            sad = sad_row8(currow[r0], pl, g.W, g.H, xP + dx, yP + dy + r0) + sad_row8(currow[r0 + 1], pl, g.W, g.H, xP + dx, yP + dy + r0 + 1);
+    // Arrival order (:474-495): j ascending; minus side before plus side; x then y inside a bucket; bucket s0 twice.
+    // Output slot of bin b >= 2: start = (excl of j's before) + (side ? count of side 0 : 0); bin 0 starts at 0 and is
+    // written again at cnt0 (the second visit). Starts replace the counts in w->bins.
+    {
+        uint32_t st = excl;            // excl already counts bucket s0 twice
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const uint32_t base0 = (lane == 0 && i == 0) ? 0u : st;
+            w->bins[lane * 12 + 2 * i] = base0;
+            w->bins[lane * 12 + 2 * i + 1] = base0 + cb[2 * i];
+            st += cj[i];
         }
-        sad += __shfl_xor_sync(0xffffffffu, sad, 1);
-        sad += __shfl_xor_sync(0xffffffffu, sad, 2);
-        if (live && (tid & 3) == 0) asad[m] = (uint16_t)sad;
     }
-    __syncthreads();
-    // arrival order (:474-495): j ascending; minus side before plus side; x then y inside a bucket; bucket s0 twice
-    uint2 *pool = S.s2pool + pool_off;
-    for (int i = tid; i < ns; i += PA_NT) {
-        const uint32_t k = akey[i];
-        if ((int)(k >> 21) > js) continue;
-        int rank = 0;
-        for (int m = 0; m < ns; m++) rank += akey[m] < k;     // entries beyond j_stop have larger keys: never counted
+    __syncwarp();
+    for (int i = lane; i < ns; i += 32) {
+        const uint32_t k = w->akey[i];
+        const int bin = (int)(k >> 20);
+        if ((bin >> 1) > js) continue;
+        w->order[atomicAdd(&w->bins[bin], 1u)] = (uint16_t)i;    // arbitrary order inside a bin, fixed below
+    }
+    __syncwarp();
+    // order inside each bin by (x, y): bins hold 0-2 entries on textured content; insertion sort per bin
+    {
+        // segment of bin (j, side) = [start, start + count): the owning lane recomputes the start
+        uint32_t st = excl;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const uint32_t base0 = (lane == 0 && i == 0) ? 0u : st;
+#pragma unroll
+            for (int sd = 0; sd < 2; sd++) {
+                const int j = lane * 6 + i;
+                const int b0 = (int)(sd ? base0 + cb[2 * i] : base0), cnt = (int)cb[2 * i + sd];
+                if (j <= js && cnt > 1) {
+                    for (int a = 1; a < cnt; a++) {
+                        const uint16_t ia = w->order[b0 + a];
+                        const uint32_t ka = w->akey[ia];
+                        int p = a - 1;
+                        while (p >= 0 && w->akey[w->order[b0 + p]] > ka) { w->order[b0 + p + 1] = w->order[b0 + p]; p--; }
+                        w->order[b0 + p + 1] = ia;
+                    }
+                }
+            }
+            st += cj[i];
+        }
+    }
+    __syncwarp();
+    // SAD at integer displacement (fraction 0 => plane 0) for the kept candidates: 8 lanes per candidate, one row
+    // each, 4 rounds of loads in flight. Slots of the second visit of bucket s0 are copies.
+    const uint8_t *pl = S.planes;
+    const int r = lane & 7;
+    const uint2 cr = pick_row(rows, r);
+    const int nuniq = n2 - cnt0;          // distinct candidates: slots [0, cnt0) and [2*cnt0, n2)
+    for (int base = 0; base < nuniq; base += 16) {
+        uint2 rr[4];
+        int idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int m = base + u * 4 + (lane >> 3);
+            rr[u] = make_uint2(0, 0); idx[u] = -1;
+            if (m < nuniq) {
+                const int slot = m < cnt0 ? m : m + cnt0;
+                idx[u] = w->order[slot];
+                const uint32_t k = w->akey[idx[u]];
+                rr[u] = load_row8(pl, g.W, g.H, xP + (int)((k >> 10) & 1023) - 279, yP + (int)(k & 1023) - 279 + r);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int sad = idx[u] >= 0 ? sad8(cr, rr[u]) : 0;
+            sad += __shfl_xor_sync(0xffffffffu, sad, 1);
+            sad += __shfl_xor_sync(0xffffffffu, sad, 2);
+            sad += __shfl_xor_sync(0xffffffffu, sad, 4);
+            if (idx[u] >= 0 && r == 0) w->afeat[idx[u]] |= (uint32_t)sad << 18;
+        }
+    }
+    __syncwarp();
+    uint2 *pool = S.s2pool + off;
+    for (int m = lane; m < nuniq; m += 32) {
+        const int slot = m < cnt0 ? m : m + cnt0, i = w->order[slot];
+        const uint32_t k = w->akey[i];
         const int dx = (int)((k >> 10) & 1023) - 279, dy = (int)(k & 1023) - 279;
-        const uint2 v = make_uint2(((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16), afeat[i] | ((uint32_t)asad[i] << 18));
-        if ((k >> 21) == 0) { pool[rank] = v; pool[cnt0 + rank] = v; }
-        else pool[cnt0 + rank] = v;
+        const uint2 v = make_uint2(((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16), w->afeat[i]);
+        pool[slot] = v;
+        if (m < cnt0) pool[cnt0 + m] = v;
     }
 }

@@ -4,13 +4,15 @@
 // order (x + 2y), interleaved over the sequences of the batch, and spin on the `done` epochs of the two
 // neighbours that dominate the dependency set. A ticket's dependencies always hold smaller tickets, so the
 // smallest unfinished ticket can always run: no co-residency assumption, no deadlock.
+// Inside a CTA the three stages of a partition run CONCURRENTLY on different warps (warp 0: stage 1, warp 1: stage 2,
+// warp 2: stage 3) with warp-synchronous selection; one block barrier per partition joins their minima.
 // Per MB: P_Skip test (mode_pred.cpp:383-401, moestimation.cpp:402-425), then per 8x8 partition: predictor,
 // stage 1 (window/16 quarter-pel window around the predictor, 17 best by feature cost -> SAD), ranking of the
 // phase-A stage-2 set with the now known multiplier (33 best -> SAD looked up), the phase-A stage-3 list;
 // winner = first strict minimum of SAD + |mv - mvp|_1 in list order; then merge and final mvd (:529-564).
 #pragma once
 #include "common.cuh"
-#include "select.cuh"
+#include "warp_select.cuh"
 #include "phase_a.cuh"
 #include "phase_c.cuh"
 
@@ -64,33 +66,38 @@ __device__ __forceinline__ void predict_mv_(const NbCache &nc, int px, int py, i
 
 __device__ __forceinline__ int mv_cost(int mvx, int mvy, int px, int py) { return iabs_(mvx - px) + iabs_(mvy - py); }
 
+struct PBShared {
+    uint32_t keys1[S1_KEY_CAP];          // warp 0: stage-1 keys  cost << 11 | arrival index
+    u64 keys2[1024];                     // warp 1: stage-2 keys  cost << 10 | arrival rank
+    WarpSelScratch ws[2];
+    uint16_t mem1[FH_S1_MAX + 3], mem2[FH_S3_MAX + 3];
+    __align__(16) uint8_t cur[16][16];
+    NbCache nc;
+    u64 best[2][4];                      // per-warp minima, double-buffered across partitions
+    uint32_t my_ticket;
+    int red[4];
+};
+
 __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ seqs, int seq0, int nseq, Geo g, fh264_params prm,
                                                    uint32_t epoch, const int *__restrict__ wf_order, uint32_t *__restrict__ ticket)
 {
-    __shared__ uint32_t keys1[S1_KEY_CAP];
-    __shared__ unsigned long long keys2[1024];
-    __shared__ __align__(16) uint8_t cur[16][16];
-    __shared__ SelectScratch sc;
-    __shared__ NbCache nc;
-    __shared__ unsigned long long best;
-    __shared__ uint32_t my_ticket;
-    __shared__ int red[4];
-    __shared__ int n_valid1;
-    const int tid = threadIdx.x;
-    if (tid == 0) my_ticket = atomicAdd(ticket, 1u);
+    __shared__ PBShared sh;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) sh.my_ticket = atomicAdd(ticket, 1u);
     __syncthreads();
-    const uint32_t t = my_ticket;
+    const uint32_t t = sh.my_ticket;
     const SeqDev &S = seqs[seq0 + (int)(t % (uint32_t)nseq)];
     const int mb = wf_order[t / (uint32_t)nseq];
     const int mbx = mb % g.Wmb, mby = mb / g.Wmb;
     const int W = g.W, H = g.H;
+    NbCache &nc = sh.nc;
 
     // ---- wait for the dependencies (left; up-right, or up in the last column) -------------------------------
     if (tid == 0) {
-        if (mbx > 0) while (ld_acquire_u32(&S.done[mb - 1]) != epoch) __nanosleep(40);
+        if (mbx > 0) while (ld_acquire_u32(&S.done[mb - 1]) != epoch) __nanosleep(20);
         if (mby > 0) {
             const int d = mbx < g.Wmb - 1 ? mb - g.Wmb + 1 : mb - g.Wmb;
-            while (ld_acquire_u32(&S.done[d]) != epoch) __nanosleep(40);
+            while (ld_acquire_u32(&S.done[d]) != epoch) __nanosleep(20);
         }
     }
     __syncthreads();
@@ -102,8 +109,10 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
         if (av) { const int v = __ldcg((const int *)&S.motion[nmb].mv[q][0]); vx = (int16_t)(v & 0xffff); vy = v >> 16; }
         nc.mvx[w][q] = vx; nc.mvy[w][q] = vy;
         if (q == 0) nc.avail[w] = av;
+    } else if (tid >= 32 && tid < 48) {
+        const int r = tid - 32;
+        *(uint4 *)&sh.cur[r][0] = *(const uint4 *)(S.cur[0] + (size_t)(mby * 16 + r) * W + mbx * 16);
     }
-    if (tid < 16) *(uint4 *)&cur[tid][0] = *(const uint4 *)(S.cur[0] + (size_t)(mby * 16 + tid) * W + mbx * 16);
     __syncthreads();
 
     // ---- P_Skip trial ---------------------------------------------------------------------------------------
@@ -114,20 +123,18 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
     const int py = tid >> 3, px = (tid & 7) * 2;                          // this thread's two luma samples
     int p2[2];
     luma_pred_block<2, 1>(S, g, mbx * 16 + px + (smx >> 2), mby * 16 + py + (smy >> 2), smx & 3, smy & 3, p2);
-    const int c0 = cur[py][px], c1 = cur[py][px + 1];
+    const int c0 = sh.cur[py][px], c1 = sh.cur[py][px + 1];
     int maxdiff = prm.maxdiff_set;
     if (prm.maxdiff_set == -1) {                                          // moestimation.cpp:407-419
-        int v = c0 + c1;
-        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if ((tid & 31) == 0) red[tid >> 5] = v;
+        int v = __reduce_add_sync(0xffffffffu, c0 + c1);
+        if (lane == 0) sh.red[warp] = v;
         __syncthreads();
-        const int mean = (red[0] + red[1] + red[2] + red[3]) / 256;
+        const int mean = (sh.red[0] + sh.red[1] + sh.red[2] + sh.red[3]) / 256;
         __syncthreads();
-        v = iabs_(c0 - mean) + iabs_(c1 - mean);
-        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if ((tid & 31) == 0) red[tid >> 5] = v;
+        v = __reduce_add_sync(0xffffffffu, iabs_(c0 - mean) + iabs_(c1 - mean));
+        if (lane == 0) sh.red[warp] = v;
         __syncthreads();
-        maxdiff = max(3, (red[0] + red[1] + red[2] + red[3]) / 256);
+        maxdiff = max(3, (sh.red[0] + sh.red[1] + sh.red[2] + sh.red[3]) / 256);
     }
     const int nbad = __syncthreads_count(iabs_(c0 - p2[0]) > maxdiff || iabs_(c1 - p2[1]) > maxdiff);
     MbMotion mo;
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
 
     // ---- 8x8 search, partitions in order ----------------------------------------------------------------------
     int mv[4][2], sadq[4], curq[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
-    const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16;
+    const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16, inv1 = 65536 / w1 + 1;
     for (int pi = 0; pi < 4; pi++) {
         const int part = mb * 4 + pi;
         const int xP = mbx * 16 + (pi & 1) * 8, yP = mby * 16 + (pi >> 1) * 8;
@@ -157,84 +164,120 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
         const int genx = mvpx >> 2, geny = mvpy >> 2;
         PartA pa = S.parta[part];
         if (prm.basic) { pa.n2 = 0; pa.n3 = 0; pa.s2_off = 0; }
-        int s[5];
-        uint2 rows[8];
+        u64 *best = sh.best[pi & 1];
+        u64 mine = KEY_NONE;
+        if (warp == 0) {
+            // stage 1 (:458-469): window/16 quarter-pel window around the predictor; key = cost << 11 | arrival index
+            uint2 rows[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) rows[r] = *(const uint2 *)&cur[(pi >> 1) * 8 + r][(pi & 1) * 8];
-        block_sums(rows, s);          // suma[0..4] (:440-451); phase A is skipped with BasicInterEncoding
-        if (tid == 0) { best = ~0ull; n_valid1 = 0; }
-        __syncthreads();
-
-        // stage 1 (:458-469): cost key = cost << 11 | arrival index
-        int valid = 0;
-        for (int i = tid; i < n1; i += PB_NT) {
-            const int f = i & 15, pos = i >> 4, ox = pos / w1 - g1, oy = pos % w1 - g1;
-            const int rx = xP + genx + ox, ry = yP + geny + oy;
-            uint32_t key = COST_INVALID;
-            if (rx >= 0 && rx < W && ry >= 0 && ry < H) { key = ((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_at(S.kar, g, s, f, rx, ry)) << 11) | (uint32_t)i; valid++; }
-            keys1[i] = key;
-        }
-        if (valid) atomicAdd(&n_valid1, valid);
-        __syncthreads();
-        const int K1 = min(FH_S1_MAX, n_valid1);
-        if (K1 > 0) {
-            int lt;
-            const uint32_t T1 = block_kth_smallest<uint32_t, PB_NT>(n1, K1, 32, [&](int i) { return keys1[i]; }, &sc, &lt);
-            // SAD of the K1 members: scan keys, every member is picked up by the thread that owns its slot;
-            // 8 rows by the same thread (K1 <= 17 members spread over the block)
-            for (int i = tid; i < n1; i += PB_NT) {
-                const uint32_t key = keys1[i];
-                if (key <= T1) {
-                    const int f = i & 15, pos = i >> 4, dx = genx + pos / w1 - g1, dy = geny + pos % w1 - g1;
-                    const int mvx = (dx << 2) | (f & 3), mvy = (dy << 2) | (f >> 2);
-                    const uint8_t *pl = S.planes + (size_t)f * g.WH;
-                    const int x0 = clampi_(xP + dx, 0, W - 1), y0 = clampi_(yP + dy, 0, H - 1);
-                    int sad = 0;
+            for (int r = 0; r < 8; r++) rows[r] = *(const uint2 *)&sh.cur[(pi >> 1) * 8 + r][(pi & 1) * 8];
+            int s[5];
+            block_sums(rows, s);                                      // suma[0..4] (:440-451)
+            // lane -> (fraction = lane & 15, position parity = lane >> 4); up to 13 independent 16-byte loads in flight
+            const int f1 = lane & 15, npos = w1 * w1;
+            const uint4 *__restrict__ Kf = S.kar + (size_t)f1 * g.WH;
+            for (int p0 = 0; p0 < npos; p0 += 26) {
+                uint4 v[13];
 #pragma unroll
-                    for (int r = 0; r < 8; r++) sad += sad_row8(rows[r], pl, W, H, x0, y0 + r);
-                    const unsigned long long fk = ((unsigned long long)(sad + mv_cost(mvx, mvy, mvpx, mvpy)) << 44) | (unsigned long long)key;
-                    atomicMin(&best, fk);
+                for (int u = 0; u < 13; u++) {
+                    const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), rx = xP + genx + cx - g1, ry = yP + geny + pos - cx * w1 - g1;
+                    v[u] = make_uint4(0, 0, 0, 1u);
+                    if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) v[u] = __ldg(Kf + (size_t)ry * W + rx);
+                }
+#pragma unroll
+                for (int u = 0; u < 13; u++) {
+                    const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), ox = cx - g1, oy = pos - cx * w1 - g1;
+                    if (pos < npos) {
+                        const int i = pos * 16 + f1;
+                        sh.keys1[i] = v[u].w ? COST_INVALID : (((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(s, v[u])) << 11) | (uint32_t)i);
+                    }
                 }
             }
-        }
-        if (!prm.basic) {
+            __syncwarp();
+            const int K1 = warp_select_smallest(n1, FH_S1_MAX, [&](int i) -> u64 { const uint32_t k = sh.keys1[i]; return k == COST_INVALID ? KEY_NONE : (u64)k; },
+                                                &sh.ws[0], sh.mem1);
+            // SADs of the (at most 17) members: 8 lanes per member, one row each; all five rounds of loads in flight
+            const int r = lane & 7;
+            const uint2 cr = pick_row(rows, r);
+            uint2 rr[5];
+            int mvxs[5], mvys[5];
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+                const int m = u * 4 + (lane >> 3);
+                rr[u] = make_uint2(0, 0); mvxs[u] = mvys[u] = 0;
+                if (m < K1) {
+                    const int i = sh.mem1[m], f = i & 15, pos = i >> 4, cx = fdiv_(pos, inv1), dx = genx + cx - g1, dy = geny + pos - cx * w1 - g1;
+                    mvxs[u] = (dx << 2) | (f & 3); mvys[u] = (dy << 2) | (f >> 2);
+                    rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, clampi_(xP + dx, 0, W - 1), clampi_(yP + dy, 0, H - 1) + r);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+                const int m = u * 4 + (lane >> 3);
+                int sad = m < K1 ? sad8(cr, rr[u]) : 0;
+                sad += __shfl_xor_sync(0xffffffffu, sad, 1);
+                sad += __shfl_xor_sync(0xffffffffu, sad, 2);
+                sad += __shfl_xor_sync(0xffffffffu, sad, 4);
+                if (m < K1 && r == 0) mine = min(mine, ((u64)(sad + mv_cost(mvxs[u], mvys[u], mvpx, mvpy)) << 44) | (u64)sh.keys1[sh.mem1[m]]);
+            }
+        } else if (warp == 1) {
             // stage 2 (:470-507): rank the phase-A set with the predictor-dependent multiplier
             const int n2 = (int)pa.n2;
             const uint2 *pool = S.s2pool + pa.s2_off;
-            for (int i = tid; i < n2; i += PB_NT) {
-                const uint2 v = __ldg(&pool[i]);
-                const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16);
-                const uint32_t cost = (uint32_t)(iabs_(dx - genx) + iabs_(dy - geny) + 4) * (v.y & 0x3ffffu);
-                keys2[i] = ((unsigned long long)cost << 10) | (unsigned long long)i;
-            }
-            __syncthreads();
-            unsigned long long T2 = ~0ull;
-            if (n2 > FH_S3_MAX) { int lt; T2 = block_kth_smallest<unsigned long long, PB_NT>(n2, FH_S3_MAX, 38, [&](int i) { return keys2[i]; }, &sc, &lt); }
-            for (int i = tid; i < n2; i += PB_NT) {
-                const unsigned long long key = keys2[i];
-                if (key <= T2 && (key >> 10) < (unsigned long long)FH_COST_EMPTY) {
-                    const uint2 v = __ldg(&pool[i]);
-                    const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16), sad = (int)(v.y >> 18);
-                    const unsigned long long fk = ((unsigned long long)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key;
-                    atomicMin(&best, fk);
+            for (int base = 0; base < n2; base += 32 * 8) {
+                uint2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int i = base + u * 32 + lane; v[u] = i < n2 ? __ldg(&pool[i]) : make_uint2(0, 0); }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = base + u * 32 + lane;
+                    if (i < n2) {
+                        const int dx = (int16_t)(v[u].x & 0xffff), dy = (int16_t)(v[u].x >> 16);
+                        const uint32_t cost = (uint32_t)(iabs_(dx - genx) + iabs_(dy - geny) + 4) * (v[u].y & 0x3ffffu);
+                        sh.keys2[i] = ((u64)cost << 10) | (u64)i;
+                    }
                 }
             }
+            __syncwarp();
+            if (n2 > FH_S3_MAX) {
+                const int K2 = warp_select_smallest(n2, FH_S3_MAX, [&](int i) -> u64 { return sh.keys2[i]; }, &sh.ws[1], sh.mem2);
+                for (int m = lane; m < K2; m += 32) {
+                    const int i = sh.mem2[m];
+                    const u64 key = sh.keys2[i];
+                    if ((key >> 10) < (u64)FH_COST_EMPTY) {
+                        const uint2 v = __ldg(&pool[i]);
+                        const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16), sad = (int)(v.y >> 18);
+                        mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
+                    }
+                }
+            } else {
+                for (int i = lane; i < n2; i += 32) {
+                    const u64 key = sh.keys2[i];
+                    if ((key >> 10) < (u64)FH_COST_EMPTY) {
+                        const uint2 v = __ldg(&pool[i]);
+                        const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16), sad = (int)(v.y >> 18);
+                        mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
+                    }
+                }
+            }
+        } else if (warp == 2) {
             // stage 3 (:508-520): phase-A list, already in list order
-            if (tid < (int)pa.n3) {
-                const S3Entry e = S.s3[(size_t)part * FH_S3_MAX + tid];
-                const unsigned long long fk = ((unsigned long long)((int)e.sad + mv_cost(e.mvx, e.mvy, mvpx, mvpy)) << 44) | (2ull << 42) | (unsigned long long)tid;
-                atomicMin(&best, fk);
+            for (int i = lane; i < (int)pa.n3; i += 32) {
+                const S3Entry e = S.s3[(size_t)part * FH_S3_MAX + i];
+                mine = min(mine, ((u64)((int)e.sad + mv_cost(e.mvx, e.mvy, mvpx, mvpy)) << 44) | (2ull << 42) | (u64)i);
             }
         }
+        mine = warp_min_u64(mine);
+        if (lane == 0) best[warp] = mine;
         __syncthreads();
         // decode the winner from its key (:523-527); no candidate at all leaves bx = by = 0 (:452)
-        const unsigned long long b = best;
+        const u64 b = min(min(best[0], best[1]), min(best[2], best[3]));
         int bx = 0, by = 0, bs = 0;
-        if (b != ~0ull) {
+        if (b != KEY_NONE) {
             const int stage = (int)((b >> 42) & 3), total = (int)(b >> 44);
             if (stage == 0) {
-                const int i = (int)(b & 2047), f = i & 15, pos = i >> 4;
-                bx = ((genx + pos / w1 - g1) << 2) | (f & 3); by = ((geny + pos % w1 - g1) << 2) | (f >> 2);
+                const int i = (int)(b & 2047), f = i & 15, pos = i >> 4, cx = fdiv_(pos, inv1);
+                bx = ((genx + cx - g1) << 2) | (f & 3); by = ((geny + pos - cx * w1 - g1) << 2) | (f >> 2);
             } else if (stage == 1) {
                 const uint2 v = __ldg(&S.s2pool[pa.s2_off + (uint32_t)(b & 1023)]);
                 bx = ((int)(int16_t)(v.x & 0xffff)) << 2; by = ((int)(int16_t)(v.x >> 16)) << 2;
@@ -244,13 +287,11 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
             }
             bs = total - mv_cost(bx, by, mvpx, mvpy);
         } else {
-            // the reference then reports SAD of MV (0,0) nowhere; sad[] is defined as the SAD of the chosen MV
             const uint8_t *pl = S.planes;
-            for (int r = 0; r < 8; r++) bs += sad_row8(rows[r], pl, W, H, xP, yP + r);
+            for (int r = 0; r < 8; r++) bs += sad_row8(*(const uint2 *)&sh.cur[(pi >> 1) * 8 + r][(pi & 1) * 8], pl, W, H, xP, yP + r);
         }
         mv[pi][0] = bx; mv[pi][1] = by; sadq[pi] = bs;
         curq[pi][0] = bx; curq[pi][1] = by;
-        __syncthreads();
     }
 
     // ---- merge (:529-551) and final mvd with the merged type's predictors (:552-564) ---------------------------

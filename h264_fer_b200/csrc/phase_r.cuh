@@ -1,6 +1,6 @@
 // Phase R — per reference picture, fully parallel (reference: FillInterpolatedRefFrame, moestimation.cpp:74-173).
 //   k_interp      16 quarter-pel luma planes             (:79-104 via mocomp.cpp:50-78)
-//   k_features    5 box-sum features x 16 planes, uint16 (:105-139)
+//   k_features    5 box-sum features x 16 planes, packed 16 B per position (:105-139)
 //   k_tile_index  plane-0 positions bucketed per 64x64 tile by (K0>>7, K1>>6); replaces the global counting
 //                 sort sortedSuma0/koliko (:140-172) with an index from which stage 2 enumerates the same set
 //   k_scene_sad   sum |frame - dpb| over luma            (ref_frames.cpp:210-224; h264_kernels.cl:1-5)
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seq
     const int tx = tid & 63, tg = tid >> 6;
     const int x = x0 + tx;
     if (x >= W) return;
-    uint16_t *K = S.kar + (size_t)f * 5 * g.WH;
+    uint4 *K = S.kar + (size_t)f * g.WH;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int r = tg * 4 + q, y = y0 + r;
@@ -102,12 +102,9 @@ __global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seq
         int k2 = 0, k4 = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) { k2 += r4[r + i][tx]; k4 += rc[r + i][tx]; }
-        const size_t o = (size_t)y * W + x;
-        K[o] = (uint16_t)(top + mid2 + low + bot);              // K0: 8x8              (:137)
-        K[(size_t)g.WH + o] = (uint16_t)(top + mid2);           // K1: rows 0-3         (:136)
-        K[2 * (size_t)g.WH + o] = (uint16_t)k2;                 // K2: columns 0-3      (:135)
-        K[3 * (size_t)g.WH + o] = (uint16_t)(top + low);        // K3: rows 0,1,4,5     (:133-134)
-        K[4 * (size_t)g.WH + o] = (uint16_t)k4;                 // K4: columns 0,1,4,5  (:131-132)
+        // K0: 8x8 (:137) | K1: rows 0-3 (:136) ; K2: columns 0-3 (:135) | K3: rows 0,1,4,5 (:133-134) ; K4: columns 0,1,4,5 (:131-132)
+        K[(size_t)y * W + x] = make_uint4((uint32_t)(top + mid2 + low + bot) | ((uint32_t)(top + mid2) << 16),
+                                          (uint32_t)k2 | ((uint32_t)(top + low) << 16), (uint32_t)k4, 0u);
     }
 }
 
@@ -121,14 +118,15 @@ __global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ s
     const int tile = blockIdx.x, tid = threadIdx.x;
     const int tx0 = (tile % g.tilesx) * FH_TILE, ty0 = (tile / g.tilesx) * FH_TILE;
     const int tw = min(FH_TILE, g.W - tx0), th = min(FH_TILE, g.H - ty0);
-    const uint16_t *__restrict__ K = S.kar;   // plane 0: f = 0, k = 0..4
+    const uint4 *__restrict__ K = S.kar;      // plane 0 (f = 0): {K0|K1<<16, K2|K3<<16, K4, 0}
     for (int i = tid; i < FH_CELLS; i += 256) hist[i] = 0;
     __syncthreads();
     bool ub = false;
     for (int i = tid; i < tw * th; i += 256) {
         int ly = i / tw, lx = i - ly * tw;
         size_t o = (size_t)(ty0 + ly) * g.W + tx0 + lx;
-        int k0 = K[o], k1 = K[(size_t)g.WH + o];
+        const uint32_t w0 = K[o].x;
+        int k0 = w0 & 0xffff, k1 = w0 >> 16;
         ub |= (k0 == 0) | (k0 >= 16203);
         atomicAdd(&hist[((k0 >> 7) << 7) | (k1 >> 6)], 1u);
     }
@@ -162,10 +160,11 @@ __global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ s
     for (int i = tid; i < tw * th; i += 256) {
         int ly = i / tw, lx = i - ly * tw;
         size_t o = (size_t)(ty0 + ly) * g.W + tx0 + lx;
+        const uint4 kv = K[o];
         TileEntry e;
         e.x = (uint16_t)(tx0 + lx); e.y = (uint16_t)(ty0 + ly);
-        e.k0 = K[o]; e.k1 = K[(size_t)g.WH + o]; e.k2 = K[2 * (size_t)g.WH + o];
-        e.k3 = K[3 * (size_t)g.WH + o]; e.k4 = K[4 * (size_t)g.WH + o]; e.pad = 0;
+        e.k0 = (uint16_t)(kv.x & 0xffff); e.k1 = (uint16_t)(kv.x >> 16); e.k2 = (uint16_t)(kv.y & 0xffff);
+        e.k3 = (uint16_t)(kv.y >> 16); e.k4 = (uint16_t)kv.z; e.pad = 0;
         uint32_t pos = atomicAdd(&hist[((e.k0 >> 7) << 7) | (e.k1 >> 6)], 1u);
         *(uint4 *)&te[pos] = *(const uint4 *)&e;
     }

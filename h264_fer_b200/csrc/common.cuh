@@ -66,6 +66,7 @@ struct SeqDev {
     uint32_t *done;         // nmb: epoch of the picture whose motion record is final
     fh264_mb_result *results;
     uint32_t *status;       // ST_WORDS
+    long long *dbg;         // optional: nmb * 12 clock samples of phase B (fh264_debug_timeline), else null
 };
 
 __device__ __forceinline__ int iabs_(int a) { return a < 0 ? -a : a; }

@@ -158,6 +158,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         OPEN_CK(dalloc(s, &S.done, (size_t)g.nmb));
         OPEN_CK(dalloc(s, &S.status, (size_t)ST_WORDS));
         S.results = results + (size_t)b * g.nmb;
+        S.dbg = nullptr;
     }
     OPEN_CK(dalloc(s, &s->d_seqs, (size_t)batch));
     OPEN_CK(cudaMemcpy(s->d_seqs, s->h.data(), sizeof(SeqDev) * batch, cudaMemcpyHostToDevice));
@@ -483,5 +484,26 @@ extern "C" int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint
     CKL();
     CK(cudaMemcpyAsync(out, s->d_scr16[0], (size_t)n * 2, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    return FH264_OK;
+}
+
+// Debug: per-macroblock clock64() samples of the phase-B wavefront of sequence seq (12 int64 per MB):
+// [0] CTA start, [1] prefetch issued, [2] dependencies satisfied, [3] neighbour MVs loaded, [4] P_Skip decided,
+// [5..8] partitions 0..3 decided, [9] published. Enable with out == NULL (allocates), read back with out != NULL.
+extern "C" int fh264_debug_timeline(fh264_session *s, int seq, long long *out)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    const size_t n = (size_t)s->g.nmb * 24;
+    if (!s->h[seq].dbg) {
+        long long *p = nullptr;
+        CK(cudaMalloc((void **)&p, n * sizeof(long long)));
+        CK(cudaMemset(p, 0, n * sizeof(long long)));
+        s->allocs.push_back(p);
+        s->h[seq].dbg = p;
+        CK(cudaMemcpy(&s->d_seqs[seq], &s->h[seq], sizeof(SeqDev), cudaMemcpyHostToDevice));
+    }
+    if (out) CK(cudaMemcpy(out, s->h[seq].dbg, n * sizeof(long long), cudaMemcpyDeviceToHost));
     return FH264_OK;
 }

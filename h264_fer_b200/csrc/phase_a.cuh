@@ -165,11 +165,13 @@ __global__ void __launch_bounds__(128, 4) k_stage3(const SeqDev *__restrict__ se
 
 #define S2_WARP_CAP 1024      // gated survivors held per partition; beyond: FH264_E_CAPACITY
 #define S2_BINS 384           // (j, side) bins: 2*j + side, j <= 180
+#define S2_CHUNK_CAP 1024      // a round of 32 short ranges (<= 64 entries each) adds at most 256 chunks
 struct S2Warp {
     uint32_t akey[S2_WARP_CAP];      // arrival key: j<<21 | side<<20 | (dx+279)<<10 | (dy+279)
     uint32_t afeat[S2_WARP_CAP];     // feature distance (18 bits) | SAD << 18
     uint16_t order[S2_WARP_CAP];     // survivor index by output slot
     uint32_t bins[S2_BINS];          // counts, then exclusive starts, then scatter cursors
+    uint32_t chunk[S2_CHUNK_CAP];    // chunks of <= 8 consecutive index entries still to be visited
     int n_surv;
 };
 
@@ -196,42 +198,71 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
     const int qlo = max(0, s[0] - 180) >> 7, qhi = min(16383, s[0] + 180) >> 7, nq = qhi - qlo + 1;
     const int k1lo = max(0, s[1] - 99) >> 6, k1hi = min(8191, s[1] + 99) >> 6;
     const int ntiles = ntx * nty, inv_ntx = 65536 / ntx + 1;
-    for (int tt = lane; tt < ntiles; tt += 32) {
-        const int tyy = fdiv_(tt, inv_ntx), tx = tx0 + tt - tyy * ntx, ty = ty0 + tyy;
-        const int rx0 = tx << FH_TILE_SHIFT, ry0 = ty << FH_TILE_SHIFT;
-        const int ddx = max(0, max(rx0 - xP, xP - (rx0 + FH_TILE - 1))), ddy = max(0, max(ry0 - yP, yP - (ry0 + FH_TILE - 1)));
-        if (ddx + ddy >= 280) continue;
-        const int tile = ty * g.tilesx + tx;
-        const uint16_t *ts = S.tstart + (size_t)tile * FH_TSTART_PITCH;
-        const uint4 *te = (const uint4 *)(S.tent + (size_t)tile * (FH_TILE * FH_TILE));
-        // cell ranges of the (at most 4) K0 rows, fetched together
-        int e0[4], e1[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            e0[q] = e1[q] = 0;
-            if (q < nq) { e0[q] = __ldg(&ts[(qlo + q) * 128 + k1lo]); e1[q] = __ldg(&ts[(qlo + q) * 128 + k1hi + 1]); }
+    const uint4 *__restrict__ tent = (const uint4 *)S.tent;
+    auto visit = [&](const uint4 v) {
+        const int x = v.x & 0xffff, y = v.x >> 16, k0 = v.y & 0xffff, k1 = v.y >> 16, k2 = v.z & 0xffff;
+        const int j = iabs_(k0 - s[0]), dx = x - xP, dy = y - yP;
+        if (j <= 180 && iabs_(dx) + iabs_(dy) < 280 && iabs_(k1 - s[1]) < 100 && iabs_(k2 - s[2]) < 100) {
+            const int side = k0 > s[0];
+            atomicAdd(&w->bins[2 * j + side], 1u);
+            const int pos = atomicAdd(&w->n_surv, 1);
+            if (pos < S2_WARP_CAP) {
+                w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
+                w->afeat[pos] = (uint32_t)feat_dist(s, k0, k1, k2, (int)(v.z >> 16), (int)(v.w & 0xffff));
+            }
         }
+    };
+    int nchunk = 0;
+    const int nitems = ntiles * 4;
+    for (int it0 = 0; it0 < nitems; it0 += 32) {
+        const int it = it0 + lane, tt = it >> 2, q = it & 3;
+        int len = 0; uint32_t gbase = 0;
+        if (tt < ntiles && q < nq) {
+            const int tyy = fdiv_(tt, inv_ntx), tx = tx0 + tt - tyy * ntx, ty = ty0 + tyy;
+            const int rx0 = tx << FH_TILE_SHIFT, ry0 = ty << FH_TILE_SHIFT;
+            const int ddx = max(0, max(rx0 - xP, xP - (rx0 + FH_TILE - 1))), ddy = max(0, max(ry0 - yP, yP - (ry0 + FH_TILE - 1)));
+            if (ddx + ddy < 280) {
+                const int tile = ty * g.tilesx + tx;
+                const uint16_t *ts = S.tstart + (size_t)tile * FH_TSTART_PITCH;
+                const int e0 = __ldg(&ts[(qlo + q) * 128 + k1lo]), e1 = __ldg(&ts[(qlo + q) * 128 + k1hi + 1]);
+                len = e1 - e0; gbase = (uint32_t)tile * (FH_TILE * FH_TILE) + (uint32_t)e0;
+            }
+        }
+        // long ranges (flat content) are walked by the whole warp right away
+        unsigned longm = __ballot_sync(0xffffffffu, len > 64);
+        while (longm) {
+            const int src = __ffs(longm) - 1;
+            longm &= longm - 1;
+            const uint32_t gb = __shfl_sync(0xffffffffu, gbase, src);
+            const int ln = __shfl_sync(0xffffffffu, len, src);
+            for (int e = lane; e < ln; e += 32) visit(__ldg(tent + gb + e));
+            if (lane == src) len = 0;
+        }
+        // short ranges: chunks of <= 8 consecutive entries (one 128-byte line): first entry | (count - 1) << 28
+        const int nc = (len + 7) >> 3;
+        int incl = nc;
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        const int pos = nchunk + incl - nc;
+        for (int c = 0; c < nc; c++) w->chunk[pos + c] = (gbase + 8u * c) | ((uint32_t)(min(8, len - 8 * c) - 1) << 28);
+        nchunk += __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        if (nchunk > S2_CHUNK_CAP - 256 || it0 + 32 >= nitems) {
+            // lanes stride the chunk list: balanced work, sequential 16-byte loads, 4 in flight
+            for (int cidx = lane; cidx < nchunk; cidx += 32) {
+                const uint32_t cw = w->chunk[cidx];
+                const uint4 *ep = tent + (cw & 0x0fffffffu);
+                const int cnt = (int)(cw >> 28) + 1;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            for (int eb = e0[q]; eb < e1[q]; eb += 4) {
-                uint4 v[4];
+                for (int h = 0; h < 2; h++) {
+                    uint4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = eb + u < e1[q] ? __ldg(&te[eb + u]) : make_uint4(0, 0xffffu, 0, 0);
+                    for (int u = 0; u < 4; u++) v[u] = h * 4 + u < cnt ? __ldg(ep + h * 4 + u) : make_uint4(0, 0xffffu, 0, 0);
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int x = v[u].x & 0xffff, y = v[u].x >> 16, k0 = v[u].y & 0xffff, k1 = v[u].y >> 16, k2 = v[u].z & 0xffff;
-                    const int j = iabs_(k0 - s[0]), dx = x - xP, dy = y - yP;
-                    if (eb + u < e1[q] && j <= 180 && iabs_(dx) + iabs_(dy) < 280 && iabs_(k1 - s[1]) < 100 && iabs_(k2 - s[2]) < 100) {
-                        const int side = k0 > s[0];
-                        atomicAdd(&w->bins[2 * j + side], 1u);
-                        const int pos = atomicAdd(&w->n_surv, 1);
-                        if (pos < S2_WARP_CAP) {
-                            w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
-                            w->afeat[pos] = (uint32_t)feat_dist(s, k0, k1, k2, (int)(v[u].z >> 16), (int)(v[u].w & 0xffff));
-                        }
-                    }
+                    for (int u = 0; u < 4; u++) visit(v[u]);
                 }
             }
+            nchunk = 0;
+            __syncwarp();
         }
     }
     __syncwarp();

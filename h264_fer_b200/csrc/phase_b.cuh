@@ -18,6 +18,7 @@
 
 #define PB_NT 128
 #define S1_KEY_CAP 1296     // (2*4+1)^2*16 at WindowSize 64
+#define PB_POOL_PREF 192    // stage-2 candidates per partition staged in shared memory (the rest is read from HBM)
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -66,24 +67,95 @@ __device__ __forceinline__ void predict_mv_(const NbCache &nc, int px, int py, i
 
 __device__ __forceinline__ int mv_cost(int mvx, int mvy, int px, int py) { return iabs_(mvx - px) + iabs_(mvy - py); }
 
+struct BlockSel { u64 skey[256]; uint16_t sidx[256]; int ns[2]; int phase; };
+
 struct PBShared {
-    uint32_t keys1[S1_KEY_CAP];          // warp 0: stage-1 keys  cost << 11 | arrival index
-    u64 keys2[1024];                     // warp 1: stage-2 keys  cost << 10 | arrival rank
-    WarpSelScratch ws[2];
+    uint32_t keys1[S1_KEY_CAP];          // stage-1 keys  cost << 11 | arrival index
+    u64 keys2[1024];                     // stage-2 keys  cost << 10 | arrival rank
+    BlockSel bs;
     uint16_t mem1[FH_S1_MAX + 3], mem2[FH_S3_MAX + 3];
     __align__(16) uint8_t cur[16][16];
     NbCache nc;
     u64 best[2][4];                      // per-warp minima, double-buffered across partitions
+    PartA pa[4];                         // phase-A products of the four partitions, fetched BEFORE the dependency wait
+    S3Entry s3[4][FH_S3_MAX + 1];
+    uint2 pool[4][PB_POOL_PREF];
     uint32_t my_ticket;
     int red[4];
 };
 
-__global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ seqs, int seq0, int nseq, Geo g, fh264_params prm,
+// Block-cooperative version of warp_select_smallest (warp_select.cuh): the K = min(k, #valid) smallest of
+// keyfn(0..n-1) in ascending order into members[]. EVERY warp scans all keys (n/32 per lane), so all warps derive the
+// same tight upper bound on the k-th key without exchanging anything; the survivors are then compacted and ranked by
+// all PB_NT threads. `call` alternates the survivor counter so that no reset barrier is needed. Ends with a barrier.
+template <typename KeyFn>
+__device__ __forceinline__ int block_select_smallest(int n, int k, KeyFn keyfn, BlockSel *bs, uint16_t *members, int call)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    u64 m1 = KEY_NONE, m2 = KEY_NONE;
+    int nv = 0;
+    for (int i = lane; i < n; i += 32) {
+        const u64 key = keyfn(i);
+        if (key != KEY_NONE) {
+            nv++;
+            const u64 lo = key < m1 ? key : m1, hi = key < m1 ? m1 : key;
+            m1 = lo; m2 = hi < m2 ? hi : m2;
+        }
+    }
+    const int K = min(k, __reduce_add_sync(0xffffffffu, nv));
+    if (K == 0) return 0;
+    const int L1 = __popc(__ballot_sync(0xffffffffu, m1 != KEY_NONE));
+    const int L2 = __popc(__ballot_sync(0xffffffffu, m2 != KEY_NONE));
+    u64 thr = KEY_NONE - 1;
+    if (L1 >= K) thr = warp_max_u64(m1 != KEY_NONE ? m1 : 0ull);
+    else if (L1 + 1 >= K && L2 >= 1) { const u64 a = warp_max_u64(m1 != KEY_NONE ? m1 : 0ull), b = warp_min_u64(m2); thr = a > b ? a : b; }
+    else if (2 * L2 >= K) thr = warp_max_u64(m2 != KEY_NONE ? m2 : 0ull);
+    int *nsp = &bs->ns[call & 1];
+    for (int i = tid; i < n; i += PB_NT) {
+        const u64 key = keyfn(i);
+        if (key <= thr) {
+            const int pos = atomicAdd(nsp, 1);
+            if (pos < 256) { bs->skey[pos] = key; bs->sidx[pos] = (uint16_t)i; }
+        }
+    }
+    __syncthreads();
+    const int ns = *nsp;
+    if (tid == 0) bs->ns[(call & 1) ^ 1] = 0;          // the other counter is idle until the next call
+    if (ns <= 64) {
+        // G threads per survivor split the comparisons, partial ranks are added by shuffles
+        const int G = ns <= 32 ? 4 : 2, sidx = tid / G, part = tid - sidx * G;
+        int rank = 0;
+        u64 key = 0;
+        if (sidx < ns) { key = bs->skey[sidx]; for (int j = part; j < ns; j += G) rank += bs->skey[j] < key; }
+        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+        if (G == 4) rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+        if (sidx < ns && part == 0 && rank < K) members[rank] = bs->sidx[sidx];
+    } else if (ns <= 256) {
+        for (int sidx = tid; sidx < ns; sidx += PB_NT) {
+            const u64 key = bs->skey[sidx];
+            int rank = 0;
+            for (int j = 0; j < ns; j++) rank += bs->skey[j] < key;
+            if (rank < K) members[rank] = bs->sidx[sidx];
+        }
+    } else {
+        for (int i = tid; i < n; i += PB_NT) {
+            const u64 key = keyfn(i);
+            if (key > thr) continue;
+            int rank = 0;
+            for (int j = 0; j < n && rank < K; j++) rank += keyfn(j) < key;
+            if (rank < K) members[rank] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+    return K;
+}
+
+__global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__ seqs, int seq0, int nseq, Geo g, fh264_params prm,
                                                    uint32_t epoch, const int *__restrict__ wf_order, uint32_t *__restrict__ ticket)
 {
     __shared__ PBShared sh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) sh.my_ticket = atomicAdd(ticket, 1u);
+    if (tid == 0) { sh.my_ticket = atomicAdd(ticket, 1u); sh.bs.ns[0] = 0; sh.bs.ns[1] = 0; }
     __syncthreads();
     const uint32_t t = sh.my_ticket;
     const SeqDev &S = seqs[seq0 + (int)(t % (uint32_t)nseq)];
@@ -91,7 +163,27 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
     const int mbx = mb % g.Wmb, mby = mb / g.Wmb;
     const int W = g.W, H = g.H;
     NbCache &nc = sh.nc;
+    long long *dbg = S.dbg ? S.dbg + (size_t)mb * 24 : nullptr;
+#define PB_STAMP(k) do { if (dbg && tid == 0) dbg[k] = clock64(); } while (0)
+#define PB_PSTAMP(k) do { if (dbg && tid == 0 && pi == 0) dbg[k] = clock64(); } while (0)
+    PB_STAMP(0);
 
+    // ---- everything that does not depend on the neighbours is fetched BEFORE waiting on them: the CTA is resident
+    //      long before its turn, so these round trips are off the wavefront's critical path
+    if (tid < 16) *(uint4 *)&sh.cur[tid][0] = *(const uint4 *)(S.cur[0] + (size_t)(mby * 16 + tid) * W + mbx * 16);
+    if (!prm.basic) {
+        if (tid >= 32 && tid < 36) sh.pa[tid - 32] = S.parta[mb * 4 + tid - 32];
+        for (int i = tid; i < 4 * FH_S3_MAX; i += PB_NT) { const int pi = i / FH_S3_MAX, k = i - pi * FH_S3_MAX; sh.s3[pi][k] = S.s3[(size_t)(mb * 4 + pi) * FH_S3_MAX + k]; }
+        __syncthreads();
+        for (int pi = 0; pi < 4; pi++) {
+            const int n = min((int)sh.pa[pi].n2, PB_POOL_PREF);
+            const uint2 *pool = S.s2pool + sh.pa[pi].s2_off;
+            for (int i = tid; i < n; i += PB_NT) sh.pool[pi][i] = __ldg(&pool[i]);
+        }
+    } else if (tid < 4) {
+        sh.pa[tid].n2 = 0; sh.pa[tid].n3 = 0; sh.pa[tid].s2_off = 0;
+    }
+    PB_STAMP(1);
     // ---- wait for the dependencies (left; up-right, or up in the last column) -------------------------------
     if (tid == 0) {
         if (mbx > 0) while (ld_acquire_u32(&S.done[mb - 1]) != epoch) __nanosleep(20);
@@ -101,6 +193,7 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
         }
     }
     __syncthreads();
+    PB_STAMP(2);
     if (tid < 16) {
         const int w = tid >> 2, q = tid & 3;
         const int nmb = w == 0 ? mb - 1 : (w == 1 ? mb - g.Wmb : (w == 2 ? mb - g.Wmb + 1 : mb - g.Wmb - 1));
@@ -109,12 +202,10 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
         if (av) { const int v = __ldcg((const int *)&S.motion[nmb].mv[q][0]); vx = (int16_t)(v & 0xffff); vy = v >> 16; }
         nc.mvx[w][q] = vx; nc.mvy[w][q] = vy;
         if (q == 0) nc.avail[w] = av;
-    } else if (tid >= 32 && tid < 48) {
-        const int r = tid - 32;
-        *(uint4 *)&sh.cur[r][0] = *(const uint4 *)(S.cur[0] + (size_t)(mby * 16 + r) * W + mbx * 16);
     }
     __syncthreads();
 
+    PB_STAMP(3);
     // ---- P_Skip trial ---------------------------------------------------------------------------------------
     int zero4[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
     int smx = 0, smy = 0;
@@ -139,6 +230,7 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
     const int nbad = __syncthreads_count(iabs_(c0 - p2[0]) > maxdiff || iabs_(c1 - p2[1]) > maxdiff);
     MbMotion mo;
     mo.maxdiff = (int16_t)maxdiff; mo.pad = 0;
+    PB_STAMP(4);
     if (nbad == 0) {
         if (tid == 0) {
             mo.mb_type = FH264_P_SKIP; mo.num_parts = 0;
@@ -146,130 +238,121 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
             uint4 *d = (uint4 *)&S.motion[mb];
             const uint4 *s4 = (const uint4 *)&mo;
             d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
-            atomicAdd(&S.status[ST_COUNTS + 0], 1u);
-            __threadfence();
             st_release_u32(&S.done[mb], epoch);
+            atomicAdd(&S.status[ST_COUNTS + 0], 1u);
         }
         return;
     }
 
-    // ---- 8x8 search, partitions in order ----------------------------------------------------------------------
-    int mv[4][2], sadq[4], curq[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
-    const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16, inv1 = 65536 / w1 + 1;
+    // ---- 8x8 search, partitions in order; inside a partition the three stages are evaluated cooperatively by the whole
+    //      block (the wavefront is latency bound: per-warp instruction count is what sits on the critical path) ----------
+    int mv[4][2], sadq[4], mvps[4][2], curq[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+    const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16, inv1 = 65536 / w1 + 1, npos = w1 * w1;
+    const int f1 = tid & 15;
+    int callno = 0;                  // alternates BlockSel's survivor counters (uniform across the block)
+    const uint4 *__restrict__ Kf = S.kar + (size_t)f1 * g.WH;
     for (int pi = 0; pi < 4; pi++) {
-        const int part = mb * 4 + pi;
         const int xP = mbx * 16 + (pi & 1) * 8, yP = mby * 16 + (pi >> 1) * 8;
         int mvpx, mvpy;
         predict_mv_(nc, (pi & 1) * 8, (pi >> 1) * 8, 8, 0, curq, mvpx, mvpy);
+        mvps[pi][0] = mvpx; mvps[pi][1] = mvpy;
         const int genx = mvpx >> 2, geny = mvpy >> 2;
-        PartA pa = S.parta[part];
-        if (prm.basic) { pa.n2 = 0; pa.n3 = 0; pa.s2_off = 0; }
+        const PartA pa = sh.pa[pi];
         u64 *best = sh.best[pi & 1];
         u64 mine = KEY_NONE;
-        if (warp == 0) {
-            // stage 1 (:458-469): window/16 quarter-pel window around the predictor; key = cost << 11 | arrival index
-            uint2 rows[8];
+        // stage 1 (:458-469), part 1: issue the feature loads of the window/16 quarter-pel window around the predictor.
+        // thread -> (fraction = tid & 15, position = (tid >> 4) + 8u); they complete while stage 2 is ranked.
+        uint4 v1[4];
 #pragma unroll
-            for (int r = 0; r < 8; r++) rows[r] = *(const uint2 *)&sh.cur[(pi >> 1) * 8 + r][(pi & 1) * 8];
-            int s[5];
-            block_sums(rows, s);                                      // suma[0..4] (:440-451)
-            // lane -> (fraction = lane & 15, position parity = lane >> 4); up to 13 independent 16-byte loads in flight
-            const int f1 = lane & 15, npos = w1 * w1;
-            const uint4 *__restrict__ Kf = S.kar + (size_t)f1 * g.WH;
-            for (int p0 = 0; p0 < npos; p0 += 26) {
-                uint4 v[13];
-#pragma unroll
-                for (int u = 0; u < 13; u++) {
-                    const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), rx = xP + genx + cx - g1, ry = yP + geny + pos - cx * w1 - g1;
-                    v[u] = make_uint4(0, 0, 0, 1u);
-                    if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) v[u] = __ldg(Kf + (size_t)ry * W + rx);
-                }
-#pragma unroll
-                for (int u = 0; u < 13; u++) {
-                    const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), ox = cx - g1, oy = pos - cx * w1 - g1;
-                    if (pos < npos) {
-                        const int i = pos * 16 + f1;
-                        sh.keys1[i] = v[u].w ? COST_INVALID : (((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(s, v[u])) << 11) | (uint32_t)i);
-                    }
-                }
-            }
-            __syncwarp();
-            const int K1 = warp_select_smallest(n1, FH_S1_MAX, [&](int i) -> u64 { const uint32_t k = sh.keys1[i]; return k == COST_INVALID ? KEY_NONE : (u64)k; },
-                                                &sh.ws[0], sh.mem1);
-            // SADs of the (at most 17) members: 8 lanes per member, one row each; all five rounds of loads in flight
-            const int r = lane & 7;
-            const uint2 cr = pick_row(rows, r);
-            uint2 rr[5];
-            int mvxs[5], mvys[5];
-#pragma unroll
-            for (int u = 0; u < 5; u++) {
-                const int m = u * 4 + (lane >> 3);
-                rr[u] = make_uint2(0, 0); mvxs[u] = mvys[u] = 0;
-                if (m < K1) {
-                    const int i = sh.mem1[m], f = i & 15, pos = i >> 4, cx = fdiv_(pos, inv1), dx = genx + cx - g1, dy = geny + pos - cx * w1 - g1;
-                    mvxs[u] = (dx << 2) | (f & 3); mvys[u] = (dy << 2) | (f >> 2);
-                    rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, clampi_(xP + dx, 0, W - 1), clampi_(yP + dy, 0, H - 1) + r);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 5; u++) {
-                const int m = u * 4 + (lane >> 3);
-                int sad = m < K1 ? sad8(cr, rr[u]) : 0;
-                sad += __shfl_xor_sync(0xffffffffu, sad, 1);
-                sad += __shfl_xor_sync(0xffffffffu, sad, 2);
-                sad += __shfl_xor_sync(0xffffffffu, sad, 4);
-                if (m < K1 && r == 0) mine = min(mine, ((u64)(sad + mv_cost(mvxs[u], mvys[u], mvpx, mvpy)) << 44) | (u64)sh.keys1[sh.mem1[m]]);
-            }
-        } else if (warp == 1) {
-            // stage 2 (:470-507): rank the phase-A set with the predictor-dependent multiplier
-            const int n2 = (int)pa.n2;
-            const uint2 *pool = S.s2pool + pa.s2_off;
-            for (int base = 0; base < n2; base += 32 * 8) {
-                uint2 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) { const int i = base + u * 32 + lane; v[u] = i < n2 ? __ldg(&pool[i]) : make_uint2(0, 0); }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = base + u * 32 + lane;
-                    if (i < n2) {
-                        const int dx = (int16_t)(v[u].x & 0xffff), dy = (int16_t)(v[u].x >> 16);
-                        const uint32_t cost = (uint32_t)(iabs_(dx - genx) + iabs_(dy - geny) + 4) * (v[u].y & 0x3ffffu);
-                        sh.keys2[i] = ((u64)cost << 10) | (u64)i;
-                    }
-                }
-            }
-            __syncwarp();
-            if (n2 > FH_S3_MAX) {
-                const int K2 = warp_select_smallest(n2, FH_S3_MAX, [&](int i) -> u64 { return sh.keys2[i]; }, &sh.ws[1], sh.mem2);
-                for (int m = lane; m < K2; m += 32) {
-                    const int i = sh.mem2[m];
-                    const u64 key = sh.keys2[i];
-                    if ((key >> 10) < (u64)FH_COST_EMPTY) {
-                        const uint2 v = __ldg(&pool[i]);
-                        const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16), sad = (int)(v.y >> 18);
-                        mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
-                    }
-                }
-            } else {
-                for (int i = lane; i < n2; i += 32) {
-                    const u64 key = sh.keys2[i];
-                    if ((key >> 10) < (u64)FH_COST_EMPTY) {
-                        const uint2 v = __ldg(&pool[i]);
-                        const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16), sad = (int)(v.y >> 18);
-                        mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
-                    }
-                }
-            }
-        } else if (warp == 2) {
-            // stage 3 (:508-520): phase-A list, already in list order
-            for (int i = lane; i < (int)pa.n3; i += 32) {
-                const S3Entry e = S.s3[(size_t)part * FH_S3_MAX + i];
-                mine = min(mine, ((u64)((int)e.sad + mv_cost(e.mvx, e.mvy, mvpx, mvpy)) << 44) | (2ull << 42) | (u64)i);
+        for (int u = 0; u < 4; u++) {
+            const int pos = (tid >> 4) + 8 * u, cx = fdiv_(pos, inv1), rx = xP + genx + cx - g1, ry = yP + geny + pos - cx * w1 - g1;
+            v1[u] = make_uint4(0, 0, 0, 1u);
+            if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) v1[u] = __ldg(Kf + (size_t)ry * W + rx);
+        }
+        PB_PSTAMP(10);
+        // stage 2 (:470-507): rank the phase-A set with the predictor-dependent multiplier, SADs looked up
+        const int n2 = (int)pa.n2;
+        const uint2 *pool = S.s2pool + pa.s2_off;
+        for (int i = tid; i < n2; i += PB_NT) {
+            const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
+            const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16);
+            const uint32_t cost = (uint32_t)(iabs_(dx - genx) + iabs_(dy - geny) + 4) * (v.y & 0x3ffffu);
+            sh.keys2[i] = ((u64)cost << 10) | (u64)i;
+        }
+        __syncthreads();
+        PB_PSTAMP(11);
+        int K2 = n2;
+        if (n2 > FH_S3_MAX) K2 = block_select_smallest(n2, FH_S3_MAX, [&](int i) -> u64 { return sh.keys2[i]; }, &sh.bs, sh.mem2, callno++);
+        PB_PSTAMP(12);
+        if (tid < K2) {
+            const int i = n2 > FH_S3_MAX ? (int)sh.mem2[tid] : tid;
+            const u64 key = sh.keys2[i];
+            if ((key >> 10) < (u64)FH_COST_EMPTY) {
+                const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
+                const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16), sad = (int)(v.y >> 18);
+                mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
             }
         }
+        // stage 3 (:508-520): phase-A list, already in list order
+        if (tid >= 64 && tid - 64 < (int)pa.n3) {
+            const int i = tid - 64;
+            const S3Entry e = sh.s3[pi][i];
+            mine = min(mine, ((u64)((int)e.sad + mv_cost(e.mvx, e.mvy, mvpx, mvpy)) << 44) | (2ull << 42) | (u64)i);
+        }
+        PB_PSTAMP(13);
+        // stage 1, part 2: keys = cost << 11 | arrival index ((dx, dy, frac) order)
+        {
+            const uint2 *rp = (const uint2 *)&sh.cur[(pi >> 1) * 8][(pi & 1) * 8];
+            uint2 rows[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) rows[r] = rp[r * 2];           // 16-byte row pitch
+            int s[5];
+            block_sums(rows, s);                                       // suma[0..4] (:440-451)
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int pos = (tid >> 4) + 8 * u, cx = fdiv_(pos, inv1), ox = cx - g1, oy = pos - cx * w1 - g1;
+                if (pos < npos) {
+                    const int i = pos * 16 + f1;
+                    sh.keys1[i] = v1[u].w ? COST_INVALID : (((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(s, v1[u])) << 11) | (uint32_t)i);
+                }
+            }
+            // windows beyond 32 positions (WindowSize 64): remaining positions, plain loop
+            for (int pos = 32 + (tid >> 4); pos < npos; pos += 8) {
+                const int cx = fdiv_(pos, inv1), ox = cx - g1, oy = pos - cx * w1 - g1, rx = xP + genx + ox, ry = yP + geny + oy, i = pos * 16 + f1;
+                uint32_t key = COST_INVALID;
+                if (rx >= 0 && rx < W && ry >= 0 && ry < H) key = ((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(s, __ldg(Kf + (size_t)ry * W + rx))) << 11) | (uint32_t)i;
+                sh.keys1[i] = key;
+            }
+            __syncthreads();
+            PB_PSTAMP(14);
+            const int K1 = block_select_smallest(n1, FH_S1_MAX, [&](int i) -> u64 { const uint32_t k = sh.keys1[i]; return k == COST_INVALID ? KEY_NONE : (u64)k; },
+                                                 &sh.bs, sh.mem1, callno++);
+            PB_PSTAMP(15);
+            // SADs of the (at most 17) members: 8 threads per member, one row each
+            const int r = tid & 7;
+            const uint2 cr = pick_row(rows, r);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int m = u * 16 + (tid >> 3);
+                int sad = 0, mvx = 0, mvy = 0;
+                if (m < K1) {
+                    const int i = sh.mem1[m], f = i & 15, pos = i >> 4, cx = fdiv_(pos, inv1), dx = genx + cx - g1, dy = geny + pos - cx * w1 - g1;
+                    mvx = (dx << 2) | (f & 3); mvy = (dy << 2) | (f >> 2);
+                    sad = sad8(cr, load_row8(S.planes + (size_t)f * g.WH, W, H, clampi_(xP + dx, 0, W - 1), clampi_(yP + dy, 0, H - 1) + r));
+                }
+                if (u == 0 || tid < 8) {                               // round 1 only concerns member 16 (threads 0-7)
+                    sad += __shfl_xor_sync(u == 0 ? 0xffffffffu : 0xffu, sad, 1);
+                    sad += __shfl_xor_sync(u == 0 ? 0xffffffffu : 0xffu, sad, 2);
+                    sad += __shfl_xor_sync(u == 0 ? 0xffffffffu : 0xffu, sad, 4);
+                }
+                if (m < K1 && r == 0) mine = min(mine, ((u64)(sad + mv_cost(mvx, mvy, mvpx, mvpy)) << 44) | (u64)sh.keys1[sh.mem1[m]]);
+            }
+        }
+        PB_PSTAMP(16);
         mine = warp_min_u64(mine);
         if (lane == 0) best[warp] = mine;
         __syncthreads();
+        PB_PSTAMP(17);
         // decode the winner from its key (:523-527); no candidate at all leaves bx = by = 0 (:452)
         const u64 b = min(min(best[0], best[1]), min(best[2], best[3]));
         int bx = 0, by = 0, bs = 0;
@@ -279,10 +362,11 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
                 const int i = (int)(b & 2047), f = i & 15, pos = i >> 4, cx = fdiv_(pos, inv1);
                 bx = ((genx + cx - g1) << 2) | (f & 3); by = ((geny + pos - cx * w1 - g1) << 2) | (f >> 2);
             } else if (stage == 1) {
-                const uint2 v = __ldg(&S.s2pool[pa.s2_off + (uint32_t)(b & 1023)]);
+                const int wi = (int)(b & 1023);
+                const uint2 v = wi < PB_POOL_PREF ? sh.pool[pi][wi] : __ldg(&S.s2pool[pa.s2_off + (uint32_t)wi]);
                 bx = ((int)(int16_t)(v.x & 0xffff)) << 2; by = ((int)(int16_t)(v.x >> 16)) << 2;
             } else {
-                const S3Entry e = S.s3[(size_t)part * FH_S3_MAX + (int)(b & 63)];
+                const S3Entry e = sh.s3[pi][(int)(b & 63)];
                 bx = e.mvx; by = e.mvy;
             }
             bs = total - mv_cost(bx, by, mvpx, mvpy);
@@ -291,6 +375,7 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
             for (int r = 0; r < 8; r++) bs += sad_row8(*(const uint2 *)&sh.cur[(pi >> 1) * 8 + r][(pi & 1) * 8], pl, W, H, xP, yP + r);
         }
         mv[pi][0] = bx; mv[pi][1] = by; sadq[pi] = bs;
+        PB_STAMP(5 + pi);
         curq[pi][0] = bx; curq[pi][1] = by;
     }
 
@@ -309,7 +394,8 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
             if (type == FH264_P_L0_L0_16x8) { ppy = i * 8; dir = i == 0 ? 1 : 2; qsel = i * 2; }
             else if (type == FH264_P_L0_L0_8x16) { ppx = i * 8; pw = 8; dir = i == 0 ? 2 : 3; }
             else if (type == FH264_P_8x8ref0) { ppx = (i & 1) * 8; ppy = (i >> 1) * 8; pw = 8; }
-            predict_mv_(nc, ppx, ppy, pw, dir, fin, ox, oy);
+            if (type == FH264_P_8x8ref0) { ox = mvps[i][0]; oy = mvps[i][1]; }        // same neighbours as during the search
+            else predict_mv_(nc, ppx, ppy, pw, dir, fin, ox, oy);
             mo.mvd[i][0] = (int16_t)(mv[qsel][0] - ox); mo.mvd[i][1] = (int16_t)(mv[qsel][1] - oy);
             for (int q = 0; q < 4; q++) {
                 const bool in = type == FH264_P_L0_16x16 || (type == FH264_P_L0_L0_16x8 && (q >> 1) == i) ||
@@ -322,8 +408,8 @@ __global__ void __launch_bounds__(PB_NT) k_phase_b(const SeqDev *__restrict__ se
         uint4 *d = (uint4 *)&S.motion[mb];
         const uint4 *s4 = (const uint4 *)&mo;
         d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
+        st_release_u32(&S.done[mb], epoch);          // release orders this thread's motion-record stores before the flag
+        PB_STAMP(9);
         atomicAdd(&S.status[ST_COUNTS + cnt], 1u);
-        __threadfence();
-        st_release_u32(&S.done[mb], epoch);
     }
 }

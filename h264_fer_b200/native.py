@@ -22,7 +22,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
-           "fh264_debug_feature", "fh264_last_timings"]
+           "fh264_debug_feature", "fh264_last_timings", "fh264_debug_timeline"]
 
 
 class Fh264Error(RuntimeError):
@@ -76,6 +76,7 @@ def load_library():
     L.fh264_debug_plane.argtypes = [vp, i32, i32, u8p]
     L.fh264_debug_feature.argtypes = [vp, i32, i32, i32, vp]
     L.fh264_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
+    L.fh264_debug_timeline.argtypes = [vp, i32, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
@@ -238,6 +239,14 @@ class Session:
         qmv = np.ascontiguousarray(qmv, dtype=np.int16).reshape(self.nmb, 4, 2)
         out = np.zeros((self.nmb, 384), np.uint8)
         self._ck(self.L.fh264_motion_compensate(self.handle, seq, _ptr(qmv), _ptr(out)))
+        return out
+
+    def debug_timeline(self, seq, read=True):
+        if not read:
+            self._ck(self.L.fh264_debug_timeline(self.handle, seq, None))
+            return None
+        out = np.zeros((self.nmb, 24), np.int64)
+        self._ck(self.L.fh264_debug_timeline(self.handle, seq, _ptr(out)))
         return out
 
     def debug_plane(self, seq, f):

@@ -154,6 +154,11 @@ int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out);
  * [5] k_stage3, [6] k_stage2, [7] k_interp, [8] k_features, [9] k_tile_index. */
 int fh264_last_timings(fh264_session *s, float ms[10]);
 
+/* Debug: clock64() samples of the phase-B wavefront, 12 int64 per macroblock of sequence seq ([0] CTA start,
+ * [1] prefetch issued, [2] dependencies satisfied, [3] neighbour MVs loaded, [4] P_Skip decided, [5..8] partitions
+ * decided, [9] published). Call with out == NULL to enable sampling, with a buffer to read the last picture back. */
+int fh264_debug_timeline(fh264_session *s, int seq, long long *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -191,7 +191,7 @@ def reference_arm(args):
 def workload_config(args, nseq_total):
     return {"workload": "BASELINE.json config 5 sharding: %d independent synthetic 1080p sequences per GPU (%d total), coded 1920x1072, "
                         "IPPP, 1 step = 1 P picture of every sequence" % (args.seqs, nseq_total),
-            "qp": QP, "window": WINDOW, "maxdiff_set": MAXDIFF, "basic": 0, "seqs_per_gpu": args.seqs, "clip": "%d-picture ping-pong" % CLIP_LEN,
+            "qp": QP, "window": WINDOW, "maxdiff_set": MAXDIFF, "basic": 0, "seqs_per_gpu": args.seqs, "groups_per_gpu": getattr(args, "groups", 1), "clip": "%d-picture ping-pong" % CLIP_LEN,
             "first_picture": "source picture 0 uploaded as the reconstruction (I pictures are host work, out of scope)",
             "l2": "per-step working set (>330 MB of reference planes/features per sequence) exceeds the 126 MB L2; no explicit flush"}
 
@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seqs", type=int, default=8, help="independent sequences per GPU")
+    ap.add_argument("--groups", type=int, default=4, help="sequence groups per GPU (session + stream + host thread each)")
+    ap.add_argument("--threaded", action="store_true", help="drive even a single group from a worker thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -223,61 +225,109 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, K, Wu = args.seqs, args.steps, max(args.warmup, 3)
+    G = max(1, min(args.groups, B))                      # sequence groups: one session + stream + host thread each
     clips = make_clips(B, 100 + rank * B)
     H = clips[0][0][0].shape[0]
     nmb = (WIDTH // 16) * (H // 16)
     ysz, csz = WIDTH * H, WIDTH * H // 4
+    master = torch.cuda.current_stream()
 
-    # host (pinned) and device-resident copies of every source picture
-    pinned = [[PinnedArray((ysz + 2 * csz,), np.uint8) for _ in range(CLIP_LEN)] for _ in range(B)]
-    for b in range(B):
-        for t in range(CLIP_LEN):
-            a = pinned[b][t].array
-            a[:ysz] = clips[b][t][0].ravel(); a[ysz:ysz + csz] = clips[b][t][1].ravel(); a[ysz + csz:] = clips[b][t][2].ravel()
-    dev = [[torch.from_numpy(pinned[b][t].array.copy()).cuda() for t in range(CLIP_LEN)] for b in range(B)]
-    results = PinnedArray((B, nmb), fh.MB_RESULT_DTYPE)
+    class Group:
+        """A slice of the GPU's sequences driven like one reference process: its own session, CUDA stream and host thread
+        (the reference is one sequence per process; here a group advances its sequences in lockstep)."""
 
-    s = fh.Session(WIDTH, H, batch=B, device=local)
-    stream = torch.cuda.current_stream()
-    s.set_stream(stream.cuda_stream)
-    idr_decisions = 0
+        def __init__(self, seq_ids):
+            self.ids = seq_ids
+            self.n = len(seq_ids)
+            self.pinned = [[PinnedArray((ysz + 2 * csz,), np.uint8) for _ in range(CLIP_LEN)] for _ in seq_ids]
+            for j, b in enumerate(seq_ids):
+                for t in range(CLIP_LEN):
+                    a = self.pinned[j][t].array
+                    a[:ysz] = clips[b][t][0].ravel(); a[ysz:ysz + csz] = clips[b][t][1].ravel(); a[ysz + csz:] = clips[b][t][2].ravel()
+            self.dev = [[torch.from_numpy(self.pinned[j][t].array.copy()).cuda() for t in range(CLIP_LEN)] for j in range(self.n)]
+            self.results = PinnedArray((self.n, nmb), fh.MB_RESULT_DTYPE)
+            self.s = fh.Session(WIDTH, H, batch=self.n, device=local)
+            self.stream = torch.cuda.Stream()
+            self.s.set_stream(self.stream.cuda_stream)
+            self.idr = 0
+            self.t = 1
 
-    def reset():
-        for b in range(B):
-            s.upload_recon(b, *clips[b][0])
-        s.sync()
+        def reset(self):
+            for j, b in enumerate(self.ids):
+                self.s.upload_recon(j, *clips[b][0])
+            self.s.sync()
+            self.t = 1
 
-    def step(t, host):
-        nonlocal idr_decisions
-        k = pingpong(t, CLIP_LEN)
-        for b in range(B):
-            if host:
-                p = pinned[b][k].ptr
-                s.upload_source_ptrs(b, p, p + ysz, p + ysz + csz, device=False)
-            else:
-                p = dev[b][k].data_ptr()
-                s.upload_source_ptrs(b, p, p + ysz, p + ysz + csz, device=True)
-        sads = s.scene_sad_batch()                                   # selectNALUnitType's measure (ref_frames.cpp:210-224)
-        idr_decisions += sum(1 for v in sads if v > (nmb << 12))
-        s.encode_p(QP, WINDOW, MAXDIFF, 0, out=results.array, sync=False, download=host)
+        def step(self, host):
+            k = pingpong(self.t, CLIP_LEN)
+            self.t += 1
+            for j in range(self.n):
+                p = self.pinned[j][k].ptr if host else self.dev[j][k].data_ptr()
+                self.s.upload_source_ptrs(j, p, p + ysz, p + ysz + csz, device=not host)
+            sads = self.s.scene_sad_batch()                      # selectNALUnitType's measure (ref_frames.cpp:210-224)
+            self.idr += sum(1 for v in sads if v > (nmb << 12))
+            self.s.encode_p(QP, WINDOW, MAXDIFF, 0, out=self.results.array, sync=False, download=host)
+
+    groups = [Group(list(range(B))[i::G]) for i in range(G)]
 
     def timed(host):
-        reset()
-        t = 1
-        for _ in range(Wu):
-            step(t, host); t += 1
-        s.sync()
+        for gr in groups:
+            gr.reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event() for _ in groups]
+        bar_warm, bar_go = threading.Barrier(G + 1), threading.Barrier(G + 1)
+        errors = []
+
+        def worker(gr, ev):
+            try:
+                torch.cuda.set_device(local)
+                for _ in range(Wu):
+                    gr.step(host)
+                gr.s.sync()
+                bar_warm.wait()
+                bar_go.wait()
+                gr.stream.wait_event(e0)                         # the timed region starts at e0 on every group stream
+                for _ in range(K):
+                    gr.step(host)
+                ev.record(gr.stream)
+            except Exception as ex:       # surfaced by the main thread
+                errors.append(ex)
+                try:
+                    bar_warm.abort(); bar_go.abort()
+                except Exception:
+                    pass
+
+        inline = G == 1 and not args.threaded            # one group: drive it from the main thread
+        threads = [] if inline else [threading.Thread(target=worker, args=(gr, ev)) for gr, ev in zip(groups, ends)]
+        for th in threads:
+            th.start()
+        if inline:
+            for _ in range(Wu):
+                groups[0].step(host)
+            groups[0].s.sync()
+        else:
+            bar_warm.wait()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(K):
-            step(t, host); t += 1
-        e1.record(stream)
+        e0.record(master)
+        if inline:
+            groups[0].stream.wait_event(e0)
+            for _ in range(K):
+                groups[0].step(host)
+            ends[0].record(groups[0].stream)
+        else:
+            bar_go.wait()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        for ev in ends:
+            master.wait_event(ev)
+        e1.record(master)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -287,25 +337,29 @@ def main():
             tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
-        for b in range(B):
-            s.picture_status(b)
+        for gr in groups:
+            for j in range(gr.n):
+                gr.s.picture_status(j)
         return ms, clocks
 
     ms_dev, clocks = timed(host=False)
     ms_e2e, clocks_e2e = timed(host=True)
+    idr_decisions = sum(gr.idr for gr in groups)
 
-    # per-kernel device times (CUDA events inside the library, on the launching stream), a few instrumented steps
-    reset()
-    acc, nsamp, t = {}, 0, 1
+    # per-kernel device times (CUDA events inside the library, on the launching stream): group 0 alone, a few steps
+    g0 = groups[0]
+    g0.reset()
+    acc, nsamp = {}, 0
     for i in range(3 + 4):
-        step(t, False); t += 1
-        tm = s.last_timings()
+        g0.step(False)
+        tm = g0.s.last_timings()
         if i >= 3:
             for k_, v in tm.items():
                 acc[k_] = acc.get(k_, 0.0) + v
             nsamp += 1
     tm = {k_: v / nsamp for k_, v in acc.items()}
-    counts = [s.mode_counts(b) for b in range(B)]
+    counts = [g0.s.mode_counts(0)]
+    Bk = g0.n                                             # pictures per kernel launch in the instrumented run
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()
@@ -315,12 +369,12 @@ def main():
         kernels = {"k_stage3": tm["k_stage3_ms"], "k_stage2": tm["k_stage2_ms"], "k_phase_b": tm["phase_b_ms"], "k_phase_c": tm["phase_c_ms"],
                    "k_interp": tm["k_interp_ms"], "k_features": tm["k_features_ms"], "k_tile_index": tm["k_tile_index_ms"]}
         dom = max(kernels, key=kernels.get)
-        alg_bytes = ALG_BYTES_PER_MB * nmb * B            # one launch processes B pictures
+        alg_bytes = ALG_BYTES_PER_MB * nmb * Bk           # one launch processes the group's pictures
         achieved = alg_bytes / (kernels[dom] / 1000.0) / 1e9
         # phase C alone is the HBM-bound kernel of the path: report it too
         c_achieved = alg_bytes / (tm["phase_c_ms"] / 1000.0) / 1e9
-        int_ops = ALG_INTOPS_PER_MB * nmb * B
-        step_ms = tm["total_ms"]
+        int_ops = ALG_INTOPS_PER_MB * nmb * B * world * K          # whole timed job
+        step_ms = ms_dev
         line = {
             "metric": "1080p P-picture frames/s, ME + transform/quant/reconstruction hot path", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": Wu, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
@@ -328,24 +382,25 @@ def main():
             "macroblocks_per_s": value * nmb,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * (ysz + 2 * csz), "d2h_bytes_per_step": B * nmb * 832 + B * 8,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": 13 * K,
+            "gpu_launches": 13 * K * G,
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": peak_src,
-                         "note": "algorithmic bytes = 1984 B/MB x %d MB x %d pictures per launch / live CUDA-event duration of the dominant kernel; "
-                                 "the ME kernels are integer-pipe bound, see int_roofline" % (nmb, B)},
+                         "note": "algorithmic bytes = 1984 B/MB x %d MB x %d pictures per launch / live CUDA-event duration of the dominant kernel "
+                                 "(one sequence group running alone); the ME kernels are integer-pipe bound, see int_roofline" % (nmb, Bk)},
             "roofline_phase_c": {"bound": "hbm", "kernel": "k_phase_c", "achieved": c_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": c_achieved / hbm_peak},
-            "int_roofline": {"ops_per_mb": ALG_INTOPS_PER_MB, "achieved_tops": int_ops / (step_ms / 1000.0) / 1e12,
+            "int_roofline": {"ops_per_mb": ALG_INTOPS_PER_MB, "achieved_tops": int_ops / (step_ms / 1000.0) / 1e12 / world,
                              "peak_tops_nominal": 148 * 128 * sm_max * 1e6 / 1e12,
-                             "frac": (int_ops / (step_ms / 1000.0) / 1e12) / (148 * 128 * sm_max * 1e6 / 1e12),
-                             "note": "SURVEY.md §8d: 0.43 M int32-lane ops per MB over the whole step; peak = 148 SMs x 128 lanes x max SM clock"},
+                             "frac": (int_ops / (step_ms / 1000.0) / 1e12 / world) / (148 * 128 * sm_max * 1e6 / 1e12),
+                             "note": "SURVEY.md §8d: 0.43 M int32-lane ops per MB over the whole timed job, per GPU; peak = 148 SMs x 128 lanes x max SM clock"},
             "kernel_ms_per_step": kernels, "phase_ms_per_step": {k_: tm[k_] for k_ in ("phase_a_ms", "phase_b_ms", "phase_c_ms", "copy_phase_r_ms", "total_ms")},
             "idr_decisions": idr_decisions, "mode_counts_last_picture_seq0": counts[0],
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
-    s.close()
+    for gr in groups:
+        gr.s.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -311,7 +311,9 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         k_stage2<<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
     CK(cudaEventRecord(s->ev[1], st));
-    k_phase_b<<<(unsigned)(g.nmb * nseq), PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
+    // persistent wavefront CTAs: about one anti-diagonal (Wmb/2) plus slack per sequence
+    const unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.nmb * nseq, (long long)nseq * (g.Wmb / 2 + 8));
+    k_phase_b<<<pb_ctas, PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
     CK(cudaEventRecord(s->ev[2], st));
     dim3 gc((g.nmb + 3) / 4, nseq);
     k_phase_c<<<gc, 128, 0, st>>>(s->d_seqs, seq0, g, prm);

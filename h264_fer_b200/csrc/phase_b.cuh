@@ -155,9 +155,15 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
 {
     __shared__ PBShared sh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Persistent CTAs: the grid holds about one wavefront's worth of CTAs per sequence (more would only spin and keep
+    // other streams' kernels off the SMs); each CTA keeps drawing tickets until the picture is done.
+    const uint32_t total = (uint32_t)g.nmb * (uint32_t)nseq;
+  for (;;) {
+    __syncthreads();                                       // previous macroblock's shared state is no longer read
     if (tid == 0) { sh.my_ticket = atomicAdd(ticket, 1u); sh.bs.ns[0] = 0; sh.bs.ns[1] = 0; }
     __syncthreads();
     const uint32_t t = sh.my_ticket;
+    if (t >= total) return;
     const SeqDev &S = seqs[seq0 + (int)(t % (uint32_t)nseq)];
     const int mb = wf_order[t / (uint32_t)nseq];
     const int mbx = mb % g.Wmb, mby = mb / g.Wmb;
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             st_release_u32(&S.done[mb], epoch);
             atomicAdd(&S.status[ST_COUNTS + 0], 1u);
         }
-        return;
+        continue;
     }
 
     // ---- 8x8 search, partitions in order; inside a partition the three stages are evaluated cooperatively by the whole
@@ -412,4 +418,5 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         PB_STAMP(9);
         atomicAdd(&S.status[ST_COUNTS + cnt], 1u);
     }
+  }
 }

@@ -1,0 +1,126 @@
+// Reference-side binding of fh264_b200 (the stub a maintainer of zoltanmaric/h264-fer would add).
+//
+// It re-implements, with the reference's own names and signatures, exactly the entry points the picture coder
+// RBSP_encode() calls on the P path (rbsp_encoding.cpp:175-192,317-322) plus selectNALUnitType() (fer_h264.cpp:65,121):
+//
+//   interEncoding(predL, predCr, predCb)            moestimation.h:4     -> per-MB copy-out of the GPU's results
+//   quantizationTransform(predL, predCb, predCr, r) quantizationTransform.h:10 -> levels into LumaLevel/ChromaDCLevel/ChromaACLevel
+//   transformDecodingP_Skip(...)                    inttransform.h:5     -> no-op (the GPU reconstructed the picture)
+//   FillInterpolatedRefFrame()                      moestimation.h:8     -> keeps host `frame`/`dpb` and the device in step
+//   selectNALUnitType()                             ref_frames.h:20      -> same rule, scene SAD from the device
+//
+// following the pattern the reference itself uses for its OpenCL offload: launch whole-picture work when
+// CurrMbAddr == 0 and consume it per macroblock (IntraCL() at rbsp_encoding.cpp:144, WaitIntraCL at intra.cpp:963-966).
+// The unmodified reference sources are compiled with -Dname=ref_name for these five symbols (integration/Makefile), so
+// I pictures and intra bit-cost trials still run the reference's own code; everything else (CAVLC, NAL, headers,
+// intra prediction, Y4M input) is the untouched reference host code.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "h264_globals.h"
+#include "headers_and_parameter_sets.h"
+#include "residual.h"
+#include "mode_pred.h"
+#include "ref_frames.h"
+#include "moestimation.h"
+#include "../include/fh264_b200.h"
+
+void ref_interEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8]);
+void ref_FillInterpolatedRefFrame();
+void ref_quantizationTransform(int predL[16][16], int predCb[8][8], int predCr[8][8], bool reconstruct);
+void ref_transformDecodingP_Skip(int predL[16][16], int predCb[8][8], int predCr[8][8], int QPy);
+int ref_selectNALUnitType();
+extern frame_type dpb;
+
+static fh264_session *g_sess = 0;
+static std::vector<fh264_mb_result> g_res;
+static bool g_last_was_p = false;
+
+static void die(const char *what, int rc)
+{
+    fprintf(stderr, "fh264 shim: %s failed (%d): %s\n", what, rc, fh264_last_error());
+    exit(3);                       // fail loudly: there is no CPU fallback behind this shim
+}
+
+static void ensure_session()
+{
+    if (g_sess) return;
+    const char *dev = getenv("FH264_DEVICE");
+    int rc = fh264_open(frame.Lwidth, frame.Lheight, 1, dev ? atoi(dev) : 0, &g_sess);
+    if (rc) die("fh264_open", rc);
+    g_res.resize((size_t)(frame.Lwidth >> 4) * (frame.Lheight >> 4));
+}
+
+int selectNALUnitType()
+{
+    // ref_frames.cpp:185-234 with the luma |frame - dpb| sum taken on the device
+    if (dpb.L == NULL || currFrameCount % IntraEvery == 0) return NAL_UNIT_TYPE_IDR;
+    ensure_session();
+    int rc = fh264_upload_source(g_sess, 0, frame.L, frame.C[0], frame.C[1]);
+    if (rc) die("fh264_upload_source", rc);
+    uint64_t sad = 0;
+    rc = fh264_scene_sad(g_sess, 0, &sad);
+    if (rc) die("fh264_scene_sad", rc);
+    const unsigned long picSizeInMBs = (unsigned long)PicWidthInMbs * PicHeightInMbs;
+    return sad > (picSizeInMBs << 12) ? NAL_UNIT_TYPE_IDR : NAL_UNIT_TYPE_NOT_IDR;
+}
+
+void interEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8])
+{
+    (void)predL; (void)predCr; (void)predCb;
+    if (CurrMbAddr == 0) {
+        // whole-picture device pipeline; `frame` was uploaded by selectNALUnitType() for this picture
+        ensure_session();
+        fh264_params p;
+        p.qp = QPy; p.window = WindowSize; p.maxdiff_set = MAXDIFF_SET; p.basic = BasicInterEncoding ? 1 : 0;
+        int rc = fh264_encode_p(g_sess, 0, 1, &p, g_res.data());
+        if (rc) die("fh264_encode_p", rc);
+        int32_t c[5];
+        if (fh264_mode_counts(g_sess, 0, c) == FH264_OK) for (int i = 0; i < 5; i++) brojTipova[i] = c[i];
+        g_last_was_p = true;
+    }
+    const fh264_mb_result &r = g_res[CurrMbAddr];
+    mb_type = r.mb_type;
+    mb_type_array[CurrMbAddr] = r.mb_type;
+    ClearMVD();
+    for (int i = 0; i < r.num_parts; i++) { mvd_l0[i][0][0] = r.mvd[i][0]; mvd_l0[i][0][1] = r.mvd[i][1]; }
+    for (int q = 0; q < 4; q++)
+        for (int j = 0; j < 4; j++) { mvL0x[CurrMbAddr][q][j] = r.mv[q][0]; mvL0y[CurrMbAddr][q][j] = r.mv[q][1]; }
+    refIdxL0[CurrMbAddr] = 0;
+}
+
+void quantizationTransform(int predL[16][16], int predCb[8][8], int predCr[8][8], bool reconstruct)
+{
+    if ((shd.slice_type % 5) != P_SLICE) { ref_quantizationTransform(predL, predCb, predCr, reconstruct); return; }
+    const fh264_mb_result &r = g_res[CurrMbAddr];
+    for (int b = 0; b < 16; b++) for (int k = 0; k < 16; k++) LumaLevel[b][k] = r.luma[b][k];
+    for (int c = 0; c < 2; c++) for (int k = 0; k < 4; k++) ChromaDCLevel[c][k] = r.chroma_dc[c][k];
+    for (int c = 0; c < 2; c++) for (int b = 0; b < 4; b++) for (int k = 0; k < 15; k++) ChromaACLevel[c][b][k] = r.chroma_ac[c][b][k];
+}
+
+void transformDecodingP_Skip(int predL[16][16], int predCb[8][8], int predCr[8][8], int qpy)
+{
+    (void)predL; (void)predCb; (void)predCr; (void)qpy;   // the device already reconstructed the picture
+}
+
+void FillInterpolatedRefFrame()
+{
+    // Called once per picture after modificationProcess() copied `frame` into `dpb` (rbsp_encoding.cpp:317-322).
+    ensure_session();
+    if (g_last_was_p) {
+        // P picture: the reconstruction lives on the device (dpb swap + phase R already done inside fh264_encode_p);
+        // bring it back so the host's `frame` / `dpb` stay what the reference would hold.
+        int rc = fh264_download_recon(g_sess, 0, frame.L, frame.C[0], frame.C[1]);
+        if (rc) die("fh264_download_recon", rc);
+        memcpy(dpb.L, frame.L, (size_t)frame.Lwidth * frame.Lheight);
+        memcpy(dpb.C[0], frame.C[0], (size_t)frame.Cwidth * frame.Cheight);
+        memcpy(dpb.C[1], frame.C[1], (size_t)frame.Cwidth * frame.Cheight);
+    } else {
+        // I picture coded by the reference host path: its reconstruction becomes the device's reference picture
+        int rc = fh264_upload_recon(g_sess, 0, frame.L, frame.C[0], frame.C[1]);
+        if (rc) die("fh264_upload_recon", rc);
+    }
+    g_last_was_p = false;
+}

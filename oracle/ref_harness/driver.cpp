@@ -68,6 +68,7 @@ static std::vector<int> mbrec;      // PicSizeInMbs * REC_INTS
 static std::vector<unsigned char> tqio;  // per MB: snapped source 384 + prediction 384
 static unsigned char savedL[256];
 
+#ifndef FH264_NO_TAPS   // the integration build (integration/) supplies these entry points itself
 static int *rec(int mb) { return &mbrec[(size_t)mb * REC_INTS]; }
 
 void interEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8])
@@ -161,6 +162,8 @@ void FillInterpolatedRefFrame()
 		chunk("KOLI", koliko, sizeof(koliko));
 	}
 }
+
+#endif  // FH264_NO_TAPS
 
 int main(int argc, char **argv)
 {

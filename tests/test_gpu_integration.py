@@ -1,0 +1,62 @@
+"""GPU suite: the drop-in claim end to end. integration/_build/fh264_encoder_b200 is the UNMODIFIED reference host code
+(CAVLC, NAL, headers, intra pictures, Y4M reader) linked against libfh264_b200.so through integration/fh264_ref_shim.cpp.
+Its Annex-B bitstream must be byte-identical to the reference encoder's, and its reconstruction too."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from h264_fer_b200 import synth
+from oracle import refdump
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENCODER = os.path.join(ROOT, "integration", "_build", "fh264_encoder_b200")
+
+needs_binary = pytest.mark.skipif(not os.path.isfile(ENCODER), reason="integration binary not built (make -C integration)")
+
+
+def run_b200_encoder(y4m, out264, dump, frames, qp, basic, window, maxdiff, intra_every=1000, dumpmask=0):
+    cmd = [ENCODER, y4m, out264, dump if dumpmask else "-", str(frames), str(qp), str(basic), str(window), str(maxdiff), str(intra_every),
+           str(dumpmask), "-1"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert res.returncode == 0, res.stderr.decode()[-2000:]
+    return res.stdout.decode()
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).digest()
+
+
+@needs_binary
+def test_bitstream_and_reconstruction_match_golden(golden, tmp_path):
+    y4m = str(tmp_path / "in.y4m")
+    z = golden.z
+    synth.write_y4m(y4m, golden.w_in, golden.h_in, golden.seed, golden.frames, noise=float(z["noise"][0]), square=bool(int(z["square"][0])))
+    assert md5(y4m) == bytes(z["y4m_md5"]), "synthetic clip generator drifted from the one that made the golden vectors"
+    out, dump = str(tmp_path / "out.264"), str(tmp_path / "dump.bin")
+    run_b200_encoder(y4m, out, dump, golden.frames, golden.qp, golden.basic, golden.window, golden.maxdiff, dumpmask=refdump.D_RECON)
+    assert md5(out) == bytes(z["bitstream_md5"]), "%s: .264 differs from the reference encoder's" % golden.name
+    pics = refdump.parse_dump(dump)
+    assert [p["nal_type"] for p in pics] == golden.types
+    for n, p in enumerate(pics):
+        ey, eu, ev = golden.rec(n)
+        assert np.array_equal(p["RECY"], ey) and np.array_equal(p["RECU"], eu) and np.array_equal(p["RECV"], ev), "picture %d" % n
+
+
+@needs_binary
+@pytest.mark.skipif(not refdump.have_ref_encoder(), reason="compiled reference not present")
+@pytest.mark.parametrize("w,h,seed,frames,qp,window,maxdiff,intra_every", [(176, 144, 1, 30, 28, 16, 3, 1000),     # BASELINE config 1 (QCIF, 30 frames)
+                                                                            (352, 288, 2, 12, 28, 32, -1, 5)])     # CIF, adaptive MAXDIFF, periodic IDR
+def test_bitstream_matches_live_reference(tmp_path, w, h, seed, frames, qp, window, maxdiff, intra_every):
+    y4m = str(tmp_path / "in.y4m")
+    synth.write_y4m(y4m, w, h, seed, frames)
+    ref264 = str(tmp_path / "ref.264")
+    summ, _, _ = refdump.run_reference(y4m, frames, qp=qp, window=window, maxdiff=maxdiff, intra_every=intra_every, out_264=ref264)
+    out = str(tmp_path / "b200.264")
+    run_b200_encoder(y4m, out, "-", frames, qp, 0, window, maxdiff, intra_every=intra_every)
+    assert "P" in summ["types"]
+    assert open(out, "rb").read() == open(ref264, "rb").read(), "bitstreams differ (%s)" % summ["types"]

@@ -77,6 +77,7 @@ struct PBShared {
     __align__(16) uint8_t cur[16][16];
     NbCache nc;
     u64 best[2][4];                      // per-warp minima, double-buffered across partitions
+    u64 sel_min[4]; int sel_cnt[4];      // lazy stage-2 verification
     PartA pa[4];                         // phase-A products of the four partitions, fetched BEFORE the dependency wait
     S3Entry s3[4][FH_S3_MAX + 1];
     uint2 pool[4][PB_POOL_PREF];
@@ -150,6 +151,79 @@ __device__ __forceinline__ int block_select_smallest(int n, int k, KeyFn keyfn, 
     return K;
 }
 
+// 32-bit-key variant for stage 1 (keys = cost << 11 | arrival index, unique; 0xffffffff = no candidate): single-instruction
+// warp reductions and half the compare cost of the 64-bit path. Same contract as block_select_smallest.
+__device__ __forceinline__ int block_select_smallest_u32(const uint32_t *keys, int n, int k, BlockSel *bs, uint16_t *members, int call)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
+    int nv = 0;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t key = keys[i];
+        nv += key != 0xffffffffu;
+        m2 = min(m2, max(m1, key));
+        m1 = min(m1, key);
+    }
+    const int K = min(k, __reduce_add_sync(0xffffffffu, nv));
+    if (K == 0) return 0;
+    const int L1 = __popc(__ballot_sync(0xffffffffu, m1 != 0xffffffffu));
+    const int L2 = __popc(__ballot_sync(0xffffffffu, m2 != 0xffffffffu));
+    uint32_t thr = 0xfffffffeu;
+    if (L1 >= K) thr = __reduce_max_sync(0xffffffffu, m1 != 0xffffffffu ? m1 : 0u);
+    else if (L1 + 1 >= K && L2 >= 1) thr = max(__reduce_max_sync(0xffffffffu, m1 != 0xffffffffu ? m1 : 0u), __reduce_min_sync(0xffffffffu, m2));
+    else if (2 * L2 >= K) thr = __reduce_max_sync(0xffffffffu, m2 != 0xffffffffu ? m2 : 0u);
+    int *nsp = &bs->ns[call & 1];
+    uint32_t *skey = (uint32_t *)bs->skey;
+    for (int i = tid; i < n; i += PB_NT) {
+        const uint32_t key = keys[i];
+        if (key <= thr) {
+            const int pos = atomicAdd(nsp, 1);
+            if (pos < 256) { skey[pos] = key; bs->sidx[pos] = (uint16_t)i; }
+        }
+    }
+    __syncthreads();
+    const int ns = *nsp;
+    if (tid == 0) bs->ns[(call & 1) ^ 1] = 0;
+    if (ns <= 64) {
+        const int G = ns <= 32 ? 4 : 2, sidx = tid / G, part = tid - sidx * G;
+        int rank = 0;
+        if (sidx < ns) { const uint32_t key = skey[sidx]; for (int j = part; j < ns; j += G) rank += skey[j] < key; }
+        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+        if (G == 4) rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+        if (sidx < ns && part == 0 && rank < K) members[rank] = bs->sidx[sidx];
+    } else if (ns <= 256) {
+        for (int sidx = tid; sidx < ns; sidx += PB_NT) {
+            const uint32_t key = skey[sidx];
+            int rank = 0;
+            for (int j = 0; j < ns; j++) rank += skey[j] < key;
+            if (rank < K) members[rank] = bs->sidx[sidx];
+        }
+    } else {
+        for (int i = tid; i < n; i += PB_NT) {
+            const uint32_t key = keys[i];
+            if (key > thr) continue;
+            int rank = 0;
+            for (int j = 0; j < n && rank < K; j++) rank += keys[j] < key;
+            if (rank < K) members[rank] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+    return K;
+}
+
+// Median prediction from three neighbour candidates with availability flags (mode_pred.cpp:299-332; every available
+// neighbour of a P picture is inter with refIdx 0, so "same reference" == available, except the A := 0 substitutions).
+__device__ __forceinline__ void median_pred(int aA, int ax, int ay, int aB, int bx, int by, int aC, int cx, int cy, int &ox, int &oy)
+{
+    int sa = aA, sb = aB, sc = aC;
+    if (!aA && !aB) { ax = ay = 0; sa = 1; }
+    else if (!aA) { ax = ay = 0; sa = 0; }
+    if (!aB) { bx = ax; by = ay; sb = sa; }
+    if (!aC) { cx = ax; cy = ay; sc = sa; }
+    if (sa + sb + sc == 1) { ox = sa ? ax : (sb ? bx : cx); oy = sa ? ay : (sb ? by : cy); return; }
+    ox = median3_(ax, bx, cx); oy = median3_(ay, by, cy);
+}
+
 __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__ seqs, int seq0, int nseq, Geo g, fh264_params prm,
                                                    uint32_t epoch, const int *__restrict__ wf_order, uint32_t *__restrict__ ticket)
 {
@@ -171,7 +245,6 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     NbCache &nc = sh.nc;
     long long *dbg = S.dbg ? S.dbg + (size_t)mb * 24 : nullptr;
 #define PB_STAMP(k) do { if (dbg && tid == 0) dbg[k] = clock64(); } while (0)
-#define PB_PSTAMP(k) do { if (dbg && tid == 0 && pi == 0) dbg[k] = clock64(); } while (0)
     PB_STAMP(0);
 
     // ---- everything that does not depend on the neighbours is fetched BEFORE waiting on them: the CTA is resident
@@ -251,23 +324,34 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     }
 
     // ---- 8x8 search, partitions in order; inside a partition the three stages are evaluated cooperatively by the whole
-    //      block (the wavefront is latency bound: per-warp instruction count is what sits on the critical path) ----------
-    int mv[4][2], sadq[4], mvps[4][2], curq[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+    //      block (the wavefront is latency bound: what sits on the critical path is dependent instructions and memory
+    //      round trips, so independent work is issued first and consumed late) --------------------------------------------
+    int mv[4][2], sadq[4], mvps[4][2];
+    int q0x = 0, q0y = 0, q1x = 0, q1y = 0, q2x = 0, q2y = 0;          // quadrant MVs decided so far
     const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16, inv1 = 65536 / w1 + 1, npos = w1 * w1;
     const int f1 = tid & 15;
     int callno = 0;                  // alternates BlockSel's survivor counters (uniform across the block)
     const uint4 *__restrict__ Kf = S.kar + (size_t)f1 * g.WH;
+    // neighbour quadrant MVs used by the 8x8 predictors, in registers (A.7): left q1/q3, up q2/q3, up-right q2, up-left q3
+    const int aL = nc.avail[0], aU = nc.avail[1], aUR = nc.avail[2], aUL = nc.avail[3];
+    const int l1x = nc.mvx[0][1], l1y = nc.mvy[0][1], l3x = nc.mvx[0][3], l3y = nc.mvy[0][3];
+    const int u2x = nc.mvx[1][2], u2y = nc.mvy[1][2], u3x = nc.mvx[1][3], u3y = nc.mvy[1][3];
+    const int r2x = nc.mvx[2][2], r2y = nc.mvy[2][2], d3x = nc.mvx[3][3], d3y = nc.mvy[3][3];
     for (int pi = 0; pi < 4; pi++) {
         const int xP = mbx * 16 + (pi & 1) * 8, yP = mby * 16 + (pi >> 1) * 8;
         int mvpx, mvpy;
-        predict_mv_(nc, (pi & 1) * 8, (pi >> 1) * 8, 8, 0, curq, mvpx, mvpy);
+        // A = (px-1,py), B = (px,py-1), C = (px+8,py-1) else D = (px-1,py-1) for an 8x8 partition (mode_pred.cpp:113-161)
+        if (pi == 0) median_pred(aL, l1x, l1y, aU, u2x, u2y, aU ? 1 : aUL, aU ? u3x : d3x, aU ? u3y : d3y, mvpx, mvpy);
+        else if (pi == 1) median_pred(1, q0x, q0y, aU, u3x, u3y, aUR ? 1 : aU, aUR ? r2x : u2x, aUR ? r2y : u2y, mvpx, mvpy);
+        else if (pi == 2) median_pred(aL, l3x, l3y, 1, q0x, q0y, 1, q1x, q1y, mvpx, mvpy);
+        else median_pred(1, q2x, q2y, 1, q1x, q1y, 1, q0x, q0y, mvpx, mvpy);
         mvps[pi][0] = mvpx; mvps[pi][1] = mvpy;
         const int genx = mvpx >> 2, geny = mvpy >> 2;
         const PartA pa = sh.pa[pi];
         u64 *best = sh.best[pi & 1];
         u64 mine = KEY_NONE;
-        // stage 1 (:458-469), part 1: issue the feature loads of the window/16 quarter-pel window around the predictor.
-        // thread -> (fraction = tid & 15, position = (tid >> 4) + 8u); they complete while stage 2 is ranked.
+        // stage 1 (:458-469): issue the feature loads of the window/16 quarter-pel window around the predictor.
+        // thread -> (fraction = tid & 15, position = (tid >> 4) + 8u)
         uint4 v1[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -275,29 +359,17 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             v1[u] = make_uint4(0, 0, 0, 1u);
             if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) v1[u] = __ldg(Kf + (size_t)ry * W + rx);
         }
-        PB_PSTAMP(10);
-        // stage 2 (:470-507): rank the phase-A set with the predictor-dependent multiplier, SADs looked up
+        // stage 2 (:470-507) keys while those loads fly: cost << 10 | arrival rank; SADs were measured in phase A
         const int n2 = (int)pa.n2;
         const uint2 *pool = S.s2pool + pa.s2_off;
+        u64 t2 = KEY_NONE;               // this thread's best stage-2 (total, key) among candidates not yet rejected
         for (int i = tid; i < n2; i += PB_NT) {
             const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
             const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16);
             const uint32_t cost = (uint32_t)(iabs_(dx - genx) + iabs_(dy - geny) + 4) * (v.y & 0x3ffffu);
-            sh.keys2[i] = ((u64)cost << 10) | (u64)i;
-        }
-        __syncthreads();
-        PB_PSTAMP(11);
-        int K2 = n2;
-        if (n2 > FH_S3_MAX) K2 = block_select_smallest(n2, FH_S3_MAX, [&](int i) -> u64 { return sh.keys2[i]; }, &sh.bs, sh.mem2, callno++);
-        PB_PSTAMP(12);
-        if (tid < K2) {
-            const int i = n2 > FH_S3_MAX ? (int)sh.mem2[tid] : tid;
-            const u64 key = sh.keys2[i];
-            if ((key >> 10) < (u64)FH_COST_EMPTY) {
-                const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
-                const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16), sad = (int)(v.y >> 18);
-                mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
-            }
+            const u64 key = ((u64)cost << 10) | (u64)i;
+            sh.keys2[i] = key;
+            if (cost < (uint32_t)FH_COST_EMPTY) t2 = min(t2, ((u64)((int)(v.y >> 18) + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
         }
         // stage 3 (:508-520): phase-A list, already in list order
         if (tid >= 64 && tid - 64 < (int)pa.n3) {
@@ -305,13 +377,12 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             const S3Entry e = sh.s3[pi][i];
             mine = min(mine, ((u64)((int)e.sad + mv_cost(e.mvx, e.mvy, mvpx, mvpy)) << 44) | (2ull << 42) | (u64)i);
         }
-        PB_PSTAMP(13);
-        // stage 1, part 2: keys = cost << 11 | arrival index ((dx, dy, frac) order)
-        {
-            const uint2 *rp = (const uint2 *)&sh.cur[(pi >> 1) * 8][(pi & 1) * 8];
-            uint2 rows[8];
+        // stage 1 keys = cost << 11 | arrival index ((dx, dy, frac) order)
+        const uint2 *rp = (const uint2 *)&sh.cur[(pi >> 1) * 8][(pi & 1) * 8];
+        uint2 rows[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) rows[r] = rp[r * 2];           // 16-byte row pitch
+        for (int r = 0; r < 8; r++) rows[r] = rp[r * 2];           // 16-byte row pitch
+        {
             int s[5];
             block_sums(rows, s);                                       // suma[0..4] (:440-451)
 #pragma unroll
@@ -329,36 +400,89 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
                 if (rx >= 0 && rx < W && ry >= 0 && ry < H) key = ((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(s, __ldg(Kf + (size_t)ry * W + rx))) << 11) | (uint32_t)i;
                 sh.keys1[i] = key;
             }
-            __syncthreads();
-            PB_PSTAMP(14);
-            const int K1 = block_select_smallest(n1, FH_S1_MAX, [&](int i) -> u64 { const uint32_t k = sh.keys1[i]; return k == COST_INVALID ? KEY_NONE : (u64)k; },
-                                                 &sh.bs, sh.mem1, callno++);
-            PB_PSTAMP(15);
-            // SADs of the (at most 17) members: 8 threads per member, one row each
-            const int r = tid & 7;
-            const uint2 cr = pick_row(rows, r);
+        }
+        __syncthreads();                                               // keys1 and keys2 complete
+        const int K1 = block_select_smallest_u32(sh.keys1, n1, FH_S1_MAX, &sh.bs, sh.mem1, callno++);
+        // SAD loads of the (at most 17) stage-1 members: 8 threads per member, one row each; consumed after stage 2
+        const int r = tid & 7;
+        const uint2 cr = pick_row(rows, r);
+        uint2 rr[2];
+        int mvx1[2], mvy1[2];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int m = u * 16 + (tid >> 3);
-                int sad = 0, mvx = 0, mvy = 0;
-                if (m < K1) {
-                    const int i = sh.mem1[m], f = i & 15, pos = i >> 4, cx = fdiv_(pos, inv1), dx = genx + cx - g1, dy = geny + pos - cx * w1 - g1;
-                    mvx = (dx << 2) | (f & 3); mvy = (dy << 2) | (f >> 2);
-                    sad = sad8(cr, load_row8(S.planes + (size_t)f * g.WH, W, H, clampi_(xP + dx, 0, W - 1), clampi_(yP + dy, 0, H - 1) + r));
-                }
-                if (u == 0 || tid < 8) {                               // round 1 only concerns member 16 (threads 0-7)
-                    sad += __shfl_xor_sync(u == 0 ? 0xffffffffu : 0xffu, sad, 1);
-                    sad += __shfl_xor_sync(u == 0 ? 0xffffffffu : 0xffu, sad, 2);
-                    sad += __shfl_xor_sync(u == 0 ? 0xffffffffu : 0xffu, sad, 4);
-                }
-                if (m < K1 && r == 0) mine = min(mine, ((u64)(sad + mv_cost(mvx, mvy, mvpx, mvpy)) << 44) | (u64)sh.keys1[sh.mem1[m]]);
+        for (int u = 0; u < 2; u++) {
+            const int m = u * 16 + (tid >> 3);
+            rr[u] = make_uint2(0, 0); mvx1[u] = mvy1[u] = 0;
+            if (m < K1) {
+                const int i = sh.mem1[m], f = i & 15, pos = i >> 4, cx = fdiv_(pos, inv1), dx = genx + cx - g1, dy = geny + pos - cx * w1 - g1;
+                mvx1[u] = (dx << 2) | (f & 3); mvy1[u] = (dy << 2) | (f >> 2);
+                rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, clampi_(xP + dx, 0, W - 1), clampi_(yP + dy, 0, H - 1) + r);
             }
         }
-        PB_PSTAMP(16);
+        // stage 2, lazily: the block's best stage-2 candidate by (total, list order) is THE stage-2 contribution iff it is
+        // one of the 33 smallest keys. Verify by counting keys below it; on failure reject it and retry, then fall back to the
+        // exact selection. (n2 <= 33: every candidate is on the list.)
+        if (n2 > 0) {
+            u64 cand = KEY_NONE;
+            bool settled = false;
+            for (int attempt = 0; attempt < 3 && !settled; attempt++) {
+                u64 wmin = warp_min_u64(t2);
+                if (lane == 0) sh.sel_min[warp] = wmin;
+                __syncthreads();
+                cand = min(min(sh.sel_min[0], sh.sel_min[1]), min(sh.sel_min[2], sh.sel_min[3]));
+                if (cand == KEY_NONE || n2 <= FH_S3_MAX) { settled = true; __syncthreads(); break; }
+                const u64 ckey = cand & ((1ull << 42) - 1);
+                int below = 0;
+                for (int i = tid; i < n2; i += PB_NT) below += sh.keys2[i] < ckey;
+                below = __reduce_add_sync(0xffffffffu, below);
+                if (lane == 0) sh.sel_cnt[warp] = below;
+                __syncthreads();
+                const int rank = sh.sel_cnt[0] + sh.sel_cnt[1] + sh.sel_cnt[2] + sh.sel_cnt[3];
+                if (rank < FH_S3_MAX) settled = true;
+                else if (t2 == cand) {
+                    // the owner rejects it and recomputes its local best without it
+                    const int rej = (int)(ckey & 1023);
+                    t2 = KEY_NONE;
+                    for (int i = tid; i < n2; i += PB_NT) {
+                        const u64 key = sh.keys2[i];
+                        if (i == rej || (key >> 10) >= (u64)FH_COST_EMPTY) continue;
+                        sh.keys2[i] = key;
+                        const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
+                        const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16);
+                        const u64 fk = ((u64)((int)(v.y >> 18) + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key;
+                        if (fk > cand) t2 = min(t2, fk);       // candidates rejected earlier compare below `cand`
+                    }
+                }
+                __syncthreads();
+            }
+            if (settled) { if (tid == 0) mine = min(mine, cand); }
+            else {
+                const int K2 = block_select_smallest(n2, FH_S3_MAX, [&](int i) -> u64 { return sh.keys2[i]; }, &sh.bs, sh.mem2, callno++);
+                if (tid < K2) {
+                    const int i = (int)sh.mem2[tid];
+                    const u64 key = sh.keys2[i];
+                    if ((key >> 10) < (u64)FH_COST_EMPTY) {
+                        const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
+                        const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16), sad = (int)(v.y >> 18);
+                        mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
+                    }
+                }
+            }
+        }
+        // stage 1 SADs
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int m = u * 16 + (tid >> 3);
+            int sad = m < K1 ? sad8(cr, rr[u]) : 0;
+            if (u == 0 || tid < 8) {                               // round 1 only concerns member 16 (threads 0-7)
+                sad += __shfl_xor_sync(u == 0 ? 0xffffffffu : 0xffu, sad, 1);
+                sad += __shfl_xor_sync(u == 0 ? 0xffffffffu : 0xffu, sad, 2);
+                sad += __shfl_xor_sync(u == 0 ? 0xffffffffu : 0xffu, sad, 4);
+            }
+            if (m < K1 && r == 0) mine = min(mine, ((u64)(sad + mv_cost(mvx1[u], mvy1[u], mvpx, mvpy)) << 44) | (u64)sh.keys1[sh.mem1[m]]);
+        }
         mine = warp_min_u64(mine);
         if (lane == 0) best[warp] = mine;
         __syncthreads();
-        PB_PSTAMP(17);
         // decode the winner from its key (:523-527); no candidate at all leaves bx = by = 0 (:452)
         const u64 b = min(min(best[0], best[1]), min(best[2], best[3]));
         int bx = 0, by = 0, bs = 0;
@@ -378,11 +502,11 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             bs = total - mv_cost(bx, by, mvpx, mvpy);
         } else {
             const uint8_t *pl = S.planes;
-            for (int r = 0; r < 8; r++) bs += sad_row8(*(const uint2 *)&sh.cur[(pi >> 1) * 8 + r][(pi & 1) * 8], pl, W, H, xP, yP + r);
+            for (int rr2 = 0; rr2 < 8; rr2++) bs += sad_row8(*(const uint2 *)&sh.cur[(pi >> 1) * 8 + rr2][(pi & 1) * 8], pl, W, H, xP, yP + rr2);
         }
         mv[pi][0] = bx; mv[pi][1] = by; sadq[pi] = bs;
         PB_STAMP(5 + pi);
-        curq[pi][0] = bx; curq[pi][1] = by;
+        if (pi == 0) { q0x = bx; q0y = by; } else if (pi == 1) { q1x = bx; q1y = by; } else if (pi == 2) { q2x = bx; q2y = by; }
     }
 
     // ---- merge (:529-551) and final mvd with the merged type's predictors (:552-564) ---------------------------

@@ -25,6 +25,7 @@
 #define ST_SAD_HI 9
 #define ST_TICKET 10
 #define ST_FLAGS_NEXT 11   // flags raised by phase R for the NEXT picture's reference
+#define ST_S2REDO 12       // set when some partition overflowed the fast stage-2 launch
 #define ST_WORDS 16
 #define FLAG_UB_INPUT 1u
 #define FLAG_CAPACITY 2u

@@ -54,6 +54,7 @@ __global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
     st[ST_FLAGS] = st[ST_FLAGS_NEXT];
     st[ST_S2CURSOR] = 0;
     for (int i = 0; i < 5; i++) st[ST_COUNTS + i] = 0;
+    st[ST_S2REDO] = 0;
     if (threadIdx.x == 0) *ticket = 0;
 }
 __global__ void k_begin_ref(SeqDev *seqs, int seq0) { seqs[seq0 + threadIdx.x].status[ST_FLAGS_NEXT] = 0; }
@@ -308,7 +309,10 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         dim3 g3d(g.nparts / 4, nseq), g2d(g.nparts / 2, nseq);
         k_stage3<<<g3d, 128, smem3, st>>>(s->d_seqs, seq0, g, prm, npad);
         CK(cudaEventRecord(s->evk[0], st));
-        k_stage2<<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
+        k_stage2<S2_CAP_FAST, 2, false><<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
+        // partitions with more than S2_CAP_FAST gated survivors (marked) are redone with the large buffers; every other warp exits at once
+        dim3 g2r(g.nparts, nseq);
+        k_stage2<S2_CAP_BIG, 1, true><<<g2r, 32, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
     CK(cudaEventRecord(s->ev[1], st));
     // persistent wavefront CTAs: about one anti-diagonal (Wmb/2) plus slack per sequence

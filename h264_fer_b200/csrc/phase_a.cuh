@@ -163,25 +163,33 @@ __global__ void __launch_bounds__(128, 4) k_stage3(const SeqDev *__restrict__ se
     }
 }
 
-#define S2_WARP_CAP 1024      // gated survivors held per partition; beyond: FH264_E_CAPACITY
 #define S2_BINS 384           // (j, side) bins: 2*j + side, j <= 180
-#define S2_CHUNK_CAP 1024      // a round of 32 short ranges (<= 64 entries each) adds at most 256 chunks
+#define S2_CHUNK_CAP 512      // a round of 32 short ranges (<= 64 entries each) adds at most 256 chunks
+#define S2_CAP_FAST 512       // gated survivors per partition held by the main launch
+#define S2_CAP_BIG 4096       // ... and by the fallback launch (beyond: FH264_E_CAPACITY)
+#define S2_REDO 0xffffffffu   // PartA::n2 marker: partition left to the fallback launch
+
+template <int CAP>
 struct S2Warp {
-    uint32_t akey[S2_WARP_CAP];      // arrival key: j<<21 | side<<20 | (dx+279)<<10 | (dy+279)
-    uint32_t afeat[S2_WARP_CAP];     // feature distance (18 bits) | SAD << 18
-    uint16_t order[S2_WARP_CAP];     // survivor index by output slot
+    uint32_t akey[CAP];              // arrival key: j<<21 | side<<20 | (dx+279)<<10 | (dy+279)
+    uint32_t aval[CAP];              // index entry number, later feature distance (18 bits) | SAD << 18
+    uint16_t order[CAP];             // survivor index by output slot
     uint32_t bins[S2_BINS];          // counts, then exclusive starts, then scatter cursors
     uint32_t chunk[S2_CHUNK_CAP];    // chunks of <= 8 consecutive index entries still to be visited
     int n_surv;
 };
 
-__global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
+// CAP = survivor capacity per warp, NW = warps (= partitions) per CTA. The main launch (CAP = 512) keeps shared memory
+// small for occupancy; partitions with more gated survivors are marked and redone by a second launch with CAP = 4096.
+template <int CAP, int NW, bool REDO>
+__global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
 {
-    __shared__ S2Warp sm[2];
+    __shared__ S2Warp<CAP> sm[NW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    S2Warp *w = &sm[warp];
+    S2Warp<CAP> *w = &sm[warp];
     const SeqDev &S = seqs[seq0 + blockIdx.y];
-    const int part = blockIdx.x * 2 + warp;
+    const int part = blockIdx.x * NW + warp;
+    if (REDO && (S.status[ST_S2REDO] == 0 || S.parta[part].n2 != S2_REDO)) return;
     int xP, yP;
     part_origin(g, part, xP, yP);
     uint2 rows[8];
@@ -199,16 +207,16 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
     const int k1lo = max(0, s[1] - 99) >> 6, k1hi = min(8191, s[1] + 99) >> 6;
     const int ntiles = ntx * nty, inv_ntx = 65536 / ntx + 1;
     const uint4 *__restrict__ tent = (const uint4 *)S.tent;
-    auto visit = [&](const uint4 v) {
+    // gate of one index entry (:481); survivors only record their arrival key and entry number here — the feature
+    // distance and the (j, side) histogram are computed afterwards in a dense pass (no divergent heavy code)
+    auto visit = [&](const uint4 v, uint32_t eidx) {
         const int x = v.x & 0xffff, y = v.x >> 16, k0 = v.y & 0xffff, k1 = v.y >> 16, k2 = v.z & 0xffff;
         const int j = iabs_(k0 - s[0]), dx = x - xP, dy = y - yP;
         if (j <= 180 && iabs_(dx) + iabs_(dy) < 280 && iabs_(k1 - s[1]) < 100 && iabs_(k2 - s[2]) < 100) {
-            const int side = k0 > s[0];
-            atomicAdd(&w->bins[2 * j + side], 1u);
             const int pos = atomicAdd(&w->n_surv, 1);
-            if (pos < S2_WARP_CAP) {
-                w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
-                w->afeat[pos] = (uint32_t)feat_dist(s, k0, k1, k2, (int)(v.z >> 16), (int)(v.w & 0xffff));
+            if (pos < CAP) {
+                w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)(k0 > s[0]) << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
+                w->aval[pos] = eidx;
             }
         }
     };
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
             longm &= longm - 1;
             const uint32_t gb = __shfl_sync(0xffffffffu, gbase, src);
             const int ln = __shfl_sync(0xffffffffu, len, src);
-            for (int e = lane; e < ln; e += 32) visit(__ldg(tent + gb + e));
+            for (int e = lane; e < ln; e += 32) visit(__ldg(tent + gb + e), gb + e);
             if (lane == src) len = 0;
         }
         // short ranges: chunks of <= 8 consecutive entries (one 128-byte line): first entry | (count - 1) << 28
@@ -247,23 +255,37 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
         nchunk += __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
         if (nchunk > S2_CHUNK_CAP - 256 || it0 + 32 >= nitems) {
-            // lanes stride the chunk list: balanced work, sequential 16-byte loads, 4 in flight
+            // lanes stride the chunk list: balanced work, 8 sequential 16-byte loads in flight
             for (int cidx = lane; cidx < nchunk; cidx += 32) {
-                const uint32_t cw = w->chunk[cidx];
-                const uint4 *ep = tent + (cw & 0x0fffffffu);
+                const uint32_t cw = w->chunk[cidx], e0 = cw & 0x0fffffffu;
                 const int cnt = (int)(cw >> 28) + 1;
+                uint4 v[8];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    uint4 v[4];
+                for (int u = 0; u < 8; u++) v[u] = u < cnt ? __ldg(tent + e0 + u) : make_uint4(0, 0xffffu, 0, 0);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = h * 4 + u < cnt ? __ldg(ep + h * 4 + u) : make_uint4(0, 0xffffu, 0, 0);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) visit(v[u]);
-                }
+                for (int u = 0; u < 8; u++) visit(v[u], e0 + u);
             }
             nchunk = 0;
             __syncwarp();
         }
+    }
+    __syncwarp();
+    const int ns = w->n_surv;
+    if (ns > CAP) {
+        // too many gated survivors for this launch's buffers
+        if (lane == 0) {
+            PartA *pa = &S.parta[part];
+            pa->s2_off = 0;
+            if (!REDO) pa->n2 = S2_REDO; else { pa->n2 = 0; atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); }
+            if (!REDO) atomicOr(&S.status[ST_S2REDO], 1u);
+        }
+        return;
+    }
+    // dense pass over the survivors: feature distance (:267-276) and the (j, side) histogram
+    for (int i = lane; i < ns; i += 32) {
+        const uint4 v = __ldg(tent + w->aval[i]);
+        w->aval[i] = (uint32_t)feat_dist(s, (int)(v.y & 0xffff), (int)(v.y >> 16), (int)(v.z & 0xffff), (int)(v.z >> 16), (int)(v.w & 0xffff));
+        atomicAdd(&w->bins[w->akey[i] >> 20], 1u);
     }
     __syncwarp();
     // j_stop: first j at which the running gated count exceeds 128 (:496), else 180. Bucket s0 is visited by both
@@ -286,10 +308,10 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
 #pragma unroll
     for (int i = 0; i < 6; i++) if (lane * 6 + i <= js) upto += cj[i];
     int n2 = (int)__reduce_add_sync(0xffffffffu, upto);
-    const int cnt0 = (int)__shfl_sync(0xffffffffu, cb[0], 0), ns = w->n_surv;
+    const int cnt0 = (int)__shfl_sync(0xffffffffu, cb[0], 0);
     uint32_t off = 0;
     if (lane == 0) {
-        if (ns > S2_WARP_CAP || n2 > 1023) { atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); n2 = 0; }
+        if (n2 > 1023) { atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); n2 = 0; }
         else if (n2 > 0) {
             off = atomicAdd(&S.status[ST_S2CURSOR], (uint32_t)n2);
             if (off + (uint32_t)n2 > S.s2pool_size) { atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); n2 = 0; }
@@ -301,15 +323,14 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
     off = __shfl_sync(0xffffffffu, off, 0);
     if (n2 == 0) return;
     // Arrival order (:474-495): j ascending; minus side before plus side; x then y inside a bucket; bucket s0 twice.
-    // Output slot of bin b >= 2: start = (excl of j's before) + (side ? count of side 0 : 0); bin 0 starts at 0 and is
-    // written again at cnt0 (the second visit). Starts replace the counts in w->bins.
+    // Output slot of bin (j, side): start = (entries of smaller j, bucket s0 counted twice) + (side ? count of side 0 : 0);
+    // the second visit of bucket s0 is a copy at cnt0. Starts replace the counts in w->bins.
     {
-        uint32_t st = excl;            // excl already counts bucket s0 twice
+        uint32_t st = excl;
 #pragma unroll
         for (int i = 0; i < 6; i++) {
-            const uint32_t base0 = (lane == 0 && i == 0) ? 0u : st;
-            w->bins[lane * 12 + 2 * i] = base0;
-            w->bins[lane * 12 + 2 * i + 1] = base0 + cb[2 * i];
+            w->bins[lane * 12 + 2 * i] = st;
+            w->bins[lane * 12 + 2 * i + 1] = st + cb[2 * i];
             st += cj[i];
         }
     }
@@ -321,17 +342,15 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
         w->order[atomicAdd(&w->bins[bin], 1u)] = (uint16_t)i;    // arbitrary order inside a bin, fixed below
     }
     __syncwarp();
-    // order inside each bin by (x, y): bins hold 0-2 entries on textured content; insertion sort per bin
     {
-        // segment of bin (j, side) = [start, start + count): the owning lane recomputes the start
+        // order inside each (j, side) bin by (x, y): insertion sort by the owning lane (bins hold 0-2 entries on textured content)
         uint32_t st = excl;
 #pragma unroll
         for (int i = 0; i < 6; i++) {
-            const uint32_t base0 = (lane == 0 && i == 0) ? 0u : st;
 #pragma unroll
             for (int sd = 0; sd < 2; sd++) {
                 const int j = lane * 6 + i;
-                const int b0 = (int)(sd ? base0 + cb[2 * i] : base0), cnt = (int)cb[2 * i + sd];
+                const int b0 = (int)(sd ? st + cb[2 * i] : st), cnt = (int)cb[2 * i + sd];
                 if (j <= js && cnt > 1) {
                     for (int a = 1; a < cnt; a++) {
                         const uint16_t ia = w->order[b0 + a];
@@ -347,16 +366,16 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
     }
     __syncwarp();
     // SAD at integer displacement (fraction 0 => plane 0) for the kept candidates: 8 lanes per candidate, one row
-    // each, 4 rounds of loads in flight. Slots of the second visit of bucket s0 are copies.
+    // each, 8 rounds of loads in flight. Slots of the second visit of bucket s0 are copies.
     const uint8_t *pl = S.planes;
     const int r = lane & 7;
     const uint2 cr = pick_row(rows, r);
     const int nuniq = n2 - cnt0;          // distinct candidates: slots [0, cnt0) and [2*cnt0, n2)
-    for (int base = 0; base < nuniq; base += 16) {
-        uint2 rr[4];
-        int idx[4];
+    for (int base = 0; base < nuniq; base += 32) {
+        uint2 rr[8];
+        int idx[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
             const int m = base + u * 4 + (lane >> 3);
             rr[u] = make_uint2(0, 0); idx[u] = -1;
             if (m < nuniq) {
@@ -367,12 +386,12 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
             int sad = idx[u] >= 0 ? sad8(cr, rr[u]) : 0;
             sad += __shfl_xor_sync(0xffffffffu, sad, 1);
             sad += __shfl_xor_sync(0xffffffffu, sad, 2);
             sad += __shfl_xor_sync(0xffffffffu, sad, 4);
-            if (idx[u] >= 0 && r == 0) w->afeat[idx[u]] |= (uint32_t)sad << 18;
+            if (idx[u] >= 0 && r == 0) w->aval[idx[u]] |= (uint32_t)sad << 18;
         }
     }
     __syncwarp();
@@ -381,7 +400,7 @@ __global__ void __launch_bounds__(64) k_stage2(const SeqDev *__restrict__ seqs, 
         const int slot = m < cnt0 ? m : m + cnt0, i = w->order[slot];
         const uint32_t k = w->akey[i];
         const int dx = (int)((k >> 10) & 1023) - 279, dy = (int)(k & 1023) - 279;
-        const uint2 v = make_uint2(((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16), w->afeat[i]);
+        const uint2 v = make_uint2(((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16), w->aval[i]);
         pool[slot] = v;
         if (m < cnt0) pool[cnt0 + m] = v;
     }

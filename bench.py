@@ -214,6 +214,7 @@ def main():
     import torch
     import torch.distributed as dist
     import h264_fer_b200 as fh
+    from h264_fer_b200 import sharding
     from h264_fer_b200.native import PinnedArray
 
     rank = int(os.environ.get("RANK", "0"))
@@ -226,7 +227,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, K, Wu = args.seqs, args.steps, max(args.warmup, 3)
     G = max(1, min(args.groups, B))                      # sequence groups: one session + stream + host thread each
-    clips = make_clips(B, 100 + rank * B)
+    my_seqs = sharding.sequences_for_rank(B * world, rank, world)       # global sequence ids of this GPU (seed = 100 + id)
+    clips = [make_clips(1, 100 + sid)[0] for sid in my_seqs]
     H = clips[0][0][0].shape[0]
     nmb = (WIDTH // 16) * (H // 16)
     ysz, csz = WIDTH * H, WIDTH * H // 4
@@ -332,11 +334,7 @@ def main():
         if world > 1:
             dist.barrier()
         clocks = sampler.stop() if rank == 0 else None
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
+        ms = sharding.reduce_max(e0.elapsed_time(e1))          # max over ranks
         for gr in groups:
             for j in range(gr.n):
                 gr.s.picture_status(j)

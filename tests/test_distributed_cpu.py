@@ -1,0 +1,82 @@
+"""CPU suite: the N>1 host logic with world_size 2 over gloo (no GPU): sequence sharding covers every sequence exactly once,
+band arithmetic, max-over-ranks time reduction, and the reference arm's rank gating of bench.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch.multiprocessing as mp
+
+from h264_fer_b200 import sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = sharding.sequences_for_rank(13, rank, world)
+    allseq = sharding.gather_counts(mine)
+    tmax = sharding.reduce_max(10.0 + rank)
+    q.put((rank, mine, allseq, tmax))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_timing():
+    world, port = 2, 29571
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4, 6, 8, 10, 12] and res[1][1] == [1, 3, 5, 7, 9, 11]
+    for _, _, allseq, tmax in res:
+        assert sorted(sum(allseq, [])) == list(range(13))      # every sequence exactly once
+        assert tmax == 11.0                                     # max over ranks, identical on every rank
+
+
+def test_mb_row_bands_and_halo():
+    assert [b - a for a, b in sharding.mb_row_bands(67, 8)] == [9, 9, 9, 8, 8, 8, 8, 8]
+    bands = sharding.mb_row_bands(67, 8)
+    assert bands[0][0] == 0 and bands[-1][1] == 67 and all(bands[i][1] == bands[i + 1][0] for i in range(7))
+    assert sharding.mb_row_bands(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    lo, hi = sharding.halo_rows(bands[3], 67)
+    assert lo == bands[3][0] * 16 - 291 and hi == bands[3][1] * 16 + 291
+    assert sharding.halo_rows(bands[0], 67)[0] == 0 and sharding.halo_rows(bands[7], 67)[1] == 67 * 16
+    with pytest.raises(ValueError):
+        sharding.sequences_for_rank(4, 2, 2)
+
+
+def test_reference_arm_non_zero_ranks_exit_without_work():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert res.returncode == 0 and res.stdout.strip() == b""
+
+
+def test_host_mirror_frame_type_rule():
+    """SequenceEncoder.select_nal_unit_type == selectNALUnitType (ref_frames.cpp:185-234) on a fake session."""
+    from h264_fer_b200.encoder import SequenceEncoder, NAL_IDR, NAL_NON_IDR
+
+    class Fake:
+        nmb = 99
+        def __init__(self): self.sad = 0
+        def scene_sad(self, seq): return self.sad
+
+    f = Fake()
+    e = SequenceEncoder(f, 0, intra_every=4)
+    assert e.select_nal_unit_type() == NAL_IDR                       # no dpb yet
+    e.have_dpb = True; e.curr_frame_count = 1
+    f.sad = 99 << 12
+    assert e.select_nal_unit_type() == NAL_NON_IDR                   # strictly greater than MBs << 12 is required
+    f.sad = (99 << 12) + 1
+    assert e.select_nal_unit_type() == NAL_IDR
+    f.sad = 0; e.curr_frame_count = 4
+    assert e.select_nal_unit_type() == NAL_IDR                       # currFrameCount % IntraEvery == 0

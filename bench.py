@@ -224,6 +224,7 @@ def main():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (the image prints the NCCL version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, K, Wu = args.seqs, args.steps, max(args.warmup, 3)
     G = max(1, min(args.groups, B))                      # sequence groups: one session + stream + host thread each

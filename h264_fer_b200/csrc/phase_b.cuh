@@ -263,12 +263,19 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         sh.pa[tid].n2 = 0; sh.pa[tid].n3 = 0; sh.pa[tid].s2_off = 0;
     }
     PB_STAMP(1);
-    // ---- wait for the dependencies (left; up-right, or up in the last column) -------------------------------
+    // ---- wait for the dependencies. `done[mb]` = epoch * 8 + number of 8x8 quadrants whose MV is final (4 when the MB is
+    //      finished or P_Skip). This MB's P_Skip test and partitions 0/1 need the left MB's quadrant 1 and the up-right
+    //      MB's quadrant 2 plus the complete MBs above / above-left; only partition 2 needs the left MB's quadrant 3. So a
+    //      macroblock starts when its left neighbour is HALF done: successive MBs of a row overlap by two partitions.
+    const uint32_t pbase = epoch * 8u;
     if (tid == 0) {
-        if (mbx > 0) while (ld_acquire_u32(&S.done[mb - 1]) != epoch) __nanosleep(20);
+        if (mbx > 0) while (ld_acquire_u32(&S.done[mb - 1]) < pbase + 2u) __nanosleep(20);
         if (mby > 0) {
-            const int d = mbx < g.Wmb - 1 ? mb - g.Wmb + 1 : mb - g.Wmb;
-            while (ld_acquire_u32(&S.done[d]) != epoch) __nanosleep(20);
+            if (mbx < g.Wmb - 1) while (ld_acquire_u32(&S.done[mb - g.Wmb + 1]) < pbase + 3u) __nanosleep(20);
+            // the MBs above and above-left must be complete; a P_Skip up-right neighbour does not imply it (it never
+            // waited for its own left neighbour to finish)
+            while (ld_acquire_u32(&S.done[mb - g.Wmb]) < pbase + 4u) __nanosleep(20);
+            if (mbx > 0) while (ld_acquire_u32(&S.done[mb - g.Wmb - 1]) < pbase + 4u) __nanosleep(20);
         }
     }
     __syncthreads();
@@ -317,7 +324,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             uint4 *d = (uint4 *)&S.motion[mb];
             const uint4 *s4 = (const uint4 *)&mo;
             d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
-            st_release_u32(&S.done[mb], epoch);
+            st_release_u32(&S.done[mb], pbase + 4u);
             atomicAdd(&S.status[ST_COUNTS + 0], 1u);
         }
         continue;
@@ -334,11 +341,22 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     const uint4 *__restrict__ Kf = S.kar + (size_t)f1 * g.WH;
     // neighbour quadrant MVs used by the 8x8 predictors, in registers (A.7): left q1/q3, up q2/q3, up-right q2, up-left q3
     const int aL = nc.avail[0], aU = nc.avail[1], aUR = nc.avail[2], aUL = nc.avail[3];
-    const int l1x = nc.mvx[0][1], l1y = nc.mvy[0][1], l3x = nc.mvx[0][3], l3y = nc.mvy[0][3];
+    const int l1x = nc.mvx[0][1], l1y = nc.mvy[0][1];
+    int l3x = 0, l3y = 0;                                            // left MB's quadrant 3: fetched before partition 2
     const int u2x = nc.mvx[1][2], u2y = nc.mvy[1][2], u3x = nc.mvx[1][3], u3y = nc.mvy[1][3];
     const int r2x = nc.mvx[2][2], r2y = nc.mvy[2][2], d3x = nc.mvx[3][3], d3y = nc.mvy[3][3];
     for (int pi = 0; pi < 4; pi++) {
         const int xP = mbx * 16 + (pi & 1) * 8, yP = mby * 16 + (pi >> 1) * 8;
+        if (pi == 2 && mbx > 0) {
+            // partition 2 predicts from the left MB's quadrant 3: now the left MB must be complete
+            if (tid == 0) {
+                while (ld_acquire_u32(&S.done[mb - 1]) < pbase + 4u) __nanosleep(20);
+                const int v = __ldcg((const int *)&S.motion[mb - 1].mv[3][0]);
+                nc.mvx[0][3] = (int16_t)(v & 0xffff); nc.mvy[0][3] = v >> 16;
+            }
+            __syncthreads();
+            l3x = nc.mvx[0][3]; l3y = nc.mvy[0][3];
+        }
         int mvpx, mvpy;
         // A = (px-1,py), B = (px,py-1), C = (px+8,py-1) else D = (px-1,py-1) for an 8x8 partition (mode_pred.cpp:113-161)
         if (pi == 0) median_pred(aL, l1x, l1y, aU, u2x, u2y, aU ? 1 : aUL, aU ? u3x : d3x, aU ? u3y : d3y, mvpx, mvpy);
@@ -505,6 +523,11 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             for (int rr2 = 0; rr2 < 8; rr2++) bs += sad_row8(*(const uint2 *)&sh.cur[(pi >> 1) * 8 + rr2][(pi & 1) * 8], pl, W, H, xP, yP + rr2);
         }
         mv[pi][0] = bx; mv[pi][1] = by; sadq[pi] = bs;
+        if (tid == 0 && pi < 3) {
+            // publish this quadrant's MV at once: the right and lower-left neighbours can start before this MB is finished
+            *(int *)&S.motion[mb].mv[pi][0] = (bx & 0xffff) | (by << 16);
+            st_release_u32(&S.done[mb], pbase + (uint32_t)pi + 1u);
+        }
         PB_STAMP(5 + pi);
         if (pi == 0) { q0x = bx; q0y = by; } else if (pi == 1) { q1x = bx; q1y = by; } else if (pi == 2) { q2x = bx; q2y = by; }
     }
@@ -538,7 +561,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         uint4 *d = (uint4 *)&S.motion[mb];
         const uint4 *s4 = (const uint4 *)&mo;
         d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
-        st_release_u32(&S.done[mb], epoch);          // release orders this thread's motion-record stores before the flag
+        st_release_u32(&S.done[mb], pbase + 4u);     // release orders this thread's motion-record stores before the flag
         PB_STAMP(9);
         atomicAdd(&S.status[ST_COUNTS + cnt], 1u);
     }

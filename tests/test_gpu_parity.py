@@ -214,3 +214,30 @@ def test_reference_undefined_input_is_reported_not_emulated():
         with pytest.raises(fh.Fh264Error) as e:
             s.encode_p(28, 16, 3)
         assert e.value.code == -5
+
+
+def test_wavefront_mix_of_skip_and_coded_macroblocks_is_exact_and_deterministic():
+    """640x480 with adaptive MAXDIFF gives a mix of P_Skip and coded MBs: stresses the fine-grained wavefront dependencies
+    (a P_Skip MB finishes early). Checked against the oracle and repeated for run-to-run determinism."""
+    w, h, qp, window = 640, 480, 30, 32
+    clip = synth.SynthClip(w, h, 77)
+    ref, cur = clip.frame(0), clip.frame(1)
+    o = port.Oracle(w, h)
+    assert not o.phase_r(ref[0])
+    want, want_recon = o.encode_p(cur, ref, qp, window, -1)
+    types = set(np.unique(want[:, 0]).tolist())
+    assert 31 in types and len(types) >= 3
+    first = None
+    for rep in range(4):
+        with fh.Session(w, h) as s:
+            s.upload_recon(0, *ref)
+            s.upload_source(0, *cur)
+            got = s.encode_p(qp, window, -1)[0]
+            recon = s.download_recon(0)
+        if first is None:
+            first = got.tobytes()
+            ints = fh.records_to_ints(got)
+            assert np.array_equal(ints, want), np.argwhere(ints != want)[:6]
+            assert all(np.array_equal(a, b) for a, b in zip(recon, want_recon))
+        else:
+            assert got.tobytes() == first, "run %d differs from run 0" % rep

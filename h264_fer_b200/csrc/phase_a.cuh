@@ -46,7 +46,7 @@ __device__ __forceinline__ void s3_decode(int i, int n3a, int w3, int g3, int w1
 
 struct S3Warp { WarpSelScratch ws; uint16_t members[FH_S3_MAX + 1]; uint16_t msad[FH_S3_MAX + 1]; };
 
-__global__ void __launch_bounds__(128, 4) k_stage3(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad)
+__global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,22 +66,22 @@ __global__ void __launch_bounds__(128, 4) k_stage3(const SeqDev *__restrict__ se
     const int n3a = w3 * w3, n3b = w1 * w1 * 16, N = n3a + n3b;
     const uint4 *__restrict__ K0p = S.kar;
     // first call: MEstimation(g = window/2, frac 0); arrival index = (dx + g3) * w3 + (dy + g3).
-    // Full 32-column chunks: lane = column (coalesced 16-byte loads), 8 rows in flight.
+    // Full 32-column chunks: lane = column (coalesced 16-byte loads), 4 rows in flight.
     const int ncf = w3 & ~31;
     for (int cb = 0; cb < ncf; cb += 32) {
         const int c = cb + lane, dx = c - g3, rx = xP + dx;
         const bool xok = rx >= 0 && rx < W;
         const int adx = iabs_(dx) + 4;
-        for (int r0 = 0; r0 < w3; r0 += 8) {
-            uint4 v[8];
+        for (int r0 = 0; r0 < w3; r0 += 4) {
+            uint4 v[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < 4; u++) {
                 const int ry = yP + r0 + u - g3;
                 v[u] = make_uint4(0, 0, 0, 1u);
                 if (xok && r0 + u < w3 && ry >= 0 && ry < H) v[u] = __ldg(K0p + (size_t)ry * W + rx);
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < 4; u++) {
                 const int r = r0 + u;
                 if (r < w3) cost[c * w3 + r] = v[u].w ? COST_INVALID : (uint32_t)((adx + iabs_(r - g3)) * feat_of(s, v[u]));
             }
@@ -99,20 +99,20 @@ __global__ void __launch_bounds__(128, 4) k_stage3(const SeqDev *__restrict__ se
         }
     }
     // second call: MEstimation(g = window/16, all 16 fractions); arrival = ((dx+g1)*w1 + (dy+g1))*16 + frac.
-    // lane -> (fraction = lane & 15, position parity = lane >> 4); 8 loads in flight
+    // lane -> (fraction = lane & 15, position parity = lane >> 4); 4 loads in flight
     {
         const int f = lane & 15, npos = w1 * w1, inv1 = 65536 / w1 + 1;
         const uint4 *__restrict__ Kf = S.kar + (size_t)f * g.WH;
-        for (int p0 = 0; p0 < npos; p0 += 16) {
-            uint4 v[8];
+        for (int p0 = 0; p0 < npos; p0 += 8) {
+            uint4 v[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < 4; u++) {
                 const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), rx = xP + cx - g1, ry = yP + pos - cx * w1 - g1;
                 v[u] = make_uint4(0, 0, 0, 1u);
                 if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) v[u] = __ldg(Kf + (size_t)ry * W + rx);
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < 4; u++) {
                 const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), dx = cx - g1, dy = pos - cx * w1 - g1;
                 if (pos < npos) cost[n3a + pos * 16 + f] = v[u].w ? COST_INVALID : (uint32_t)((iabs_(dx) + iabs_(dy) + 4) * feat_of(s, v[u]));
             }

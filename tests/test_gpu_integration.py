@@ -60,3 +60,17 @@ def test_bitstream_matches_live_reference(tmp_path, w, h, seed, frames, qp, wind
     run_b200_encoder(y4m, out, "-", frames, qp, 0, window, maxdiff, intra_every=intra_every)
     assert "P" in summ["types"]
     assert open(out, "rb").read() == open(ref264, "rb").read(), "bitstreams differ (%s)" % summ["types"]
+
+
+@needs_binary
+@pytest.mark.skipif(not refdump.have_ref_encoder(), reason="compiled reference not present")
+def test_720p_window32_bitstream_matches_live_reference(tmp_path):
+    """BASELINE config 3 geometry (1280x720, +-16 search): 1 I + 2 P pictures, byte-identical bitstream."""
+    y4m = str(tmp_path / "in.y4m")
+    synth.write_y4m(y4m, 1280, 720, 3, 3)
+    ref264 = str(tmp_path / "ref.264")
+    summ, _, _ = refdump.run_reference(y4m, 3, qp=28, window=32, maxdiff=3, out_264=ref264)
+    out = str(tmp_path / "b200.264")
+    run_b200_encoder(y4m, out, "-", 3, 28, 0, 32, 3)
+    assert summ["types"] == "IPP"
+    assert open(out, "rb").read() == open(ref264, "rb").read()

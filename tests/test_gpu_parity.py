@@ -241,3 +241,28 @@ def test_wavefront_mix_of_skip_and_coded_macroblocks_is_exact_and_deterministic(
             assert all(np.array_equal(a, b) for a, b in zip(recon, want_recon))
         else:
             assert got.tobytes() == first, "run %d differs from run 0" % rep
+
+
+def test_1080p_picture_against_oracle():
+    """BASELINE's full size (1920x1080 input -> coded 1920x1072, WindowSize 32): one P picture, every record and the
+    reconstruction against the oracle (the reference itself needs ~22 s per 1080p picture; the pinned port ~10 s)."""
+    clip = synth.SynthClip(1920, 1080, 100)
+    fr = [tuple(synth.crop16(p, chroma=(i > 0)) for i, p in enumerate(clip.frame(t))) for t in range(2)]
+    h, w = fr[0][0].shape
+    assert (w, h) == (1920, 1072)
+    o = port.Oracle(w, h)
+    assert not o.phase_r(fr[0][0])
+    want, want_recon = o.encode_p(fr[1], fr[0], 28, 32, 3)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, *fr[0])
+        s.upload_source(0, *fr[1])
+        assert s.scene_sad(0) == port.scene_sad(fr[1][0], fr[0][0])
+        got = fh.records_to_ints(s.encode_p(28, 32, 3)[0])
+        recon = s.download_recon(0)
+        counts = s.mode_counts(0)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:6]
+    assert all(np.array_equal(a, b) for a, b in zip(recon, want_recon))
+    assert sum(counts) == got.shape[0] == 8040
+    # size-independent property: P_Skip macroblocks carry no levels and reconstruct to the prediction-only picture
+    skip = got[:, 0] == 31
+    assert not got[skip, 9:].any()

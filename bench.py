@@ -204,7 +204,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seqs", type=int, default=8, help="independent sequences per GPU")
-    ap.add_argument("--groups", type=int, default=4, help="sequence groups per GPU (session + stream + host thread each)")
+    ap.add_argument("--groups", type=int, default=1, help="sequence groups per GPU (session + stream + host thread each)")
     ap.add_argument("--threaded", action="store_true", help="drive even a single group from a worker thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -25,7 +25,7 @@
 #define ST_SAD_HI 9
 #define ST_TICKET 10
 #define ST_FLAGS_NEXT 11   // flags raised by phase R for the NEXT picture's reference
-#define ST_S2REDO 12       // set when some partition overflowed the fast stage-2 launch
+#define ST_S2REDO 12       // number of partitions that overflowed the fast stage-2 launch
 #define ST_WORDS 16
 #define FLAG_UB_INPUT 1u
 #define FLAG_CAPACITY 2u
@@ -63,6 +63,7 @@ struct SeqDev {
     S3Entry *s3;            // nparts * 33
     uint2 *s2pool;          // stage-2 candidates in arrival order: {dx | dy<<16, feat | sad<<18}
     uint32_t s2pool_size;
+    uint32_t *s2redo;       // partitions whose gated survivors overflowed the fast stage-2 launch (count in status[ST_S2REDO])
     MbMotion *motion;       // nmb
     uint32_t *done;         // nmb: epoch of the picture whose motion record is final
     fh264_mb_result *results;

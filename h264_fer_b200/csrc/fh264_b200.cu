@@ -153,8 +153,9 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         OPEN_CK(dalloc(s, &S.tstart, (size_t)g.ntiles * FH_TSTART_PITCH));
         OPEN_CK(dalloc(s, &S.parta, (size_t)g.nparts));
         OPEN_CK(dalloc(s, &S.s3, (size_t)g.nparts * FH_S3_MAX));
-        S.s2pool_size = (uint32_t)std::min<size_t>((size_t)g.nparts * 320, 0x7fffffffu);
+        S.s2pool_size = (uint32_t)std::min<size_t>((size_t)g.nparts * 1024, 0x7fffffffu);   // worst case: 1023 candidates per partition
         OPEN_CK(dalloc(s, &S.s2pool, (size_t)S.s2pool_size));
+        OPEN_CK(dalloc(s, &S.s2redo, (size_t)S2_REDO_MAX));
         OPEN_CK(dalloc(s, &S.motion, (size_t)g.nmb));
         OPEN_CK(dalloc(s, &S.done, (size_t)g.nmb));
         OPEN_CK(dalloc(s, &S.status, (size_t)ST_WORDS));
@@ -311,7 +312,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         CK(cudaEventRecord(s->evk[0], st));
         k_stage2<S2_CAP_FAST, 2, false><<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
         // partitions with more than S2_CAP_FAST gated survivors (marked) are redone with the large buffers; every other warp exits at once
-        dim3 g2r(g.nparts, nseq);
+        dim3 g2r(S2_REDO_MAX, nseq);
         k_stage2<S2_CAP_BIG, 1, true><<<g2r, 32, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
     CK(cudaEventRecord(s->ev[1], st));
@@ -352,7 +353,7 @@ extern "C" int fh264_picture_status(fh264_session *s, int seq)
     CK(cudaStreamSynchronize(s->stream));
     const uint32_t f = s->h_status[(size_t)seq * ST_WORDS + ST_FLAGS];
     if (f & FLAG_UB_INPUT) return fail(FH264_E_UB_INPUT, "reference picture has an 8x8 window sum of 0 or >= 16203: undefined in the reference (moestimation.cpp:153-158,477-480)");
-    if (f & FLAG_CAPACITY) return fail(FH264_E_CAPACITY, "stage-2 candidate capacity exceeded (flat content)");
+    if (f & FLAG_CAPACITY) return fail(FH264_E_CAPACITY, "stage-2 candidate capacity exceeded: a partition has more than 1023 candidates up to j_stop (flat content)");
     return FH264_OK;
 }
 
@@ -364,6 +365,18 @@ extern "C" int fh264_mode_counts(fh264_session *s, int seq, int32_t counts[5])
     CK(cudaStreamSynchronize(s->stream));
     // device counters: [0] skip, [1] 16x16, [2] 16x8, [3] 8x16, [4] 8x8 == brojTipova order
     for (int i = 0; i < 5; i++) counts[i] = (int32_t)s->h_status[(size_t)seq * ST_WORDS + ST_COUNTS + i];
+    return FH264_OK;
+}
+
+// Snapshot of the 16 status words of sequence seq taken after phase C of its last encode_p (tests / diagnostics):
+// [0] flags, [1] stage-2 pool entries used, [2..6] mode counts, [12] partitions redone by the large stage-2 launch.
+extern "C" int fh264_debug_status(fh264_session *s, int seq, uint32_t out[16])
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!out) return fail(FH264_E_ARG, "null output");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    memcpy(out, s->h_status + (size_t)seq * ST_WORDS, sizeof(uint32_t) * ST_WORDS);
     return FH264_OK;
 }
 

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
 #define S2_CHUNK_CAP 512      // a round of 32 short ranges (<= 64 entries each) adds at most 256 chunks
 #define S2_CAP_FAST 512       // gated survivors per partition held by the main launch
 #define S2_CAP_BIG 4096       // ... and by the fallback launch (beyond: FH264_E_CAPACITY)
-#define S2_REDO 0xffffffffu   // PartA::n2 marker: partition left to the fallback launch
+#define S2_REDO_MAX 1024      // partitions per picture the fallback launch can take over
 
 template <int CAP>
 struct S2Warp {
@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ s
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     S2Warp<CAP> *w = &sm[warp];
     const SeqDev &S = seqs[seq0 + blockIdx.y];
-    const int part = blockIdx.x * NW + warp;
-    if (REDO && (S.status[ST_S2REDO] == 0 || S.parta[part].n2 != S2_REDO)) return;
+    // REDO launch: CTA b takes the b-th partition the main launch listed as overflowing (usually none: exit at once)
+    if (REDO && blockIdx.x >= min(S.status[ST_S2REDO], (uint32_t)S2_REDO_MAX)) return;
+    const int part = REDO ? (int)S.s2redo[blockIdx.x] : blockIdx.x * NW + warp;
     int xP, yP;
     part_origin(g, part, xP, yP);
     uint2 rows[8];
@@ -207,18 +208,59 @@ __global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ s
     const int k1lo = max(0, s[1] - 99) >> 6, k1hi = min(8191, s[1] + 99) >> 6;
     const int ntiles = ntx * nty, inv_ntx = 65536 / ntx + 1;
     const uint4 *__restrict__ tent = (const uint4 *)S.tent;
-    // gate of one index entry (:481); survivors only record their arrival key and entry number here — the feature
-    // distance and the (j, side) histogram are computed afterwards in a dense pass (no divergent heavy code)
+    // gate of one index entry (:481). Gated entries are counted per (j, side); they are KEPT only while j <= jb, a running
+    // upper bound of j_stop (counts only grow, so the first j whose running total exceeds 128 can only move down). The
+    // feature distance is computed afterwards in a dense pass over the kept entries.
+    int jb = 180;
     auto visit = [&](const uint4 v, uint32_t eidx) {
         const int x = v.x & 0xffff, y = v.x >> 16, k0 = v.y & 0xffff, k1 = v.y >> 16, k2 = v.z & 0xffff;
         const int j = iabs_(k0 - s[0]), dx = x - xP, dy = y - yP;
         if (j <= 180 && iabs_(dx) + iabs_(dy) < 280 && iabs_(k1 - s[1]) < 100 && iabs_(k2 - s[2]) < 100) {
-            const int pos = atomicAdd(&w->n_surv, 1);
-            if (pos < CAP) {
-                w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)(k0 > s[0]) << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
-                w->aval[pos] = eidx;
+            const int side = k0 > s[0];
+            atomicAdd(&w->bins[2 * j + side], 1u);
+            if (j <= jb) {
+                const int pos = atomicAdd(&w->n_surv, 1);
+                if (pos < CAP) {
+                    w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
+                    w->aval[pos] = eidx;
+                }
             }
         }
+    };
+    // j_stop bound from the counts so far: first j whose running gated count (bucket s0 twice) exceeds 128 (:496)
+    auto bound_from_bins = [&]() -> int {
+        uint32_t local = 0, c6[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { c6[i] = w->bins[lane * 12 + 2 * i] + w->bins[lane * 12 + 2 * i + 1]; if (lane == 0 && i == 0) c6[i] *= 2; local += c6[i]; }
+        uint32_t incl = local;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        uint32_t run = incl - local;
+        int first = 180;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { run += c6[i]; if (run > 128 && first == 180) first = min(180, lane * 6 + i); }
+        return __reduce_min_sync(0xffffffffu, first);
+    };
+    // keep the kept-entry buffer from overflowing: tighten jb and drop entries beyond it (called at warp-uniform points)
+    auto tighten = [&]() {
+        __syncwarp();
+        if (w->n_surv <= CAP - 256) return;
+        const int nb = bound_from_bins();
+        const int n = min(w->n_surv, CAP);
+        int outn = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const uint32_t k = i < n ? w->akey[i] : 0xffffffffu, e = i < n ? w->aval[i] : 0u;
+            const bool keep = i < n && (int)(k >> 21) <= nb;
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) { const int p = outn + __popc(b & ((1u << lane) - 1u)); w->akey[p] = k; w->aval[p] = e; }
+            outn += __popc(b);
+        }
+        __syncwarp();
+        // entries lost to an overflow since the last call cannot be recovered: poison the count so the partition is redone
+        if (lane == 0) w->n_surv = (w->n_surv > CAP) ? 0x40000000 : outn;
+        jb = nb;
+        __syncwarp();
     };
     int nchunk = 0;
     const int nitems = ntiles * 4;
@@ -243,7 +285,8 @@ __global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ s
             longm &= longm - 1;
             const uint32_t gb = __shfl_sync(0xffffffffu, gbase, src);
             const int ln = __shfl_sync(0xffffffffu, len, src);
-            for (int e = lane; e < ln; e += 32) visit(__ldg(tent + gb + e), gb + e);
+            for (int e0 = 0; e0 < ln; e0 += 32) { if (e0 + lane < ln) visit(__ldg(tent + gb + e0 + lane), gb + e0 + lane); if ((e0 & 255) == 224) tighten(); }
+            tighten();
             if (lane == src) len = 0;
         }
         // short ranges: chunks of <= 8 consecutive entries (one 128-byte line): first entry | (count - 1) << 28
@@ -256,14 +299,16 @@ __global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ s
         __syncwarp();
         if (nchunk > S2_CHUNK_CAP - 256 || it0 + 32 >= nitems) {
             // lanes stride the chunk list: balanced work, 8 sequential 16-byte loads in flight
-            for (int cidx = lane; cidx < nchunk; cidx += 32) {
-                const uint32_t cw = w->chunk[cidx], e0 = cw & 0x0fffffffu;
-                const int cnt = (int)(cw >> 28) + 1;
+            for (int c0 = 0; c0 < nchunk; c0 += 32) {
+                const int cidx = c0 + lane;
+                const uint32_t cw = cidx < nchunk ? w->chunk[cidx] : 0u, e0 = cw & 0x0fffffffu;
+                const int cnt = cidx < nchunk ? (int)(cw >> 28) + 1 : 0;
                 uint4 v[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++) v[u] = u < cnt ? __ldg(tent + e0 + u) : make_uint4(0, 0xffffu, 0, 0);
 #pragma unroll
                 for (int u = 0; u < 8; u++) visit(v[u], e0 + u);
+                tighten();                                  // at most 256 entries were added since the last check
             }
             nchunk = 0;
             __syncwarp();
@@ -276,16 +321,17 @@ __global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ s
         if (lane == 0) {
             PartA *pa = &S.parta[part];
             pa->s2_off = 0;
-            if (!REDO) pa->n2 = S2_REDO; else { pa->n2 = 0; atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); }
-            if (!REDO) atomicOr(&S.status[ST_S2REDO], 1u);
+            pa->n2 = 0;
+            bool listed = false;
+            if (!REDO) { const uint32_t k = atomicAdd(&S.status[ST_S2REDO], 1u); if (k < S2_REDO_MAX) { S.s2redo[k] = (uint32_t)part; listed = true; } }
+            if (!listed) atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY);
         }
         return;
     }
-    // dense pass over the survivors: feature distance (:267-276) and the (j, side) histogram
+    // dense pass over the kept entries: feature distance (:267-276)
     for (int i = lane; i < ns; i += 32) {
         const uint4 v = __ldg(tent + w->aval[i]);
         w->aval[i] = (uint32_t)feat_dist(s, (int)(v.y & 0xffff), (int)(v.y >> 16), (int)(v.z & 0xffff), (int)(v.z >> 16), (int)(v.w & 0xffff));
-        atomicAdd(&w->bins[w->akey[i] >> 20], 1u);
     }
     __syncwarp();
     // j_stop: first j at which the running gated count exceeds 128 (:496), else 180. Bucket s0 is visited by both

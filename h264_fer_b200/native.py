@@ -22,7 +22,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
-           "fh264_debug_feature", "fh264_last_timings", "fh264_debug_timeline"]
+           "fh264_debug_feature", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status"]
 
 
 class Fh264Error(RuntimeError):
@@ -77,6 +77,7 @@ def load_library():
     L.fh264_debug_feature.argtypes = [vp, i32, i32, i32, vp]
     L.fh264_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.fh264_debug_timeline.argtypes = [vp, i32, vp]
+    L.fh264_debug_status.argtypes = [vp, i32, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
@@ -247,6 +248,11 @@ class Session:
             return None
         out = np.zeros((self.nmb, 24), np.int64)
         self._ck(self.L.fh264_debug_timeline(self.handle, seq, _ptr(out)))
+        return out
+
+    def debug_status(self, seq):
+        out = np.zeros(16, np.uint32)
+        self._ck(self.L.fh264_debug_status(self.handle, seq, _ptr(out)))
         return out
 
     def debug_plane(self, seq, f):

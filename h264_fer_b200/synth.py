@@ -24,9 +24,9 @@ def _box5(a: np.ndarray) -> np.ndarray:
 class SynthClip:
     """Frame generator: ``clip.frame(t) -> (Y, Cb, Cr)`` uint8 arrays of the *input* size (before crop)."""
 
-    def __init__(self, width: int, height: int, seed: int, pan=(2, 1), noise=1.0, square=True):
+    def __init__(self, width: int, height: int, seed: int, pan=(2, 1), noise=1.0, square=True, contrast=1.0):
         self.w, self.h, self.seed = int(width), int(height), int(seed)
-        self.pan, self.noise, self.square = pan, float(noise), bool(square)
+        self.pan, self.noise, self.square, self.contrast = pan, float(noise), bool(square), float(contrast)
         rng = np.random.default_rng(seed)
         gh, gw = self.h // 8 + 40, self.w // 8 + 40
         grid = rng.integers(40, 200, size=(gh, gw), dtype=np.int32)
@@ -39,6 +39,8 @@ class SynthClip:
         rows = (np.arange(h) + oy) % ch
         cols = (np.arange(w) + ox) % cw
         y = self.canvas[np.ix_(rows, cols)].astype(np.float64)
+        if self.contrast != 1.0:
+            y = 128.0 + (y - 128.0) * self.contrast
         # moving inverted square
         sx = (16 + 5 * t) % max(1, w - 32)
         sy = (h // 3 + 3 * t) % max(1, h - 32)

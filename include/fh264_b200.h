@@ -154,6 +154,10 @@ int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out);
  * [5] k_stage3, [6] k_stage2, [7] k_interp, [8] k_features, [9] k_tile_index. */
 int fh264_last_timings(fh264_session *s, float ms[10]);
 
+/* Snapshot of the 16 status words of sequence seq after phase C of its last encode_p: [0] flags, [1] stage-2 pool
+ * entries used, [2..6] mode counts, [12] partitions redone by the large-buffer stage-2 launch. */
+int fh264_debug_status(fh264_session *s, int seq, uint32_t out[16]);
+
 /* Debug: clock64() samples of the phase-B wavefront, 12 int64 per macroblock of sequence seq ([0] CTA start,
  * [1] prefetch issued, [2] dependencies satisfied, [3] neighbour MVs loaded, [4] P_Skip decided, [5..8] partitions
  * decided, [9] published). Call with out == NULL to enable sampling, with a buffer to read the last picture back. */

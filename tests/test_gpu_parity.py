@@ -266,3 +266,24 @@ def test_1080p_picture_against_oracle():
     # size-independent property: P_Skip macroblocks carry no levels and reconstruct to the prediction-only picture
     skip = got[:, 0] == 31
     assert not got[skip, 9:].any()
+
+
+@pytest.mark.parametrize("contrast,noise", [(0.06, 0.5), (0.15, 1.0)])
+def test_low_contrast_content_many_gated_candidates(contrast, noise):
+    """Low-contrast pictures gate tens of thousands of stage-2 positions per partition (dense 8x8 sums); only those up to
+    j_stop are candidates. Exercises the running j_stop bound / compaction of k_stage2 against the oracle."""
+    w, h, qp, window = 320, 240, 28, 16
+    clip = synth.SynthClip(w, h, 5, contrast=contrast, noise=noise, square=False)
+    ref, cur = clip.frame(0), clip.frame(1)
+    o = port.Oracle(w, h)
+    assert not o.phase_r(ref[0])
+    want, want_recon = o.encode_p(cur, ref, qp, window, 3)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, *ref)
+        s.upload_source(0, *cur)
+        got = fh.records_to_ints(s.encode_p(qp, window, 3)[0])       # raises on FH264_E_CAPACITY
+        recon = s.download_recon(0)
+        st = s.debug_status(0)
+    assert st[0] == 0, "status flags %d" % st[0]
+    assert np.array_equal(got, want), np.argwhere(got != want)[:6]
+    assert all(np.array_equal(a, b) for a, b in zip(recon, want_recon))

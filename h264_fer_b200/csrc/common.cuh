@@ -29,11 +29,15 @@
 #define ST_WORDS 16
 #define FLAG_UB_INPUT 1u
 #define FLAG_CAPACITY 2u
+#define FLAG_TIMEOUT 4u      // a bounded wavefront / cross-GPU wait gave up (peer rank missing or far behind)
 
 struct Geo {
     int W, H, Wmb, Hmb, nmb, nparts, tilesx, tilesy, ntiles;
     int WH;
+    // macroblock-row band of this rank (band mode): MBs [band_mb0, band_mb0 + band_nmb); whole picture otherwise
+    int band_mb0, band_nmb, rank, world;
 };
+#define FH_MAX_WORLD 8
 
 struct __align__(16) TileEntry { uint16_t x, y, k0, k1, k2, k3, k4, pad; };
 
@@ -68,6 +72,10 @@ struct SeqDev {
     uint32_t *done;         // nmb: epoch of the picture whose motion record is final
     fh264_mb_result *results;
     uint32_t *status;       // ST_WORDS
+    // band mode: the same buffers of the other ranks, mapped through CUDA IPC (NVLink peer access)
+    uint8_t *peer_ref[FH_MAX_WORLD][3], *peer_rec[FH_MAX_WORLD][3];
+    MbMotion *peer_motion_next;   // rank + 1: mirror of the band's last MB row (quadrant MVs)
+    uint32_t *peer_done_next;     // rank + 1: mirror of the band's last MB row (wavefront progress)
     long long *dbg;         // optional: nmb * 12 clock samples of phase B (fh264_debug_timeline), else null
 };
 

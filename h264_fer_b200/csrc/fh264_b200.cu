@@ -26,6 +26,8 @@ static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(FH264_E_CUDA, #call, e_); } while (0)
 #define CKL() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(FH264_E_CUDA, "kernel launch", e_); } while (0)
 
+struct PeerSync { uint32_t *p[FH_MAX_WORLD]; };
+
 struct fh264_session {
     Geo g;
     int batch, device;
@@ -46,6 +48,10 @@ struct fh264_session {
     std::vector<void *> allocs;
     // scratch for the stand-alone entry points
     uint8_t *d_scr[3]; int16_t *d_scr16[2]; size_t scr_mbs;
+    // band mode
+    uint32_t *d_sync;               // FH_MAX_WORLD arrival slots (written by the peers)
+    PeerSync peer_sync;             // every rank's sync area (own included)
+    std::vector<void *> ipc_opened;
 };
 
 __global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
@@ -68,6 +74,19 @@ __global__ void k_swap_ref(SeqDev *seqs, int seq0)
 {
     SeqDev &S = seqs[seq0 + threadIdx.x];
     for (int c = 0; c < 3; c++) { uint8_t *t = S.ref[c]; S.ref[c] = S.rec[c]; S.rec[c] = t; }
+    for (int r = 0; r < FH_MAX_WORLD; r++)
+        for (int c = 0; c < 3; c++) { uint8_t *t = S.peer_ref[r][c]; S.peer_ref[r][c] = S.peer_rec[r][c]; S.peer_rec[r][c] = t; }
+}
+
+// Band mode: all ranks' reconstructed bands must have landed in this rank's picture before phase R reads it.
+// One thread: announce "my phase C of picture `epoch` is complete" in every rank's sync area, then wait (bounded) for all.
+__global__ void k_band_barrier(PeerSync ps, uint32_t *status, uint32_t epoch, int rank, int world)
+{
+    __threadfence_system();
+    for (int r = 0; r < world; r++) st_release_sys_u32(&ps.p[r][rank], epoch);
+    bool ok = true;
+    for (int r = 0; r < world; r++) ok &= wait_progress(&ps.p[rank][r], epoch, true);
+    if (!ok) atomicOr(&status[ST_FLAGS_NEXT], FLAG_TIMEOUT);
 }
 
 template <typename T>
@@ -88,6 +107,7 @@ extern "C" int fh264_close(fh264_session *s)
     if (!s) return FH264_OK;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
+    for (void *p : s->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : s->allocs) cudaFree(p);
     for (int i = 0; i < 3; i++) if (s->d_scr[i]) cudaFree(s->d_scr[i]);
     for (int i = 0; i < 2; i++) if (s->d_scr16[i]) cudaFree(s->d_scr16[i]);
@@ -118,6 +138,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
 
     fh264_session *s = new fh264_session();
     s->batch = batch; s->device = device; s->epoch = 0; s->timed = false; s->own_stream = true;
+    s->d_sync = nullptr; memset(&s->peer_sync, 0, sizeof s->peer_sync);
     s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->d_sadout = nullptr; s->scr_mbs = 0;
     for (int i = 0; i < 5; i++) s->ev[i] = nullptr;
     for (int i = 0; i < 4; i++) s->evk[i] = nullptr;
@@ -127,6 +148,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     g.W = width; g.H = height; g.Wmb = width >> 4; g.Hmb = height >> 4; g.nmb = g.Wmb * g.Hmb; g.nparts = g.nmb * 4;
     g.tilesx = (width + FH_TILE - 1) / FH_TILE; g.tilesy = (height + FH_TILE - 1) / FH_TILE; g.ntiles = g.tilesx * g.tilesy;
     g.WH = width * height;
+    g.band_mb0 = 0; g.band_nmb = g.nmb; g.rank = 0; g.world = 1;
     s->has_ref.assign(batch, 0);
     s->h.resize(batch);
 #define OPEN_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(FH264_E_CUDA, #call, e_); fh264_close(s); return FH264_E_CUDA; } } while (0)
@@ -161,6 +183,8 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         OPEN_CK(dalloc(s, &S.status, (size_t)ST_WORDS));
         S.results = results + (size_t)b * g.nmb;
         S.dbg = nullptr;
+        memset(S.peer_ref, 0, sizeof S.peer_ref); memset(S.peer_rec, 0, sizeof S.peer_rec);
+        S.peer_motion_next = nullptr; S.peer_done_next = nullptr;
     }
     OPEN_CK(dalloc(s, &s->d_seqs, (size_t)batch));
     OPEN_CK(cudaMemcpy(s->d_seqs, s->h.data(), sizeof(SeqDev) * batch, cudaMemcpyHostToDevice));
@@ -172,6 +196,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     OPEN_CK(dalloc(s, &s->d_wf_order, (size_t)g.nmb));
     OPEN_CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.nmb, cudaMemcpyHostToDevice));
     OPEN_CK(dalloc(s, &s->d_ticket, (size_t)4));
+    OPEN_CK(dalloc(s, &s->d_sync, (size_t)FH_MAX_WORLD));
     OPEN_CK(cudaFuncSetAttribute(k_tile_index, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_CELLS * 4));
     OPEN_CK(cudaFuncSetAttribute(k_stage3, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     OPEN_CK(cudaDeviceSynchronize());
@@ -307,7 +332,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         const int n3 = (2 * g3 + 1) * (2 * g3 + 1) + (2 * g1 + 1) * (2 * g1 + 1) * 16;
         const int npad = (n3 + 31) & ~31;
         const size_t smem3 = 4 * sizeof(S3Warp) + (size_t)4 * npad * sizeof(uint32_t);
-        dim3 g3d(g.nparts / 4, nseq), g2d(g.nparts / 2, nseq);
+        dim3 g3d(g.band_nmb, nseq), g2d(g.band_nmb * 2, nseq);          // 4 / 2 partitions per CTA
         k_stage3<<<g3d, 128, smem3, st>>>(s->d_seqs, seq0, g, prm, npad);
         CK(cudaEventRecord(s->evk[0], st));
         k_stage2<S2_CAP_FAST, 2, false><<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
@@ -317,21 +342,29 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     }
     CK(cudaEventRecord(s->ev[1], st));
     // persistent wavefront CTAs: about one anti-diagonal (Wmb/2) plus slack per sequence
-    const unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.nmb * nseq, (long long)nseq * (g.Wmb / 2 + 8));
+    const unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, (long long)nseq * (g.Wmb / 2 + 8));
     k_phase_b<<<pb_ctas, PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
     CK(cudaEventRecord(s->ev[2], st));
-    dim3 gc((g.nmb + 3) / 4, nseq);
+    dim3 gc((g.band_nmb + 3) / 4, nseq);
     k_phase_c<<<gc, 128, 0, st>>>(s->d_seqs, seq0, g, prm);
     CKL();
     CK(cudaEventRecord(s->ev[3], st));
     for (int b = seq0; b < seq0 + nseq; b++)
         CK(cudaMemcpyAsync(s->h_status + (size_t)b * ST_WORDS, s->h[b].status, sizeof(uint32_t) * ST_WORDS, cudaMemcpyDeviceToHost, st));
     if (results)
-        CK(cudaMemcpyAsync(results, s->h[seq0].results, sizeof(fh264_mb_result) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, st));
+    {
+        if (g.world == 1) CK(cudaMemcpyAsync(results, s->h[seq0].results, sizeof(fh264_mb_result) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, st));
+        else for (int b = 0; b < nseq; b++)      // band mode: only this rank's band of every sequence is valid
+            CK(cudaMemcpyAsync(results + (size_t)b * g.nmb + g.band_mb0, s->h[seq0 + b].results + g.band_mb0, sizeof(fh264_mb_result) * (size_t)g.band_nmb, cudaMemcpyDeviceToHost, st));
+    }
     // dpb := reconstruction (frameDeepCopy, ref_frames.cpp:17-35) by pointer swap, then phase R for the next picture
+    if (g.world > 1) k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->h[seq0].status, s->epoch, g.rank, g.world);
     k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
     for (int b = seq0; b < seq0 + nseq; b++)
-        for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
+        {
+            for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
+            for (int r = 0; r < FH_MAX_WORLD; r++) for (int c = 0; c < 3; c++) std::swap(s->h[b].peer_ref[r][c], s->h[b].peer_rec[r][c]);
+        }
     rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
     CK(cudaEventRecord(s->ev[4], st));
     s->timed = true;
@@ -353,6 +386,7 @@ extern "C" int fh264_picture_status(fh264_session *s, int seq)
     CK(cudaStreamSynchronize(s->stream));
     const uint32_t f = s->h_status[(size_t)seq * ST_WORDS + ST_FLAGS];
     if (f & FLAG_UB_INPUT) return fail(FH264_E_UB_INPUT, "reference picture has an 8x8 window sum of 0 or >= 16203: undefined in the reference (moestimation.cpp:153-158,477-480)");
+    if (f & FLAG_TIMEOUT) return fail(FH264_E_STATE, "a wavefront / cross-GPU wait timed out (band mode: is every rank encoding the same picture?)");
     if (f & FLAG_CAPACITY) return fail(FH264_E_CAPACITY, "stage-2 candidate capacity exceeded: a partition has more than 1023 candidates up to j_stop (flat content)");
     return FH264_OK;
 }
@@ -524,5 +558,70 @@ extern "C" int fh264_debug_timeline(fh264_session *s, int seq, long long *out)
         CK(cudaMemcpy(&s->d_seqs[seq], &s->h[seq], sizeof(SeqDev), cudaMemcpyHostToDevice));
     }
     if (out) CK(cudaMemcpy(out, s->h[seq].dbg, n * sizeof(long long), cudaMemcpyDeviceToHost));
+    return FH264_OK;
+}
+
+// ---- band mode (BASELINE config 4): one picture split into macroblock-row bands over the ranks of a node.
+// Every rank keeps the whole reference picture; phases A/B/C run on the band only. The wavefront crosses GPUs through
+// mirrored progress flags (phase B writes the band's last MB row into the next rank's memory), the reconstruction exchange
+// is fused into phase C (peer stores), k_band_barrier separates pictures. Buffers are shared with CUDA IPC.
+extern "C" int fh264_band_config(fh264_session *s, int rank, int world, int mb_row0, int mb_row1)
+{
+    if (!s) return fail(FH264_E_ARG, "null session");
+    if (world < 1 || world > FH_MAX_WORLD || rank < 0 || rank >= world) return fail(FH264_E_ARG, "rank/world out of range (at most 8 ranks)");
+    if (mb_row0 < 0 || mb_row1 <= mb_row0 || mb_row1 > s->g.Hmb) return fail(FH264_E_ARG, "empty or out-of-range macroblock-row band");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    Geo &g = s->g;
+    g.rank = rank; g.world = world; g.band_mb0 = mb_row0 * g.Wmb; g.band_nmb = (mb_row1 - mb_row0) * g.Wmb;
+    // wavefront order restricted to the band
+    std::vector<int> order(g.band_nmb);
+    for (int i = 0; i < g.band_nmb; i++) order[i] = g.band_mb0 + i;
+    const int Wmb = g.Wmb;
+    std::stable_sort(order.begin(), order.end(), [Wmb](int a, int b) { return (a % Wmb) + 2 * (a / Wmb) < (b % Wmb) + 2 * (b / Wmb); });
+    CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.band_nmb, cudaMemcpyHostToDevice));
+    s->peer_sync.p[rank] = s->d_sync;
+    for (int b = 0; b < s->batch; b++)
+        for (int c = 0; c < 3; c++) { s->h[b].peer_ref[rank][c] = s->h[b].ref[c]; s->h[b].peer_rec[rank][c] = s->h[b].rec[c]; }
+    CK(cudaMemcpy(s->d_seqs, s->h.data(), sizeof(SeqDev) * s->batch, cudaMemcpyHostToDevice));
+    return FH264_OK;
+}
+
+// handles: FH264_IPC_HANDLES x 64 bytes = ref[3], rec[3], motion, done, sync
+extern "C" int fh264_ipc_export(fh264_session *s, int seq, uint8_t *handles)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!handles) return fail(FH264_E_ARG, "null output");
+    CK(cudaSetDevice(s->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == FH264_IPC_HANDLE_BYTES, "IPC handle size");
+    const SeqDev &S = s->h[seq];
+    void *ptrs[FH264_IPC_HANDLES] = { S.ref[0], S.ref[1], S.ref[2], S.rec[0], S.rec[1], S.rec[2], S.motion, S.done, s->d_sync };
+    for (int i = 0; i < FH264_IPC_HANDLES; i++) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ptrs[i]));
+        memcpy(handles + (size_t)i * FH264_IPC_HANDLE_BYTES, &h, FH264_IPC_HANDLE_BYTES);
+    }
+    return FH264_OK;
+}
+
+extern "C" int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const uint8_t *handles)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!handles || peer_rank < 0 || peer_rank >= s->g.world || peer_rank == s->g.rank) return fail(FH264_E_ARG, "bad peer rank / handles");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    void *ptrs[FH264_IPC_HANDLES];
+    for (int i = 0; i < FH264_IPC_HANDLES; i++) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)i * FH264_IPC_HANDLE_BYTES, FH264_IPC_HANDLE_BYTES);
+        if (i == FH264_IPC_HANDLES - 1 && s->peer_sync.p[peer_rank]) { ptrs[i] = s->peer_sync.p[peer_rank]; continue; }   // sync area: once per peer
+        CK(cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
+        s->ipc_opened.push_back(ptrs[i]);
+    }
+    SeqDev &S = s->h[seq];
+    for (int c = 0; c < 3; c++) { S.peer_ref[peer_rank][c] = (uint8_t *)ptrs[c]; S.peer_rec[peer_rank][c] = (uint8_t *)ptrs[3 + c]; }
+    if (peer_rank == s->g.rank + 1) { S.peer_motion_next = (MbMotion *)ptrs[6]; S.peer_done_next = (uint32_t *)ptrs[7]; }
+    s->peer_sync.p[peer_rank] = (uint32_t *)ptrs[8];
+    CK(cudaMemcpy(&s->d_seqs[seq], &S, sizeof(SeqDev), cudaMemcpyHostToDevice));
     return FH264_OK;
 }

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
     S3Warp *sw = (S3Warp *)smem_raw + warp;
     uint32_t *cost = (uint32_t *)(smem_raw + 4 * sizeof(S3Warp)) + (size_t)warp * npad;
     const SeqDev &S = seqs[seq0 + blockIdx.y];
-    const int part = blockIdx.x * 4 + warp;
+    const int part = g.band_mb0 * 4 + blockIdx.x * 4 + warp;
     int xP, yP;
     part_origin(g, part, xP, yP);
     uint2 rows[8];
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ s
     const SeqDev &S = seqs[seq0 + blockIdx.y];
     // REDO launch: CTA b takes the b-th partition the main launch listed as overflowing (usually none: exit at once)
     if (REDO && blockIdx.x >= min(S.status[ST_S2REDO], (uint32_t)S2_REDO_MAX)) return;
-    const int part = REDO ? (int)S.s2redo[blockIdx.x] : blockIdx.x * NW + warp;
+    const int part = REDO ? (int)S.s2redo[blockIdx.x] : g.band_mb0 * 4 + blockIdx.x * NW + warp;
     int xP, yP;
     part_origin(g, part, xP, yP);
     uint2 rows[8];

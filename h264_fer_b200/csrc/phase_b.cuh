@@ -21,6 +21,18 @@
 #define PB_POOL_PREF 192    // stage-2 candidates per partition staged in shared memory (the rest is read from HBM)
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// Bounded wait until *p >= target (flags written by another CTA, or in band mode by another GPU). Returns false on timeout.
+__device__ __forceinline__ bool wait_progress(const uint32_t *p, uint32_t target, bool sys)
+{
+    for (unsigned it = 0; it < (1u << 25); it++) {
+        const uint32_t v = sys ? ld_acquire_sys_u32(p) : ld_acquire_u32(p);
+        if (v >= target) return true;
+        __nanosleep(20);
+    }
+    return false;
+}
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 struct NbCache {            // quadrant MVs of the four neighbouring macroblocks (A.7): 0 left, 1 up, 2 up-right, 3 up-left
@@ -231,7 +243,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // Persistent CTAs: the grid holds about one wavefront's worth of CTAs per sequence (more would only spin and keep
     // other streams' kernels off the SMs); each CTA keeps drawing tickets until the picture is done.
-    const uint32_t total = (uint32_t)g.nmb * (uint32_t)nseq;
+    const uint32_t total = (uint32_t)g.band_nmb * (uint32_t)nseq;
   for (;;) {
     __syncthreads();                                       // previous macroblock's shared state is no longer read
     if (tid == 0) { sh.my_ticket = atomicAdd(ticket, 1u); sh.bs.ns[0] = 0; sh.bs.ns[1] = 0; }
@@ -268,15 +280,19 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     //      MB's quadrant 2 plus the complete MBs above / above-left; only partition 2 needs the left MB's quadrant 3. So a
     //      macroblock starts when its left neighbour is HALF done: successive MBs of a row overlap by two partitions.
     const uint32_t pbase = epoch * 8u;
+    const bool sysw = g.world > 1;                       // band mode: the row above this band is written by another GPU
+    const bool mirror = S.peer_done_next != nullptr && mby == (g.band_mb0 + g.band_nmb) / g.Wmb - 1;   // band's last MB row
     if (tid == 0) {
-        if (mbx > 0) while (ld_acquire_u32(&S.done[mb - 1]) < pbase + 2u) __nanosleep(20);
+        bool ok = true;
+        if (mbx > 0) ok &= wait_progress(&S.done[mb - 1], pbase + 2u, false);
         if (mby > 0) {
-            if (mbx < g.Wmb - 1) while (ld_acquire_u32(&S.done[mb - g.Wmb + 1]) < pbase + 3u) __nanosleep(20);
+            if (mbx < g.Wmb - 1) ok &= wait_progress(&S.done[mb - g.Wmb + 1], pbase + 3u, sysw);
             // the MBs above and above-left must be complete; a P_Skip up-right neighbour does not imply it (it never
             // waited for its own left neighbour to finish)
-            while (ld_acquire_u32(&S.done[mb - g.Wmb]) < pbase + 4u) __nanosleep(20);
-            if (mbx > 0) while (ld_acquire_u32(&S.done[mb - g.Wmb - 1]) < pbase + 4u) __nanosleep(20);
+            ok &= wait_progress(&S.done[mb - g.Wmb], pbase + 4u, sysw);
+            if (mbx > 0) ok &= wait_progress(&S.done[mb - g.Wmb - 1], pbase + 4u, sysw);
         }
+        if (!ok) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
     }
     __syncthreads();
     PB_STAMP(2);
@@ -325,6 +341,13 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             const uint4 *s4 = (const uint4 *)&mo;
             d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
             st_release_u32(&S.done[mb], pbase + 4u);
+            if (mirror) {
+                int *pm = (int *)&S.peer_motion_next[mb].mv[0][0];
+                const int v = (smx & 0xffff) | (smy << 16);
+                pm[0] = v; pm[1] = v; pm[2] = v; pm[3] = v;
+                __threadfence_system();
+                st_release_sys_u32(&S.peer_done_next[mb], pbase + 4u);
+            }
             atomicAdd(&S.status[ST_COUNTS + 0], 1u);
         }
         continue;
@@ -350,7 +373,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         if (pi == 2 && mbx > 0) {
             // partition 2 predicts from the left MB's quadrant 3: now the left MB must be complete
             if (tid == 0) {
-                while (ld_acquire_u32(&S.done[mb - 1]) < pbase + 4u) __nanosleep(20);
+                if (!wait_progress(&S.done[mb - 1], pbase + 4u, false)) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
                 const int v = __ldcg((const int *)&S.motion[mb - 1].mv[3][0]);
                 nc.mvx[0][3] = (int16_t)(v & 0xffff); nc.mvy[0][3] = v >> 16;
             }
@@ -527,6 +550,12 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             // publish this quadrant's MV at once: the right and lower-left neighbours can start before this MB is finished
             *(int *)&S.motion[mb].mv[pi][0] = (bx & 0xffff) | (by << 16);
             st_release_u32(&S.done[mb], pbase + (uint32_t)pi + 1u);
+        }
+        if (tid == 0 && mirror) {
+            // band mode: the rank below predicts from this row — mirror the quadrant MV and the progress flag into its memory
+            *(int *)&S.peer_motion_next[mb].mv[pi][0] = (bx & 0xffff) | (by << 16);
+            __threadfence_system();
+            st_release_sys_u32(&S.peer_done_next[mb], pbase + (uint32_t)pi + 1u);
         }
         PB_STAMP(5 + pi);
         if (pi == 0) { q0x = bx; q0y = by; } else if (pi == 1) { q1x = bx; q1y = by; } else if (pi == 2) { q2x = bx; q2y = by; }

@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(128) k_phase_c(const SeqDev *__restrict__ seqs
     __shared__ __align__(16) fh264_mb_result recs[4];
     const SeqDev &S = seqs[seq0 + blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mb = blockIdx.x * 4 + warp;
-    if (mb >= g.nmb) return;
+    const int mb = g.band_mb0 + blockIdx.x * 4 + warp;
+    if (mb >= g.band_mb0 + g.band_nmb) return;
     fh264_mb_result *rec = &recs[warp];
     {   // zero the record (52 x 16 bytes)
         uint4 z = make_uint4(0, 0, 0, 0);
@@ -260,12 +260,23 @@ __global__ void __launch_bounds__(128) k_phase_c(const SeqDev *__restrict__ seqs
         tq_lane(lane, prm.qp, src, pred, rec, recon);
     }
     if (luma || chroma) {
-        uint8_t *dp = luma ? S.rec[0] + (size_t)(mby * 16 + by) * g.W + mbx * 16 + bx
-                           : S.rec[1 + comp] + (size_t)(mby * 8 + by) * CW + mbx * 8 + bx;
         const int pitch = luma ? g.W : CW;
+        const size_t off = luma ? (size_t)(mby * 16 + by) * g.W + mbx * 16 + bx : (size_t)(mby * 8 + by) * CW + mbx * 8 + bx;
+        const int plane = luma ? 0 : 1 + comp;
+        uint32_t rw[4];
 #pragma unroll
-        for (int r = 0; r < 4; r++)
-            *(uint32_t *)(dp + (size_t)r * pitch) = (uint32_t)recon[r * 4] | ((uint32_t)recon[r * 4 + 1] << 8) | ((uint32_t)recon[r * 4 + 2] << 16) | ((uint32_t)recon[r * 4 + 3] << 24);
+        for (int r = 0; r < 4; r++) rw[r] = (uint32_t)recon[r * 4] | ((uint32_t)recon[r * 4 + 1] << 8) | ((uint32_t)recon[r * 4 + 2] << 16) | ((uint32_t)recon[r * 4 + 3] << 24);
+        uint8_t *dp = S.rec[plane] + off;
+#pragma unroll
+        for (int r = 0; r < 4; r++) *(uint32_t *)(dp + (size_t)r * pitch) = rw[r];
+        // band mode: the reconstruction exchange is fused here — the band's rows go straight into every other rank's
+        // picture over NVLink peer stores (completed by the kernel boundary + k_band_barrier before anyone reads them)
+        for (int pr = 0; pr < g.world; pr++) {
+            if (pr == g.rank) continue;
+            uint8_t *pp = S.peer_rec[pr][plane] + off;
+#pragma unroll
+            for (int r = 0; r < 4; r++) *(uint32_t *)(pp + (size_t)r * pitch) = rw[r];
+        }
     }
     __syncwarp();
     uint4 *dst = (uint4 *)&S.results[mb];

@@ -22,7 +22,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
-           "fh264_debug_feature", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status"]
+           "fh264_debug_feature", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
 
 
 class Fh264Error(RuntimeError):
@@ -78,6 +78,9 @@ def load_library():
     L.fh264_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.fh264_debug_timeline.argtypes = [vp, i32, vp]
     L.fh264_debug_status.argtypes = [vp, i32, vp]
+    L.fh264_band_config.argtypes = [vp, i32, i32, i32, i32]
+    L.fh264_ipc_export.argtypes = [vp, i32, vp]
+    L.fh264_ipc_import.argtypes = [vp, i32, i32, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
@@ -249,6 +252,21 @@ class Session:
         out = np.zeros((self.nmb, 24), np.int64)
         self._ck(self.L.fh264_debug_timeline(self.handle, seq, _ptr(out)))
         return out
+
+    # -- band mode
+    def band_config(self, rank, world, mb_row0, mb_row1):
+        self._ck(self.L.fh264_band_config(self.handle, rank, world, mb_row0, mb_row1))
+        self.band = (mb_row0, mb_row1)
+
+    def ipc_export(self, seq=0) -> bytes:
+        buf = np.zeros(9 * 64, np.uint8)
+        self._ck(self.L.fh264_ipc_export(self.handle, seq, _ptr(buf)))
+        return buf.tobytes()
+
+    def ipc_import(self, seq, peer_rank, blob: bytes):
+        buf = np.frombuffer(blob, np.uint8).copy()
+        assert buf.size == 9 * 64
+        self._ck(self.L.fh264_ipc_import(self.handle, seq, peer_rank, _ptr(buf)))
 
     def debug_status(self, seq):
         out = np.zeros(16, np.uint32)

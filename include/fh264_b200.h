@@ -154,6 +154,19 @@ int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out);
  * [5] k_stage3, [6] k_stage2, [7] k_interp, [8] k_features, [9] k_tile_index. */
 int fh264_last_timings(fh264_session *s, float ms[10]);
 
+/* ---- band mode: one picture split into macroblock-row bands over the GPUs of a node (BASELINE config 4) --------------
+ * One process and one session per GPU, every rank encodes the same pictures in the same order. Each rank keeps the whole
+ * reference picture (upload_source / upload_recon take full pictures on every rank) and codes MB rows [mb_row0, mb_row1);
+ * fh264_encode_p fills only those records of `results`. The phase-B wavefront crosses GPUs through progress flags mirrored
+ * into the next rank's memory, the reconstructed bands are exchanged by peer stores inside phase C (NVLink, CUDA IPC), a
+ * device-side barrier separates pictures. Setup: band_config on every rank, then exchange the export blobs (e.g. with
+ * torch.distributed all_gather_object) and import every other rank's blob. */
+#define FH264_IPC_HANDLE_BYTES 64
+#define FH264_IPC_HANDLES 9
+int fh264_band_config(fh264_session *s, int rank, int world, int mb_row0, int mb_row1);
+int fh264_ipc_export(fh264_session *s, int seq, uint8_t *handles /* FH264_IPC_HANDLES * FH264_IPC_HANDLE_BYTES */);
+int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const uint8_t *handles);
+
 /* Snapshot of the 16 status words of sequence seq after phase C of its last encode_p: [0] flags, [1] stage-2 pool
  * entries used, [2..6] mode counts, [12] partitions redone by the large-buffer stage-2 launch. */
 int fh264_debug_status(fh264_session *s, int seq, uint32_t out[16]);

@@ -1,0 +1,72 @@
+"""GPU suite, needs >= 2 GPUs (skipped otherwise): band mode — one picture split into macroblock-row bands over the GPUs,
+wavefront crossing GPUs through mirrored progress flags, reconstruction exchanged by peer stores inside phase C.
+Bit-exact against the oracle, picture after picture (each picture predicts from the exchanged reconstruction)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, w, h, seed, npics, qp, window, maxdiff, q):
+    import torch
+    import torch.distributed as dist
+    import h264_fer_b200 as fh
+    from h264_fer_b200 import synth
+    from h264_fer_b200.bands import BandSession
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    clip = synth.SynthClip(w, h, seed)
+    bs = BandSession(w, h, device=rank)
+    bs.upload_recon(*clip.frame(0))
+    out = []
+    for t in range(1, npics):
+        bs.upload_source(*clip.frame(t))
+        band = bs.encode_p(qp, window, maxdiff)
+        rec = bs.gather_records(band)
+        recon = bs.download_recon()
+        out.append((fh.records_to_ints(rec), recon))
+    q.put((rank, out))
+    bs.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="band mode needs at least 2 GPUs")
+@pytest.mark.parametrize("world,w,h,window,maxdiff", [(2, 352, 288, 32, 3), (2, 640, 480, 32, -1)])
+def test_band_mode_matches_oracle(world, w, h, window, maxdiff):
+    import torch.multiprocessing as mp
+    from h264_fer_b200 import synth
+    from oracle import port
+    world = min(world, _ngpu())
+    seed, npics, qp = 9, 4, 28
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, 29641, w, h, seed, npics, qp, window, maxdiff, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    clip = synth.SynthClip(w, h, seed)
+    o = port.Oracle(w, h)
+    ref = clip.frame(0)
+    for t in range(1, npics):
+        assert not o.phase_r(ref[0])
+        want, want_recon = o.encode_p(clip.frame(t), ref, qp, window, maxdiff)
+        for r in range(world):
+            got, recon = res[r][t - 1]
+            assert np.array_equal(got, want), "rank %d picture %d: %s" % (r, t, np.argwhere(got != want)[:6].tolist())
+            assert all(np.array_equal(a, b) for a, b in zip(recon, want_recon)), "rank %d picture %d recon" % (r, t)
+        ref = want_recon

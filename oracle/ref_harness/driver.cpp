@@ -13,6 +13,7 @@
 // usage: ref_encoder in.y4m out.264 dump.bin|- frames qp basic window maxdiff intraEvery [dumpmask [planes_pic]]
 //   dumpmask bits: 1 per-MB records (P pictures)   2 reconstruction per picture   4 cropped source per picture
 //                  8 phase-R data after picture `planes_pic`   16 per-MB TQ input (snapped source + prediction)
+//                  32 Intra16x16 luma records of I pictures (source, prediction, DC/AC levels, reconstruction)
 // stdout: one JSON line with per-picture types/bytes and timings.
 #include <chrono>
 #include <cstdio>
@@ -67,6 +68,7 @@ enum { REC_INTS = 1 + 8 + 8 + 4 + 256 + 8 + 120 };
 static std::vector<int> mbrec;      // PicSizeInMbs * REC_INTS
 static std::vector<unsigned char> tqio;  // per MB: snapped source 384 + prediction 384
 static unsigned char savedL[256];
+static std::vector<short> i16rec;        // per Intra16x16 MB: 256 src, 256 pred, 16 dc, 240 ac, 256 recon (as int16)
 
 #ifndef FH264_NO_TAPS   // the integration build (integration/) supplies these entry points itself
 static int *rec(int mb) { return &mbrec[(size_t)mb * REC_INTS]; }
@@ -125,9 +127,24 @@ void quantizationTransform(int predL[16][16], int predCb[8][8], int predCr[8][8]
 {
 	const bool p_pic = (shd.slice_type % 5) == P_SLICE;
 	if (p_pic) tap_tq_input(predL, predCb, predCr);
+	const bool i16 = !p_pic && reconstruct && (dumpmask & 32) && MbPartPredMode(mb_type, 0) == Intra_16x16;
+	const int W = frame.Lwidth, xp = (CurrMbAddr % PicWidthInMbs) << 4, yp = (CurrMbAddr / PicWidthInMbs) << 4;
+	size_t i16base = 0;
+	if (i16) {
+		i16base = i16rec.size();
+		i16rec.resize(i16base + 1024);
+		short *o = &i16rec[i16base];
+		for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) { o[r * 16 + c] = frame.L[(yp + r) * W + xp + c]; o[256 + r * 16 + c] = (short)predL[r][c]; }
+	}
 	clk::time_point t0 = clk::now();
 	ref_quantizationTransform(predL, predCb, predCr, reconstruct);
 	if (p_pic) t_tq += since(t0);
+	if (i16) {
+		short *o = &i16rec[i16base];
+		for (int k = 0; k < 16; k++) o[512 + k] = (short)Intra16x16DCLevel[k];
+		for (int b = 0; b < 16; b++) for (int k = 0; k < 15; k++) o[528 + b * 15 + k] = (short)Intra16x16ACLevel[b][k];
+		for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) o[768 + r * 16 + c] = frame.L[(yp + r) * W + xp + c];
+	}
 	if (p_pic && (dumpmask & 1)) {
 		int *R = rec(CurrMbAddr) + 21;
 		for (int b = 0; b < 16; b++) for (int k = 0; k < 16; k++) *R++ = LumaLevel[b][k];
@@ -238,6 +255,8 @@ int main(int argc, char **argv)
 		chunk("PICH", hdr, sizeof hdr);
 		if (isP && (dumpmask & 1)) chunk("MBRC", mbrec.data(), mbrec.size() * sizeof(int));
 		if (isP && (dumpmask & 16)) chunk("TQIO", tqio.data(), tqio.size());
+		if (!isP && (dumpmask & 32) && !i16rec.empty()) chunk("I16M", i16rec.data(), i16rec.size() * sizeof(short));
+		i16rec.clear();
 		if (dumpmask & 2) {
 			chunk("RECY", frame.L, (size_t)W * H);
 			chunk("RECU", frame.C[0], (size_t)W * H / 4);

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ENCODER = os.path.join(HERE, "_ref", "ref_encoder")
 REC_INTS = 405
 
-D_MBREC, D_RECON, D_SOURCE, D_PHASE_R, D_TQIO = 1, 2, 4, 8, 16
+D_MBREC, D_RECON, D_SOURCE, D_PHASE_R, D_TQIO, D_INTRA16 = 1, 2, 4, 8, 16, 32
 
 
 def have_ref_encoder() -> bool:
@@ -54,6 +54,8 @@ def parse_dump(path):
             p["nal_type"], p["bytes"], p["w"], p["h"], p["counts"], p["qp"] = h[0], h[1], h[2], h[3], list(h[4:9]), h[9]
         elif tag == "MBRC":
             p["mbrec"] = np.frombuffer(payload, dtype=np.int32).reshape(-1, REC_INTS).copy()
+        elif tag == "I16M":
+            p["i16"] = np.frombuffer(payload, dtype=np.int16).reshape(-1, 1024).copy()
         elif tag == "TQIO":
             p["tqio"] = np.frombuffer(payload, dtype=np.uint8).reshape(-1, 768).copy()
         elif tag in ("RECY", "RECU", "RECV", "SRCY", "SRCU", "SRCV"):

@@ -43,6 +43,11 @@ class Golden:
     def counts(self, n):
         return [int(c) for c in self.z["counts_%d" % n]]
 
+    def i16(self):
+        """Intra16x16 luma records of the I pictures: [n, 1024] int16 = 256 src, 256 pred, 16 dc, 240 ac, 256 recon."""
+        out = [self.z[k] for k in self.z.files if k.startswith("i16_")]
+        return np.concatenate(out) if out else np.zeros((0, 1024), np.int16)
+
     def p_pictures(self):
         return [n for n, t in enumerate(self.types) if t == 1]
 

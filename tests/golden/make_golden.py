@@ -23,25 +23,31 @@ CASES = {
     "qcif_w16_qp28": (176, 144, 1, 4, 28, 16, 3, 0, 1.0, True),
     "cif_crop_w32_qp20_adaptive": (200, 120, 11, 4, 20, 32, -1, 0, 0.0, True),
     "small_basic_qp33": (128, 96, 12, 3, 33, 16, 2, 1, 0.5, False),
+    # I-only, low contrast: the reference picks Intra16x16 for most MBs -> pins the luma-DC Hadamard path
+    "intra16_lowcontrast_qp30": (176, 144, 13, 1, 30, 16, 3, 0, 0.3, False, 0.08),
+    "intra16_lowcontrast_qp40": (176, 144, 14, 1, 40, 16, 3, 0, 0.3, False, 0.08),
 }
 
 
 def main():
     assert refdump.have_ref_encoder(), "build oracle/_ref/ref_encoder first (make -C oracle ref)"
-    for name, (w, h, seed, frames, qp, window, maxdiff, basic, noise, square) in CASES.items():
+    for name, case in CASES.items():
+        (w, h, seed, frames, qp, window, maxdiff, basic, noise, square), contrast = case[:10], (case[10] if len(case) > 10 else 1.0)
         tmp = tempfile.mkdtemp()
         y4m = os.path.join(tmp, "in.y4m")
-        synth.write_y4m(y4m, w, h, seed, frames, noise=noise, square=square)
+        synth.write_y4m(y4m, w, h, seed, frames, noise=noise, square=square, contrast=contrast)
         summ, dump, out264 = refdump.run_reference(y4m, frames, qp=qp, basic=basic, window=window, maxdiff=maxdiff,
-                                                   dumpmask=refdump.D_MBREC | refdump.D_RECON | refdump.D_SOURCE | refdump.D_TQIO)
+                                                   dumpmask=refdump.D_MBREC | refdump.D_RECON | refdump.D_SOURCE | refdump.D_TQIO | refdump.D_INTRA16)
         pics = refdump.parse_dump(dump)
         arrays = dict(params=np.array([w, h, seed, frames, qp, window, maxdiff, basic], np.int32),
-                      noise=np.array([noise]), square=np.array([int(square)]), types=np.array([p["nal_type"] for p in pics], np.int32),
+                      noise=np.array([noise]), square=np.array([int(square)]), contrast=np.array([contrast]), types=np.array([p["nal_type"] for p in pics], np.int32),
                       bitstream_md5=np.frombuffer(hashlib.md5(open(out264, "rb").read()).digest(), np.uint8),
                       y4m_md5=np.frombuffer(hashlib.md5(open(y4m, "rb").read()).digest(), np.uint8))
         for n, p in enumerate(pics):
             for t in ("SRCY", "SRCU", "SRCV", "RECY", "RECU", "RECV"):
                 arrays["%s_%d" % (t, n)] = p[t]
+            if "i16" in p:
+                arrays["i16_%d" % n] = p["i16"][:96]          # Intra16x16 luma records of this I picture (a13)
             if "mbrec" in p:
                 arrays["mbrec_%d" % n] = p["mbrec"].astype(np.int16)
                 arrays["tqio_%d" % n] = p["tqio"]

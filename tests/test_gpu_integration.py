@@ -35,7 +35,8 @@ def md5(path):
 def test_bitstream_and_reconstruction_match_golden(golden, tmp_path):
     y4m = str(tmp_path / "in.y4m")
     z = golden.z
-    synth.write_y4m(y4m, golden.w_in, golden.h_in, golden.seed, golden.frames, noise=float(z["noise"][0]), square=bool(int(z["square"][0])))
+    synth.write_y4m(y4m, golden.w_in, golden.h_in, golden.seed, golden.frames, noise=float(z["noise"][0]), square=bool(int(z["square"][0])),
+                    contrast=float(z["contrast"][0]))
     assert md5(y4m) == bytes(z["y4m_md5"]), "synthetic clip generator drifted from the one that made the golden vectors"
     out, dump = str(tmp_path / "out.264"), str(tmp_path / "dump.bin")
     run_b200_encoder(y4m, out, dump, golden.frames, golden.qp, golden.basic, golden.window, golden.maxdiff, dumpmask=refdump.D_RECON)

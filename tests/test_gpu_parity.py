@@ -79,6 +79,16 @@ def test_intra16_luma_dc_path_against_oracle(qp):
         assert np.array_equal(dc[i].astype(np.int32), edc) and np.array_equal(ac[i].astype(np.int32), eac) and np.array_equal(rc[i], erc), (qp, i)
 
 
+def test_intra16_luma_dc_path_against_reference_golden(golden):
+    rec = golden.i16()
+    if rec.shape[0] == 0:
+        pytest.skip("no Intra16x16 macroblocks in this fixture")
+    with fh.Session(64, 48) as s:
+        dc, ac, recon = s.tq_luma_intra16(rec[:, :256].astype(np.uint8), rec[:, 256:512].astype(np.uint8), golden.qp)
+    assert np.array_equal(dc, rec[:, 512:528]) and np.array_equal(ac.reshape(-1, 240), rec[:, 528:768])
+    assert np.array_equal(recon, rec[:, 768:].astype(np.uint8))
+
+
 def test_fused_tq_against_golden_tqio(golden):
     with fh.Session(64, 48) as s:
         for n in golden.p_pictures():

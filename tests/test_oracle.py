@@ -52,6 +52,22 @@ def test_mode_coverage_of_goldens():
     assert qps == {True, False}
 
 
+def test_oracle_intra16_luma_dc_path_matches_reference(golden):
+    """a13: per-block transform with DC kept + 4x4 Hadamard of the DCs, against records tapped from the reference's I pictures
+    (quantizationTransform for Intra16x16 MBs; both quantiser branches qP < 36 and >= 36 are in the goldens)."""
+    rec = golden.i16()
+    for r in rec:
+        src, pred = r[:256].astype(np.uint8), r[256:512].astype(np.uint8)
+        dc, ac, recon = port.tq_luma_intra16(src, pred, golden.qp)
+        assert np.array_equal(dc, r[512:528]) and np.array_equal(ac.ravel(), r[528:768]) and np.array_equal(recon, r[768:].astype(np.uint8))
+
+
+def test_intra16_goldens_cover_both_dc_quantiser_branches():
+    from conftest import Golden, golden_paths
+    qps = [Golden(p).qp for p in golden_paths() if Golden(p).i16().shape[0] >= 50]
+    assert any(q < 36 for q in qps) and any(q >= 36 for q in qps)
+
+
 def test_scene_sad_oracle():
     rng = np.random.default_rng(3)
     a = rng.integers(0, 256, 5000, dtype=np.uint8)

@@ -113,14 +113,18 @@ __device__ __forceinline__ int sad_row8(uint2 cur, const uint8_t *plane, int W, 
 // n / d for 0 <= n < 65536 / d with inv = 65536 / d + 1 (window geometry: d <= 129)
 __device__ __forceinline__ int fdiv_(int n, int inv) { return (int)(((unsigned)n * (unsigned)inv) >> 16); }
 
-// Feature distance (moestimation.cpp:267-276).
+// Feature distance (moestimation.cpp:267-276):
+//   |s0-K0| + sum_k ( |sk-Kk| + |(s0-sk)-(K0-Kk)| ),  k = 1..4.
+// With d = s0-K0 and a = sk-Kk the k-th pair is |a| + |d-a| = max(|d|, |2a-d|) (the identity |x|+|y| = max(|x+y|,|x-y|)),
+// an exact integer rewrite that needs one abs + one max per pair instead of two abs: 2a-d = (2sk-s0) + K0 - 2Kk.
 __device__ __forceinline__ int feat_dist(const int s[5], int K0, int K1, int K2, int K3, int K4)
 {
-    int d = iabs_(s[0] - K0);
-    d += iabs_(s[1] - K1) + iabs_(s[0] - s[1] - K0 + K1);
-    d += iabs_(s[2] - K2) + iabs_(s[0] - s[2] - K0 + K2);
-    d += iabs_(s[3] - K3) + iabs_(s[0] - s[3] - K0 + K3);
-    d += iabs_(s[4] - K4) + iabs_(s[0] - s[4] - K0 + K4);
+    const int ad = iabs_(s[0] - K0);
+    int d = ad;
+    d += max(ad, iabs_((2 * s[1] - s[0]) + K0 - 2 * K1));
+    d += max(ad, iabs_((2 * s[2] - s[0]) + K0 - 2 * K2));
+    d += max(ad, iabs_((2 * s[3] - s[0]) + K0 - 2 * K3));
+    d += max(ad, iabs_((2 * s[4] - s[0]) + K0 - 2 * K4));
     return d;
 }
 

@@ -58,7 +58,6 @@ __global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
 {
     uint32_t *st = seqs[seq0 + threadIdx.x].status;
     st[ST_FLAGS] = st[ST_FLAGS_NEXT];
-    st[ST_S2CURSOR] = 0;
     for (int i = 0; i < 5; i++) st[ST_COUNTS + i] = 0;
     st[ST_S2REDO] = 0;
     if (threadIdx.x == 0) *ticket = 0;
@@ -341,8 +340,9 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         k_stage2<S2_CAP_BIG, 1, true><<<g2r, 32, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
     CK(cudaEventRecord(s->ev[1], st));
-    // persistent wavefront CTAs: about one anti-diagonal (Wmb/2) plus slack per sequence
-    const unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, (long long)nseq * (g.Wmb / 2 + 8));
+    // persistent wavefront CTAs: two anti-diagonals' worth per sequence — one set working, one set that has already
+    // drawn its ticket and prefetched (otherwise ticket + prefetch latency sits on the wavefront's critical path)
+    const unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, (long long)nseq * (g.Wmb + 16));
     k_phase_b<<<pb_ctas, PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
     CK(cudaEventRecord(s->ev[2], st));
     dim3 gc((g.band_nmb + 3) / 4, nseq);

@@ -355,18 +355,15 @@ __global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ s
     for (int i = 0; i < 6; i++) if (lane * 6 + i <= js) upto += cj[i];
     int n2 = (int)__reduce_add_sync(0xffffffffu, upto);
     const int cnt0 = (int)__shfl_sync(0xffffffffu, cb[0], 0);
-    uint32_t off = 0;
+    // every partition owns a fixed 1024-entry slice of the candidate pool (no allocation, and phase B can prefetch it
+    // without first reading the partition header)
+    uint32_t off = (uint32_t)part * 1024u;
     if (lane == 0) {
         if (n2 > 1023) { atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); n2 = 0; }
-        else if (n2 > 0) {
-            off = atomicAdd(&S.status[ST_S2CURSOR], (uint32_t)n2);
-            if (off + (uint32_t)n2 > S.s2pool_size) { atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); n2 = 0; }
-        }
         PartA *pa = &S.parta[part];
         pa->s2_off = off; pa->n2 = (uint32_t)n2;
     }
     n2 = __shfl_sync(0xffffffffu, n2, 0);
-    off = __shfl_sync(0xffffffffu, off, 0);
     if (n2 == 0) return;
     // Arrival order (:474-495): j ascending; minus side before plus side; x then y inside a bucket; bucket s0 twice.
     // Output slot of bin (j, side): start = (entries of smaller j, bucket s0 counted twice) + (side ? count of side 0 : 0);

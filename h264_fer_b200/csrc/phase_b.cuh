@@ -79,6 +79,8 @@ __device__ __forceinline__ void predict_mv_(const NbCache &nc, int px, int py, i
 
 __device__ __forceinline__ int mv_cost(int mvx, int mvy, int px, int py) { return iabs_(mvx - px) + iabs_(mvy - py); }
 
+__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 struct BlockSel { u64 skey[256]; uint16_t sidx[256]; int ns[2]; int phase; };
 
 struct PBShared {
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     const int W = g.W, H = g.H;
     NbCache &nc = sh.nc;
     long long *dbg = S.dbg ? S.dbg + (size_t)mb * 24 : nullptr;
-#define PB_STAMP(k) do { if (dbg && tid == 0) dbg[k] = clock64(); } while (0)
+#define PB_STAMP(k) do { if (dbg && tid == 0) dbg[k] = gtime_ns(); } while (0)
     PB_STAMP(0);
 
     // ---- everything that does not depend on the neighbours is fetched BEFORE waiting on them: the CTA is resident
@@ -265,12 +267,9 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     if (!prm.basic) {
         if (tid >= 32 && tid < 36) sh.pa[tid - 32] = S.parta[mb * 4 + tid - 32];
         for (int i = tid; i < 4 * FH_S3_MAX; i += PB_NT) { const int pi = i / FH_S3_MAX, k = i - pi * FH_S3_MAX; sh.s3[pi][k] = S.s3[(size_t)(mb * 4 + pi) * FH_S3_MAX + k]; }
-        __syncthreads();
-        for (int pi = 0; pi < 4; pi++) {
-            const int n = min((int)sh.pa[pi].n2, PB_POOL_PREF);
-            const uint2 *pool = S.s2pool + sh.pa[pi].s2_off;
-            for (int i = tid; i < n; i += PB_NT) sh.pool[pi][i] = __ldg(&pool[i]);
-        }
+        // each partition's candidates live in a fixed pool slice: fetch the first PB_POOL_PREF of every slice right away
+        // (entries beyond the partition's count are never looked at)
+        for (int i = tid; i < 4 * PB_POOL_PREF; i += PB_NT) { const int pi = i / PB_POOL_PREF, k = i - pi * PB_POOL_PREF; sh.pool[pi][k] = __ldg(&S.s2pool[(size_t)(mb * 4 + pi) * 1024u + k]); }
     } else if (tid < 4) {
         sh.pa[tid].n2 = 0; sh.pa[tid].n3 = 0; sh.pa[tid].s2_off = 0;
     }
@@ -546,8 +545,9 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             for (int rr2 = 0; rr2 < 8; rr2++) bs += sad_row8(*(const uint2 *)&sh.cur[(pi >> 1) * 8 + rr2][(pi & 1) * 8], pl, W, H, xP, yP + rr2);
         }
         mv[pi][0] = bx; mv[pi][1] = by; sadq[pi] = bs;
-        if (tid == 0 && pi < 3) {
+        if (tid == 0) {
             // publish this quadrant's MV at once: the right and lower-left neighbours can start before this MB is finished
+            // (neighbours only ever read quadrant MVs; the merged type / mvd / SADs of the record are read by phase C)
             *(int *)&S.motion[mb].mv[pi][0] = (bx & 0xffff) | (by << 16);
             st_release_u32(&S.done[mb], pbase + (uint32_t)pi + 1u);
         }
@@ -590,7 +590,6 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         uint4 *d = (uint4 *)&S.motion[mb];
         const uint4 *s4 = (const uint4 *)&mo;
         d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
-        st_release_u32(&S.done[mb], pbase + 4u);     // release orders this thread's motion-record stores before the flag
         PB_STAMP(9);
         atomicAdd(&S.status[ST_COUNTS + cnt], 1u);
     }

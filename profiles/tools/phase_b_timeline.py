@@ -22,10 +22,10 @@ skip = rec["mb_type"] == 31
 names = ["prefetch issue", "wait deps", "nb mv load", "skip test", "part0", "part1", "part2", "part3", "merge+publish"]
 d = np.diff(tl[:, :10], axis=1).astype(float)
 ns = d[~skip]
-print("non-skip MBs: %d, skip: %d  (cycles @ SM clock; 1965 MHz => 1000 cyc = 0.51 us)" % ((~skip).sum(), skip.sum()))
+print("non-skip MBs: %d, skip: %d  (globaltimer ns)" % ((~skip).sum(), skip.sum()))
 for i, n in enumerate(names):
     print("  %-16s mean %8.0f  median %8.0f  p90 %8.0f" % (n, ns[:, i].mean(), np.median(ns[:, i]), np.percentile(ns[:, i], 90)))
-print("  busy (after deps) mean %.0f cycles = %.1f us" % (ns[:, 2:].sum(1).mean(), ns[:, 2:].sum(1).mean() / 1965.0))
+print("  busy (after deps) mean %.0f ns" % (ns[:, 2:].sum(1).mean()))
 sub = np.diff(np.concatenate([tl[~skip][:, 4:5], tl[~skip][:, 10:18], tl[~skip][:, 5:6]], axis=1), axis=1).astype(float)
 for i, n in enumerate(["mvp + issue feature loads", "stage-2 keys + barrier", "stage-2 select", "stage-2/3 evaluate", "stage-1 keys + barrier",
                        "stage-1 select", "stage-1 SAD", "warp min + barrier", "decode"]):
@@ -33,3 +33,22 @@ for i, n in enumerate(["mvp + issue feature loads", "stage-2 keys + barrier", "s
 sk = d[skip]
 if len(sk):
     print("skip MBs: after-deps mean %.0f cycles" % (tl[skip, 4] - tl[skip, 2]).mean())
+
+# critical-path view: when were the dependencies published vs when did the MB notice and start?
+Wmb, Hmb = W // 16, fr[0][0].shape[0] // 16
+T = tl.reshape(Hmb, Wmb, -1)
+lag, starve = [], []
+for y in range(Hmb):
+    for x in range(Wmb):
+        ready = 0
+        if x > 0: ready = max(ready, T[y, x - 1, 6] if T[y, x - 1, 6] else T[y, x - 1, 4])       # left: quadrant 1 published (or skip decided)
+        if y > 0:
+            if x < Wmb - 1: ready = max(ready, T[y - 1, x + 1, 7] if T[y - 1, x + 1, 7] else T[y - 1, x + 1, 4])
+            ready = max(ready, T[y - 1, x, 8] if T[y - 1, x, 8] else T[y - 1, x, 4])
+        if ready:
+            lag.append(T[y, x, 2] - ready)            # > 0: noticed after the deps were ready
+            starve.append(T[y, x, 1] - ready)         # > 0: the CTA had not even finished prefetching when the deps were ready
+lag, starve = np.array(lag, float), np.array(starve, float)
+print("dependency ready -> MB proceeds: median %.0f ns, mean %.0f, p90 %.0f" % (np.median(lag), lag.mean(), np.percentile(lag, 90)))
+print("MBs whose CTA was still fetching its ticket/prefetch when the deps were ready: %.1f%% (median lateness %.0f ns)" % (100 * (starve > 0).mean(), np.median(starve[starve > 0]) if (starve > 0).any() else 0))
+print("picture wavefront: first start -> last publish = %.3f ms" % ((tl[:, 9].max() - tl[:, 0].min()) / 1e6))

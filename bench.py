@@ -296,6 +296,8 @@ def main():
                 gr.stream.wait_event(e0)                         # the timed region starts at e0 on every group stream
                 for _ in range(K):
                     gr.step(host)
+                if host:
+                    gr.s.sync()                                  # the last records' D2H (library copy stream) is inside the timed region
                 ev.record(gr.stream)
             except Exception as ex:       # surfaced by the main thread
                 errors.append(ex)
@@ -325,6 +327,8 @@ def main():
             groups[0].stream.wait_event(e0)
             for _ in range(K):
                 groups[0].step(host)
+            if host:
+                groups[0].s.sync()                               # the last records' D2H (library copy stream) is inside the timed region
             ends[0].record(groups[0].stream)
         else:
             bar_go.wait()

@@ -28,11 +28,17 @@ static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
 
 struct PeerSync { uint32_t *p[FH_MAX_WORLD]; };
 
+struct fh264_session;
+static cudaError_t sync_streams(fh264_session *s);
+
 struct fh264_session {
     Geo g;
     int batch, device;
     cudaStream_t stream;
     bool own_stream;
+    cudaStream_t copy_stream;       // result records go home on their own stream, overlapping phase R and the next picture
+    cudaEvent_t ev_c_done, ev_copy_done;
+    bool copy_pending;
     std::vector<SeqDev> h;          // host mirror of the device SeqDev array
     SeqDev *d_seqs;
     int *d_wf_order;
@@ -88,6 +94,13 @@ __global__ void k_band_barrier(PeerSync ps, uint32_t *status, uint32_t epoch, in
     if (!ok) atomicOr(&status[ST_FLAGS_NEXT], FLAG_TIMEOUT);
 }
 
+static cudaError_t sync_streams(fh264_session *s)
+{
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess && s->copy_stream) e = cudaStreamSynchronize(s->copy_stream);
+    return e;
+}
+
 template <typename T>
 static cudaError_t dalloc(fh264_session *s, T **p, size_t count)
 {
@@ -115,6 +128,9 @@ extern "C" int fh264_close(fh264_session *s)
     for (int i = 0; i < 5; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int i = 0; i < 4; i++) if (s->evk[i]) cudaEventDestroy(s->evk[i]);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->ev_c_done) cudaEventDestroy(s->ev_c_done);
+    if (s->ev_copy_done) cudaEventDestroy(s->ev_copy_done);
     delete s;
     return FH264_OK;
 }
@@ -138,6 +154,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     fh264_session *s = new fh264_session();
     s->batch = batch; s->device = device; s->epoch = 0; s->timed = false; s->own_stream = true;
     s->d_sync = nullptr; memset(&s->peer_sync, 0, sizeof s->peer_sync);
+    s->copy_stream = nullptr; s->ev_c_done = nullptr; s->ev_copy_done = nullptr; s->copy_pending = false;
     s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->d_sadout = nullptr; s->scr_mbs = 0;
     for (int i = 0; i < 5; i++) s->ev[i] = nullptr;
     for (int i = 0; i < 4; i++) s->evk[i] = nullptr;
@@ -152,6 +169,9 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->h.resize(batch);
 #define OPEN_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(FH264_E_CUDA, #call, e_); fh264_close(s); return FH264_E_CUDA; } } while (0)
     OPEN_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    OPEN_CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    OPEN_CK(cudaEventCreateWithFlags(&s->ev_c_done, cudaEventDisableTiming));
+    OPEN_CK(cudaEventCreateWithFlags(&s->ev_copy_done, cudaEventDisableTiming));
     for (int i = 0; i < 5; i++) OPEN_CK(cudaEventCreate(&s->ev[i]));
     for (int i = 0; i < 4; i++) OPEN_CK(cudaEventCreate(&s->evk[i]));
     OPEN_CK(cudaHostAlloc((void **)&s->h_status, sizeof(uint32_t) * ST_WORDS * batch, cudaHostAllocDefault));
@@ -207,7 +227,7 @@ extern "C" int fh264_set_stream(fh264_session *s, void *cuda_stream)
 {
     if (!s) return fail(FH264_E_ARG, "null session");
     CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
     if (cuda_stream) s->stream = (cudaStream_t)cuda_stream;
     else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
@@ -218,7 +238,7 @@ extern "C" int fh264_sync(fh264_session *s)
 {
     if (!s) return fail(FH264_E_ARG, "null session");
     CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     return FH264_OK;
 }
 
@@ -289,7 +309,7 @@ extern "C" int fh264_scene_sad_batch(fh264_session *s, int seq0, int nseq, uint6
     k_gather_sad<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0, s->d_sadout);
     CKL();
     CK(cudaMemcpyAsync(s->h_sad, s->d_sadout, sizeof(uint64_t) * nseq, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     memcpy(sads, s->h_sad, sizeof(uint64_t) * nseq);
     return FH264_OK;
 }
@@ -346,6 +366,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     k_phase_b<<<pb_ctas, PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
     CK(cudaEventRecord(s->ev[2], st));
     dim3 gc((g.band_nmb + 3) / 4, nseq);
+    if (s->copy_pending) { CK(cudaStreamWaitEvent(st, s->ev_copy_done, 0)); s->copy_pending = false; }   // records of the previous picture are home
     k_phase_c<<<gc, 128, 0, st>>>(s->d_seqs, seq0, g, prm);
     CKL();
     CK(cudaEventRecord(s->ev[3], st));
@@ -353,9 +374,14 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         CK(cudaMemcpyAsync(s->h_status + (size_t)b * ST_WORDS, s->h[b].status, sizeof(uint32_t) * ST_WORDS, cudaMemcpyDeviceToHost, st));
     if (results)
     {
-        if (g.world == 1) CK(cudaMemcpyAsync(results, s->h[seq0].results, sizeof(fh264_mb_result) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, st));
+        // the records travel on the copy stream while this stream goes on with the dpb swap, phase R and the next picture
+        CK(cudaEventRecord(s->ev_c_done, st));
+        CK(cudaStreamWaitEvent(s->copy_stream, s->ev_c_done, 0));
+        if (g.world == 1) CK(cudaMemcpyAsync(results, s->h[seq0].results, sizeof(fh264_mb_result) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, s->copy_stream));
         else for (int b = 0; b < nseq; b++)      // band mode: only this rank's band of every sequence is valid
-            CK(cudaMemcpyAsync(results + (size_t)b * g.nmb + g.band_mb0, s->h[seq0 + b].results + g.band_mb0, sizeof(fh264_mb_result) * (size_t)g.band_nmb, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(results + (size_t)b * g.nmb + g.band_mb0, s->h[seq0 + b].results + g.band_mb0, sizeof(fh264_mb_result) * (size_t)g.band_nmb, cudaMemcpyDeviceToHost, s->copy_stream));
+        CK(cudaEventRecord(s->ev_copy_done, s->copy_stream));
+        s->copy_pending = true;
     }
     // dpb := reconstruction (frameDeepCopy, ref_frames.cpp:17-35) by pointer swap, then phase R for the next picture
     if (g.world > 1) k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->h[seq0].status, s->epoch, g.rank, g.world);
@@ -374,7 +400,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
 extern "C" int fh264_encode_p(fh264_session *s, int seq0, int nseq, const fh264_params *p, fh264_mb_result *results)
 {
     int rc = fh264_encode_p_async(s, seq0, nseq, p, results); if (rc) return rc;
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     for (int b = seq0; b < seq0 + nseq; b++) { rc = fh264_picture_status(s, b); if (rc) return rc; }
     return FH264_OK;
 }
@@ -383,7 +409,7 @@ extern "C" int fh264_picture_status(fh264_session *s, int seq)
 {
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     const uint32_t f = s->h_status[(size_t)seq * ST_WORDS + ST_FLAGS];
     if (f & FLAG_UB_INPUT) return fail(FH264_E_UB_INPUT, "reference picture has an 8x8 window sum of 0 or >= 16203: undefined in the reference (moestimation.cpp:153-158,477-480)");
     if (f & FLAG_TIMEOUT) return fail(FH264_E_STATE, "a wavefront / cross-GPU wait timed out (band mode: is every rank encoding the same picture?)");
@@ -396,7 +422,7 @@ extern "C" int fh264_mode_counts(fh264_session *s, int seq, int32_t counts[5])
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     if (!counts) return fail(FH264_E_ARG, "null output");
     CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     // device counters: [0] skip, [1] 16x16, [2] 16x8, [3] 8x16, [4] 8x8 == brojTipova order
     for (int i = 0; i < 5; i++) counts[i] = (int32_t)s->h_status[(size_t)seq * ST_WORDS + ST_COUNTS + i];
     return FH264_OK;
@@ -409,7 +435,7 @@ extern "C" int fh264_debug_status(fh264_session *s, int seq, uint32_t out[16])
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     if (!out) return fail(FH264_E_ARG, "null output");
     CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     memcpy(out, s->h_status + (size_t)seq * ST_WORDS, sizeof(uint32_t) * ST_WORDS);
     return FH264_OK;
 }
@@ -424,7 +450,7 @@ extern "C" int fh264_download_recon(fh264_session *s, int seq, uint8_t *y, uint8
     CK(cudaMemcpyAsync(y, s->h[seq].ref[0], WH, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(cb, s->h[seq].ref[1], WH / 4, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(cr, s->h[seq].ref[2], WH / 4, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     return FH264_OK;
 }
 
@@ -447,7 +473,7 @@ extern "C" int fh264_last_timings(fh264_session *s, float ms[10])
 static int ensure_scratch(fh264_session *s, size_t nmbs)
 {
     if (nmbs <= s->scr_mbs) return FH264_OK;
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     for (int i = 0; i < 3; i++) if (s->d_scr[i]) { cudaFree(s->d_scr[i]); s->d_scr[i] = nullptr; }
     for (int i = 0; i < 2; i++) if (s->d_scr16[i]) { cudaFree(s->d_scr16[i]); s->d_scr16[i] = nullptr; }
     for (int i = 0; i < 3; i++) CK(cudaMalloc((void **)&s->d_scr[i], nmbs * 384));
@@ -469,7 +495,7 @@ extern "C" int fh264_tq_macroblocks(fh264_session *s, int n, const uint8_t *src3
     CKL();
     CK(cudaMemcpyAsync(levels384, s->d_scr16[0], (size_t)n * 384 * 2, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(recon384, s->d_scr[2], (size_t)n * 384, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(sync_streams(s));
     return FH264_OK;
 }
 
@@ -487,7 +513,7 @@ extern "C" int fh264_tq_luma_intra16(fh264_session *s, int n, const uint8_t *src
     CK(cudaMemcpyAsync(dc16, s->d_scr16[0], (size_t)n * 16 * 2, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ac16x15, s->d_scr16[1], (size_t)n * 240 * 2, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(recon256, s->d_scr[2], (size_t)n * 256, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(sync_streams(s));
     return FH264_OK;
 }
 
@@ -504,7 +530,7 @@ extern "C" int fh264_motion_compensate(fh264_session *s, int seq, const int16_t 
     k_mc_only<<<(n + 3) / 4, 128, 0, st>>>(s->d_seqs, seq, s->g, s->d_scr16[0], s->d_scr[2]);
     CKL();
     CK(cudaMemcpyAsync(pred384, s->d_scr[2], (size_t)n * 384, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(sync_streams(s));
     return FH264_OK;
 }
 
@@ -514,7 +540,7 @@ extern "C" int fh264_debug_plane(fh264_session *s, int seq, int f, uint8_t *out)
     if (!out || f < 0 || f > 15) return fail(FH264_E_ARG, "bad argument");
     CK(cudaSetDevice(s->device));
     CK(cudaMemcpyAsync(out, s->h[seq].planes + (size_t)f * s->g.WH, (size_t)s->g.WH, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     return FH264_OK;
 }
 
@@ -536,7 +562,7 @@ extern "C" int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint
     k_unpack_feature<<<(n + 255) / 256, 256, 0, s->stream>>>(s->h[seq].kar + (size_t)f * n, n, k, (uint16_t *)s->d_scr16[0]);
     CKL();
     CK(cudaMemcpyAsync(out, s->d_scr16[0], (size_t)n * 2, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     return FH264_OK;
 }
 
@@ -547,7 +573,7 @@ extern "C" int fh264_debug_timeline(fh264_session *s, int seq, long long *out)
 {
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     const size_t n = (size_t)s->g.nmb * 24;
     if (!s->h[seq].dbg) {
         long long *p = nullptr;
@@ -571,7 +597,7 @@ extern "C" int fh264_band_config(fh264_session *s, int rank, int world, int mb_r
     if (world < 1 || world > FH_MAX_WORLD || rank < 0 || rank >= world) return fail(FH264_E_ARG, "rank/world out of range (at most 8 ranks)");
     if (mb_row0 < 0 || mb_row1 <= mb_row0 || mb_row1 > s->g.Hmb) return fail(FH264_E_ARG, "empty or out-of-range macroblock-row band");
     CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     Geo &g = s->g;
     g.rank = rank; g.world = world; g.band_mb0 = mb_row0 * g.Wmb; g.band_nmb = (mb_row1 - mb_row0) * g.Wmb;
     // wavefront order restricted to the band
@@ -609,7 +635,7 @@ extern "C" int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const 
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     if (!handles || peer_rank < 0 || peer_rank >= s->g.world || peer_rank == s->g.rank) return fail(FH264_E_ARG, "bad peer rank / handles");
     CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(sync_streams(s));
     void *ptrs[FH264_IPC_HANDLES];
     for (int i = 0; i < FH264_IPC_HANDLES; i++) {
         cudaIpcMemHandle_t h;

@@ -60,7 +60,7 @@ struct SeqDev {
     uint8_t *ref[3];        // `dpb`: previous reconstruction
     uint8_t *rec[3];        // reconstruction of the picture being coded (swapped with ref afterwards)
     uint8_t *planes;        // refFrameInterpolated[f].L, f-major, WH each (+16 bytes slack at the end)
-    uint4 *kar;             // refFrameKar[0..4][f] packed per position: [f][y][x] = {K0|K1<<16, K2|K3<<16, K4, 0}
+    uint4 *kar;             // refFrameKar[0..4][f] per position: [f][y][x] = {F1|F2<<16, F3|F4<<16, K0, 0}, Fk = K0 - 2*Kk (int16)
     TileEntry *tent;        // ntiles * 4096 entries
     uint16_t *tstart;       // ntiles * FH_TSTART_PITCH
     PartA *parta;           // nparts
@@ -86,14 +86,28 @@ __device__ __forceinline__ int clip255_(int v) { return min(max(v, 0), 255); }
 __device__ __forceinline__ int tap6_(int a, int b, int c, int d, int e, int f) { return clip255_((a - 5 * b + 20 * c + 20 * d - 5 * e + f + 16) >> 5); }
 __device__ __forceinline__ int mid_(int a, int b) { return (a + b + 1) >> 1; }
 
-// 8 consecutive bytes starting at an arbitrary address, as two little-endian words (reads up to 3 bytes past).
+// 8 consecutive bytes starting at an arbitrary address, as two little-endian words: two aligned 8-byte loads (two LSU
+// wavefronts per lane instead of three 4-byte ones) and a funnel shift; reads up to 7 bytes past the block (the plane
+// buffers carry 16 bytes of slack).
+#ifndef FH_ROW_LD64
+#define FH_ROW_LD64 1
+#endif
 __device__ __forceinline__ uint2 load8_unaligned(const uint8_t *p)
 {
     const uintptr_t a = (uintptr_t)p;
+#if FH_ROW_LD64
+    const uint2 *q = (const uint2 *)(a & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(a & 7) * 8;
+    const uint2 lo = __ldg(q), hi = __ldg(q + 1);
+    const bool b = sh >= 32;
+    const uint32_t w0 = b ? lo.y : lo.x, w1 = b ? hi.x : lo.y, w2 = b ? hi.y : hi.x;
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));       // shift amount is taken mod 32
+#else
     const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(a & 3) * 8;
     uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+#endif
 }
 
 // satdLuma8x8MVs (moestimation.cpp:175-195), one row of the reference block with the reference's clamping rule
@@ -126,6 +140,42 @@ __device__ __forceinline__ int feat_dist(const int s[5], int K0, int K1, int K2,
     d += max(ad, iabs_((2 * s[3] - s[0]) + K0 - 2 * K3));
     d += max(ad, iabs_((2 * s[4] - s[0]) + K0 - 2 * K4));
     return d;
+}
+
+// The same distance on the packed feature record {F1|F2<<16, F3|F4<<16, K0, -} with Fk = K0 - 2*Kk (|Fk| <= 8160):
+// the k-th pair is max(|d|, |ck + Fk|) with ck = 2sk - s0, evaluated two at a time in 16-bit lanes
+// (VIADDMNMX.S16x2: max(a + b, c); -(c + F) = ~F + (1 - c) per lane). All lane values stay within +-16320.
+struct FeatQ { uint32_t c12, c34, n12, n34; int s0; };
+__device__ __forceinline__ FeatQ feat_query(const int s[5])
+{
+    FeatQ q;
+    const int c1 = 2 * s[1] - s[0], c2 = 2 * s[2] - s[0], c3 = 2 * s[3] - s[0], c4 = 2 * s[4] - s[0];
+    q.c12 = ((uint32_t)c1 & 0xffffu) | ((uint32_t)c2 << 16); q.c34 = ((uint32_t)c3 & 0xffffu) | ((uint32_t)c4 << 16);
+    q.n12 = ((uint32_t)(1 - c1) & 0xffffu) | ((uint32_t)(1 - c2) << 16); q.n34 = ((uint32_t)(1 - c3) & 0xffffu) | ((uint32_t)(1 - c4) << 16);
+    q.s0 = s[0];
+    return q;
+}
+__device__ __forceinline__ int feat_of(const FeatQ &q, const uint4 v)
+{
+    const int ad = iabs_(q.s0 - (int)v.z);
+    const uint32_t dd = (uint32_t)ad * 0x10001u;
+    uint32_t m12 = __vmaxs2(__vadd2(v.x, q.c12), dd), m34 = __vmaxs2(__vadd2(v.y, q.c34), dd);
+    m12 = __vmaxs2(__vadd2(~v.x, q.n12), m12); m34 = __vmaxs2(__vadd2(~v.y, q.n34), m34);
+    return (int)__dp2a_lo(__vadd2(m12, m34), 0x0101u, (uint32_t)ad);
+}
+__device__ __forceinline__ uint4 feat_record(int k0, int k1, int k2, int k3, int k4)
+{
+    return make_uint4(((uint32_t)(k0 - 2 * k1) & 0xffffu) | ((uint32_t)(k0 - 2 * k2) << 16),
+                      ((uint32_t)(k0 - 2 * k3) & 0xffffu) | ((uint32_t)(k0 - 2 * k4) << 16), (uint32_t)k0, 0u);
+}
+// raw box sums K1..K4 back from a record (index build, debug taps)
+__device__ __forceinline__ int feat_raw(const uint4 v, int k)
+{
+    const int k0 = (int)v.z;
+    if (k == 0) return k0;
+    const uint32_t w = k <= 2 ? v.x : v.y;
+    const int F = (k & 1) ? (int)(int16_t)(w & 0xffffu) : (int)(int16_t)(w >> 16);
+    return (k0 - F) >> 1;
 }
 
 // suma[0..4] of one 8x8 source block held as 8 rows of two words (moestimation.cpp:440-451):

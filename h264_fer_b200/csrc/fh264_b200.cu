@@ -362,7 +362,8 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     CK(cudaEventRecord(s->ev[1], st));
     // persistent wavefront CTAs: two anti-diagonals' worth per sequence — one set working, one set that has already
     // drawn its ticket and prefetched (otherwise ticket + prefetch latency sits on the wavefront's critical path)
-    const unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, (long long)nseq * (g.Wmb + 16));
+    unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, (long long)nseq * (g.Wmb + 16));
+    { static const char *e = getenv("FH264_PB_CTAS"); if (e && atoi(e) > 0) pb_ctas = std::min<unsigned>(pb_ctas, (unsigned)atoi(e)); }
     k_phase_b<<<pb_ctas, PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
     CK(cudaEventRecord(s->ev[2], st));
     dim3 gc((g.band_nmb + 3) / 4, nseq);
@@ -549,7 +550,7 @@ __global__ void k_unpack_feature(const uint4 *__restrict__ kar, int n, int k, ui
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4 v = kar[i];
-    out[i] = (uint16_t)(k == 0 ? v.x & 0xffff : k == 1 ? v.x >> 16 : k == 2 ? v.y & 0xffff : k == 3 ? v.y >> 16 : v.z);
+    out[i] = (uint16_t)feat_raw(v, k);
 }
 
 extern "C" int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out)

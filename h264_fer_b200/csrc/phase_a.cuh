@@ -10,17 +10,21 @@
 #include "warp_select.cuh"
 
 #define COST_INVALID 0xffffffffu
+#ifndef FH_S3_PIPE
+#define FH_S3_PIPE 0
+#endif
+#ifndef FH_S3_SADR
+#define FH_S3_SADR 9      // stage-3 SAD rounds: member loads in flight per lane
+#endif
+#ifndef FH_S2_MINB
+#define FH_S2_MINB 12     // fast stage-2 launch: 80 registers, 12 CTAs per SM
+#endif
 
 __device__ __forceinline__ void part_origin(const Geo &g, int part, int &xP, int &yP)
 {
     const int mb = part >> 2, pi = part & 3;
     xP = (mb % g.Wmb) * 16 + (pi & 1) * 8;
     yP = (mb / g.Wmb) * 16 + (pi >> 1) * 8;
-}
-
-__device__ __forceinline__ int feat_of(const int s[5], const uint4 v)
-{
-    return feat_dist(s, (int)(v.x & 0xffff), (int)(v.x >> 16), (int)(v.y & 0xffff), (int)(v.y >> 16), (int)v.z);
 }
 
 // Loads the 8x8 source block of a partition (8 rows of two words) into every lane's registers.
@@ -37,14 +41,69 @@ __device__ __forceinline__ uint2 pick_row(const uint2 rows[8], int r)
     return cr;
 }
 
-// arrival index of the stage-3 list -> displacement and fraction
-__device__ __forceinline__ void s3_decode(int i, int n3a, int w3, int g3, int w1, int g1, int &dx, int &dy, int &f)
+// arrival index of the stage-3 list -> displacement and fraction (i3 / i1 = 2^32 / w + 1: exact quotients by one IMAD.HI)
+__device__ __forceinline__ void s3_decode(int i, int n3a, int w3, int g3, uint32_t i3, int w1, int g1, uint32_t i1, int &dx, int &dy, int &f)
 {
-    if (i < n3a) { const int c = i / w3; dx = c - g3; dy = i - c * w3 - g3; f = 0; }
-    else { const int t = i - n3a, pos = t >> 4, c = pos / w1; f = t & 15; dx = c - g1; dy = pos - c * w1 - g1; }
+    const bool a = i < n3a;
+    const int t = a ? i : (i - n3a) >> 4, w = a ? w3 : w1, gg = a ? g3 : g1;
+    const int c = (int)__umulhi((uint32_t)t, a ? i3 : i1);
+    dx = c - gg; dy = t - c * w - gg; f = a ? 0 : (i - n3a) & 15;
 }
 
 struct S3Warp { WarpSelScratch ws; uint16_t members[FH_S3_MAX + 1]; uint16_t msad[FH_S3_MAX + 1]; };
+
+// Selection of the K = min(k, nvalid) smallest (cost, arrival index) pairs of cost[0..n-1] (0xffffffff = no candidate) when
+// every lane already holds the two smallest COSTS (m1 <= m2) of the elements it produced. The bound on the K-th cost
+// is the one of warp_select_smallest; survivors are the elements with cost <= bound (ties included), ranked exactly by
+// the 64-bit (cost, index) key. Same contract as warp_select_smallest.
+__device__ __forceinline__ int warp_select_costs(const uint32_t *cost, int n, int k, int nvalid, uint32_t m1, uint32_t m2, WarpSelScratch *ws, uint16_t *members)
+{
+    const int lane = threadIdx.x & 31;
+    const int K = min(k, nvalid);
+    if (K == 0) return 0;
+    const int L1 = __popc(__ballot_sync(0xffffffffu, m1 != COST_INVALID));
+    const int L2 = __popc(__ballot_sync(0xffffffffu, m2 != COST_INVALID));
+    uint32_t thr = COST_INVALID - 1;
+    if (L1 >= K) thr = __reduce_max_sync(0xffffffffu, m1 != COST_INVALID ? m1 : 0u);
+    else if (L1 + 1 >= K && L2 >= 1) thr = max(__reduce_max_sync(0xffffffffu, m1 != COST_INVALID ? m1 : 0u), __reduce_min_sync(0xffffffffu, m2));
+    else if (2 * L2 >= K) thr = __reduce_max_sync(0xffffffffu, m2 != COST_INVALID ? m2 : 0u);
+    int ns = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const uint32_t c = i < n ? cost[i] : COST_INVALID;
+        const bool sv = c <= thr;                              // COST_INVALID > thr always
+        const unsigned b = __ballot_sync(0xffffffffu, sv);
+        if (sv) {
+            const int pos = ns + __popc(b & ((1u << lane) - 1u));
+            if (pos < WSEL_CAP) { ws->skey[pos] = ((u64)c << 16) | (u64)i; ws->sidx[pos] = (uint16_t)i; }
+        }
+        ns += __popc(b);
+    }
+    __syncwarp();
+    if (ns <= WSEL_CAP) {
+        for (int s = lane; s < ns; s += 64) {
+            const u64 ka = ws->skey[s];
+            const bool hb = s + 32 < ns;
+            const u64 kb = hb ? ws->skey[s + 32] : 0ull;
+            int ra = 0, rb = 0;
+            for (int j = 0; j < ns; j++) { const u64 kj = ws->skey[j]; ra += kj < ka; rb += kj < kb; }
+            if (ra < K) members[ra] = ws->sidx[s];
+            if (hb && rb < K) members[rb] = ws->sidx[s + 32];
+        }
+    } else {
+        // degenerate (flat content / hundreds of equal costs): rank against every candidate
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t c = cost[i];
+            if (c > thr) continue;
+            const u64 key = ((u64)c << 16) | (u64)i;
+            int rank = 0;
+            for (int j = 0; j < n && rank < K; j++) rank += (((u64)cost[j] << 16) | (u64)j) < key;
+            if (rank < K) members[rank] = (uint16_t)i;
+        }
+    }
+    __syncwarp();
+    return K;
+}
 
 __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad)
 {
@@ -60,85 +119,132 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
     load_cur8x8(S.cur[0], g, xP, yP, rows);
     int s[5];
     block_sums(rows, s);
+    const FeatQ fq = feat_query(s);
     const int W = g.W, H = g.H;
     const int g3 = prm.window / 2, g1 = prm.window / 16;
     const int w3 = 2 * g3 + 1, w1 = 2 * g1 + 1;
     const int n3a = w3 * w3, n3b = w1 * w1 * 16, N = n3a + n3b;
+    const uint32_t i3 = 0xffffffffu / (uint32_t)w3 + 1u, i1 = 0xffffffffu / (uint32_t)w1 + 1u;
     const uint4 *__restrict__ K0p = S.kar;
+    uint32_t m1 = COST_INVALID, m2 = COST_INVALID;     // this lane's two smallest costs so far (selection bound)
     // first call: MEstimation(g = window/2, frac 0); arrival index = (dx + g3) * w3 + (dy + g3).
-    // Full 32-column chunks: lane = column (coalesced 16-byte loads), 4 rows in flight.
+    // lane = column (coalesced 16-byte loads), 4 rows in flight; rows [rlo, rhi) lie inside the picture.
+    const int rlo = max(0, g3 - yP), rhi = min(w3, H - yP + g3);
     const int ncf = w3 & ~31;
     for (int cb = 0; cb < ncf; cb += 32) {
         const int c = cb + lane, dx = c - g3, rx = xP + dx;
         const bool xok = rx >= 0 && rx < W;
         const int adx = iabs_(dx) + 4;
-        for (int r0 = 0; r0 < w3; r0 += 4) {
-            uint4 v[4];
+        uint32_t *cc = cost + c * w3;
+        for (int r = 0; r < rlo; r++) cc[r] = COST_INVALID;
+        for (int r = rhi; r < w3; r++) cc[r] = COST_INVALID;
+        // software pipeline: the loads of the next 4 rows are in flight while the current 4 are evaluated
+        const uint4 *kp = K0p + (size_t)(yP - g3 + rlo) * W + rx;
+        auto ld4 = [&](const uint4 *q, int r0, uint4 (&v)[4]) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int ry = yP + r0 + u - g3;
-                v[u] = make_uint4(0, 0, 0, 1u);
-                if (xok && r0 + u < w3 && ry >= 0 && ry < H) v[u] = __ldg(K0p + (size_t)ry * W + rx);
-            }
+            for (int u = 0; u < 4; u++) { v[u] = make_uint4(0, 0, 0, 0); if (xok && r0 + u < rhi) v[u] = __ldg(q + (size_t)u * W); }
+        };
+        auto ev4 = [&](const uint4 (&v)[4], int r0) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int r = r0 + u;
-                if (r < w3) cost[c * w3 + r] = v[u].w ? COST_INVALID : (uint32_t)((adx + iabs_(r - g3)) * feat_of(s, v[u]));
+                if (r < rhi) {
+                    const uint32_t cst = xok ? (uint32_t)((adx + iabs_(r - g3)) * feat_of(fq, v[u])) : COST_INVALID;
+                    cc[r] = cst;
+                    m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
+                }
             }
+        };
+#if FH_S3_PIPE
+        uint4 va[4], vb[4];
+        ld4(kp, rlo, va);
+        for (int r0 = rlo; r0 < rhi; r0 += 8) {
+            ld4(kp + (size_t)4 * W, r0 + 4, vb);
+            ev4(va, r0);
+            ld4(kp + (size_t)8 * W, r0 + 8, va);
+            ev4(vb, r0 + 4);
+            kp += (size_t)8 * W;
         }
+#else
+        uint4 va[4];
+        for (int r0 = rlo; r0 < rhi; r0 += 4) { ld4(kp, r0, va); ev4(va, r0); kp += (size_t)4 * W; }
+#endif
     }
     // leftover columns: lane = row
     for (int c = ncf; c < w3; c++) {
         const int dx = c - g3, rx = xP + dx;
         const bool xok = rx >= 0 && rx < W;
         for (int r = lane; r < w3; r += 32) {
-            const int ry = yP + r - g3;
             uint32_t cst = COST_INVALID;
-            if (xok && ry >= 0 && ry < H) cst = (uint32_t)((iabs_(dx) + iabs_(r - g3) + 4) * feat_of(s, __ldg(K0p + (size_t)ry * W + rx)));
+            if (xok && r >= rlo && r < rhi) cst = (uint32_t)((iabs_(dx) + iabs_(r - g3) + 4) * feat_of(fq, __ldg(K0p + (size_t)(yP + r - g3) * W + rx)));
             cost[c * w3 + r] = cst;
+            m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
         }
     }
     // second call: MEstimation(g = window/16, all 16 fractions); arrival = ((dx+g1)*w1 + (dy+g1))*16 + frac.
     // lane -> (fraction = lane & 15, position parity = lane >> 4); 4 loads in flight
     {
-        const int f = lane & 15, npos = w1 * w1, inv1 = 65536 / w1 + 1;
+        const int f = lane & 15, npos = w1 * w1;
         const uint4 *__restrict__ Kf = S.kar + (size_t)f * g.WH;
-        for (int p0 = 0; p0 < npos; p0 += 8) {
-            uint4 v[4];
+        auto ld4 = [&](int p0, uint4 (&v)[4], unsigned &okm) {
+            okm = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), rx = xP + cx - g1, ry = yP + pos - cx * w1 - g1;
-                v[u] = make_uint4(0, 0, 0, 1u);
-                if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) v[u] = __ldg(Kf + (size_t)ry * W + rx);
+                const int pos = p0 + 2 * u + (lane >> 4), cx = (int)__umulhi((uint32_t)pos, i1), rx = xP + cx - g1, ry = yP + pos - cx * w1 - g1;
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) { v[u] = __ldg(Kf + (size_t)ry * W + rx); okm |= 1u << u; }
             }
+        };
+        auto ev4 = [&](int p0, const uint4 (&v)[4], unsigned okm) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int pos = p0 + 2 * u + (lane >> 4), cx = fdiv_(pos, inv1), dx = cx - g1, dy = pos - cx * w1 - g1;
-                if (pos < npos) cost[n3a + pos * 16 + f] = v[u].w ? COST_INVALID : (uint32_t)((iabs_(dx) + iabs_(dy) + 4) * feat_of(s, v[u]));
+                const int pos = p0 + 2 * u + (lane >> 4), cx = (int)__umulhi((uint32_t)pos, i1), dx = cx - g1, dy = pos - cx * w1 - g1;
+                if (pos < npos) {
+                    const uint32_t cst = ((okm >> u) & 1u) ? (uint32_t)((iabs_(dx) + iabs_(dy) + 4) * feat_of(fq, v[u])) : COST_INVALID;
+                    cost[n3a + pos * 16 + f] = cst;
+                    m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
+                }
             }
+        };
+#if FH_S3_PIPE
+        uint4 va[4], vb[4];
+        unsigned oa, ob;
+        ld4(0, va, oa);
+        for (int p0 = 0; p0 < npos; p0 += 16) {
+            ld4(p0 + 8, vb, ob);
+            ev4(p0, va, oa);
+            ld4(p0 + 16, va, oa);
+            ev4(p0 + 8, vb, ob);
         }
+#else
+        uint4 va[4];
+        unsigned oa;
+        for (int p0 = 0; p0 < npos; p0 += 8) { ld4(p0, va, oa); ev4(p0, va, oa); }
+#endif
     }
     __syncwarp();
+    // candidates = positions whose block origin lies inside the picture (:263-266)
+    const int nva = max(0, min(W - 1, xP + g3) - max(0, xP - g3) + 1) * max(0, rhi - rlo);
+    const int nvb = max(0, min(W - 1, xP + g1) - max(0, xP - g1) + 1) * max(0, min(H - 1, yP + g1) - max(0, yP - g1) + 1) * 16;
     // the 33 smallest by (cost, arrival index), in list order
-    const int nm = warp_select_smallest(N, FH_S3_MAX, [&](int i) -> u64 { const uint32_t c = cost[i]; return c == COST_INVALID ? KEY_NONE : (((u64)c << 16) | (u64)i); },
-                                        &sw->ws, sw->members);
+    const int nm = warp_select_costs(cost, N, FH_S3_MAX, nva + nvb, m1, m2, &sw->ws, sw->members);
     // SADs of the members (satdLuma8x8MVs): 8 lanes per member, one row each; 3 rounds of loads in flight
     const int r = lane & 7;
     const uint2 cr = pick_row(rows, r);
-    for (int base = 0; base < nm; base += 12) {
-        uint2 rr[3];
+    for (int base = 0; base < nm; base += 4 * FH_S3_SADR) {
+        uint2 rr[FH_S3_SADR];                           // 33 members x 8 rows = 264 row loads
 #pragma unroll
-        for (int u = 0; u < 3; u++) {
+        for (int u = 0; u < FH_S3_SADR; u++) {
             const int m = base + u * 4 + (lane >> 3);
             rr[u] = make_uint2(0, 0);
             if (m < nm) {
                 int dx, dy, f;
-                s3_decode((int)sw->members[m], n3a, w3, g3, w1, g1, dx, dy, f);
+                s3_decode((int)sw->members[m], n3a, w3, g3, i3, w1, g1, i1, dx, dy, f);
                 rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, xP + dx, yP + dy + r);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 3; u++) {
+        for (int u = 0; u < FH_S3_SADR; u++) {
             const int m = base + u * 4 + (lane >> 3);
             int sad = m < nm ? sad8(cr, rr[u]) : 0;
             sad += __shfl_xor_sync(0xffffffffu, sad, 1);
@@ -150,7 +256,7 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
     __syncwarp();
     for (int m = lane; m < nm; m += 32) {
         int dx, dy, f;
-        s3_decode((int)sw->members[m], n3a, w3, g3, w1, g1, dx, dy, f);
+        s3_decode((int)sw->members[m], n3a, w3, g3, i3, w1, g1, i1, dx, dy, f);
         S3Entry e;
         e.mvx = (int16_t)((dx << 2) | (f & 3)); e.mvy = (int16_t)((dy << 2) | (f >> 2)); e.sad = sw->msad[m]; e.pad = 0;
         S.s3[(size_t)part * FH_S3_MAX + m] = e;
@@ -182,7 +288,7 @@ struct S2Warp {
 // CAP = survivor capacity per warp, NW = warps (= partitions) per CTA. The main launch (CAP = 512) keeps shared memory
 // small for occupancy; partitions with more gated survivors are marked and redone by a second launch with CAP = 4096.
 template <int CAP, int NW, bool REDO>
-__global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
+__global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
 {
     __shared__ S2Warp<CAP> sm[NW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -298,16 +404,21 @@ __global__ void __launch_bounds__(32 * NW) k_stage2(const SeqDev *__restrict__ s
         nchunk += __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
         if (nchunk > S2_CHUNK_CAP - 256 || it0 + 32 >= nitems) {
-            // lanes stride the chunk list: balanced work, 8 sequential 16-byte loads in flight
+            // 32 chunks per round: 8 lanes share a chunk (one 128-byte line per 8 lanes: coalesced, 4 lines per load
+            // instruction instead of 32), lane takes entry (lane & 7) of chunks c0 + (lane >> 3) + 4u; 8 loads in flight
             for (int c0 = 0; c0 < nchunk; c0 += 32) {
-                const int cidx = c0 + lane;
-                const uint32_t cw = cidx < nchunk ? w->chunk[cidx] : 0u, e0 = cw & 0x0fffffffu;
-                const int cnt = cidx < nchunk ? (int)(cw >> 28) + 1 : 0;
                 uint4 v[8];
+                uint32_t eid[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = u < cnt ? __ldg(tent + e0 + u) : make_uint4(0, 0xffffu, 0, 0);
+                for (int u = 0; u < 8; u++) {
+                    const int cidx = c0 + 4 * u + (lane >> 3);
+                    const uint32_t cw = cidx < nchunk ? w->chunk[cidx] : 0u;
+                    const int cnt = cidx < nchunk ? (int)(cw >> 28) + 1 : 0;
+                    eid[u] = (cw & 0x0fffffffu) + (uint32_t)(lane & 7);
+                    v[u] = (lane & 7) < cnt ? __ldg(tent + eid[u]) : make_uint4(0, 0xffffu, 0, 0);
+                }
 #pragma unroll
-                for (int u = 0; u < 8; u++) visit(v[u], e0 + u);
+                for (int u = 0; u < 8; u++) visit(v[u], eid[u]);
                 tighten();                                  // at most 256 entries were added since the last check
             }
             nchunk = 0;

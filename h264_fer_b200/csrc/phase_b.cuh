@@ -425,19 +425,20 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         {
             int s[5];
             block_sums(rows, s);                                       // suma[0..4] (:440-451)
+            const FeatQ fq = feat_query(s);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int pos = (tid >> 4) + 8 * u, cx = fdiv_(pos, inv1), ox = cx - g1, oy = pos - cx * w1 - g1;
                 if (pos < npos) {
                     const int i = pos * 16 + f1;
-                    sh.keys1[i] = v1[u].w ? COST_INVALID : (((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(s, v1[u])) << 11) | (uint32_t)i);
+                    sh.keys1[i] = v1[u].w ? COST_INVALID : (((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(fq, v1[u])) << 11) | (uint32_t)i);
                 }
             }
             // windows beyond 32 positions (WindowSize 64): remaining positions, plain loop
             for (int pos = 32 + (tid >> 4); pos < npos; pos += 8) {
                 const int cx = fdiv_(pos, inv1), ox = cx - g1, oy = pos - cx * w1 - g1, rx = xP + genx + ox, ry = yP + geny + oy, i = pos * 16 + f1;
                 uint32_t key = COST_INVALID;
-                if (rx >= 0 && rx < W && ry >= 0 && ry < H) key = ((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(s, __ldg(Kf + (size_t)ry * W + rx))) << 11) | (uint32_t)i;
+                if (rx >= 0 && rx < W && ry >= 0 && ry < H) key = ((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(fq, __ldg(Kf + (size_t)ry * W + rx))) << 11) | (uint32_t)i;
                 sh.keys1[i] = key;
             }
         }

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seq
         const int k1 = a[q & 7] + a[(q + 1) & 7] + a[(q + 2) & 7] + a[(q + 3) & 7];
         const int k3 = a[q & 7] + a[(q + 1) & 7] + a[(q + 4) & 7] + a[(q + 5) & 7];
         // K0: 8x8 (:137) | K1: rows 0-3 (:136) ; K2: columns 0-3 (:135) | K3: rows 0,1,4,5 (:133-134) ; K4: columns 0,1,4,5 (:131-132)
-        if (y < H) K[(size_t)y * W + x] = make_uint4((uint32_t)k0 | ((uint32_t)k1 << 16), (uint32_t)k2 | ((uint32_t)k3 << 16), (uint32_t)k4, 0u);
+        if (y < H) K[(size_t)y * W + x] = feat_record(k0, k1, k2, k3, k4);
         if (q + 1 < FT_H / 4) {
             const int na = r8[rs + q + 8][tx], n4 = r4[rs + q + 8][tx], nc = rc[rs + q + 8][tx];
             k0 += na - a[q & 7]; k2 += n4 - q4[q & 7]; k4 += nc - qc[q & 7];
@@ -144,15 +144,15 @@ __global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ s
     const int tile = blockIdx.x, tid = threadIdx.x;
     const int tx0 = (tile % g.tilesx) * FH_TILE, ty0 = (tile / g.tilesx) * FH_TILE;
     const int tw = min(FH_TILE, g.W - tx0), th = min(FH_TILE, g.H - ty0);
-    const uint4 *__restrict__ K = S.kar;      // plane 0 (f = 0): {K0|K1<<16, K2|K3<<16, K4, 0}
+    const uint4 *__restrict__ K = S.kar;      // plane 0 (f = 0) feature records
     for (int i = tid; i < FH_CELLS; i += 256) hist[i] = 0;
     __syncthreads();
     bool ub = false;
     for (int i = tid; i < tw * th; i += 256) {
         int ly = i / tw, lx = i - ly * tw;
         size_t o = (size_t)(ty0 + ly) * g.W + tx0 + lx;
-        const uint32_t w0 = K[o].x;
-        int k0 = w0 & 0xffff, k1 = w0 >> 16;
+        const uint4 kv = K[o];
+        const int k0 = feat_raw(kv, 0), k1 = feat_raw(kv, 1);
         ub |= (k0 == 0) | (k0 >= 16203);
         atomicAdd(&hist[((k0 >> 7) << 7) | (k1 >> 6)], 1u);
     }
@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ s
         const uint4 kv = K[o];
         TileEntry e;
         e.x = (uint16_t)(tx0 + lx); e.y = (uint16_t)(ty0 + ly);
-        e.k0 = (uint16_t)(kv.x & 0xffff); e.k1 = (uint16_t)(kv.x >> 16); e.k2 = (uint16_t)(kv.y & 0xffff);
-        e.k3 = (uint16_t)(kv.y >> 16); e.k4 = (uint16_t)kv.z; e.pad = 0;
+        e.k0 = (uint16_t)feat_raw(kv, 0); e.k1 = (uint16_t)feat_raw(kv, 1); e.k2 = (uint16_t)feat_raw(kv, 2);
+        e.k3 = (uint16_t)feat_raw(kv, 3); e.k4 = (uint16_t)feat_raw(kv, 4); e.pad = 0;
         uint32_t pos = atomicAdd(&hist[((e.k0 >> 7) << 7) | (e.k1 >> 6)], 1u);
         *(uint4 *)&te[pos] = *(const uint4 *)&e;
     }

@@ -36,7 +36,8 @@ class Params(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(HERE, "libfh264_b200.so")
+    # FH264_B200_LIB: development only — an alternative BUILD of this same library (A/B kernel experiments)
+    return os.environ.get("FH264_B200_LIB") or os.path.join(HERE, "libfh264_b200.so")
 
 
 _lib = None

@@ -363,7 +363,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     // persistent wavefront CTAs: two anti-diagonals' worth per sequence — one set working, one set that has already
     // drawn its ticket and prefetched (otherwise ticket + prefetch latency sits on the wavefront's critical path)
     unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, (long long)nseq * (g.Wmb + 16));
-    { static const char *e = getenv("FH264_PB_CTAS"); if (e && atoi(e) > 0) pb_ctas = std::min<unsigned>(pb_ctas, (unsigned)atoi(e)); }
+    { static const char *e = getenv("FH264_PB_CTAS"); if (e && atoi(e) > 0) pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, atoll(e)); }   // development knob
     k_phase_b<<<pb_ctas, PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
     CK(cudaEventRecord(s->ev[2], st));
     dim3 gc((g.band_nmb + 3) / 4, nseq);

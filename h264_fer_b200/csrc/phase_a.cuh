@@ -16,6 +16,22 @@
 #ifndef FH_S3_SADR
 #define FH_S3_SADR 9      // stage-3 SAD rounds: member loads in flight per lane
 #endif
+#ifndef FH_S2_SIMD
+#define FH_S2_SIMD 1
+#endif
+#ifndef FH_S2_UNR
+#define FH_S2_UNR 4        // index entries in flight per lane in the stage-2 visit loop
+#endif
+#ifndef FH_S2_SADR
+#define FH_S2_SADR 8       // stage-2 SAD: candidate rows in flight per lane
+#endif
+#ifndef FH_S3_UNR
+#define FH_S3_UNR 4
+#endif
+#ifndef FH_X_SKIPA
+#define FH_X_SKIPA 0     // experiments only: drop the stage-3 feature loads (wrong results, timing probes)
+#define FH_X_SKIPB 0
+#endif
 #ifndef FH_S2_MINB
 #define FH_S2_MINB 12     // fast stage-2 launch: 80 registers, 12 CTAs per SM
 #endif
@@ -140,13 +156,13 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
         for (int r = rhi; r < w3; r++) cc[r] = COST_INVALID;
         // software pipeline: the loads of the next 4 rows are in flight while the current 4 are evaluated
         const uint4 *kp = K0p + (size_t)(yP - g3 + rlo) * W + rx;
-        auto ld4 = [&](const uint4 *q, int r0, uint4 (&v)[4]) {
+        auto ld4 = [&](const uint4 *q, int r0, uint4 (&v)[FH_S3_UNR]) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) { v[u] = make_uint4(0, 0, 0, 0); if (xok && r0 + u < rhi) v[u] = __ldg(q + (size_t)u * W); }
+            for (int u = 0; u < FH_S3_UNR; u++) { v[u] = make_uint4(0, 0, 0, 0); if (xok && r0 + u < rhi && !FH_X_SKIPA) v[u] = __ldg(q + (size_t)u * W); }
         };
-        auto ev4 = [&](const uint4 (&v)[4], int r0) {
+        auto ev4 = [&](const uint4 (&v)[FH_S3_UNR], int r0) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < FH_S3_UNR; u++) {
                 const int r = r0 + u;
                 if (r < rhi) {
                     const uint32_t cst = xok ? (uint32_t)((adx + iabs_(r - g3)) * feat_of(fq, v[u])) : COST_INVALID;
@@ -156,7 +172,7 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
             }
         };
 #if FH_S3_PIPE
-        uint4 va[4], vb[4];
+        uint4 va[FH_S3_UNR], vb[FH_S3_UNR];
         ld4(kp, rlo, va);
         for (int r0 = rlo; r0 < rhi; r0 += 8) {
             ld4(kp + (size_t)4 * W, r0 + 4, vb);
@@ -166,8 +182,8 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
             kp += (size_t)8 * W;
         }
 #else
-        uint4 va[4];
-        for (int r0 = rlo; r0 < rhi; r0 += 4) { ld4(kp, r0, va); ev4(va, r0); kp += (size_t)4 * W; }
+        uint4 va[FH_S3_UNR];
+        for (int r0 = rlo; r0 < rhi; r0 += FH_S3_UNR) { ld4(kp, r0, va); ev4(va, r0); kp += (size_t)FH_S3_UNR * W; }
 #endif
     }
     // leftover columns: lane = row
@@ -192,7 +208,7 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
             for (int u = 0; u < 4; u++) {
                 const int pos = p0 + 2 * u + (lane >> 4), cx = (int)__umulhi((uint32_t)pos, i1), rx = xP + cx - g1, ry = yP + pos - cx * w1 - g1;
                 v[u] = make_uint4(0, 0, 0, 0);
-                if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) { v[u] = __ldg(Kf + (size_t)ry * W + rx); okm |= 1u << u; }
+                if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) { if (!FH_X_SKIPB) v[u] = __ldg(Kf + (size_t)ry * W + rx); okm |= 1u << u; }
             }
         };
         auto ev4 = [&](int p0, const uint4 (&v)[4], unsigned okm) {
@@ -318,6 +334,27 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
     // upper bound of j_stop (counts only grow, so the first j whose running total exceeds 128 can only move down). The
     // feature distance is computed afterwards in a dense pass over the kept entries.
     int jb = 180;
+#if FH_S2_SIMD
+    // the four gates in 16-bit lanes: (|dx|, |dy|) and (j, |dK1|) by max(a - b, b - a), the Manhattan sum by a dot product
+    const uint32_t Pxy = (uint32_t)xP | ((uint32_t)yP << 16), S01 = (uint32_t)s[0] | ((uint32_t)s[1] << 16), LIM01 = 180u | (99u << 16);
+    const int s2m = s[2] - 99;
+    auto visit = [&](const uint4 v, uint32_t eidx) {
+        const uint32_t ad = __vmaxs2(__vsub2(v.x, Pxy), __vsub2(Pxy, v.x)), ae = __vmaxs2(__vsub2(v.y, S01), __vsub2(S01, v.y));
+        const bool ok = __vmaxu2(ae, LIM01) == LIM01 && __dp2a_lo(ad, 0x0101u, 0u) < 280u && (uint32_t)((int)(v.z & 0xffffu) - s2m) < 199u;
+        if (ok) {
+            const int j = (int)(ae & 0xffffu), side = (int)(v.y & 0xffffu) > s[0];
+            atomicAdd(&w->bins[2 * j + side], 1u);
+            if (j <= jb) {
+                const int pos = atomicAdd(&w->n_surv, 1);
+                if (pos < CAP) {
+                    const int dx = (int)(v.x & 0xffffu) - xP, dy = (int)(v.x >> 16) - yP;
+                    w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
+                    w->aval[pos] = eidx;
+                }
+            }
+        }
+    };
+#else
     auto visit = [&](const uint4 v, uint32_t eidx) {
         const int x = v.x & 0xffff, y = v.x >> 16, k0 = v.y & 0xffff, k1 = v.y >> 16, k2 = v.z & 0xffff;
         const int j = iabs_(k0 - s[0]), dx = x - xP, dy = y - yP;
@@ -333,6 +370,7 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
             }
         }
     };
+#endif
     // j_stop bound from the counts so far: first j whose running gated count (bucket s0 twice) exceeds 128 (:496)
     auto bound_from_bins = [&]() -> int {
         uint32_t local = 0, c6[6];
@@ -406,19 +444,19 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
         if (nchunk > S2_CHUNK_CAP - 256 || it0 + 32 >= nitems) {
             // 32 chunks per round: 8 lanes share a chunk (one 128-byte line per 8 lanes: coalesced, 4 lines per load
             // instruction instead of 32), lane takes entry (lane & 7) of chunks c0 + (lane >> 3) + 4u; 8 loads in flight
-            for (int c0 = 0; c0 < nchunk; c0 += 32) {
-                uint4 v[8];
-                uint32_t eid[8];
+            for (int c0 = 0; c0 < nchunk; c0 += 4 * FH_S2_UNR) {
+                uint4 v[FH_S2_UNR];
+                uint32_t eid[FH_S2_UNR];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                for (int u = 0; u < FH_S2_UNR; u++) {
                     const int cidx = c0 + 4 * u + (lane >> 3);
                     const uint32_t cw = cidx < nchunk ? w->chunk[cidx] : 0u;
                     const int cnt = cidx < nchunk ? (int)(cw >> 28) + 1 : 0;
                     eid[u] = (cw & 0x0fffffffu) + (uint32_t)(lane & 7);
-                    v[u] = (lane & 7) < cnt ? __ldg(tent + eid[u]) : make_uint4(0, 0xffffu, 0, 0);
+                    v[u] = (lane & 7) < cnt ? __ldg(tent + eid[u]) : make_uint4(0, 0xffffu, 0x7fffu, 0);
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) visit(v[u], eid[u]);
+                for (int u = 0; u < FH_S2_UNR; u++) visit(v[u], eid[u]);
                 tighten();                                  // at most 256 entries were added since the last check
             }
             nchunk = 0;
@@ -525,11 +563,11 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
     const int r = lane & 7;
     const uint2 cr = pick_row(rows, r);
     const int nuniq = n2 - cnt0;          // distinct candidates: slots [0, cnt0) and [2*cnt0, n2)
-    for (int base = 0; base < nuniq; base += 32) {
-        uint2 rr[8];
-        int idx[8];
+    for (int base = 0; base < nuniq; base += 4 * FH_S2_SADR) {
+        uint2 rr[FH_S2_SADR];
+        int idx[FH_S2_SADR];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < FH_S2_SADR; u++) {
             const int m = base + u * 4 + (lane >> 3);
             rr[u] = make_uint2(0, 0); idx[u] = -1;
             if (m < nuniq) {
@@ -540,7 +578,7 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
             }
         }
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < FH_S2_SADR; u++) {
             int sad = idx[u] >= 0 ? sad8(cr, rr[u]) : 0;
             sad += __shfl_xor_sync(0xffffffffu, sad, 1);
             sad += __shfl_xor_sync(0xffffffffu, sad, 2);

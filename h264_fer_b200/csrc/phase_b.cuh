@@ -259,7 +259,9 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     NbCache &nc = sh.nc;
     long long *dbg = S.dbg ? S.dbg + (size_t)mb * 24 : nullptr;
 #define PB_STAMP(k) do { if (dbg && tid == 0) dbg[k] = gtime_ns(); } while (0)
+#define PB_SUB(k) do { if (dbg && tid == 0 && pi == 1) dbg[k] = gtime_ns(); } while (0)
     PB_STAMP(0);
+    if (dbg && tid == 0) { dbg[10] = 0; dbg[11] = 0; }
 
     // ---- everything that does not depend on the neighbours is fetched BEFORE waiting on them: the CTA is resident
     //      long before its turn, so these round trips are off the wavefront's critical path
@@ -274,23 +276,20 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         sh.pa[tid].n2 = 0; sh.pa[tid].n3 = 0; sh.pa[tid].s2_off = 0;
     }
     PB_STAMP(1);
-    // ---- wait for the dependencies. `done[mb]` = epoch * 8 + number of 8x8 quadrants whose MV is final (4 when the MB is
-    //      finished or P_Skip). This MB's P_Skip test and partitions 0/1 need the left MB's quadrant 1 and the up-right
-    //      MB's quadrant 2 plus the complete MBs above / above-left; only partition 2 needs the left MB's quadrant 3. So a
-    //      macroblock starts when its left neighbour is HALF done: successive MBs of a row overlap by two partitions.
+    // ---- dependencies. `done[mb]` = epoch * 8 + number of 8x8 quadrants whose MV is final (4 when the MB is finished or
+    //      P_Skip). The row ABOVE is waited for here (up-right quadrant 2, up and up-left complete). The LEFT neighbour is
+    //      only waited for where a predictor really depends on it: a median of three with two equal inputs is that input,
+    //      so wherever the motion field above is locally uniform (up q2 == up q3, up q2 == up-right q2, own q0 == q1) the
+    //      P_Skip decision and the partition predictors are known without the left MB and the row's serial chain is cut.
     const uint32_t pbase = epoch * 8u;
     const bool sysw = g.world > 1;                       // band mode: the row above this band is written by another GPU
     const bool mirror = S.peer_done_next != nullptr && mby == (g.band_mb0 + g.band_nmb) / g.Wmb - 1;   // band's last MB row
-    if (tid == 0) {
+    if (tid == 0 && mby > 0) {
         bool ok = true;
-        if (mbx > 0) ok &= wait_progress(&S.done[mb - 1], pbase + 2u, false);
-        if (mby > 0) {
-            if (mbx < g.Wmb - 1) ok &= wait_progress(&S.done[mb - g.Wmb + 1], pbase + 3u, sysw);
-            // the MBs above and above-left must be complete; a P_Skip up-right neighbour does not imply it (it never
-            // waited for its own left neighbour to finish)
-            ok &= wait_progress(&S.done[mb - g.Wmb], pbase + 4u, sysw);
-            if (mbx > 0) ok &= wait_progress(&S.done[mb - g.Wmb - 1], pbase + 4u, sysw);
-        }
+        if (mbx < g.Wmb - 1) ok &= wait_progress(&S.done[mb - g.Wmb + 1], pbase + 3u, sysw);
+        // the MBs above and above-left must be complete; a P_Skip up-right neighbour does not imply it
+        ok &= wait_progress(&S.done[mb - g.Wmb], pbase + 4u, sysw);
+        if (mbx > 0) ok &= wait_progress(&S.done[mb - g.Wmb - 1], pbase + 4u, sysw);
         if (!ok) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
     }
     __syncthreads();
@@ -300,21 +299,32 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         const int nmb = w == 0 ? mb - 1 : (w == 1 ? mb - g.Wmb : (w == 2 ? mb - g.Wmb + 1 : mb - g.Wmb - 1));
         const bool av = w == 0 ? mbx > 0 : (w == 1 ? mby > 0 : (w == 2 ? (mby > 0 && mbx < g.Wmb - 1) : (mby > 0 && mbx > 0)));
         int vx = 0, vy = 0;
-        if (av) { const int v = __ldcg((const int *)&S.motion[nmb].mv[q][0]); vx = (int16_t)(v & 0xffff); vy = v >> 16; }
-        nc.mvx[w][q] = vx; nc.mvy[w][q] = vy;
+        if (av && w != 0) { const int v = __ldcg((const int *)&S.motion[nmb].mv[q][0]); vx = (int16_t)(v & 0xffff); vy = v >> 16; }
+        nc.mvx[w][q] = vx; nc.mvy[w][q] = vy;           // the left MB's quadrants 1 / 3 are fetched on demand (fetch_left)
         if (q == 0) nc.avail[w] = av;
     }
     __syncthreads();
+    const bool leftA = mbx > 0;
+    bool left1 = !leftA, left3 = !leftA;                 // left quadrant 1 / 3 present in nc (or not needed)
+    auto fetch_left = [&](int q, uint32_t need, int where) {        // block-uniform: wait until the left MB has published `need` quadrants
+        if (tid == 0) {
+            const long long t0 = dbg ? gtime_ns() : 0;
+            if (!wait_progress(&S.done[mb - 1], pbase + need, false)) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
+            const int v = __ldcg((const int *)&S.motion[mb - 1].mv[q][0]);
+            nc.mvx[0][q] = (int16_t)(v & 0xffff); nc.mvy[0][q] = v >> 16;
+            if (dbg) { dbg[10] += 1ll << (8 * where); dbg[11] += gtime_ns() - t0; }      // timeline: where and how long the left MB was waited for
+        }
+        __syncthreads();
+    };
+    // neighbour quadrant MVs used by the predictors, in registers (A.7): up q2/q3, up-right q2, up-left q3
+    const int aL = nc.avail[0], aU = nc.avail[1], aUR = nc.avail[2], aUL = nc.avail[3];
+    const int u2x = nc.mvx[1][2], u2y = nc.mvy[1][2], u3x = nc.mvx[1][3], u3y = nc.mvy[1][3];
+    const int r2x = nc.mvx[2][2], r2y = nc.mvy[2][2], d3x = nc.mvx[3][3], d3y = nc.mvy[3][3];
 
     PB_STAMP(3);
-    // ---- P_Skip trial ---------------------------------------------------------------------------------------
+    // ---- P_Skip trial (mode_pred.cpp:383-401, moestimation.cpp:402-425) -----------------------------------------
     int zero4[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
-    int smx = 0, smy = 0;
-    if (mbx > 0 && mby > 0 && !(nc.mvx[1][2] == 0 && nc.mvy[1][2] == 0) && !(nc.mvx[0][1] == 0 && nc.mvy[0][1] == 0))
-        predict_mv_(nc, 0, 0, 16, 0, zero4, smx, smy);                    // mode_pred.cpp:383-401
     const int py = tid >> 3, px = (tid & 7) * 2;                          // this thread's two luma samples
-    int p2[2];
-    luma_pred_block<2, 1>(S, g, mbx * 16 + px + (smx >> 2), mby * 16 + py + (smy >> 2), smx & 3, smy & 3, p2);
     const int c0 = sh.cur[py][px], c1 = sh.cur[py][px + 1];
     int maxdiff = prm.maxdiff_set;
     if (prm.maxdiff_set == -1) {                                          // moestimation.cpp:407-419
@@ -328,7 +338,38 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         __syncthreads();
         maxdiff = max(3, (sh.red[0] + sh.red[1] + sh.red[2] + sh.red[3]) / 256);
     }
-    const int nbad = __syncthreads_count(iabs_(c0 - p2[0]) > maxdiff || iabs_(c1 - p2[1]) > maxdiff);
+    auto skip_pred = [&](int vx, int vy, int (&p2)[2]) {
+        luma_pred_block<2, 1>(S, g, mbx * 16 + px + (vx >> 2), mby * 16 + py + (vy >> 2), vx & 3, vy & 3, p2);
+    };
+    auto skip_bad = [&](const int (&p2)[2]) -> int { return __syncthreads_count(iabs_(c0 - p2[0]) > maxdiff || iabs_(c1 - p2[1]) > maxdiff); };
+    int smx = 0, smy = 0, nbad;
+    if (!leftA || mby == 0 || (u2x == 0 && u2y == 0)) {                  // the skip MV is zero whatever the left MB holds
+        int p2[2];
+        skip_pred(0, 0, p2);
+        nbad = skip_bad(p2);
+    } else {
+        // 16x16 predictor: A = left q1, B = up q2, C = up-right q2 else up-left q3 (all available here)
+        const int cx16 = aUR ? r2x : d3x, cy16 = aUR ? r2y : d3y;
+        if (u2x == cx16 && u2y == cy16) {
+            // B == C: the skip MV is B, or zero if the left quadrant turns out to be zero — try both without waiting
+            int pB[2], p0[2];
+            skip_pred(u2x, u2y, pB);
+            skip_pred(0, 0, p0);
+            const int nbB = skip_bad(pB), nb0 = skip_bad(p0);
+            if (nbB != 0 && nb0 != 0) nbad = 1;
+            else {
+                fetch_left(1, 2u, 0); left1 = true;
+                const bool lz = nc.mvx[0][1] == 0 && nc.mvy[0][1] == 0;
+                smx = lz ? 0 : u2x; smy = lz ? 0 : u2y; nbad = lz ? nb0 : nbB;
+            }
+        } else {
+            fetch_left(1, 2u, 1); left1 = true;
+            if (!(nc.mvx[0][1] == 0 && nc.mvy[0][1] == 0)) predict_mv_(nc, 0, 0, 16, 0, zero4, smx, smy);
+            int p2[2];
+            skip_pred(smx, smy, p2);
+            nbad = skip_bad(p2);
+        }
+    }
     MbMotion mo;
     mo.maxdiff = (int16_t)maxdiff; mo.pad = 0;
     PB_STAMP(4);
@@ -361,24 +402,14 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     const int f1 = tid & 15;
     int callno = 0;                  // alternates BlockSel's survivor counters (uniform across the block)
     const uint4 *__restrict__ Kf = S.kar + (size_t)f1 * g.WH;
-    // neighbour quadrant MVs used by the 8x8 predictors, in registers (A.7): left q1/q3, up q2/q3, up-right q2, up-left q3
-    const int aL = nc.avail[0], aU = nc.avail[1], aUR = nc.avail[2], aUL = nc.avail[3];
-    const int l1x = nc.mvx[0][1], l1y = nc.mvy[0][1];
-    int l3x = 0, l3y = 0;                                            // left MB's quadrant 3: fetched before partition 2
-    const int u2x = nc.mvx[1][2], u2y = nc.mvy[1][2], u3x = nc.mvx[1][3], u3y = nc.mvy[1][3];
-    const int r2x = nc.mvx[2][2], r2y = nc.mvy[2][2], d3x = nc.mvx[3][3], d3y = nc.mvy[3][3];
+    int l1x = 0, l1y = 0, l3x = 0, l3y = 0;                           // left MB's quadrants 1 / 3 once fetched
     for (int pi = 0; pi < 4; pi++) {
         const int xP = mbx * 16 + (pi & 1) * 8, yP = mby * 16 + (pi >> 1) * 8;
-        if (pi == 2 && mbx > 0) {
-            // partition 2 predicts from the left MB's quadrant 3: now the left MB must be complete
-            if (tid == 0) {
-                if (!wait_progress(&S.done[mb - 1], pbase + 4u, false)) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
-                const int v = __ldcg((const int *)&S.motion[mb - 1].mv[3][0]);
-                nc.mvx[0][3] = (int16_t)(v & 0xffff); nc.mvy[0][3] = v >> 16;
-            }
-            __syncthreads();
-            l3x = nc.mvx[0][3]; l3y = nc.mvy[0][3];
-        }
+        // partition 0 predicts from left q1 unless up q2 == up q3; partition 2 from left q3 unless own q0 == q1
+        if (pi == 0 && !left1 && !(aU && u2x == u3x && u2y == u3y)) { fetch_left(1, 2u, 2); left1 = true; }
+        if (pi == 2 && !left3 && !(q0x == q1x && q0y == q1y)) { fetch_left(3, 4u, 3); left3 = true; }
+        if (pi == 0 && left1) { l1x = nc.mvx[0][1]; l1y = nc.mvy[0][1]; }
+        if (pi == 2 && left3) { l3x = nc.mvx[0][3]; l3y = nc.mvy[0][3]; }
         int mvpx, mvpy;
         // A = (px-1,py), B = (px,py-1), C = (px+8,py-1) else D = (px-1,py-1) for an 8x8 partition (mode_pred.cpp:113-161)
         if (pi == 0) median_pred(aL, l1x, l1y, aU, u2x, u2y, aU ? 1 : aUL, aU ? u3x : d3x, aU ? u3y : d3y, mvpx, mvpy);
@@ -386,6 +417,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         else if (pi == 2) median_pred(aL, l3x, l3y, 1, q0x, q0y, 1, q1x, q1y, mvpx, mvpy);
         else median_pred(1, q2x, q2y, 1, q1x, q1y, 1, q0x, q0y, mvpx, mvpy);
         mvps[pi][0] = mvpx; mvps[pi][1] = mvpy;
+        PB_SUB(12);
         const int genx = mvpx >> 2, geny = mvpy >> 2;
         const PartA pa = sh.pa[pi];
         u64 *best = sh.best[pi & 1];
@@ -418,6 +450,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             mine = min(mine, ((u64)((int)e.sad + mv_cost(e.mvx, e.mvy, mvpx, mvpy)) << 44) | (2ull << 42) | (u64)i);
         }
         // stage 1 keys = cost << 11 | arrival index ((dx, dy, frac) order)
+        PB_SUB(13);
         const uint2 *rp = (const uint2 *)&sh.cur[(pi >> 1) * 8][(pi & 1) * 8];
         uint2 rows[8];
 #pragma unroll
@@ -443,7 +476,9 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             }
         }
         __syncthreads();                                               // keys1 and keys2 complete
+        PB_SUB(14);
         const int K1 = block_select_smallest_u32(sh.keys1, n1, FH_S1_MAX, &sh.bs, sh.mem1, callno++);
+        PB_SUB(15);
         // SAD loads of the (at most 17) stage-1 members: 8 threads per member, one row each; consumed after stage 2
         const int r = tid & 7;
         const uint2 cr = pick_row(rows, r);
@@ -510,6 +545,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             }
         }
         // stage 1 SADs
+        PB_SUB(16);
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int m = u * 16 + (tid >> 3);
@@ -526,6 +562,7 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         __syncthreads();
         // decode the winner from its key (:523-527); no candidate at all leaves bx = by = 0 (:452)
         const u64 b = min(min(best[0], best[1]), min(best[2], best[3]));
+        PB_SUB(17);
         int bx = 0, by = 0, bs = 0;
         if (b != KEY_NONE) {
             const int stage = (int)((b >> 42) & 3), total = (int)(b >> 44);
@@ -563,6 +600,13 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     }
 
     // ---- merge (:529-551) and final mvd with the merged type's predictors (:552-564) ---------------------------
+    {
+        const bool m01 = mv[0][0] == mv[1][0] && mv[0][1] == mv[1][1], m23 = mv[2][0] == mv[3][0] && mv[2][1] == mv[3][1];
+        const bool m02 = mv[0][0] == mv[2][0] && mv[0][1] == mv[2][1], m13 = mv[1][0] == mv[3][0] && mv[1][1] == mv[3][1];
+        const bool merged = (m01 && m23) || (m02 && m13);                  // 16x16 / 16x8 / 8x16: predictors read the left MB
+        if (merged && !left1) { fetch_left(1, 2u, 4); left1 = true; }
+        if (merged && !left3) { fetch_left(3, 4u, 5); left3 = true; }
+    }
     if (tid == 0) {
         const bool eq01 = mv[0][0] == mv[1][0] && mv[0][1] == mv[1][1], eq23 = mv[2][0] == mv[3][0] && mv[2][1] == mv[3][1];
         const bool eq02 = mv[0][0] == mv[2][0] && mv[0][1] == mv[2][1], eq13 = mv[1][0] == mv[3][0] && mv[1][1] == mv[3][1];

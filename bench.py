@@ -38,6 +38,26 @@ ALG_BYTES_PER_MB = 1984               # 384 src + 384 ref + 384 
 ALG_INTOPS_PER_MB = 0.43e6
 
 
+def ncu_traffic(dom, seqs_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by profiles/tools/ncu_traffic.py); null when no capture matches this launch size."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+    except (OSError, ValueError):
+        return None, None, None
+    if t.get("seqs_per_launch") != seqs_per_launch:
+        return None, None, "profiles/ncu_traffic.json holds a capture at %s sequences per launch, this run uses %d" % (t.get("seqs_per_launch"), seqs_per_launch)
+    by = {}
+    for name, v in t["kernels"].items():
+        short = name.split("<")[0]
+        if short == "k_stage2" and "4096" in name:
+            continue                                    # the (usually empty) fallback launch
+        by[short] = v["traffic_bytes"]
+    return by.get(dom), by, "profiles/ncu_traffic.json (%s)" % os.path.basename(t.get("source", "?"))
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -382,6 +402,7 @@ def main():
         c_achieved = alg_bytes / (tm["phase_c_ms"] / 1000.0) / 1e9
         int_ops = ALG_INTOPS_PER_MB * nmb * B * world * K          # whole timed job
         step_ms = ms_dev
+        traffic, traffic_by_kernel, traffic_src = ncu_traffic(dom, Bk)
         line = {
             "metric": "1080p P-picture frames/s, ME + transform/quant/reconstruction hot path", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": Wu, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
@@ -392,7 +413,7 @@ def main():
             "gpu_launches": 13 * K * G,
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "note": "algorithmic bytes = 1984 B/MB x %d MB x %d pictures per launch / live CUDA-event duration of the dominant kernel "
                                  "(one sequence group running alone); the ME kernels are integer-pipe bound, see int_roofline" % (nmb, Bk)},
             "roofline_phase_c": {"bound": "hbm", "kernel": "k_phase_c", "achieved": c_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": c_achieved / hbm_peak},
@@ -400,6 +421,7 @@ def main():
                              "peak_tops_nominal": 148 * 128 * sm_max * 1e6 / 1e12,
                              "frac": (int_ops / (step_ms / 1000.0) / 1e12 / world) / (148 * 128 * sm_max * 1e6 / 1e12),
                              "note": "SURVEY.md §8d: 0.43 M int32-lane ops per MB over the whole timed job, per GPU; peak = 148 SMs x 128 lanes x max SM clock"},
+            "dram_traffic_bytes_per_launch": traffic_by_kernel,
             "kernel_ms_per_step": kernels, "phase_ms_per_step": {k_: tm[k_] for k_ in ("phase_a_ms", "phase_b_ms", "phase_c_ms", "copy_phase_r_ms", "total_ms")},
             "idr_decisions": idr_decisions, "mode_counts_last_picture_seq0": counts[0],
         }

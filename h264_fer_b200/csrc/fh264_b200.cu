@@ -189,7 +189,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
             OPEN_CK(dalloc(s, &S.rec[c], c ? CWH : WH));
         }
         OPEN_CK(dalloc(s, &S.planes, 16 * WH));
-        OPEN_CK(dalloc(s, &S.kar, 16 * WH));
+        OPEN_CK(dalloc(s, &S.kar, WH));                  // plane 0 only (16 B per position)
         OPEN_CK(dalloc(s, &S.tent, (size_t)g.ntiles * FH_TILE * FH_TILE));
         OPEN_CK(dalloc(s, &S.tstart, (size_t)g.ntiles * FH_TSTART_PITCH));
         OPEN_CK(dalloc(s, &S.parta, (size_t)g.nparts));
@@ -273,8 +273,8 @@ static int launch_phase_r(fh264_session *s, int seq0, int nseq)
     cudaEventRecord(s->evk[1], s->stream);
     k_interp<<<gi, 256, 0, s->stream>>>(s->d_seqs, seq0, g);
     cudaEventRecord(s->evk[2], s->stream);
-    dim3 gf((g.W + FT_W - 1) / FT_W, (g.H + FT_H - 1) / FT_H, 16 * nseq);
-    k_features<<<gf, 256, 0, s->stream>>>(s->d_seqs, seq0, g);
+    dim3 gf((g.W + FT_W - 1) / FT_W, (g.H + FT_H - 1) / FT_H, nseq);
+    k_features<<<gf, 256, 0, s->stream>>>(s->d_seqs, seq0, g, 0, nullptr);
     cudaEventRecord(s->evk[3], s->stream);
     dim3 gt(g.ntiles, nseq);
     k_tile_index<<<gt, 256, FH_CELLS * 4, s->stream>>>(s->d_seqs, seq0, g);
@@ -560,10 +560,17 @@ extern "C" int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint
     CK(cudaSetDevice(s->device));
     const int n = s->g.WH;
     rc = ensure_scratch(s, (size_t)(n * 2 + 767) / 768); if (rc) return rc;
-    k_unpack_feature<<<(n + 255) / 256, 256, 0, s->stream>>>(s->h[seq].kar + (size_t)f * n, n, k, (uint16_t *)s->d_scr16[0]);
+    // the path keeps plane 0 only; the tap evaluates the same kernel for plane f into a temporary
+    uint4 *tmp = nullptr;
+    CK(cudaMalloc(&tmp, (size_t)n * sizeof(uint4)));
+    const Geo &g = s->g;
+    dim3 gf((g.W + FT_W - 1) / FT_W, (g.H + FT_H - 1) / FT_H, 1);
+    k_features<<<gf, 256, 0, s->stream>>>(s->d_seqs, seq, g, f, tmp);
+    k_unpack_feature<<<(n + 255) / 256, 256, 0, s->stream>>>(tmp, n, k, (uint16_t *)s->d_scr16[0]);
     CKL();
     CK(cudaMemcpyAsync(out, s->d_scr16[0], (size_t)n * 2, cudaMemcpyDeviceToHost, s->stream));
     CK(sync_streams(s));
+    cudaFree(tmp);
     return FH264_OK;
 }
 

@@ -8,6 +8,7 @@
 #pragma once
 #include "common.cuh"
 #include "warp_select.cuh"
+#include "qfeat.cuh"
 
 #define COST_INVALID 0xffffffffu
 #ifndef FH_S3_PIPE
@@ -96,6 +97,30 @@ __device__ __forceinline__ int warp_select_costs(const uint32_t *cost, int n, in
         ns += __popc(b);
     }
     __syncwarp();
+    if (ns > WSEL_CAP) {
+        // the bound was loose (the good candidates sat in few lanes): bisect the exact K-th smallest cost, then compact again
+        uint32_t lo = 0, hi = thr;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            int c = 0;
+            for (int i = lane; i < n; i += 32) c += cost[i] <= mid;
+            if (__reduce_add_sync(0xffffffffu, c) >= K) hi = mid; else lo = mid + 1;
+        }
+        thr = lo;
+        ns = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const uint32_t c = i < n ? cost[i] : COST_INVALID;
+            const bool sv = c <= thr;
+            const unsigned b = __ballot_sync(0xffffffffu, sv);
+            if (sv) {
+                const int pos = ns + __popc(b & ((1u << lane) - 1u));
+                if (pos < WSEL_CAP) { ws->skey[pos] = ((u64)c << 16) | (u64)i; ws->sidx[pos] = (uint16_t)i; }
+            }
+            ns += __popc(b);
+        }
+        __syncwarp();
+    }
     if (ns <= WSEL_CAP) {
         for (int s = lane; s < ns; s += 64) {
             const u64 ka = ws->skey[s];
@@ -107,7 +132,7 @@ __device__ __forceinline__ int warp_select_costs(const uint32_t *cost, int n, in
             if (hb && rb < K) members[rb] = ws->sidx[s + 32];
         }
     } else {
-        // degenerate (flat content / hundreds of equal costs): rank against every candidate
+        // degenerate (flat content: hundreds of candidates tie at the K-th cost): rank against every candidate
         for (int i = lane; i < n; i += 32) {
             const uint32_t c = cost[i];
             if (c > thr) continue;
@@ -198,45 +223,41 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
         }
     }
     // second call: MEstimation(g = window/16, all 16 fractions); arrival = ((dx+g1)*w1 + (dy+g1))*16 + frac.
-    // lane -> (fraction = lane & 15, position parity = lane >> 4); 4 loads in flight
+    // The features of the quarter-pel planes are computed from the planes themselves (qfeat.cuh), a few planes per batch,
+    // in the selection scratch (free until the selection below).
     {
-        const int f = lane & 15, npos = w1 * w1;
-        const uint4 *__restrict__ Kf = S.kar + (size_t)f * g.WH;
-        auto ld4 = [&](int p0, uint4 (&v)[4], unsigned &okm) {
-            okm = 0;
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int pos = p0 + 2 * u + (lane >> 4), cx = (int)__umulhi((uint32_t)pos, i1), rx = xP + cx - g1, ry = yP + pos - cx * w1 - g1;
-                v[u] = make_uint4(0, 0, 0, 0);
-                if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) { if (!FH_X_SKIPB) v[u] = __ldg(Kf + (size_t)ry * W + rx); okm |= 1u << u; }
+        const int npos = w1 * w1, R = 8 + w1 - 1, ps = R * w1, pb = w1 <= 5 ? 4 : 1;
+        uint32_t *X = (uint32_t *)sw->ws.skey;
+        uint16_t *RC = sw->ws.sidx;
+        const uint32_t iR = 0xffffffffu / (uint32_t)R + 1u, iN = 0xffffffffu / (uint32_t)npos + 1u;
+        for (int f0 = 0; f0 < 16; f0 += pb) {
+            // step A: two rows per lane in flight
+            for (int sg0 = 0; sg0 < pb * R; sg0 += 64) {
+                uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;
+                const int sa = sg0 + lane, sb = sg0 + 32 + lane;
+                const int fa = (int)__umulhi((uint32_t)sa, iR), ra = sa - fa * R, fb = (int)__umulhi((uint32_t)sb, iR), rb = sb - fb * R;
+                if (sa < pb * R) wa = qf_load16(S.planes + (size_t)(f0 + fa) * g.WH, W, H, xP - g1, yP - g1 + ra);
+                if (sb < pb * R) wb = qf_load16(S.planes + (size_t)(f0 + fb) * g.WH, W, H, xP - g1, yP - g1 + rb);
+                if (sa < pb * R) qf_row_sums(wa, w1, X + fa * ps + ra * w1, RC + fa * ps + ra * w1);
+                if (sb < pb * R) qf_row_sums(wb, w1, X + fb * ps + rb * w1, RC + fb * ps + rb * w1);
             }
-        };
-        auto ev4 = [&](int p0, const uint4 (&v)[4], unsigned okm) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int pos = p0 + 2 * u + (lane >> 4), cx = (int)__umulhi((uint32_t)pos, i1), dx = cx - g1, dy = pos - cx * w1 - g1;
-                if (pos < npos) {
-                    const uint32_t cst = ((okm >> u) & 1u) ? (uint32_t)((iabs_(dx) + iabs_(dy) + 4) * feat_of(fq, v[u])) : COST_INVALID;
-                    cost[n3a + pos * 16 + f] = cst;
-                    m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
-                }
+            __syncwarp();
+            // step B: one (plane, position) per lane and round
+            // (the lane -> element map is rotated from batch to batch: every lane should meet many different window
+            // positions, or the per-lane minima that bound the selection below stay loose)
+            const int rot = (f0 * 13) % (pb * npos);
+            for (int o0 = lane; o0 < pb * npos; o0 += 32) {
+                const int o = o0 + rot < pb * npos ? o0 + rot : o0 + rot - pb * npos;
+                const int fl = (int)__umulhi((uint32_t)o, iN), pos = o - fl * npos, cx = (int)__umulhi((uint32_t)pos, i1), cy = pos - cx * w1;
+                const int rx = xP + cx - g1, ry = yP + cy - g1;
+                uint32_t cst = COST_INVALID;
+                if (rx >= 0 && rx < W && ry >= 0 && ry < H)
+                    cst = (uint32_t)((iabs_(cx - g1) + iabs_(cy - g1) + 4) * feat_of(fq, qf_record(X, RC, fl, ps, w1, cx, cy)));
+                cost[n3a + pos * 16 + f0 + fl] = cst;
+                m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
             }
-        };
-#if FH_S3_PIPE
-        uint4 va[4], vb[4];
-        unsigned oa, ob;
-        ld4(0, va, oa);
-        for (int p0 = 0; p0 < npos; p0 += 16) {
-            ld4(p0 + 8, vb, ob);
-            ev4(p0, va, oa);
-            ld4(p0 + 16, va, oa);
-            ev4(p0 + 8, vb, ob);
+            __syncwarp();
         }
-#else
-        uint4 va[4];
-        unsigned oa;
-        for (int p0 = 0; p0 < npos; p0 += 8) { ld4(p0, va, oa); ev4(p0, va, oa); }
-#endif
     }
     __syncwarp();
     // candidates = positions whose block origin lies inside the picture (:263-266)

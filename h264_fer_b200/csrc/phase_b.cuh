@@ -13,6 +13,7 @@
 #pragma once
 #include "common.cuh"
 #include "warp_select.cuh"
+#include "qfeat.cuh"
 #include "phase_a.cuh"
 #include "phase_c.cuh"
 
@@ -95,6 +96,8 @@ struct PBShared {
     PartA pa[4];                         // phase-A products of the four partitions, fetched BEFORE the dependency wait
     S3Entry s3[4][FH_S3_MAX + 1];
     uint2 pool[4][PB_POOL_PREF];
+    uint32_t qx[16 * 61];                // qfeat.cuh step A: row sums of the stage-1 window (16 planes x 12 rows x 5 positions at WindowSize 32)
+    uint16_t qrc[16 * 61];
     uint32_t my_ticket;
     int red[4];
 };
@@ -399,9 +402,13 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     int mv[4][2], sadq[4], mvps[4][2];
     int q0x = 0, q0y = 0, q1x = 0, q1y = 0, q2x = 0, q2y = 0;          // quadrant MVs decided so far
     const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16, inv1 = 65536 / w1 + 1, npos = w1 * w1;
-    const int f1 = tid & 15;
+    // qfeat.cuh geometry: window rows, plane stride, planes per warp and batch. Each WARP produces and consumes its own planes
+    // (warp w: planes f0 + w*qpw ..), so the row sums and the records only need warp barriers.
+    const int qR = 8 + w1 - 1, qps = (qR * w1) | 1, qpw = w1 <= 5 ? 4 : 1, qseg = qpw * qR;
+    const uint32_t iR = 0xffffffffu / (uint32_t)qR + 1u, iNp = 0xffffffffu / (uint32_t)npos + 1u;
+    uint32_t *qx = sh.qx + warp * (qpw * qps);
+    uint16_t *qrc = sh.qrc + warp * (qpw * qps);
     int callno = 0;                  // alternates BlockSel's survivor counters (uniform across the block)
-    const uint4 *__restrict__ Kf = S.kar + (size_t)f1 * g.WH;
     int l1x = 0, l1y = 0, l3x = 0, l3y = 0;                           // left MB's quadrants 1 / 3 once fetched
     for (int pi = 0; pi < 4; pi++) {
         const int xP = mbx * 16 + (pi & 1) * 8, yP = mby * 16 + (pi >> 1) * 8;
@@ -422,15 +429,14 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         const PartA pa = sh.pa[pi];
         u64 *best = sh.best[pi & 1];
         u64 mine = KEY_NONE;
-        // stage 1 (:458-469): issue the feature loads of the window/16 quarter-pel window around the predictor.
-        // thread -> (fraction = tid & 15, position = (tid >> 4) + 8u)
-        uint4 v1[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int pos = (tid >> 4) + 8 * u, cx = fdiv_(pos, inv1), rx = xP + genx + cx - g1, ry = yP + geny + pos - cx * w1 - g1;
-            v1[u] = make_uint4(0, 0, 0, 1u);
-            if (pos < npos && rx >= 0 && rx < W && ry >= 0 && ry < H) v1[u] = __ldg(Kf + (size_t)ry * W + rx);
-        }
+        // stage 1 (:458-469): the window/16 quarter-pel window around the predictor. Its features are computed from the
+        // interpolated planes (qfeat.cuh): issue the pixel-row loads now (thread -> (plane, window row)), consume them later.
+        const int x0 = xP + genx - g1, y0 = yP + geny - g1;
+        const int sa = lane, sb = lane + 32;                  // this lane's (plane, row) segments among the warp's qseg (<= 64)
+        const int fa = (int)__umulhi((uint32_t)sa, iR), ra = sa - fa * qR, fb = (int)__umulhi((uint32_t)sb, iR), rb = sb - fb * qR;
+        uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;
+        if (sa < qseg) wa = qf_load16(S.planes + (size_t)(warp * qpw + fa) * g.WH, W, H, x0, y0 + ra);
+        if (sb < qseg) wb = qf_load16(S.planes + (size_t)(warp * qpw + fb) * g.WH, W, H, x0, y0 + rb);
         // stage 2 (:470-507) keys while those loads fly: cost << 10 | arrival rank; SADs were measured in phase A
         const int n2 = (int)pa.n2;
         const uint2 *pool = S.s2pool + pa.s2_off;
@@ -459,20 +465,25 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             int s[5];
             block_sums(rows, s);                                       // suma[0..4] (:440-451)
             const FeatQ fq = feat_query(s);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int pos = (tid >> 4) + 8 * u, cx = fdiv_(pos, inv1), ox = cx - g1, oy = pos - cx * w1 - g1;
-                if (pos < npos) {
-                    const int i = pos * 16 + f1;
-                    sh.keys1[i] = v1[u].w ? COST_INVALID : (((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(fq, v1[u])) << 11) | (uint32_t)i);
+            // planes in batches of 4 * qpw (all 16 at once up to WindowSize 32): row sums -> warp barrier -> records and keys
+            for (int f0 = 0; f0 < 16; f0 += 4 * qpw) {
+                const int fw = f0 + warp * qpw;                        // this warp's first plane of the batch
+                if (f0 > 0) {
+                    __syncwarp();                                      // previous batch consumed
+                    if (sa < qseg) wa = qf_load16(S.planes + (size_t)(fw + fa) * g.WH, W, H, x0, y0 + ra);
+                    if (sb < qseg) wb = qf_load16(S.planes + (size_t)(fw + fb) * g.WH, W, H, x0, y0 + rb);
                 }
-            }
-            // windows beyond 32 positions (WindowSize 64): remaining positions, plain loop
-            for (int pos = 32 + (tid >> 4); pos < npos; pos += 8) {
-                const int cx = fdiv_(pos, inv1), ox = cx - g1, oy = pos - cx * w1 - g1, rx = xP + genx + ox, ry = yP + geny + oy, i = pos * 16 + f1;
-                uint32_t key = COST_INVALID;
-                if (rx >= 0 && rx < W && ry >= 0 && ry < H) key = ((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(fq, __ldg(Kf + (size_t)ry * W + rx))) << 11) | (uint32_t)i;
-                sh.keys1[i] = key;
+                if (sa < qseg) qf_row_sums(wa, w1, qx + fa * qps + ra * w1, qrc + fa * qps + ra * w1);
+                if (sb < qseg) qf_row_sums(wb, w1, qx + fb * qps + rb * w1, qrc + fb * qps + rb * w1);
+                __syncwarp();
+                for (int o = lane; o < qpw * npos; o += 32) {
+                    const int fl = (int)__umulhi((uint32_t)o, iNp), pos = o - fl * npos, cx = fdiv_(pos, inv1), cy = pos - cx * w1, ox = cx - g1, oy = cy - g1;
+                    const int rx = xP + genx + ox, ry = yP + geny + oy, i = pos * 16 + fw + fl;
+                    uint32_t key = COST_INVALID;
+                    if (rx >= 0 && rx < W && ry >= 0 && ry < H)
+                        key = ((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(fq, qf_record(qx, qrc, fl, qps, w1, cx, cy))) << 11) | (uint32_t)i;
+                    sh.keys1[i] = key;
+                }
             }
         }
         __syncthreads();                                               // keys1 and keys2 complete

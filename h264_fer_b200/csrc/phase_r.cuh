@@ -69,10 +69,11 @@ __global__ void __launch_bounds__(256) k_interp(const SeqDev *__restrict__ seqs,
 // row from three aligned words (12 bytes) and slides the 8-wide / 4-wide / columns{0,1,4,5} sums. Vertical pass: a thread
 // walks down one column and slides the 8-row / 4-row / rows{0,1,4,5} sums: ~35 instructions per position instead of the
 // ~140 of a direct evaluation, so the kernel is bound by its 16-byte-per-position HBM writes.
-__global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seqs, int seq0, Geo g)
+// Only plane `f` is materialised (phase R: f = 0 into S.kar, read by stage 3's integer window and the stage-2 index; the
+// quarter-pel planes' features are computed where they are needed, qfeat.cuh). `out` overrides the destination (debug tap).
+__global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seqs, int seq0, Geo g, int f, uint4 *__restrict__ out)
 {
-    const int f = blockIdx.z & 15;
-    const SeqDev &S = seqs[seq0 + (blockIdx.z >> 4)];
+    const SeqDev &S = seqs[seq0 + blockIdx.z];
     const uint8_t *__restrict__ pl = S.planes + (size_t)f * g.WH;
     __shared__ __align__(16) uint32_t t[FT_H + 8][(FT_W + 8) / 4];      // padded plane rows as words
     __shared__ uint16_t r8[FT_H + 8][FT_W + 2], r4[FT_H + 8][FT_W + 2], rc[FT_H + 8][FT_W + 2];
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seq
     const int tx = tid & 63, tg = tid >> 6;
     const int x = x0 + tx;
     if (x >= W) return;
-    uint4 *K = S.kar + (size_t)f * g.WH;
+    uint4 *K = out ? out : S.kar;
     const int rs = tg * (FT_H / 4);
     int a[8], q4[8], qc[8];                // rows rs .. rs+7 of the three horizontal sums (ring of 8)
 #pragma unroll

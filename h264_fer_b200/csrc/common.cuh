@@ -69,13 +69,12 @@ struct SeqDev {
     uint32_t s2pool_size;
     uint32_t *s2redo;       // partitions whose gated survivors overflowed the fast stage-2 launch (count in status[ST_S2REDO])
     MbMotion *motion;       // nmb
-    uint32_t *done;         // nmb: epoch of the picture whose motion record is final
+    unsigned long long *qmv; // nmb * 4 tagged quadrant words (phase B wavefront): epoch << 32 | mvy << 16 | (mvx & 0xffff)
     fh264_mb_result *results;
     uint32_t *status;       // ST_WORDS
     // band mode: the same buffers of the other ranks, mapped through CUDA IPC (NVLink peer access)
     uint8_t *peer_ref[FH_MAX_WORLD][3], *peer_rec[FH_MAX_WORLD][3];
-    MbMotion *peer_motion_next;   // rank + 1: mirror of the band's last MB row (quadrant MVs)
-    uint32_t *peer_done_next;     // rank + 1: mirror of the band's last MB row (wavefront progress)
+    unsigned long long *peer_qmv_next;   // rank + 1: mirror of the band's last MB row (tagged quadrant words)
     long long *dbg;         // optional: nmb * 12 clock samples of phase B (fh264_debug_timeline), else null
 };
 

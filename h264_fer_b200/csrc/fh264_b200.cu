@@ -198,12 +198,12 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         OPEN_CK(dalloc(s, &S.s2pool, (size_t)S.s2pool_size));
         OPEN_CK(dalloc(s, &S.s2redo, (size_t)S2_REDO_MAX));
         OPEN_CK(dalloc(s, &S.motion, (size_t)g.nmb));
-        OPEN_CK(dalloc(s, &S.done, (size_t)g.nmb));
+        OPEN_CK(dalloc(s, &S.qmv, (size_t)g.nmb * 4));
         OPEN_CK(dalloc(s, &S.status, (size_t)ST_WORDS));
         S.results = results + (size_t)b * g.nmb;
         S.dbg = nullptr;
         memset(S.peer_ref, 0, sizeof S.peer_ref); memset(S.peer_rec, 0, sizeof S.peer_rec);
-        S.peer_motion_next = nullptr; S.peer_done_next = nullptr;
+        S.peer_qmv_next = nullptr;
     }
     OPEN_CK(dalloc(s, &s->d_seqs, (size_t)batch));
     OPEN_CK(cudaMemcpy(s->d_seqs, s->h.data(), sizeof(SeqDev) * batch, cudaMemcpyHostToDevice));
@@ -629,7 +629,7 @@ extern "C" int fh264_ipc_export(fh264_session *s, int seq, uint8_t *handles)
     CK(cudaSetDevice(s->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == FH264_IPC_HANDLE_BYTES, "IPC handle size");
     const SeqDev &S = s->h[seq];
-    void *ptrs[FH264_IPC_HANDLES] = { S.ref[0], S.ref[1], S.ref[2], S.rec[0], S.rec[1], S.rec[2], S.motion, S.done, s->d_sync };
+    void *ptrs[FH264_IPC_HANDLES] = { S.ref[0], S.ref[1], S.ref[2], S.rec[0], S.rec[1], S.rec[2], S.motion, S.qmv, s->d_sync };
     for (int i = 0; i < FH264_IPC_HANDLES; i++) {
         cudaIpcMemHandle_t h;
         CK(cudaIpcGetMemHandle(&h, ptrs[i]));
@@ -654,7 +654,7 @@ extern "C" int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const 
     }
     SeqDev &S = s->h[seq];
     for (int c = 0; c < 3; c++) { S.peer_ref[peer_rank][c] = (uint8_t *)ptrs[c]; S.peer_rec[peer_rank][c] = (uint8_t *)ptrs[3 + c]; }
-    if (peer_rank == s->g.rank + 1) { S.peer_motion_next = (MbMotion *)ptrs[6]; S.peer_done_next = (uint32_t *)ptrs[7]; }
+    if (peer_rank == s->g.rank + 1) S.peer_qmv_next = (unsigned long long *)ptrs[7];
     s->peer_sync.p[peer_rank] = (uint32_t *)ptrs[8];
     CK(cudaMemcpy(&s->d_seqs[seq], &S, sizeof(SeqDev), cudaMemcpyHostToDevice));
     return FH264_OK;

@@ -1,8 +1,8 @@
 // Phase B — the predictor-dependent part of interEncoding (moestimation.cpp:392-570), a wavefront over
 // macroblocks: every cost uses the median MV predictor of the already decided left / up / up-right / up-left
 // neighbours (mode_pred.cpp:252-371). One CTA (128 threads) per macroblock; CTAs draw tickets in anti-diagonal
-// order (x + 2y), interleaved over the sequences of the batch, and spin on the `done` epochs of the two
-// neighbours that dominate the dependency set. A ticket's dependencies always hold smaller tickets, so the
+// order (x + 2y), interleaved over the sequences of the batch, and spin on the tagged quadrant words of the
+// neighbours their predictors read. A ticket's dependencies always hold smaller tickets, so the
 // smallest unfinished ticket can always run: no co-residency assumption, no deadlock.
 // Inside a CTA the three stages of a partition run CONCURRENTLY on different warps (warp 0: stage 1, warp 1: stage 2,
 // warp 2: stage 3) with warp-synchronous selection; one block barrier per partition joins their minima.
@@ -35,6 +35,34 @@ __device__ __forceinline__ bool wait_progress(const uint32_t *p, uint32_t target
     return false;
 }
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// Wavefront hand-off. A quadrant's final MV travels in ONE naturally aligned 64-bit word together with the epoch of the
+// picture it belongs to (epoch << 32 | mvy << 16 | mvx & 0xffff). An aligned 8-byte access is single-copy atomic, so the
+// reader that sees the tag has the value: no release fence at the producer, no second round trip at the consumer.
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p, bool sys)
+{
+    unsigned long long v;
+    if (sys) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v, bool sys)
+{
+    if (sys) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long qmv_word(uint32_t epoch, int mvx, int mvy) { return ((unsigned long long)epoch << 32) | (uint32_t)((mvx & 0xffff) | (mvy << 16)); }
+// Bounded wait for a quadrant word of this picture (written by another CTA, or in band mode by another GPU).
+__device__ __forceinline__ bool wait_qmv(const unsigned long long *p, uint32_t epoch, bool sys, int &mvx, int &mvy)
+{
+    for (unsigned it = 0; it < (1u << 25); it++) {
+        const unsigned long long v = ld_relaxed_u64(p, sys);
+        if ((uint32_t)(v >> 32) == epoch) { mvx = (int)(int16_t)(v & 0xffffu); mvy = (int)(int16_t)((v >> 16) & 0xffffu); return true; }
+        __nanosleep(20);
+    }
+    mvx = mvy = 0;
+    return false;
+}
 
 struct NbCache {            // quadrant MVs of the four neighbouring macroblocks (A.7): 0 left, 1 up, 2 up-right, 3 up-left
     int mvx[4][4], mvy[4][4];
@@ -279,42 +307,35 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         sh.pa[tid].n2 = 0; sh.pa[tid].n3 = 0; sh.pa[tid].s2_off = 0;
     }
     PB_STAMP(1);
-    // ---- dependencies. `done[mb]` = epoch * 8 + number of 8x8 quadrants whose MV is final (4 when the MB is finished or
-    //      P_Skip). The row ABOVE is waited for here (up-right quadrant 2, up and up-left complete). The LEFT neighbour is
-    //      only waited for where a predictor really depends on it: a median of three with two equal inputs is that input,
-    //      so wherever the motion field above is locally uniform (up q2 == up q3, up q2 == up-right q2, own q0 == q1) the
+    // ---- dependencies. Every final quadrant MV is published as a tagged word (qmv_word). The row ABOVE is waited for here:
+    //      exactly the quadrants the predictors can address (up q2/q3, up-right q2, up-left q3). The LEFT neighbour is only
+    //      waited for where a predictor really depends on it: a median of three with two equal inputs is that input, so
+    //      wherever the motion field above is locally uniform (up q2 == up q3, up q2 == up-right q2, own q0 == q1) the
     //      P_Skip decision and the partition predictors are known without the left MB and the row's serial chain is cut.
-    const uint32_t pbase = epoch * 8u;
     const bool sysw = g.world > 1;                       // band mode: the row above this band is written by another GPU
-    const bool mirror = S.peer_done_next != nullptr && mby == (g.band_mb0 + g.band_nmb) / g.Wmb - 1;   // band's last MB row
-    if (tid == 0 && mby > 0) {
-        bool ok = true;
-        if (mbx < g.Wmb - 1) ok &= wait_progress(&S.done[mb - g.Wmb + 1], pbase + 3u, sysw);
-        // the MBs above and above-left must be complete; a P_Skip up-right neighbour does not imply it
-        ok &= wait_progress(&S.done[mb - g.Wmb], pbase + 4u, sysw);
-        if (mbx > 0) ok &= wait_progress(&S.done[mb - g.Wmb - 1], pbase + 4u, sysw);
-        if (!ok) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
-    }
-    __syncthreads();
-    PB_STAMP(2);
+    const bool mirror = S.peer_qmv_next != nullptr && mby == (g.band_mb0 + g.band_nmb) / g.Wmb - 1;   // band's last MB row
     if (tid < 16) {
         const int w = tid >> 2, q = tid & 3;
         const int nmb = w == 0 ? mb - 1 : (w == 1 ? mb - g.Wmb : (w == 2 ? mb - g.Wmb + 1 : mb - g.Wmb - 1));
         const bool av = w == 0 ? mbx > 0 : (w == 1 ? mby > 0 : (w == 2 ? (mby > 0 && mbx < g.Wmb - 1) : (mby > 0 && mbx > 0)));
+        // the quadrants the predictors can address (A.7): up q2/q3, up-right q2, up-left q3 — each polled by its own thread;
+        // the left MB's quadrants 1 / 3 are fetched on demand (fetch_left)
+        const bool used = av && ((w == 1 && q >= 2) || (w == 2 && q == 2) || (w == 3 && q == 3));
         int vx = 0, vy = 0;
-        if (av && w != 0) { const int v = __ldcg((const int *)&S.motion[nmb].mv[q][0]); vx = (int16_t)(v & 0xffff); vy = v >> 16; }
-        nc.mvx[w][q] = vx; nc.mvy[w][q] = vy;           // the left MB's quadrants 1 / 3 are fetched on demand (fetch_left)
+        if (used && !wait_qmv(&S.qmv[(size_t)nmb * 4 + q], epoch, sysw, vx, vy)) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
+        nc.mvx[w][q] = vx; nc.mvy[w][q] = vy;
         if (q == 0) nc.avail[w] = av;
     }
     __syncthreads();
+    PB_STAMP(2);
     const bool leftA = mbx > 0;
     bool left1 = !leftA, left3 = !leftA;                 // left quadrant 1 / 3 present in nc (or not needed)
-    auto fetch_left = [&](int q, uint32_t need, int where) {        // block-uniform: wait until the left MB has published `need` quadrants
+    auto fetch_left = [&](int q, int where) {            // block-uniform: wait until the left MB has published quadrant q
         if (tid == 0) {
             const long long t0 = dbg ? gtime_ns() : 0;
-            if (!wait_progress(&S.done[mb - 1], pbase + need, false)) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
-            const int v = __ldcg((const int *)&S.motion[mb - 1].mv[q][0]);
-            nc.mvx[0][q] = (int16_t)(v & 0xffff); nc.mvy[0][q] = v >> 16;
+            int vx, vy;
+            if (!wait_qmv(&S.qmv[(size_t)(mb - 1) * 4 + q], epoch, false, vx, vy)) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
+            nc.mvx[0][q] = vx; nc.mvy[0][q] = vy;
             if (dbg) { dbg[10] += 1ll << (8 * where); dbg[11] += gtime_ns() - t0; }      // timeline: where and how long the left MB was waited for
         }
         __syncthreads();
@@ -361,12 +382,12 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             const int nbB = skip_bad(pB), nb0 = skip_bad(p0);
             if (nbB != 0 && nb0 != 0) nbad = 1;
             else {
-                fetch_left(1, 2u, 0); left1 = true;
+                fetch_left(1, 0); left1 = true;
                 const bool lz = nc.mvx[0][1] == 0 && nc.mvy[0][1] == 0;
                 smx = lz ? 0 : u2x; smy = lz ? 0 : u2y; nbad = lz ? nb0 : nbB;
             }
         } else {
-            fetch_left(1, 2u, 1); left1 = true;
+            fetch_left(1, 1); left1 = true;
             if (!(nc.mvx[0][1] == 0 && nc.mvy[0][1] == 0)) predict_mv_(nc, 0, 0, 16, 0, zero4, smx, smy);
             int p2[2];
             skip_pred(smx, smy, p2);
@@ -383,14 +404,9 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             uint4 *d = (uint4 *)&S.motion[mb];
             const uint4 *s4 = (const uint4 *)&mo;
             d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
-            st_release_u32(&S.done[mb], pbase + 4u);
-            if (mirror) {
-                int *pm = (int *)&S.peer_motion_next[mb].mv[0][0];
-                const int v = (smx & 0xffff) | (smy << 16);
-                pm[0] = v; pm[1] = v; pm[2] = v; pm[3] = v;
-                __threadfence_system();
-                st_release_sys_u32(&S.peer_done_next[mb], pbase + 4u);
-            }
+            const unsigned long long wq = qmv_word(epoch, smx, smy);
+            for (int i = 0; i < 4; i++) st_relaxed_u64(&S.qmv[(size_t)mb * 4 + i], wq, false);
+            if (mirror) for (int i = 0; i < 4; i++) st_relaxed_u64(&S.peer_qmv_next[(size_t)mb * 4 + i], wq, true);
             atomicAdd(&S.status[ST_COUNTS + 0], 1u);
         }
         continue;
@@ -413,8 +429,8 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
     for (int pi = 0; pi < 4; pi++) {
         const int xP = mbx * 16 + (pi & 1) * 8, yP = mby * 16 + (pi >> 1) * 8;
         // partition 0 predicts from left q1 unless up q2 == up q3; partition 2 from left q3 unless own q0 == q1
-        if (pi == 0 && !left1 && !(aU && u2x == u3x && u2y == u3y)) { fetch_left(1, 2u, 2); left1 = true; }
-        if (pi == 2 && !left3 && !(q0x == q1x && q0y == q1y)) { fetch_left(3, 4u, 3); left3 = true; }
+        if (pi == 0 && !left1 && !(aU && u2x == u3x && u2y == u3y)) { fetch_left(1, 2); left1 = true; }
+        if (pi == 2 && !left3 && !(q0x == q1x && q0y == q1y)) { fetch_left(3, 3); left3 = true; }
         if (pi == 0 && left1) { l1x = nc.mvx[0][1]; l1y = nc.mvy[0][1]; }
         if (pi == 2 && left3) { l3x = nc.mvx[0][3]; l3y = nc.mvy[0][3]; }
         int mvpx, mvpy;
@@ -596,15 +612,11 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         mv[pi][0] = bx; mv[pi][1] = by; sadq[pi] = bs;
         if (tid == 0) {
             // publish this quadrant's MV at once: the right and lower-left neighbours can start before this MB is finished
-            // (neighbours only ever read quadrant MVs; the merged type / mvd / SADs of the record are read by phase C)
-            *(int *)&S.motion[mb].mv[pi][0] = (bx & 0xffff) | (by << 16);
-            st_release_u32(&S.done[mb], pbase + (uint32_t)pi + 1u);
-        }
-        if (tid == 0 && mirror) {
-            // band mode: the rank below predicts from this row — mirror the quadrant MV and the progress flag into its memory
-            *(int *)&S.peer_motion_next[mb].mv[pi][0] = (bx & 0xffff) | (by << 16);
-            __threadfence_system();
-            st_release_sys_u32(&S.peer_done_next[mb], pbase + (uint32_t)pi + 1u);
+            // (neighbours only ever read quadrant MVs; the merged type / mvd / SADs of the record are read by phase C).
+            // Band mode: the rank below predicts from this row — the same word goes into its memory over NVLink.
+            const unsigned long long wq = qmv_word(epoch, bx, by);
+            st_relaxed_u64(&S.qmv[(size_t)mb * 4 + pi], wq, false);
+            if (mirror) st_relaxed_u64(&S.peer_qmv_next[(size_t)mb * 4 + pi], wq, true);
         }
         PB_STAMP(5 + pi);
         if (pi == 0) { q0x = bx; q0y = by; } else if (pi == 1) { q1x = bx; q1y = by; } else if (pi == 2) { q2x = bx; q2y = by; }
@@ -615,8 +627,8 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         const bool m01 = mv[0][0] == mv[1][0] && mv[0][1] == mv[1][1], m23 = mv[2][0] == mv[3][0] && mv[2][1] == mv[3][1];
         const bool m02 = mv[0][0] == mv[2][0] && mv[0][1] == mv[2][1], m13 = mv[1][0] == mv[3][0] && mv[1][1] == mv[3][1];
         const bool merged = (m01 && m23) || (m02 && m13);                  // 16x16 / 16x8 / 8x16: predictors read the left MB
-        if (merged && !left1) { fetch_left(1, 2u, 4); left1 = true; }
-        if (merged && !left3) { fetch_left(3, 4u, 5); left3 = true; }
+        if (merged && !left1) { fetch_left(1, 4); left1 = true; }
+        if (merged && !left3) { fetch_left(3, 5); left3 = true; }
     }
     if (tid == 0) {
         const bool eq01 = mv[0][0] == mv[1][0] && mv[0][1] == mv[1][1], eq23 = mv[2][0] == mv[3][0] && mv[2][1] == mv[3][1];

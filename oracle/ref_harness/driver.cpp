@@ -14,6 +14,8 @@
 //   dumpmask bits: 1 per-MB records (P pictures)   2 reconstruction per picture   4 cropped source per picture
 //                  8 phase-R data after picture `planes_pic`   16 per-MB TQ input (snapped source + prediction)
 //                  32 Intra16x16 luma records of I pictures (source, prediction, DC/AC levels, reconstruction)
+//                  64 slice RBSP of P pictures (SLDT: bit position of the first slice_data bit, then the RBSP bytes)
+//                  128 the CAVLC coder tables once (CVTB; fixture for the table check of the device coder)
 // stdout: one JSON line with per-picture types/bytes and timings.
 #include <chrono>
 #include <cstdio>
@@ -68,6 +70,7 @@ enum { REC_INTS = 1 + 8 + 8 + 4 + 256 + 8 + 120 };
 static std::vector<int> mbrec;      // PicSizeInMbs * REC_INTS
 static std::vector<unsigned char> tqio;  // per MB: snapped source 384 + prediction 384
 static unsigned char savedL[256];
+static int slice_data_bit0 = 0;           // writer position when the first macroblock of the slice starts
 static std::vector<short> i16rec;        // per Intra16x16 MB: 256 src, 256 pred, 16 dc, 240 ac, 256 recon (as int16)
 
 #ifndef FH264_NO_TAPS   // the integration build (integration/) supplies these entry points itself
@@ -77,6 +80,7 @@ void interEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8])
 {
 	const int W = frame.Lwidth;
 	const int xp = (CurrMbAddr % PicWidthInMbs) << 4, yp = (CurrMbAddr / PicWidthInMbs) << 4;
+	if (CurrMbAddr == 0) slice_data_bit0 = (int)(RBSP_write_current_byte * 8 + RBSP_write_current_bit + RBSP_write_buffer_bit);
 	const bool tap = (dumpmask & 1) != 0;
 	if (tap)
 		for (int r = 0; r < 16; r++) memcpy(savedL + r * 16, frame.L + (yp + r) * W + xp, 16);
@@ -226,6 +230,22 @@ int main(int argc, char **argv)
 	writeNAL(nu);
 
 	const int W = frame.Lwidth, H = frame.Lheight, nmb = (W * H) >> 8;
+	if (dumpmask & 128) {
+		// coder tables as (length, code) int pairs, in a fixed order: coeff_token nC 0-1 / 2-3 / 4-7 / 8+ [17][4], chroma DC [17][4],
+		// total_zeros 4x4 [15][16], total_zeros chroma DC [3][4], run_before [6][7], coded_block_pattern inter map [48]
+		std::vector<int> t;
+		auto add = [&](const int *len, const unsigned int *code, int n) { for (int i = 0; i < n; i++) { t.push_back(len[i]); t.push_back((int)code[i]); } };
+		add(&CoeffTokenCodesCoder_nC_0_to_2_length[0][0], &CoeffTokenCodesCoder_nC_0_to_2_data_int[0][0], 68);
+		add(&CoeffTokenCodesCoder_nC_2_to_4_length[0][0], &CoeffTokenCodesCoder_nC_2_to_4_data_int[0][0], 68);
+		add(&CoeffTokenCodesCoder_nC_4_to_8_length[0][0], &CoeffTokenCodesCoder_nC_4_to_8_data_int[0][0], 68);
+		add(&CoeffTokenCodesCoder_nC_8_to_max_length[0][0], &CoeffTokenCodesCoder_nC_8_to_max_data_int[0][0], 68);
+		add(&CoeffTokenCodeTableCoder_ChromaDC_length[0][0], &CoeffTokenCodeTableCoder_ChromaDC_data_int[0][0], 68);
+		add(&TotalZerosCodeTableCoder_4x4_length[0][0], &TotalZerosCodeTableCoder_4x4_data_int[0][0], 240);
+		add(&TotalZerosCodeTableCoder_ChromaDC_length[0][0], &TotalZerosCodeTableCoder_ChromaDC_data_int[0][0], 12);
+		add(&RunBeforeCodeTableCoder_length[0][0], &RunBeforeCodeTableCoder_data_int[0][0], 42);
+		for (int i = 0; i < 48; i++) t.push_back(coded_block_pattern_to_codeNum_inter[i]);
+		chunk("CVTB", t.data(), t.size() * sizeof(int));
+	}
 	mbrec.assign((size_t)nmb * REC_INTS, 0);
 	tqio.assign((size_t)nmb * 768, 0);
 
@@ -255,6 +275,12 @@ int main(int argc, char **argv)
 		chunk("PICH", hdr, sizeof hdr);
 		if (isP && (dumpmask & 1)) chunk("MBRC", mbrec.data(), mbrec.size() * sizeof(int));
 		if (isP && (dumpmask & 16)) chunk("TQIO", tqio.data(), tqio.size());
+		if (isP && (dumpmask & 64)) {
+			std::vector<unsigned char> sl(4 + nu.NumBytesInRBSP);
+			memcpy(sl.data(), &slice_data_bit0, 4);
+			memcpy(sl.data() + 4, nu.rbsp_byte, nu.NumBytesInRBSP);
+			chunk("SLDT", sl.data(), sl.size());
+		}
 		if (!isP && (dumpmask & 32) && !i16rec.empty()) chunk("I16M", i16rec.data(), i16rec.size() * sizeof(short));
 		i16rec.clear();
 		if (dumpmask & 2) {

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ENCODER = os.path.join(HERE, "_ref", "ref_encoder")
 REC_INTS = 405
 
-D_MBREC, D_RECON, D_SOURCE, D_PHASE_R, D_TQIO, D_INTRA16 = 1, 2, 4, 8, 16, 32
+D_MBREC, D_RECON, D_SOURCE, D_PHASE_R, D_TQIO, D_INTRA16, D_SLICE, D_TABLES = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 def have_ref_encoder() -> bool:
@@ -68,6 +68,11 @@ def parse_dump(path):
             p.setdefault("sorted", []).append(np.frombuffer(payload, dtype=np.int32).copy())
         elif tag == "KOLI":
             p["koliko"] = np.frombuffer(payload, dtype=np.int32).copy()
+        elif tag == "SLDT":         # P picture: bit position of the first slice_data bit, then the whole slice RBSP
+            p["slice_bit0"] = struct.unpack_from("<i", payload, 0)[0]
+            p["rbsp"] = np.frombuffer(payload[4:], dtype=np.uint8).copy()
+        elif tag == "CVTB":         # the reference's CAVLC coder tables (see driver.cpp for the order)
+            p["cavlc_tables"] = np.frombuffer(payload, dtype=np.int32).copy()
     out = []
     for k in sorted(pics):
         d = pics[k]

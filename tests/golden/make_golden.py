@@ -37,7 +37,7 @@ def main():
         y4m = os.path.join(tmp, "in.y4m")
         synth.write_y4m(y4m, w, h, seed, frames, noise=noise, square=square, contrast=contrast)
         summ, dump, out264 = refdump.run_reference(y4m, frames, qp=qp, basic=basic, window=window, maxdiff=maxdiff,
-                                                   dumpmask=refdump.D_MBREC | refdump.D_RECON | refdump.D_SOURCE | refdump.D_TQIO | refdump.D_INTRA16)
+                                                   dumpmask=refdump.D_MBREC | refdump.D_RECON | refdump.D_SOURCE | refdump.D_TQIO | refdump.D_INTRA16 | refdump.D_SLICE | refdump.D_TABLES)
         pics = refdump.parse_dump(dump)
         arrays = dict(params=np.array([w, h, seed, frames, qp, window, maxdiff, basic], np.int32),
                       noise=np.array([noise]), square=np.array([int(square)]), contrast=np.array([contrast]), types=np.array([p["nal_type"] for p in pics], np.int32),
@@ -52,6 +52,10 @@ def main():
                 arrays["mbrec_%d" % n] = p["mbrec"].astype(np.int16)
                 arrays["tqio_%d" % n] = p["tqio"]
                 arrays["counts_%d" % n] = np.array(p["counts"], np.int32)
+                arrays["slbit0_%d" % n] = np.array([p["slice_bit0"]], np.int32)     # first slice_data bit in the RBSP (after the slice header)
+                arrays["rbsp_%d" % n] = p["rbsp"]                                   # slice RBSP (header + slice data + trailing bits)
+        if name == "qcif_w16_qp28":
+            np.savez_compressed(os.path.join(HERE, "cavlc_tables.npz"), tables=pics[0]["cavlc_tables"])
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **arrays)
         print(name, summ["types"], os.path.getsize(path), "bytes")

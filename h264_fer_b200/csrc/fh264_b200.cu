@@ -13,6 +13,7 @@
 #include "phase_a.cuh"
 #include "phase_b.cuh"
 #include "phase_c.cuh"
+#include "cavlc.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
@@ -58,6 +59,10 @@ struct fh264_session {
     uint32_t *d_sync;               // FH_MAX_WORLD arrival slots (written by the peers)
     PeerSync peer_sync;             // every rank's sync area (own included)
     std::vector<void *> ipc_opened;
+    // device CAVLC (allocated on first use)
+    std::vector<CvSeq> cvh;
+    CvSeq *d_cvs;
+    uint32_t *h_cvstat;             // pinned: batch * 2 (flags, total bits)
 };
 
 __global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
@@ -125,6 +130,7 @@ extern "C" int fh264_close(fh264_session *s)
     for (int i = 0; i < 2; i++) if (s->d_scr16[i]) cudaFree(s->d_scr16[i]);
     if (s->h_status) cudaFreeHost(s->h_status);
     if (s->h_sad) cudaFreeHost(s->h_sad);
+    if (s->h_cvstat) cudaFreeHost(s->h_cvstat);
     for (int i = 0; i < 5; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int i = 0; i < 4; i++) if (s->evk[i]) cudaEventDestroy(s->evk[i]);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -155,6 +161,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->batch = batch; s->device = device; s->epoch = 0; s->timed = false; s->own_stream = true;
     s->d_sync = nullptr; memset(&s->peer_sync, 0, sizeof s->peer_sync);
     s->copy_stream = nullptr; s->ev_c_done = nullptr; s->ev_copy_done = nullptr; s->copy_pending = false;
+    s->d_cvs = nullptr; s->h_cvstat = nullptr;
     s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->d_sadout = nullptr; s->scr_mbs = 0;
     for (int i = 0; i < 5; i++) s->ev[i] = nullptr;
     for (int i = 0; i < 4; i++) s->evk[i] = nullptr;
@@ -426,6 +433,57 @@ extern "C" int fh264_mode_counts(fh264_session *s, int seq, int32_t counts[5])
     CK(sync_streams(s));
     // device counters: [0] skip, [1] 16x16, [2] 16x8, [3] 8x16, [4] 8x8 == brojTipova order
     for (int i = 0; i < 5; i++) counts[i] = (int32_t)s->h_status[(size_t)seq * ST_WORDS + ST_COUNTS + i];
+    return FH264_OK;
+}
+
+// Slice data of the P picture(s) last coded by fh264_encode_p, entropy-coded on the device (cavlc.cuh). See the header.
+static int ensure_cavlc(fh264_session *s)
+{
+    if (s->d_cvs) return FH264_OK;
+    const size_t nmb = (size_t)s->g.nmb;
+    s->cvh.assign(s->batch, CvSeq());
+    for (int b = 0; b < s->batch; b++) {
+        CvSeq &c = s->cvh[b];
+        CK(dalloc(s, &c.info, nmb));
+        CK(dalloc(s, &c.buf, (nmb + 1) * CV_MB_WORDS));
+        CK(dalloc(s, &c.bits, nmb + 1));
+        CK(dalloc(s, &c.off, nmb + 2));
+        CK(dalloc(s, &c.stream, (size_t)CV_STREAM_BYTES / 4 + 16));
+        CK(dalloc(s, &c.stat, (size_t)2));
+    }
+    CK(dalloc(s, &s->d_cvs, (size_t)s->batch));
+    CK(cudaMemcpy(s->d_cvs, s->cvh.data(), sizeof(CvSeq) * s->batch, cudaMemcpyHostToDevice));
+    CK(cudaHostAlloc((void **)&s->h_cvstat, sizeof(uint32_t) * 2 * s->batch, cudaHostAllocDefault));
+    return FH264_OK;
+}
+
+extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits)
+{
+    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
+    if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
+    if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
+    if (s->epoch == 0) return fail(FH264_E_STATE, "cavlc_p before any encode_p");
+    CK(cudaSetDevice(s->device));
+    rc = ensure_cavlc(s); if (rc) return rc;
+    const int nmb = s->g.nmb, wmb = s->g.Wmb;
+    cudaStream_t st = s->stream;
+    for (int b = seq0; b < seq0 + nseq; b++) CK(cudaMemsetAsync(s->cvh[b].stream, 0, (size_t)CV_STREAM_BYTES + 64, st));
+    k_cavlc_prep<<<dim3((nmb + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb);
+    k_cavlc_code<<<dim3((nmb + 1 + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb, wmb);
+    k_cavlc_scan<<<nseq, 1024, 0, st>>>(s->d_cvs, seq0, nmb, first_bit);
+    k_cavlc_pack<<<dim3((nmb + 1 + 3) / 4, nseq), 128, 0, st>>>(s->d_cvs, seq0, nmb, first_bit);
+    CKL();
+    for (int b = seq0; b < seq0 + nseq; b++) CK(cudaMemcpyAsync(s->h_cvstat + 2 * b, s->cvh[b].stat, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int b = seq0; b < seq0 + nseq; b++) {
+        const uint32_t fl = s->h_cvstat[2 * b], total = s->h_cvstat[2 * b + 1];
+        if (fl & CV_FLAG_LEVEL_RANGE) return fail(FH264_E_UNSUPPORTED, "a level is outside the reference's level table (level_prefix > 15, residual_tables.cpp:940-1008)");
+        if (fl & (CV_FLAG_MB_OVERFLOW | CV_FLAG_STREAM_OVERFLOW)) return fail(FH264_E_CAPACITY, "slice data exceeds the 500000-byte RBSP buffer of the reference (fer_h264.cpp:93)");
+        if (((size_t)total + 7) / 8 > out_stride) return fail(FH264_E_ARG, "out_stride smaller than the slice data");
+        nbits[b - seq0] = total;
+        CK(cudaMemcpyAsync(out + (size_t)(b - seq0) * out_stride, s->cvh[b].stream, ((size_t)total + 7) / 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
     return FH264_OK;
 }
 

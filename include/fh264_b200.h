@@ -154,6 +154,19 @@ int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out);
  * [5] k_stage3, [6] k_stage2, [7] k_interp, [8] k_features, [9] k_tile_index. */
 int fh264_last_timings(fh264_session *s, float ms[10]);
 
+/* ---- device entropy coding of a P slice ---------------------------------------------------------
+ * slice_data() of the P picture last coded by fh264_encode_p for sequences [seq0, seq0 + nseq): what the P-slice macroblock
+ * loop of RBSP_encode writes between shd_write() and RBSP_trailing_bits() (rbsp_encoding.cpp:175-313): mb_skip_run, mb_type,
+ * sub_mb_type, mvd_l0, coded_block_pattern (setCodedBlockPattern :21-105), mb_qp_delta and the CAVLC residual
+ * (residual_write / residual_block_cavlc_write, residual.cpp:300-666), including the mb_skip_run that ends the slice (:310).
+ * The caller has written the slice header with the reference's own shd_write(); `first_bit` (0..7) is the bit position inside
+ * its last, partially filled byte, so the returned bytes can be OR-ed / appended without shifting: sequence b's bytes start at
+ * out + b * out_stride, bits [0, first_bit) are zero, slice data occupies bits [first_bit, nbits[b]), the rest of the last
+ * byte is zero (RBSP_trailing_bits stays with the caller). Errors: FH264_E_UNSUPPORTED if a level needs level_prefix > 15
+ * (outside the reference's level table, residual_tables.cpp:940-1008) or in band mode; FH264_E_CAPACITY if the slice data
+ * exceeds the reference's 500000-byte RBSP buffer (fer_h264.cpp:93). */
+int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits);
+
 /* ---- band mode: one picture split into macroblock-row bands over the GPUs of a node (BASELINE config 4) --------------
  * One process and one session per GPU, every rank encodes the same pictures in the same order. Each rank keeps the whole
  * reference picture (upload_source / upload_recon take full pictures on every rank) and codes MB rows [mb_row0, mb_row1);

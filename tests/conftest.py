@@ -48,12 +48,17 @@ class Golden:
         out = [self.z[k] for k in self.z.files if k.startswith("i16_")]
         return np.concatenate(out) if out else np.zeros((0, 1024), np.int16)
 
+    def slice_rbsp(self, n):
+        """P picture n: (RBSP bytes of the slice NAL, bit position of the first slice_data bit) as written by the reference."""
+        return self.z["rbsp_%d" % n], int(self.z["slbit0_%d" % n][0])
+
     def p_pictures(self):
         return [n for n, t in enumerate(self.types) if t == 1]
 
 
 def golden_paths():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    # clip fixtures only (cavlc_tables.npz holds the reference's CAVLC coder tables, see tests/test_cavlc_host.py)
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if os.path.basename(p) != "cavlc_tables.npz")
 
 
 @pytest.fixture(params=golden_paths(), ids=lambda p: os.path.splitext(os.path.basename(p))[0])

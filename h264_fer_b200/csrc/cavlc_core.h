@@ -159,7 +159,7 @@ FH_HD int cv_block(CvBits &b, const int16_t *coef, int maxc, int nC, int *bad)
 //      and mb_type_array): 32 bytes. tc_* hold 0 for blocks that are not coded (P_Skip, or their CBP bit clear), which is what
 //      residual.cpp:458-486 substitutes when it reads a neighbour ------------------------------------------------------------
 struct CvInfo {
-    uint8_t skip, cbp_luma, cbp_chroma, pad;
+    uint8_t skip, cbp_luma, cbp_chroma, mb_type;
     uint8_t tc_luma[16];        // by luma4x4BlkIdx (z-order)
     uint8_t tc_chroma[2][4];    // by chroma4x4BlkIdx
     uint8_t pad2[4];
@@ -172,7 +172,7 @@ FH_HD void cv_prepare(int mb_type, const int16_t luma[16][16], const int16_t cdc
 {
     for (int i = 0; i < 16; i++) o.tc_luma[i] = 0;
     for (int i = 0; i < 8; i++) o.tc_chroma[i >> 2][i & 3] = 0;
-    o.pad = 0; o.pad2[0] = o.pad2[1] = o.pad2[2] = o.pad2[3] = 0;
+    o.mb_type = (uint8_t)mb_type; o.pad2[0] = o.pad2[1] = o.pad2[2] = o.pad2[3] = 0;
     o.skip = mb_type == p_skip_type; o.cbp_luma = 0; o.cbp_chroma = 0;
     if (o.skip) return;
     int cl = 0;

@@ -14,6 +14,7 @@
 #include "phase_b.cuh"
 #include "phase_c.cuh"
 #include "cavlc.cuh"
+static_assert(sizeof(CvInfo) == sizeof(fh264_cavlc_mb_info) && sizeof(CvInfo) == 32, "CvInfo is the public fh264_cavlc_mb_info");
 
 static thread_local std::string g_err;
 static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
@@ -457,7 +458,8 @@ static int ensure_cavlc(fh264_session *s)
     return FH264_OK;
 }
 
-extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits)
+extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits,
+                             fh264_cavlc_mb_info *mb_info)
 {
     int rc = check_seq(s, seq0, nseq); if (rc) return rc;
     if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
@@ -482,6 +484,7 @@ extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit
         if (((size_t)total + 7) / 8 > out_stride) return fail(FH264_E_ARG, "out_stride smaller than the slice data");
         nbits[b - seq0] = total;
         CK(cudaMemcpyAsync(out + (size_t)(b - seq0) * out_stride, s->cvh[b].stream, ((size_t)total + 7) / 8, cudaMemcpyDeviceToHost, st));
+        if (mb_info) CK(cudaMemcpyAsync(mb_info + (size_t)(b - seq0) * nmb, s->cvh[b].info, sizeof(CvInfo) * (size_t)nmb, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
     return FH264_OK;

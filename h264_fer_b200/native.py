@@ -14,6 +14,9 @@ MB_RESULT_DTYPE = np.dtype([("mb_type", "<i2"), ("num_parts", "<i2"), ("mv", "<i
                             ("sad", "<u2", (4,)), ("luma", "<i2", (16, 16)), ("chroma_dc", "<i2", (2, 4)),
                             ("chroma_ac", "<i2", (2, 4, 15)), ("reserved", "<i2", (10,))])
 assert MB_RESULT_DTYPE.itemsize == 832
+CAVLC_MB_INFO_DTYPE = np.dtype([("skip", "u1"), ("cbp_luma", "u1"), ("cbp_chroma", "u1"), ("mb_type", "u1"), ("total_coeff_luma", "u1", (16,)),
+                                ("total_coeff_chroma", "u1", (2, 4)), ("reserved", "u1", (4,))])
+assert CAVLC_MB_INFO_DTYPE.itemsize == 32
 
 ERRORS = {-1: "FH264_E_ARG", -2: "FH264_E_CUDA", -3: "FH264_E_NO_DEVICE", -4: "FH264_E_STATE", -5: "FH264_E_UB_INPUT",
           -6: "FH264_E_CAPACITY", -7: "FH264_E_UNSUPPORTED"}
@@ -78,7 +81,7 @@ def load_library():
     L.fh264_debug_feature.argtypes = [vp, i32, i32, i32, vp]
     L.fh264_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.fh264_debug_timeline.argtypes = [vp, i32, vp]
-    L.fh264_cavlc_p.argtypes = [vp, i32, i32, i32, vp, C.c_size_t, vp]
+    L.fh264_cavlc_p.argtypes = [vp, i32, i32, i32, vp, C.c_size_t, vp, vp]
     L.fh264_debug_status.argtypes = [vp, i32, vp]
     L.fh264_band_config.argtypes = [vp, i32, i32, i32, i32]
     L.fh264_ipc_export.argtypes = [vp, i32, vp]
@@ -247,14 +250,16 @@ class Session:
         self._ck(self.L.fh264_motion_compensate(self.handle, seq, _ptr(qmv), _ptr(out)))
         return out
 
-    def cavlc_p(self, first_bit=0, seq0=0, nseq=None, capacity=500064):
+    def cavlc_p(self, first_bit=0, seq0=0, nseq=None, capacity=500064, mb_info=False):
         """Device CAVLC of the P picture(s) last coded by encode_p: list of (bytes, nbits) per sequence; slice data occupies bits
         [first_bit, nbits) of the returned bytes (rbsp_encoding.cpp:175-313)."""
         nseq = self.batch - seq0 if nseq is None else nseq
         out = np.zeros((nseq, capacity), np.uint8)
         nbits = np.zeros(nseq, np.uint32)
-        self._ck(self.L.fh264_cavlc_p(self.handle, seq0, nseq, first_bit, _ptr(out), capacity, _ptr(nbits)))
-        return [(out[b, :(int(nbits[b]) + 7) // 8].copy(), int(nbits[b])) for b in range(nseq)]
+        info = np.zeros((nseq, self.nmb), CAVLC_MB_INFO_DTYPE) if mb_info else None
+        self._ck(self.L.fh264_cavlc_p(self.handle, seq0, nseq, first_bit, _ptr(out), capacity, _ptr(nbits), _ptr(info) if mb_info else None))
+        res = [(out[b, :(int(nbits[b]) + 7) // 8].copy(), int(nbits[b])) for b in range(nseq)]
+        return (res, info) if mb_info else res
 
     def debug_timeline(self, seq, read=True):
         if not read:

@@ -165,7 +165,18 @@ int fh264_last_timings(fh264_session *s, float ms[10]);
  * byte is zero (RBSP_trailing_bits stays with the caller). Errors: FH264_E_UNSUPPORTED if a level needs level_prefix > 15
  * (outside the reference's level table, residual_tables.cpp:940-1008) or in band mode; FH264_E_CAPACITY if the slice data
  * exceeds the reference's 500000-byte RBSP buffer (fer_h264.cpp:93). */
-int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits);
+typedef struct fh264_cavlc_mb_info {   /* per macroblock, 32 bytes: what the reference's macroblock loop leaves in its host arrays */
+    uint8_t skip;                      /* mb_type == P_Skip */
+    uint8_t cbp_luma, cbp_chroma;      /* CodedBlockPatternLumaArray / ChromaArray (rbsp_encoding.cpp:103-104); 0 for P_Skip */
+    uint8_t mb_type;                   /* mb_type_array (:180) */
+    uint8_t total_coeff_luma[16];      /* totalcoeff_array_luma by luma4x4BlkIdx (residual.cpp:508); 0 where the block is not coded */
+    uint8_t total_coeff_chroma[2][4];  /* totalcoeff_array_chroma */
+    uint8_t reserved[4];
+} fh264_cavlc_mb_info;
+/* mb_info (nullable, nseq * MBs entries): side information a host that keeps coding I pictures with the reference's own code
+ * needs to keep those arrays as the reference would (its intra bit-cost trials read them across pictures). */
+int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits,
+                  fh264_cavlc_mb_info *mb_info);
 
 /* ---- band mode: one picture split into macroblock-row bands over the GPUs of a node (BASELINE config 4) --------------
  * One process and one session per GPU, every rank encodes the same pictures in the same order. Each rank keeps the whole

@@ -26,6 +26,11 @@
 #include "ref_frames.h"
 #include "moestimation.h"
 #include "../include/fh264_b200.h"
+#ifdef FH264_SHIM_DEVICE_CAVLC
+#include "nal.h"
+#include "rbsp_IO.h"
+#include "rbsp_encoding.h"
+#endif
 
 void ref_interEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8]);
 void ref_FillInterpolatedRefFrame();
@@ -124,3 +129,66 @@ void FillInterpolatedRefFrame()
     }
     g_last_was_p = false;
 }
+
+#ifdef FH264_SHIM_DEVICE_CAVLC
+// ---- variant with the P-slice entropy coding on the device (integration/_build/fh264_encoder_b200_cavlc) --
+// rbsp_encoding.cpp is compiled with -DRBSP_encode=ref_RBSP_encode: SPS, PPS and IDR slices still run the reference's own
+// RBSP_encode; for a P slice this restates its frame (rbsp_encoding.cpp:119-127,160-170,308-325) around ONE device call
+// chain: slice header by the reference's shd_write(), slice_data() from fh264_cavlc_p(), RBSP_trailing_bits() by the
+// reference. No per-macroblock record crosses PCIe any more (fh264_encode_p with results == NULL).
+void ref_RBSP_encode(NALunit &nal_unit);
+void RBSP_trailing_bits();
+
+void RBSP_encode(NALunit &nal_unit)
+{
+    if (nal_unit.nal_unit_type != NAL_UNIT_TYPE_NOT_IDR) { ref_RBSP_encode(nal_unit); return; }
+    initRawWriter(nal_unit.rbsp_byte, 500000);
+    shd.slice_type = P_SLICE;
+    shd.frame_num++;
+    shd_write(nal_unit);
+    flushWriteBuffer();                                  // header bits out of the 64-bit staging word: byte / bit position is exact now
+
+    ensure_session();
+    fh264_params p;
+    p.qp = QPy; p.window = WindowSize; p.maxdiff_set = MAXDIFF_SET; p.basic = BasicInterEncoding ? 1 : 0;
+    int rc = fh264_encode_p(g_sess, 0, 1, &p, NULL);     // `frame` was uploaded by selectNALUnitType() for this picture
+    if (rc) die("fh264_encode_p", rc);
+    int32_t c[5];
+    if (fh264_mode_counts(g_sess, 0, c) == FH264_OK) for (int i = 0; i < 5; i++) brojTipova[i] = c[i];
+    g_last_was_p = true;
+
+    static std::vector<unsigned char> sl(500064);
+    uint32_t nbits = 0;
+    const int first_bit = (int)RBSP_write_current_bit;
+    static std::vector<fh264_cavlc_mb_info> info;
+    info.resize(g_res.size());
+    rc = fh264_cavlc_p(g_sess, 0, 1, first_bit, sl.data(), sl.size(), &nbits, info.data());
+    if (rc) die("fh264_cavlc_p", rc);
+    // The reference's intra bit-cost trials (coded_mb_size -> residual_block_cavlc_size) read mb_type_array, the
+    // CodedBlockPattern arrays and totalcoeff_array_* of the PREVIOUS picture for blocks not yet coded in the current one, so
+    // the next I picture only comes out identical if the P loop's leftovers are: rbsp_encoding.cpp:180,103-104, residual.cpp:508-517.
+    for (size_t m = 0; m < info.size(); m++) {
+        const fh264_cavlc_mb_info &f = info[m];
+        mb_type_array[m] = f.mb_type;
+        if (f.skip) continue;
+        CodedBlockPatternLumaArray[m] = f.cbp_luma;
+        CodedBlockPatternChromaArray[m] = f.cbp_chroma;
+        for (int b = 0; b < 16; b++) if (f.cbp_luma & (1 << (b >> 2))) totalcoeff_array_luma[m][b] = f.total_coeff_luma[b];
+        if (f.cbp_chroma & 2) for (int c = 0; c < 2; c++) for (int b = 0; b < 4; b++) totalcoeff_array_chroma[c][m][b] = f.total_coeff_chroma[c][b];
+    }
+    unsigned char *dst = RBSP_write_data + RBSP_write_current_byte;
+    const size_t nbytes = ((size_t)nbits + 7) / 8;
+    if (nbytes) {
+        if (first_bit) dst[0] |= sl[0]; else dst[0] = sl[0];
+        memcpy(dst + 1, sl.data() + 1, nbytes - 1);
+    }
+    RBSP_write_current_byte += nbits >> 3;
+    RBSP_write_current_bit = nbits & 7;
+    if (RBSP_write_current_bit == 0 && nbytes) { /* byte aligned: the next byte is cleared by the writer itself */ }
+    RBSP_trailing_bits();
+    nal_unit.NumBytesInRBSP = RBSP_write_current_byte;
+    modificationProcess();
+    FillInterpolatedRefFrame();
+    flushWriteBuffer();
+}
+#endif

@@ -15,12 +15,14 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ENCODER = os.path.join(ROOT, "integration", "_build", "fh264_encoder_b200")
+ENCODER_CAVLC = ENCODER + "_cavlc"          # same, with the P-slice entropy coding on the device too
 
-needs_binary = pytest.mark.skipif(not os.path.isfile(ENCODER), reason="integration binary not built (make -C integration)")
+needs_binary = pytest.mark.skipif(not (os.path.isfile(ENCODER) and os.path.isfile(ENCODER_CAVLC)), reason="integration binaries not built (make -C integration)")
+both_encoders = pytest.mark.parametrize("encoder", [ENCODER, ENCODER_CAVLC], ids=["host_cavlc", "device_cavlc"])
 
 
-def run_b200_encoder(y4m, out264, dump, frames, qp, basic, window, maxdiff, intra_every=1000, dumpmask=0):
-    cmd = [ENCODER, y4m, out264, dump if dumpmask else "-", str(frames), str(qp), str(basic), str(window), str(maxdiff), str(intra_every),
+def run_b200_encoder(y4m, out264, dump, frames, qp, basic, window, maxdiff, intra_every=1000, dumpmask=0, encoder=ENCODER):
+    cmd = [encoder, y4m, out264, dump if dumpmask else "-", str(frames), str(qp), str(basic), str(window), str(maxdiff), str(intra_every),
            str(dumpmask), "-1"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
     assert res.returncode == 0, res.stderr.decode()[-2000:]
@@ -32,14 +34,15 @@ def md5(path):
 
 
 @needs_binary
-def test_bitstream_and_reconstruction_match_golden(golden, tmp_path):
+@both_encoders
+def test_bitstream_and_reconstruction_match_golden(golden, tmp_path, encoder):
     y4m = str(tmp_path / "in.y4m")
     z = golden.z
     synth.write_y4m(y4m, golden.w_in, golden.h_in, golden.seed, golden.frames, noise=float(z["noise"][0]), square=bool(int(z["square"][0])),
                     contrast=float(z["contrast"][0]))
     assert md5(y4m) == bytes(z["y4m_md5"]), "synthetic clip generator drifted from the one that made the golden vectors"
     out, dump = str(tmp_path / "out.264"), str(tmp_path / "dump.bin")
-    run_b200_encoder(y4m, out, dump, golden.frames, golden.qp, golden.basic, golden.window, golden.maxdiff, dumpmask=refdump.D_RECON)
+    run_b200_encoder(y4m, out, dump, golden.frames, golden.qp, golden.basic, golden.window, golden.maxdiff, dumpmask=refdump.D_RECON, encoder=encoder)
     assert md5(out) == bytes(z["bitstream_md5"]), "%s: .264 differs from the reference encoder's" % golden.name
     pics = refdump.parse_dump(dump)
     assert [p["nal_type"] for p in pics] == golden.types
@@ -52,26 +55,28 @@ def test_bitstream_and_reconstruction_match_golden(golden, tmp_path):
 @pytest.mark.skipif(not refdump.have_ref_encoder(), reason="compiled reference not present")
 @pytest.mark.parametrize("w,h,seed,frames,qp,window,maxdiff,intra_every", [(176, 144, 1, 30, 28, 16, 3, 1000),     # BASELINE config 1 (QCIF, 30 frames)
                                                                             (352, 288, 2, 12, 28, 32, -1, 5)])     # CIF, adaptive MAXDIFF, periodic IDR
-def test_bitstream_matches_live_reference(tmp_path, w, h, seed, frames, qp, window, maxdiff, intra_every):
+@both_encoders
+def test_bitstream_matches_live_reference(tmp_path, w, h, seed, frames, qp, window, maxdiff, intra_every, encoder):
     y4m = str(tmp_path / "in.y4m")
     synth.write_y4m(y4m, w, h, seed, frames)
     ref264 = str(tmp_path / "ref.264")
     summ, _, _ = refdump.run_reference(y4m, frames, qp=qp, window=window, maxdiff=maxdiff, intra_every=intra_every, out_264=ref264)
     out = str(tmp_path / "b200.264")
-    run_b200_encoder(y4m, out, "-", frames, qp, 0, window, maxdiff, intra_every=intra_every)
+    run_b200_encoder(y4m, out, "-", frames, qp, 0, window, maxdiff, intra_every=intra_every, encoder=encoder)
     assert "P" in summ["types"]
     assert open(out, "rb").read() == open(ref264, "rb").read(), "bitstreams differ (%s)" % summ["types"]
 
 
 @needs_binary
 @pytest.mark.skipif(not refdump.have_ref_encoder(), reason="compiled reference not present")
-def test_720p_window32_bitstream_matches_live_reference(tmp_path):
+@both_encoders
+def test_720p_window32_bitstream_matches_live_reference(tmp_path, encoder):
     """BASELINE config 3 geometry (1280x720, +-16 search): 1 I + 2 P pictures, byte-identical bitstream."""
     y4m = str(tmp_path / "in.y4m")
     synth.write_y4m(y4m, 1280, 720, 3, 3)
     ref264 = str(tmp_path / "ref.264")
     summ, _, _ = refdump.run_reference(y4m, 3, qp=28, window=32, maxdiff=3, out_264=ref264)
     out = str(tmp_path / "b200.264")
-    run_b200_encoder(y4m, out, "-", 3, 28, 0, 32, 3)
+    run_b200_encoder(y4m, out, "-", 3, 28, 0, 32, 3, encoder=encoder)
     assert summ["types"] == "IPP"
     assert open(out, "rb").read() == open(ref264, "rb").read()

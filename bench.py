@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--mode", default="sequences", choices=["sequences", "bands"],
                     help="sequences: independent sequences per GPU (weak scaling, the headline); bands: ONE 1080p sequence split into MB-row bands over all GPUs (BASELINE config 4, strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cavlc", action="store_true", help="skip the device-CAVLC line item (SURVEY.md §8(f) rank 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -373,6 +374,47 @@ def main():
     ms_e2e, clocks_e2e = timed(host=True)
     idr_decisions = sum(gr.idr for gr in groups)
 
+    # device CAVLC line item: the same end-to-end step, but what comes back per picture is the coded
+    # slice data + 32 B/MB of side information instead of the 832-byte records. Reported beside the headline, not in it.
+    cavlc = None
+    if not args.no_cavlc and G == 1:
+        g0 = groups[0]
+        g0.reset()
+        slice_out = PinnedArray((g0.n, 500064), np.uint8)
+        info_out = PinnedArray((g0.n, nmb), fh.CAVLC_MB_INFO_DTYPE)
+        nbits = np.zeros(g0.n, np.uint32)
+
+        def cavlc_step():
+            k = pingpong(g0.t, CLIP_LEN)
+            g0.t += 1
+            for j in range(g0.n):
+                pp = g0.pinned[j][k].ptr
+                g0.s.upload_source_ptrs(j, pp, pp + ysz, pp + ysz + csz, device=False)
+            g0.s.scene_sad_batch()
+            g0.s.encode_p(QP, WINDOW, MAXDIFF, 0, out=g0.results.array, sync=False, download=False)
+            t0 = time.perf_counter()
+            g0.s._ck(g0.s.L.fh264_cavlc_p(g0.s.handle, 0, g0.n, 0, slice_out.ptr, 500064, nbits.ctypes.data, info_out.ptr))
+            return time.perf_counter() - t0
+
+        for _ in range(Wu):
+            cavlc_step()
+        torch.cuda.synchronize()
+        ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ec0.record(g0.stream)
+        calls = [cavlc_step() for _ in range(K)]
+        ec1.record(g0.stream)
+        torch.cuda.synchronize()
+        ms_c = ec0.elapsed_time(ec1)
+        t0 = time.perf_counter()                            # the picture is finished: this call is the entropy coding alone
+        g0.s._ck(g0.s.L.fh264_cavlc_p(g0.s.handle, 0, g0.n, 0, slice_out.ptr, 500064, nbits.ctypes.data, info_out.ptr))
+        cavlc_alone_ms = 1000.0 * (time.perf_counter() - t0)
+        cavlc = {"e2e_value": g0.n * K / (ms_c / 1000.0), "unit": "frames/s (this GPU)", "ms_per_step": ms_c / K,
+                 "cavlc_call_ms": 1000.0 * sum(calls) / len(calls), "cavlc_alone_ms": cavlc_alone_ms,
+                 "slice_bytes_per_step": int(sum((int(b) + 7) // 8 for b in nbits)), "d2h_bytes_per_step": int(sum((int(b) + 7) // 8 for b in nbits)) + g0.n * nmb * 32,
+                 "note": "fh264_cavlc_p after every encode_p: 4 kernels (prep, code, scan, pack) + D2H of the slice data and 32 B/MB side information; "
+                         "the call waits for the picture (no record D2H); cavlc_call_ms includes that wait, cavlc_alone_ms is a repeat call on the finished "
+                         "pictures (kernels + copies + two stream syncs, host wall clock)"}
+
     # per-kernel device times (CUDA events inside the library, on the launching stream): group 0 alone, a few steps
     g0 = groups[0]
     g0.reset()
@@ -425,6 +467,8 @@ def main():
             "kernel_ms_per_step": kernels, "phase_ms_per_step": {k_: tm[k_] for k_ in ("phase_a_ms", "phase_b_ms", "phase_c_ms", "copy_phase_r_ms", "total_ms")},
             "idr_decisions": idr_decisions, "mode_counts_last_picture_seq0": counts[0],
         }
+        if cavlc is not None:
+            line["device_cavlc"] = cavlc
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))

@@ -280,27 +280,39 @@ def main():
             self.idr = 0
             self.t = 1
 
-        def reset(self):
+        def reset(self, host=False):
             for j, b in enumerate(self.ids):
                 self.s.upload_recon(j, *clips[b][0])
             self.s.sync()
             self.t = 1
+            self.upload(host)                                    # prime: the first picture to code
+            self.s.sync()
 
-        def step(self, host):
+        def upload(self, host):
+            """Hands the next picture of every sequence to the library (pinned H2D when host, else D2D): the copy runs on the
+            library's upload stream into the source buffer that is not being coded."""
             k = pingpong(self.t, CLIP_LEN)
             self.t += 1
             for j in range(self.n):
                 p = self.pinned[j][k].ptr if host else self.dev[j][k].data_ptr()
                 self.s.upload_source_ptrs(j, p, p + ysz, p + ysz + csz, device=not host)
+
+        def code(self, host):
             sads = self.s.scene_sad_batch()                      # selectNALUnitType's measure (ref_frames.cpp:210-224)
             self.idr += sum(1 for v in sads if v > (nmb << 12))
             self.s.encode_p(QP, WINDOW, MAXDIFF, 0, out=self.results.array, sync=False, download=host)
+
+        def step(self, host):
+            """One step = code the picture uploaded last, then upload the next one (its H2D overlaps this picture's coding;
+            every step still moves one picture per sequence in and one set of records out)."""
+            self.code(host)
+            self.upload(host)
 
     groups = [Group(list(range(B))[i::G]) for i in range(G)]
 
     def timed(host):
         for gr in groups:
-            gr.reset()
+            gr.reset(host)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ends = [torch.cuda.Event() for _ in groups]
         bar_warm, bar_go = threading.Barrier(G + 1), threading.Barrier(G + 1)
@@ -379,19 +391,15 @@ def main():
     cavlc = None
     if not args.no_cavlc and G == 1:
         g0 = groups[0]
-        g0.reset()
+        g0.reset(True)
         slice_out = PinnedArray((g0.n, 500064), np.uint8)
         info_out = PinnedArray((g0.n, nmb), fh.CAVLC_MB_INFO_DTYPE)
         nbits = np.zeros(g0.n, np.uint32)
 
         def cavlc_step():
-            k = pingpong(g0.t, CLIP_LEN)
-            g0.t += 1
-            for j in range(g0.n):
-                pp = g0.pinned[j][k].ptr
-                g0.s.upload_source_ptrs(j, pp, pp + ysz, pp + ysz + csz, device=False)
             g0.s.scene_sad_batch()
             g0.s.encode_p(QP, WINDOW, MAXDIFF, 0, out=g0.results.array, sync=False, download=False)
+            g0.upload(True)
             t0 = time.perf_counter()
             g0.s._ck(g0.s.L.fh264_cavlc_p(g0.s.handle, 0, g0.n, 0, slice_out.ptr, 500064, nbits.ctypes.data, info_out.ptr))
             return time.perf_counter() - t0

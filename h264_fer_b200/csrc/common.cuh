@@ -57,6 +57,7 @@ static_assert(sizeof(MbMotion) == 48, "MbMotion size");
 
 struct SeqDev {
     uint8_t *cur[3];        // `frame`: source picture (Y, Cb, Cr)
+    uint8_t *cur_alt[3];    // the other source buffer: the NEXT picture is uploaded here while this one is being coded
     uint8_t *ref[3];        // `dpb`: previous reconstruction
     uint8_t *rec[3];        // reconstruction of the picture being coded (swapped with ref afterwards)
     uint8_t *planes;        // refFrameInterpolated[f].L, f-major, WH each (+16 bytes slack at the end)

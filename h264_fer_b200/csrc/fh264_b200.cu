@@ -41,6 +41,11 @@ struct fh264_session {
     cudaStream_t copy_stream;       // result records go home on their own stream, overlapping phase R and the next picture
     cudaEvent_t ev_c_done, ev_copy_done;
     bool copy_pending;
+    // double-buffered source pictures: uploads run on their own stream into the buffer that is not being coded
+    cudaStream_t up_stream;
+    std::vector<cudaEvent_t> ev_up;                 // per sequence: upload complete
+    std::vector<cudaEvent_t> ev_free[2];            // per sequence and buffer: last picture that read it is through phase C
+    std::vector<char> up_pending, cur_set, free_valid[2];
     std::vector<SeqDev> h;          // host mirror of the device SeqDev array
     SeqDev *d_seqs;
     int *d_wf_order;
@@ -104,6 +109,7 @@ static cudaError_t sync_streams(fh264_session *s)
 {
     cudaError_t e = cudaStreamSynchronize(s->stream);
     if (e == cudaSuccess && s->copy_stream) e = cudaStreamSynchronize(s->copy_stream);
+    if (e == cudaSuccess && s->up_stream) e = cudaStreamSynchronize(s->up_stream);
     return e;
 }
 
@@ -136,6 +142,9 @@ extern "C" int fh264_close(fh264_session *s)
     for (int i = 0; i < 4; i++) if (s->evk[i]) cudaEventDestroy(s->evk[i]);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->up_stream) cudaStreamDestroy(s->up_stream);
+    for (auto e : s->ev_up) cudaEventDestroy(e);
+    for (int k = 0; k < 2; k++) for (auto e : s->ev_free[k]) cudaEventDestroy(e);
     if (s->ev_c_done) cudaEventDestroy(s->ev_c_done);
     if (s->ev_copy_done) cudaEventDestroy(s->ev_copy_done);
     delete s;
@@ -161,6 +170,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     fh264_session *s = new fh264_session();
     s->batch = batch; s->device = device; s->epoch = 0; s->timed = false; s->own_stream = true;
     s->d_sync = nullptr; memset(&s->peer_sync, 0, sizeof s->peer_sync);
+    s->up_stream = nullptr;
     s->copy_stream = nullptr; s->ev_c_done = nullptr; s->ev_copy_done = nullptr; s->copy_pending = false;
     s->d_cvs = nullptr; s->h_cvstat = nullptr;
     s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->d_sadout = nullptr; s->scr_mbs = 0;
@@ -178,6 +188,13 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
 #define OPEN_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(FH264_E_CUDA, #call, e_); fh264_close(s); return FH264_E_CUDA; } } while (0)
     OPEN_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     OPEN_CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    OPEN_CK(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
+    s->ev_up.assign(batch, nullptr); s->up_pending.assign(batch, 0); s->cur_set.assign(batch, 0);
+    for (int k = 0; k < 2; k++) { s->ev_free[k].assign(batch, nullptr); s->free_valid[k].assign(batch, 0); }
+    for (int b = 0; b < batch; b++) {
+        OPEN_CK(cudaEventCreateWithFlags(&s->ev_up[b], cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) OPEN_CK(cudaEventCreateWithFlags(&s->ev_free[k][b], cudaEventDisableTiming));
+    }
     OPEN_CK(cudaEventCreateWithFlags(&s->ev_c_done, cudaEventDisableTiming));
     OPEN_CK(cudaEventCreateWithFlags(&s->ev_copy_done, cudaEventDisableTiming));
     for (int i = 0; i < 5; i++) OPEN_CK(cudaEventCreate(&s->ev[i]));
@@ -193,6 +210,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         SeqDev &S = s->h[b];
         for (int c = 0; c < 3; c++) {
             OPEN_CK(dalloc(s, &S.cur[c], c ? CWH : WH));
+            OPEN_CK(dalloc(s, &S.cur_alt[c], c ? CWH : WH));
             OPEN_CK(dalloc(s, &S.ref[c], c ? CWH : WH));
             OPEN_CK(dalloc(s, &S.rec[c], c ? CWH : WH));
         }
@@ -260,16 +278,56 @@ static int check_seq(fh264_session *s, int seq0, int nseq)
     return FH264_OK;
 }
 
+// Source pictures are double buffered: an upload goes, on its own stream, into the buffer that is NOT being coded (after the
+// last picture that read that buffer is through phase C), so the H2D copy of picture t+1 overlaps the coding of picture t.
+// The buffers swap when the picture is first used (scene_sad / encode_p), which also makes the coding stream wait for the copy.
+static int upload_planes(fh264_session *s, int seq, const void *y, const void *cb, const void *cr, cudaMemcpyKind kind)
+{
+    const size_t WH = (size_t)s->g.WH;
+    const int target = 1 - s->cur_set[seq];
+    if (s->free_valid[target][seq]) CK(cudaStreamWaitEvent(s->up_stream, s->ev_free[target][seq], 0));
+    uint8_t **dst = s->h[seq].cur_alt;
+    CK(cudaMemcpyAsync(dst[0], y, WH, kind, s->up_stream));
+    CK(cudaMemcpyAsync(dst[1], cb, WH / 4, kind, s->up_stream));
+    CK(cudaMemcpyAsync(dst[2], cr, WH / 4, kind, s->up_stream));
+    CK(cudaEventRecord(s->ev_up[seq], s->up_stream));
+    s->up_pending[seq] = 1;
+    return FH264_OK;
+}
+
+__global__ void k_swap_cur(SeqDev *seqs, int seq0, unsigned long long mask)
+{
+    if (!((mask >> threadIdx.x) & 1ull)) return;
+    SeqDev &S = seqs[seq0 + threadIdx.x];
+    for (int c = 0; c < 3; c++) { uint8_t *t = S.cur[c]; S.cur[c] = S.cur_alt[c]; S.cur_alt[c] = t; }
+}
+
+// Makes the pictures uploaded since the last use current for sequences [seq0, seq0+nseq) (called by everything that reads `cur`).
+static int adopt_uploads(fh264_session *s, int seq0, int nseq)
+{
+    for (int b0 = seq0; b0 < seq0 + nseq; b0 += 64) {
+        const int n = std::min(64, seq0 + nseq - b0);
+        unsigned long long mask = 0;
+        for (int i = 0; i < n; i++) {
+            const int b = b0 + i;
+            if (!s->up_pending[b]) continue;
+            CK(cudaStreamWaitEvent(s->stream, s->ev_up[b], 0));
+            mask |= 1ull << i;
+            for (int c = 0; c < 3; c++) std::swap(s->h[b].cur[c], s->h[b].cur_alt[c]);
+            s->cur_set[b] ^= 1;
+            s->up_pending[b] = 0;
+        }
+        if (mask) k_swap_cur<<<1, n, 0, s->stream>>>(s->d_seqs, b0, mask);
+    }
+    return FH264_OK;
+}
+
 extern "C" int fh264_upload_source(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr)
 {
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     if (!y || !cb || !cr) return fail(FH264_E_ARG, "null plane");
     CK(cudaSetDevice(s->device));
-    const size_t WH = (size_t)s->g.WH;
-    CK(cudaMemcpyAsync(s->h[seq].cur[0], y, WH, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaMemcpyAsync(s->h[seq].cur[1], cb, WH / 4, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaMemcpyAsync(s->h[seq].cur[2], cr, WH / 4, cudaMemcpyHostToDevice, s->stream));
-    return FH264_OK;
+    return upload_planes(s, seq, y, cb, cr, cudaMemcpyHostToDevice);
 }
 
 // Phase R on the current dpb of sequences [seq0, seq0+nseq).
@@ -311,6 +369,7 @@ extern "C" int fh264_scene_sad_batch(fh264_session *s, int seq0, int nseq, uint6
     for (int b = seq0; b < seq0 + nseq; b++)
         if (!s->has_ref[b]) return fail(FH264_E_STATE, "scene_sad before any reference picture (dpb.L == NULL => IDR, ref_frames.cpp:191)");
     CK(cudaSetDevice(s->device));
+    rc = adopt_uploads(s, seq0, nseq); if (rc) return rc;
     k_zero_sad<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0);
     dim3 gs(nseq >= 8 ? 74 : 296, nseq);
     k_scene_sad<<<gs, 256, 0, s->stream>>>(s->d_seqs, seq0, s->g);
@@ -329,11 +388,7 @@ extern "C" int fh264_upload_source_device(fh264_session *s, int seq, const void 
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     if (!dy || !dcb || !dcr) return fail(FH264_E_ARG, "null plane");
     CK(cudaSetDevice(s->device));
-    const size_t WH = (size_t)s->g.WH;
-    CK(cudaMemcpyAsync(s->h[seq].cur[0], dy, WH, cudaMemcpyDeviceToDevice, s->stream));
-    CK(cudaMemcpyAsync(s->h[seq].cur[1], dcb, WH / 4, cudaMemcpyDeviceToDevice, s->stream));
-    CK(cudaMemcpyAsync(s->h[seq].cur[2], dcr, WH / 4, cudaMemcpyDeviceToDevice, s->stream));
-    return FH264_OK;
+    return upload_planes(s, seq, dy, dcb, dcr, cudaMemcpyDeviceToDevice);
 }
 
 extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const fh264_params *p, fh264_mb_result *results)
@@ -351,6 +406,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     prm.basic = prm.basic ? 1 : 0;
     s->epoch++;
     cudaStream_t st = s->stream;
+    rc = adopt_uploads(s, seq0, nseq); if (rc) return rc;
     CK(cudaEventRecord(s->ev[0], st));
     k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, s->d_ticket);
     if (prm.basic) CK(cudaEventRecord(s->evk[0], st));
@@ -378,6 +434,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     if (s->copy_pending) { CK(cudaStreamWaitEvent(st, s->ev_copy_done, 0)); s->copy_pending = false; }   // records of the previous picture are home
     k_phase_c<<<gc, 128, 0, st>>>(s->d_seqs, seq0, g, prm);
     CKL();
+    for (int b = seq0; b < seq0 + nseq; b++) { CK(cudaEventRecord(s->ev_free[(int)s->cur_set[b]][b], st)); s->free_valid[(int)s->cur_set[b]][b] = 1; }   // `cur` is free for the upload after next
     CK(cudaEventRecord(s->ev[3], st));
     for (int b = seq0; b < seq0 + nseq; b++)
         CK(cudaMemcpyAsync(s->h_status + (size_t)b * ST_WORDS, s->h[b].status, sizeof(uint32_t) * ST_WORDS, cudaMemcpyDeviceToHost, st));

@@ -91,8 +91,11 @@ int fh264_sync(fh264_session *s);
 void *fh264_host_alloc(size_t bytes);
 void fh264_host_free(void *p);
 
-/* `frame` := source picture of sequence `seq` (planar 4:2:0, row-major, stride == width). Asynchronous on the
- * session stream; the host buffers must stay valid until the next fh264_sync()/synchronous call. */
+/* `frame` := source picture of sequence `seq` (planar 4:2:0, row-major, stride == width). Asynchronous; the host buffers
+ * must stay valid until the next fh264_sync()/synchronous call. Source pictures are double buffered:
+ * the copy runs on the session's upload stream into the buffer that is not being coded, so the picture for t+1 may be handed
+ * over right after fh264_encode_p_async(t) and its H2D overlaps the coding of t; the first call that reads `frame`
+ * (fh264_scene_sad*, fh264_encode_p*) waits for the copy and makes it current. */
 int fh264_upload_source(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
 
 /* Same, from planes already resident in device memory (device pointers; device-to-device copy on the stream). */

@@ -322,6 +322,29 @@ static int adopt_uploads(fh264_session *s, int seq0, int nseq)
     return FH264_OK;
 }
 
+// One Y4M FRAME payload (Y in_w x in_h, then Cb, Cr at half size), centre-cropped to the coded size on the copy engine:
+// ReadFromY4M (fileIO.cpp:286-337) — luma rows/columns from ((in - coded) >> 1), chroma from that offset >> 1.
+extern "C" int fh264_upload_source_frame(fh264_session *s, int seq, const uint8_t *frame420, int in_w, int in_h)
+{
+    int rc = check_seq(s, seq, 1); if (rc) return rc;
+    if (!frame420) return fail(FH264_E_ARG, "null frame");
+    const int W = s->g.W, H = s->g.H;
+    if ((in_w & ~15) != W || (in_h & ~15) != H) return fail(FH264_E_ARG, "input size does not crop to the session's coded size (fileIO.cpp:242-243)");
+    CK(cudaSetDevice(s->device));
+    const int target = 1 - s->cur_set[seq];
+    if (s->free_valid[target][seq]) CK(cudaStreamWaitEvent(s->up_stream, s->ev_free[target][seq], 0));
+    uint8_t **dst = s->h[seq].cur_alt;
+    const int ct = (in_h - H) >> 1, cl = (in_w - W) >> 1, in_wc = in_w >> 1, in_hc = in_h >> 1;
+    const size_t luma = (size_t)in_w * in_h, chroma = luma >> 2;       // as the reference sizes them (:262-263)
+    (void)in_hc;
+    CK(cudaMemcpy2DAsync(dst[0], W, frame420 + (size_t)ct * in_w + cl, in_w, W, H, cudaMemcpyHostToDevice, s->up_stream));
+    CK(cudaMemcpy2DAsync(dst[1], W / 2, frame420 + luma + (size_t)(ct >> 1) * in_wc + (cl >> 1), in_wc, W / 2, H / 2, cudaMemcpyHostToDevice, s->up_stream));
+    CK(cudaMemcpy2DAsync(dst[2], W / 2, frame420 + luma + chroma + (size_t)(ct >> 1) * in_wc + (cl >> 1), in_wc, W / 2, H / 2, cudaMemcpyHostToDevice, s->up_stream));
+    CK(cudaEventRecord(s->ev_up[seq], s->up_stream));
+    s->up_pending[seq] = 1;
+    return FH264_OK;
+}
+
 extern "C" int fh264_upload_source(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr)
 {
     int rc = check_seq(s, seq, 1); if (rc) return rc;

@@ -22,7 +22,7 @@ ERRORS = {-1: "FH264_E_ARG", -2: "FH264_E_CUDA", -3: "FH264_E_NO_DEVICE", -4: "F
           -6: "FH264_E_CAPACITY", -7: "FH264_E_UNSUPPORTED"}
 
 EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version", "fh264_set_stream", "fh264_sync",
-           "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
+           "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_frame", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
            "fh264_debug_feature", "fh264_cavlc_p", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
@@ -65,6 +65,7 @@ def load_library():
     L.fh264_host_alloc.argtypes = [C.c_size_t]
     L.fh264_host_free.argtypes = [vp]
     L.fh264_upload_source.argtypes = [vp, i32, u8p, u8p, u8p]
+    L.fh264_upload_source_frame.argtypes = [vp, i32, u8p, i32, i32]
     L.fh264_upload_recon.argtypes = [vp, i32, u8p, u8p, u8p]
     L.fh264_scene_sad.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
     L.fh264_scene_sad_batch.argtypes = [vp, i32, i32, C.POINTER(C.c_uint64)]
@@ -170,6 +171,13 @@ class Session:
         assert y.size == self.w * self.h and cb.size == y.size // 4 and cr.size == y.size // 4
         self._keep = (y, cb, cr)
         self._ck(self.L.fh264_upload_source(self.handle, seq, _ptr(y), _ptr(cb), _ptr(cr)))
+
+    def upload_source_frame(self, seq, frame420, in_w, in_h):
+        """One raw Y4M FRAME payload (Y, Cb, Cr of the INPUT size); the reference's centre crop happens in the H2D copy."""
+        f = _u8(frame420)
+        assert f.size >= in_w * in_h * 3 // 2
+        self._keep = (f,)
+        self._ck(self.L.fh264_upload_source_frame(self.handle, seq, _ptr(f), in_w, in_h))
 
     def upload_source_ptrs(self, seq, py, pcb, pcr, device=False):
         """Raw-pointer variant (pinned host memory, or device memory with device=True); asynchronous."""

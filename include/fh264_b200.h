@@ -98,6 +98,11 @@ void fh264_host_free(void *p);
  * (fh264_scene_sad*, fh264_encode_p*) waits for the copy and makes it current. */
 int fh264_upload_source(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
 
+/* Same for one raw Y4M FRAME payload (Y in_w x in_h, then Cb and Cr at half size) of ANY input size that crops to the session's
+ * coded size: the centre crop of ReadFromY4M (fileIO.cpp:286-337: rows / columns from (in - coded) >> 1, chroma from that
+ * offset >> 1) is done by the copy engine (strided H2D), no host-side repacking. */
+int fh264_upload_source_frame(fh264_session *s, int seq, const uint8_t *frame420, int in_w, int in_h);
+
 /* Same, from planes already resident in device memory (device pointers; device-to-device copy on the stream). */
 int fh264_upload_source_device(fh264_session *s, int seq, const void *dy, const void *dcb, const void *dcr);
 

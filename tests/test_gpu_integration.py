@@ -54,7 +54,8 @@ def test_bitstream_and_reconstruction_match_golden(golden, tmp_path, encoder):
 @needs_binary
 @pytest.mark.skipif(not refdump.have_ref_encoder(), reason="compiled reference not present")
 @pytest.mark.parametrize("w,h,seed,frames,qp,window,maxdiff,intra_every", [(176, 144, 1, 30, 28, 16, 3, 1000),     # BASELINE config 1 (QCIF, 30 frames)
-                                                                            (352, 288, 2, 12, 28, 32, -1, 5)])     # CIF, adaptive MAXDIFF, periodic IDR
+                                                                            (352, 288, 2, 12, 28, 32, -1, 5),      # CIF, adaptive MAXDIFF, periodic IDR
+                                                                            (176, 144, 7, 5, 12, 16, 3, 1000)])    # QP 12: large levels (CAVLC escape codes, suffixLength up to 6)
 @both_encoders
 def test_bitstream_matches_live_reference(tmp_path, w, h, seed, frames, qp, window, maxdiff, intra_every, encoder):
     y4m = str(tmp_path / "in.y4m")

@@ -297,3 +297,32 @@ def test_low_contrast_content_many_gated_candidates(contrast, noise):
     assert st[0] == 0, "status flags %d" % st[0]
     assert np.array_equal(got, want), np.argwhere(got != want)[:6]
     assert all(np.array_equal(a, b) for a, b in zip(recon, want_recon))
+
+
+def test_y4m_frame_ingest_crops_like_the_reference():
+    """fh264_upload_source_frame: the centre crop of ReadFromY4M (fileIO.cpp:286-337) done by the strided H2D copy gives the
+    same pictures — hence the same records and reconstruction — as cropping on the host (200x120 -> 192x112, odd crop offsets)."""
+    w_in, h_in = 200, 120
+    c = synth.SynthClip(w_in, h_in, 11)
+    raw = [c.frame(t) for t in range(3)]
+    crop = [tuple(synth.crop16(p, chroma=(i > 0)) for i, p in enumerate(f)) for f in raw]
+    h, w = crop[0][0].shape
+    out = []
+    for mode in ("host_crop", "frame"):
+        with fh.Session(w, h) as s:
+            s.upload_recon(0, *crop[0])
+            for t in (1, 2):
+                if mode == "frame":
+                    s.upload_source_frame(0, np.concatenate([p.ravel() for p in raw[t]]), w_in, h_in)
+                else:
+                    s.upload_source(0, *crop[t])
+                sad = s.scene_sad(0)
+                rec = s.encode_p(24, 32, 3, 0)[0].copy()
+            out.append((sad, rec, s.download_recon(0)))
+    assert out[0][0] == out[1][0]
+    assert np.array_equal(out[0][1], out[1][1])
+    for a, b in zip(out[0][2], out[1][2]):
+        assert np.array_equal(a, b)
+    with fh.Session(w, h) as s:
+        with pytest.raises(fh.Fh264Error):
+            s.upload_source_frame(0, np.zeros(176 * 144 * 3 // 2, np.uint8), 176, 144)      # does not crop to 192x112

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seq
     }
 }
 
-// One CTA per 64x64 tile of plane-0 positions. Cell = (K0>>7)*128 + (K1>>6). Order inside a cell is arbitrary:
+// One CTA per 64x64 tile of plane-0 positions. Cell = (K1>>6)*128 + (K2>>6) (the two half-sum gates of stage 2). Order inside a cell is arbitrary:
 // stage 2 re-derives the reference's arrival order (sum bucket, side, x, y) from the entry itself.
 __global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ seqs, int seq0, Geo g)
 {
@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ s
         int ly = i / tw, lx = i - ly * tw;
         size_t o = (size_t)(ty0 + ly) * g.W + tx0 + lx;
         const uint4 kv = K[o];
-        const int k0 = feat_raw(kv, 0), k1 = feat_raw(kv, 1);
+        const int k0 = feat_raw(kv, 0), k1 = feat_raw(kv, 1), k2 = feat_raw(kv, 2);
         ub |= (k0 == 0) | (k0 >= 16203);
-        atomicAdd(&hist[((k0 >> 7) << 7) | (k1 >> 6)], 1u);
+        atomicAdd(&hist[((k1 >> 6) << 7) | (k2 >> 6)], 1u);
     }
     if (ub) atomicOr(&S.status[ST_FLAGS_NEXT], FLAG_UB_INPUT);
     __syncthreads();
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ s
         e.x = (uint16_t)(tx0 + lx); e.y = (uint16_t)(ty0 + ly);
         e.k0 = (uint16_t)feat_raw(kv, 0); e.k1 = (uint16_t)feat_raw(kv, 1); e.k2 = (uint16_t)feat_raw(kv, 2);
         e.k3 = (uint16_t)feat_raw(kv, 3); e.k4 = (uint16_t)feat_raw(kv, 4); e.pad = 0;
-        uint32_t pos = atomicAdd(&hist[((e.k0 >> 7) << 7) | (e.k1 >> 6)], 1u);
+        uint32_t pos = atomicAdd(&hist[((e.k1 >> 6) << 7) | (e.k2 >> 6)], 1u);
         *(uint4 *)&te[pos] = *(const uint4 *)&e;
     }
 }

@@ -502,7 +502,24 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
                 }
             }
         }
-        __syncthreads();                                               // keys1 and keys2 complete
+        // stage 2, lazily: the block's best stage-2 candidate by (total, list order) is THE stage-2 contribution iff it is one of
+        // the 33 smallest keys. Its verification shares the barriers of the stage-1 selection: per-warp minima before the key
+        // barrier, count of the keys below it before the selection's first barrier, verdict after the selection.
+        if (n2 > 0) { const u64 wmin = warp_min_u64(t2); if (lane == 0) sh.sel_min[warp] = wmin; }
+        __syncthreads();                                               // keys1, keys2 and the stage-2 minima complete
+        u64 cand = KEY_NONE;
+        bool need_count = false;
+        if (n2 > 0) {
+            cand = min(min(sh.sel_min[0], sh.sel_min[1]), min(sh.sel_min[2], sh.sel_min[3]));
+            need_count = cand != KEY_NONE && n2 > FH_S3_MAX;            // n2 <= 33: every candidate is on the list
+            if (need_count) {
+                const u64 ckey = cand & ((1ull << 42) - 1);
+                int below = 0;
+                for (int i = tid; i < n2; i += PB_NT) below += sh.keys2[i] < ckey;
+                below = __reduce_add_sync(0xffffffffu, below);
+                if (lane == 0) sh.sel_cnt[warp] = below;
+            }
+        }
         PB_SUB(14);
         const int K1 = block_select_smallest_u32(sh.keys1, n1, FH_S1_MAX, &sh.bs, sh.mem1, callno++);
         PB_SUB(15);
@@ -521,41 +538,40 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
                 rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, clampi_(xP + dx, 0, W - 1), clampi_(yP + dy, 0, H - 1) + r);
             }
         }
-        // stage 2, lazily: the block's best stage-2 candidate by (total, list order) is THE stage-2 contribution iff it is
-        // one of the 33 smallest keys. Verify by counting keys below it; on failure reject it and retry, then fall back to the
-        // exact selection. (n2 <= 33: every candidate is on the list.)
+        // stage 2 verdict; on failure the owner rejects the candidate and the block retries (twice), then falls back to the exact selection
         if (n2 > 0) {
-            u64 cand = KEY_NONE;
-            bool settled = false;
-            for (int attempt = 0; attempt < 3 && !settled; attempt++) {
-                u64 wmin = warp_min_u64(t2);
-                if (lane == 0) sh.sel_min[warp] = wmin;
-                __syncthreads();
-                cand = min(min(sh.sel_min[0], sh.sel_min[1]), min(sh.sel_min[2], sh.sel_min[3]));
-                if (cand == KEY_NONE || n2 <= FH_S3_MAX) { settled = true; __syncthreads(); break; }
-                const u64 ckey = cand & ((1ull << 42) - 1);
-                int below = 0;
-                for (int i = tid; i < n2; i += PB_NT) below += sh.keys2[i] < ckey;
-                below = __reduce_add_sync(0xffffffffu, below);
-                if (lane == 0) sh.sel_cnt[warp] = below;
-                __syncthreads();
-                const int rank = sh.sel_cnt[0] + sh.sel_cnt[1] + sh.sel_cnt[2] + sh.sel_cnt[3];
-                if (rank < FH_S3_MAX) settled = true;
-                else if (t2 == cand) {
+            bool settled = !need_count;
+            if (need_count) {
+                const int rank0 = sh.sel_cnt[0] + sh.sel_cnt[1] + sh.sel_cnt[2] + sh.sel_cnt[3];
+                settled = rank0 < FH_S3_MAX;
+            }
+            for (int attempt = 1; attempt < 3 && !settled; attempt++) {
+                if (t2 == cand) {
                     // the owner rejects it and recomputes its local best without it
-                    const int rej = (int)(ckey & 1023);
+                    const int rej = (int)(cand & 1023);
                     t2 = KEY_NONE;
                     for (int i = tid; i < n2; i += PB_NT) {
                         const u64 key = sh.keys2[i];
                         if (i == rej || (key >> 10) >= (u64)FH_COST_EMPTY) continue;
-                        sh.keys2[i] = key;
                         const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
                         const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16);
                         const u64 fk = ((u64)((int)(v.y >> 18) + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key;
                         if (fk > cand) t2 = min(t2, fk);       // candidates rejected earlier compare below `cand`
                     }
                 }
+                __syncthreads();                               // everybody has read sel_min / sel_cnt of the previous attempt
+                const u64 wmin = warp_min_u64(t2);
+                if (lane == 0) sh.sel_min[warp] = wmin;
                 __syncthreads();
+                cand = min(min(sh.sel_min[0], sh.sel_min[1]), min(sh.sel_min[2], sh.sel_min[3]));
+                if (cand == KEY_NONE) { settled = true; break; }
+                const u64 ckey = cand & ((1ull << 42) - 1);
+                int below = 0;
+                for (int i = tid; i < n2; i += PB_NT) below += sh.keys2[i] < ckey;
+                below = __reduce_add_sync(0xffffffffu, below);
+                if (lane == 0) sh.sel_cnt[warp] = below;
+                __syncthreads();
+                settled = sh.sel_cnt[0] + sh.sel_cnt[1] + sh.sel_cnt[2] + sh.sel_cnt[3] < FH_S3_MAX;
             }
             if (settled) { if (tid == 0) mine = min(mine, cand); }
             else {

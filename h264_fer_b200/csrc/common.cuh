@@ -51,6 +51,9 @@ struct __align__(16) MbMotion {       // phase B output per macroblock (48 bytes
 
 struct S3Entry { int16_t mvx, mvy; uint16_t sad, pad; };           // stage-3 list slot, list order
 struct PartA { uint16_t suma[5]; uint16_t n3; uint32_t s2_off; uint32_t n2; };   // per 8x8 partition
+// n2 with this bit: the stage-2 candidate set up to j_stop (low 8 bits) does not fit the phase-A buffers (flat / low-contrast
+// content: thousands of positions share one 8x8 sum); phase B enumerates it itself once the predictor is known (stage2_slow).
+#define S2_SLOW 0x80000000u
 
 static_assert(sizeof(fh264_mb_result) == 832, "ABI record size");
 static_assert(sizeof(MbMotion) == 48, "MbMotion size");

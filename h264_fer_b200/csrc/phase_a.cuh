@@ -502,14 +502,15 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
     __syncwarp();
     const int ns = w->n_surv;
     if (ns > CAP) {
-        // too many gated survivors for this launch's buffers
+        // too many gated survivors for this launch's buffers: the fallback launch takes the partition over; when that cannot
+        // hold it either (or its list is full) phase B enumerates the set itself. j_stop is final here (the counts saw every entry).
+        const int jsb = bound_from_bins();
         if (lane == 0) {
             PartA *pa = &S.parta[part];
             pa->s2_off = 0;
-            pa->n2 = 0;
             bool listed = false;
             if (!REDO) { const uint32_t k = atomicAdd(&S.status[ST_S2REDO], 1u); if (k < S2_REDO_MAX) { S.s2redo[k] = (uint32_t)part; listed = true; } }
-            if (!listed) atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY);
+            pa->n2 = listed ? 0u : (S2_SLOW | (uint32_t)jsb);
         }
         return;
     }
@@ -544,9 +545,10 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
     // without first reading the partition header)
     uint32_t off = (uint32_t)part * 1024u;
     if (lane == 0) {
-        if (n2 > 1023) { atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); n2 = 0; }
         PartA *pa = &S.parta[part];
-        pa->s2_off = off; pa->n2 = (uint32_t)n2;
+        pa->s2_off = off;
+        if (n2 > 1023) { pa->n2 = S2_SLOW | (uint32_t)js; n2 = 0; }      // more candidates than a pool slice: phase B's own enumeration
+        else pa->n2 = (uint32_t)n2;
     }
     n2 = __shfl_sync(0xffffffffu, n2, 0);
     if (n2 == 0) return;

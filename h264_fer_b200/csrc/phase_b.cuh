@@ -128,6 +128,11 @@ struct PBShared {
     uint16_t qrc[16 * 61];
     uint32_t my_ticket;
     int red[4];
+    // stage2_slow
+    int slow_ns, slow_total, slow_arg[12];
+    u64 slow_thr;
+    u64 slow_key[FH_S3_MAX + 1];
+    uint32_t slow_pos[FH_S3_MAX + 1];        // (dx + 512) | (dy + 512) << 16 of the selected candidates, list order
 };
 
 // Block-cooperative version of warp_select_smallest (warp_select.cuh): the K = min(k, #valid) smallest of
@@ -267,6 +272,111 @@ __device__ __forceinline__ void median_pred(int aA, int ax, int ay, int aB, int 
     if (!aC) { cx = ax; cy = ay; sc = sa; }
     if (sa + sb + sc == 1) { ox = sa ? ax : (sb ? bx : cx); oy = sa ? ay : (sb ? by : cy); return; }
     ox = median3_(ax, bx, cx); oy = median3_(ay, by, cy);
+}
+
+// Stage 2 for a partition whose candidate set did not fit the phase-A buffers (PartA.n2 & S2_SLOW): flat or low-contrast
+// content, where thousands of positions share one 8x8 sum and the set "up to j_stop" (moestimation.cpp:470-497) is most of
+// the search diamond. The set cannot be stored for every partition of such a picture, and which 33 of it the reference would
+// evaluate depends on the predictor, so phase B walks the index itself now that the predictor is known:
+//   pass 1  every warp walks (tile, K1-row) ranges with its lanes striding the entries; each thread keeps the two smallest
+//           keys (cost << 32 | arrival key) it met -> the 33rd smallest of those 256 keys bounds the 33rd smallest key
+//   pass 2  the same walk collects the keys at or below the bound, which are ranked exactly
+// then the SADs of the 33 list members (8 threads each). Bucket s0 is visited twice by the reference (:476,486): its entries
+// are emitted a second time with the side bit set, which orders them right after the first visit. Returns this thread's
+// candidate for the partition minimum; sh.slow_pos[] maps list positions back to displacements. Block-uniform call.
+#define SLOW_CAP 512
+// (arguments travel through sh.slow_arg: the call must not cost the common path registers)
+__device__ __noinline__ u64 stage2_slow(const SeqDev &S, const Geo &g, PBShared &sh, uint2 cur_row)
+{
+    const int xP = sh.slow_arg[0], yP = sh.slow_arg[1], js = sh.slow_arg[2], genx = sh.slow_arg[3], geny = sh.slow_arg[4], mvpx = sh.slow_arg[5], mvpy = sh.slow_arg[6];
+    const int s[5] = { sh.slow_arg[7], sh.slow_arg[8], sh.slow_arg[9], sh.slow_arg[10], sh.slow_arg[11] };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tx0 = max(0, xP - 279) >> FH_TILE_SHIFT, tx1 = min(g.W - 1, xP + 279) >> FH_TILE_SHIFT;
+    const int ty0 = max(0, yP - 279) >> FH_TILE_SHIFT, ty1 = min(g.H - 1, yP + 279) >> FH_TILE_SHIFT;
+    const int ntx = tx1 - tx0 + 1, ntiles = ntx * (ty1 - ty0 + 1);
+    const int qlo = max(0, s[1] - 99) >> 6, qhi = min(8191, s[1] + 99) >> 6, nq = qhi - qlo + 1;
+    const int k2lo = max(0, s[2] - 99) >> 6, k2hi = min(8191, s[2] + 99) >> 6;
+    const uint4 *__restrict__ tent = (const uint4 *)S.tent;
+    u64 *smin = sh.keys2;                       // [0, 256): per-thread minima; [256, 256 + SLOW_CAP): survivor keys
+    u64 *skey = sh.keys2 + 256;
+    uint32_t *spos = sh.keys1;                  // survivor displacements
+    // walks every gated entry with j <= js; fn(key, packed displacement)
+    auto walk = [&](auto fn) {
+        for (int it = warp; it < ntiles * nq; it += PB_NT / 32) {
+            const int tt = it / nq, q = it - tt * nq, tyy = tt / ntx, tx = tx0 + tt - tyy * ntx, ty = ty0 + tyy;
+            const int rx0 = tx << FH_TILE_SHIFT, ry0 = ty << FH_TILE_SHIFT;
+            const int ddx = max(0, max(rx0 - xP, xP - (rx0 + FH_TILE - 1))), ddy = max(0, max(ry0 - yP, yP - (ry0 + FH_TILE - 1)));
+            if (ddx + ddy >= 280) continue;
+            const int tile = ty * g.tilesx + tx;
+            const uint16_t *ts = S.tstart + (size_t)tile * FH_TSTART_PITCH;
+            const int e0 = __ldg(&ts[(qlo + q) * 128 + k2lo]), e1 = __ldg(&ts[(qlo + q) * 128 + k2hi + 1]);
+            const uint32_t gbase = (uint32_t)tile * (FH_TILE * FH_TILE);
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const uint4 v = __ldg(tent + gbase + e);
+                const int x = v.x & 0xffff, y = v.x >> 16, k0 = v.y & 0xffff, k1 = v.y >> 16, k2 = v.z & 0xffff;
+                const int j = iabs_(k0 - s[0]), dx = x - xP, dy = y - yP;
+                if (j > js || j > 180 || iabs_(dx) + iabs_(dy) >= 280 || iabs_(k1 - s[1]) >= 100 || iabs_(k2 - s[2]) >= 100) continue;
+                const uint32_t feat = (uint32_t)feat_dist(s, k0, k1, k2, (int)(v.z >> 16), (int)(v.w & 0xffff));
+                const uint32_t cost = (uint32_t)(iabs_(dx - genx) + iabs_(dy - geny) + 4) * feat;
+                const uint32_t akey = ((uint32_t)j << 21) | ((uint32_t)(k0 > s[0]) << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
+                const uint32_t pos = (uint32_t)(dx + 512) | ((uint32_t)(dy + 512) << 16);
+                fn(((u64)cost << 32) | akey, pos);
+                if (j == 0) fn(((u64)cost << 32) | akey | (1u << 20), pos);         // second visit of bucket s0
+            }
+        }
+    };
+    // pass 1
+    u64 m1 = KEY_NONE, m2 = KEY_NONE;
+    int cnt = 0;
+    walk([&](u64 key, uint32_t) { cnt++; const u64 lo = key < m1 ? key : m1, hi = key < m1 ? m1 : key; m1 = lo; m2 = hi < m2 ? hi : m2; });
+    smin[tid] = m1; smin[PB_NT + tid] = m2;
+    if (tid == 0) { sh.slow_ns = 0; sh.slow_total = 0; sh.slow_thr = KEY_NONE - 1; }
+    __syncthreads();
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) atomicAdd(&sh.slow_total, cnt);
+    // the 33rd smallest of the 256 minima (keys are unique): the thread that holds it publishes it
+    {
+        int r1 = 0, r2 = 0;
+        for (int i = 0; i < 2 * PB_NT; i++) { const u64 k = smin[i]; r1 += k < m1; r2 += k < m2; }
+        if (m1 != KEY_NONE && r1 == FH_S3_MAX - 1) sh.slow_thr = m1;
+        if (m2 != KEY_NONE && r2 == FH_S3_MAX - 1) sh.slow_thr = m2;
+    }
+    __syncthreads();
+    const u64 thr = sh.slow_thr;
+    const int K = min(FH_S3_MAX, sh.slow_total);
+    if (K == 0) return KEY_NONE;
+    // pass 2
+    walk([&](u64 key, uint32_t pos) {
+        if (key <= thr) { const int p = atomicAdd(&sh.slow_ns, 1); if (p < SLOW_CAP) { skey[p] = key; spos[p] = pos; } }
+    });
+    __syncthreads();
+    const int ns = sh.slow_ns;
+    if (ns > SLOW_CAP) { if (tid == 0) atomicOr(&S.status[ST_FLAGS], FLAG_CAPACITY); return KEY_NONE; }
+    for (int i = tid; i < ns; i += PB_NT) {
+        const u64 key = skey[i];
+        int rank = 0;
+        for (int k = 0; k < ns; k++) rank += skey[k] < key;
+        if (rank < K) { sh.slow_key[rank] = key; sh.slow_pos[rank] = spos[i]; }
+    }
+    __syncthreads();
+    // SADs of the list members (integer displacement: plane 0), 8 threads per member, and their totals
+    u64 mine = KEY_NONE;
+    const int r = tid & 7;
+    for (int m0 = 0; m0 < K; m0 += PB_NT / 8) {
+        const int m = m0 + (tid >> 3);
+        int sad = 0, dx = 0, dy = 0;
+        if (m < K) {
+            const uint32_t pos = sh.slow_pos[m];
+            dx = (int)(pos & 0xffff) - 512; dy = (int)(pos >> 16) - 512;
+            sad = sad8(cur_row, load_row8(S.planes, g.W, g.H, xP + dx, yP + dy + r));
+        }
+        sad += __shfl_xor_sync(0xffffffffu, sad, 1);
+        sad += __shfl_xor_sync(0xffffffffu, sad, 2);
+        sad += __shfl_xor_sync(0xffffffffu, sad, 4);
+        if (m < K && r == 0 && (uint32_t)(sh.slow_key[m] >> 32) < (uint32_t)FH_COST_EMPTY)
+            mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | (u64)m);
+    }
+    return mine;
 }
 
 __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__ seqs, int seq0, int nseq, Geo g, fh264_params prm,
@@ -454,7 +564,8 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
         if (sa < qseg) wa = qf_load16(S.planes + (size_t)(warp * qpw + fa) * g.WH, W, H, x0, y0 + ra);
         if (sb < qseg) wb = qf_load16(S.planes + (size_t)(warp * qpw + fb) * g.WH, W, H, x0, y0 + rb);
         // stage 2 (:470-507) keys while those loads fly: cost << 10 | arrival rank; SADs were measured in phase A
-        const int n2 = (int)pa.n2;
+        const bool slow2 = (pa.n2 & S2_SLOW) != 0;                     // candidate set too large for phase A: enumerated below
+        const int n2 = slow2 ? 0 : (int)pa.n2;
         const uint2 *pool = S.s2pool + pa.s2_off;
         u64 t2 = KEY_NONE;               // this thread's best stage-2 (total, key) among candidates not yet rejected
         for (int i = tid; i < n2; i += PB_NT) {
@@ -481,6 +592,15 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
             int s[5];
             block_sums(rows, s);                                       // suma[0..4] (:440-451)
             const FeatQ fq = feat_query(s);
+            if (slow2) {
+                if (tid == 0) {
+                    sh.slow_arg[0] = xP; sh.slow_arg[1] = yP; sh.slow_arg[2] = (int)(pa.n2 & 0xffu); sh.slow_arg[3] = genx; sh.slow_arg[4] = geny;
+                    sh.slow_arg[5] = mvpx; sh.slow_arg[6] = mvpy;
+                    for (int k = 0; k < 5; k++) sh.slow_arg[7 + k] = s[k];
+                }
+                __syncthreads();
+                mine = min(mine, stage2_slow(S, g, sh, pick_row(rows, tid & 7)));
+            }
             // planes in batches of 4 * qpw (all 16 at once up to WindowSize 32): row sums -> warp barrier -> records and keys
             for (int f0 = 0; f0 < 16; f0 += 4 * qpw) {
                 const int fw = f0 + warp * qpw;                        // this warp's first plane of the batch
@@ -614,8 +734,11 @@ __global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__
                 bx = ((genx + cx - g1) << 2) | (f & 3); by = ((geny + pos - cx * w1 - g1) << 2) | (f >> 2);
             } else if (stage == 1) {
                 const int wi = (int)(b & 1023);
-                const uint2 v = wi < PB_POOL_PREF ? sh.pool[pi][wi] : __ldg(&S.s2pool[pa.s2_off + (uint32_t)wi]);
-                bx = ((int)(int16_t)(v.x & 0xffff)) << 2; by = ((int)(int16_t)(v.x >> 16)) << 2;
+                if (slow2) { const uint32_t pos = sh.slow_pos[wi]; bx = ((int)(pos & 0xffff) - 512) << 2; by = ((int)(pos >> 16) - 512) << 2; }
+                else {
+                    const uint2 v = wi < PB_POOL_PREF ? sh.pool[pi][wi] : __ldg(&S.s2pool[pa.s2_off + (uint32_t)wi]);
+                    bx = ((int)(int16_t)(v.x & 0xffff)) << 2; by = ((int)(int16_t)(v.x >> 16)) << 2;
+                }
             } else {
                 const S3Entry e = sh.s3[pi][(int)(b & 63)];
                 bx = e.mvx; by = e.mvy;

@@ -326,3 +326,28 @@ def test_y4m_frame_ingest_crops_like_the_reference():
     with fh.Session(w, h) as s:
         with pytest.raises(fh.Fh264Error):
             s.upload_source_frame(0, np.zeros(176 * 144 * 3 // 2, np.uint8), 176, 144)      # does not crop to 192x112
+
+
+@pytest.mark.parametrize("contrast,noise", [(0.0, 1.0), (0.0, 0.0), (0.02, 0.5)])
+def test_flat_content_takes_the_slow_stage2_path_and_stays_exact(contrast, noise):
+    """Flat / noisy-flat pictures: thousands of positions share one 8x8 sum, the stage-2 candidate set up to j_stop no longer
+    fits the phase-A buffers, and phase B enumerates it itself (stage2_slow). Records and reconstruction against the oracle."""
+    from oracle import port
+    w, h, qp, window, maxdiff = 176, 144, 28, 16, 3
+    clip = synth.SynthClip(w, h, 21, noise=noise, contrast=contrast)
+    ref, cur = clip.frame(0), clip.frame(1)
+    o = port.Oracle(w, h)
+    ub = o.phase_r(ref[0])
+    want_rec, want_recon = o.encode_p(cur, ref, qp, window, maxdiff)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, *ref)
+        s.upload_source(0, *cur)
+        if ub:
+            with pytest.raises(fh.Fh264Error):
+                s.encode_p(qp, window, maxdiff)
+            return
+        got = fh.records_to_ints(s.encode_p(qp, window, maxdiff)[0])
+        recon = s.download_recon(0)
+    assert np.array_equal(got, want_rec), "records differ: MBs %s" % np.nonzero((got != want_rec).any(1))[0][:10]
+    for a, b in zip(recon, want_recon):
+        assert np.array_equal(a, b)

@@ -42,7 +42,7 @@ enum {
     FH264_E_STATE = -4,        /* call order violated (e.g. encode_p before any reference picture) */
     FH264_E_UB_INPUT = -5,     /* reference-undefined input: an 8x8 reference window sums to 0 or >= 16203
                                   (moestimation.cpp:153-158,477-480) */
-    FH264_E_CAPACITY = -6,     /* stage-2 candidate pool exhausted (flat content); see DESIGN.md */
+    FH264_E_CAPACITY = -6,     /* a fixed-size buffer cannot hold the picture's data */
     FH264_E_UNSUPPORTED = -7   /* parameter outside the supported range (WindowSize > 64) */
 };
 

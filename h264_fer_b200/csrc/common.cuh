@@ -92,25 +92,15 @@ __device__ __forceinline__ int mid_(int a, int b) { return (a + b + 1) >> 1; }
 // 8 consecutive bytes starting at an arbitrary address, as two little-endian words: two aligned 8-byte loads (two LSU
 // wavefronts per lane instead of three 4-byte ones) and a funnel shift; reads up to 7 bytes past the block (the plane
 // buffers carry 16 bytes of slack).
-#ifndef FH_ROW_LD64
-#define FH_ROW_LD64 1
-#endif
 __device__ __forceinline__ uint2 load8_unaligned(const uint8_t *p)
 {
     const uintptr_t a = (uintptr_t)p;
-#if FH_ROW_LD64
     const uint2 *q = (const uint2 *)(a & ~(uintptr_t)7);
     const uint32_t sh = (uint32_t)(a & 7) * 8;
     const uint2 lo = __ldg(q), hi = __ldg(q + 1);
     const bool b = sh >= 32;
     const uint32_t w0 = b ? lo.y : lo.x, w1 = b ? hi.x : lo.y, w2 = b ? hi.y : hi.x;
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));       // shift amount is taken mod 32
-#else
-    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(a & 3) * 8;
-    uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
-#endif
 }
 
 // satdLuma8x8MVs (moestimation.cpp:175-195), one row of the reference block with the reference's clamping rule

@@ -11,14 +11,9 @@
 #include "qfeat.cuh"
 
 #define COST_INVALID 0xffffffffu
-#ifndef FH_S3_PIPE
-#define FH_S3_PIPE 0
-#endif
+// tuning constants (each one the winner of an A/B build on the B200, profiles/tools/ab_variants.sh)
 #ifndef FH_S3_SADR
-#define FH_S3_SADR 9      // stage-3 SAD rounds: member loads in flight per lane
-#endif
-#ifndef FH_S2_SIMD
-#define FH_S2_SIMD 1
+#define FH_S3_SADR 9      // stage-3 SAD: member rows in flight per lane (all 33 members in one round)
 #endif
 #ifndef FH_S2_UNR
 #define FH_S2_UNR 4        // index entries in flight per lane in the stage-2 visit loop
@@ -27,11 +22,7 @@
 #define FH_S2_SADR 8       // stage-2 SAD: candidate rows in flight per lane
 #endif
 #ifndef FH_S3_UNR
-#define FH_S3_UNR 4
-#endif
-#ifndef FH_X_SKIPA
-#define FH_X_SKIPA 0     // experiments only: drop the stage-3 feature loads (wrong results, timing probes)
-#define FH_X_SKIPB 0
+#define FH_S3_UNR 4        // stage-3 first call: feature records in flight per lane
 #endif
 #ifndef FH_S2_MINB
 #define FH_S2_MINB 12     // fast stage-2 launch: 80 registers, 12 CTAs per SM
@@ -190,11 +181,10 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
         uint32_t *cc = cost + c * w3;
         for (int r = 0; r < rlo; r++) cc[r] = COST_INVALID;
         for (int r = rhi; r < w3; r++) cc[r] = COST_INVALID;
-        // software pipeline: the loads of the next 4 rows are in flight while the current 4 are evaluated
         const uint4 *kp = K0p + (size_t)(yP - g3 + rlo) * W + rx;
         auto ld4 = [&](const uint4 *q, int r0, uint4 (&v)[FH_S3_UNR]) {
 #pragma unroll
-            for (int u = 0; u < FH_S3_UNR; u++) { v[u] = make_uint4(0, 0, 0, 0); if (xok && r0 + u < rhi && !FH_X_SKIPA) v[u] = __ldg(q + (size_t)u * W); }
+            for (int u = 0; u < FH_S3_UNR; u++) { v[u] = make_uint4(0, 0, 0, 0); if (xok && r0 + u < rhi) v[u] = __ldg(q + (size_t)u * W); }
         };
         auto ev4 = [&](const uint4 (&v)[FH_S3_UNR], int r0) {
 #pragma unroll
@@ -207,20 +197,8 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
                 }
             }
         };
-#if FH_S3_PIPE
-        uint4 va[FH_S3_UNR], vb[FH_S3_UNR];
-        ld4(kp, rlo, va);
-        for (int r0 = rlo; r0 < rhi; r0 += 8) {
-            ld4(kp + (size_t)4 * W, r0 + 4, vb);
-            ev4(va, r0);
-            ld4(kp + (size_t)8 * W, r0 + 8, va);
-            ev4(vb, r0 + 4);
-            kp += (size_t)8 * W;
-        }
-#else
         uint4 va[FH_S3_UNR];
         for (int r0 = rlo; r0 < rhi; r0 += FH_S3_UNR) { ld4(kp, r0, va); ev4(va, r0); kp += (size_t)FH_S3_UNR * W; }
-#endif
     }
     // leftover columns: lane = row
     for (int c = ncf; c < w3; c++) {
@@ -370,7 +348,6 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
     // upper bound of j_stop (counts only grow, so the first j whose running total exceeds 128 can only move down). The
     // feature distance is computed afterwards in a dense pass over the kept entries.
     int jb = 180;
-#if FH_S2_SIMD
     // the four gates in 16-bit lanes: (|dx|, |dy|) and (j, |dK1|) by max(a - b, b - a), the Manhattan sum by a dot product
     const uint32_t Pxy = (uint32_t)xP | ((uint32_t)yP << 16), S01 = (uint32_t)s[0] | ((uint32_t)s[1] << 16), LIM01 = 180u | (99u << 16);
     const int s2m = s[2] - 99;
@@ -390,23 +367,6 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
             }
         }
     };
-#else
-    auto visit = [&](const uint4 v, uint32_t eidx) {
-        const int x = v.x & 0xffff, y = v.x >> 16, k0 = v.y & 0xffff, k1 = v.y >> 16, k2 = v.z & 0xffff;
-        const int j = iabs_(k0 - s[0]), dx = x - xP, dy = y - yP;
-        if (j <= 180 && iabs_(dx) + iabs_(dy) < 280 && iabs_(k1 - s[1]) < 100 && iabs_(k2 - s[2]) < 100) {
-            const int side = k0 > s[0];
-            atomicAdd(&w->bins[2 * j + side], 1u);
-            if (j <= jb) {
-                const int pos = atomicAdd(&w->n_surv, 1);
-                if (pos < CAP) {
-                    w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
-                    w->aval[pos] = eidx;
-                }
-            }
-        }
-    };
-#endif
     // j_stop bound from the counts so far: first j whose running gated count (bucket s0 twice) exceeds 128 (:496)
     auto bound_from_bins = [&]() -> int {
         uint32_t local = 0, c6[6];

@@ -113,6 +113,11 @@ static cudaError_t sync_streams(fh264_session *s)
     return e;
 }
 
+// Wavefront visiting order x + slope * y. Any slope >= 2 keeps every dependency (left, up, up-right, up-left) on a smaller
+// ticket. 3 is the measured optimum (a macroblock needs THREE quadrants of its up-right neighbour, so with slope 2 it is drawn
+// before they can be ready and its CTA idles: 1080p alone 4.07 -> 3.51 ms, 8 sequences 5.60 -> 5.24 ms); FH264_WF_SLOPE overrides.
+static int wf_slope() { const char *e = getenv("FH264_WF_SLOPE"); const int v = e ? atoi(e) : 3; return v >= 2 ? v : 2; }
+
 template <typename T>
 static cudaError_t dalloc(fh264_session *s, T **p, size_t count)
 {
@@ -233,11 +238,12 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     }
     OPEN_CK(dalloc(s, &s->d_seqs, (size_t)batch));
     OPEN_CK(cudaMemcpy(s->d_seqs, s->h.data(), sizeof(SeqDev) * batch, cudaMemcpyHostToDevice));
-    // anti-diagonal (x + 2y) visiting order of the wavefront
+    // anti-diagonal (x + slope * y) visiting order of the wavefront
     std::vector<int> order(g.nmb);
     for (int i = 0; i < g.nmb; i++) order[i] = i;
     const int Wmb = g.Wmb;
-    std::stable_sort(order.begin(), order.end(), [Wmb](int a, int b) { return (a % Wmb) + 2 * (a / Wmb) < (b % Wmb) + 2 * (b / Wmb); });
+    const int slope = wf_slope();
+    std::stable_sort(order.begin(), order.end(), [Wmb, slope](int a, int b) { return (a % Wmb) + slope * (a / Wmb) < (b % Wmb) + slope * (b / Wmb); });
     OPEN_CK(dalloc(s, &s->d_wf_order, (size_t)g.nmb));
     OPEN_CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.nmb, cudaMemcpyHostToDevice));
     OPEN_CK(dalloc(s, &s->d_ticket, (size_t)4));
@@ -753,7 +759,8 @@ extern "C" int fh264_band_config(fh264_session *s, int rank, int world, int mb_r
     std::vector<int> order(g.band_nmb);
     for (int i = 0; i < g.band_nmb; i++) order[i] = g.band_mb0 + i;
     const int Wmb = g.Wmb;
-    std::stable_sort(order.begin(), order.end(), [Wmb](int a, int b) { return (a % Wmb) + 2 * (a / Wmb) < (b % Wmb) + 2 * (b / Wmb); });
+    const int slope = wf_slope();
+    std::stable_sort(order.begin(), order.end(), [Wmb, slope](int a, int b) { return (a % Wmb) + slope * (a / Wmb) < (b % Wmb) + slope * (b / Wmb); });
     CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.band_nmb, cudaMemcpyHostToDevice));
     s->peer_sync.p[rank] = s->d_sync;
     for (int b = 0; b < s->batch; b++)

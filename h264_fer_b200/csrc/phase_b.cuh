@@ -1,7 +1,7 @@
 // Phase B — the predictor-dependent part of interEncoding (moestimation.cpp:392-570), a wavefront over
 // macroblocks: every cost uses the median MV predictor of the already decided left / up / up-right / up-left
 // neighbours (mode_pred.cpp:252-371). One CTA (128 threads) per macroblock; CTAs draw tickets in anti-diagonal
-// order (x + 2y), interleaved over the sequences of the batch, and spin on the tagged quadrant words of the
+// order (x + 3y), interleaved over the sequences of the batch, and spin on the tagged quadrant words of the
 // neighbours their predictors read. A ticket's dependencies always hold smaller tickets, so the
 // smallest unfinished ticket can always run: no co-residency assumption, no deadlock.
 // Inside a CTA the three stages of a partition run CONCURRENTLY on different warps (warp 0: stage 1, warp 1: stage 2,

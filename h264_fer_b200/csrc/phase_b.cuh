@@ -18,6 +18,9 @@
 #include "phase_c.cuh"
 
 #define PB_NT 128
+#ifndef PB_MINB
+#define PB_MINB 4            // resident CTAs per SM the register budget is set for (4 -> 128 registers)
+#endif
 #define S1_KEY_CAP 1296     // (2*4+1)^2*16 at WindowSize 64
 #define PB_POOL_PREF 192    // stage-2 candidates per partition staged in shared memory (the rest is read from HBM)
 
@@ -379,7 +382,7 @@ __device__ __noinline__ u64 stage2_slow(const SeqDev &S, const Geo &g, PBShared 
     return mine;
 }
 
-__global__ void __launch_bounds__(PB_NT, 4) k_phase_b(const SeqDev *__restrict__ seqs, int seq0, int nseq, Geo g, fh264_params prm,
+__global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__restrict__ seqs, int seq0, int nseq, Geo g, fh264_params prm,
                                                    uint32_t epoch, const int *__restrict__ wf_order, uint32_t *__restrict__ ticket)
 {
     __shared__ PBShared sh;

@@ -465,11 +465,20 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
         // too many gated survivors for this launch's buffers: the fallback launch takes the partition over; when that cannot
         // hold it either (or its list is full) phase B enumerates the set itself. j_stop is final here (the counts saw every entry).
         const int jsb = bound_from_bins();
+        // candidates up to j_stop (bucket s0 twice): more than a pool slice holds -> no point in the fallback launch either
+        uint32_t upto = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            uint32_t c = w->bins[lane * 12 + 2 * i] + w->bins[lane * 12 + 2 * i + 1];
+            if (lane == 0 && i == 0) c *= 2;
+            if (lane * 6 + i <= jsb) upto += c;
+        }
+        const bool fits = __reduce_add_sync(0xffffffffu, upto) <= 1023u;
         if (lane == 0) {
             PartA *pa = &S.parta[part];
             pa->s2_off = 0;
             bool listed = false;
-            if (!REDO) { const uint32_t k = atomicAdd(&S.status[ST_S2REDO], 1u); if (k < S2_REDO_MAX) { S.s2redo[k] = (uint32_t)part; listed = true; } }
+            if (!REDO && fits) { const uint32_t k = atomicAdd(&S.status[ST_S2REDO], 1u); if (k < S2_REDO_MAX) { S.s2redo[k] = (uint32_t)part; listed = true; } }
             pa->n2 = listed ? 0u : (S2_SLOW | (uint32_t)jsb);
         }
         return;

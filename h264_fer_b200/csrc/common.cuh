@@ -117,6 +117,10 @@ __device__ __forceinline__ uint2 load_row8(const uint8_t *plane, int W, int H, i
 __device__ __forceinline__ int sad8(uint2 a, uint2 b) { return __vsadu4(a.x, b.x) + __vsadu4(a.y, b.y); }
 __device__ __forceinline__ int sad_row8(uint2 cur, const uint8_t *plane, int W, int H, int x0, int y) { return sad8(cur, load_row8(plane, W, H, x0, y)); }
 
+// Exact n / d by one IMAD.HI for n * d < 2^32: magic = 2^32 / d + 1; d == 1 has no 32-bit magic and is marked by 0.
+__host__ __device__ __forceinline__ uint32_t udiv_magic(uint32_t d) { return d > 1u ? 0xffffffffu / d + 1u : 0u; }
+__device__ __forceinline__ int udiv_by(int n, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)n, magic) : n; }
+
 // n / d for 0 <= n < 65536 / d with inv = 65536 / d + 1 (window geometry: d <= 129)
 __device__ __forceinline__ int fdiv_(int n, int inv) { return (int)(((unsigned)n * (unsigned)inv) >> 16); }
 

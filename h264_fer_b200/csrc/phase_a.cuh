@@ -54,7 +54,7 @@ __device__ __forceinline__ void s3_decode(int i, int n3a, int w3, int g3, uint32
 {
     const bool a = i < n3a;
     const int t = a ? i : (i - n3a) >> 4, w = a ? w3 : w1, gg = a ? g3 : g1;
-    const int c = (int)__umulhi((uint32_t)t, a ? i3 : i1);
+    const int c = udiv_by(t, a ? i3 : i1);
     dx = c - gg; dy = t - c * w - gg; f = a ? 0 : (i - n3a) & 15;
 }
 
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
     const int g3 = prm.window / 2, g1 = prm.window / 16;
     const int w3 = 2 * g3 + 1, w1 = 2 * g1 + 1;
     const int n3a = w3 * w3, n3b = w1 * w1 * 16, N = n3a + n3b;
-    const uint32_t i3 = 0xffffffffu / (uint32_t)w3 + 1u, i1 = 0xffffffffu / (uint32_t)w1 + 1u;
+    const uint32_t i3 = udiv_magic((uint32_t)w3), i1 = udiv_magic((uint32_t)w1);
     const uint4 *__restrict__ K0p = S.kar;
     uint32_t m1 = COST_INVALID, m2 = COST_INVALID;     // this lane's two smallest costs so far (selection bound)
     // first call: MEstimation(g = window/2, frac 0); arrival index = (dx + g3) * w3 + (dy + g3).
@@ -218,13 +218,13 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
         const int npos = w1 * w1, R = 8 + w1 - 1, ps = R * w1, pb = w1 <= 5 ? 4 : 1;
         uint32_t *X = (uint32_t *)sw->ws.skey;
         uint16_t *RC = sw->ws.sidx;
-        const uint32_t iR = 0xffffffffu / (uint32_t)R + 1u, iN = 0xffffffffu / (uint32_t)npos + 1u;
+        const uint32_t iR = udiv_magic((uint32_t)R), iN = udiv_magic((uint32_t)npos);
         for (int f0 = 0; f0 < 16; f0 += pb) {
             // step A: two rows per lane in flight
             for (int sg0 = 0; sg0 < pb * R; sg0 += 64) {
                 uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;
                 const int sa = sg0 + lane, sb = sg0 + 32 + lane;
-                const int fa = (int)__umulhi((uint32_t)sa, iR), ra = sa - fa * R, fb = (int)__umulhi((uint32_t)sb, iR), rb = sb - fb * R;
+                const int fa = udiv_by(sa, iR), ra = sa - fa * R, fb = udiv_by(sb, iR), rb = sb - fb * R;
                 if (sa < pb * R) wa = qf_load16(S.planes + (size_t)(f0 + fa) * g.WH, W, H, xP - g1, yP - g1 + ra);
                 if (sb < pb * R) wb = qf_load16(S.planes + (size_t)(f0 + fb) * g.WH, W, H, xP - g1, yP - g1 + rb);
                 if (sa < pb * R) qf_row_sums(wa, w1, X + fa * ps + ra * w1, RC + fa * ps + ra * w1);
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
             const int rot = (f0 * 13) % (pb * npos);
             for (int o0 = lane; o0 < pb * npos; o0 += 32) {
                 const int o = o0 + rot < pb * npos ? o0 + rot : o0 + rot - pb * npos;
-                const int fl = (int)__umulhi((uint32_t)o, iN), pos = o - fl * npos, cx = (int)__umulhi((uint32_t)pos, i1), cy = pos - cx * w1;
+                const int fl = udiv_by(o, iN), pos = o - fl * npos, cx = udiv_by(pos, i1), cy = pos - cx * w1;
                 const int rx = xP + cx - g1, ry = yP + cy - g1;
                 uint32_t cst = COST_INVALID;
                 if (rx >= 0 && rx < W && ry >= 0 && ry < H)

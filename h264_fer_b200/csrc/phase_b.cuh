@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
     // qfeat.cuh geometry: window rows, plane stride, planes per warp and batch. Each WARP produces and consumes its own planes
     // (warp w: planes f0 + w*qpw ..), so the row sums and the records only need warp barriers.
     const int qR = 8 + w1 - 1, qps = (qR * w1) | 1, qpw = w1 <= 5 ? 4 : 1, qseg = qpw * qR;
-    const uint32_t iR = 0xffffffffu / (uint32_t)qR + 1u, iNp = 0xffffffffu / (uint32_t)npos + 1u;
+    const uint32_t iR = udiv_magic((uint32_t)qR), iNp = udiv_magic((uint32_t)npos);
     uint32_t *qx = sh.qx + warp * (qpw * qps);
     uint16_t *qrc = sh.qrc + warp * (qpw * qps);
     int callno = 0;                  // alternates BlockSel's survivor counters (uniform across the block)
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
         // interpolated planes (qfeat.cuh): issue the pixel-row loads now (thread -> (plane, window row)), consume them later.
         const int x0 = xP + genx - g1, y0 = yP + geny - g1;
         const int sa = lane, sb = lane + 32;                  // this lane's (plane, row) segments among the warp's qseg (<= 64)
-        const int fa = (int)__umulhi((uint32_t)sa, iR), ra = sa - fa * qR, fb = (int)__umulhi((uint32_t)sb, iR), rb = sb - fb * qR;
+        const int fa = udiv_by(sa, iR), ra = sa - fa * qR, fb = udiv_by(sb, iR), rb = sb - fb * qR;
         uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;
         if (sa < qseg) wa = qf_load16(S.planes + (size_t)(warp * qpw + fa) * g.WH, W, H, x0, y0 + ra);
         if (sb < qseg) wb = qf_load16(S.planes + (size_t)(warp * qpw + fb) * g.WH, W, H, x0, y0 + rb);
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
                 if (sb < qseg) qf_row_sums(wb, w1, qx + fb * qps + rb * w1, qrc + fb * qps + rb * w1);
                 __syncwarp();
                 for (int o = lane; o < qpw * npos; o += 32) {
-                    const int fl = (int)__umulhi((uint32_t)o, iNp), pos = o - fl * npos, cx = fdiv_(pos, inv1), cy = pos - cx * w1, ox = cx - g1, oy = cy - g1;
+                    const int fl = udiv_by(o, iNp), pos = o - fl * npos, cx = fdiv_(pos, inv1), cy = pos - cx * w1, ox = cx - g1, oy = cy - g1;
                     const int rx = xP + genx + ox, ry = yP + geny + oy, i = pos * 16 + fw + fl;
                     uint32_t key = COST_INVALID;
                     if (rx >= 0 && rx < W && ry >= 0 && ry < H)

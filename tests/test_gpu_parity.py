@@ -351,3 +351,49 @@ def test_flat_content_takes_the_slow_stage2_path_and_stays_exact(contrast, noise
     assert np.array_equal(got, want_rec), "records differ: MBs %s" % np.nonzero((got != want_rec).any(1))[0][:10]
     for a, b in zip(recon, want_recon):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("window", [0, 2, 8, 24, 48, 64])
+def test_other_window_sizes_against_oracle(window):
+    """WindowSize 8 / 24 / 48 / 64: window/16 = 0, 1, 3, 4 -> 1x1, 3x3, 7x7, 9x9 quarter-pel windows (the batched variants of the
+    on-the-fly feature computation, stage-1 key sets up to 1296) and window/2 = 4 .. 32 integer search ranges."""
+    from oracle import port
+    w, h, qp, maxdiff = 176, 144, 27, 3
+    clip = synth.SynthClip(w, h, 31 + window)
+    ref, cur = clip.frame(0), clip.frame(1)
+    o = port.Oracle(w, h)
+    assert not o.phase_r(ref[0])
+    want_rec, want_recon = o.encode_p(cur, ref, qp, window, maxdiff)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, *ref)
+        s.upload_source(0, *cur)
+        got = fh.records_to_ints(s.encode_p(qp, window, maxdiff)[0])
+        recon = s.download_recon(0)
+    assert np.array_equal(got, want_rec), "window %d: records differ at MBs %s" % (window, np.nonzero((got != want_rec).any(1))[0][:10])
+    for a, b in zip(recon, want_recon):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("w,h", [(16, 16), (48, 16), (16, 64), (32, 32)])
+def test_tiny_pictures_against_oracle(w, h):
+    """One macroblock, one macroblock row, one macroblock column: every neighbour-availability corner of the wavefront, search
+    windows and the 64x64 index tiles larger than the picture."""
+    from oracle import port
+    qp, window, maxdiff = 30, 32, 3
+    clip = synth.SynthClip(w, h, 50 + w + h, square=False)
+    for t in (1, 2):
+        ref, cur = clip.frame(t - 1), clip.frame(t)
+        o = port.Oracle(w, h)
+        if o.phase_r(ref[0]):
+            continue
+        want_rec, want_recon = o.encode_p(cur, ref, qp, window, maxdiff)
+        with fh.Session(w, h) as s:
+            s.upload_recon(0, *ref)
+            s.upload_source(0, *cur)
+            got = fh.records_to_ints(s.encode_p(qp, window, maxdiff)[0])
+            recon = s.download_recon(0)
+            bits = s.cavlc_p()[0][1]
+        assert np.array_equal(got, want_rec), "%dx%d picture %d: records differ" % (w, h, t)
+        for a, b in zip(recon, want_recon):
+            assert np.array_equal(a, b)
+        assert bits > 0

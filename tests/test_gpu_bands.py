@@ -43,8 +43,10 @@ def _worker(rank, world, port, w, h, seed, npics, qp, window, maxdiff, q):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="band mode needs at least 2 GPUs")
-@pytest.mark.parametrize("world,w,h,window,maxdiff", [(2, 352, 288, 32, 3), (2, 640, 480, 32, -1)])
+@pytest.mark.parametrize("world,w,h,window,maxdiff", [(2, 352, 288, 32, 3), (2, 640, 480, 32, -1), (4, 352, 288, 32, 3), (8, 640, 480, 32, 3)])
 def test_band_mode_matches_oracle(world, w, h, window, maxdiff):
+    if world > 2 and _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     from h264_fer_b200 import synth
     from oracle import port

@@ -1,14 +1,13 @@
 // Phase B — the predictor-dependent part of interEncoding (moestimation.cpp:392-570), a wavefront over
 // macroblocks: every cost uses the median MV predictor of the already decided left / up / up-right / up-left
-// neighbours (mode_pred.cpp:252-371). One CTA (128 threads) per macroblock; CTAs draw tickets in anti-diagonal
-// order (x + 3y), interleaved over the sequences of the batch, and spin on the tagged quadrant words of the
-// neighbours their predictors read. A ticket's dependencies always hold smaller tickets, so the
-// smallest unfinished ticket can always run: no co-residency assumption, no deadlock.
-// Inside a CTA the three stages of a partition run CONCURRENTLY on different warps (warp 0: stage 1, warp 1: stage 2,
-// warp 2: stage 3) with warp-synchronous selection; one block barrier per partition joins their minima.
-// Per MB: P_Skip test (mode_pred.cpp:383-401, moestimation.cpp:402-425), then per 8x8 partition: predictor,
-// stage 1 (window/16 quarter-pel window around the predictor, 17 best by feature cost -> SAD), ranking of the
-// phase-A stage-2 set with the now known multiplier (33 best -> SAD looked up), the phase-A stage-3 list;
+// neighbours (mode_pred.cpp:252-371). One CTA (128 threads) per macroblock; persistent CTAs draw tickets in anti-diagonal
+// order (x + 3y), interleaved over the sequences of the batch, and poll the tagged quadrant words of exactly the
+// neighbours their predictors read. A ticket's dependencies always hold smaller tickets, so the smallest unfinished
+// ticket can always run: no co-residency assumption, no deadlock; every wait is bounded.
+// Per MB: P_Skip test (mode_pred.cpp:383-401, moestimation.cpp:402-425), then per 8x8 partition, by the whole block:
+// predictor; stage 1 (window/16 quarter-pel window around the predictor, features computed from the planes, 17 best by
+// feature cost -> SAD); the phase-A stage-2 set ranked with the now known multiplier (lazily: the best candidate is verified
+// to be among the 33 smallest keys; oversized sets are enumerated here, stage2_slow); the phase-A stage-3 list;
 // winner = first strict minimum of SAD + |mv - mvp|_1 in list order; then merge and final mvd (:529-564).
 #pragma once
 #include "common.cuh"

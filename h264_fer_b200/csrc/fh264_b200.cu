@@ -505,6 +505,32 @@ extern "C" int fh264_encode_p(fh264_session *s, int seq0, int nseq, const fh264_
     return FH264_OK;
 }
 
+// Decoder inverse path: reconstructs the P picture described by `records` (quadrant MVs, mb_type,
+// levels — what the reference's decoder holds per macroblock after entropy decoding, rbsp_decoding.cpp:98-109,330-346) from the
+// current reference picture, then makes it the reference (dpb swap + phase R) exactly as fh264_encode_p does.
+extern "C" int fh264_decode_p(fh264_session *s, int seq0, int nseq, int qp, const fh264_mb_result *records)
+{
+    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
+    if (!records) return fail(FH264_E_ARG, "null records");
+    if (qp < 0 || qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
+    if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "decode_p is not available in band mode");
+    for (int b = seq0; b < seq0 + nseq; b++)
+        if (!s->has_ref[b]) return fail(FH264_E_STATE, "decode_p before any reference picture (upload_recon first)");
+    CK(cudaSetDevice(s->device));
+    const Geo &g = s->g;
+    cudaStream_t st = s->stream;
+    if (s->copy_pending) { CK(cudaStreamWaitEvent(st, s->ev_copy_done, 0)); s->copy_pending = false; }
+    CK(cudaMemcpyAsync(s->h[seq0].results, records, sizeof(fh264_mb_result) * (size_t)g.nmb * nseq, cudaMemcpyHostToDevice, st));
+    k_decode_p<<<dim3((g.nmb + 3) / 4, nseq), 128, 0, st>>>(s->d_seqs, seq0, g, qp);
+    CKL();
+    k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
+    for (int b = seq0; b < seq0 + nseq; b++)
+        for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
+    rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
+    CK(sync_streams(s));
+    return FH264_OK;
+}
+
 extern "C" int fh264_picture_status(fh264_session *s, int seq)
 {
     int rc = check_seq(s, seq, 1); if (rc) return rc;

@@ -284,6 +284,85 @@ __global__ void __launch_bounds__(128) k_phase_c(const SeqDev *__restrict__ seqs
 }
 
 // Stand-alone fused TQ over n macroblocks given source and prediction (unit tests; I-picture helper).
+// ---- decoder side: the inverse half of the same per-lane body --------------------------------
+// Levels come from the record instead of the forward transform: inverse zigzag, chroma-DC inverse Hadamard + scaling
+// (scaleTransform.cpp:247-262,408-420), dequantisation, inverse 4x4, Clip1(pred + r) — what rbsp_decoding.cpp:330-346 does per
+// macroblock through transformDecoding4x4LumaResidual / transformDecodingChroma (inttransform.cpp:133-154,237-321).
+__device__ __forceinline__ void dec_lane(int lane, int qp, const int pred[16], const fh264_mb_result *rec, int recon[16])
+{
+    const bool luma = lane < 16, chroma = lane >= 16 && lane < 24;
+    const int qpc = c_QPC[clampi_(qp, 0, 51)];
+    const int q = luma ? qp : qpc;
+    int c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = 0;
+    if (luma) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) c[c_ZZ[k]] = rec->luma[lane][k];
+    } else if (chroma) {
+        const int blk = (lane - 16) & 3, comp = (lane - 16) >> 2;
+        const int per = qpc / 6, rem = qpc - per * 6;
+#pragma unroll
+        for (int k = 1; k < 16; k++) c[c_ZZ[k]] = rec->chroma_ac[comp][blk][k - 1];
+        const int l0 = rec->chroma_dc[comp][0], l1 = rec->chroma_dc[comp][1], l2 = rec->chroma_dc[comp][2], l3 = rec->chroma_dc[comp][3];
+        const int gm = blk == 0 ? l0 + l1 + l2 + l3 : (blk == 1 ? l0 - l1 + l2 - l3 : (blk == 2 ? l0 + l1 - l2 - l3 : l0 - l1 - l2 + l3));
+        c[0] = ((gm * c_LS[rem][0]) * (1 << per)) >> 5;
+    }
+    int x[16], rr[16];
+    dequant4x4_(c, x, q, !luma);
+    inverse4x4_(x, rr);
+#pragma unroll
+    for (int i = 0; i < 16; i++) recon[i] = clip255_(pred[i] + rr[i]);
+}
+
+// One warp per macroblock: motion compensation from the record's quadrant MVs (Decode, mocomp.cpp:200-208) + dec_lane;
+// the reconstruction goes into S.rec like the encoder's (P_Skip: reconstruction = prediction, inttransform.cpp:215-229).
+__global__ void __launch_bounds__(128) k_decode_p(const SeqDev *__restrict__ seqs, int seq0, Geo g, int qp)
+{
+    const SeqDev &S = seqs[seq0 + blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * 4 + warp;
+    if (mb >= g.nmb) return;
+    const fh264_mb_result *rec = &S.results[mb];
+    const int mbx = mb % g.Wmb, mby = mb / g.Wmb;
+    const bool skip = rec->mb_type == FH264_P_SKIP;
+    const bool luma = lane < 16, chroma = lane >= 16 && lane < 24;
+    int pred[16], recon[16];
+    int comp = 0, bx = 0, by = 0;
+    const int CW = g.W >> 1;
+#pragma unroll
+    for (int i = 0; i < 16; i++) pred[i] = 0;
+    if (luma) {
+        bx = blkx_(lane); by = blky_(lane);
+        const int qd = (by >> 3) * 2 + (bx >> 3);
+        const int mvx = rec->mv[qd][0], mvy = rec->mv[qd][1];
+        luma_pred_block<4, 4>(S, g, mbx * 16 + bx + (mvx >> 2), mby * 16 + by + (mvy >> 2), mvx & 3, mvy & 3, pred);
+    } else if (chroma) {
+        comp = (lane - 16) >> 2;
+        const int blk = (lane - 16) & 3;
+        bx = (blk & 1) * 4; by = (blk >> 1) * 4;
+        const int mvx = rec->mv[blk][0], mvy = rec->mv[blk][1];
+        ImgRef R = { S.ref[1 + comp], CW, g.H >> 1 };
+        const int X = mbx * 8 + bx + (mvx >> 3), Y = mby * 8 + by + (mvy >> 3);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) pred[r * 4 + c] = chroma_frac_(R, X + c, Y + r, mvx & 7, mvy & 7);
+    }
+    if (skip) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) recon[i] = pred[i];
+    } else dec_lane(lane, qp, pred, rec, recon);
+    if (luma || chroma) {
+        const int pitch = luma ? g.W : CW;
+        const size_t off = luma ? (size_t)(mby * 16 + by) * g.W + mbx * 16 + bx : (size_t)(mby * 8 + by) * CW + mbx * 8 + bx;
+        uint8_t *dp = S.rec[luma ? 0 : 1 + comp] + off;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            *(uint32_t *)(dp + (size_t)r * pitch) = (uint32_t)recon[r * 4] | ((uint32_t)recon[r * 4 + 1] << 8) | ((uint32_t)recon[r * 4 + 2] << 16) | ((uint32_t)recon[r * 4 + 3] << 24);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_tq_only(const uint8_t *__restrict__ src384, const uint8_t *__restrict__ pred384, int n, int qp,
                                                  int16_t *__restrict__ levels384, uint8_t *__restrict__ recon384)
 {

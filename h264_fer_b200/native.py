@@ -25,7 +25,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_frame", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
-           "fh264_debug_feature", "fh264_cavlc_p", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
+           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
 
 
 class Fh264Error(RuntimeError):
@@ -83,6 +83,7 @@ def load_library():
     L.fh264_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.fh264_debug_timeline.argtypes = [vp, i32, vp]
     L.fh264_cavlc_p.argtypes = [vp, i32, i32, i32, vp, C.c_size_t, vp, vp]
+    L.fh264_decode_p.argtypes = [vp, i32, i32, i32, vp]
     L.fh264_debug_status.argtypes = [vp, i32, vp]
     L.fh264_band_config.argtypes = [vp, i32, i32, i32, i32]
     L.fh264_ipc_export.argtypes = [vp, i32, vp]
@@ -257,6 +258,12 @@ class Session:
         out = np.zeros((self.nmb, 384), np.uint8)
         self._ck(self.L.fh264_motion_compensate(self.handle, seq, _ptr(qmv), _ptr(out)))
         return out
+
+    def decode_p(self, records, qp, seq0=0):
+        """Decoder inverse path: reconstruct the P picture(s) described by records [nseq, nmb] (MB_RESULT_DTYPE) from the current
+        reference picture; the result becomes the reference picture (read it with download_recon)."""
+        r = np.ascontiguousarray(records, dtype=MB_RESULT_DTYPE).reshape(-1, self.nmb)
+        self._ck(self.L.fh264_decode_p(self.handle, seq0, r.shape[0], qp, _ptr(r)))
 
     def cavlc_p(self, first_bit=0, seq0=0, nseq=None, capacity=500064, mb_info=False):
         """Device CAVLC of the P picture(s) last coded by encode_p: list of (bytes, nbits) per sequence; slice data occupies bits

@@ -186,6 +186,14 @@ typedef struct fh264_cavlc_mb_info {   /* per macroblock, 32 bytes: what the ref
 int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits,
                   fh264_cavlc_mb_info *mb_info);
 
+/* ---- decoder inverse path ------------------------------------------------------------------------
+ * Reconstructs the P picture described by `records` ([nseq][MBs]: mb_type, quadrant MVs and levels, i.e. what RBSP_decode holds
+ * per macroblock after entropy decoding, rbsp_decoding.cpp:98-109,330-346) from the current reference picture with the same
+ * motion-compensation and inverse-transform code the encoder reconstructs with (Decode, mocomp.cpp:200-208;
+ * transformDecoding4x4LumaResidual / transformDecodingChroma / transformDecodingP_Skip, inttransform.cpp:133-321), then makes
+ * it the reference picture like fh264_encode_p does. Read it back with fh264_download_recon. Synchronous. */
+int fh264_decode_p(fh264_session *s, int seq0, int nseq, int qp, const fh264_mb_result *records);
+
 /* ---- band mode: one picture split into macroblock-row bands over the GPUs of a node (BASELINE config 4) --------------
  * One process and one session per GPU, every rank encodes the same pictures in the same order. Each rank keeps the whole
  * reference picture (upload_source / upload_recon take full pictures on every rank) and codes MB rows [mb_row0, mb_row1);

@@ -48,6 +48,22 @@ class Golden:
         out = [self.z[k] for k in self.z.files if k.startswith("i16_")]
         return np.concatenate(out) if out else np.zeros((0, 1024), np.int16)
 
+    def records(self, n):
+        """P picture n as fh264_mb_result records (the layout the device CAVLC and the decoder path read)."""
+        from h264_fer_b200 import native as fh
+        r = self.mbrec(n)
+        out = np.zeros(len(r), fh.MB_RESULT_DTYPE)
+        out["mb_type"] = r[:, 0]
+        nparts = {0: 1, 1: 2, 2: 2, 4: 4, 31: 0}
+        out["num_parts"] = [nparts[int(t)] for t in r[:, 0]]
+        out["mv"] = r[:, 1:9].reshape(-1, 4, 2)
+        out["mvd"] = r[:, 9:17].reshape(-1, 4, 2)
+        out["sad"] = r[:, 17:21]
+        out["luma"] = r[:, 21:277].reshape(-1, 16, 16)
+        out["chroma_dc"] = r[:, 277:285].reshape(-1, 2, 4)
+        out["chroma_ac"] = r[:, 285:405].reshape(-1, 2, 4, 15)
+        return out
+
     def slice_rbsp(self, n):
         """P picture n: (RBSP bytes of the slice NAL, bit position of the first slice_data bit) as written by the reference."""
         return self.z["rbsp_%d" % n], int(self.z["slbit0_%d" % n][0])

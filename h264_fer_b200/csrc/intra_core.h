@@ -1,0 +1,577 @@
+// One macroblock of an I picture: what the reference's I-slice macroblock loop computes before it
+// writes the macroblock (rbsp_encoding.cpp:196-215): intraPredictionEncoding (intra.cpp:949-1109) = Intra16x16 mode search,
+// Intra4x4 mode search on the unreconstructed macroblock, block-by-block Intra4x4 coding, the two coded_mb_size() bit-cost
+// trials (rbsp_encoding.cpp:330-487 with residual_block_cavlc_size, residual.cpp:673-957) and the decision; then
+// quantizationTransform(..., true) (quantizationTransform.cpp:349-485) of the winner with its in-loop reconstruction.
+// The semantics are the CPU (non-OpenCL) ones (intra.cpp:978-1049).
+//
+// The core is plain scalar C++ that compiles for the device (intra.cuh, the product path) and for the host (tests only: the
+// same source is checked against the compiled reference's I pictures without a GPU, tests/intra_host.cpp).
+#pragma once
+#include "../../include/fh264_b200.h"
+#include "cavlc_core.h"
+
+// ---- tables ---------------------------------------------------------------------------------------------------------------
+FH_TAB int16_t ic_LQ[6][3] = { { 205, 158, 128 }, { 186, 146, 114 }, { 158, 128, 102 }, { 146, 114, 89 }, { 128, 102, 82 }, { 114, 89, 71 } };   // LevelQuantize by (row & 1) + (col & 1), quantizationTransform.cpp:24-32
+FH_TAB int16_t ic_LS[6][3] = { { 160, 208, 256 }, { 176, 224, 288 }, { 208, 256, 320 }, { 224, 288, 368 }, { 256, 320, 400 }, { 288, 368, 464 } };   // LevelScale, scaleTransform.cpp:32-40
+FH_TAB uint8_t ic_ZZ[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };           // zigzag: scan position -> row * 4 + col (scaleTransform.cpp:43-47)
+FH_TAB uint8_t ic_QPC[52] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30,
+                              31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39 };                              // inttransform.cpp:8-14
+// coded_block_pattern -> codeNum for Intra macroblocks (Table 9-4, ChromaArrayType 1; h264_globals.cpp:155)
+FH_TAB uint8_t ic_cbp_intra[48] = { 3, 29, 30, 17, 31, 18, 37, 8, 32, 38, 19, 9, 20, 10, 11, 2, 16, 33, 34, 21, 35, 22, 39, 4, 36, 40, 23, 5, 24, 6, 7, 1,
+                                    41, 42, 43, 25, 44, 26, 46, 12, 45, 47, 27, 13, 28, 14, 15, 0 };
+FH_TAB uint8_t ic_chroma_of_16[4] = { 2, 1, 0, 3 };                                          // intraToChromaPredMode, intra.cpp:16
+
+// ---- per-macroblock state the neighbours read (48 bytes): final mb_type, CodedBlockPattern, TotalCoeff of the coded blocks
+//      (0 elsewhere, which is what residual.cpp:473,493 substitute), Intra4x4PredMode ------------------------------------------
+struct IcInfo {
+    uint8_t mb_type, cbp_luma, cbp_chroma, is4x4;
+    uint8_t tc_luma[16];
+    uint8_t tc_chroma[2][4];
+    uint8_t mode4[16];
+    uint8_t pad[4];
+};
+
+struct IcCtx {
+    const uint8_t *src[3];      // `frame` as read from the file
+    uint8_t *rec[3];            // `frame` as left by the macroblocks already coded (reconstruction)
+    int W, H, xP, yP, qp, qpc;
+    uint8_t S[256];             // source luma of this macroblock (originalMB, intra.cpp:1057)
+    uint8_t L[256];             // `frame.L` inside this macroblock: source, overwritten block by block by the Intra4x4 reconstruction
+    uint8_t SC[2][64];          // source chroma
+};
+
+FH_HD int ic_abs(int a) { return a < 0 ? -a : a; }
+FH_HD int ic_clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+FH_HD int ic_blkx(int b) { return ((b & 1) << 2) | ((b & 4) << 1); }      // Intra4x4ScanOrder, h264_globals.cpp:209-214
+FH_HD int ic_blky(int b) { return ((b & 2) << 1) | (b & 8); }
+FH_HD int ic_ue_len(int v) { return 2 * cv_ilog2((uint32_t)v + 1u) + 1; }  // expgolomb_UC_codes[v][0] * 2 + 1 (expgolomb.cpp:8-40)
+
+// `frame.L` at absolute (x, y): inside the current macroblock its working copy, elsewhere the reconstruction
+FH_HD int ic_px(const IcCtx &c, int x, int y)
+{
+    const int lx = x - c.xP, ly = y - c.yP;
+    if ((unsigned)lx < 16u && (unsigned)ly < 16u) return c.L[ly * 16 + lx];
+    return c.rec[0][(size_t)y * c.W + x];
+}
+
+// ---- transform / quantisation (quantizationTransform.cpp:41-100,183-223; scaleTransform.cpp:101-150,308-340) ----------------
+FH_HD void ic_fwd4(int a, int b, int c, int d, int &o0, int &o1, int &o2, int &o3)
+{
+    o0 = ((a + b + c + d) * 256 + 512) >> 10;
+    o1 = (416 * a + 208 * b - 208 * c - 416 * d + 512) >> 10;
+    o2 = ((a - b - c + d) * 256 + 512) >> 10;
+    o3 = (208 * a - 416 * b + 416 * c - 208 * d + 512) >> 10;
+}
+FH_HD void ic_forward4x4(const int r[16], int d[16])
+{
+    int h[16], f[16];
+    for (int i = 0; i < 16; i++) h[i] = r[i] == 0 ? 0 : r[i] * 64 - 32;
+    for (int j = 0; j < 4; j++) ic_fwd4(h[j], h[4 + j], h[8 + j], h[12 + j], f[j], f[4 + j], f[8 + j], f[12 + j]);
+    for (int i = 0; i < 4; i++) ic_fwd4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3], d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+}
+FH_HD void ic_quant4x4(const int d[16], int c[16], int qP, bool keep_dc)
+{
+    const int per = qP / 6, rem = qP % 6;
+    for (int i = 0; i < 16; i++) {
+        const int lq = ic_LQ[rem][((i >> 2) & 1) + (i & 1)];
+        const int t = qP < 24 ? (d[i] * (1 << (4 - per)) - (1 << (3 - per))) * lq : (d[i] >> (per - 4)) * lq;
+        c[i] = (t + 16384) >> 15;
+    }
+    if (keep_dc) c[0] = d[0];
+}
+FH_HD void ic_dequant4x4(const int c[16], int d[16], int qP, bool keep_dc)
+{
+    const int per = qP / 6, rem = qP % 6;
+    for (int i = 0; i < 16; i++) {
+        const int ls = ic_LS[rem][((i >> 2) & 1) + (i & 1)];
+        d[i] = qP >= 24 ? (c[i] * ls) * (1 << (per - 4)) : (c[i] * ls + (1 << (3 - per))) >> (4 - per);
+    }
+    if (keep_dc) d[0] = c[0];
+}
+FH_HD void ic_inverse4x4(const int d[16], int r[16])
+{
+    int f[16], h[16];
+    for (int i = 0; i < 4; i++) {
+        const int *q = d + 4 * i;
+        const int e0 = q[0] + q[2], e1 = q[0] - q[2], e2 = (q[1] >> 1) - q[3], e3 = q[1] + (q[3] >> 1);
+        f[4 * i] = e0 + e3; f[4 * i + 1] = e1 + e2; f[4 * i + 2] = e1 - e2; f[4 * i + 3] = e0 - e3;
+    }
+    for (int j = 0; j < 4; j++) {
+        const int g0 = f[j] + f[8 + j], g1 = f[j] - f[8 + j], g2 = (f[4 + j] >> 1) - f[12 + j], g3 = f[4 + j] + (f[12 + j] >> 1);
+        h[j] = g0 + g3; h[4 + j] = g1 + g2; h[8 + j] = g1 - g2; h[12 + j] = g0 - g3;
+    }
+    for (int i = 0; i < 16; i++) r[i] = (h[i] + 32) >> 6;
+}
+// residual -> quantised coefficients of one 4x4 block (forwardResidual, quantizationTransform.cpp:284-291)
+FH_HD void ic_forward_residual(const int diff[16], int c[16], int qP, bool keep_dc)
+{
+    int d[16];
+    ic_forward4x4(diff, d);
+    ic_quant4x4(d, c, qP, keep_dc);
+}
+// chroma DC: forward + quantisation (quantizationTransform.cpp:157-178,264-282), inverse + scaling (scaleTransform.cpp:247-262,408-420)
+FH_HD void ic_chroma_dc_forward(const int dc[4], int qPc, int lvl[4])
+{
+    const int a = dc[0], b = dc[1], c = dc[2], d = dc[3];
+    const int f[4] = { (a + b + c + d + 2) >> 2, (a - b + c - d + 2) >> 2, (a + b - c - d + 2) >> 2, (a - b - c + d + 2) >> 2 };
+    for (int i = 0; i < 4; i++) lvl[i] = ((((f[i] * 32) >> (qPc / 6)) * ic_LQ[qPc % 6][0]) + 16384) >> 15;
+}
+FH_HD void ic_chroma_dc_inverse(const int lvl[4], int qPc, int dc[4])
+{
+    const int a = lvl[0], b = lvl[1], c = lvl[2], d = lvl[3];
+    const int f[4] = { a + b + c + d, a - b + c - d, a + b - c - d, a - b - c + d };
+    for (int i = 0; i < 4; i++) dc[i] = ((f[i] * ic_LS[qPc % 6][0]) * (1 << (qPc / 6))) >> 5;
+}
+// Intra16x16 luma DC: 4x4 Hadamard + quantisation (quantizationTransform.cpp:105-152,227-260); DC[row][col] -> levels in zigzag order
+FH_HD void ic_luma_dc_forward(const int DC[16], int qp, int cq[16])
+{
+    int t[16], u[16];
+    for (int j = 0; j < 4; j++) {
+        const int g0 = DC[j] + DC[12 + j], g1 = DC[4 + j] + DC[8 + j], g2 = DC[4 + j] - DC[8 + j], g3 = DC[j] - DC[12 + j];
+        t[j] = g0 + g1; t[4 + j] = g3 + g2; t[8 + j] = g0 - g1; t[12 + j] = g3 - g2;
+    }
+    for (int i = 0; i < 4; i++) {
+        const int *q = t + 4 * i;
+        const int d0 = q[0] + q[3], d1 = q[1] + q[2], d2 = q[1] - q[2], d3 = q[0] - q[3];
+        u[4 * i] = (d0 + d1 + 8) >> 4; u[4 * i + 1] = (d3 + d2 + 8) >> 4; u[4 * i + 2] = (d0 - d1 + 8) >> 4; u[4 * i + 3] = (d3 - d2 + 8) >> 4;
+    }
+    const int per = qp / 6, lq = ic_LQ[qp % 6][0];
+    for (int i = 0; i < 16; i++) {
+        const int tt = qp >= 36 ? (u[i] >> (per - 6)) * lq : (u[i] * (1 << (6 - per)) - (1 << (5 - per))) * lq;
+        cq[i] = (tt + 16384) >> 15;
+    }
+}
+// inverse Hadamard + scaling (scaleTransform.cpp:154-189,344-376): quantised DC (row-major) -> DC coefficient of every block (row-major)
+FH_HD void ic_luma_dc_inverse(const int cq[16], int qp, int DC[16])
+{
+    int t[16], u[16];
+    for (int i = 0; i < 4; i++) {
+        const int *q = cq + 4 * i;
+        const int d0 = q[0] + q[2], d1 = q[0] - q[2], d2 = q[1] - q[3], d3 = q[1] + q[3];
+        t[4 * i] = d0 + d3; t[4 * i + 1] = d1 + d2; t[4 * i + 2] = d1 - d2; t[4 * i + 3] = d0 - d3;
+    }
+    for (int j = 0; j < 4; j++) {
+        const int g0 = t[j] + t[8 + j], g1 = t[j] - t[8 + j], g2 = t[4 + j] - t[12 + j], g3 = t[4 + j] + t[12 + j];
+        u[j] = g0 + g3; u[4 + j] = g1 + g2; u[8 + j] = g1 - g2; u[12 + j] = g0 - g3;
+    }
+    const int per = qp / 6, ls = ic_LS[qp % 6][0];
+    for (int i = 0; i < 16; i++) DC[i] = qp >= 36 ? (u[i] * ls) * (1 << (per - 6)) : (u[i] * ls + (1 << (5 - per))) >> (6 - per);
+}
+
+// ---- Intra4x4 prediction (intra.cpp:143-420) ---------------------------------------------------------------------------------
+// p[0] = p[-1,-1], p[1..4] = p[-1,0..3], p[5..12] = p[0..7,-1]; -1 = not available
+FH_HD void ic_fetch4(const IcCtx &c, int blk, int p[13])
+{
+    const int x = c.xP + ic_blkx(blk), y = c.yP + ic_blky(blk);
+    p[0] = (x - 1 < 0 || y - 1 < 0) ? -1 : ic_px(c, x - 1, y - 1);
+    for (int i = 0; i < 4; i++) p[1 + i] = x - 1 < 0 ? -1 : ic_px(c, x - 1, y + i);
+    if (y - 1 < 0) { for (int i = 5; i < 13; i++) p[i] = -1; return; }
+    for (int i = 0; i < 4; i++) p[5 + i] = ic_px(c, x + i, y - 1);
+    // above-right: replaced by the last sample above when it lies outside the picture, in a macroblock coded later
+    // (x0 == 12 below the first block row) or in a block of this macroblock coded later (blocks 3 and 11), intra.cpp:353-375
+    const bool edge = (x + 4 >= c.W) || (ic_blkx(blk) == 12 && ic_blky(blk) > 0) || blk == 3 || blk == 11;
+    for (int i = 0; i < 4; i++) p[9 + i] = edge ? p[8] : ic_px(c, x + 4 + i, y - 1);
+}
+#define IC_T(i) p[(i) + 5]      /* p[i, -1], i = 0 .. 7 */
+#define IC_L(i) p[(i) + 1]      /* p[-1, i], i = 0 .. 3 */
+#define IC_C p[0]               /* p[-1, -1] */
+FH_HD int ic_f3(int a, int b, int c) { return (a + 2 * b + c + 2) >> 2; }
+FH_HD int ic_f2(int a, int b) { return (a + b + 1) >> 1; }
+// p(x, -1) for x = -1 .. 7 and p(-1, y) for y = -1 .. 3 with the corner shared
+FH_HD int ic_top(const int p[13], int x) { return x < 0 ? p[0] : p[x + 5]; }
+FH_HD int ic_left(const int p[13], int y) { return y < 0 ? p[0] : p[y + 1]; }
+FH_HD void ic_pred4(int mode, const int p[13], int o[16])
+{
+    for (int y = 0; y < 4; y++)
+        for (int x = 0; x < 4; x++) {
+            int v;
+            switch (mode) {
+            case 0: v = IC_T(x); break;                                                                         // vertical
+            case 1: v = IC_L(y); break;                                                                         // horizontal
+            case 2:                                                                                            // DC (intra.cpp:168-186: the corner decides "both available")
+                if (IC_C != -1) v = (IC_T(0) + IC_T(1) + IC_T(2) + IC_T(3) + IC_L(0) + IC_L(1) + IC_L(2) + IC_L(3) + 4) >> 3;
+                else if (IC_L(0) != -1) v = (IC_L(0) + IC_L(1) + IC_L(2) + IC_L(3) + 2) >> 2;
+                else if (IC_T(0) != -1) v = (IC_T(0) + IC_T(1) + IC_T(2) + IC_T(3) + 2) >> 2;
+                else v = 128;
+                break;
+            case 3:                                                                                            // diagonal down-left
+                v = (x == 3 && y == 3) ? (IC_T(6) + 3 * IC_T(7) + 2) >> 2 : ic_f3(IC_T(x + y), IC_T(x + y + 1), IC_T(x + y + 2));
+                break;
+            case 4:                                                                                            // diagonal down-right
+                if (x > y) v = ic_f3(ic_top(p, x - y - 2), ic_top(p, x - y - 1), ic_top(p, x - y));
+                else if (x < y) v = ic_f3(ic_left(p, y - x - 2), ic_left(p, y - x - 1), ic_left(p, y - x));
+                else v = ic_f3(IC_T(0), IC_C, IC_L(0));
+                break;
+            case 5: {                                                                                          // vertical-right
+                const int z = 2 * x - y, i = x - (y >> 1);
+                if (z >= 0 && !(z & 1)) v = ic_f2(ic_top(p, i - 1), ic_top(p, i));
+                else if (z >= 0) v = ic_f3(ic_top(p, i - 2), ic_top(p, i - 1), ic_top(p, i));
+                else if (z == -1) v = ic_f3(IC_L(0), IC_C, IC_T(0));
+                else v = ic_f3(ic_left(p, y - 1), ic_left(p, y - 2), ic_left(p, y - 3));
+                break;
+            }
+            case 6: {                                                                                          // horizontal-down
+                const int z = 2 * y - x, i = y - (x >> 1);
+                if (z >= 0 && !(z & 1)) v = ic_f2(ic_left(p, i - 1), ic_left(p, i));
+                else if (z >= 0) v = ic_f3(ic_left(p, i - 2), ic_left(p, i - 1), ic_left(p, i));
+                else if (z == -1) v = ic_f3(IC_L(0), IC_C, IC_T(0));
+                else v = ic_f3(ic_top(p, x - 1), ic_top(p, x - 2), ic_top(p, x - 3));
+                break;
+            }
+            case 7: {                                                                                          // vertical-left
+                const int i = x + (y >> 1);
+                v = (y & 1) ? ic_f3(IC_T(i), IC_T(i + 1), IC_T(i + 2)) : ic_f2(IC_T(i), IC_T(i + 1));
+                break;
+            }
+            default: {                                                                                         // horizontal-up
+                const int z = x + 2 * y, i = y + (x >> 1);
+                if (z > 5) v = IC_L(3);
+                else if (z == 5) v = (IC_L(2) + 3 * IC_L(3) + 2) >> 2;
+                else if (z & 1) v = ic_f3(IC_L(i), IC_L(i + 1), IC_L(i + 2));
+                else v = ic_f2(IC_L(i), IC_L(i + 1));
+                break;
+            }
+            }
+            o[y * 4 + x] = v;
+        }
+}
+// a mode is tried only when the samples it is defined on exist (intra.cpp:1022-1033)
+FH_HD bool ic_mode4_allowed(int mode, const int p[13])
+{
+    switch (mode) {
+    case 0: case 3: case 7: return p[5] != -1;
+    case 1: case 8: return p[1] != -1;
+    case 4: case 5: case 6: return p[0] != -1;
+    default: return true;
+    }
+}
+
+// sum of the absolute QUANTISED transform coefficients of (frame.L - pred) for one 4x4 block (satdLuma4x4, intra.cpp:820-852)
+FH_HD int ic_satd4(const IcCtx &c, int blk, const int pred[16])
+{
+    const int x0 = ic_blkx(blk), y0 = ic_blky(blk);
+    int diff[16], r[16];
+    for (int i = 0; i < 16; i++) diff[i] = (int)c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] - pred[i];
+    ic_forward_residual(diff, r, c.qp, false);
+    int s = 0;
+    for (int i = 0; i < 16; i++) s += ic_abs(r[i]);
+    return s;
+}
+
+// ---- Intra16x16 prediction (intra.cpp:422-560): p[0] corner, p[1..16] left column, p[17..32] row above -----------------------
+FH_HD void ic_fetch16(const IcCtx &c, int p[33])
+{
+    const int xP = c.xP, yP = c.yP;
+    p[0] = (xP > 0 && yP > 0) ? c.rec[0][(size_t)(yP - 1) * c.W + xP - 1] : -1;
+    for (int i = 0; i < 16; i++) p[1 + i] = xP > 0 ? c.rec[0][(size_t)(yP + i) * c.W + xP - 1] : -1;
+    for (int i = 0; i < 16; i++) p[17 + i] = yP > 0 ? c.rec[0][(size_t)(yP - 1) * c.W + xP + i] : -1;
+}
+FH_HD void ic_pred16(int mode, const int p[33], uint8_t o[256])
+{
+    if (mode == 0) { for (int i = 0; i < 256; i++) o[i] = (uint8_t)p[17 + (i & 15)]; return; }
+    if (mode == 1) { for (int i = 0; i < 256; i++) o[i] = (uint8_t)p[1 + (i >> 4)]; return; }
+    if (mode == 2) {
+        int sx = 0, sy = 0;
+        for (int i = 0; i < 16; i++) { sx += p[17 + i]; sy += p[1 + i]; }
+        int v = 128;
+        if (p[0] != -1) v = (sx + sy + 16) >> 5;            // intra.cpp:462-467: the corner decides "both available"
+        else if (p[1] != -1) v = (sy + 8) >> 4;
+        else if (p[17] != -1) v = (sx + 8) >> 4;
+        for (int i = 0; i < 256; i++) o[i] = (uint8_t)v;
+        return;
+    }
+    int Hh = 0, V = 0;
+    for (int i = 0; i <= 7; i++) {
+        Hh += (i + 1) * (p[17 + 8 + i] - (6 - i >= 0 ? p[17 + 6 - i] : p[0]));
+        V += (i + 1) * (p[1 + 8 + i] - (6 - i >= 0 ? p[1 + 6 - i] : p[0]));
+    }
+    const int a = (p[16] + p[32]) << 4, b = (5 * Hh + 32) >> 6, cc = (5 * V + 32) >> 6;
+    for (int y = 0; y < 16; y++)
+        for (int x = 0; x < 16; x++) o[y * 16 + x] = (uint8_t)ic_clip255((a + b * (x - 7) + cc * (y - 7) + 16) >> 5);
+}
+FH_HD bool ic_mode16_allowed(int mode, const int p[33]) { return mode == 0 ? p[17] != -1 : (mode == 1 ? p[1] != -1 : (mode == 3 ? p[0] != -1 : true)); }
+
+// ---- chroma prediction (intra.cpp:562-790): p[0] corner, p[1..8] left column, p[9..16] row above -----------------------------
+FH_HD void ic_pred_chroma(const IcCtx &c, int comp, int mode, uint8_t o[64])
+{
+    const int CW = c.W >> 1, xM = c.xP >> 1, yM = c.yP >> 1;
+    const uint8_t *r = c.rec[1 + comp];
+    int p[17];
+    p[0] = (xM > 0 && yM > 0) ? r[(size_t)(yM - 1) * CW + xM - 1] : -1;
+    for (int i = 0; i < 8; i++) p[1 + i] = xM > 0 ? r[(size_t)(yM + i) * CW + xM - 1] : -1;
+    for (int i = 0; i < 8; i++) p[9 + i] = yM > 0 ? r[(size_t)(yM - 1) * CW + xM + i] : -1;
+    if (mode == 1) { for (int i = 0; i < 64; i++) o[i] = (uint8_t)p[1 + (i >> 3)]; return; }
+    if (mode == 2) { for (int i = 0; i < 64; i++) o[i] = (uint8_t)p[9 + (i & 7)]; return; }
+    if (mode == 0) {
+        for (int b = 0; b < 4; b++) {
+            const int x0 = (b & 1) << 2, y0 = (b >> 1) << 2;
+            int sx = 0, sy = 0;
+            for (int i = 0; i < 4; i++) { sx += p[9 + x0 + i]; sy += p[1 + y0 + i]; }
+            const bool la = p[1 + y0] != -1, ta = p[9 + x0] != -1;
+            int v = 128;
+            if (x0 == y0) { if (la && ta) v = (sx + sy + 4) >> 3; else if (la) v = (sy + 2) >> 2; else if (ta) v = (sx + 2) >> 2; }
+            else if (x0 > 0) { if (ta) v = (sx + 2) >> 2; else if (la) v = (sy + 2) >> 2; }
+            else { if (la) v = (sy + 2) >> 2; else if (ta) v = (sx + 2) >> 2; }
+            for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) o[(y0 + y) * 8 + x0 + x] = (uint8_t)v;
+        }
+        return;
+    }
+    int Hh = 0, V = 0;
+    for (int i = 0; i <= 3; i++) {
+        Hh += (i + 1) * (p[9 + 4 + i] - (2 - i >= 0 ? p[9 + 2 - i] : p[0]));
+        V += (i + 1) * (p[1 + 4 + i] - (2 - i >= 0 ? p[1 + 2 - i] : p[0]));
+    }
+    const int a = (p[8] + p[16]) << 4, b = (34 * Hh + 32) >> 6, cc = (34 * V + 32) >> 6;
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) o[y * 8 + x] = (uint8_t)ic_clip255((a + b * (x - 3) + cc * (y - 3) + 16) >> 5);
+}
+
+// ---- levels of one macroblock -------------------------------------------------------------------------------------------------
+struct IcLevels {
+    int16_t luma[16][16];       // LumaLevel (Intra4x4)
+    int16_t dc16[16];           // Intra16x16DCLevel
+    int16_t ac16[16][15];       // Intra16x16ACLevel
+    int16_t cdc[2][4];
+    int16_t cac[2][4][15];
+};
+
+// Intra16x16 luma of quantizationTransform (quantizationTransform.cpp:381-420); reconstruct = transformDecodingIntra_16x16Luma
+// (inttransform.cpp:157-208) into L
+FH_HD void ic_tq_luma16(IcCtx &c, const uint8_t pred[256], IcLevels &lv, bool reconstruct)
+{
+    int DC[16], cq[16], diff[16], r[16];
+    for (int b = 0; b < 16; b++) {
+        const int x0 = ic_blkx(b), y0 = ic_blky(b);
+        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 16 + x0 + (i & 3); diff[i] = (int)c.L[o] - (int)pred[o]; }
+        ic_forward_residual(diff, r, c.qp, true);
+        DC[(y0 >> 2) * 4 + (x0 >> 2)] = r[0];
+        for (int k = 1; k < 16; k++) lv.ac16[b][k - 1] = (int16_t)r[ic_ZZ[k]];
+    }
+    ic_luma_dc_forward(DC, c.qp, cq);
+    for (int k = 0; k < 16; k++) lv.dc16[k] = (int16_t)cq[ic_ZZ[k]];
+    if (!reconstruct) return;
+    ic_luma_dc_inverse(cq, c.qp, DC);
+    for (int b = 0; b < 16; b++) {
+        const int x0 = ic_blkx(b), y0 = ic_blky(b);
+        int cf[16], d[16], rr[16];
+        cf[0] = DC[(y0 >> 2) * 4 + (x0 >> 2)];
+        for (int k = 1; k < 16; k++) cf[ic_ZZ[k]] = lv.ac16[b][k - 1];
+        ic_dequant4x4(cf, d, c.qp, true);
+        ic_inverse4x4(d, rr);
+        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 16 + x0 + (i & 3); c.L[o] = (uint8_t)ic_clip255((int)pred[o] + rr[i]); }
+    }
+}
+// chroma of quantizationTransform (quantizationTransform.cpp:424-484); reconstruct = transformDecodingChroma (inttransform.cpp:237-321)
+FH_HD void ic_tq_chroma(const IcCtx &c, int comp, const uint8_t pred[64], IcLevels &lv, uint8_t *recon /* 64 or null */)
+{
+    int ac[4][16], dc[4], dl[4], diff[16];
+    for (int b = 0; b < 4; b++) {
+        const int x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
+        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 8 + x0 + (i & 3); diff[i] = (int)c.SC[comp][o] - (int)pred[o]; }
+        ic_forward_residual(diff, ac[b], c.qpc, true);
+        dc[b] = ac[b][0];
+        for (int k = 1; k < 16; k++) lv.cac[comp][b][k - 1] = (int16_t)ac[b][ic_ZZ[k]];
+    }
+    ic_chroma_dc_forward(dc, c.qpc, dl);
+    for (int i = 0; i < 4; i++) lv.cdc[comp][i] = (int16_t)dl[i];
+    if (!recon) return;
+    ic_chroma_dc_inverse(dl, c.qpc, dc);
+    for (int b = 0; b < 4; b++) {
+        const int x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
+        int d[16], rr[16];
+        ac[b][0] = dc[b];
+        ic_dequant4x4(ac[b], d, c.qpc, true);
+        ic_inverse4x4(d, rr);
+        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 8 + x0 + (i & 3); recon[o] = (uint8_t)ic_clip255((int)pred[o] + rr[i]); }
+    }
+}
+
+// setCodedBlockPattern (rbsp_encoding.cpp:21-105)
+FH_HD void ic_cbp(bool is16, const IcLevels &lv, int &cbpl, int &cbpc)
+{
+    cbpl = 0;
+    for (int i8 = 0; i8 < 4; i8++) {
+        int any = 0;
+        for (int i4 = 0; i4 < 4; i4++) any |= is16 ? cv_count(lv.ac16[i8 * 4 + i4], 15) : cv_count(lv.luma[i8 * 4 + i4], 16);
+        if (any) cbpl |= 1 << i8;
+    }
+    if (is16 && cbpl) cbpl = 15;
+    cbpc = 0;
+    for (int i = 0; i < 4; i++) if (lv.cdc[0][i] != 0 || lv.cdc[1][i] != 0) cbpc = 1;
+    for (int i4 = 0; i4 < 4; i4++) if (cv_count(lv.cac[0][i4], 15) || cv_count(lv.cac[1][i4], 15)) cbpc = 2;
+}
+
+// coded_mb_size (rbsp_encoding.cpp:330-487) of an I macroblock. self_skip: mb_type_array[CurrMbAddr] == P_Skip while the
+// trial runs — during the Intra16x16 trial that entry still holds the PREVIOUS picture's type (intra.cpp:1012 clears it only
+// afterwards), and residual.cpp:473,493 then take every neighbour block inside this macroblock as empty.
+// tcl / tcc receive the TotalCoeff of the blocks the trial codes (0 elsewhere).
+FH_HD int ic_mb_bits(bool is16, int mb_type, int chroma_mode, const uint8_t prev_flag[16], const IcLevels &lv, int cbpl, int cbpc, bool self_skip,
+                     const IcInfo *left, const IcInfo *up, uint8_t tcl[16], uint8_t tcc[2][4])
+{
+    CvBits b;
+    cv_init(b, nullptr, 0);                                   // counts only
+    int bad = 0;
+    int bits = ic_ue_len(mb_type);
+    if (!is16) for (int k = 0; k < 16; k++) bits += prev_flag[k] ? 1 : 4;
+    bits += ic_ue_len(chroma_mode);
+    if (!is16) bits += ic_ue_len(ic_cbp_intra[(cbpc << 4) | cbpl]);
+    for (int i = 0; i < 16; i++) tcl[i] = 0;
+    for (int i = 0; i < 8; i++) tcc[i >> 2][i & 3] = 0;
+    if (!(cbpl > 0 || cbpc > 0 || is16)) return bits;
+    bits += 1;                                                // mb_qp_delta
+    if (is16) {
+        const int nA = left ? left->tc_luma[5] : -1, nB = up ? up->tc_luma[10] : -1;
+        cv_block(b, lv.dc16, 16, cv_nc(nA, nB), &bad);
+    }
+    for (int blk = 0; blk < 16; blk++) {
+        if (!(cbpl & (1 << (blk >> 2)))) continue;
+        const int bx = ((blk >> 2) & 1) * 2 + (blk & 1), by = (blk >> 3) * 2 + ((blk >> 1) & 1);
+        int nA, nB;
+        if (bx > 0) { const int a = (by >> 1) * 8 + ((bx - 1) >> 1) * 4 + (by & 1) * 2 + ((bx - 1) & 1); nA = self_skip ? 0 : tcl[a]; }
+        else { const int a = (by >> 1) * 8 + 4 + (by & 1) * 2 + 1; nA = left ? left->tc_luma[a] : -1; }
+        if (by > 0) { const int a = ((by - 1) >> 1) * 8 + (bx >> 1) * 4 + ((by - 1) & 1) * 2 + (bx & 1); nB = self_skip ? 0 : tcl[a]; }
+        else { const int a = 8 + (bx >> 1) * 4 + 2 + (bx & 1); nB = up ? up->tc_luma[a] : -1; }
+        tcl[blk] = (uint8_t)(is16 ? cv_block(b, lv.ac16[blk], 15, cv_nc(nA, nB), &bad) : cv_block(b, lv.luma[blk], 16, cv_nc(nA, nB), &bad));
+    }
+    if (cbpc & 3) for (int c = 0; c < 2; c++) cv_block(b, lv.cdc[c], 4, -1, &bad);
+    if (cbpc & 2)
+        for (int c = 0; c < 2; c++)
+            for (int blk = 0; blk < 4; blk++) {
+                const int bx = blk & 1, by = blk >> 1;
+                const int nA = bx ? (self_skip ? 0 : tcc[c][blk - 1]) : (left ? left->tc_chroma[c][blk + 1] : -1);
+                const int nB = by ? (self_skip ? 0 : tcc[c][blk - 2]) : (up ? up->tc_chroma[c][blk + 2] : -1);
+                tcc[c][blk] = (uint8_t)cv_block(b, lv.cac[c][blk], 15, cv_nc(nA, nB), &bad);
+            }
+    return bits + cv_bits(b);
+}
+
+// predIntra4x4PredMode of block blk (setIntra4x4PredMode, intra.cpp:877-941): min of the neighbours' modes, DC when a
+// neighbour macroblock is missing or not Intra4x4. mine = the modes of this macroblock.
+FH_HD int ic_pred_mode_of(int blk, const uint8_t mine[16], const IcInfo *left, const IcInfo *up)
+{
+    const int bx = ((blk >> 2) & 1) * 2 + (blk & 1), by = (blk >> 3) * 2 + ((blk >> 1) & 1);
+    int mA, mB;
+    if (bx > 0) mA = mine[(by >> 1) * 8 + ((bx - 1) >> 1) * 4 + (by & 1) * 2 + ((bx - 1) & 1)];
+    else { if (!left) return 2; mA = left->is4x4 ? left->mode4[(by >> 1) * 8 + 4 + (by & 1) * 2 + 1] : 2; }
+    if (by > 0) mB = mine[((by - 1) >> 1) * 8 + (bx >> 1) * 4 + ((by - 1) & 1) * 2 + (bx & 1)];
+    else { if (!up) return 2; mB = up->is4x4 ? up->mode4[8 + (bx >> 1) * 4 + 2 + (bx & 1)] : 2; }
+    return mA <= mB ? mA : mB;
+}
+
+// ---- the macroblock ------------------------------------------------------------------------------------------------------------
+// c: picture pointers, W, H, xP, yP, qp set by the caller. prev_skip: this macroblock was P_Skip in the previous picture.
+// left / up: state of the neighbouring macroblocks of THIS picture (null outside the picture); the macroblock above-right must
+// be complete as well (its reconstruction feeds the Intra4x4 above-right samples). Writes the reconstruction into c.rec.
+FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcInfo *up, fh264_mb_result_i &out, IcInfo &info)
+{
+    const int W = c.W, CW = c.W >> 1, xP = c.xP, yP = c.yP;
+    c.qpc = ic_QPC[c.qp < 0 ? 0 : (c.qp > 51 ? 51 : c.qp)];
+    for (int i = 0; i < 256; i++) c.S[i] = c.L[i] = c.src[0][(size_t)(yP + (i >> 4)) * W + xP + (i & 15)];
+    for (int k = 0; k < 2; k++)
+        for (int i = 0; i < 64; i++) c.SC[k][i] = c.src[1 + k][(size_t)((yP >> 1) + (i >> 3)) * CW + (xP >> 1) + (i & 7)];
+
+    // Intra16x16 mode search (intra.cpp:980-1001): smallest sum of absolute quantised coefficients, first mode wins ties
+    int p16[33];
+    uint8_t pred16[256];
+    ic_fetch16(c, p16);
+    int mode16 = 2, min16 = 0x7fffffff;
+    for (int m = 0; m < 4; m++) {
+        if (!ic_mode16_allowed(m, p16)) continue;
+        ic_pred16(m, p16, pred16);
+        int satd = 0;
+        for (int b = 0; b < 16; b++) {
+            const int x0 = ic_blkx(b), y0 = ic_blky(b);
+            int pb[16];
+            for (int i = 0; i < 16; i++) pb[i] = pred16[(y0 + (i >> 2)) * 16 + x0 + (i & 3)];
+            satd += ic_satd4(c, b, pb);
+        }
+        if (satd < min16) { min16 = satd; mode16 = m; }
+    }
+    ic_pred16(mode16, p16, pred16);
+    const int chroma_mode = ic_chroma_of_16[mode16];
+    uint8_t predC[2][64];
+    ic_pred_chroma(c, 0, chroma_mode, predC[0]);
+    ic_pred_chroma(c, 1, chroma_mode, predC[1]);
+
+    // first trial: the macroblock as Intra16x16 (intra.cpp:1008)
+    IcLevels lv;
+    uint8_t tcl16[16], tcc16[2][4], tcl4[16], tcc4[2][4];
+    int cbpl16, cbpl4, cbpc;
+    ic_tq_luma16(c, pred16, lv, false);
+    ic_tq_chroma(c, 0, predC[0], lv, nullptr);
+    ic_tq_chroma(c, 1, predC[1], lv, nullptr);
+    ic_cbp(true, lv, cbpl16, cbpc);
+    const int type16 = mode16 + 1 + (cbpc << 2) + (cbpl16 == 15 ? 12 : 0);
+    const int bits16 = ic_mb_bits(true, type16, chroma_mode, nullptr, lv, cbpl16, cbpc, prev_skip, left, up, tcl16, tcc16);
+
+    // Intra4x4 mode search on the macroblock as it stands: neighbours inside it are still SOURCE samples (intra.cpp:1011-1049)
+    uint8_t mode4[16], flag[16], rem[16];
+    for (int blk = 0; blk < 16; blk++) {
+        int p[13], pb[16], min4 = 0x7fffffff;
+        ic_fetch4(c, blk, p);
+        mode4[blk] = 2;
+        for (int m = 0; m < 9; m++) {
+            if (!ic_mode4_allowed(m, p)) continue;
+            ic_pred4(m, p, pb);
+            const int satd = ic_satd4(c, blk, pb);
+            if (satd < min4) { min4 = satd; mode4[blk] = (uint8_t)m; if (satd == 0) break; }
+        }
+    }
+    // code the blocks one by one with those modes; each reconstruction feeds the next prediction (intra.cpp:1063-1086)
+    for (int blk = 0; blk < 16; blk++) {
+        const int pm = ic_pred_mode_of(blk, mode4, left, up);
+        flag[blk] = mode4[blk] == pm;
+        rem[blk] = (uint8_t)(mode4[blk] < pm ? mode4[blk] : mode4[blk] - 1);
+        int p[13], pb[16], diff[16], r[16], d[16], rr[16];
+        ic_fetch4(c, blk, p);
+        ic_pred4(mode4[blk], p, pb);
+        const int x0 = ic_blkx(blk), y0 = ic_blky(blk);
+        for (int i = 0; i < 16; i++) diff[i] = (int)c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] - pb[i];
+        ic_forward_residual(diff, r, c.qp, false);
+        for (int k = 0; k < 16; k++) lv.luma[blk][k] = (int16_t)r[ic_ZZ[k]];
+        ic_dequant4x4(r, d, c.qp, false);
+        ic_inverse4x4(d, rr);
+        for (int i = 0; i < 16; i++) c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] = (uint8_t)ic_clip255(pb[i] + rr[i]);
+    }
+    // second trial: Intra4x4 (intra.cpp:1088)
+    int cbpc4;
+    ic_cbp(false, lv, cbpl4, cbpc4);
+    const int bits4 = ic_mb_bits(false, 0, chroma_mode, flag, lv, cbpl4, cbpc4, false, left, up, tcl4, tcc4);
+    const bool use4 = bits4 < bits16;
+    if (!use4) {
+        for (int i = 0; i < 256; i++) c.L[i] = c.S[i];          // restore the source, code as Intra16x16 (intra.cpp:1095-1106)
+        ic_tq_luma16(c, pred16, lv, true);
+    }
+    uint8_t recC[2][64];
+    ic_tq_chroma(c, 0, predC[0], lv, recC[0]);
+    ic_tq_chroma(c, 1, predC[1], lv, recC[1]);
+    for (int i = 0; i < 256; i++) c.rec[0][(size_t)(yP + (i >> 4)) * W + xP + (i & 15)] = c.L[i];
+    for (int k = 0; k < 2; k++)
+        for (int i = 0; i < 64; i++) c.rec[1 + k][(size_t)((yP >> 1) + (i >> 3)) * CW + (xP >> 1) + (i & 7)] = recC[k][i];
+
+    out.mb_type = (int16_t)(use4 ? 0 : type16);
+    out.intra16x16_pred_mode = (int8_t)(use4 ? -1 : mode16);
+    out.intra_chroma_pred_mode = (uint8_t)chroma_mode;
+    out.cbp_luma = (uint8_t)(use4 ? cbpl4 : cbpl16);
+    out.cbp_chroma = (uint8_t)cbpc;
+    out.bits_intra16x16 = (uint16_t)bits16;
+    out.bits_intra4x4 = (uint16_t)bits4;
+    for (int i = 0; i < 16; i++) { out.intra4x4_pred_mode[i] = mode4[i]; out.prev_intra4x4_pred_mode_flag[i] = flag[i]; out.rem_intra4x4_pred_mode[i] = rem[i]; }
+    int16_t *ol = &out.luma[0][0];
+    if (use4) for (int i = 0; i < 256; i++) ol[i] = lv.luma[i >> 4][i & 15];
+    else {
+        for (int k = 0; k < 16; k++) ol[k] = lv.dc16[k];
+        for (int b = 0; b < 16; b++) for (int k = 0; k < 15; k++) ol[16 + b * 15 + k] = lv.ac16[b][k];
+    }
+    for (int k = 0; k < 2; k++) {
+        for (int i = 0; i < 4; i++) out.chroma_dc[k][i] = lv.cdc[k][i];
+        for (int b = 0; b < 4; b++) for (int i = 0; i < 15; i++) out.chroma_ac[k][b][i] = lv.cac[k][b][i];
+    }
+    out.reserved[0] = out.reserved[1] = out.reserved[2] = 0;
+
+    info.mb_type = (uint8_t)out.mb_type; info.cbp_luma = out.cbp_luma; info.cbp_chroma = out.cbp_chroma; info.is4x4 = use4;
+    for (int i = 0; i < 16; i++) { info.tc_luma[i] = use4 ? tcl4[i] : tcl16[i]; info.mode4[i] = mode4[i]; }
+    for (int i = 0; i < 8; i++) info.tc_chroma[i >> 2][i & 3] = use4 ? tcc4[i >> 2][i & 3] : tcc16[i >> 2][i & 3];
+    info.pad[0] = info.pad[1] = info.pad[2] = info.pad[3] = 0;
+}

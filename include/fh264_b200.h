@@ -194,6 +194,32 @@ int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *
  * it the reference picture like fh264_encode_p does. Read it back with fh264_download_recon. Synchronous. */
 int fh264_decode_p(fh264_session *s, int seq0, int nseq, int qp, const fh264_mb_result *records);
 
+/* ---- I pictures on the device ---------------------------------------------------------------------
+ * One macroblock of an I picture = what intraPredictionEncoding() (intra.cpp:949-1109, CPU semantics) and the following
+ * quantizationTransform(..., true) (rbsp_encoding.cpp:196-215) leave in the reference's globals. 832 bytes like fh264_mb_result. */
+typedef struct fh264_mb_result_i {
+    int16_t mb_type;                            /* as stored in mb_type_array[]: 0 = I_4x4, 1..24 = I_16x16_<pred>_<cbp chroma>_<cbp luma> */
+    int8_t intra16x16_pred_mode;                /* return value of intraPredictionEncoding(): 0..3, -1 = Intra4x4 chosen */
+    uint8_t intra_chroma_pred_mode;
+    uint8_t cbp_luma, cbp_chroma;               /* CodedBlockPatternLuma / Chroma (setCodedBlockPattern, rbsp_encoding.cpp:21-105) */
+    uint16_t bits_intra16x16, bits_intra4x4;    /* coded_mb_size() of the two trials (intra.cpp:1008,1088); Intra4x4 wins when smaller */
+    uint8_t intra4x4_pred_mode[16];             /* Intra4x4PredMode[(CurrMbAddr << 4) + luma4x4BlkIdx] (the search result, kept either way) */
+    uint8_t prev_intra4x4_pred_mode_flag[16];
+    uint8_t rem_intra4x4_pred_mode[16];         /* meaningful where the flag is 0 */
+    int16_t luma[16][16];                       /* Intra4x4: LumaLevel[blk][k]; Intra16x16: flat [0..15] = Intra16x16DCLevel, [16 + blk*15 + k] = Intra16x16ACLevel[blk][k] */
+    int16_t chroma_dc[2][4];
+    int16_t chroma_ac[2][4][15];
+    int16_t reserved[3];
+} fh264_mb_result_i;
+
+/* Code the current source picture of sequences [seq0, seq0+nseq) as an I picture: for every macroblock the Intra16x16 and
+ * Intra4x4 mode searches, the two CAVLC bit-cost trials, the decision, transform/quantisation and in-loop reconstruction
+ * (intraPredictionEncoding + quantizationTransform, rbsp_encoding.cpp:196-215); then dpb := reconstruction and phase R, as after
+ * fh264_encode_p. The bit-cost trial of a macroblock reads whether the SAME macroblock was P_Skip in the previous picture
+ * (mb_type_array is only cleared after the first trial, intra.cpp:1008-1012); the session remembers that from its last
+ * fh264_encode_p / fh264_decode_p. results: nseq * MBs records (host) or NULL. Synchronous. Not available in band mode. */
+int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh264_mb_result_i *results);
+
 /* ---- band mode: one picture split into macroblock-row bands over the GPUs of a node (BASELINE config 4) --------------
  * One process and one session per GPU, every rank encodes the same pictures in the same order. Each rank keeps the whole
  * reference picture (upload_source / upload_recon take full pictures on every rank) and codes MB rows [mb_row0, mb_row1);

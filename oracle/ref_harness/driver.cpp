@@ -16,6 +16,7 @@
 //                  32 Intra16x16 luma records of I pictures (source, prediction, DC/AC levels, reconstruction)
 //                  64 slice RBSP of P pictures (SLDT: bit position of the first slice_data bit, then the RBSP bytes)
 //                  128 the CAVLC coder tables once (CVTB; fixture for the table check of the device coder)
+//                  256 per-MB records of I pictures (IMBR: final mb_type, prediction modes, both bit-cost trials, CBP, levels)
 // stdout: one JSON line with per-picture types/bytes and timings.
 #include <chrono>
 #include <cstdio>
@@ -43,6 +44,8 @@ void ref_interEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8]);
 void ref_FillInterpolatedRefFrame();
 void ref_quantizationTransform(int predL[16][16], int predCb[8][8], int predCr[8][8], bool reconstruct);
 void ref_transformDecodingP_Skip(int predL[16][16], int predCb[8][8], int predCr[8][8], int QPy);
+int ref_intraPredictionEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8]);
+unsigned int ref_coded_mb_size(int intra16x16PredMode, int predL[16][16], int predCb[8][8], int predCr[8][8]);
 // non-static helpers of moestimation.cpp used by the taps
 int satdLuma8x8MVs(int mvx, int mvy, int luma8x8BlkIdx);
 extern int **refFrameKar[6][16];
@@ -72,6 +75,12 @@ static std::vector<unsigned char> tqio;  // per MB: snapped source 384 + predict
 static unsigned char savedL[256];
 static int slice_data_bit0 = 0;           // writer position when the first macroblock of the slice starts
 static std::vector<short> i16rec;        // per Intra16x16 MB: 256 src, 256 pred, 16 dc, 240 ac, 256 recon (as int16)
+
+// ---- per-MB record of an I picture: mb_type (final), Intra16x16PredMode (-1 = Intra4x4), intra_chroma_pred_mode, bits of the
+//      Intra16x16 trial, bits of the Intra4x4 trial, CBP luma, CBP chroma, Intra4x4PredMode[16], prev_intra4x4_pred_mode_flag[16],
+//      rem_intra4x4_pred_mode[16], 256 luma levels (Intra4x4: LumaLevel[16][16]; Intra16x16: DC[16] then AC[16][15]), cdc[2][4], cac[2][4][15]
+enum { IREC_INTS = 7 + 48 + 256 + 8 + 120 };
+static std::vector<int> imbrec;
 
 #ifndef FH264_NO_TAPS   // the integration build (integration/) supplies these entry points itself
 static int *rec(int mb) { return &mbrec[(size_t)mb * REC_INTS]; }
@@ -113,6 +122,29 @@ void interEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8])
 	}
 }
 
+int intraPredictionEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8])
+{
+	const int m = ref_intraPredictionEncoding(predL, predCr, predCb);
+	if (dumpmask & 256) {
+		int *R = &imbrec[(size_t)CurrMbAddr * IREC_INTS];
+		R[1] = m;
+		R[2] = intra_chroma_pred_mode;
+		for (int b = 0; b < 16; b++) {
+			R[7 + b] = Intra4x4PredMode[(CurrMbAddr << 4) + b];
+			R[23 + b] = prev_intra4x4_pred_mode_flag[b] ? 1 : 0;
+			R[39 + b] = rem_intra4x4_pred_mode[b];
+		}
+	}
+	return m;
+}
+
+unsigned int coded_mb_size(int intra16x16PredMode, int predL[16][16], int predCb[8][8], int predCr[8][8])
+{
+	const unsigned int n = ref_coded_mb_size(intra16x16PredMode, predL, predCb, predCr);
+	if (dumpmask & 256) imbrec[(size_t)CurrMbAddr * IREC_INTS + (intra16x16PredMode == -1 ? 4 : 3)] = (int)n;
+	return n;
+}
+
 static void tap_tq_input(int predL[16][16], int predCb[8][8], int predCr[8][8])
 {
 	if (!(dumpmask & 16)) return;
@@ -148,6 +180,16 @@ void quantizationTransform(int predL[16][16], int predCb[8][8], int predCr[8][8]
 		for (int k = 0; k < 16; k++) o[512 + k] = (short)Intra16x16DCLevel[k];
 		for (int b = 0; b < 16; b++) for (int k = 0; k < 15; k++) o[528 + b * 15 + k] = (short)Intra16x16ACLevel[b][k];
 		for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) o[768 + r * 16 + c] = frame.L[(yp + r) * W + xp + c];
+	}
+	if (!p_pic && reconstruct && (dumpmask & 256)) {
+		int *R = &imbrec[(size_t)CurrMbAddr * IREC_INTS + 55];
+		if (MbPartPredMode(mb_type, 0) == Intra_16x16) {
+			for (int k = 0; k < 16; k++) *R++ = Intra16x16DCLevel[k];
+			for (int b = 0; b < 16; b++) for (int k = 0; k < 15; k++) *R++ = Intra16x16ACLevel[b][k];
+		} else
+			for (int b = 0; b < 16; b++) for (int k = 0; k < 16; k++) *R++ = LumaLevel[b][k];
+		for (int c = 0; c < 2; c++) for (int k = 0; k < 4; k++) *R++ = ChromaDCLevel[c][k];
+		for (int c = 0; c < 2; c++) for (int b = 0; b < 4; b++) for (int k = 0; k < 15; k++) *R++ = ChromaACLevel[c][b][k];
 	}
 	if (p_pic && (dumpmask & 1)) {
 		int *R = rec(CurrMbAddr) + 21;
@@ -248,6 +290,7 @@ int main(int argc, char **argv)
 	}
 	mbrec.assign((size_t)nmb * REC_INTS, 0);
 	tqio.assign((size_t)nmb * 768, 0);
+	imbrec.assign((size_t)nmb * IREC_INTS, 0);
 
 	std::string types, bytes, tpic, tsel, tin, ttq, tfl;
 	double total = 0, total_p = 0, hot_p = 0;
@@ -280,6 +323,13 @@ int main(int argc, char **argv)
 			memcpy(sl.data(), &slice_data_bit0, 4);
 			memcpy(sl.data() + 4, nu.rbsp_byte, nu.NumBytesInRBSP);
 			chunk("SLDT", sl.data(), sl.size());
+		}
+		if (!isP && (dumpmask & 256)) {
+			for (int m = 0; m < nmb; m++) {
+				int *R = &imbrec[(size_t)m * IREC_INTS];
+				R[0] = mb_type_array[m]; R[5] = CodedBlockPatternLumaArray[m]; R[6] = CodedBlockPatternChromaArray[m];
+			}
+			chunk("IMBR", imbrec.data(), imbrec.size() * sizeof(int));
 		}
 		if (!isP && (dumpmask & 32) && !i16rec.empty()) chunk("I16M", i16rec.data(), i16rec.size() * sizeof(short));
 		i16rec.clear();

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ENCODER = os.path.join(HERE, "_ref", "ref_encoder")
 REC_INTS = 405
 
-D_MBREC, D_RECON, D_SOURCE, D_PHASE_R, D_TQIO, D_INTRA16, D_SLICE, D_TABLES = 1, 2, 4, 8, 16, 32, 64, 128
+D_MBREC, D_RECON, D_SOURCE, D_PHASE_R, D_TQIO, D_INTRA16, D_SLICE, D_TABLES, D_IMBREC = 1, 2, 4, 8, 16, 32, 64, 128, 256
+IREC_INTS = 439
 
 
 def have_ref_encoder() -> bool:
@@ -54,6 +55,8 @@ def parse_dump(path):
             p["nal_type"], p["bytes"], p["w"], p["h"], p["counts"], p["qp"] = h[0], h[1], h[2], h[3], list(h[4:9]), h[9]
         elif tag == "MBRC":
             p["mbrec"] = np.frombuffer(payload, dtype=np.int32).reshape(-1, REC_INTS).copy()
+        elif tag == "IMBR":
+            p["imbrec"] = np.frombuffer(payload, dtype=np.int32).reshape(-1, IREC_INTS).copy()
         elif tag == "I16M":
             p["i16"] = np.frombuffer(payload, dtype=np.int16).reshape(-1, 1024).copy()
         elif tag == "TQIO":

@@ -14,6 +14,7 @@
 #include "phase_b.cuh"
 #include "phase_c.cuh"
 #include "cavlc.cuh"
+#include "intra.cuh"
 static_assert(sizeof(CvInfo) == sizeof(fh264_cavlc_mb_info) && sizeof(CvInfo) == 32, "CvInfo is the public fh264_cavlc_mb_info");
 
 static thread_local std::string g_err;
@@ -69,6 +70,13 @@ struct fh264_session {
     std::vector<CvSeq> cvh;
     CvSeq *d_cvs;
     uint32_t *h_cvstat;             // pinned: batch * 2 (flags, total bits)
+    // I pictures (allocated on first use)
+    std::vector<IntraSeq> ih;
+    IntraSeq *d_is;
+    cudaEvent_t ev_i[2];            // around k_intra
+    bool intra_timed;
+    int *d_prev_p;                  // per sequence: the previous picture was a P picture whose records are in `results`
+    std::vector<int> prev_p;
 };
 
 __global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
@@ -149,6 +157,7 @@ extern "C" int fh264_close(fh264_session *s)
     if (s->h_cvstat) cudaFreeHost(s->h_cvstat);
     for (int i = 0; i < 5; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int i = 0; i < 4; i++) if (s->evk[i]) cudaEventDestroy(s->evk[i]);
+    for (int i = 0; i < 2; i++) if (s->ev_i[i]) cudaEventDestroy(s->ev_i[i]);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->up_stream) cudaStreamDestroy(s->up_stream);
@@ -182,6 +191,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->up_stream = nullptr;
     s->copy_stream = nullptr; s->ev_c_done = nullptr; s->ev_copy_done = nullptr; s->copy_pending = false;
     s->d_cvs = nullptr; s->h_cvstat = nullptr;
+    s->d_is = nullptr; s->d_prev_p = nullptr; s->ev_i[0] = s->ev_i[1] = nullptr; s->intra_timed = false;
     s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->d_sadout = nullptr; s->scr_mbs = 0;
     for (int i = 0; i < 5; i++) s->ev[i] = nullptr;
     for (int i = 0; i < 4; i++) s->evk[i] = nullptr;
@@ -193,6 +203,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     g.WH = width * height;
     g.band_mb0 = 0; g.band_nmb = g.nmb; g.rank = 0; g.world = 1;
     s->has_ref.assign(batch, 0);
+    s->prev_p.assign(batch, 0);
     s->h.resize(batch);
 #define OPEN_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(FH264_E_CUDA, #call, e_); fh264_close(s); return FH264_E_CUDA; } } while (0)
     OPEN_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -393,6 +404,7 @@ extern "C" int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, c
     CK(cudaMemcpyAsync(s->h[seq].ref[2], cr, WH / 4, cudaMemcpyHostToDevice, s->stream));
     rc = launch_phase_r(s, seq, 1); if (rc) return rc;
     s->has_ref[seq] = 1;
+    if (!s->prev_p.empty()) s->prev_p[seq] = 0;     // a picture coded elsewhere: no P_Skip entries in mb_type_array
     return FH264_OK;
 }
 
@@ -494,6 +506,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
     CK(cudaEventRecord(s->ev[4], st));
     s->timed = true;
+    if (!s->prev_p.empty()) for (int b = seq0; b < seq0 + nseq; b++) s->prev_p[b] = 1;
     return FH264_OK;
 }
 
@@ -528,6 +541,73 @@ extern "C" int fh264_decode_p(fh264_session *s, int seq0, int nseq, int qp, cons
         for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
     rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
     CK(sync_streams(s));
+    if (!s->prev_p.empty()) for (int b = seq0; b < seq0 + nseq; b++) s->prev_p[b] = 1;
+    return FH264_OK;
+}
+
+extern "C" int fh264_last_intra_ms(fh264_session *s, float *ms)
+{
+    if (!s || !ms) return fail(FH264_E_ARG, "null argument");
+    if (!s->intra_timed) return fail(FH264_E_STATE, "no encode_i yet");
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventSynchronize(s->ev_i[1]));
+    CK(cudaEventElapsedTime(ms, s->ev_i[0], s->ev_i[1]));
+    return FH264_OK;
+}
+
+// I pictures on the device (intra.cuh). See the header.
+static int ensure_intra(fh264_session *s)
+{
+    if (s->d_is) return FH264_OK;
+    const size_t nmb = (size_t)s->g.nmb;
+    s->ih.assign(s->batch, IntraSeq());
+    for (int b = 0; b < s->batch; b++) {
+        CK(dalloc(s, &s->ih[b].info, nmb));
+        CK(dalloc(s, &s->ih[b].done, nmb));
+        CK(cudaMemset(s->ih[b].done, 0, sizeof(uint32_t) * nmb));
+    }
+    CK(dalloc(s, &s->d_prev_p, (size_t)s->batch));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreate(&s->ev_i[i]));
+    CK(dalloc(s, &s->d_is, (size_t)s->batch));
+    CK(cudaMemcpy(s->d_is, s->ih.data(), sizeof(IntraSeq) * s->batch, cudaMemcpyHostToDevice));
+    return FH264_OK;
+}
+
+extern "C" int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh264_mb_result_i *results)
+{
+    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
+    if (qp < 0 || qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
+    if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "encode_i is not available in band mode");
+    CK(cudaSetDevice(s->device));
+    rc = ensure_intra(s); if (rc) return rc;
+    const Geo &g = s->g;
+    cudaStream_t st = s->stream;
+    rc = adopt_uploads(s, seq0, nseq); if (rc) return rc;
+    if (s->copy_pending) { CK(cudaStreamWaitEvent(st, s->ev_copy_done, 0)); s->copy_pending = false; }   // the I records reuse the result buffer
+    s->epoch++;
+    CK(cudaMemcpyAsync(s->d_prev_p + seq0, s->prev_p.data() + seq0, sizeof(int) * nseq, cudaMemcpyHostToDevice, st));
+    k_begin_intra<<<1, 1, 0, st>>>(s->d_ticket + 1);
+    int nl = 32;
+    { const char *e = getenv("FH264_INTRA_LANES"); if (e && atoi(e) == 1) nl = 1; }   // development knob (read per call): everything on lane 0
+    const unsigned ctas = (unsigned)std::min<long long>((long long)g.nmb * nseq, (long long)nseq * (g.Wmb + 16));
+    CK(cudaEventRecord(s->ev_i[0], st));
+    k_intra<<<ctas, 32, 0, st>>>(s->d_seqs, s->d_is, s->d_prev_p, seq0, nseq, g, qp, s->epoch, s->d_wf_order, s->d_ticket + 1, nl);
+    CKL();
+    CK(cudaEventRecord(s->ev_i[1], st));
+    s->intra_timed = true;
+    for (int b = seq0; b < seq0 + nseq; b++) { CK(cudaEventRecord(s->ev_free[(int)s->cur_set[b]][b], st)); s->free_valid[(int)s->cur_set[b]][b] = 1; }
+    for (int b = seq0; b < seq0 + nseq; b++)
+        CK(cudaMemcpyAsync(s->h_status + (size_t)b * ST_WORDS, s->h[b].status, sizeof(uint32_t) * ST_WORDS, cudaMemcpyDeviceToHost, st));
+    if (results) CK(cudaMemcpyAsync(results, s->h[seq0].results, sizeof(fh264_mb_result_i) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, st));
+    // dpb := reconstruction, then phase R for the next picture (rbsp_encoding.cpp:317-322)
+    k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
+    for (int b = seq0; b < seq0 + nseq; b++)
+        for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
+    rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
+    for (int b = seq0; b < seq0 + nseq; b++) { s->has_ref[b] = 1; s->prev_p[b] = 0; }
+    CK(sync_streams(s));
+    for (int b = seq0; b < seq0 + nseq; b++)
+        if (s->h_status[(size_t)b * ST_WORDS + ST_FLAGS] & FLAG_TIMEOUT) return fail(FH264_E_CUDA, "intra wavefront wait timed out");
     return FH264_OK;
 }
 

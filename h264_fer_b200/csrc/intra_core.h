@@ -11,6 +11,18 @@
 #include "../../include/fh264_b200.h"
 #include "cavlc_core.h"
 
+// ---- lanes: on the device the macroblock is worked on by nl = 32 lanes of one warp (the two mode searches are spread over the
+//      lanes, the serial remainder runs on lane 0) or by nl = 1 lane; on the host always by one -------------------------------
+#ifdef __CUDACC__
+FH_HD void ic_sync(int nl) { if (nl > 1) __syncwarp(); }
+FH_HD int ic_red_add(int v, int nl) { return nl > 1 ? __reduce_add_sync(0xffffffffu, v) : v; }
+FH_HD int ic_red_min(int v, int nl) { return nl > 1 ? __reduce_min_sync(0xffffffffu, v) : v; }
+#else
+FH_HD void ic_sync(int) {}
+FH_HD int ic_red_add(int v, int) { return v; }
+FH_HD int ic_red_min(int v, int) { return v; }
+#endif
+
 // ---- tables ---------------------------------------------------------------------------------------------------------------
 FH_TAB int16_t ic_LQ[6][3] = { { 205, 158, 128 }, { 186, 146, 114 }, { 158, 128, 102 }, { 146, 114, 89 }, { 128, 102, 82 }, { 114, 89, 71 } };   // LevelQuantize by (row & 1) + (col & 1), quantizationTransform.cpp:24-32
 FH_TAB int16_t ic_LS[6][3] = { { 160, 208, 256 }, { 176, 224, 288 }, { 208, 256, 320 }, { 224, 288, 368 }, { 256, 320, 400 }, { 288, 368, 464 } };   // LevelScale, scaleTransform.cpp:32-40
@@ -39,6 +51,7 @@ struct IcCtx {
     uint8_t S[256];             // source luma of this macroblock (originalMB, intra.cpp:1057)
     uint8_t L[256];             // `frame.L` inside this macroblock: source, overwritten block by block by the Intra4x4 reconstruction
     uint8_t SC[2][64];          // source chroma
+    uint8_t RC[2][64];          // reconstructed chroma
 };
 
 FH_HD int ic_abs(int a) { return a < 0 ? -a : a; }
@@ -290,6 +303,30 @@ FH_HD void ic_pred16(int mode, const int p[33], uint8_t o[256])
     for (int y = 0; y < 16; y++)
         for (int x = 0; x < 16; x++) o[y * 16 + x] = (uint8_t)ic_clip255((a + b * (x - 7) + cc * (y - 7) + 16) >> 5);
 }
+// the same prediction for the samples of one 4x4 block only
+FH_HD void ic_pred16_block(int mode, const int p[33], int blk, int o[16])
+{
+    const int x0 = ic_blkx(blk), y0 = ic_blky(blk);
+    if (mode == 0) { for (int i = 0; i < 16; i++) o[i] = p[17 + x0 + (i & 3)]; return; }
+    if (mode == 1) { for (int i = 0; i < 16; i++) o[i] = p[1 + y0 + (i >> 2)]; return; }
+    if (mode == 2) {
+        int sx = 0, sy = 0;
+        for (int i = 0; i < 16; i++) { sx += p[17 + i]; sy += p[1 + i]; }
+        int v = 128;
+        if (p[0] != -1) v = (sx + sy + 16) >> 5;
+        else if (p[1] != -1) v = (sy + 8) >> 4;
+        else if (p[17] != -1) v = (sx + 8) >> 4;
+        for (int i = 0; i < 16; i++) o[i] = v;
+        return;
+    }
+    int Hh = 0, V = 0;
+    for (int i = 0; i <= 7; i++) {
+        Hh += (i + 1) * (p[17 + 8 + i] - (6 - i >= 0 ? p[17 + 6 - i] : p[0]));
+        V += (i + 1) * (p[1 + 8 + i] - (6 - i >= 0 ? p[1 + 6 - i] : p[0]));
+    }
+    const int a = (p[16] + p[32]) << 4, b = (5 * Hh + 32) >> 6, cc = (5 * V + 32) >> 6;
+    for (int i = 0; i < 16; i++) o[i] = ic_clip255((a + b * (x0 + (i & 3) - 7) + cc * (y0 + (i >> 2) - 7) + 16) >> 5);
+}
 FH_HD bool ic_mode16_allowed(int mode, const int p[33]) { return mode == 0 ? p[17] != -1 : (mode == 1 ? p[1] != -1 : (mode == 3 ? p[0] != -1 : true)); }
 
 // ---- chroma prediction (intra.cpp:562-790): p[0] corner, p[1..8] left column, p[9..16] row above -----------------------------
@@ -460,118 +497,124 @@ FH_HD int ic_pred_mode_of(int blk, const uint8_t mine[16], const IcInfo *left, c
 }
 
 // ---- the macroblock ------------------------------------------------------------------------------------------------------------
-// c: picture pointers, W, H, xP, yP, qp set by the caller. prev_skip: this macroblock was P_Skip in the previous picture.
-// left / up: state of the neighbouring macroblocks of THIS picture (null outside the picture); the macroblock above-right must
-// be complete as well (its reconstruction feeds the Intra4x4 above-right samples). Writes the reconstruction into c.rec.
-FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcInfo *up, fh264_mb_result_i &out, IcInfo &info)
+// c: picture pointers, W, H, xP, yP, qp set by the caller (shared by the lanes). prev_skip: this macroblock was P_Skip in the
+// previous picture. left / up: state of the neighbouring macroblocks of THIS picture (null outside the picture); the macroblock
+// above-right must be complete as well (its reconstruction feeds the Intra4x4 above-right samples). Writes the reconstruction
+// into c.rec; out and info are written by lane 0. Called by lanes 0 .. nl-1 of a warp (nl = 32), or by one lane with nl = 1.
+FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcInfo *up, fh264_mb_result_i &out, IcInfo &info, int lane, int nl)
 {
     const int W = c.W, CW = c.W >> 1, xP = c.xP, yP = c.yP;
-    c.qpc = ic_QPC[c.qp < 0 ? 0 : (c.qp > 51 ? 51 : c.qp)];
-    for (int i = 0; i < 256; i++) c.S[i] = c.L[i] = c.src[0][(size_t)(yP + (i >> 4)) * W + xP + (i & 15)];
-    for (int k = 0; k < 2; k++)
-        for (int i = 0; i < 64; i++) c.SC[k][i] = c.src[1 + k][(size_t)((yP >> 1) + (i >> 3)) * CW + (xP >> 1) + (i & 7)];
+    if (lane == 0) c.qpc = ic_QPC[c.qp < 0 ? 0 : (c.qp > 51 ? 51 : c.qp)];
+    for (int i = lane; i < 256; i += nl) c.S[i] = c.L[i] = c.src[0][(size_t)(yP + (i >> 4)) * W + xP + (i & 15)];
+    for (int i = lane; i < 128; i += nl) c.SC[i >> 6][i & 63] = c.src[1 + (i >> 6)][(size_t)((yP >> 1) + ((i & 63) >> 3)) * CW + (xP >> 1) + (i & 7)];
+    ic_sync(nl);
 
-    // Intra16x16 mode search (intra.cpp:980-1001): smallest sum of absolute quantised coefficients, first mode wins ties
+    // Intra16x16 mode search (intra.cpp:980-1001): smallest sum of absolute quantised coefficients, first mode wins ties.
+    // 4 modes x 16 blocks spread over the lanes.
     int p16[33];
-    uint8_t pred16[256];
     ic_fetch16(c, p16);
+    int part[4] = { 0, 0, 0, 0 };
+    for (int item = lane; item < 64; item += nl) {
+        const int m = item >> 4, b = item & 15;
+        if (!ic_mode16_allowed(m, p16)) continue;
+        int pb[16];
+        ic_pred16_block(m, p16, b, pb);
+        part[m] += ic_satd4(c, b, pb);
+    }
     int mode16 = 2, min16 = 0x7fffffff;
     for (int m = 0; m < 4; m++) {
-        if (!ic_mode16_allowed(m, p16)) continue;
-        ic_pred16(m, p16, pred16);
-        int satd = 0;
-        for (int b = 0; b < 16; b++) {
-            const int x0 = ic_blkx(b), y0 = ic_blky(b);
-            int pb[16];
-            for (int i = 0; i < 16; i++) pb[i] = pred16[(y0 + (i >> 2)) * 16 + x0 + (i & 3)];
-            satd += ic_satd4(c, b, pb);
-        }
-        if (satd < min16) { min16 = satd; mode16 = m; }
+        const int satd = ic_red_add(part[m], nl);
+        if (ic_mode16_allowed(m, p16) && satd < min16) { min16 = satd; mode16 = m; }
     }
-    ic_pred16(mode16, p16, pred16);
-    const int chroma_mode = ic_chroma_of_16[mode16];
-    uint8_t predC[2][64];
-    ic_pred_chroma(c, 0, chroma_mode, predC[0]);
-    ic_pred_chroma(c, 1, chroma_mode, predC[1]);
-
-    // first trial: the macroblock as Intra16x16 (intra.cpp:1008)
-    IcLevels lv;
-    uint8_t tcl16[16], tcc16[2][4], tcl4[16], tcc4[2][4];
-    int cbpl16, cbpl4, cbpc;
-    ic_tq_luma16(c, pred16, lv, false);
-    ic_tq_chroma(c, 0, predC[0], lv, nullptr);
-    ic_tq_chroma(c, 1, predC[1], lv, nullptr);
-    ic_cbp(true, lv, cbpl16, cbpc);
-    const int type16 = mode16 + 1 + (cbpc << 2) + (cbpl16 == 15 ? 12 : 0);
-    const int bits16 = ic_mb_bits(true, type16, chroma_mode, nullptr, lv, cbpl16, cbpc, prev_skip, left, up, tcl16, tcc16);
-
-    // Intra4x4 mode search on the macroblock as it stands: neighbours inside it are still SOURCE samples (intra.cpp:1011-1049)
-    uint8_t mode4[16], flag[16], rem[16];
-    for (int blk = 0; blk < 16; blk++) {
-        int p[13], pb[16], min4 = 0x7fffffff;
+    // Intra4x4 mode search on the macroblock as it stands: neighbours inside it are still SOURCE samples (intra.cpp:1011-1049).
+    // 16 blocks x 9 modes spread over the lanes; the smallest (cost, mode) pair is the first mode reaching the minimum.
+    int best[16];
+    for (int b = 0; b < 16; b++) best[b] = 0x7fffffff;
+    for (int item = lane; item < 144; item += nl) {
+        const int blk = item & 15, m = item >> 4;
+        int p[13], pb[16];
         ic_fetch4(c, blk, p);
-        mode4[blk] = 2;
-        for (int m = 0; m < 9; m++) {
-            if (!ic_mode4_allowed(m, p)) continue;
-            ic_pred4(m, p, pb);
-            const int satd = ic_satd4(c, blk, pb);
-            if (satd < min4) { min4 = satd; mode4[blk] = (uint8_t)m; if (satd == 0) break; }
+        if (!ic_mode4_allowed(m, p)) continue;
+        ic_pred4(m, p, pb);
+        const int key = (ic_satd4(c, blk, pb) << 4) | m;
+        if (key < best[blk]) best[blk] = key;
+    }
+    for (int b = 0; b < 16; b++) best[b] = ic_red_min(best[b], nl);
+    ic_sync(nl);
+
+    if (lane == 0) {
+        uint8_t pred16[256], predC[2][64];
+        ic_pred16(mode16, p16, pred16);
+        const int chroma_mode = ic_chroma_of_16[mode16];
+        ic_pred_chroma(c, 0, chroma_mode, predC[0]);
+        ic_pred_chroma(c, 1, chroma_mode, predC[1]);
+
+        // first trial: the macroblock as Intra16x16 (intra.cpp:1008)
+        IcLevels lv;
+        uint8_t tcl16[16], tcc16[2][4], tcl4[16], tcc4[2][4];
+        int cbpl16, cbpl4, cbpc, cbpc4;
+        ic_tq_luma16(c, pred16, lv, false);
+        ic_tq_chroma(c, 0, predC[0], lv, nullptr);
+        ic_tq_chroma(c, 1, predC[1], lv, nullptr);
+        ic_cbp(true, lv, cbpl16, cbpc);
+        const int type16 = mode16 + 1 + (cbpc << 2) + (cbpl16 == 15 ? 12 : 0);
+        const int bits16 = ic_mb_bits(true, type16, chroma_mode, nullptr, lv, cbpl16, cbpc, prev_skip, left, up, tcl16, tcc16);
+
+        // code the blocks one by one with the modes found; each reconstruction feeds the next prediction (intra.cpp:1063-1086)
+        uint8_t mode4[16], flag[16], rem[16];
+        for (int blk = 0; blk < 16; blk++) mode4[blk] = (uint8_t)(best[blk] & 15);
+        for (int blk = 0; blk < 16; blk++) {
+            const int pm = ic_pred_mode_of(blk, mode4, left, up);
+            flag[blk] = mode4[blk] == pm;
+            rem[blk] = (uint8_t)(mode4[blk] < pm ? mode4[blk] : mode4[blk] - 1);
+            int p[13], pb[16], diff[16], r[16], d[16], rr[16];
+            ic_fetch4(c, blk, p);
+            ic_pred4(mode4[blk], p, pb);
+            const int x0 = ic_blkx(blk), y0 = ic_blky(blk);
+            for (int i = 0; i < 16; i++) diff[i] = (int)c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] - pb[i];
+            ic_forward_residual(diff, r, c.qp, false);
+            for (int k = 0; k < 16; k++) lv.luma[blk][k] = (int16_t)r[ic_ZZ[k]];
+            ic_dequant4x4(r, d, c.qp, false);
+            ic_inverse4x4(d, rr);
+            for (int i = 0; i < 16; i++) c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] = (uint8_t)ic_clip255(pb[i] + rr[i]);
         }
-    }
-    // code the blocks one by one with those modes; each reconstruction feeds the next prediction (intra.cpp:1063-1086)
-    for (int blk = 0; blk < 16; blk++) {
-        const int pm = ic_pred_mode_of(blk, mode4, left, up);
-        flag[blk] = mode4[blk] == pm;
-        rem[blk] = (uint8_t)(mode4[blk] < pm ? mode4[blk] : mode4[blk] - 1);
-        int p[13], pb[16], diff[16], r[16], d[16], rr[16];
-        ic_fetch4(c, blk, p);
-        ic_pred4(mode4[blk], p, pb);
-        const int x0 = ic_blkx(blk), y0 = ic_blky(blk);
-        for (int i = 0; i < 16; i++) diff[i] = (int)c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] - pb[i];
-        ic_forward_residual(diff, r, c.qp, false);
-        for (int k = 0; k < 16; k++) lv.luma[blk][k] = (int16_t)r[ic_ZZ[k]];
-        ic_dequant4x4(r, d, c.qp, false);
-        ic_inverse4x4(d, rr);
-        for (int i = 0; i < 16; i++) c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] = (uint8_t)ic_clip255(pb[i] + rr[i]);
-    }
-    // second trial: Intra4x4 (intra.cpp:1088)
-    int cbpc4;
-    ic_cbp(false, lv, cbpl4, cbpc4);
-    const int bits4 = ic_mb_bits(false, 0, chroma_mode, flag, lv, cbpl4, cbpc4, false, left, up, tcl4, tcc4);
-    const bool use4 = bits4 < bits16;
-    if (!use4) {
-        for (int i = 0; i < 256; i++) c.L[i] = c.S[i];          // restore the source, code as Intra16x16 (intra.cpp:1095-1106)
-        ic_tq_luma16(c, pred16, lv, true);
-    }
-    uint8_t recC[2][64];
-    ic_tq_chroma(c, 0, predC[0], lv, recC[0]);
-    ic_tq_chroma(c, 1, predC[1], lv, recC[1]);
-    for (int i = 0; i < 256; i++) c.rec[0][(size_t)(yP + (i >> 4)) * W + xP + (i & 15)] = c.L[i];
-    for (int k = 0; k < 2; k++)
-        for (int i = 0; i < 64; i++) c.rec[1 + k][(size_t)((yP >> 1) + (i >> 3)) * CW + (xP >> 1) + (i & 7)] = recC[k][i];
+        // second trial: Intra4x4 (intra.cpp:1088)
+        ic_cbp(false, lv, cbpl4, cbpc4);
+        const int bits4 = ic_mb_bits(false, 0, chroma_mode, flag, lv, cbpl4, cbpc4, false, left, up, tcl4, tcc4);
+        const bool use4 = bits4 < bits16;
+        if (!use4) {
+            for (int i = 0; i < 256; i++) c.L[i] = c.S[i];          // restore the source, code as Intra16x16 (intra.cpp:1095-1106)
+            ic_tq_luma16(c, pred16, lv, true);
+        }
+        ic_tq_chroma(c, 0, predC[0], lv, c.RC[0]);
+        ic_tq_chroma(c, 1, predC[1], lv, c.RC[1]);
 
-    out.mb_type = (int16_t)(use4 ? 0 : type16);
-    out.intra16x16_pred_mode = (int8_t)(use4 ? -1 : mode16);
-    out.intra_chroma_pred_mode = (uint8_t)chroma_mode;
-    out.cbp_luma = (uint8_t)(use4 ? cbpl4 : cbpl16);
-    out.cbp_chroma = (uint8_t)cbpc;
-    out.bits_intra16x16 = (uint16_t)bits16;
-    out.bits_intra4x4 = (uint16_t)bits4;
-    for (int i = 0; i < 16; i++) { out.intra4x4_pred_mode[i] = mode4[i]; out.prev_intra4x4_pred_mode_flag[i] = flag[i]; out.rem_intra4x4_pred_mode[i] = rem[i]; }
-    int16_t *ol = &out.luma[0][0];
-    if (use4) for (int i = 0; i < 256; i++) ol[i] = lv.luma[i >> 4][i & 15];
-    else {
-        for (int k = 0; k < 16; k++) ol[k] = lv.dc16[k];
-        for (int b = 0; b < 16; b++) for (int k = 0; k < 15; k++) ol[16 + b * 15 + k] = lv.ac16[b][k];
-    }
-    for (int k = 0; k < 2; k++) {
-        for (int i = 0; i < 4; i++) out.chroma_dc[k][i] = lv.cdc[k][i];
-        for (int b = 0; b < 4; b++) for (int i = 0; i < 15; i++) out.chroma_ac[k][b][i] = lv.cac[k][b][i];
-    }
-    out.reserved[0] = out.reserved[1] = out.reserved[2] = 0;
+        out.mb_type = (int16_t)(use4 ? 0 : type16);
+        out.intra16x16_pred_mode = (int8_t)(use4 ? -1 : mode16);
+        out.intra_chroma_pred_mode = (uint8_t)chroma_mode;
+        out.cbp_luma = (uint8_t)(use4 ? cbpl4 : cbpl16);
+        out.cbp_chroma = (uint8_t)cbpc;
+        out.bits_intra16x16 = (uint16_t)bits16;
+        out.bits_intra4x4 = (uint16_t)bits4;
+        for (int i = 0; i < 16; i++) { out.intra4x4_pred_mode[i] = mode4[i]; out.prev_intra4x4_pred_mode_flag[i] = flag[i]; out.rem_intra4x4_pred_mode[i] = rem[i]; }
+        int16_t *ol = &out.luma[0][0];
+        if (use4) for (int i = 0; i < 256; i++) ol[i] = lv.luma[i >> 4][i & 15];
+        else {
+            for (int k = 0; k < 16; k++) ol[k] = lv.dc16[k];
+            for (int b = 0; b < 16; b++) for (int k = 0; k < 15; k++) ol[16 + b * 15 + k] = lv.ac16[b][k];
+        }
+        for (int k = 0; k < 2; k++) {
+            for (int i = 0; i < 4; i++) out.chroma_dc[k][i] = lv.cdc[k][i];
+            for (int b = 0; b < 4; b++) for (int i = 0; i < 15; i++) out.chroma_ac[k][b][i] = lv.cac[k][b][i];
+        }
+        out.reserved[0] = out.reserved[1] = out.reserved[2] = 0;
 
-    info.mb_type = (uint8_t)out.mb_type; info.cbp_luma = out.cbp_luma; info.cbp_chroma = out.cbp_chroma; info.is4x4 = use4;
-    for (int i = 0; i < 16; i++) { info.tc_luma[i] = use4 ? tcl4[i] : tcl16[i]; info.mode4[i] = mode4[i]; }
-    for (int i = 0; i < 8; i++) info.tc_chroma[i >> 2][i & 3] = use4 ? tcc4[i >> 2][i & 3] : tcc16[i >> 2][i & 3];
-    info.pad[0] = info.pad[1] = info.pad[2] = info.pad[3] = 0;
+        info.mb_type = (uint8_t)out.mb_type; info.cbp_luma = out.cbp_luma; info.cbp_chroma = out.cbp_chroma; info.is4x4 = use4;
+        for (int i = 0; i < 16; i++) { info.tc_luma[i] = use4 ? tcl4[i] : tcl16[i]; info.mode4[i] = mode4[i]; }
+        for (int i = 0; i < 8; i++) info.tc_chroma[i >> 2][i & 3] = use4 ? tcc4[i >> 2][i & 3] : tcc16[i >> 2][i & 3];
+        info.pad[0] = info.pad[1] = info.pad[2] = info.pad[3] = 0;
+    }
+    ic_sync(nl);
+    for (int i = lane; i < 256; i += nl) c.rec[0][(size_t)(yP + (i >> 4)) * W + xP + (i & 15)] = c.L[i];
+    for (int i = lane; i < 128; i += nl) c.rec[1 + (i >> 6)][(size_t)((yP >> 1) + ((i & 63) >> 3)) * CW + (xP >> 1) + (i & 7)] = c.RC[i >> 6][i & 63];
 }

@@ -1,8 +1,9 @@
 """Host-side mirror of the reference's per-picture driver for the P path (fer_h264.cpp:55-79 NastaviEncode,
 ref_frames.cpp:185-234 selectNALUnitType, rbsp_encoding.cpp:139-323 RBSP_encode slice branch).
 
-Intra (IDR) pictures are NOT coded here: as in the integration build the reference's host code
-codes them and hands the reconstruction to the device (``intra_coder`` callback -> ``fh264_upload_recon``)."""
+Intra (IDR) pictures: by default coded on the device as well (``fh264_encode_i``); with an
+``intra_coder`` callback the reference's host code codes them, as in the integration build, and hands the
+reconstruction to the device (``fh264_upload_recon``)."""
 from __future__ import annotations
 
 from typing import Callable, Optional
@@ -35,16 +36,18 @@ class SequenceEncoder:
         return NAL_IDR if sad > (self.nmb << 12) else NAL_NON_IDR
 
     def encode_picture(self, y, cb, cr):
-        """One picture. Returns (nal_unit_type, records or None). For IDR the intra_coder callback must return the
-        reconstruction (Y, Cb, Cr) of the host-coded picture."""
+        """One picture. Returns (nal_unit_type, records): fh264_mb_result records for a P picture, fh264_mb_result_i records for
+        an IDR picture coded on the device, None for an IDR picture coded by the intra_coder callback (which must return the
+        reconstruction (Y, Cb, Cr) of the host-coded picture)."""
         self.s.upload_source(self.seq, y, cb, cr)
         nal = self.select_nal_unit_type()
         rec = None
         if nal == NAL_IDR:
             if self.intra_coder is None:
-                raise RuntimeError("IDR picture: an intra_coder (the reference host path) is required")
-            ry, rcb, rcr = self.intra_coder(y, cb, cr)
-            self.s.upload_recon(self.seq, ry, rcb, rcr)
+                rec = self.s.encode_i(self.qp, seq0=self.seq, nseq=1)[0]
+            else:
+                ry, rcb, rcr = self.intra_coder(y, cb, cr)
+                self.s.upload_recon(self.seq, ry, rcb, rcr)
             self.have_dpb = True
         else:
             rec = self.s.encode_p(self.qp, self.window, self.maxdiff_set, self.basic, seq0=self.seq, nseq=1)[0]

@@ -14,6 +14,12 @@ MB_RESULT_DTYPE = np.dtype([("mb_type", "<i2"), ("num_parts", "<i2"), ("mv", "<i
                             ("sad", "<u2", (4,)), ("luma", "<i2", (16, 16)), ("chroma_dc", "<i2", (2, 4)),
                             ("chroma_ac", "<i2", (2, 4, 15)), ("reserved", "<i2", (10,))])
 assert MB_RESULT_DTYPE.itemsize == 832
+# struct fh264_mb_result_i (832 bytes): one macroblock of an I picture
+MB_RESULT_I_DTYPE = np.dtype([("mb_type", "<i2"), ("intra16x16_pred_mode", "i1"), ("intra_chroma_pred_mode", "u1"), ("cbp_luma", "u1"),
+                              ("cbp_chroma", "u1"), ("bits_intra16x16", "<u2"), ("bits_intra4x4", "<u2"), ("intra4x4_pred_mode", "u1", (16,)),
+                              ("prev_intra4x4_pred_mode_flag", "u1", (16,)), ("rem_intra4x4_pred_mode", "u1", (16,)), ("luma", "<i2", (16, 16)),
+                              ("chroma_dc", "<i2", (2, 4)), ("chroma_ac", "<i2", (2, 4, 15)), ("reserved", "<i2", (3,))])
+assert MB_RESULT_I_DTYPE.itemsize == 832
 CAVLC_MB_INFO_DTYPE = np.dtype([("skip", "u1"), ("cbp_luma", "u1"), ("cbp_chroma", "u1"), ("mb_type", "u1"), ("total_coeff_luma", "u1", (16,)),
                                 ("total_coeff_chroma", "u1", (2, 4)), ("reserved", "u1", (4,))])
 assert CAVLC_MB_INFO_DTYPE.itemsize == 32
@@ -25,7 +31,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_frame", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
-           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
+           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
 
 
 class Fh264Error(RuntimeError):
@@ -84,6 +90,8 @@ def load_library():
     L.fh264_debug_timeline.argtypes = [vp, i32, vp]
     L.fh264_cavlc_p.argtypes = [vp, i32, i32, i32, vp, C.c_size_t, vp, vp]
     L.fh264_decode_p.argtypes = [vp, i32, i32, i32, vp]
+    L.fh264_encode_i.argtypes = [vp, i32, i32, i32, vp]
+    L.fh264_last_intra_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.fh264_debug_status.argtypes = [vp, i32, vp]
     L.fh264_band_config.argtypes = [vp, i32, i32, i32, i32]
     L.fh264_ipc_export.argtypes = [vp, i32, vp]
@@ -265,6 +273,21 @@ class Session:
         r = np.ascontiguousarray(records, dtype=MB_RESULT_DTYPE).reshape(-1, self.nmb)
         self._ck(self.L.fh264_decode_p(self.handle, seq0, r.shape[0], qp, _ptr(r)))
 
+    def encode_i(self, qp, seq0=0, nseq=None):
+        """Code the current source picture(s) as I pictures on the device (intraPredictionEncoding + quantizationTransform of every
+        macroblock, rbsp_encoding.cpp:196-215); the reconstruction becomes the reference picture. Returns [nseq, nmb] records
+        (MB_RESULT_I_DTYPE)."""
+        nseq = self.batch - seq0 if nseq is None else nseq
+        out = np.zeros((nseq, self.nmb), dtype=MB_RESULT_I_DTYPE)
+        self._ck(self.L.fh264_encode_i(self.handle, seq0, nseq, qp, _ptr(out)))
+        return out
+
+    def last_intra_ms(self):
+        """Device time of the intra wavefront kernel of the last encode_i call (ms)."""
+        ms = C.c_float(0)
+        self._ck(self.L.fh264_last_intra_ms(self.handle, C.byref(ms)))
+        return float(ms.value)
+
     def cavlc_p(self, first_bit=0, seq0=0, nseq=None, capacity=500064, mb_info=False):
         """Device CAVLC of the P picture(s) last coded by encode_p: list of (bytes, nbits) per sequence; slice data occupies bits
         [first_bit, nbits) of the returned bytes (rbsp_encoding.cpp:175-313)."""
@@ -313,6 +336,28 @@ class Session:
         out = np.zeros((self.h, self.w), np.uint16)
         self._ck(self.L.fh264_debug_feature(self.handle, seq, k, f, _ptr(out)))
         return out
+
+
+def i_records_to_ints(rec: np.ndarray) -> np.ndarray:
+    """[nmb] MB_RESULT_I_DTYPE -> [nmb, 439] int32 in the layout of the reference dump's I-picture records (chunk IMBR of
+    oracle/ref_harness/driver.cpp): mb_type, Intra16x16PredMode, intra_chroma_pred_mode, bits of the two trials, CBP luma / chroma,
+    Intra4x4PredMode[16], prev flags[16], rem modes[16], 256 luma levels, cdc[2][4], cac[2][4][15]."""
+    n = rec.shape[0]
+    out = np.zeros((n, 439), np.int32)
+    out[:, 0] = rec["mb_type"]
+    out[:, 1] = rec["intra16x16_pred_mode"]
+    out[:, 2] = rec["intra_chroma_pred_mode"]
+    out[:, 3] = rec["bits_intra16x16"]
+    out[:, 4] = rec["bits_intra4x4"]
+    out[:, 5] = rec["cbp_luma"]
+    out[:, 6] = rec["cbp_chroma"]
+    out[:, 7:23] = rec["intra4x4_pred_mode"]
+    out[:, 23:39] = rec["prev_intra4x4_pred_mode_flag"]
+    out[:, 39:55] = rec["rem_intra4x4_pred_mode"]
+    out[:, 55:311] = rec["luma"].reshape(n, 256)
+    out[:, 311:319] = rec["chroma_dc"].reshape(n, 8)
+    out[:, 319:439] = rec["chroma_ac"].reshape(n, 120)
+    return out
 
 
 def records_to_ints(rec: np.ndarray) -> np.ndarray:

@@ -219,6 +219,8 @@ typedef struct fh264_mb_result_i {
  * (mb_type_array is only cleared after the first trial, intra.cpp:1008-1012); the session remembers that from its last
  * fh264_encode_p / fh264_decode_p. results: nseq * MBs records (host) or NULL. Synchronous. Not available in band mode. */
 int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh264_mb_result_i *results);
+/* Device time of the intra wavefront kernel of the last fh264_encode_i call, milliseconds (CUDA events on the session stream). */
+int fh264_last_intra_ms(fh264_session *s, float *ms);
 
 /* ---- band mode: one picture split into macroblock-row bands over the GPUs of a node (BASELINE config 4) --------------
  * One process and one session per GPU, every rank encodes the same pictures in the same order. Each rank keeps the whole

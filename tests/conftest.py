@@ -73,8 +73,10 @@ class Golden:
 
 
 def golden_paths():
-    # clip fixtures only (cavlc_tables.npz holds the reference's CAVLC coder tables, see tests/test_cavlc_host.py)
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if os.path.basename(p) != "cavlc_tables.npz")
+    # P-path clip fixtures only (cavlc_tables.npz holds the reference's CAVLC coder tables, see tests/test_cavlc_host.py; the
+    # intra_*.npz fixtures have their own layout and tests: tests/test_intra_host.py, tests/test_gpu_intra.py)
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if os.path.basename(p) != "cavlc_tables.npz" and not os.path.basename(p).startswith("intra_"))
 
 
 @pytest.fixture(params=golden_paths(), ids=lambda p: os.path.splitext(os.path.basename(p))[0])

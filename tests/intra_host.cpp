@@ -17,7 +17,7 @@ extern "C" int intra_host_picture(const unsigned char *sy, const unsigned char *
         IcCtx c;
         c.src[0] = sy; c.src[1] = su; c.src[2] = sv; c.rec[0] = ry; c.rec[1] = ru; c.rec[2] = rv;
         c.W = W; c.H = H; c.xP = (m % wmb) * 16; c.yP = (m / wmb) * 16; c.qp = qp;
-        ic_macroblock(c, prev_types && prev_types[m] == 31, (m % wmb) ? &info[m - 1] : nullptr, m >= wmb ? &info[m - wmb] : nullptr, out[m], info[m]);
+        ic_macroblock(c, prev_types && prev_types[m] == 31, (m % wmb) ? &info[m - 1] : nullptr, m >= wmb ? &info[m - wmb] : nullptr, out[m], info[m], 0, 1);
     }
     return 0;
 }

@@ -1,0 +1,134 @@
+"""CPU checks of the device I-picture core (h264_fer_b200/csrc/intra_core.h, compiled for the host by g++) against I pictures of
+the compiled reference: the committed fixtures tests/golden/intra_*.npz (made by tests/golden/make_golden.py from
+oracle/_ref/ref_encoder, chunk IMBR) and, when the reference binary is present, live runs. Every field the reference's
+intraPredictionEncoding + quantizationTransform leave behind is compared bit for bit: final mb_type, prediction modes, the
+bits of both coded_mb_size() trials, CodedBlockPattern, all levels and the reconstruction. SURVEY.md §8(f) rank 2."""
+import ctypes as C
+import glob
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+from h264_fer_b200 import native as fh  # noqa: E402
+
+INTRA_GOLDENS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "intra_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    out = os.path.join(tempfile.mkdtemp(prefix="fh264_intra_"), "libintra_host.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "intra_host.cpp")], check=True)
+    return C.CDLL(out)
+
+
+def host_picture(lib, sy, su, sv, qp, prev_types):
+    h, w = sy.shape
+    out = np.zeros((w // 16) * (h // 16), fh.MB_RESULT_I_DTYPE)
+    rec = [np.zeros_like(np.ascontiguousarray(p)) for p in (sy, su, sv)]
+    pt = None if prev_types is None else np.ascontiguousarray(prev_types, np.int32)
+    vp = C.c_void_p
+    lib.intra_host_picture(*[np.ascontiguousarray(p).ctypes.data_as(vp) for p in (sy, su, sv)], *[r.ctypes.data_as(vp) for r in rec], w, h, qp,
+                           None if pt is None else pt.ctypes.data_as(vp), out.ctypes.data_as(vp))
+    return out, rec
+
+
+def compare_i_records(mine, ref, what):
+    """mine: [nmb, 439] from i_records_to_ints; ref: the reference dump's IMBR records."""
+    ref = np.asarray(ref, np.int32)
+    names = [("mb_type", 0, 1), ("Intra16x16PredMode", 1, 2), ("intra_chroma_pred_mode", 2, 3), ("bits of the Intra16x16 trial", 3, 4),
+             ("bits of the Intra4x4 trial", 4, 5), ("CodedBlockPatternLuma", 5, 6), ("CodedBlockPatternChroma", 6, 7), ("Intra4x4PredMode", 7, 23),
+             ("prev_intra4x4_pred_mode_flag", 23, 39), ("luma levels", 55, 311), ("chroma DC levels", 311, 319), ("chroma AC levels", 319, 439)]
+    for name, a, b in names:
+        bad = np.nonzero((mine[:, a:b] != ref[:, a:b]).any(axis=1))[0]
+        assert len(bad) == 0, "%s: %s differs in %d macroblocks, first %d: mine %s ref %s" % (what, name, len(bad), bad[0], mine[bad[0], a:b], ref[bad[0], a:b])
+    coded = ref[:, 23:39] == 0          # rem_intra4x4_pred_mode is only meaningful where the flag is 0
+    assert np.array_equal(mine[:, 39:55][coded], ref[:, 39:55][coded]), what + ": rem_intra4x4_pred_mode differs"
+
+
+def check_clip(lib, pics, qp, what):
+    """pics: list of dicts with SRCY/SRCU/SRCV, RECY/RECU/RECV and imbrec (I pictures) or mbrec (P pictures)."""
+    prev, n_i = None, 0
+    for n, p in enumerate(pics):
+        if "imbrec" not in p:
+            prev = np.asarray(p["mbrec"])[:, 0].astype(np.int32)
+            continue
+        out, rec = host_picture(lib, p["SRCY"], p["SRCU"], p["SRCV"], qp, prev)
+        compare_i_records(fh.i_records_to_ints(out), p["imbrec"], "%s picture %d" % (what, n))
+        for r, t in zip(rec, ("RECY", "RECU", "RECV")):
+            assert np.array_equal(r, p[t]), "%s picture %d: %s differs" % (what, n, t)
+        prev = np.asarray(p["imbrec"])[:, 0].astype(np.int32)
+        n_i += 1
+    assert n_i > 0
+
+
+def golden_pictures(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    pics = []
+    for n in range(len(g["types"])):
+        p = {t: g["%s_%d" % (t, n)] for t in ("SRCY", "SRCU", "SRCV", "RECY", "RECU", "RECV")}
+        for k in ("imbrec", "mbrec"):
+            if "%s_%d" % (k, n) in g:
+                p[k] = g["%s_%d" % (k, n)].astype(np.int32)
+        pics.append(p)
+    return g["params"], pics
+
+
+def test_fixtures_exist():
+    assert len(INTRA_GOLDENS) >= 5
+
+
+@pytest.mark.parametrize("name", INTRA_GOLDENS)
+def test_core_matches_the_reference_on_the_golden_i_pictures(host_lib, name):
+    params, pics = golden_pictures(name)
+    check_clip(host_lib, pics, int(params[4]), name)
+
+
+def test_fixtures_cover_both_macroblock_kinds_and_the_p_skip_state():
+    kinds, skipped_before_i = set(), 0
+    for name in INTRA_GOLDENS:
+        _, pics = golden_pictures(name)
+        for n, p in enumerate(pics):
+            if "imbrec" in p:
+                kinds |= set(np.unique(np.minimum(p["imbrec"][:, 0], 1)))
+                if n and "mbrec" in pics[n - 1]:
+                    skipped_before_i += int((pics[n - 1]["mbrec"][:, 0] == 31).sum())
+    assert kinds == {0, 1}, "fixtures must contain Intra4x4 and Intra16x16 macroblocks"
+    assert skipped_before_i > 0, "fixtures must contain an I picture that follows P_Skip macroblocks"
+
+
+def test_the_previous_pictures_p_skip_state_is_part_of_the_result(host_lib):
+    """The first bit-cost trial reads mb_type_array[CurrMbAddr] of the PREVIOUS picture (intra.cpp:1008-1012): with that state
+    dropped, the Intra16x16 trial bits of some macroblock after P_Skip macroblocks must change."""
+    params, pics = golden_pictures("intra_static_qp12_ipi")
+    p = pics[2]
+    prev = pics[1]["mbrec"][:, 0].astype(np.int32)
+    with_state, _ = host_picture(host_lib, p["SRCY"], p["SRCU"], p["SRCV"], int(params[4]), prev)
+    without, _ = host_picture(host_lib, p["SRCY"], p["SRCU"], p["SRCV"], int(params[4]), None)
+    assert np.array_equal(with_state["bits_intra16x16"], p["imbrec"][:, 3])
+    assert (with_state["bits_intra16x16"] != without["bits_intra16x16"]).sum() > 50
+    assert (with_state["mb_type"] != without["mb_type"]).any()
+
+
+@pytest.mark.parametrize("w,h,seed,frames,qp,intra_every,kw", [
+    (176, 144, 21, 3, 24, 2, {}),
+    (96, 80, 22, 3, 36, 1, {"contrast": 0.2}),
+    (352, 288, 23, 2, 28, 1000, {}),
+    (128, 64, 24, 4, 51, 2, {"contrast": 0.6}),
+    (64, 64, 25, 2, 0, 1, {}),
+])
+def test_core_matches_live_runs_of_the_reference(host_lib, w, h, seed, frames, qp, intra_every, kw):
+    from h264_fer_b200 import synth
+    from oracle import refdump
+    if not refdump.have_ref_encoder():
+        pytest.skip("oracle/_ref/ref_encoder not built")
+    y4m = os.path.join(tempfile.mkdtemp(prefix="fh264_intra_live_"), "in.y4m")
+    synth.write_y4m(y4m, w, h, seed, frames, **kw)
+    _, dump, _ = refdump.run_reference(y4m, frames, qp=qp, intra_every=intra_every, dumpmask=refdump.D_MBREC | refdump.D_RECON | refdump.D_SOURCE | refdump.D_IMBREC)
+    check_clip(host_lib, refdump.parse_dump(dump), qp, "live %dx%d qp %d" % (w, h, qp))

@@ -230,6 +230,7 @@ def main():
                     help="sequences: independent sequences per GPU (weak scaling, the headline); bands: ONE 1080p sequence split into MB-row bands over all GPUs (BASELINE config 4, strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cavlc", action="store_true", help="skip the device-CAVLC line item (SURVEY.md §8(f) rank 1)")
+    ap.add_argument("--no-intra", action="store_true", help="skip the device I-picture line item (SURVEY.md §8(f) rank 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -423,6 +424,30 @@ def main():
                          "the call waits for the picture (no record D2H); cavlc_call_ms includes that wait, cavlc_alone_ms is a repeat call on the finished "
                          "pictures (kernels + copies + two stream syncs, host wall clock)"}
 
+    # device I-picture line item: every sequence of group 0 codes its current source picture as an IDR
+    # picture on the device (fh264_encode_i: intra mode searches, both CAVLC bit-cost trials, TQ, reconstruction, then phase R),
+    # pinned H2D of the pictures and D2H of the 832-byte records inside the timed region. Reported beside the headline, not in it.
+    intra = None
+    if not args.no_intra and G == 1:
+        g0 = groups[0]
+        i_out = PinnedArray((g0.n, nmb), fh.MB_RESULT_I_DTYPE)
+        ker_ms, call_ms = [], []
+        for it in range(1 + 3):
+            g0.t = 1 + it
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g0.upload(True)
+            g0.s._ck(g0.s.L.fh264_encode_i(g0.s.handle, 0, g0.n, QP, i_out.ptr))
+            if it:
+                call_ms.append(1000.0 * (time.perf_counter() - t0))
+                ker_ms.append(g0.s.last_intra_ms())
+        km, cm = sum(ker_ms) / len(ker_ms), sum(call_ms) / len(call_ms)
+        intra = {"e2e_value": g0.n / (cm / 1000.0), "unit": "I pictures/s (this GPU)", "call_ms": cm, "k_intra_ms": km, "pictures_per_launch": g0.n,
+                 "intra4x4_share": float((i_out.array["mb_type"] == 0).mean()), "gpu_launches_per_call": 7,
+                 "note": "fh264_encode_i on the group's pictures: k_intra (wavefront, one warp per macroblock) + dpb swap + phase R; call_ms is host wall "
+                         "clock around upload + the synchronous call (H2D of the pictures, D2H of the records included), k_intra_ms the CUDA-event time of "
+                         "the wavefront kernel; the reference codes one 1080p I picture in about 1.7-3.3 s on one host core"}
+
     # per-kernel device times (CUDA events inside the library, on the launching stream): group 0 alone, a few steps
     g0 = groups[0]
     g0.reset()
@@ -477,6 +502,8 @@ def main():
         }
         if cavlc is not None:
             line["device_cavlc"] = cavlc
+        if intra is not None:
+            line["device_intra"] = intra
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))

@@ -517,6 +517,16 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
         PartA *pa = &S.parta[part];
         pa->s2_off = off;
         if (n2 > 1023) { pa->n2 = S2_SLOW | (uint32_t)js; n2 = 0; }      // more candidates than a pool slice: phase B's own enumeration
+        else if (!REDO && n2 > CAP) {
+            // the kept entries fit, but with bucket s0 listed twice the output slots would run past order[CAP] (half-flat content:
+            // hundreds of positions share the block's exact sum): the fallback launch, whose buffers hold any pool slice, redoes it
+            const uint32_t k = atomicAdd(&S.status[ST_S2REDO], 1u);
+            const bool listed = k < S2_REDO_MAX;
+            if (listed) S.s2redo[k] = (uint32_t)part;
+            pa->s2_off = 0;
+            pa->n2 = listed ? 0u : (S2_SLOW | (uint32_t)js);
+            n2 = 0;
+        }
         else pa->n2 = (uint32_t)n2;
     }
     n2 = __shfl_sync(0xffffffffu, n2, 0);

@@ -75,6 +75,7 @@ struct fh264_session {
     IntraSeq *d_is;
     cudaEvent_t ev_i[2];            // around k_intra
     bool intra_timed;
+    int *d_iwf_order;               // anti-diagonal order x + 2y: an I macroblock needs left, up-left, up and up-right complete
     int *d_prev_p;                  // per sequence: the previous picture was a P picture whose records are in `results`
     std::vector<int> prev_p;
 };
@@ -191,7 +192,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->up_stream = nullptr;
     s->copy_stream = nullptr; s->ev_c_done = nullptr; s->ev_copy_done = nullptr; s->copy_pending = false;
     s->d_cvs = nullptr; s->h_cvstat = nullptr;
-    s->d_is = nullptr; s->d_prev_p = nullptr; s->ev_i[0] = s->ev_i[1] = nullptr; s->intra_timed = false;
+    s->d_is = nullptr; s->d_prev_p = nullptr; s->d_iwf_order = nullptr; s->ev_i[0] = s->ev_i[1] = nullptr; s->intra_timed = false;
     s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->d_sadout = nullptr; s->scr_mbs = 0;
     for (int i = 0; i < 5; i++) s->ev[i] = nullptr;
     for (int i = 0; i < 4; i++) s->evk[i] = nullptr;
@@ -567,6 +568,15 @@ static int ensure_intra(fh264_session *s)
         CK(cudaMemset(s->ih[b].done, 0, sizeof(uint32_t) * nmb));
     }
     CK(dalloc(s, &s->d_prev_p, (size_t)s->batch));
+    {
+        // every dependency of a macroblock has a smaller key x + 2y (up-right: -1), so it holds a smaller ticket
+        std::vector<int> order(nmb);
+        for (size_t i = 0; i < nmb; i++) order[i] = (int)i;
+        const int Wmb = s->g.Wmb;
+        std::stable_sort(order.begin(), order.end(), [Wmb](int a, int b) { return (a % Wmb) + 2 * (a / Wmb) < (b % Wmb) + 2 * (b / Wmb); });
+        CK(dalloc(s, &s->d_iwf_order, nmb));
+        CK(cudaMemcpy(s->d_iwf_order, order.data(), sizeof(int) * nmb, cudaMemcpyHostToDevice));
+    }
     for (int i = 0; i < 2; i++) CK(cudaEventCreate(&s->ev_i[i]));
     CK(dalloc(s, &s->d_is, (size_t)s->batch));
     CK(cudaMemcpy(s->d_is, s->ih.data(), sizeof(IntraSeq) * s->batch, cudaMemcpyHostToDevice));
@@ -591,7 +601,7 @@ extern "C" int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh26
     { const char *e = getenv("FH264_INTRA_LANES"); if (e && atoi(e) == 1) nl = 1; }   // development knob (read per call): everything on lane 0
     const unsigned ctas = (unsigned)std::min<long long>((long long)g.nmb * nseq, (long long)nseq * (g.Wmb + 16));
     CK(cudaEventRecord(s->ev_i[0], st));
-    k_intra<<<ctas, 32, 0, st>>>(s->d_seqs, s->d_is, s->d_prev_p, seq0, nseq, g, qp, s->epoch, s->d_wf_order, s->d_ticket + 1, nl);
+    k_intra<<<ctas, 32, 0, st>>>(s->d_seqs, s->d_is, s->d_prev_p, seq0, nseq, g, qp, s->epoch, s->d_iwf_order, s->d_ticket + 1, nl);
     CKL();
     CK(cudaEventRecord(s->ev_i[1], st));
     s->intra_timed = true;

@@ -13,7 +13,8 @@
 // CurrMbAddr == 0 and consume it per macroblock (IntraCL() at rbsp_encoding.cpp:144, WaitIntraCL at intra.cpp:963-966).
 // The unmodified reference sources are compiled with -Dname=ref_name for these five symbols (integration/Makefile), so
 // I pictures and intra bit-cost trials still run the reference's own code; everything else (CAVLC, NAL, headers,
-// intra prediction, Y4M input) is the untouched reference host code.
+// intra prediction, Y4M input) is the untouched reference host code. Two further variants move more onto the device:
+// -DFH264_SHIM_DEVICE_CAVLC (P-slice entropy coding) and -DFH264_SHIM_DEVICE_INTRA (I pictures: intraPredictionEncoding()).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,6 +43,7 @@ extern frame_type dpb;
 static fh264_session *g_sess = 0;
 static std::vector<fh264_mb_result> g_res;
 static bool g_last_was_p = false;
+static bool g_last_was_device_i = false;     // FH264_SHIM_DEVICE_INTRA: the I picture was coded (and made the reference) on the device
 
 static void die(const char *what, int rc)
 {
@@ -96,8 +98,67 @@ void interEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8])
     refIdxL0[CurrMbAddr] = 0;
 }
 
+#ifdef FH264_SHIM_DEVICE_INTRA
+// ---- variant with the I pictures on the device too (integration/_build/fh264_encoder_b200_intra) ---------
+// intra.cpp is compiled with -DintraPredictionEncoding=ref_intraPredictionEncoding. The I-slice macroblock loop of RBSP_encode
+// (rbsp_encoding.cpp:196-215) stays the reference's: it calls intraPredictionEncoding() and quantizationTransform(..., true),
+// derives mb_type / CodedBlockPattern from the levels it finds in the globals and writes the macroblock with its own CAVLC.
+// Here intraPredictionEncoding() runs the whole picture on the device when CurrMbAddr == 0 (the pattern of IntraCL() /
+// WaitIntraCL(), rbsp_encoding.cpp:144, intra.cpp:963-966) and then hands out, per macroblock, what the reference function
+// leaves in the globals; quantizationTransform() copies the levels and the reconstructed samples.
+static std::vector<fh264_mb_result_i> g_ires;
+static std::vector<unsigned char> g_irec[3];
+
+int intraPredictionEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8])
+{
+    (void)predL; (void)predCr; (void)predCb;      // the prediction samples are only inputs of quantizationTransform(), replaced below
+    if (CurrMbAddr == 0) {
+        ensure_session();
+        g_ires.resize(g_res.size());
+        const size_t WH = (size_t)frame.Lwidth * frame.Lheight;
+        g_irec[0].resize(WH); g_irec[1].resize(WH / 4); g_irec[2].resize(WH / 4);
+        int rc = fh264_upload_source(g_sess, 0, frame.L, frame.C[0], frame.C[1]);
+        if (rc) die("fh264_upload_source", rc);
+        rc = fh264_encode_i(g_sess, 0, 1, QPy, g_ires.data());
+        if (rc) die("fh264_encode_i", rc);
+        rc = fh264_download_recon(g_sess, 0, g_irec[0].data(), g_irec[1].data(), g_irec[2].data());
+        if (rc) die("fh264_download_recon", rc);
+        g_last_was_device_i = true;
+    }
+    const fh264_mb_result_i &r = g_ires[CurrMbAddr];
+    for (int b = 0; b < 16; b++) {
+        Intra4x4PredMode[(CurrMbAddr << 4) + b] = r.intra4x4_pred_mode[b];
+        prev_intra4x4_pred_mode_flag[b] = r.prev_intra4x4_pred_mode_flag[b] != 0;
+        rem_intra4x4_pred_mode[b] = r.rem_intra4x4_pred_mode[b];
+    }
+    intra_chroma_pred_mode = r.intra_chroma_pred_mode;
+    mb_type_array[CurrMbAddr] = 0;                // intra.cpp:1012,1058; the macroblock loop stores the final type afterwards
+    return r.intra16x16_pred_mode;
+}
+
+static void intra_levels_and_reconstruction()
+{
+    const fh264_mb_result_i &r = g_ires[CurrMbAddr];
+    const int16_t *l = &r.luma[0][0];
+    if (r.intra16x16_pred_mode < 0) for (int b = 0; b < 16; b++) for (int k = 0; k < 16; k++) LumaLevel[b][k] = l[b * 16 + k];
+    else {
+        for (int k = 0; k < 16; k++) Intra16x16DCLevel[k] = l[k];
+        for (int b = 0; b < 16; b++) for (int k = 0; k < 15; k++) Intra16x16ACLevel[b][k] = l[16 + b * 15 + k];
+    }
+    for (int c = 0; c < 2; c++) for (int k = 0; k < 4; k++) ChromaDCLevel[c][k] = r.chroma_dc[c][k];
+    for (int c = 0; c < 2; c++) for (int b = 0; b < 4; b++) for (int k = 0; k < 15; k++) ChromaACLevel[c][b][k] = r.chroma_ac[c][b][k];
+    const int W = frame.Lwidth, CW = frame.Cwidth, xP = (CurrMbAddr % PicWidthInMbs) << 4, yP = (CurrMbAddr / PicWidthInMbs) << 4;
+    for (int y = 0; y < 16; y++) memcpy(frame.L + (size_t)(yP + y) * W + xP, g_irec[0].data() + (size_t)(yP + y) * W + xP, 16);
+    for (int c = 0; c < 2; c++)
+        for (int y = 0; y < 8; y++) memcpy(frame.C[c] + (size_t)(yP / 2 + y) * CW + xP / 2, g_irec[1 + c].data() + (size_t)(yP / 2 + y) * CW + xP / 2, 8);
+}
+#endif
+
 void quantizationTransform(int predL[16][16], int predCb[8][8], int predCr[8][8], bool reconstruct)
 {
+#ifdef FH264_SHIM_DEVICE_INTRA
+    if ((shd.slice_type % 5) != P_SLICE && reconstruct) { intra_levels_and_reconstruction(); return; }
+#endif
     if ((shd.slice_type % 5) != P_SLICE) { ref_quantizationTransform(predL, predCb, predCr, reconstruct); return; }
     const fh264_mb_result &r = g_res[CurrMbAddr];
     for (int b = 0; b < 16; b++) for (int k = 0; k < 16; k++) LumaLevel[b][k] = r.luma[b][k];
@@ -122,12 +183,13 @@ void FillInterpolatedRefFrame()
         memcpy(dpb.L, frame.L, (size_t)frame.Lwidth * frame.Lheight);
         memcpy(dpb.C[0], frame.C[0], (size_t)frame.Cwidth * frame.Cheight);
         memcpy(dpb.C[1], frame.C[1], (size_t)frame.Cwidth * frame.Cheight);
-    } else {
+    } else if (!g_last_was_device_i) {
         // I picture coded by the reference host path: its reconstruction becomes the device's reference picture
         int rc = fh264_upload_recon(g_sess, 0, frame.L, frame.C[0], frame.C[1]);
         if (rc) die("fh264_upload_recon", rc);
-    }
+    }   // else: I picture coded by fh264_encode_i, which already made its reconstruction the reference picture (host `frame` holds it too)
     g_last_was_p = false;
+    g_last_was_device_i = false;
 }
 
 #ifdef FH264_SHIM_DEVICE_CAVLC

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ENCODER = os.path.join(ROOT, "integration", "_build", "fh264_encoder_b200")
 ENCODER_CAVLC = ENCODER + "_cavlc"          # same, with the P-slice entropy coding on the device too
+ENCODER_INTRA = ENCODER + "_intra"          # same as the first, with the I pictures coded on the device too
 
 needs_binary = pytest.mark.skipif(not (os.path.isfile(ENCODER) and os.path.isfile(ENCODER_CAVLC)), reason="integration binaries not built (make -C integration)")
 both_encoders = pytest.mark.parametrize("encoder", [ENCODER, ENCODER_CAVLC], ids=["host_cavlc", "device_cavlc"])
@@ -81,3 +82,32 @@ def test_720p_window32_bitstream_matches_live_reference(tmp_path, encoder):
     run_b200_encoder(y4m, out, "-", 3, 28, 0, 32, 3, encoder=encoder)
     assert summ["types"] == "IPP"
     assert open(out, "rb").read() == open(ref264, "rb").read()
+
+
+needs_intra_binary = pytest.mark.skipif(not os.path.isfile(ENCODER_INTRA), reason="integration binary with device I pictures not built (make -C integration)")
+
+
+@needs_intra_binary
+@pytest.mark.skipif(not refdump.have_ref_encoder(), reason="compiled reference not present")
+@pytest.mark.parametrize("w,h,seed,frames,qp,window,maxdiff,intra_every,kw", [
+    (176, 144, 1, 30, 28, 16, 3, 1000, {}),                                   # BASELINE config 1: first picture + a scene-change IDR
+    (352, 288, 2, 9, 28, 32, -1, 3, {}),                                      # CIF, periodic IDR every 3 pictures
+    (176, 144, 6, 6, 30, 16, 3, 2, {"contrast": 0.05, "noise": 0.3}),         # low contrast: Intra16x16 macroblocks, flat P pictures
+    (176, 144, 31, 5, 12, 16, 3, 2, {"pan": (0, 0), "noise": 0.0, "square": False}),   # static: all-P_Skip pictures before the IDRs
+    (200, 120, 9, 4, 44, 16, 3, 2, {}),                                       # cropped input, coarse quantiser
+])
+def test_bitstream_with_device_i_pictures_matches_live_reference(tmp_path, w, h, seed, frames, qp, window, maxdiff, intra_every, kw):
+    """The unmodified reference host code with BOTH picture types coded on the device (fh264_encode_i + fh264_encode_p): the
+    reference's own CAVLC writes what the device decided, and the Annex-B stream must be byte-identical to the reference's."""
+    y4m = str(tmp_path / "in.y4m")
+    synth.write_y4m(y4m, w, h, seed, frames, **kw)
+    ref264, refdumpf = str(tmp_path / "ref.264"), str(tmp_path / "ref.bin")
+    summ, rd, _ = refdump.run_reference(y4m, frames, qp=qp, window=window, maxdiff=maxdiff, intra_every=intra_every, out_264=ref264,
+                                        dumpmask=refdump.D_RECON, dump_path=refdumpf)
+    out, dump = str(tmp_path / "b200.264"), str(tmp_path / "b200.bin")
+    run_b200_encoder(y4m, out, dump, frames, qp, 0, window, maxdiff, intra_every=intra_every, dumpmask=refdump.D_RECON, encoder=ENCODER_INTRA)
+    assert summ["types"].count("I") >= 1 and "P" in summ["types"]
+    for n, (a, b) in enumerate(zip(refdump.parse_dump(dump), refdump.parse_dump(rd))):
+        assert a["nal_type"] == b["nal_type"], "picture %d type" % n
+        assert np.array_equal(a["RECY"], b["RECY"]) and np.array_equal(a["RECU"], b["RECU"]) and np.array_equal(a["RECV"], b["RECV"]), "picture %d reconstruction (%s)" % (n, summ["types"])
+    assert open(out, "rb").read() == open(ref264, "rb").read(), "bitstreams differ (%s)" % summ["types"]

@@ -44,6 +44,16 @@ struct IcInfo {
     uint8_t pad[4];
 };
 
+// levels of one macroblock
+struct IcLevels {
+    int16_t luma[16][16];       // LumaLevel (Intra4x4)
+    int16_t dc16[16];           // Intra16x16DCLevel
+    int16_t ac16[16][15];       // Intra16x16ACLevel
+    int16_t cdc[2][4];
+    int16_t cac[2][4][15];
+};
+
+// Working state of one macroblock, shared by the lanes that work on it (shared memory on the device).
 struct IcCtx {
     const uint8_t *src[3];      // `frame` as read from the file
     uint8_t *rec[3];            // `frame` as left by the macroblocks already coded (reconstruction)
@@ -52,6 +62,15 @@ struct IcCtx {
     uint8_t L[256];             // `frame.L` inside this macroblock: source, overwritten block by block by the Intra4x4 reconstruction
     uint8_t SC[2][64];          // source chroma
     uint8_t RC[2][64];          // reconstructed chroma
+    uint8_t pred16[256];        // Intra16x16 prediction of the chosen mode
+    uint8_t predC[2][64];       // chroma prediction
+    IcLevels lv;
+    int DC[16], cq16[16];       // Intra16x16: DC of every block before / after the Hadamard + quantisation (row-major)
+    int cdcraw[2][4];           // chroma: DC of every block before the 2x2 transform
+    int rdc[16], crdc[2][4];    // reconstructed (scaled) DCs
+    uint8_t tcl[2][16], tcc[2][2][4];   // TotalCoeff of the coded blocks, [0] Intra16x16 trial, [1] Intra4x4 trial
+    uint8_t mode4[16], flag[16], rem[16];
+    int cbpl16, cbpl4, cbpc, type16;
 };
 
 FH_HD int ic_abs(int a) { return a < 0 ? -a : a; }
@@ -364,63 +383,66 @@ FH_HD void ic_pred_chroma(const IcCtx &c, int comp, int mode, uint8_t o[64])
         for (int x = 0; x < 8; x++) o[y * 8 + x] = (uint8_t)ic_clip255((a + b * (x - 3) + cc * (y - 3) + 16) >> 5);
 }
 
-// ---- levels of one macroblock -------------------------------------------------------------------------------------------------
-struct IcLevels {
-    int16_t luma[16][16];       // LumaLevel (Intra4x4)
-    int16_t dc16[16];           // Intra16x16DCLevel
-    int16_t ac16[16][15];       // Intra16x16ACLevel
-    int16_t cdc[2][4];
-    int16_t cac[2][4][15];
-};
-
-// Intra16x16 luma of quantizationTransform (quantizationTransform.cpp:381-420); reconstruct = transformDecodingIntra_16x16Luma
-// (inttransform.cpp:157-208) into L
-FH_HD void ic_tq_luma16(IcCtx &c, const uint8_t pred[256], IcLevels &lv, bool reconstruct)
+// ---- transform / quantisation of the macroblock, one 4x4 block per call so that the blocks can be spread over the lanes ---------
+// unit v of the forward pass: v < 16 luma block v as Intra16x16 (quantizationTransform.cpp:381-412), v = 16 .. 23 chroma block
+// (v - 16) & 3 of component (v - 16) >> 2 (:424-462). DC coefficients are left unquantised for the DC transforms.
+FH_HD void ic_forward_unit(IcCtx &c, int v)
 {
-    int DC[16], cq[16], diff[16], r[16];
-    for (int b = 0; b < 16; b++) {
-        const int x0 = ic_blkx(b), y0 = ic_blky(b);
-        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 16 + x0 + (i & 3); diff[i] = (int)c.L[o] - (int)pred[o]; }
+    int diff[16], r[16];
+    if (v < 16) {
+        const int x0 = ic_blkx(v), y0 = ic_blky(v);
+        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 16 + x0 + (i & 3); diff[i] = (int)c.L[o] - (int)c.pred16[o]; }
         ic_forward_residual(diff, r, c.qp, true);
-        DC[(y0 >> 2) * 4 + (x0 >> 2)] = r[0];
-        for (int k = 1; k < 16; k++) lv.ac16[b][k - 1] = (int16_t)r[ic_ZZ[k]];
-    }
-    ic_luma_dc_forward(DC, c.qp, cq);
-    for (int k = 0; k < 16; k++) lv.dc16[k] = (int16_t)cq[ic_ZZ[k]];
-    if (!reconstruct) return;
-    ic_luma_dc_inverse(cq, c.qp, DC);
-    for (int b = 0; b < 16; b++) {
-        const int x0 = ic_blkx(b), y0 = ic_blky(b);
-        int cf[16], d[16], rr[16];
-        cf[0] = DC[(y0 >> 2) * 4 + (x0 >> 2)];
-        for (int k = 1; k < 16; k++) cf[ic_ZZ[k]] = lv.ac16[b][k - 1];
-        ic_dequant4x4(cf, d, c.qp, true);
-        ic_inverse4x4(d, rr);
-        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 16 + x0 + (i & 3); c.L[o] = (uint8_t)ic_clip255((int)pred[o] + rr[i]); }
+        c.DC[(y0 >> 2) * 4 + (x0 >> 2)] = r[0];
+        for (int k = 1; k < 16; k++) c.lv.ac16[v][k - 1] = (int16_t)r[ic_ZZ[k]];
+    } else {
+        const int comp = (v - 16) >> 2, b = (v - 16) & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
+        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 8 + x0 + (i & 3); diff[i] = (int)c.SC[comp][o] - (int)c.predC[comp][o]; }
+        ic_forward_residual(diff, r, c.qpc, true);
+        c.cdcraw[comp][b] = r[0];
+        for (int k = 1; k < 16; k++) c.lv.cac[comp][b][k - 1] = (int16_t)r[ic_ZZ[k]];
     }
 }
-// chroma of quantizationTransform (quantizationTransform.cpp:424-484); reconstruct = transformDecodingChroma (inttransform.cpp:237-321)
-FH_HD void ic_tq_chroma(const IcCtx &c, int comp, const uint8_t pred[64], IcLevels &lv, uint8_t *recon /* 64 or null */)
+// the DC transforms that follow (forwardDCLumaIntra :393-397, forwardDCChroma :464-478)
+FH_HD void ic_forward_dcs(IcCtx &c)
 {
-    int ac[4][16], dc[4], dl[4], diff[16];
-    for (int b = 0; b < 4; b++) {
-        const int x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
-        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 8 + x0 + (i & 3); diff[i] = (int)c.SC[comp][o] - (int)pred[o]; }
-        ic_forward_residual(diff, ac[b], c.qpc, true);
-        dc[b] = ac[b][0];
-        for (int k = 1; k < 16; k++) lv.cac[comp][b][k - 1] = (int16_t)ac[b][ic_ZZ[k]];
+    ic_luma_dc_forward(c.DC, c.qp, c.cq16);
+    for (int k = 0; k < 16; k++) c.lv.dc16[k] = (int16_t)c.cq16[ic_ZZ[k]];
+    for (int comp = 0; comp < 2; comp++) {
+        int dl[4];
+        ic_chroma_dc_forward(c.cdcraw[comp], c.qpc, dl);
+        for (int i = 0; i < 4; i++) c.lv.cdc[comp][i] = (int16_t)dl[i];
     }
-    ic_chroma_dc_forward(dc, c.qpc, dl);
-    for (int i = 0; i < 4; i++) lv.cdc[comp][i] = (int16_t)dl[i];
-    if (!recon) return;
-    ic_chroma_dc_inverse(dl, c.qpc, dc);
-    for (int b = 0; b < 4; b++) {
-        const int x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
-        int d[16], rr[16];
-        ac[b][0] = dc[b];
-        ic_dequant4x4(ac[b], d, c.qpc, true);
+}
+// reconstruction: DCs first (scaleTransform.cpp:154-189,344-376 luma; :247-262,408-420 chroma) ...
+FH_HD void ic_inverse_dcs(IcCtx &c, bool luma16)
+{
+    if (luma16) ic_luma_dc_inverse(c.cq16, c.qp, c.rdc);
+    for (int comp = 0; comp < 2; comp++) {
+        int dl[4];
+        for (int i = 0; i < 4; i++) dl[i] = c.lv.cdc[comp][i];
+        ic_chroma_dc_inverse(dl, c.qpc, c.crdc[comp]);
+    }
+}
+// ... then unit v: v < 16 luma block of an Intra16x16 macroblock (transformDecodingIntra_16x16Luma, inttransform.cpp:157-208) into L,
+// v = 16 .. 23 chroma block (transformDecodingChroma, inttransform.cpp:237-321) into RC
+FH_HD void ic_inverse_unit(IcCtx &c, int v)
+{
+    int cf[16], d[16], rr[16];
+    if (v < 16) {
+        const int x0 = ic_blkx(v), y0 = ic_blky(v);
+        cf[0] = c.rdc[(y0 >> 2) * 4 + (x0 >> 2)];
+        for (int k = 1; k < 16; k++) cf[ic_ZZ[k]] = c.lv.ac16[v][k - 1];
+        ic_dequant4x4(cf, d, c.qp, true);
         ic_inverse4x4(d, rr);
-        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 8 + x0 + (i & 3); recon[o] = (uint8_t)ic_clip255((int)pred[o] + rr[i]); }
+        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 16 + x0 + (i & 3); c.L[o] = (uint8_t)ic_clip255((int)c.pred16[o] + rr[i]); }
+    } else {
+        const int comp = (v - 16) >> 2, b = (v - 16) & 3, x0 = (b & 1) * 4, y0 = (b >> 1) * 4;
+        cf[0] = c.crdc[comp][b];
+        for (int k = 1; k < 16; k++) cf[ic_ZZ[k]] = c.lv.cac[comp][b][k - 1];
+        ic_dequant4x4(cf, d, c.qpc, true);
+        ic_inverse4x4(d, rr);
+        for (int i = 0; i < 16; i++) { const int o = (y0 + (i >> 2)) * 8 + x0 + (i & 3); c.RC[comp][o] = (uint8_t)ic_clip255((int)c.predC[comp][o] + rr[i]); }
     }
 }
 
@@ -439,48 +461,52 @@ FH_HD void ic_cbp(bool is16, const IcLevels &lv, int &cbpl, int &cbpc)
     for (int i4 = 0; i4 < 4; i4++) if (cv_count(lv.cac[0][i4], 15) || cv_count(lv.cac[1][i4], 15)) cbpc = 2;
 }
 
-// coded_mb_size (rbsp_encoding.cpp:330-487) of an I macroblock. self_skip: mb_type_array[CurrMbAddr] == P_Skip while the
-// trial runs — during the Intra16x16 trial that entry still holds the PREVIOUS picture's type (intra.cpp:1012 clears it only
-// afterwards), and residual.cpp:473,493 then take every neighbour block inside this macroblock as empty.
-// tcl / tcc receive the TotalCoeff of the blocks the trial codes (0 elsewhere).
-FH_HD int ic_mb_bits(bool is16, int mb_type, int chroma_mode, const uint8_t prev_flag[16], const IcLevels &lv, int cbpl, int cbpc, bool self_skip,
-                     const IcInfo *left, const IcInfo *up, uint8_t tcl[16], uint8_t tcc[2][4])
+// coded_mb_size (rbsp_encoding.cpp:330-487) of an I macroblock, the residual blocks spread over the lanes: the size of a block
+// depends on its neighbours only through their TotalCoeff (nC), and those are plain non-zero counts, so they are taken first.
+// self_skip: mb_type_array[CurrMbAddr] == P_Skip while the trial runs — during the Intra16x16 trial that entry still holds the
+// PREVIOUS picture's type (intra.cpp:1012 clears it only afterwards), and residual.cpp:473,493 then take every neighbour block
+// inside this macroblock as empty. tcl / tcc (shared by the lanes) receive the TotalCoeff of the blocks the trial codes, 0 elsewhere.
+FH_HD int ic_mb_bits(const IcLevels &lv, bool is16, int mb_type, int chroma_mode, const uint8_t prev_flag[16], int cbpl, int cbpc, bool self_skip,
+                     const IcInfo *left, const IcInfo *up, uint8_t tcl[16], uint8_t tcc[2][4], int lane, int nl)
 {
+    for (int v = lane; v < 24; v += nl) {
+        if (v < 16) tcl[v] = (uint8_t)((cbpl >> (v >> 2)) & 1 ? (is16 ? cv_count(lv.ac16[v], 15) : cv_count(lv.luma[v], 16)) : 0);
+        else tcc[(v - 16) >> 2][(v - 16) & 3] = (uint8_t)((cbpc & 2) ? cv_count(lv.cac[(v - 16) >> 2][(v - 16) & 3], 15) : 0);
+    }
+    ic_sync(nl);
+    int head = ic_ue_len(mb_type);
+    if (!is16) for (int k = 0; k < 16; k++) head += prev_flag[k] ? 1 : 4;
+    head += ic_ue_len(chroma_mode);
+    if (!is16) head += ic_ue_len(ic_cbp_intra[(cbpc << 4) | cbpl]);
+    if (!(cbpl > 0 || cbpc > 0 || is16)) return head;
+    head += 1;                                                // mb_qp_delta
     CvBits b;
     cv_init(b, nullptr, 0);                                   // counts only
     int bad = 0;
-    int bits = ic_ue_len(mb_type);
-    if (!is16) for (int k = 0; k < 16; k++) bits += prev_flag[k] ? 1 : 4;
-    bits += ic_ue_len(chroma_mode);
-    if (!is16) bits += ic_ue_len(ic_cbp_intra[(cbpc << 4) | cbpl]);
-    for (int i = 0; i < 16; i++) tcl[i] = 0;
-    for (int i = 0; i < 8; i++) tcc[i >> 2][i & 3] = 0;
-    if (!(cbpl > 0 || cbpc > 0 || is16)) return bits;
-    bits += 1;                                                // mb_qp_delta
-    if (is16) {
-        const int nA = left ? left->tc_luma[5] : -1, nB = up ? up->tc_luma[10] : -1;
-        cv_block(b, lv.dc16, 16, cv_nc(nA, nB), &bad);
+    for (int v = lane; v < 27; v += nl) {
+        if (v == 0) {                                         // Intra16x16DCLevel: neighbours of block 0
+            if (is16) cv_block(b, lv.dc16, 16, cv_nc(left ? left->tc_luma[5] : -1, up ? up->tc_luma[10] : -1), &bad);
+        } else if (v <= 16) {
+            const int blk = v - 1;
+            if (!(cbpl & (1 << (blk >> 2)))) continue;
+            const int bx = ((blk >> 2) & 1) * 2 + (blk & 1), by = (blk >> 3) * 2 + ((blk >> 1) & 1);
+            int nA, nB;
+            if (bx > 0) { const int a = (by >> 1) * 8 + ((bx - 1) >> 1) * 4 + (by & 1) * 2 + ((bx - 1) & 1); nA = self_skip ? 0 : tcl[a]; }
+            else { const int a = (by >> 1) * 8 + 4 + (by & 1) * 2 + 1; nA = left ? left->tc_luma[a] : -1; }
+            if (by > 0) { const int a = ((by - 1) >> 1) * 8 + (bx >> 1) * 4 + ((by - 1) & 1) * 2 + (bx & 1); nB = self_skip ? 0 : tcl[a]; }
+            else { const int a = 8 + (bx >> 1) * 4 + 2 + (bx & 1); nB = up ? up->tc_luma[a] : -1; }
+            if (is16) cv_block(b, lv.ac16[blk], 15, cv_nc(nA, nB), &bad); else cv_block(b, lv.luma[blk], 16, cv_nc(nA, nB), &bad);
+        } else if (v <= 18) {
+            if (cbpc & 3) cv_block(b, lv.cdc[v - 17], 4, -1, &bad);
+        } else {
+            if (!(cbpc & 2)) continue;
+            const int c = (v - 19) >> 2, blk = (v - 19) & 3, bx = blk & 1, by = blk >> 1;
+            const int nA = bx ? (self_skip ? 0 : tcc[c][blk - 1]) : (left ? left->tc_chroma[c][blk + 1] : -1);
+            const int nB = by ? (self_skip ? 0 : tcc[c][blk - 2]) : (up ? up->tc_chroma[c][blk + 2] : -1);
+            cv_block(b, lv.cac[c][blk], 15, cv_nc(nA, nB), &bad);
+        }
     }
-    for (int blk = 0; blk < 16; blk++) {
-        if (!(cbpl & (1 << (blk >> 2)))) continue;
-        const int bx = ((blk >> 2) & 1) * 2 + (blk & 1), by = (blk >> 3) * 2 + ((blk >> 1) & 1);
-        int nA, nB;
-        if (bx > 0) { const int a = (by >> 1) * 8 + ((bx - 1) >> 1) * 4 + (by & 1) * 2 + ((bx - 1) & 1); nA = self_skip ? 0 : tcl[a]; }
-        else { const int a = (by >> 1) * 8 + 4 + (by & 1) * 2 + 1; nA = left ? left->tc_luma[a] : -1; }
-        if (by > 0) { const int a = ((by - 1) >> 1) * 8 + (bx >> 1) * 4 + ((by - 1) & 1) * 2 + (bx & 1); nB = self_skip ? 0 : tcl[a]; }
-        else { const int a = 8 + (bx >> 1) * 4 + 2 + (bx & 1); nB = up ? up->tc_luma[a] : -1; }
-        tcl[blk] = (uint8_t)(is16 ? cv_block(b, lv.ac16[blk], 15, cv_nc(nA, nB), &bad) : cv_block(b, lv.luma[blk], 16, cv_nc(nA, nB), &bad));
-    }
-    if (cbpc & 3) for (int c = 0; c < 2; c++) cv_block(b, lv.cdc[c], 4, -1, &bad);
-    if (cbpc & 2)
-        for (int c = 0; c < 2; c++)
-            for (int blk = 0; blk < 4; blk++) {
-                const int bx = blk & 1, by = blk >> 1;
-                const int nA = bx ? (self_skip ? 0 : tcc[c][blk - 1]) : (left ? left->tc_chroma[c][blk + 1] : -1);
-                const int nB = by ? (self_skip ? 0 : tcc[c][blk - 2]) : (up ? up->tc_chroma[c][blk + 2] : -1);
-                tcc[c][blk] = (uint8_t)cv_block(b, lv.cac[c][blk], 15, cv_nc(nA, nB), &bad);
-            }
-    return bits + cv_bits(b);
+    return head + ic_red_add(cv_bits(b), nl);
 }
 
 // predIntra4x4PredMode of block blk (setIntra4x4PredMode, intra.cpp:877-941): min of the neighbours' modes, DC when a
@@ -500,7 +526,8 @@ FH_HD int ic_pred_mode_of(int blk, const uint8_t mine[16], const IcInfo *left, c
 // c: picture pointers, W, H, xP, yP, qp set by the caller (shared by the lanes). prev_skip: this macroblock was P_Skip in the
 // previous picture. left / up: state of the neighbouring macroblocks of THIS picture (null outside the picture); the macroblock
 // above-right must be complete as well (its reconstruction feeds the Intra4x4 above-right samples). Writes the reconstruction
-// into c.rec; out and info are written by lane 0. Called by lanes 0 .. nl-1 of a warp (nl = 32), or by one lane with nl = 1.
+// into c.rec. Called by lanes 0 .. nl-1 of a warp (nl = 32), or by one lane with nl = 1. Only the block-by-block Intra4x4 coding,
+// whose blocks depend on each other, and the small DC transforms run on lane 0 alone.
 FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcInfo *up, fh264_mb_result_i &out, IcInfo &info, int lane, int nl)
 {
     const int W = c.W, CW = c.W >> 1, xP = c.xP, yP = c.yP;
@@ -526,6 +553,7 @@ FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcI
         const int satd = ic_red_add(part[m], nl);
         if (ic_mode16_allowed(m, p16) && satd < min16) { min16 = satd; mode16 = m; }
     }
+    const int chroma_mode = ic_chroma_of_16[mode16];
     // Intra4x4 mode search on the macroblock as it stands: neighbours inside it are still SOURCE samples (intra.cpp:1011-1049).
     // 16 blocks x 9 modes spread over the lanes; the smallest (cost, mode) pair is the first mode reaching the minimum.
     int best[16];
@@ -540,81 +568,82 @@ FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcI
         if (key < best[blk]) best[blk] = key;
     }
     for (int b = 0; b < 16; b++) best[b] = ic_red_min(best[b], nl);
+
+    // predictions of the chosen Intra16x16 / chroma modes, then the first trial: the macroblock as Intra16x16 (intra.cpp:1003-1008)
+    for (int v = lane; v < 18; v += nl) {
+        if (v < 16) {
+            int pb[16];
+            ic_pred16_block(mode16, p16, v, pb);
+            const int x0 = ic_blkx(v), y0 = ic_blky(v);
+            for (int i = 0; i < 16; i++) c.pred16[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] = (uint8_t)pb[i];
+        } else ic_pred_chroma(c, v - 16, chroma_mode, c.predC[v - 16]);
+    }
     ic_sync(nl);
-
+    for (int v = lane; v < 24; v += nl) ic_forward_unit(c, v);
+    ic_sync(nl);
     if (lane == 0) {
-        uint8_t pred16[256], predC[2][64];
-        ic_pred16(mode16, p16, pred16);
-        const int chroma_mode = ic_chroma_of_16[mode16];
-        ic_pred_chroma(c, 0, chroma_mode, predC[0]);
-        ic_pred_chroma(c, 1, chroma_mode, predC[1]);
+        ic_forward_dcs(c);
+        ic_cbp(true, c.lv, c.cbpl16, c.cbpc);
+        c.type16 = mode16 + 1 + (c.cbpc << 2) + (c.cbpl16 == 15 ? 12 : 0);
+    }
+    ic_sync(nl);
+    const int bits16 = ic_mb_bits(c.lv, true, c.type16, chroma_mode, nullptr, c.cbpl16, c.cbpc, prev_skip, left, up, c.tcl[0], c.tcc[0], lane, nl);
 
-        // first trial: the macroblock as Intra16x16 (intra.cpp:1008)
-        IcLevels lv;
-        uint8_t tcl16[16], tcc16[2][4], tcl4[16], tcc4[2][4];
-        int cbpl16, cbpl4, cbpc, cbpc4;
-        ic_tq_luma16(c, pred16, lv, false);
-        ic_tq_chroma(c, 0, predC[0], lv, nullptr);
-        ic_tq_chroma(c, 1, predC[1], lv, nullptr);
-        ic_cbp(true, lv, cbpl16, cbpc);
-        const int type16 = mode16 + 1 + (cbpc << 2) + (cbpl16 == 15 ? 12 : 0);
-        const int bits16 = ic_mb_bits(true, type16, chroma_mode, nullptr, lv, cbpl16, cbpc, prev_skip, left, up, tcl16, tcc16);
-
-        // code the blocks one by one with the modes found; each reconstruction feeds the next prediction (intra.cpp:1063-1086)
-        uint8_t mode4[16], flag[16], rem[16];
-        for (int blk = 0; blk < 16; blk++) mode4[blk] = (uint8_t)(best[blk] & 15);
+    // code the blocks one by one with the modes found; each reconstruction feeds the next prediction (intra.cpp:1063-1086)
+    if (lane == 0) {
+        for (int blk = 0; blk < 16; blk++) c.mode4[blk] = (uint8_t)(best[blk] & 15);
         for (int blk = 0; blk < 16; blk++) {
-            const int pm = ic_pred_mode_of(blk, mode4, left, up);
-            flag[blk] = mode4[blk] == pm;
-            rem[blk] = (uint8_t)(mode4[blk] < pm ? mode4[blk] : mode4[blk] - 1);
+            const int pm = ic_pred_mode_of(blk, c.mode4, left, up);
+            c.flag[blk] = c.mode4[blk] == pm;
+            c.rem[blk] = (uint8_t)(c.mode4[blk] < pm ? c.mode4[blk] : c.mode4[blk] - 1);
             int p[13], pb[16], diff[16], r[16], d[16], rr[16];
             ic_fetch4(c, blk, p);
-            ic_pred4(mode4[blk], p, pb);
+            ic_pred4(c.mode4[blk], p, pb);
             const int x0 = ic_blkx(blk), y0 = ic_blky(blk);
             for (int i = 0; i < 16; i++) diff[i] = (int)c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] - pb[i];
             ic_forward_residual(diff, r, c.qp, false);
-            for (int k = 0; k < 16; k++) lv.luma[blk][k] = (int16_t)r[ic_ZZ[k]];
+            for (int k = 0; k < 16; k++) c.lv.luma[blk][k] = (int16_t)r[ic_ZZ[k]];
             ic_dequant4x4(r, d, c.qp, false);
             ic_inverse4x4(d, rr);
             for (int i = 0; i < 16; i++) c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] = (uint8_t)ic_clip255(pb[i] + rr[i]);
         }
-        // second trial: Intra4x4 (intra.cpp:1088)
-        ic_cbp(false, lv, cbpl4, cbpc4);
-        const int bits4 = ic_mb_bits(false, 0, chroma_mode, flag, lv, cbpl4, cbpc4, false, left, up, tcl4, tcc4);
-        const bool use4 = bits4 < bits16;
-        if (!use4) {
-            for (int i = 0; i < 256; i++) c.L[i] = c.S[i];          // restore the source, code as Intra16x16 (intra.cpp:1095-1106)
-            ic_tq_luma16(c, pred16, lv, true);
-        }
-        ic_tq_chroma(c, 0, predC[0], lv, c.RC[0]);
-        ic_tq_chroma(c, 1, predC[1], lv, c.RC[1]);
-
-        out.mb_type = (int16_t)(use4 ? 0 : type16);
-        out.intra16x16_pred_mode = (int8_t)(use4 ? -1 : mode16);
-        out.intra_chroma_pred_mode = (uint8_t)chroma_mode;
-        out.cbp_luma = (uint8_t)(use4 ? cbpl4 : cbpl16);
-        out.cbp_chroma = (uint8_t)cbpc;
-        out.bits_intra16x16 = (uint16_t)bits16;
-        out.bits_intra4x4 = (uint16_t)bits4;
-        for (int i = 0; i < 16; i++) { out.intra4x4_pred_mode[i] = mode4[i]; out.prev_intra4x4_pred_mode_flag[i] = flag[i]; out.rem_intra4x4_pred_mode[i] = rem[i]; }
-        int16_t *ol = &out.luma[0][0];
-        if (use4) for (int i = 0; i < 256; i++) ol[i] = lv.luma[i >> 4][i & 15];
-        else {
-            for (int k = 0; k < 16; k++) ol[k] = lv.dc16[k];
-            for (int b = 0; b < 16; b++) for (int k = 0; k < 15; k++) ol[16 + b * 15 + k] = lv.ac16[b][k];
-        }
-        for (int k = 0; k < 2; k++) {
-            for (int i = 0; i < 4; i++) out.chroma_dc[k][i] = lv.cdc[k][i];
-            for (int b = 0; b < 4; b++) for (int i = 0; i < 15; i++) out.chroma_ac[k][b][i] = lv.cac[k][b][i];
-        }
-        out.reserved[0] = out.reserved[1] = out.reserved[2] = 0;
-
-        info.mb_type = (uint8_t)out.mb_type; info.cbp_luma = out.cbp_luma; info.cbp_chroma = out.cbp_chroma; info.is4x4 = use4;
-        for (int i = 0; i < 16; i++) { info.tc_luma[i] = use4 ? tcl4[i] : tcl16[i]; info.mode4[i] = mode4[i]; }
-        for (int i = 0; i < 8; i++) info.tc_chroma[i >> 2][i & 3] = use4 ? tcc4[i >> 2][i & 3] : tcc16[i >> 2][i & 3];
-        info.pad[0] = info.pad[1] = info.pad[2] = info.pad[3] = 0;
+        int cbpc4;
+        ic_cbp(false, c.lv, c.cbpl4, cbpc4);            // the chroma levels are the first trial's: same CodedBlockPatternChroma
     }
     ic_sync(nl);
+    // second trial: Intra4x4 (intra.cpp:1088), then the decision
+    const int bits4 = ic_mb_bits(c.lv, false, 0, chroma_mode, c.flag, c.cbpl4, c.cbpc, false, left, up, c.tcl[1], c.tcc[1], lane, nl);
+    const bool use4 = bits4 < bits16;
+    if (!use4) for (int i = lane; i < 256; i += nl) c.L[i] = c.S[i];       // restore the source, code as Intra16x16 (intra.cpp:1095-1106)
+    if (lane == 0) ic_inverse_dcs(c, !use4);
+    ic_sync(nl);
+    for (int v = lane + (use4 ? 16 : 0); v < 24; v += nl) ic_inverse_unit(c, v);
+    ic_sync(nl);
+
+    // results
+    int16_t *ol = &out.luma[0][0];
+    if (use4) for (int i = lane; i < 256; i += nl) ol[i] = c.lv.luma[i >> 4][i & 15];
+    else for (int i = lane; i < 256; i += nl) ol[i] = i < 16 ? c.lv.dc16[i] : c.lv.ac16[(i - 16) / 15][(i - 16) % 15];
+    for (int i = lane; i < 128; i += nl) {
+        if (i < 8) out.chroma_dc[i >> 2][i & 3] = c.lv.cdc[i >> 2][i & 3];
+        else out.chroma_ac[(i - 8) / 60][((i - 8) % 60) / 15][(i - 8) % 15] = c.lv.cac[(i - 8) / 60][((i - 8) % 60) / 15][(i - 8) % 15];
+    }
+    if (lane == 0) {
+        out.mb_type = (int16_t)(use4 ? 0 : c.type16);
+        out.intra16x16_pred_mode = (int8_t)(use4 ? -1 : mode16);
+        out.intra_chroma_pred_mode = (uint8_t)chroma_mode;
+        out.cbp_luma = (uint8_t)(use4 ? c.cbpl4 : c.cbpl16);
+        out.cbp_chroma = (uint8_t)c.cbpc;
+        out.bits_intra16x16 = (uint16_t)bits16;
+        out.bits_intra4x4 = (uint16_t)bits4;
+        for (int i = 0; i < 16; i++) { out.intra4x4_pred_mode[i] = c.mode4[i]; out.prev_intra4x4_pred_mode_flag[i] = c.flag[i]; out.rem_intra4x4_pred_mode[i] = c.rem[i]; }
+        out.reserved[0] = out.reserved[1] = out.reserved[2] = 0;
+        info.mb_type = (uint8_t)out.mb_type; info.cbp_luma = out.cbp_luma; info.cbp_chroma = out.cbp_chroma; info.is4x4 = use4;
+        const int t = use4 ? 1 : 0;
+        for (int i = 0; i < 16; i++) { info.tc_luma[i] = c.tcl[t][i]; info.mode4[i] = c.mode4[i]; }
+        for (int i = 0; i < 8; i++) info.tc_chroma[i >> 2][i & 3] = c.tcc[t][i >> 2][i & 3];
+        info.pad[0] = info.pad[1] = info.pad[2] = info.pad[3] = 0;
+    }
     for (int i = lane; i < 256; i += nl) c.rec[0][(size_t)(yP + (i >> 4)) * W + xP + (i & 15)] = c.L[i];
     for (int i = lane; i < 128; i += nl) c.rec[1 + (i >> 6)][(size_t)((yP >> 1) + ((i & 63) >> 3)) * CW + (xP >> 1) + (i & 7)] = c.RC[i >> 6][i & 63];
 }

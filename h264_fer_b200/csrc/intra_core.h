@@ -27,6 +27,7 @@ FH_HD int ic_red_min(int v, int) { return v; }
 FH_TAB int16_t ic_LQ[6][3] = { { 205, 158, 128 }, { 186, 146, 114 }, { 158, 128, 102 }, { 146, 114, 89 }, { 128, 102, 82 }, { 114, 89, 71 } };   // LevelQuantize by (row & 1) + (col & 1), quantizationTransform.cpp:24-32
 FH_TAB int16_t ic_LS[6][3] = { { 160, 208, 256 }, { 176, 224, 288 }, { 208, 256, 320 }, { 224, 288, 368 }, { 256, 320, 400 }, { 288, 368, 464 } };   // LevelScale, scaleTransform.cpp:32-40
 FH_TAB uint8_t ic_ZZ[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };           // zigzag: scan position -> row * 4 + col (scaleTransform.cpp:43-47)
+FH_TAB uint8_t ic_ZZI[16] = { 0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15 };          // row * 4 + col -> scan position
 FH_TAB uint8_t ic_QPC[52] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30,
                               31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39 };                              // inttransform.cpp:8-14
 // coded_block_pattern -> codeNum for Intra macroblocks (Table 9-4, ChromaArrayType 1; h264_globals.cpp:155)
@@ -71,6 +72,7 @@ struct IcCtx {
     uint8_t tcl[2][16], tcc[2][2][4];   // TotalCoeff of the coded blocks, [0] Intra16x16 trial, [1] Intra4x4 trial
     uint8_t mode4[16], flag[16], rem[16];
     int cbpl16, cbpl4, cbpc, type16;
+    int w0[16], w1[16], pb[16]; // one Intra4x4 block in flight: residual / coefficients, intermediate, prediction
 };
 
 FH_HD int ic_abs(int a) { return a < 0 ? -a : a; }
@@ -102,23 +104,25 @@ FH_HD void ic_forward4x4(const int r[16], int d[16])
     for (int j = 0; j < 4; j++) ic_fwd4(h[j], h[4 + j], h[8 + j], h[12 + j], f[j], f[4 + j], f[8 + j], f[12 + j]);
     for (int i = 0; i < 4; i++) ic_fwd4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3], d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
 }
+FH_HD int ic_quant1(int d, int i, int qP)                 // coefficient i = row * 4 + col
+{
+    const int per = qP / 6, lq = ic_LQ[qP % 6][((i >> 2) & 1) + (i & 1)];
+    const int t = qP < 24 ? (d * (1 << (4 - per)) - (1 << (3 - per))) * lq : (d >> (per - 4)) * lq;
+    return (t + 16384) >> 15;
+}
+FH_HD int ic_dequant1(int c, int i, int qP)
+{
+    const int per = qP / 6, ls = ic_LS[qP % 6][((i >> 2) & 1) + (i & 1)];
+    return qP >= 24 ? (c * ls) * (1 << (per - 4)) : (c * ls + (1 << (3 - per))) >> (4 - per);
+}
 FH_HD void ic_quant4x4(const int d[16], int c[16], int qP, bool keep_dc)
 {
-    const int per = qP / 6, rem = qP % 6;
-    for (int i = 0; i < 16; i++) {
-        const int lq = ic_LQ[rem][((i >> 2) & 1) + (i & 1)];
-        const int t = qP < 24 ? (d[i] * (1 << (4 - per)) - (1 << (3 - per))) * lq : (d[i] >> (per - 4)) * lq;
-        c[i] = (t + 16384) >> 15;
-    }
+    for (int i = 0; i < 16; i++) c[i] = ic_quant1(d[i], i, qP);
     if (keep_dc) c[0] = d[0];
 }
 FH_HD void ic_dequant4x4(const int c[16], int d[16], int qP, bool keep_dc)
 {
-    const int per = qP / 6, rem = qP % 6;
-    for (int i = 0; i < 16; i++) {
-        const int ls = ic_LS[rem][((i >> 2) & 1) + (i & 1)];
-        d[i] = qP >= 24 ? (c[i] * ls) * (1 << (per - 4)) : (c[i] * ls + (1 << (3 - per))) >> (4 - per);
-    }
+    for (int i = 0; i < 16; i++) d[i] = ic_dequant1(c[i], i, qP);
     if (keep_dc) d[0] = c[0];
 }
 FH_HD void ic_inverse4x4(const int d[16], int r[16])
@@ -213,60 +217,61 @@ FH_HD int ic_f2(int a, int b) { return (a + b + 1) >> 1; }
 // p(x, -1) for x = -1 .. 7 and p(-1, y) for y = -1 .. 3 with the corner shared
 FH_HD int ic_top(const int p[13], int x) { return x < 0 ? p[0] : p[x + 5]; }
 FH_HD int ic_left(const int p[13], int y) { return y < 0 ? p[0] : p[y + 1]; }
+FH_HD int ic_pred4_px(int mode, const int p[13], int x, int y)
+{
+    int v;
+    switch (mode) {
+    case 0: v = IC_T(x); break;                                                                         // vertical
+    case 1: v = IC_L(y); break;                                                                         // horizontal
+    case 2:                                                                                            // DC (intra.cpp:168-186: the corner decides "both available")
+        if (IC_C != -1) v = (IC_T(0) + IC_T(1) + IC_T(2) + IC_T(3) + IC_L(0) + IC_L(1) + IC_L(2) + IC_L(3) + 4) >> 3;
+        else if (IC_L(0) != -1) v = (IC_L(0) + IC_L(1) + IC_L(2) + IC_L(3) + 2) >> 2;
+        else if (IC_T(0) != -1) v = (IC_T(0) + IC_T(1) + IC_T(2) + IC_T(3) + 2) >> 2;
+        else v = 128;
+        break;
+    case 3:                                                                                            // diagonal down-left
+        v = (x == 3 && y == 3) ? (IC_T(6) + 3 * IC_T(7) + 2) >> 2 : ic_f3(IC_T(x + y), IC_T(x + y + 1), IC_T(x + y + 2));
+        break;
+    case 4:                                                                                            // diagonal down-right
+        if (x > y) v = ic_f3(ic_top(p, x - y - 2), ic_top(p, x - y - 1), ic_top(p, x - y));
+        else if (x < y) v = ic_f3(ic_left(p, y - x - 2), ic_left(p, y - x - 1), ic_left(p, y - x));
+        else v = ic_f3(IC_T(0), IC_C, IC_L(0));
+        break;
+    case 5: {                                                                                          // vertical-right
+        const int z = 2 * x - y, i = x - (y >> 1);
+        if (z >= 0 && !(z & 1)) v = ic_f2(ic_top(p, i - 1), ic_top(p, i));
+        else if (z >= 0) v = ic_f3(ic_top(p, i - 2), ic_top(p, i - 1), ic_top(p, i));
+        else if (z == -1) v = ic_f3(IC_L(0), IC_C, IC_T(0));
+        else v = ic_f3(ic_left(p, y - 1), ic_left(p, y - 2), ic_left(p, y - 3));
+        break;
+    }
+    case 6: {                                                                                          // horizontal-down
+        const int z = 2 * y - x, i = y - (x >> 1);
+        if (z >= 0 && !(z & 1)) v = ic_f2(ic_left(p, i - 1), ic_left(p, i));
+        else if (z >= 0) v = ic_f3(ic_left(p, i - 2), ic_left(p, i - 1), ic_left(p, i));
+        else if (z == -1) v = ic_f3(IC_L(0), IC_C, IC_T(0));
+        else v = ic_f3(ic_top(p, x - 1), ic_top(p, x - 2), ic_top(p, x - 3));
+        break;
+    }
+    case 7: {                                                                                          // vertical-left
+        const int i = x + (y >> 1);
+        v = (y & 1) ? ic_f3(IC_T(i), IC_T(i + 1), IC_T(i + 2)) : ic_f2(IC_T(i), IC_T(i + 1));
+        break;
+    }
+    default: {                                                                                         // horizontal-up
+        const int z = x + 2 * y, i = y + (x >> 1);
+        if (z > 5) v = IC_L(3);
+        else if (z == 5) v = (IC_L(2) + 3 * IC_L(3) + 2) >> 2;
+        else if (z & 1) v = ic_f3(IC_L(i), IC_L(i + 1), IC_L(i + 2));
+        else v = ic_f2(IC_L(i), IC_L(i + 1));
+        break;
+    }
+    }
+    return v;
+}
 FH_HD void ic_pred4(int mode, const int p[13], int o[16])
 {
-    for (int y = 0; y < 4; y++)
-        for (int x = 0; x < 4; x++) {
-            int v;
-            switch (mode) {
-            case 0: v = IC_T(x); break;                                                                         // vertical
-            case 1: v = IC_L(y); break;                                                                         // horizontal
-            case 2:                                                                                            // DC (intra.cpp:168-186: the corner decides "both available")
-                if (IC_C != -1) v = (IC_T(0) + IC_T(1) + IC_T(2) + IC_T(3) + IC_L(0) + IC_L(1) + IC_L(2) + IC_L(3) + 4) >> 3;
-                else if (IC_L(0) != -1) v = (IC_L(0) + IC_L(1) + IC_L(2) + IC_L(3) + 2) >> 2;
-                else if (IC_T(0) != -1) v = (IC_T(0) + IC_T(1) + IC_T(2) + IC_T(3) + 2) >> 2;
-                else v = 128;
-                break;
-            case 3:                                                                                            // diagonal down-left
-                v = (x == 3 && y == 3) ? (IC_T(6) + 3 * IC_T(7) + 2) >> 2 : ic_f3(IC_T(x + y), IC_T(x + y + 1), IC_T(x + y + 2));
-                break;
-            case 4:                                                                                            // diagonal down-right
-                if (x > y) v = ic_f3(ic_top(p, x - y - 2), ic_top(p, x - y - 1), ic_top(p, x - y));
-                else if (x < y) v = ic_f3(ic_left(p, y - x - 2), ic_left(p, y - x - 1), ic_left(p, y - x));
-                else v = ic_f3(IC_T(0), IC_C, IC_L(0));
-                break;
-            case 5: {                                                                                          // vertical-right
-                const int z = 2 * x - y, i = x - (y >> 1);
-                if (z >= 0 && !(z & 1)) v = ic_f2(ic_top(p, i - 1), ic_top(p, i));
-                else if (z >= 0) v = ic_f3(ic_top(p, i - 2), ic_top(p, i - 1), ic_top(p, i));
-                else if (z == -1) v = ic_f3(IC_L(0), IC_C, IC_T(0));
-                else v = ic_f3(ic_left(p, y - 1), ic_left(p, y - 2), ic_left(p, y - 3));
-                break;
-            }
-            case 6: {                                                                                          // horizontal-down
-                const int z = 2 * y - x, i = y - (x >> 1);
-                if (z >= 0 && !(z & 1)) v = ic_f2(ic_left(p, i - 1), ic_left(p, i));
-                else if (z >= 0) v = ic_f3(ic_left(p, i - 2), ic_left(p, i - 1), ic_left(p, i));
-                else if (z == -1) v = ic_f3(IC_L(0), IC_C, IC_T(0));
-                else v = ic_f3(ic_top(p, x - 1), ic_top(p, x - 2), ic_top(p, x - 3));
-                break;
-            }
-            case 7: {                                                                                          // vertical-left
-                const int i = x + (y >> 1);
-                v = (y & 1) ? ic_f3(IC_T(i), IC_T(i + 1), IC_T(i + 2)) : ic_f2(IC_T(i), IC_T(i + 1));
-                break;
-            }
-            default: {                                                                                         // horizontal-up
-                const int z = x + 2 * y, i = y + (x >> 1);
-                if (z > 5) v = IC_L(3);
-                else if (z == 5) v = (IC_L(2) + 3 * IC_L(3) + 2) >> 2;
-                else if (z & 1) v = ic_f3(IC_L(i), IC_L(i + 1), IC_L(i + 2));
-                else v = ic_f2(IC_L(i), IC_L(i + 1));
-                break;
-            }
-            }
-            o[y * 4 + x] = v;
-        }
+    for (int i = 0; i < 16; i++) o[i] = ic_pred4_px(mode, p, i & 3, i >> 2);
 }
 // a mode is tried only when the samples it is defined on exist (intra.cpp:1022-1033)
 FH_HD bool ic_mode4_allowed(int mode, const int p[13])
@@ -526,8 +531,8 @@ FH_HD int ic_pred_mode_of(int blk, const uint8_t mine[16], const IcInfo *left, c
 // c: picture pointers, W, H, xP, yP, qp set by the caller (shared by the lanes). prev_skip: this macroblock was P_Skip in the
 // previous picture. left / up: state of the neighbouring macroblocks of THIS picture (null outside the picture); the macroblock
 // above-right must be complete as well (its reconstruction feeds the Intra4x4 above-right samples). Writes the reconstruction
-// into c.rec. Called by lanes 0 .. nl-1 of a warp (nl = 32), or by one lane with nl = 1. Only the block-by-block Intra4x4 coding,
-// whose blocks depend on each other, and the small DC transforms run on lane 0 alone.
+// into c.rec. Called by lanes 0 .. nl-1 of a warp (nl = 32), or by one lane with nl = 1. The blocks of the Intra4x4 coding
+// depend on each other and are taken one after the other (16 lanes per block); the small DC transforms run on lane 0 alone.
 FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcInfo *up, fh264_mb_result_i &out, IcInfo &info, int lane, int nl)
 {
     const int W = c.W, CW = c.W >> 1, xP = c.xP, yP = c.yP;
@@ -589,24 +594,50 @@ FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcI
     ic_sync(nl);
     const int bits16 = ic_mb_bits(c.lv, true, c.type16, chroma_mode, nullptr, c.cbpl16, c.cbpc, prev_skip, left, up, c.tcl[0], c.tcc[0], lane, nl);
 
-    // code the blocks one by one with the modes found; each reconstruction feeds the next prediction (intra.cpp:1063-1086)
-    if (lane == 0) {
-        for (int blk = 0; blk < 16; blk++) c.mode4[blk] = (uint8_t)(best[blk] & 15);
-        for (int blk = 0; blk < 16; blk++) {
-            const int pm = ic_pred_mode_of(blk, c.mode4, left, up);
-            c.flag[blk] = c.mode4[blk] == pm;
-            c.rem[blk] = (uint8_t)(c.mode4[blk] < pm ? c.mode4[blk] : c.mode4[blk] - 1);
-            int p[13], pb[16], diff[16], r[16], d[16], rr[16];
-            ic_fetch4(c, blk, p);
-            ic_pred4(c.mode4[blk], p, pb);
-            const int x0 = ic_blkx(blk), y0 = ic_blky(blk);
-            for (int i = 0; i < 16; i++) diff[i] = (int)c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] - pb[i];
-            ic_forward_residual(diff, r, c.qp, false);
-            for (int k = 0; k < 16; k++) c.lv.luma[blk][k] = (int16_t)r[ic_ZZ[k]];
-            ic_dequant4x4(r, d, c.qp, false);
-            ic_inverse4x4(d, rr);
-            for (int i = 0; i < 16; i++) c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] = (uint8_t)ic_clip255(pb[i] + rr[i]);
+    // code the blocks one by one with the modes found; each reconstruction feeds the next prediction (intra.cpp:1063-1086).
+    // The blocks are serial, the 16 samples / coefficients of a block are not: one lane each, the 4x4 butterflies one row or
+    // column per lane, the stages separated by warp barriers.
+    for (int blk = lane; blk < 16; blk += nl) c.mode4[blk] = (uint8_t)(best[blk] & 15);
+    ic_sync(nl);
+    for (int blk = lane; blk < 16; blk += nl) {
+        const int pm = ic_pred_mode_of(blk, c.mode4, left, up);
+        c.flag[blk] = c.mode4[blk] == pm;
+        c.rem[blk] = (uint8_t)(c.mode4[blk] < pm ? c.mode4[blk] : c.mode4[blk] - 1);
+    }
+    for (int blk = 0; blk < 16; blk++) {
+        const int x0 = ic_blkx(blk), y0 = ic_blky(blk), mode = c.mode4[blk];
+        int p[13];
+        ic_fetch4(c, blk, p);
+        for (int i = lane; i < 16; i += nl) {
+            const int pv = ic_pred4_px(mode, p, i & 3, i >> 2), r = (int)c.L[(y0 + (i >> 2)) * 16 + x0 + (i & 3)] - pv;
+            c.pb[i] = pv;
+            c.w0[i] = r == 0 ? 0 : r * 64 - 32;                                   // forwardTransform4x4's input scaling
         }
+        ic_sync(nl);
+        for (int j = lane; j < 4; j += nl) ic_fwd4(c.w0[j], c.w0[4 + j], c.w0[8 + j], c.w0[12 + j], c.w1[j], c.w1[4 + j], c.w1[8 + j], c.w1[12 + j]);
+        ic_sync(nl);
+        for (int i = lane; i < 4; i += nl) ic_fwd4(c.w1[4 * i], c.w1[4 * i + 1], c.w1[4 * i + 2], c.w1[4 * i + 3], c.w0[4 * i], c.w0[4 * i + 1], c.w0[4 * i + 2], c.w0[4 * i + 3]);
+        ic_sync(nl);
+        for (int i = lane; i < 16; i += nl) {
+            const int q = ic_quant1(c.w0[i], i, c.qp);
+            c.lv.luma[blk][ic_ZZI[i]] = (int16_t)q;
+            c.w1[i] = ic_dequant1(q, i, c.qp);
+        }
+        ic_sync(nl);
+        for (int i = lane; i < 4; i += nl) {                                      // inverseTransform4x4: rows, then columns
+            const int *q = c.w1 + 4 * i;
+            const int e0 = q[0] + q[2], e1 = q[0] - q[2], e2 = (q[1] >> 1) - q[3], e3 = q[1] + (q[3] >> 1);
+            c.w0[4 * i] = e0 + e3; c.w0[4 * i + 1] = e1 + e2; c.w0[4 * i + 2] = e1 - e2; c.w0[4 * i + 3] = e0 - e3;
+        }
+        ic_sync(nl);
+        for (int j = lane; j < 4; j += nl) {
+            const int g0 = c.w0[j] + c.w0[8 + j], g1 = c.w0[j] - c.w0[8 + j], g2 = (c.w0[4 + j] >> 1) - c.w0[12 + j], g3 = c.w0[4 + j] + (c.w0[12 + j] >> 1);
+            const int h[4] = { g0 + g3, g1 + g2, g1 - g2, g0 - g3 };
+            for (int y = 0; y < 4; y++) c.L[(y0 + y) * 16 + x0 + j] = (uint8_t)ic_clip255(c.pb[4 * y + j] + ((h[y] + 32) >> 6));
+        }
+        ic_sync(nl);
+    }
+    if (lane == 0) {
         int cbpc4;
         ic_cbp(false, c.lv, c.cbpl4, cbpc4);            // the chroma levels are the first trial's: same CodedBlockPatternChroma
     }

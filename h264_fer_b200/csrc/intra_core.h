@@ -63,6 +63,8 @@ struct IcCtx {
     uint8_t L[256];             // `frame.L` inside this macroblock: source, overwritten block by block by the Intra4x4 reconstruction
     uint8_t SC[2][64];          // source chroma
     uint8_t RC[2][64];          // reconstructed chroma
+    uint8_t nbT[24], nbL[16];   // luma samples around the macroblock, fetched once: row above x = -1 .. 19 (nbT[x + 1]), left column
+    uint8_t nbC[2][20];         // chroma: [0] corner, [1..8] left column, [9..16] row above
     uint8_t pred16[256];        // Intra16x16 prediction of the chosen mode
     uint8_t predC[2][64];       // chroma prediction
     IcLevels lv;
@@ -81,12 +83,33 @@ FH_HD int ic_blkx(int b) { return ((b & 1) << 2) | ((b & 4) << 1); }      // Int
 FH_HD int ic_blky(int b) { return ((b & 2) << 1) | (b & 8); }
 FH_HD int ic_ue_len(int v) { return 2 * cv_ilog2((uint32_t)v + 1u) + 1; }  // expgolomb_UC_codes[v][0] * 2 + 1 (expgolomb.cpp:8-40)
 
-// `frame.L` at absolute (x, y): inside the current macroblock its working copy, elsewhere the reconstruction
+// `frame.L` at absolute (x, y) (inside the picture): inside the current macroblock its working copy, elsewhere the reconstruction
+// of the macroblocks coded before — only the row above and the column to the left are ever asked for, and those were staged
+// by ic_stage_neighbours
 FH_HD int ic_px(const IcCtx &c, int x, int y)
 {
     const int lx = x - c.xP, ly = y - c.yP;
-    if ((unsigned)lx < 16u && (unsigned)ly < 16u) return c.L[ly * 16 + lx];
-    return c.rec[0][(size_t)y * c.W + x];
+    if (ly < 0) return c.nbT[lx + 1];
+    if (lx < 0) return c.nbL[ly];
+    return c.L[ly * 16 + lx];
+}
+// one read of every reconstructed sample the macroblock predicts from (spread over the lanes; the caller synchronises)
+FH_HD void ic_stage_neighbours(IcCtx &c, int lane, int nl)
+{
+    const int W = c.W, CW = c.W >> 1, xP = c.xP, yP = c.yP, xM = xP >> 1, yM = yP >> 1;
+    for (int i = lane; i < 21 + 16 + 34; i += nl) {
+        if (i < 21) { const int x = xP - 1 + i; c.nbT[i] = (yP > 0 && x >= 0 && x < W) ? c.rec[0][(size_t)(yP - 1) * W + x] : 0; }
+        else if (i < 37) c.nbL[i - 21] = xP > 0 ? c.rec[0][(size_t)(yP + i - 21) * W + xP - 1] : 0;
+        else {
+            const int k = (i - 37) / 17, j = (i - 37) % 17;
+            const uint8_t *r = c.rec[1 + k];
+            int v = 0;
+            if (j == 0) { if (xM > 0 && yM > 0) v = r[(size_t)(yM - 1) * CW + xM - 1]; }
+            else if (j <= 8) { if (xM > 0) v = r[(size_t)(yM + j - 1) * CW + xM - 1]; }
+            else if (yM > 0) v = r[(size_t)(yM - 1) * CW + xM + j - 9];
+            c.nbC[k][j] = (uint8_t)v;
+        }
+    }
 }
 
 // ---- transform / quantisation (quantizationTransform.cpp:41-100,183-223; scaleTransform.cpp:101-150,308-340) ----------------
@@ -300,9 +323,9 @@ FH_HD int ic_satd4(const IcCtx &c, int blk, const int pred[16])
 FH_HD void ic_fetch16(const IcCtx &c, int p[33])
 {
     const int xP = c.xP, yP = c.yP;
-    p[0] = (xP > 0 && yP > 0) ? c.rec[0][(size_t)(yP - 1) * c.W + xP - 1] : -1;
-    for (int i = 0; i < 16; i++) p[1 + i] = xP > 0 ? c.rec[0][(size_t)(yP + i) * c.W + xP - 1] : -1;
-    for (int i = 0; i < 16; i++) p[17 + i] = yP > 0 ? c.rec[0][(size_t)(yP - 1) * c.W + xP + i] : -1;
+    p[0] = (xP > 0 && yP > 0) ? c.nbT[0] : -1;
+    for (int i = 0; i < 16; i++) p[1 + i] = xP > 0 ? c.nbL[i] : -1;
+    for (int i = 0; i < 16; i++) p[17 + i] = yP > 0 ? c.nbT[1 + i] : -1;
 }
 FH_HD void ic_pred16(int mode, const int p[33], uint8_t o[256])
 {
@@ -356,12 +379,11 @@ FH_HD bool ic_mode16_allowed(int mode, const int p[33]) { return mode == 0 ? p[1
 // ---- chroma prediction (intra.cpp:562-790): p[0] corner, p[1..8] left column, p[9..16] row above -----------------------------
 FH_HD void ic_pred_chroma(const IcCtx &c, int comp, int mode, uint8_t o[64])
 {
-    const int CW = c.W >> 1, xM = c.xP >> 1, yM = c.yP >> 1;
-    const uint8_t *r = c.rec[1 + comp];
+    const int xM = c.xP >> 1, yM = c.yP >> 1;
     int p[17];
-    p[0] = (xM > 0 && yM > 0) ? r[(size_t)(yM - 1) * CW + xM - 1] : -1;
-    for (int i = 0; i < 8; i++) p[1 + i] = xM > 0 ? r[(size_t)(yM + i) * CW + xM - 1] : -1;
-    for (int i = 0; i < 8; i++) p[9 + i] = yM > 0 ? r[(size_t)(yM - 1) * CW + xM + i] : -1;
+    p[0] = (xM > 0 && yM > 0) ? c.nbC[comp][0] : -1;
+    for (int i = 0; i < 8; i++) p[1 + i] = xM > 0 ? c.nbC[comp][1 + i] : -1;
+    for (int i = 0; i < 8; i++) p[9 + i] = yM > 0 ? c.nbC[comp][9 + i] : -1;
     if (mode == 1) { for (int i = 0; i < 64; i++) o[i] = (uint8_t)p[1 + (i >> 3)]; return; }
     if (mode == 2) { for (int i = 0; i < 64; i++) o[i] = (uint8_t)p[9 + (i & 7)]; return; }
     if (mode == 0) {
@@ -539,6 +561,7 @@ FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcI
     if (lane == 0) c.qpc = ic_QPC[c.qp < 0 ? 0 : (c.qp > 51 ? 51 : c.qp)];
     for (int i = lane; i < 256; i += nl) c.S[i] = c.L[i] = c.src[0][(size_t)(yP + (i >> 4)) * W + xP + (i & 15)];
     for (int i = lane; i < 128; i += nl) c.SC[i >> 6][i & 63] = c.src[1 + (i >> 6)][(size_t)((yP >> 1) + ((i & 63) >> 3)) * CW + (xP >> 1) + (i & 7)];
+    ic_stage_neighbours(c, lane, nl);
     ic_sync(nl);
 
     // Intra16x16 mode search (intra.cpp:980-1001): smallest sum of absolute quantised coefficients, first mode wins ties.

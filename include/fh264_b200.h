@@ -1,5 +1,6 @@
 /*
- * fh264_b200 — C ABI of the B200 (sm_100a) implementation of the P-picture hot path of zoltanmaric/h264-fer.
+ * fh264_b200 — C ABI of the B200 (sm_100a) implementation of the encoder hot path of zoltanmaric/h264-fer (P pictures; I pictures
+ * through fh264_encode_i).
  *
  * This is the drop-in boundary: plain C, opaque handle, plain pointers and sizes, int status codes.
  * Each entry point names the reference interface it stands in for (paths relative to the reference's
@@ -19,6 +20,8 @@
  *                            then modificationProcess()/frameDeepCopy() and
  *                            FillInterpolatedRefFrame() for the next picture       (rbsp_encoding.cpp:317-322)
  *   fh264_upload_recon    <- after a host-coded I picture: frame -> dpb, then FillInterpolatedRefFrame()
+ *   fh264_encode_i        <- the I-slice MB loop: intraPredictionEncoding() + quantizationTransform() for every MB
+ *                            (rbsp_encoding.cpp:196-215), then the same dpb copy and reference preparation
  * All arithmetic is integer; results are bit-exact with the reference CPU path.
  */
 #ifndef FH264_B200_H

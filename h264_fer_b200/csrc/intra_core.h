@@ -701,3 +701,56 @@ FH_HD void ic_macroblock(IcCtx &c, bool prev_skip, const IcInfo *left, const IcI
     for (int i = lane; i < 256; i += nl) c.rec[0][(size_t)(yP + (i >> 4)) * W + xP + (i & 15)] = c.L[i];
     for (int i = lane; i < 128; i += nl) c.rec[1 + (i >> 6)][(size_t)((yP >> 1) + ((i & 63) >> 3)) * CW + (xP >> 1) + (i & 7)] = c.RC[i >> 6][i & 63];
 }
+
+// ---- macroblock_layer() of one I macroblock as the reference writes it (rbsp_encoding.cpp:221-305, residual_write
+//      residual.cpp:300-372): mb_type, the Intra4x4 mode syntax, intra_chroma_pred_mode, coded_block_pattern, mb_qp_delta and
+//      the residual blocks — the same walk as the bit-cost trial above, with the bits kept --------------------------------------
+// state of a coded macroblock from its record (what ic_macroblock leaves in IcInfo)
+FH_HD void ic_info_from_record(const fh264_mb_result_i &r, IcInfo &o)
+{
+    const bool is16 = r.intra16x16_pred_mode >= 0;
+    const int16_t *l = &r.luma[0][0];
+    o.mb_type = (uint8_t)r.mb_type; o.cbp_luma = r.cbp_luma; o.cbp_chroma = r.cbp_chroma; o.is4x4 = !is16;
+    for (int b = 0; b < 16; b++) {
+        o.tc_luma[b] = (uint8_t)((r.cbp_luma >> (b >> 2)) & 1 ? (is16 ? cv_count(l + 16 + b * 15, 15) : cv_count(l + b * 16, 16)) : 0);
+        o.mode4[b] = r.intra4x4_pred_mode[b];
+    }
+    for (int c = 0; c < 2; c++) for (int b = 0; b < 4; b++) o.tc_chroma[c][b] = (uint8_t)((r.cbp_chroma & 2) ? cv_count(r.chroma_ac[c][b], 15) : 0);
+    o.pad[0] = o.pad[1] = o.pad[2] = o.pad[3] = 0;
+}
+FH_HD void ic_write_macroblock(CvBits &b, const fh264_mb_result_i &r, const IcInfo &me, const IcInfo *left, const IcInfo *up, int *bad)
+{
+    const bool is16 = r.intra16x16_pred_mode >= 0;
+    const int16_t *l = &r.luma[0][0];
+    const int cbpl = me.cbp_luma, cbpc = me.cbp_chroma;
+    cv_ue(b, (uint32_t)r.mb_type);
+    if (!is16)
+        for (int k = 0; k < 16; k++) {
+            cv_put(b, 1, r.prev_intra4x4_pred_mode_flag[k] ? 1u : 0u);
+            if (!r.prev_intra4x4_pred_mode_flag[k]) cv_put(b, 3, r.rem_intra4x4_pred_mode[k]);
+        }
+    cv_ue(b, r.intra_chroma_pred_mode);
+    if (!is16) cv_ue(b, ic_cbp_intra[(cbpc << 4) | cbpl]);
+    if (!(cbpl > 0 || cbpc > 0 || is16)) return;
+    cv_se(b, 0);                                              // mb_qp_delta
+    if (is16) cv_block(b, l, 16, cv_nc(left ? left->tc_luma[5] : -1, up ? up->tc_luma[10] : -1), bad);
+    for (int blk = 0; blk < 16; blk++) {
+        if (!(cbpl & (1 << (blk >> 2)))) continue;
+        const int bx = ((blk >> 2) & 1) * 2 + (blk & 1), by = (blk >> 3) * 2 + ((blk >> 1) & 1);
+        int nA, nB;
+        if (bx > 0) nA = me.tc_luma[(by >> 1) * 8 + ((bx - 1) >> 1) * 4 + (by & 1) * 2 + ((bx - 1) & 1)];
+        else nA = left ? left->tc_luma[(by >> 1) * 8 + 4 + (by & 1) * 2 + 1] : -1;
+        if (by > 0) nB = me.tc_luma[((by - 1) >> 1) * 8 + (bx >> 1) * 4 + ((by - 1) & 1) * 2 + (bx & 1)];
+        else nB = up ? up->tc_luma[8 + (bx >> 1) * 4 + 2 + (bx & 1)] : -1;
+        if (is16) cv_block(b, l + 16 + blk * 15, 15, cv_nc(nA, nB), bad); else cv_block(b, l + blk * 16, 16, cv_nc(nA, nB), bad);
+    }
+    if (cbpc & 3) for (int c = 0; c < 2; c++) cv_block(b, r.chroma_dc[c], 4, -1, bad);
+    if (cbpc & 2)
+        for (int c = 0; c < 2; c++)
+            for (int blk = 0; blk < 4; blk++) {
+                const int bx = blk & 1, by = blk >> 1;
+                const int nA = bx ? me.tc_chroma[c][blk - 1] : (left ? left->tc_chroma[c][blk + 1] : -1);
+                const int nB = by ? me.tc_chroma[c][blk - 2] : (up ? up->tc_chroma[c][blk + 2] : -1);
+                cv_block(b, r.chroma_ac[c][blk], 15, cv_nc(nA, nB), bad);
+            }
+}

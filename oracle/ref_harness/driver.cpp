@@ -14,7 +14,7 @@
 //   dumpmask bits: 1 per-MB records (P pictures)   2 reconstruction per picture   4 cropped source per picture
 //                  8 phase-R data after picture `planes_pic`   16 per-MB TQ input (snapped source + prediction)
 //                  32 Intra16x16 luma records of I pictures (source, prediction, DC/AC levels, reconstruction)
-//                  64 slice RBSP of P pictures (SLDT: bit position of the first slice_data bit, then the RBSP bytes)
+//                  64 slice RBSP of P pictures, with 256 also of I pictures (SLDT: bit position of the first slice_data bit, then the RBSP bytes)
 //                  128 the CAVLC coder tables once (CVTB; fixture for the table check of the device coder)
 //                  256 per-MB records of I pictures (IMBR: final mb_type, prediction modes, both bit-cost trials, CBP, levels)
 // stdout: one JSON line with per-picture types/bytes and timings.
@@ -124,6 +124,7 @@ void interEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8])
 
 int intraPredictionEncoding(int predL[16][16], int predCr[8][8], int predCb[8][8])
 {
+	if (CurrMbAddr == 0) slice_data_bit0 = (int)(RBSP_write_current_byte * 8 + RBSP_write_current_bit + RBSP_write_buffer_bit);
 	const int m = ref_intraPredictionEncoding(predL, predCr, predCb);
 	if (dumpmask & 256) {
 		int *R = &imbrec[(size_t)CurrMbAddr * IREC_INTS];
@@ -318,7 +319,7 @@ int main(int argc, char **argv)
 		chunk("PICH", hdr, sizeof hdr);
 		if (isP && (dumpmask & 1)) chunk("MBRC", mbrec.data(), mbrec.size() * sizeof(int));
 		if (isP && (dumpmask & 16)) chunk("TQIO", tqio.data(), tqio.size());
-		if (isP && (dumpmask & 64)) {
+		if ((isP || (dumpmask & 256)) && (dumpmask & 64)) {
 			std::vector<unsigned char> sl(4 + nu.NumBytesInRBSP);
 			memcpy(sl.data(), &slice_data_bit0, 4);
 			memcpy(sl.data() + 4, nu.rbsp_byte, nu.NumBytesInRBSP);

@@ -52,7 +52,7 @@ def main_intra():
         y4m = os.path.join(tmp, "in.y4m")
         synth.write_y4m(y4m, w, h, seed, frames, noise=noise, square=square, contrast=contrast, pan=case[11] if len(case) > 11 else (2, 1))
         summ, dump, out264 = refdump.run_reference(y4m, frames, qp=qp, window=window, maxdiff=maxdiff, intra_every=intra_every,
-                                                   dumpmask=refdump.D_MBREC | refdump.D_RECON | refdump.D_SOURCE | refdump.D_IMBREC)
+                                                   dumpmask=refdump.D_MBREC | refdump.D_RECON | refdump.D_SOURCE | refdump.D_IMBREC | refdump.D_SLICE)
         pics = refdump.parse_dump(dump)
         arrays = dict(params=np.array([w, h, seed, frames, qp, window, maxdiff, intra_every], np.int32),
                       types=np.array([p["nal_type"] for p in pics], np.int32),
@@ -62,6 +62,8 @@ def main_intra():
                 arrays["%s_%d" % (t, n)] = p[t]
             if "imbrec" in p:
                 arrays["imbrec_%d" % n] = p["imbrec"].astype(np.int16)
+                arrays["slbit0_%d" % n] = np.array([p["slice_bit0"]], np.int32)     # first slice_data bit of the I slice's RBSP
+                arrays["rbsp_%d" % n] = p["rbsp"]
             if "mbrec" in p:
                 arrays["mbrec_%d" % n] = p["mbrec"].astype(np.int16)
         path = os.path.join(HERE, name + ".npz")

@@ -21,3 +21,23 @@ extern "C" int intra_host_picture(const unsigned char *sy, const unsigned char *
     }
     return 0;
 }
+
+// slice_data() of an I picture from its records: bits [first_bit, *nbits) of out (MSB first), like cavlc_host_slice for P pictures
+extern "C" int intra_host_slice(const fh264_mb_result_i *rec, int nmb, int wmb, int first_bit, unsigned char *out, int cap_bytes, int *nbits, int *bad)
+{
+    std::vector<IcInfo> info(nmb);
+    for (int m = 0; m < nmb; m++) ic_info_from_record(rec[m], info[m]);
+    std::vector<uint32_t> words(cap_bytes / 4 + 2, 0u);
+    CvBits b;
+    cv_init(b, words.data(), (int)words.size());
+    cv_put(b, first_bit, 0);
+    *bad = 0;
+    for (int m = 0; m < nmb; m++)
+        ic_write_macroblock(b, rec[m], info[m], (m % wmb) ? &info[m - 1] : nullptr, m >= wmb ? &info[m - wmb] : nullptr, bad);
+    *nbits = cv_bits(b);
+    cv_flush(b);
+    if (b.ovf) return -1;
+    const int nbytes = (*nbits + 7) / 8;
+    for (int i = 0; i < nbytes; i++) out[i] = (unsigned char)(words[i >> 2] >> (24 - 8 * (i & 3)));
+    return 0;
+}

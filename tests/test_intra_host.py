@@ -76,6 +76,8 @@ def golden_pictures(name):
         for k in ("imbrec", "mbrec"):
             if "%s_%d" % (k, n) in g:
                 p[k] = g["%s_%d" % (k, n)].astype(np.int32)
+        if "rbsp_%d" % n in g:
+            p["rbsp"], p["slice_bit0"] = g["rbsp_%d" % n], int(g["slbit0_%d" % n][0])
         pics.append(p)
     return g["params"], pics
 
@@ -132,3 +134,49 @@ def test_core_matches_live_runs_of_the_reference(host_lib, w, h, seed, frames, q
     synth.write_y4m(y4m, w, h, seed, frames, **kw)
     _, dump, _ = refdump.run_reference(y4m, frames, qp=qp, intra_every=intra_every, dumpmask=refdump.D_MBREC | refdump.D_RECON | refdump.D_SOURCE | refdump.D_IMBREC)
     check_clip(host_lib, refdump.parse_dump(dump), qp, "live %dx%d qp %d" % (w, h, qp))
+
+
+def i_records_from_ints(r):
+    """reference dump records [nmb, 439] -> fh264_mb_result_i array (what fh264_encode_i returns)."""
+    r = np.asarray(r, np.int32)
+    out = np.zeros(len(r), fh.MB_RESULT_I_DTYPE)
+    out["mb_type"], out["intra16x16_pred_mode"], out["intra_chroma_pred_mode"] = r[:, 0], r[:, 1], r[:, 2]
+    out["bits_intra16x16"], out["bits_intra4x4"], out["cbp_luma"], out["cbp_chroma"] = r[:, 3], r[:, 4], r[:, 5], r[:, 6]
+    out["intra4x4_pred_mode"], out["prev_intra4x4_pred_mode_flag"] = r[:, 7:23], r[:, 23:39]
+    out["rem_intra4x4_pred_mode"] = np.where(r[:, 23:39] == 0, r[:, 39:55], 0)
+    out["luma"] = r[:, 55:311].reshape(-1, 16, 16)
+    out["chroma_dc"] = r[:, 311:319].reshape(-1, 2, 4)
+    out["chroma_ac"] = r[:, 319:439].reshape(-1, 2, 4, 15)
+    return out
+
+
+def check_slice_bits(data, nbits, rbsp, bit0, what):
+    """slice data in bits [bit0 % 8, nbits) of data == the reference RBSP from its first slice_data bit, up to the trailing bits."""
+    ref = np.unpackbits(np.asarray(rbsp, np.uint8))
+    mine = np.unpackbits(np.asarray(data, np.uint8))[bit0 % 8:nbits]
+    want = ref[bit0:bit0 + len(mine)]
+    assert len(want) == len(mine), what + ": slice data longer than the reference RBSP"
+    bad = np.nonzero(mine != want)[0]
+    assert len(bad) == 0, "%s: slice data differs from bit %d of %d" % (what, bad[0], len(mine))
+    tail = ref[bit0 + len(mine):]
+    assert tail[0] == 1 and not tail[1:].any() and len(tail) <= 8, what + ": the reference's slice data does not end where ours does (rbsp_trailing_bits expected)"
+
+
+@pytest.mark.parametrize("name", INTRA_GOLDENS)
+def test_i_slice_data_matches_the_reference_rbsp(host_lib, name):
+    """macroblock_layer() of every I macroblock (ic_write_macroblock) from the reference's records against the reference's RBSP."""
+    params, pics = golden_pictures(name)
+    done = 0
+    for n, p in enumerate(pics):
+        if "imbrec" not in p:
+            continue
+        h, w = p["SRCY"].shape
+        rec = i_records_from_ints(p["imbrec"])
+        out = np.zeros(len(p["rbsp"]) + 64, np.uint8)
+        nbits, bad = C.c_int(0), C.c_int(0)
+        bit0 = p["slice_bit0"]
+        rc = host_lib.intra_host_slice(rec.ctypes.data_as(C.c_void_p), len(rec), w // 16, bit0 % 8, out.ctypes.data_as(C.c_void_p), len(out), C.byref(nbits), C.byref(bad))
+        assert rc == 0 and bad.value == 0
+        check_slice_bits(out, nbits.value, p["rbsp"], bit0, "%s picture %d" % (name, n))
+        done += 1
+    assert done > 0

@@ -78,6 +78,7 @@ struct fh264_session {
     int *d_iwf_order;               // anti-diagonal order x + 2y: an I macroblock needs left, up-left, up and up-right complete
     int *d_prev_p;                  // per sequence: the previous picture was a P picture whose records are in `results`
     std::vector<int> prev_p;
+    std::vector<char> last_i;       // per sequence: `results` holds the I records of the picture coded last
 };
 
 __global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
@@ -205,6 +206,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     g.band_mb0 = 0; g.band_nmb = g.nmb; g.rank = 0; g.world = 1;
     s->has_ref.assign(batch, 0);
     s->prev_p.assign(batch, 0);
+    s->last_i.assign(batch, 0);
     s->h.resize(batch);
 #define OPEN_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(FH264_E_CUDA, #call, e_); fh264_close(s); return FH264_E_CUDA; } } while (0)
     OPEN_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -405,7 +407,7 @@ extern "C" int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, c
     CK(cudaMemcpyAsync(s->h[seq].ref[2], cr, WH / 4, cudaMemcpyHostToDevice, s->stream));
     rc = launch_phase_r(s, seq, 1); if (rc) return rc;
     s->has_ref[seq] = 1;
-    if (!s->prev_p.empty()) s->prev_p[seq] = 0;     // a picture coded elsewhere: no P_Skip entries in mb_type_array
+    if (!s->prev_p.empty()) { s->prev_p[seq] = 0; s->last_i[seq] = 0; }     // a picture coded elsewhere: no P_Skip entries in mb_type_array
     return FH264_OK;
 }
 
@@ -507,7 +509,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
     CK(cudaEventRecord(s->ev[4], st));
     s->timed = true;
-    if (!s->prev_p.empty()) for (int b = seq0; b < seq0 + nseq; b++) s->prev_p[b] = 1;
+    if (!s->prev_p.empty()) for (int b = seq0; b < seq0 + nseq; b++) { s->prev_p[b] = 1; s->last_i[b] = 0; }
     return FH264_OK;
 }
 
@@ -542,7 +544,7 @@ extern "C" int fh264_decode_p(fh264_session *s, int seq0, int nseq, int qp, cons
         for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
     rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
     CK(sync_streams(s));
-    if (!s->prev_p.empty()) for (int b = seq0; b < seq0 + nseq; b++) s->prev_p[b] = 1;
+    if (!s->prev_p.empty()) for (int b = seq0; b < seq0 + nseq; b++) { s->prev_p[b] = 1; s->last_i[b] = 0; }
     return FH264_OK;
 }
 
@@ -614,7 +616,7 @@ extern "C" int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh26
     for (int b = seq0; b < seq0 + nseq; b++)
         for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
     rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
-    for (int b = seq0; b < seq0 + nseq; b++) { s->has_ref[b] = 1; s->prev_p[b] = 0; }
+    for (int b = seq0; b < seq0 + nseq; b++) { s->has_ref[b] = 1; s->prev_p[b] = 0; s->last_i[b] = 1; }
     CK(sync_streams(s));
     for (int b = seq0; b < seq0 + nseq; b++)
         if (s->h_status[(size_t)b * ST_WORDS + ST_FLAGS] & FLAG_TIMEOUT) return fail(FH264_E_CUDA, "intra wavefront wait timed out");
@@ -665,20 +667,11 @@ static int ensure_cavlc(fh264_session *s)
     return FH264_OK;
 }
 
-extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits,
-                             fh264_cavlc_mb_info *mb_info)
+// shared tail of fh264_cavlc_p / fh264_cavlc_i: offsets, packing, status and the copies home
+static int cavlc_finish(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits, fh264_cavlc_mb_info *mb_info)
 {
-    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
-    if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
-    if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
-    if (s->epoch == 0) return fail(FH264_E_STATE, "cavlc_p before any encode_p");
-    CK(cudaSetDevice(s->device));
-    rc = ensure_cavlc(s); if (rc) return rc;
-    const int nmb = s->g.nmb, wmb = s->g.Wmb;
+    const int nmb = s->g.nmb;
     cudaStream_t st = s->stream;
-    for (int b = seq0; b < seq0 + nseq; b++) CK(cudaMemsetAsync(s->cvh[b].stream, 0, (size_t)CV_STREAM_BYTES + 64, st));
-    k_cavlc_prep<<<dim3((nmb + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb);
-    k_cavlc_code<<<dim3((nmb + 1 + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb, wmb);
     k_cavlc_scan<<<nseq, 1024, 0, st>>>(s->d_cvs, seq0, nmb, first_bit);
     k_cavlc_pack<<<dim3((nmb + 1 + 3) / 4, nseq), 128, 0, st>>>(s->d_cvs, seq0, nmb, first_bit);
     CKL();
@@ -695,6 +688,42 @@ extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit
     }
     CK(cudaStreamSynchronize(st));
     return FH264_OK;
+}
+
+extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits,
+                             fh264_cavlc_mb_info *mb_info)
+{
+    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
+    if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
+    if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
+    if (s->epoch == 0) return fail(FH264_E_STATE, "cavlc_p before any encode_p");
+    CK(cudaSetDevice(s->device));
+    rc = ensure_cavlc(s); if (rc) return rc;
+    const int nmb = s->g.nmb, wmb = s->g.Wmb;
+    cudaStream_t st = s->stream;
+    for (int b = seq0; b < seq0 + nseq; b++) CK(cudaMemsetAsync(s->cvh[b].stream, 0, (size_t)CV_STREAM_BYTES + 64, st));
+    k_cavlc_prep<<<dim3((nmb + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb);
+    k_cavlc_code<<<dim3((nmb + 1 + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb, wmb);
+    return cavlc_finish(s, seq0, nseq, first_bit, out, out_stride, nbits, mb_info);
+}
+
+// slice_data() of the I picture(s) last coded by fh264_encode_i (intra.cuh, k_cavlc_code_i). See the header.
+extern "C" int fh264_cavlc_i(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits)
+{
+    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
+    if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
+    if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
+    for (int b = seq0; b < seq0 + nseq; b++) if (!s->last_i[b]) return fail(FH264_E_STATE, "cavlc_i: the last picture of the sequence was not coded by encode_i");
+    CK(cudaSetDevice(s->device));
+    rc = ensure_cavlc(s); if (rc) return rc;
+    const int nmb = s->g.nmb, wmb = s->g.Wmb;
+    cudaStream_t st = s->stream;
+    for (int b = seq0; b < seq0 + nseq; b++) {
+        CK(cudaMemsetAsync(s->cvh[b].stream, 0, (size_t)CV_STREAM_BYTES + 64, st));
+        CK(cudaMemsetAsync(s->cvh[b].stat, 0, sizeof(uint32_t) * 2, st));
+    }
+    k_cavlc_code_i<<<dim3((nmb + 1 + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb, wmb);
+    return cavlc_finish(s, seq0, nseq, first_bit, out, out_stride, nbits, nullptr);
 }
 
 // Snapshot of the 16 status words of sequence seq taken after phase C of its last encode_p (tests / diagnostics):

@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "intra_core.h"
+#include "cavlc.cuh"
 
 struct IntraSeq {
     IcInfo *info;           // nmb: state of the macroblocks of the picture being coded
@@ -72,4 +73,29 @@ __global__ void __launch_bounds__(32) k_intra(const SeqDev *__restrict__ seqs, c
         __syncwarp();
         if (lane == 0) { __threadfence(); st_release_u32(&I.done[mb], epoch); }
     }
+}
+
+// slice_data() of an I picture from the records fh264_encode_i left (SURVEY.md §8(f) ranks 1 + 2): every macroblock codes itself
+// into its private bit buffer (ic_write_macroblock; the nC contexts come from the neighbours' records), k_cavlc_scan and
+// k_cavlc_pack of the P path then concatenate the buffers. Slot nmb stays empty (no mb_skip_run in an I slice).
+__global__ void __launch_bounds__(128) k_cavlc_code_i(const SeqDev *__restrict__ seqs, const CvSeq *__restrict__ cvs, int seq0, int nmb, int wmb)
+{
+    const int mb = blockIdx.x * 128 + threadIdx.x;
+    if (mb > nmb) return;
+    const CvSeq &cv = cvs[seq0 + blockIdx.y];
+    if (mb == nmb) { cv.bits[mb] = 0; return; }
+    const fh264_mb_result_i *rec = (const fh264_mb_result_i *)seqs[seq0 + blockIdx.y].results;
+    IcInfo me, left, up;
+    const bool hl = (mb % wmb) != 0, hu = mb >= wmb;
+    ic_info_from_record(rec[mb], me);
+    if (hl) ic_info_from_record(rec[mb - 1], left);
+    if (hu) ic_info_from_record(rec[mb - wmb], up);
+    CvBits b;
+    cv_init(b, cv.buf + (size_t)mb * CV_MB_WORDS, CV_MB_WORDS);
+    int bad = 0;
+    ic_write_macroblock(b, rec[mb], me, hl ? &left : nullptr, hu ? &up : nullptr, &bad);
+    cv_flush(b);
+    cv.bits[mb] = (uint32_t)cv_bits(b);
+    const uint32_t fl = (b.ovf ? CV_FLAG_MB_OVERFLOW : 0u) | (bad ? CV_FLAG_LEVEL_RANGE : 0u);
+    if (fl) atomicOr(&cv.stat[0], fl);
 }

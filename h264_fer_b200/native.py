@@ -31,7 +31,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_frame", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
-           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
+           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_cavlc_i", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
 
 
 class Fh264Error(RuntimeError):
@@ -92,6 +92,7 @@ def load_library():
     L.fh264_decode_p.argtypes = [vp, i32, i32, i32, vp]
     L.fh264_encode_i.argtypes = [vp, i32, i32, i32, vp]
     L.fh264_last_intra_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.fh264_cavlc_i.argtypes = [vp, i32, i32, i32, vp, C.c_size_t, vp]
     L.fh264_debug_status.argtypes = [vp, i32, vp]
     L.fh264_band_config.argtypes = [vp, i32, i32, i32, i32]
     L.fh264_ipc_export.argtypes = [vp, i32, vp]
@@ -298,6 +299,15 @@ class Session:
         self._ck(self.L.fh264_cavlc_p(self.handle, seq0, nseq, first_bit, _ptr(out), capacity, _ptr(nbits), _ptr(info) if mb_info else None))
         res = [(out[b, :(int(nbits[b]) + 7) // 8].copy(), int(nbits[b])) for b in range(nseq)]
         return (res, info) if mb_info else res
+
+    def cavlc_i(self, first_bit=0, seq0=0, nseq=None, capacity=500064):
+        """Device CAVLC of the I picture(s) last coded by encode_i: list of (bytes, nbits) per sequence, like cavlc_p
+        (rbsp_encoding.cpp:221-305)."""
+        nseq = self.batch - seq0 if nseq is None else nseq
+        out = np.zeros((nseq, capacity), np.uint8)
+        nbits = np.zeros(nseq, np.uint32)
+        self._ck(self.L.fh264_cavlc_i(self.handle, seq0, nseq, first_bit, _ptr(out), capacity, _ptr(nbits)))
+        return [(out[b, :(int(nbits[b]) + 7) // 8].copy(), int(nbits[b])) for b in range(nseq)]
 
     def debug_timeline(self, seq, read=True):
         if not read:

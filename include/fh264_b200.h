@@ -222,6 +222,11 @@ typedef struct fh264_mb_result_i {
  * (mb_type_array is only cleared after the first trial, intra.cpp:1008-1012); the session remembers that from its last
  * fh264_encode_p / fh264_decode_p. results: nseq * MBs records (host) or NULL. Synchronous. Not available in band mode. */
 int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh264_mb_result_i *results);
+/* slice_data() of the I picture last coded by fh264_encode_i for sequences [seq0, seq0 + nseq): what the I-slice macroblock loop of
+ * RBSP_encode writes between shd_write() and RBSP_trailing_bits() (rbsp_encoding.cpp:221-305: mb_type, prev_intra4x4_pred_mode_flag /
+ * rem_intra4x4_pred_mode, intra_chroma_pred_mode, coded_block_pattern, mb_qp_delta, residual_write residual.cpp:300-372).
+ * Arguments, bit alignment and errors as fh264_cavlc_p. */
+int fh264_cavlc_i(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits);
 /* Device time of the intra wavefront kernel of the last fh264_encode_i call, milliseconds (CUDA events on the session stream). */
 int fh264_last_intra_ms(fh264_session *s, float *ms);
 

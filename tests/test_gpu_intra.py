@@ -12,7 +12,7 @@ import pytest
 
 import h264_fer_b200 as fh
 from h264_fer_b200 import synth
-from test_intra_host import INTRA_GOLDENS, compare_i_records, golden_pictures
+from test_intra_host import INTRA_GOLDENS, check_slice_bits, compare_i_records, golden_pictures
 
 pytestmark = pytest.mark.gpu
 
@@ -34,6 +34,9 @@ def run_clip(s, seq, pics, qp, window, maxdiff, what):
         if "imbrec" in p:
             rec = s.encode_i(qp, seq0=seq, nseq=1)[0]
             compare_i_records(fh.i_records_to_ints(rec), p["imbrec"], "%s picture %d (I)" % (what, n))
+            if "rbsp" in p:          # the I slice's slice_data() entropy-coded on the device against the reference's RBSP
+                data, nbits = s.cavlc_i(first_bit=p["slice_bit0"] % 8, seq0=seq, nseq=1)[0]
+                check_slice_bits(data, nbits, p["rbsp"], p["slice_bit0"], "%s picture %d (I slice data)" % (what, n))
         else:
             rec = s.encode_p(qp, window, maxdiff, 0, seq0=seq, nseq=1)[0]
             mine, ref = fh.records_to_ints(rec), p["mbrec"]
@@ -95,6 +98,27 @@ def test_1080p_i_picture_matches_a_live_reference_run():
         s.encode_i(qp)
         dt = time.perf_counter() - t0
     print("\n1080p I picture: device %.1f ms (call incl. record D2H and phase R), reference %.0f ms on one host core" % (dt * 1e3, summ["t_picture"][0] * 1e3))
+
+
+def test_cavlc_i_of_a_batch_and_its_error_path():
+    w, h, qp = 320, 240, 27
+    frames = [synth.SynthClip(w, h, 70 + b, contrast=(1.0, 0.1)[b]).frame(0) for b in range(2)]
+    single = []
+    for b in range(2):
+        with fh.Session(w, h) as s:
+            s.upload_source(0, *frames[b])
+            s.encode_i(qp)
+            single.append(s.cavlc_i(first_bit=3)[0])
+    with fh.Session(w, h, batch=2) as s:
+        with pytest.raises(fh.Fh264Error) as e:
+            s.cavlc_i()
+        assert e.value.code == -4                     # no I picture coded yet
+        for b in range(2):
+            s.upload_source(b, *frames[b])
+        s.encode_i(qp)
+        for b, (data, nbits) in enumerate(s.cavlc_i(first_bit=3)):
+            assert nbits == single[b][1] and np.array_equal(data, single[b][0]), "sequence %d" % b
+            assert nbits > 3 and not (data[0] & 0xE0)          # the first three bits stay clear for the slice header's tail
 
 
 def test_encode_i_error_paths():

@@ -80,3 +80,31 @@ def test_host_mirror_frame_type_rule():
     assert e.select_nal_unit_type() == NAL_IDR
     f.sad = 0; e.curr_frame_count = 4
     assert e.select_nal_unit_type() == NAL_IDR                       # currFrameCount % IntraEvery == 0
+
+
+def test_host_mirror_routes_idr_pictures():
+    """SequenceEncoder.encode_picture: IDR pictures go to fh264_encode_i on the device, or to the intra_coder callback followed by
+    fh264_upload_recon when one is given (the reference's host path); P pictures to fh264_encode_p."""
+    from h264_fer_b200.encoder import SequenceEncoder, NAL_IDR, NAL_NON_IDR
+
+    class Fake:
+        nmb = 99
+        def __init__(self): self.calls = []
+        def upload_source(self, seq, y, cb, cr): self.calls.append("src")
+        def scene_sad(self, seq): return 0
+        def encode_i(self, qp, seq0=0, nseq=None): self.calls.append("encode_i"); return ["I"]
+        def encode_p(self, qp, window, maxdiff_set, basic, seq0=0, nseq=None): self.calls.append("encode_p"); return ["P"]
+        def upload_recon(self, seq, y, cb, cr): self.calls.append("upload_recon")
+
+    f = Fake()
+    e = SequenceEncoder(f, 0, intra_every=3)
+    out = [e.encode_picture(None, None, None) for _ in range(4)]
+    assert [n for n, _ in out] == [NAL_IDR, NAL_NON_IDR, NAL_NON_IDR, NAL_IDR]
+    assert [r for _, r in out] == ["I", "P", "P", "I"]
+    assert f.calls == ["src", "encode_i", "src", "encode_p", "src", "encode_p", "src", "encode_i"]
+
+    f = Fake()
+    e = SequenceEncoder(f, 0, intra_every=1000, intra_coder=lambda y, cb, cr: (y, cb, cr))
+    assert e.encode_picture(None, None, None) == (NAL_IDR, None)
+    assert e.encode_picture(None, None, None)[0] == NAL_NON_IDR
+    assert f.calls == ["src", "upload_recon", "src", "encode_p"]

@@ -66,6 +66,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def measured_int_peak():
+    """Sustained integer-pipe rate measured on a B200 of this pool by profiles/tools/int_peak.cu (profiles/r01_int_peak.json):
+    the instructions the ME kernels are made of (VABSDIFF4.U8.ACC, VIADDMNMX[.S16x2], IMAD, LOP3, SHF) issue at 64 lanes per SM
+    per clock; only plain adds (VIADD / IADD3) have the second 64 lanes. Returns T lane-ops/s of that 64-lane pipe, or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_int_peak.json")))
+        return float(min(d["imad (1 instr)"], d["viaddmnmx (1 instr)"], d["viaddmnmx.s16x2 (1 instr)"]))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -495,11 +506,16 @@ def main():
             "int_roofline": {"ops_per_mb": ALG_INTOPS_PER_MB, "achieved_tops": int_ops / (step_ms / 1000.0) / 1e12 / world,
                              "peak_tops_nominal": 148 * 128 * sm_max * 1e6 / 1e12,
                              "frac": (int_ops / (step_ms / 1000.0) / 1e12 / world) / (148 * 128 * sm_max * 1e6 / 1e12),
-                             "note": "SURVEY.md §8d: 0.43 M int32-lane ops per MB over the whole timed job, per GPU; peak = 148 SMs x 128 lanes x max SM clock"},
+                             "note": "SURVEY.md §8d: 0.43 M int32-lane ops per MB over the whole timed job, per GPU; peak = 148 SMs x 128 lanes x max SM clock; "
+                                     "peak_tops_measured = sustained rate of the 64-lane integer pipe the ME instructions issue on (profiles/r01_int_peak.json)"},
             "dram_traffic_bytes_per_launch": traffic_by_kernel,
             "kernel_ms_per_step": kernels, "phase_ms_per_step": {k_: tm[k_] for k_ in ("phase_a_ms", "phase_b_ms", "phase_c_ms", "copy_phase_r_ms", "total_ms")},
             "idr_decisions": idr_decisions, "mode_counts_last_picture_seq0": counts[0],
         }
+        ipk = measured_int_peak()
+        if ipk:
+            line["int_roofline"]["peak_tops_measured"] = ipk
+            line["int_roofline"]["frac_measured"] = line["int_roofline"]["achieved_tops"] / ipk
         if cavlc is not None:
             line["device_cavlc"] = cavlc
         if intra is not None:

@@ -17,7 +17,7 @@
 FH_HD void ic_sync(int nl) { if (nl > 1) __syncwarp(); }
 FH_HD int ic_red_add(int v, int nl) { return nl > 1 ? __reduce_add_sync(0xffffffffu, v) : v; }
 FH_HD int ic_red_min(int v, int nl) { return nl > 1 ? __reduce_min_sync(0xffffffffu, v) : v; }
-#else
+#elif !defined(IC_CUSTOM_LANES)     // (a host test may supply its own lane primitives: tests/intra_host_lanes.cpp runs 32 threads)
 FH_HD void ic_sync(int) {}
 FH_HD int ic_red_add(int v, int) { return v; }
 FH_HD int ic_red_min(int v, int) { return v; }

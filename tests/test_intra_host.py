@@ -136,6 +136,40 @@ def test_core_matches_live_runs_of_the_reference(host_lib, w, h, seed, frames, q
     check_clip(host_lib, refdump.parse_dump(dump), qp, "live %dx%d qp %d" % (w, h, qp))
 
 
+def build_lanes_lib(tsan):
+    out = os.path.join(tempfile.mkdtemp(prefix="fh264_intra_lanes_"), "libintra_lanes.so")
+    cmd = ["g++", "-O1", "-g", "-std=c++20", "-pthread", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "intra_host_lanes.cpp")]
+    if tsan:
+        cmd.insert(1, "-fsanitize=thread")
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def test_core_run_as_32_lanes_matches_the_reference():
+    """The device runs a macroblock on the 32 lanes of a warp. tests/intra_host_lanes.cpp runs the same source as 32 host threads
+    sharing one IcCtx (ic_sync = barrier, reductions through a shared array): the cross-lane structure gives the reference's results."""
+    lib = build_lanes_lib(False)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "intra_lanes_check.py"), lib] + INTRA_GOLDENS,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert res.returncode == 0 and res.stdout.decode().count("LANES-OK") == len(INTRA_GOLDENS), res.stdout.decode()[-3000:]
+
+
+def test_core_run_as_32_lanes_has_no_data_race():
+    """The same under ThreadSanitizer: every access to the state the lanes share is ordered by a barrier (on the device: __syncwarp)."""
+    tsan = subprocess.run(["gcc", "-print-file-name=libtsan.so"], stdout=subprocess.PIPE).stdout.decode().strip()
+    if not os.path.isabs(tsan) or not os.path.isfile(tsan):
+        pytest.skip("libtsan not available")
+    lib = build_lanes_lib(True)
+    env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="halt_on_error=0 exitcode=0")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "intra_lanes_check.py"), lib, "intra_small_qp12_iii", "intra_lowcontrast_qp30_ipi"],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    text = res.stdout.decode()
+    if "Running under ThreadSanitizer" not in text and "LANES-OK" not in text:
+        pytest.skip("ThreadSanitizer could not be started here: " + text[-300:])
+    assert "WARNING: ThreadSanitizer" not in text, text[text.index("WARNING: ThreadSanitizer"):][:3000]
+    assert text.count("LANES-OK") == 2, text[-3000:]
+
+
 def i_records_from_ints(r):
     """reference dump records [nmb, 439] -> fh264_mb_result_i array (what fh264_encode_i returns)."""
     r = np.asarray(r, np.int32)

@@ -201,8 +201,59 @@ void FillInterpolatedRefFrame()
 void ref_RBSP_encode(NALunit &nal_unit);
 void RBSP_trailing_bits();
 
+#ifdef FH264_SHIM_DEVICE_INTRA
+// ---- both variants together (integration/_build/fh264_encoder_b200_all): the IDR slice is coded AND entropy-coded on the device.
+// Restates the frame of RBSP_encode around an IDR slice (rbsp_encoding.cpp:119-123,141-170,308-325) with ONE device call chain in
+// place of the macroblock loop: slice header by the reference's shd_write(), slice_data() from fh264_encode_i + fh264_cavlc_i,
+// RBSP_trailing_bits() by the reference. Neither the 832-byte records nor the prediction modes cross PCIe.
+static void encode_idr_on_device(NALunit &nal_unit)
+{
+    initRawWriter(nal_unit.rbsp_byte, 500000);
+    static bool firstFrame = true;                       // rbsp_encoding.cpp:146-162
+    shd.slice_type = I_SLICE;
+    if (firstFrame) { firstFrame = false; shd.idr_pic_id = 0; }
+    else if (shd.frame_num == 0) shd.idr_pic_id++;
+    else shd.idr_pic_id = 0;
+    shd.frame_num = 0;
+    shd_write(nal_unit);
+    flushWriteBuffer();
+
+    ensure_session();
+    int rc = fh264_upload_source(g_sess, 0, frame.L, frame.C[0], frame.C[1]);
+    if (rc) die("fh264_upload_source", rc);
+    rc = fh264_encode_i(g_sess, 0, 1, QPy, NULL);
+    if (rc) die("fh264_encode_i", rc);
+    static std::vector<unsigned char> sl(500064);
+    uint32_t nbits = 0;
+    const int first_bit = (int)RBSP_write_current_bit;
+    rc = fh264_cavlc_i(g_sess, 0, 1, first_bit, sl.data(), sl.size(), &nbits);
+    if (rc) die("fh264_cavlc_i", rc);
+    unsigned char *dst = RBSP_write_data + RBSP_write_current_byte;
+    const size_t nbytes = ((size_t)nbits + 7) / 8;
+    if (nbytes) {
+        if (first_bit) dst[0] |= sl[0]; else dst[0] = sl[0];
+        memcpy(dst + 1, sl.data() + 1, nbytes - 1);
+    }
+    RBSP_write_current_byte += nbits >> 3;
+    RBSP_write_current_bit = nbits & 7;
+    RBSP_trailing_bits();
+    nal_unit.NumBytesInRBSP = RBSP_write_current_byte;
+    // host `frame` := reconstruction, as it is after the reference's own macroblock loop (modificationProcess copies it into dpb)
+    rc = fh264_download_recon(g_sess, 0, frame.L, frame.C[0], frame.C[1]);
+    if (rc) die("fh264_download_recon", rc);
+    g_last_was_device_i = true;
+    initialisationProcess();                             // rbsp_encoding.cpp:314-317
+    modificationProcess();
+    FillInterpolatedRefFrame();
+    flushWriteBuffer();
+}
+#endif
+
 void RBSP_encode(NALunit &nal_unit)
 {
+#ifdef FH264_SHIM_DEVICE_INTRA
+    if (nal_unit.nal_unit_type == NAL_UNIT_TYPE_IDR) { encode_idr_on_device(nal_unit); return; }
+#endif
     if (nal_unit.nal_unit_type != NAL_UNIT_TYPE_NOT_IDR) { ref_RBSP_encode(nal_unit); return; }
     initRawWriter(nal_unit.rbsp_byte, 500000);
     shd.slice_type = P_SLICE;

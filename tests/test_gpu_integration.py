@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ENCODER = os.path.join(ROOT, "integration", "_build", "fh264_encoder_b200")
 ENCODER_CAVLC = ENCODER + "_cavlc"          # same, with the P-slice entropy coding on the device too
 ENCODER_INTRA = ENCODER + "_intra"          # same as the first, with the I pictures coded on the device too
+ENCODER_ALL = ENCODER + "_all"              # both picture types coded AND entropy-coded on the device (fh264_cavlc_p + fh264_cavlc_i)
 
 needs_binary = pytest.mark.skipif(not (os.path.isfile(ENCODER) and os.path.isfile(ENCODER_CAVLC)), reason="integration binaries not built (make -C integration)")
 both_encoders = pytest.mark.parametrize("encoder", [ENCODER, ENCODER_CAVLC], ids=["host_cavlc", "device_cavlc"])
@@ -106,6 +107,30 @@ def test_bitstream_with_device_i_pictures_matches_live_reference(tmp_path, w, h,
                                         dumpmask=refdump.D_RECON, dump_path=refdumpf)
     out, dump = str(tmp_path / "b200.264"), str(tmp_path / "b200.bin")
     run_b200_encoder(y4m, out, dump, frames, qp, 0, window, maxdiff, intra_every=intra_every, dumpmask=refdump.D_RECON, encoder=ENCODER_INTRA)
+    assert summ["types"].count("I") >= 1 and "P" in summ["types"]
+    for n, (a, b) in enumerate(zip(refdump.parse_dump(dump), refdump.parse_dump(rd))):
+        assert a["nal_type"] == b["nal_type"], "picture %d type" % n
+        assert np.array_equal(a["RECY"], b["RECY"]) and np.array_equal(a["RECU"], b["RECU"]) and np.array_equal(a["RECV"], b["RECV"]), "picture %d reconstruction (%s)" % (n, summ["types"])
+    assert open(out, "rb").read() == open(ref264, "rb").read(), "bitstreams differ (%s)" % summ["types"]
+
+
+@pytest.mark.skipif(not os.path.isfile(ENCODER_ALL), reason="integration binary with everything on the device not built (make -C integration)")
+@pytest.mark.skipif(not refdump.have_ref_encoder(), reason="compiled reference not present")
+@pytest.mark.parametrize("w,h,seed,frames,qp,window,maxdiff,intra_every,kw", [
+    (176, 144, 1, 30, 28, 16, 3, 1000, {}),                                   # BASELINE config 1: first picture + a scene-change IDR
+    (352, 288, 2, 7, 28, 32, -1, 3, {}),                                      # CIF, periodic IDR every 3 pictures
+    (176, 144, 31, 4, 12, 16, 3, 2, {"pan": (0, 0), "noise": 0.0, "square": False}),   # static: all-P_Skip pictures before the IDRs
+])
+def test_bitstream_with_everything_on_the_device_matches_live_reference(tmp_path, w, h, seed, frames, qp, window, maxdiff, intra_every, kw):
+    """fh264_encoder_b200_all: slice_data() of BOTH picture types comes from the device (fh264_encode_i + fh264_cavlc_i,
+    fh264_encode_p + fh264_cavlc_p); the reference host code only writes parameter sets, slice headers and NAL framing."""
+    y4m = str(tmp_path / "in.y4m")
+    synth.write_y4m(y4m, w, h, seed, frames, **kw)
+    ref264 = str(tmp_path / "ref.264")
+    summ, rd, _ = refdump.run_reference(y4m, frames, qp=qp, window=window, maxdiff=maxdiff, intra_every=intra_every, out_264=ref264,
+                                        dumpmask=refdump.D_RECON, dump_path=str(tmp_path / "ref.bin"))
+    out, dump = str(tmp_path / "b200.264"), str(tmp_path / "b200.bin")
+    run_b200_encoder(y4m, out, dump, frames, qp, 0, window, maxdiff, intra_every=intra_every, dumpmask=refdump.D_RECON, encoder=ENCODER_ALL)
     assert summ["types"].count("I") >= 1 and "P" in summ["types"]
     for n, (a, b) in enumerate(zip(refdump.parse_dump(dump), refdump.parse_dump(rd))):
         assert a["nal_type"] == b["nal_type"], "picture %d type" % n

@@ -214,3 +214,32 @@ def test_i_slice_data_matches_the_reference_rbsp(host_lib, name):
         check_slice_bits(out, nbits.value, p["rbsp"], bit0, "%s picture %d" % (name, n))
         done += 1
     assert done > 0
+
+
+SHIM_MOCK = os.path.join(ROOT, "integration", "_build", "shimtest_all_on_cpu_mock")
+
+
+@pytest.mark.skipif(not os.path.isfile(SHIM_MOCK), reason="integration/_build/shimtest_all_on_cpu_mock not built (make -C integration, needs the reference sources)")
+@pytest.mark.parametrize("w,h,seed,frames,qp,kw", [(176, 144, 41, 3, 28, {}), (96, 80, 42, 3, 36, {"contrast": 0.1}), (200, 120, 43, 2, 12, {})])
+def test_reference_side_binding_for_device_idr_slices_on_a_mock_device(tmp_path, w, h, seed, frames, qp, kw):
+    """Host logic of the all-on-device integration variant (integration/fh264_ref_shim.cpp, encode_idr_on_device: slice header by the
+    reference, the device's slice data appended without shifting, trailing bits, idr_pic_id sequence, frame / dpb bookkeeping),
+    linked against tests/mock_fh264_intra.cpp — a TEST-ONLY stand-in for the C ABI built from the host compile of the same
+    I-picture core. All-IDR clips (IntraEvery 1): the Annex-B stream and the reconstructions must equal the reference's. The real
+    library runs the same binding on the B200 in tests/test_gpu_integration.py."""
+    from h264_fer_b200 import synth
+    from oracle import refdump
+    if not refdump.have_ref_encoder():
+        pytest.skip("oracle/_ref/ref_encoder not built")
+    y4m = str(tmp_path / "in.y4m")
+    synth.write_y4m(y4m, w, h, seed, frames, **kw)
+    summ, rd, ref264 = refdump.run_reference(y4m, frames, qp=qp, intra_every=1, dumpmask=refdump.D_RECON, out_264=str(tmp_path / "ref.264"),
+                                             dump_path=str(tmp_path / "ref.bin"))
+    out, dump = str(tmp_path / "mock.264"), str(tmp_path / "mock.bin")
+    res = subprocess.run([SHIM_MOCK, y4m, out, dump, str(frames), str(qp), "0", "16", "3", "1", str(refdump.D_RECON), "-1"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert res.returncode == 0, res.stderr.decode()[-2000:]
+    assert summ["types"] == "I" * frames
+    assert open(out, "rb").read() == open(ref264, "rb").read(), "bitstreams differ"
+    for n, (a, b) in enumerate(zip(refdump.parse_dump(dump), refdump.parse_dump(rd))):
+        assert np.array_equal(a["RECY"], b["RECY"]) and np.array_equal(a["RECU"], b["RECU"]) and np.array_equal(a["RECV"], b["RECV"]), "picture %d" % n

@@ -327,30 +327,7 @@ FH_HD void ic_fetch16(const IcCtx &c, int p[33])
     for (int i = 0; i < 16; i++) p[1 + i] = xP > 0 ? c.nbL[i] : -1;
     for (int i = 0; i < 16; i++) p[17 + i] = yP > 0 ? c.nbT[1 + i] : -1;
 }
-FH_HD void ic_pred16(int mode, const int p[33], uint8_t o[256])
-{
-    if (mode == 0) { for (int i = 0; i < 256; i++) o[i] = (uint8_t)p[17 + (i & 15)]; return; }
-    if (mode == 1) { for (int i = 0; i < 256; i++) o[i] = (uint8_t)p[1 + (i >> 4)]; return; }
-    if (mode == 2) {
-        int sx = 0, sy = 0;
-        for (int i = 0; i < 16; i++) { sx += p[17 + i]; sy += p[1 + i]; }
-        int v = 128;
-        if (p[0] != -1) v = (sx + sy + 16) >> 5;            // intra.cpp:462-467: the corner decides "both available"
-        else if (p[1] != -1) v = (sy + 8) >> 4;
-        else if (p[17] != -1) v = (sx + 8) >> 4;
-        for (int i = 0; i < 256; i++) o[i] = (uint8_t)v;
-        return;
-    }
-    int Hh = 0, V = 0;
-    for (int i = 0; i <= 7; i++) {
-        Hh += (i + 1) * (p[17 + 8 + i] - (6 - i >= 0 ? p[17 + 6 - i] : p[0]));
-        V += (i + 1) * (p[1 + 8 + i] - (6 - i >= 0 ? p[1 + 6 - i] : p[0]));
-    }
-    const int a = (p[16] + p[32]) << 4, b = (5 * Hh + 32) >> 6, cc = (5 * V + 32) >> 6;
-    for (int y = 0; y < 16; y++)
-        for (int x = 0; x < 16; x++) o[y * 16 + x] = (uint8_t)ic_clip255((a + b * (x - 7) + cc * (y - 7) + 16) >> 5);
-}
-// the same prediction for the samples of one 4x4 block only
+// the prediction of one mode for the samples of one 4x4 block (Intra_16x16_Vertical / Horizontal / DC / Plane, intra.cpp:424-500)
 FH_HD void ic_pred16_block(int mode, const int p[33], int blk, int o[16])
 {
     const int x0 = ic_blkx(blk), y0 = ic_blky(blk);

@@ -100,6 +100,20 @@ def test_1080p_i_picture_matches_a_live_reference_run():
     print("\n1080p I picture: device %.1f ms (call incl. record D2H and phase R), reference %.0f ms on one host core" % (dt * 1e3, summ["t_picture"][0] * 1e3))
 
 
+@pytest.mark.parametrize("w,h,seed", [(16, 16, 51), (176, 16, 52), (16, 144, 53)], ids=["one_mb", "one_row", "one_column"])
+def test_degenerate_picture_shapes_match_a_live_reference_run(w, h, seed):
+    """One macroblock, one macroblock row, one macroblock column: the wavefront's neighbour waits at every picture edge."""
+    from oracle import refdump
+    if not refdump.have_ref_encoder():
+        pytest.skip("oracle/_ref/ref_encoder not built")
+    qp = 28
+    y4m = os.path.join(tempfile.mkdtemp(prefix="fh264_intra_edge_"), "in.y4m")
+    synth.write_y4m(y4m, w, h, seed, 2)
+    _, dump, _ = refdump.run_reference(y4m, 2, qp=qp, intra_every=1, dumpmask=refdump.D_RECON | refdump.D_SOURCE | refdump.D_IMBREC | refdump.D_SLICE)
+    with fh.Session(w, h) as s:
+        run_clip(s, 0, refdump.parse_dump(dump), qp, 16, 3, "%dx%d" % (w, h))
+
+
 def test_cavlc_i_of_a_batch_and_its_error_path():
     w, h, qp = 320, 240, 27
     frames = [synth.SynthClip(w, h, 70 + b, contrast=(1.0, 0.1)[b]).frame(0) for b in range(2)]

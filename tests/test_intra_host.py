@@ -124,6 +124,9 @@ def test_the_previous_pictures_p_skip_state_is_part_of_the_result(host_lib):
     (352, 288, 23, 2, 28, 1000, {}),
     (128, 64, 24, 4, 51, 2, {"contrast": 0.6}),
     (64, 64, 25, 2, 0, 1, {}),
+    (16, 16, 51, 3, 28, 1, {}),             # one macroblock
+    (176, 16, 52, 3, 30, 2, {}),            # one macroblock row
+    (16, 144, 53, 3, 26, 2, {}),            # one macroblock column
 ])
 def test_core_matches_live_runs_of_the_reference(host_lib, w, h, seed, frames, qp, intra_every, kw):
     from h264_fer_b200 import synth

@@ -82,3 +82,38 @@ def test_slice_data_matches_the_reference(host_lib, name):
         assert tail[0] == 1 and not tail[1:].any() and len(tail) <= 8
         checked += 1
     assert checked >= 2
+
+
+def test_all_skip_slices_match_a_live_reference_run(host_lib):
+    """A static clip at a fine quantiser: P pictures of 98 and 99 P_Skip macroblocks out of 99 — the slice data is (almost) nothing
+    but the mb_skip_run that ends the slice (rbsp_encoding.cpp:310)."""
+    import tempfile
+    from h264_fer_b200 import native as fh, synth
+    from oracle import refdump
+    if not refdump.have_ref_encoder():
+        pytest.skip("oracle/_ref/ref_encoder not built")
+    y4m = os.path.join(tempfile.mkdtemp(prefix="fh264_cavlc_static_"), "in.y4m")
+    synth.write_y4m(y4m, 176, 144, 31, 4, pan=(0, 0), noise=0.0, square=False)
+    _, dump, _ = refdump.run_reference(y4m, 4, qp=12, intra_every=2, dumpmask=refdump.D_MBREC | refdump.D_SLICE)
+    skipped = []
+    for n, p in enumerate(refdump.parse_dump(dump)):
+        if "mbrec" not in p:
+            continue
+        r = p["mbrec"]
+        rec = np.zeros(len(r), fh.MB_RESULT_DTYPE)
+        rec["mb_type"] = r[:, 0]
+        rec["num_parts"] = [{0: 1, 1: 2, 2: 2, 4: 4, 31: 0}[int(t)] for t in r[:, 0]]
+        rec["mv"], rec["mvd"] = r[:, 1:9].reshape(-1, 4, 2), r[:, 9:17].reshape(-1, 4, 2)
+        rec["luma"], rec["chroma_dc"], rec["chroma_ac"] = r[:, 21:277].reshape(-1, 16, 16), r[:, 277:285].reshape(-1, 2, 4), r[:, 285:405].reshape(-1, 2, 4, 15)
+        bit0 = p["slice_bit0"]
+        out = np.zeros(len(p["rbsp"]) + 64, np.uint8)
+        nbits, bad = C.c_int(0), C.c_int(0)
+        rc = host_lib.cavlc_host_slice(rec.ctypes.data_as(C.c_void_p), len(rec), 11, bit0 % 8, out.ctypes.data_as(C.c_void_p), len(out), C.byref(nbits), C.byref(bad))
+        assert rc == 0 and bad.value == 0
+        nd = nbits.value - bit0 % 8
+        ref_bits = bits_of(p["rbsp"])
+        assert np.array_equal(bits_of(out)[bit0 % 8:bit0 % 8 + nd], ref_bits[bit0:bit0 + nd]), "picture %d" % n
+        tail = ref_bits[bit0 + nd:]
+        assert tail[0] == 1 and not tail[1:].any() and len(tail) <= 8
+        skipped.append(int((r[:, 0] == 31).sum()))
+    assert skipped and max(skipped) == 99

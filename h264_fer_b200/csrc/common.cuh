@@ -26,6 +26,8 @@
 #define ST_TICKET 10
 #define ST_FLAGS_NEXT 11   // flags raised by phase R for the NEXT picture's reference
 #define ST_S2REDO 12       // number of partitions that overflowed the fast stage-2 launch
+#define ST_SPEC_HIT 13     // partitions decided from the speculative finalists (spec.cuh)
+#define ST_SPEC_MISS 14    // partitions that took the full search inside the wavefront
 #define ST_WORDS 16
 #define FLAG_UB_INPUT 1u
 #define FLAG_CAPACITY 2u
@@ -55,6 +57,8 @@ struct PartA { uint16_t suma[5]; uint16_t n3; uint32_t s2_off; uint32_t n2; };  
 // content: thousands of positions share one 8x8 sum); phase B enumerates it itself once the predictor is known (stage2_slow).
 #define S2_SLOW 0x80000000u
 
+struct PartSpec;                     // spec.cuh: finalists per partition for the guessed integer predictors
+
 static_assert(sizeof(fh264_mb_result) == 832, "ABI record size");
 static_assert(sizeof(MbMotion) == 48, "MbMotion size");
 
@@ -74,6 +78,8 @@ struct SeqDev {
     uint32_t *s2redo;       // partitions whose gated survivors overflowed the fast stage-2 launch (count in status[ST_S2REDO])
     MbMotion *motion;       // nmb
     unsigned long long *qmv; // nmb * 4 tagged quadrant words (phase B wavefront): epoch << 32 | mvy << 16 | (mvx & 0xffff)
+    PartSpec *spec;         // nparts: speculative finalists of the 8x8 search (phase S, read by phase B)
+    uint32_t *prev_gen;     // nparts: mvp >> 2 phase B used for the partition in the previous P picture (genx & 0xffff | geny << 16)
     fh264_mb_result *results;
     uint32_t *status;       // ST_WORDS
     // band mode: the same buffers of the other ranks, mapped through CUDA IPC (NVLink peer access)

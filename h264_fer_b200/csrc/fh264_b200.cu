@@ -58,6 +58,8 @@ struct fh264_session {
     unsigned long long *d_sadout;
     cudaEvent_t ev[5];
     cudaEvent_t evk[4];             // after stage3, after interp, after features (per-kernel split of phases A and R)
+    cudaEvent_t ev_spec;            // after stage 2, before phase S
+    int use_spec;                   // phase S + fast path in phase B (FH264_SPEC=0 turns it off: every partition takes the full search)
     bool timed;
     std::vector<void *> allocs;
     // scratch for the stand-alone entry points
@@ -86,7 +88,7 @@ __global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
     uint32_t *st = seqs[seq0 + threadIdx.x].status;
     st[ST_FLAGS] = st[ST_FLAGS_NEXT];
     for (int i = 0; i < 5; i++) st[ST_COUNTS + i] = 0;
-    st[ST_S2REDO] = 0;
+    st[ST_S2REDO] = 0; st[ST_SPEC_HIT] = 0; st[ST_SPEC_MISS] = 0;
     if (threadIdx.x == 0) *ticket = 0;
 }
 __global__ void k_begin_ref(SeqDev *seqs, int seq0) { seqs[seq0 + threadIdx.x].status[ST_FLAGS_NEXT] = 0; }
@@ -159,6 +161,7 @@ extern "C" int fh264_close(fh264_session *s)
     if (s->h_cvstat) cudaFreeHost(s->h_cvstat);
     for (int i = 0; i < 5; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int i = 0; i < 4; i++) if (s->evk[i]) cudaEventDestroy(s->evk[i]);
+    if (s->ev_spec) cudaEventDestroy(s->ev_spec);
     for (int i = 0; i < 2; i++) if (s->ev_i[i]) cudaEventDestroy(s->ev_i[i]);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -197,6 +200,8 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->d_sadout = nullptr; s->scr_mbs = 0;
     for (int i = 0; i < 5; i++) s->ev[i] = nullptr;
     for (int i = 0; i < 4; i++) s->evk[i] = nullptr;
+    s->ev_spec = nullptr;
+    { const char *e = getenv("FH264_SPEC"); s->use_spec = !(e && atoi(e) == 0); }
     for (int i = 0; i < 3; i++) s->d_scr[i] = nullptr;
     s->d_scr16[0] = s->d_scr16[1] = nullptr;
     Geo &g = s->g;
@@ -222,6 +227,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     OPEN_CK(cudaEventCreateWithFlags(&s->ev_copy_done, cudaEventDisableTiming));
     for (int i = 0; i < 5; i++) OPEN_CK(cudaEventCreate(&s->ev[i]));
     for (int i = 0; i < 4; i++) OPEN_CK(cudaEventCreate(&s->evk[i]));
+    OPEN_CK(cudaEventCreate(&s->ev_spec));
     OPEN_CK(cudaHostAlloc((void **)&s->h_status, sizeof(uint32_t) * ST_WORDS * batch, cudaHostAllocDefault));
     OPEN_CK(cudaHostAlloc((void **)&s->h_sad, sizeof(uint64_t) * batch, cudaHostAllocDefault));
     OPEN_CK(dalloc(s, &s->d_sadout, (size_t)batch));
@@ -247,6 +253,9 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         OPEN_CK(dalloc(s, &S.s2pool, (size_t)S.s2pool_size));
         OPEN_CK(dalloc(s, &S.s2redo, (size_t)S2_REDO_MAX));
         OPEN_CK(dalloc(s, &S.motion, (size_t)g.nmb));
+        OPEN_CK(dalloc(s, &S.spec, (size_t)g.nparts));
+        OPEN_CK(dalloc(s, &S.prev_gen, (size_t)g.nparts));
+        OPEN_CK(cudaMemset(S.prev_gen, 0x7f, sizeof(uint32_t) * (size_t)g.nparts));       // SPEC_PREV_NONE: no previous P picture
         OPEN_CK(dalloc(s, &S.qmv, (size_t)g.nmb * 4));
         OPEN_CK(dalloc(s, &S.status, (size_t)ST_WORDS));
         S.results = results + (size_t)b * g.nmb;
@@ -269,6 +278,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     OPEN_CK(dalloc(s, &s->d_sync, (size_t)FH_MAX_WORLD));
     OPEN_CK(cudaFuncSetAttribute(k_tile_index, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_CELLS * 4));
     OPEN_CK(cudaFuncSetAttribute(k_stage3, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    OPEN_CK(cudaFuncSetAttribute(k_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     OPEN_CK(cudaDeviceSynchronize());
     *out = s;
     return FH264_OK;
@@ -472,12 +482,19 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         dim3 g2r(S2_REDO_MAX, nseq);
         k_stage2<S2_CAP_BIG, 1, true><<<g2r, 32, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
+    CK(cudaEventRecord(s->ev_spec, st));
+    if (s->use_spec) {
+        // phase S: the search completed for the guessed integer predictors (spec.cuh)
+        const int g1 = prm.window / 16, n1 = (2 * g1 + 1) * (2 * g1 + 1) * 16, npad1 = (n1 + 31) & ~31;
+        const size_t smems = 4 * sizeof(SpecWarp) + (size_t)4 * npad1 * sizeof(uint32_t);
+        k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, npad1, 1);
+    }
     CK(cudaEventRecord(s->ev[1], st));
     // persistent wavefront CTAs: two anti-diagonals' worth per sequence — one set working, one set that has already
     // drawn its ticket and prefetched (otherwise ticket + prefetch latency sits on the wavefront's critical path)
     unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, (long long)nseq * (g.Wmb + 16));
     { static const char *e = getenv("FH264_PB_CTAS"); if (e && atoi(e) > 0) pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, atoll(e)); }   // development knob
-    k_phase_b<<<pb_ctas, PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket);
+    k_phase_b<<<pb_ctas, PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket, s->use_spec);
     CK(cudaEventRecord(s->ev[2], st));
     dim3 gc((g.band_nmb + 3) / 4, nseq);
     if (s->copy_pending) { CK(cudaStreamWaitEvent(st, s->ev_copy_done, 0)); s->copy_pending = false; }   // records of the previous picture are home
@@ -761,10 +778,21 @@ extern "C" int fh264_last_timings(fh264_session *s, float ms[10])
     for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms[i], s->ev[i], s->ev[i + 1]));
     CK(cudaEventElapsedTime(&ms[4], s->ev[0], s->ev[4]));
     CK(cudaEventElapsedTime(&ms[5], s->ev[0], s->evk[0]));      // k_stage3 (+ k_begin_picture)
-    CK(cudaEventElapsedTime(&ms[6], s->evk[0], s->ev[1]));      // k_stage2
+    CK(cudaEventElapsedTime(&ms[6], s->evk[0], s->ev_spec));    // k_stage2
     CK(cudaEventElapsedTime(&ms[7], s->evk[1], s->evk[2]));     // k_interp
     CK(cudaEventElapsedTime(&ms[8], s->evk[2], s->evk[3]));     // k_features
     CK(cudaEventElapsedTime(&ms[9], s->evk[3], s->ev[4]));      // k_tile_index
+    return FH264_OK;
+}
+
+// k_spec (phase S) of the last encode_p, in ms (0 when FH264_SPEC=0)
+extern "C" int fh264_last_spec_ms(fh264_session *s, float *ms)
+{
+    if (!s || !ms) return fail(FH264_E_ARG, "null argument");
+    if (!s->timed) return fail(FH264_E_STATE, "no encode_p issued yet");
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventSynchronize(s->ev[4]));
+    CK(cudaEventElapsedTime(ms, s->ev_spec, s->ev[1]));
     return FH264_OK;
 }
 

@@ -15,6 +15,7 @@
 #include "qfeat.cuh"
 #include "phase_a.cuh"
 #include "phase_c.cuh"
+#include "spec.cuh"
 
 #define PB_NT 128
 #ifndef PB_MINB
@@ -123,6 +124,7 @@ struct PBShared {
     NbCache nc;
     u64 best[2][4];                      // per-warp minima, double-buffered across partitions
     u64 sel_min[4]; int sel_cnt[4];      // lazy stage-2 verification
+    __align__(16) PartSpec spec[4];      // phase-S finalists of the four partitions (spec.cuh)
     PartA pa[4];                         // phase-A products of the four partitions, fetched BEFORE the dependency wait
     S3Entry s3[4][FH_S3_MAX + 1];
     uint2 pool[4][PB_POOL_PREF];
@@ -390,7 +392,7 @@ __device__ __noinline__ u64 stage2_slow(const SeqDev &S, const Geo &g, PBShared 
 }
 
 __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__restrict__ seqs, int seq0, int nseq, Geo g, fh264_params prm,
-                                                   uint32_t epoch, const int *__restrict__ wf_order, uint32_t *__restrict__ ticket)
+                                                   uint32_t epoch, const int *__restrict__ wf_order, uint32_t *__restrict__ ticket, int use_spec)
 {
     __shared__ PBShared sh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
     // ---- everything that does not depend on the neighbours is fetched BEFORE waiting on them: the CTA is resident
     //      long before its turn, so these round trips are off the wavefront's critical path
     if (tid < 16) *(uint4 *)&sh.cur[tid][0] = *(const uint4 *)(S.cur[0] + (size_t)(mby * 16 + tid) * W + mbx * 16);
+    if (use_spec && tid >= 96) ((uint4 *)sh.spec)[tid - 96] = ((const uint4 *)&S.spec[(size_t)mb * 4])[tid - 96];       // 4 x 128 bytes
     if (!prm.basic) {
         if (tid >= 32 && tid < 36) sh.pa[tid - 32] = S.parta[mb * 4 + tid - 32];
         for (int i = tid; i < 4 * FH_S3_MAX; i += PB_NT) { const int pi = i / FH_S3_MAX, k = i - pi * FH_S3_MAX; sh.s3[pi][k] = S.s3[(size_t)(mb * 4 + pi) * FH_S3_MAX + k]; }
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
     uint32_t *qx = sh.qx + warp * (qpw * qps);
     uint16_t *qrc = sh.qrc + warp * (qpw * qps);
     int callno = 0;                  // alternates BlockSel's survivor counters (uniform across the block)
+    int nhit = 0;                    // partitions decided from the phase-S finalists
     int l1x = 0, l1y = 0, l3x = 0, l3y = 0;                           // left MB's quadrants 1 / 3 once fetched
     for (int pi = 0; pi < 4; pi++) {
         const int xP = mbx * 16 + (pi & 1) * 8, yP = mby * 16 + (pi >> 1) * 8;
@@ -562,6 +566,31 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
         mvps[pi][0] = mvpx; mvps[pi][1] = mvpy;
         PB_SUB(12);
         const int genx = mvpx >> 2, geny = mvpy >> 2;
+        if (tid == 0) S.prev_gen[(size_t)mb * 4 + pi] = ((uint32_t)genx & 0xffffu) | ((uint32_t)geny << 16);      // next picture's temporal guess
+        int bx = 0, by = 0, bs = 0;
+        // Speculative fast path (spec.cuh): phase S already ran the whole search for up to two guessed values of gen and left the
+        // few candidates that can win for some predictor of that cell; with the true predictor known the winner is the first
+        // minimum of SAD + |mv - mvp|_1 in (stage, list position) order among them (:460-469,498-507,511-520). Block-uniform.
+        bool hit = false;
+        if (use_spec) {
+            const PartSpec &sp = sh.spec[pi];
+            int slot = -1;
+            if (sp.nf[0] != SPEC_INVALID && sp.gx[0] == genx && sp.gy[0] == geny) slot = 0;
+            else if (sp.nf[1] != SPEC_INVALID && sp.gx[1] == genx && sp.gy[1] == geny) slot = 1;
+            if (slot >= 0) {
+                const int nf = sp.nf[slot];
+                u64 bk = KEY_NONE;
+                for (int k = 0; k < nf; k++) {
+                    const SpecFinal f = sp.f[slot][k];
+                    const u64 key = ((u64)((int)f.sad + mv_cost(f.mvx, f.mvy, mvpx, mvpy)) << 32) | ((u64)f.order << 16) | (u64)k;
+                    bk = min(bk, key);
+                }
+                const SpecFinal f = sp.f[slot][(int)(bk & 15)];
+                bx = f.mvx; by = f.mvy; bs = f.sad;
+                hit = true; nhit++;
+            }
+        }
+        if (!hit) {
         const PartA pa = sh.pa[pi];
         u64 *best = sh.best[pi & 1];
         u64 mine = KEY_NONE;
@@ -736,7 +765,6 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
         // decode the winner from its key (:523-527); no candidate at all leaves bx = by = 0 (:452)
         const u64 b = min(min(best[0], best[1]), min(best[2], best[3]));
         PB_SUB(17);
-        int bx = 0, by = 0, bs = 0;
         if (b != KEY_NONE) {
             const int stage = (int)((b >> 42) & 3), total = (int)(b >> 44);
             if (stage == 0) {
@@ -758,6 +786,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
             const uint8_t *pl = S.planes;
             for (int rr2 = 0; rr2 < 8; rr2++) bs += sad_row8(*(const uint2 *)&sh.cur[(pi >> 1) * 8 + rr2][(pi & 1) * 8], pl, W, H, xP, yP + rr2);
         }
+        }   // !hit
         mv[pi][0] = bx; mv[pi][1] = by; sadq[pi] = bs;
         if (tid == 0) {
             // publish this quadrant's MV at once: the right and lower-left neighbours can start before this MB is finished
@@ -809,6 +838,8 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
         d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
         PB_STAMP(9);
         atomicAdd(&S.status[ST_COUNTS + cnt], 1u);
+        if (nhit) atomicAdd(&S.status[ST_SPEC_HIT], (uint32_t)nhit);
+        if (nhit < 4) atomicAdd(&S.status[ST_SPEC_MISS], (uint32_t)(4 - nhit));
     }
   }
 }

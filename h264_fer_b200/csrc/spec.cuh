@@ -1,0 +1,286 @@
+// Phase S — speculative completion of the 8x8 search, fully parallel over partitions (one warp each).
+//
+// Everything in interEncoding's per-partition search (moestimation.cpp:430-528) that depends on the MV predictor depends on
+// it in two steps: the three candidate lists depend only on gen = mvp >> 2 (window centre of stage 1 and the multiplier
+// |dx-genx|+|dy-geny|+4 of stages 1 and 2, :433-437,458,492-494; stage 3 uses centre 0, :509-510), and the final choice
+// argmin(SAD + |mv-mvp|_1) (:460-469,498-507,511-520) on mvp itself. The predictor is only known inside the wavefront
+// (phase B), but gen is highly predictable: it equals the integer part of the partition's own best stage-3 vector, or the
+// gen the same partition had one picture earlier, for ~99 % of the partitions of moving content. So for up to two GUESSED
+// values of gen this kernel runs stage 1 (feature window around the guess, 17 best, SADs), ranks the stage-2 set with the
+// guess's multiplier (33 best) and takes the stage-3 list, and reduces the <= 83 evaluated candidates to the few FINALISTS
+// that can win for SOME mvp of the guessed cell [4*gen, 4*gen+3]^2:
+//   hi(c) = SAD(c) + max over the cell of |mv(c)-mvp|_1,  lo(c) likewise with min;   U = min_c hi(c)
+//   c can be the strict first minimum for some mvp of the cell only if lo(c) <= U; of candidates with equal MVs only the
+//   first in (stage, list position) order can. (Exact: the candidate attaining U beats every c with lo(c) > U for every
+//   mvp of the cell, strictly.)
+// Phase B then only compares gen with the guesses and evaluates the finalists (<= SPEC_NF, 1.4 on average) with the true
+// mvp; a wrong guess, an overflow or an oversized stage-2 set falls back to the full search there. Results never depend on
+// the guesses — only the time does.
+#pragma once
+#include "common.cuh"
+#include "warp_select.cuh"
+#include "qfeat.cuh"
+#include "phase_a.cuh"
+
+#define SPEC_NF 7
+#define SPEC_INVALID 0xffu
+#define SPEC_NOGUESS 0x7fff
+#define SPEC_PF_CAP 96           // stage 1 (17) + stage 2 (33) + stage 3 (33) evaluated candidates at most
+#define SPEC_PREV_NONE 0x7f7f7f7fu     // cudaMemset(0x7f): no previous P picture
+
+struct __align__(8) SpecFinal { int16_t mvx, mvy; uint16_t sad, order; };        // order = stage << 14 | list position
+struct __align__(16) PartSpec {
+    int16_t gx[2], gy[2];         // guessed gen per slot (SPEC_NOGUESS: none)
+    uint8_t nf[2];                // finalists per slot (SPEC_INVALID: slot unusable)
+    uint8_t pad[6];
+    SpecFinal f[2][SPEC_NF];
+};
+static_assert(sizeof(PartSpec) == 128, "PartSpec size");
+
+// |v - t| over t in [4g, 4g+3] with a = v - 4g: smallest and largest value
+__device__ __forceinline__ int cell_min_(int a) { return a < 0 ? -a : (a > 3 ? a - 3 : 0); }
+__device__ __forceinline__ int cell_max_(int a) { return max(iabs_(a), iabs_(a - 3)); }
+
+struct SpecWarp {
+    WarpSelScratch ws;                       // selection scratch; before that the row sums of the feature window (qfeat.cuh)
+    uint16_t members[FH_S1_MAX + 3];
+    uint16_t msad[FH_S1_MAX + 3];
+    S3Entry s3[FH_S3_MAX + 1];
+    uint32_t pf_mv[SPEC_PF_CAP];             // evaluated candidates that can still win: mvx & 0xffff | mvy << 16
+    uint32_t pf_so[SPEC_PF_CAP];             // sad | order << 16
+};
+
+// MEstimation(g = window/16, all 16 fractions, gen = centre = (Gx, Gy)) (moestimation.cpp:254-296 as called at :458):
+// cost[((dx+g1)*w1 + (dy+g1))*16 + frac] for the displacements dx, dy relative to the centre; COST_INVALID where the block
+// origin leaves the picture (:265). The features of the quarter-pel planes come from the planes themselves (qfeat.cuh), a few
+// planes per batch, through the X / RC scratch. m1 <= m2 collect this lane's two smallest costs (selection bound).
+__device__ __forceinline__ void window_costs(const SeqDev &S, const Geo &g, int xP, int yP, int Gx, int Gy, int g1, const FeatQ &fq,
+                                             uint32_t *cost, uint32_t *X, uint16_t *RC, uint32_t &m1, uint32_t &m2)
+{
+    const int lane = threadIdx.x & 31, W = g.W, H = g.H;
+    const int w1 = 2 * g1 + 1, npos = w1 * w1, R = 8 + w1 - 1, ps = R * w1, pb = w1 <= 5 ? 4 : 1;
+    const uint32_t iR = udiv_magic((uint32_t)R), iN = udiv_magic((uint32_t)npos), i1 = udiv_magic((uint32_t)w1);
+    const int x0 = xP + Gx - g1, y0 = yP + Gy - g1;
+    for (int f0 = 0; f0 < 16; f0 += pb) {
+        for (int sg0 = 0; sg0 < pb * R; sg0 += 64) {
+            uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;
+            const int sa = sg0 + lane, sb = sg0 + 32 + lane;
+            const int fa = udiv_by(sa, iR), ra = sa - fa * R, fb = udiv_by(sb, iR), rb = sb - fb * R;
+            if (sa < pb * R) wa = qf_load16(S.planes + (size_t)(f0 + fa) * g.WH, W, H, x0, y0 + ra);
+            if (sb < pb * R) wb = qf_load16(S.planes + (size_t)(f0 + fb) * g.WH, W, H, x0, y0 + rb);
+            if (sa < pb * R) qf_row_sums(wa, w1, X + fa * ps + ra * w1, RC + fa * ps + ra * w1);
+            if (sb < pb * R) qf_row_sums(wb, w1, X + fb * ps + rb * w1, RC + fb * ps + rb * w1);
+        }
+        __syncwarp();
+        const int rot = (f0 * 13) % (pb * npos);
+        for (int o0 = lane; o0 < pb * npos; o0 += 32) {
+            const int o = o0 + rot < pb * npos ? o0 + rot : o0 + rot - pb * npos;
+            const int fl = udiv_by(o, iN), pos = o - fl * npos, cx = udiv_by(pos, i1), cy = pos - cx * w1;
+            const int rx = x0 + cx, ry = y0 + cy;
+            uint32_t cst = COST_INVALID;
+            if (rx >= 0 && rx < W && ry >= 0 && ry < H)
+                cst = (uint32_t)((iabs_(cx - g1) + iabs_(cy - g1) + 4) * feat_of(fq, qf_record(X, RC, fl, ps, w1, cx, cy)));
+            cost[pos * 16 + f0 + fl] = cst;
+            m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void pf_emit(bool have, int mvx, int mvy, int sad, int order, SpecWarp *sw, int &npf)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned b = __ballot_sync(0xffffffffu, have);
+    if (have) {
+        const int p = npf + __popc(b & ((1u << lane) - 1u));
+        if (p < SPEC_PF_CAP) { sw->pf_mv[p] = ((uint32_t)mvx & 0xffffu) | ((uint32_t)mvy << 16); sw->pf_so[p] = (uint32_t)sad | ((uint32_t)order << 16); }
+    }
+    npf += __popc(b);
+}
+
+// The finalists of one partition for one guessed gen = (Gx, Gy) into out->f[slot]. Warp-uniform call.
+__device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const fh264_params &prm, int part, int xP, int yP, const uint2 (&rows)[8],
+                                          const FeatQ &fq, int n3, uint32_t n2w, uint32_t s2_off, int Gx, int Gy, int slot,
+                                          SpecWarp *sw, uint32_t *cost, PartSpec *out)
+{
+    const int lane = threadIdx.x & 31, W = g.W, H = g.H;
+    const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16;
+    const uint32_t i1 = udiv_magic((uint32_t)w1);
+    const int cxq = 4 * Gx, cyq = 4 * Gy;
+    int npf = 0;
+    bool usable = !(n2w & S2_SLOW);                        // oversized stage-2 set: phase B enumerates it itself
+    // ---- stage 3 (list of phase A, SADs known): bound U, then the entries that can still win
+    int U = 0x7fffffff;
+    for (int i = lane; i < n3; i += 32) {
+        const S3Entry e = sw->s3[i];
+        U = min(U, (int)e.sad + cell_max_(e.mvx - cxq) + cell_max_(e.mvy - cyq));
+    }
+    U = __reduce_min_sync(0xffffffffu, U);
+    for (int i0 = 0; i0 < n3; i0 += 32) {
+        const int i = i0 + lane;
+        bool have = false; int mvx = 0, mvy = 0, sad = 0;
+        if (i < n3) {
+            const S3Entry e = sw->s3[i];
+            mvx = e.mvx; mvy = e.mvy; sad = e.sad;
+            have = sad + cell_min_(mvx - cxq) + cell_min_(mvy - cyq) <= U;
+        }
+        pf_emit(have, mvx, mvy, sad, (2 << 14) | i, sw, npf);
+    }
+    // ---- stage 2 (:470-507): candidates of phase A in arrival order with feature distance and SAD. List membership = one of
+    //      the 33 smallest keys (cost << 10 | arrival); only candidates that can still win have their rank counted.
+    if (usable) {
+        const int n2 = (int)n2w;
+        const uint2 *__restrict__ pool = S.s2pool + s2_off;
+        for (int i0 = 0; i0 < n2; i0 += 32) {
+            const int i = i0 + lane;
+            bool pot = false; int dx = 0, dy = 0, sad = 0; uint32_t cst = 0;
+            if (i < n2) {
+                const uint2 v = __ldg(&pool[i]);
+                dx = (int16_t)(v.x & 0xffff); dy = (int16_t)(v.x >> 16); sad = (int)(v.y >> 18);
+                cst = (uint32_t)(iabs_(dx - Gx) + iabs_(dy - Gy) + 4) * (v.y & 0x3ffffu);
+                pot = cst < (uint32_t)FH_COST_EMPTY && sad + cell_min_(4 * dx - cxq) + cell_min_(4 * dy - cyq) <= U;
+            }
+            unsigned pm = __ballot_sync(0xffffffffu, pot);
+            bool member = false; int myrank = 0;
+            while (pm) {
+                const int src = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t ci = __shfl_sync(0xffffffffu, cst, src);
+                const int ii = i0 + src;
+                int c = 0;
+                for (int j = lane; j < n2; j += 32) {
+                    const uint2 w = __ldg(&pool[j]);
+                    const int jx = (int16_t)(w.x & 0xffff), jy = (int16_t)(w.x >> 16);
+                    const uint32_t cj = (uint32_t)(iabs_(jx - Gx) + iabs_(jy - Gy) + 4) * (w.y & 0x3ffffu);
+                    c += (cj < ci) || (cj == ci && j < ii);
+                }
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (lane == src) { member = c < FH_S3_MAX; myrank = c; }
+            }
+            pf_emit(member, dx * 4, dy * 4, sad, (1 << 14) | myrank, sw, npf);
+        }
+    }
+    // ---- stage 1 (:458-469): feature window around the guess, 17 best by (cost, arrival), their SADs
+    {
+        uint32_t m1 = COST_INVALID, m2 = COST_INVALID;
+        window_costs(S, g, xP, yP, Gx, Gy, g1, fq, cost, (uint32_t *)sw->ws.skey, sw->ws.sidx, m1, m2);
+        __syncwarp();
+        const int nvalid = max(0, min(W - 1, xP + Gx + g1) - max(0, xP + Gx - g1) + 1) * max(0, min(H - 1, yP + Gy + g1) - max(0, yP + Gy - g1) + 1) * 16;
+        const int nm = warp_select_costs(cost, n1, FH_S1_MAX, nvalid, m1, m2, &sw->ws, sw->members);
+        const int r = lane & 7;
+        const uint2 cr = pick_row(rows, r);
+        for (int base = 0; base < nm; base += 4 * 5) {
+            uint2 rr[5];
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+                const int m = base + u * 4 + (lane >> 3);
+                rr[u] = make_uint2(0, 0);
+                if (m < nm) {
+                    const int i = (int)sw->members[m], f = i & 15, pos = i >> 4, cx = udiv_by(pos, i1), dx = Gx + cx - g1, dy = Gy + pos - cx * w1 - g1;
+                    rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, xP + dx, yP + dy + r);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+                const int m = base + u * 4 + (lane >> 3);
+                int sad = m < nm ? sad8(cr, rr[u]) : 0;
+                sad += __shfl_xor_sync(0xffffffffu, sad, 1);
+                sad += __shfl_xor_sync(0xffffffffu, sad, 2);
+                sad += __shfl_xor_sync(0xffffffffu, sad, 4);
+                if (m < nm && r == 0) sw->msad[m] = (uint16_t)sad;
+            }
+        }
+        __syncwarp();
+        {
+            const int m = lane;
+            bool have = false; int mvx = 0, mvy = 0, sad = 0;
+            if (m < nm) {
+                const int i = (int)sw->members[m], f = i & 15, pos = i >> 4, cx = udiv_by(pos, i1), dx = Gx + cx - g1, dy = Gy + pos - cx * w1 - g1;
+                mvx = (dx << 2) | (f & 3); mvy = (dy << 2) | (f >> 2); sad = sw->msad[m];
+                have = sad + cell_min_(mvx - cxq) + cell_min_(mvy - cyq) <= U;
+            }
+            pf_emit(have, mvx, mvy, sad, m, sw, npf);
+        }
+    }
+    __syncwarp();
+    // ---- finalists: bound over everything still in the race, duplicates of one MV dropped (the first in list order stays)
+    if (npf > SPEC_PF_CAP) usable = false;                 // cannot happen (17 + 33 + 33 candidates at most)
+    const int n = min(npf, SPEC_PF_CAP);
+    int Uf = 0x7fffffff;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t mv = sw->pf_mv[i], so = sw->pf_so[i];
+        Uf = min(Uf, (int)(so & 0xffffu) + cell_max_((int)(int16_t)(mv & 0xffffu) - cxq) + cell_max_((int)(int16_t)(mv >> 16) - cyq));
+    }
+    Uf = __reduce_min_sync(0xffffffffu, Uf);
+    int nf = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false; uint32_t mv = 0, so = 0;
+        if (i < n) {
+            mv = sw->pf_mv[i]; so = sw->pf_so[i];
+            keep = (int)(so & 0xffffu) + cell_min_((int)(int16_t)(mv & 0xffffu) - cxq) + cell_min_((int)(int16_t)(mv >> 16) - cyq) <= Uf;
+            for (int j = 0; j < n && keep; j++) keep = !(sw->pf_mv[j] == mv && (sw->pf_so[j] >> 16) < (so >> 16));
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int p = nf + __popc(b & ((1u << lane) - 1u));
+            if (p < SPEC_NF) {
+                SpecFinal sf;
+                sf.mvx = (int16_t)(mv & 0xffffu); sf.mvy = (int16_t)(mv >> 16); sf.sad = (uint16_t)(so & 0xffffu); sf.order = (uint16_t)(so >> 16);
+                out->f[slot][p] = sf;
+            }
+        }
+        nf += __popc(b);
+    }
+    if (nf > SPEC_NF || nf == 0) usable = false;
+    if (lane == 0) {
+        out->gx[slot] = (int16_t)Gx; out->gy[slot] = (int16_t)Gy;
+        out->nf[slot] = usable ? (uint8_t)nf : (uint8_t)SPEC_INVALID;
+    }
+    __syncwarp();
+}
+
+// One warp per partition, four per CTA (one macroblock). Guesses: the integer part of the partition's best stage-3 vector by
+// SAD, and the gen phase B used for this partition in the previous P picture (use_prev).
+__global__ void __launch_bounds__(128, 6) k_spec(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad1, int use_prev)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SpecWarp *sw = (SpecWarp *)smem_raw + warp;
+    uint32_t *cost = (uint32_t *)(smem_raw + 4 * sizeof(SpecWarp)) + (size_t)warp * npad1;
+    const SeqDev &S = seqs[seq0 + blockIdx.y];
+    const int part = g.band_mb0 * 4 + blockIdx.x * 4 + warp;
+    int xP, yP;
+    part_origin(g, part, xP, yP);
+    uint2 rows[8];
+    load_cur8x8(S.cur[0], g, xP, yP, rows);
+    int s[5];
+    block_sums(rows, s);
+    const FeatQ fq = feat_query(s);
+    PartSpec *out = &S.spec[part];
+    int n3 = 0; uint32_t n2w = 0, s2_off = 0;
+    if (!prm.basic) { const PartA pa = S.parta[part]; n3 = pa.n3; n2w = pa.n2; s2_off = pa.s2_off; }
+    for (int i = lane; i < n3; i += 32) sw->s3[i] = S.s3[(size_t)part * FH_S3_MAX + i];
+    __syncwarp();
+    // guesses
+    int g0x = 0, g0y = 0, g1x = 0, g1y = 0, ng = 0;
+    if (n3 > 0) {
+        uint32_t k = 0xffffffffu;
+        for (int i = lane; i < n3; i += 32) k = min(k, ((uint32_t)sw->s3[i].sad << 8) | (uint32_t)i);
+        k = __reduce_min_sync(0xffffffffu, k);
+        const S3Entry e = sw->s3[k & 255u];
+        g0x = e.mvx >> 2; g0y = e.mvy >> 2; ng = 1;
+    }
+    if (use_prev) {
+        const uint32_t pg = S.prev_gen[part];
+        if (pg != SPEC_PREV_NONE) {
+            const int px = (int16_t)(pg & 0xffffu), py = (int16_t)(pg >> 16);
+            if (ng == 0) { g0x = px; g0y = py; ng = 1; }
+            else if (px != g0x || py != g0y) { g1x = px; g1y = py; ng = 2; }
+        }
+    }
+    if (ng == 0) ng = 1;                                   // no list and no history: guess gen = (0, 0)
+    for (int slot = 0; slot < ng; slot++)
+        spec_slot(S, g, prm, part, xP, yP, rows, fq, n3, n2w, s2_off, slot ? g1x : g0x, slot ? g1y : g0y, slot, sw, cost, out);
+    if (ng == 1 && lane == 0) { out->gx[1] = SPEC_NOGUESS; out->gy[1] = SPEC_NOGUESS; out->nf[1] = SPEC_INVALID; }
+}

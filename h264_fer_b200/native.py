@@ -31,7 +31,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_frame", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
-           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_cavlc_i", "fh264_last_timings", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
+           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_cavlc_i", "fh264_last_timings", "fh264_last_spec_ms", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
 
 
 class Fh264Error(RuntimeError):
@@ -87,6 +87,7 @@ def load_library():
     L.fh264_debug_plane.argtypes = [vp, i32, i32, u8p]
     L.fh264_debug_feature.argtypes = [vp, i32, i32, i32, vp]
     L.fh264_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
+    L.fh264_last_spec_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.fh264_debug_timeline.argtypes = [vp, i32, vp]
     L.fh264_cavlc_p.argtypes = [vp, i32, i32, i32, vp, C.c_size_t, vp, vp]
     L.fh264_decode_p.argtypes = [vp, i32, i32, i32, vp]
@@ -242,7 +243,11 @@ class Session:
         self._ck(self.L.fh264_last_timings(self.handle, t))
         names = ("phase_a_ms", "phase_b_ms", "phase_c_ms", "copy_phase_r_ms", "total_ms", "k_stage3_ms", "k_stage2_ms",
                  "k_interp_ms", "k_features_ms", "k_tile_index_ms")
-        return dict(zip(names, [float(x) for x in t]))
+        d = dict(zip(names, [float(x) for x in t]))
+        ms = C.c_float(0)
+        self._ck(self.L.fh264_last_spec_ms(self.handle, C.byref(ms)))
+        d["k_spec_ms"] = float(ms.value)
+        return d
 
     # -- building blocks
     def tq_macroblocks(self, src384, pred384, qp):

@@ -164,6 +164,9 @@ int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint16_t *out);
  * [3] result copies + phase R (reference preparation for the next picture), [4] total; per kernel:
  * [5] k_stage3, [6] k_stage2, [7] k_interp, [8] k_features, [9] k_tile_index. */
 int fh264_last_timings(fh264_session *s, float ms[10]);
+/* Phase S of the last fh264_encode_p (k_spec: the search completed in parallel for the guessed integer predictors, so that the
+ * wavefront only evaluates a handful of finalists per 8x8 partition), milliseconds; it is part of [0] above. */
+int fh264_last_spec_ms(fh264_session *s, float *ms);
 
 /* ---- device entropy coding of a P slice ---------------------------------------------------------
  * slice_data() of the P picture last coded by fh264_encode_p for sequences [seq0, seq0 + nseq): what the P-slice macroblock

@@ -397,3 +397,34 @@ def test_tiny_pictures_against_oracle(w, h):
         for a, b in zip(recon, want_recon):
             assert np.array_equal(a, b)
         assert bits > 0
+
+
+@pytest.mark.parametrize("spec", ["1", "0"])
+def test_speculative_fast_path_and_full_search_agree_with_the_oracle(spec, monkeypatch):
+    """Phase S (spec.cuh) guesses the integer predictor and leaves finalists; phase B falls back to the full search on a wrong
+    guess. Both paths against the oracle over chained pictures (the second picture also has the temporal guess), with the
+    fast path switched off (FH264_SPEC=0: every partition takes the full search) and on (most partitions must hit)."""
+    monkeypatch.setenv("FH264_SPEC", spec)
+    w, h, qp, window, maxdiff = 320, 208, 27, 32, 3
+    clip = synth.SynthClip(w, h, 57)
+    o = port.Oracle(w, h)
+    ref = clip.frame(0)
+    with fh.Session(w, h) as s:
+        s.upload_recon(0, *ref)
+        for t in range(1, 4):
+            cur = clip.frame(t)
+            assert not o.phase_r(ref[0])
+            erec, erecon = o.encode_p(cur, ref, qp, window, maxdiff)
+            s.upload_source(0, *cur)
+            got = fh.records_to_ints(s.encode_p(qp, window, maxdiff)[0])
+            assert np.array_equal(got, erec), np.argwhere(got != erec)[:6]
+            assert all(np.array_equal(a, b) for a, b in zip(s.download_recon(0), erecon))
+            st = s.debug_status(0)
+            hits, misses = int(st[13]), int(st[14])
+            coded = int((erec[:, 0] != 31).sum())
+            assert hits + misses == 4 * coded, (hits, misses, coded)
+            if spec == "0":
+                assert hits == 0
+            else:
+                assert hits > 2 * misses, (hits, misses)
+            ref = erecon

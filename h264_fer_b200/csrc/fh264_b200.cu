@@ -60,6 +60,10 @@ struct fh264_session {
     cudaEvent_t evk[4];             // after stage3, after interp, after features (per-kernel split of phases A and R)
     cudaEvent_t ev_spec;            // after stage 2, before phase S
     int use_spec;                   // phase S + fast path in phase B (FH264_SPEC=0 turns it off: every partition takes the full search)
+    // TMA descriptors of the 16 interpolated planes of every sequence (qwin.cuh): box 16 bytes x tmap_rows rows x 16 planes
+    CUtensorMap *d_tmaps;
+    int tmap_rows;
+    int use_tma;                    // FH264_TMA=0: fill the pixel windows with ordinary loads (development knob)
     bool timed;
     std::vector<void *> allocs;
     // scratch for the stand-alone entry points
@@ -202,6 +206,8 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     for (int i = 0; i < 4; i++) s->evk[i] = nullptr;
     s->ev_spec = nullptr;
     { const char *e = getenv("FH264_SPEC"); s->use_spec = !(e && atoi(e) == 0); }
+    { const char *e = getenv("FH264_TMA"); s->use_tma = !(e && atoi(e) == 0); }
+    s->d_tmaps = nullptr; s->tmap_rows = 0;
     for (int i = 0; i < 3; i++) s->d_scr[i] = nullptr;
     s->d_scr16[0] = s->d_scr16[1] = nullptr;
     Geo &g = s->g;
@@ -275,10 +281,11 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     OPEN_CK(dalloc(s, &s->d_wf_order, (size_t)g.nmb));
     OPEN_CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.nmb, cudaMemcpyHostToDevice));
     OPEN_CK(dalloc(s, &s->d_ticket, (size_t)4));
+    OPEN_CK(dalloc(s, &s->d_tmaps, (size_t)batch));
     OPEN_CK(dalloc(s, &s->d_sync, (size_t)FH_MAX_WORLD));
     OPEN_CK(cudaFuncSetAttribute(k_tile_index, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_CELLS * 4));
     OPEN_CK(cudaFuncSetAttribute(k_stage3, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    OPEN_CK(cudaFuncSetAttribute(k_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    OPEN_CK(cudaFuncSetAttribute(k_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     OPEN_CK(cudaDeviceSynchronize());
     *out = s;
     return FH264_OK;
@@ -406,6 +413,37 @@ static int launch_phase_r(fh264_session *s, int seq0, int nseq)
     return FH264_OK;
 }
 
+// Tensor maps over the interpolated planes [16][H][W] of every sequence with a box of 32 bytes x `rows` rows x 16 planes
+// (re-encoded when the window geometry changes; stream-ordered copy, so launches in flight keep the maps they were issued with).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int ensure_tmaps(fh264_session *s, int rows)
+{
+    if (!s->use_tma || s->tmap_rows == rows) return FH264_OK;
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) return fail(FH264_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        enc = (EncodeTiledFn)fn;
+    }
+    const Geo &g = s->g;
+    std::vector<CUtensorMap> maps(s->batch);
+    for (int b = 0; b < s->batch; b++) {
+        const cuuint64_t dims[3] = { (cuuint64_t)g.W, (cuuint64_t)g.H, 16 };
+        const cuuint64_t strides[2] = { (cuuint64_t)g.W, (cuuint64_t)g.WH };
+        const cuuint32_t box[3] = { QW_ROWB, (cuuint32_t)rows, 16 }, estr[3] = { 1, 1, 1 };
+        const CUresult r = enc(&maps[b], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s->h[b].planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(FH264_E_CUDA, "cuTensorMapEncodeTiled failed");
+    }
+    CK(cudaMemcpyAsync(s->d_tmaps, maps.data(), sizeof(CUtensorMap) * s->batch, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));          // `maps` is a local
+    s->tmap_rows = rows;
+    return FH264_OK;
+}
+
 extern "C" int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, const uint8_t *cb, const uint8_t *cr)
 {
     int rc = check_seq(s, seq, 1); if (rc) return rc;
@@ -465,6 +503,7 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     prm.basic = prm.basic ? 1 : 0;
     s->epoch++;
     cudaStream_t st = s->stream;
+    rc = ensure_tmaps(s, 8 + 2 * (prm.window / 16) + 1); if (rc) return rc;
     rc = adopt_uploads(s, seq0, nseq); if (rc) return rc;
     CK(cudaEventRecord(s->ev[0], st));
     k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, s->d_ticket);
@@ -486,8 +525,8 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     if (s->use_spec) {
         // phase S: the search completed for the guessed integer predictors (spec.cuh)
         const int g1 = prm.window / 16, n1 = (2 * g1 + 1) * (2 * g1 + 1) * 16, npad1 = (n1 + 31) & ~31;
-        const size_t smems = 4 * sizeof(SpecWarp) + (size_t)4 * npad1 * sizeof(uint32_t);
-        k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, npad1, 1);
+        const size_t smems = 4 * (size_t)qwin_bytes(g1) + 4 * sizeof(SpecWarp) + (size_t)4 * npad1 * sizeof(uint32_t) + 16;
+        k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, npad1, 1, s->use_tma ? s->d_tmaps : nullptr);
     }
     CK(cudaEventRecord(s->ev[1], st));
     // persistent wavefront CTAs: two anti-diagonals' worth per sequence — one set working, one set that has already

@@ -21,6 +21,7 @@
 #include "warp_select.cuh"
 #include "qfeat.cuh"
 #include "phase_a.cuh"
+#include "qwin.cuh"
 
 #define SPEC_NF 7
 #define SPEC_INVALID 0xffu
@@ -41,51 +42,15 @@ static_assert(sizeof(PartSpec) == 128, "PartSpec size");
 __device__ __forceinline__ int cell_min_(int a) { return a < 0 ? -a : (a > 3 ? a - 3 : 0); }
 __device__ __forceinline__ int cell_max_(int a) { return max(iabs_(a), iabs_(a - 3)); }
 
-struct SpecWarp {
-    WarpSelScratch ws;                       // selection scratch; before that the row sums of the feature window (qfeat.cuh)
+struct __align__(128) SpecWarp {
+    uint64_t bar;                            // mbarrier of the TMA-staged pixel window (qwin.cuh)
+    WarpSelScratch ws;                       // selection scratch
     uint16_t members[FH_S1_MAX + 3];
     uint16_t msad[FH_S1_MAX + 3];
     S3Entry s3[FH_S3_MAX + 1];
     uint32_t pf_mv[SPEC_PF_CAP];             // evaluated candidates that can still win: mvx & 0xffff | mvy << 16
     uint32_t pf_so[SPEC_PF_CAP];             // sad | order << 16
 };
-
-// MEstimation(g = window/16, all 16 fractions, gen = centre = (Gx, Gy)) (moestimation.cpp:254-296 as called at :458):
-// cost[((dx+g1)*w1 + (dy+g1))*16 + frac] for the displacements dx, dy relative to the centre; COST_INVALID where the block
-// origin leaves the picture (:265). The features of the quarter-pel planes come from the planes themselves (qfeat.cuh), a few
-// planes per batch, through the X / RC scratch. m1 <= m2 collect this lane's two smallest costs (selection bound).
-__device__ __forceinline__ void window_costs(const SeqDev &S, const Geo &g, int xP, int yP, int Gx, int Gy, int g1, const FeatQ &fq,
-                                             uint32_t *cost, uint32_t *X, uint16_t *RC, uint32_t &m1, uint32_t &m2)
-{
-    const int lane = threadIdx.x & 31, W = g.W, H = g.H;
-    const int w1 = 2 * g1 + 1, npos = w1 * w1, R = 8 + w1 - 1, ps = R * w1, pb = w1 <= 5 ? 4 : 1;
-    const uint32_t iR = udiv_magic((uint32_t)R), iN = udiv_magic((uint32_t)npos), i1 = udiv_magic((uint32_t)w1);
-    const int x0 = xP + Gx - g1, y0 = yP + Gy - g1;
-    for (int f0 = 0; f0 < 16; f0 += pb) {
-        for (int sg0 = 0; sg0 < pb * R; sg0 += 64) {
-            uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;
-            const int sa = sg0 + lane, sb = sg0 + 32 + lane;
-            const int fa = udiv_by(sa, iR), ra = sa - fa * R, fb = udiv_by(sb, iR), rb = sb - fb * R;
-            if (sa < pb * R) wa = qf_load16(S.planes + (size_t)(f0 + fa) * g.WH, W, H, x0, y0 + ra);
-            if (sb < pb * R) wb = qf_load16(S.planes + (size_t)(f0 + fb) * g.WH, W, H, x0, y0 + rb);
-            if (sa < pb * R) qf_row_sums(wa, w1, X + fa * ps + ra * w1, RC + fa * ps + ra * w1);
-            if (sb < pb * R) qf_row_sums(wb, w1, X + fb * ps + rb * w1, RC + fb * ps + rb * w1);
-        }
-        __syncwarp();
-        const int rot = (f0 * 13) % (pb * npos);
-        for (int o0 = lane; o0 < pb * npos; o0 += 32) {
-            const int o = o0 + rot < pb * npos ? o0 + rot : o0 + rot - pb * npos;
-            const int fl = udiv_by(o, iN), pos = o - fl * npos, cx = udiv_by(pos, i1), cy = pos - cx * w1;
-            const int rx = x0 + cx, ry = y0 + cy;
-            uint32_t cst = COST_INVALID;
-            if (rx >= 0 && rx < W && ry >= 0 && ry < H)
-                cst = (uint32_t)((iabs_(cx - g1) + iabs_(cy - g1) + 4) * feat_of(fq, qf_record(X, RC, fl, ps, w1, cx, cy)));
-            cost[pos * 16 + f0 + fl] = cst;
-            m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
-        }
-        __syncwarp();
-    }
-}
 
 __device__ __forceinline__ void pf_emit(bool have, int mvx, int mvy, int sad, int order, SpecWarp *sw, int &npf)
 {
@@ -101,7 +66,7 @@ __device__ __forceinline__ void pf_emit(bool have, int mvx, int mvy, int sad, in
 // The finalists of one partition for one guessed gen = (Gx, Gy) into out->f[slot]. Warp-uniform call.
 __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const fh264_params &prm, int part, int xP, int yP, const uint2 (&rows)[8],
                                           const FeatQ &fq, int n3, uint32_t n2w, uint32_t s2_off, int Gx, int Gy, int slot,
-                                          SpecWarp *sw, uint32_t *cost, PartSpec *out)
+                                          SpecWarp *sw, uint8_t *win, uint32_t *cost, PartSpec *out, const CUtensorMap *tmap, uint32_t &phase)
 {
     const int lane = threadIdx.x & 31, W = g.W, H = g.H;
     const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16;
@@ -109,6 +74,10 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
     const int cxq = 4 * Gx, cyq = 4 * Gy;
     int npf = 0;
     bool usable = !(n2w & S2_SLOW);                        // oversized stage-2 set: phase B enumerates it itself
+    // the pixel window of stage 1 starts to arrive now (TMA) and is consumed after stages 3 and 2
+    const QWinGeo qg = qwin_geo(g1);
+    int woff;
+    const bool tma = qwin_fill(S, g, tmap, qg, xP + Gx - g1, yP + Gy - g1, win, &sw->bar, woff);
     // ---- stage 3 (list of phase A, SADs known): bound U, then the entries that can still win
     int U = 0x7fffffff;
     for (int i = lane; i < n3; i += 32) {
@@ -163,7 +132,14 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
     // ---- stage 1 (:458-469): feature window around the guess, 17 best by (cost, arrival), their SADs
     {
         uint32_t m1 = COST_INVALID, m2 = COST_INVALID;
-        window_costs(S, g, xP, yP, Gx, Gy, g1, fq, cost, (uint32_t *)sw->ws.skey, sw->ws.sidx, m1, m2);
+        qwin_wait(tma, &sw->bar, phase);
+        switch (w1) {
+        case 1: qwin_costs<1>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
+        case 3: qwin_costs<3>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
+        case 5: qwin_costs<5>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
+        case 7: qwin_costs<7>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
+        default: qwin_costs<9>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
+        }
         __syncwarp();
         const int nvalid = max(0, min(W - 1, xP + Gx + g1) - max(0, xP + Gx - g1) + 1) * max(0, min(H - 1, yP + Gy + g1) - max(0, yP + Gy - g1) + 1) * 16;
         const int nm = warp_select_costs(cost, n1, FH_S1_MAX, nvalid, m1, m2, &sw->ws, sw->members);
@@ -176,8 +152,9 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
                 const int m = base + u * 4 + (lane >> 3);
                 rr[u] = make_uint2(0, 0);
                 if (m < nm) {
-                    const int i = (int)sw->members[m], f = i & 15, pos = i >> 4, cx = udiv_by(pos, i1), dx = Gx + cx - g1, dy = Gy + pos - cx * w1 - g1;
-                    rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, xP + dx, yP + dy + r);
+                    // the candidate's block lies inside the staged window (same clamping as satdLuma8x8MVs for an origin inside the picture)
+                    const int i = (int)sw->members[m], f = i & 15, pos = i >> 4, cx = udiv_by(pos, i1), cy = pos - cx * w1;
+                    rr[u] = qwin_row8(qg, win, woff, f, cx, cy + r);
                 }
             }
 #pragma unroll
@@ -242,13 +219,21 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
 
 // One warp per partition, four per CTA (one macroblock). Guesses: the integer part of the partition's best stage-3 vector by
 // SAD, and the gen phase B used for this partition in the previous P picture (use_prev).
-__global__ void __launch_bounds__(128, 6) k_spec(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad1, int use_prev)
+__global__ void __launch_bounds__(128, 4) k_spec(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad1, int use_prev,
+                                                 const CUtensorMap *__restrict__ tmaps)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SpecWarp *sw = (SpecWarp *)smem_raw + warp;
-    uint32_t *cost = (uint32_t *)(smem_raw + 4 * sizeof(SpecWarp)) + (size_t)warp * npad1;
+    // dynamic shared memory: 4 windows (128-byte aligned, qwin_bytes each) | 4 SpecWarp | 4 cost arrays
+    const int wbytes = qwin_bytes(prm.window / 16);
+    uint8_t *win = smem_raw + (size_t)warp * wbytes;
+    SpecWarp *sw = (SpecWarp *)(smem_raw + 4 * (size_t)wbytes) + warp;
+    uint32_t *cost = (uint32_t *)(smem_raw + 4 * (size_t)wbytes + 4 * sizeof(SpecWarp)) + (size_t)warp * npad1;
     const SeqDev &S = seqs[seq0 + blockIdx.y];
+    const CUtensorMap *tmap = tmaps ? tmaps + seq0 + blockIdx.y : nullptr;
+    uint32_t phase = 0;
+    if (lane == 0) mbar_init(&sw->bar, 1);
+    __syncwarp();
     const int part = g.band_mb0 * 4 + blockIdx.x * 4 + warp;
     int xP, yP;
     part_origin(g, part, xP, yP);
@@ -281,6 +266,6 @@ __global__ void __launch_bounds__(128, 6) k_spec(const SeqDev *__restrict__ seqs
     }
     if (ng == 0) ng = 1;                                   // no list and no history: guess gen = (0, 0)
     for (int slot = 0; slot < ng; slot++)
-        spec_slot(S, g, prm, part, xP, yP, rows, fq, n3, n2w, s2_off, slot ? g1x : g0x, slot ? g1y : g0y, slot, sw, cost, out);
+        spec_slot(S, g, prm, part, xP, yP, rows, fq, n3, n2w, s2_off, slot ? g1x : g0x, slot ? g1y : g0y, slot, sw, win, cost, out, tmap, phase);
     if (ng == 1 && lane == 0) { out->gx[1] = SPEC_NOGUESS; out->gy[1] = SPEC_NOGUESS; out->nf[1] = SPEC_INVALID; }
 }

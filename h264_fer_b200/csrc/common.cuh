@@ -58,6 +58,7 @@ struct PartA { uint16_t suma[5]; uint16_t n3; uint32_t s2_off; uint32_t n2; };  
 #define S2_SLOW 0x80000000u
 
 struct PartSpec;                     // spec.cuh: finalists per partition for the guessed integer predictors
+struct MbSpec;                       // spec.cuh: P_Skip trial results per macroblock for the guessed skip vectors
 
 static_assert(sizeof(fh264_mb_result) == 832, "ABI record size");
 static_assert(sizeof(MbMotion) == 48, "MbMotion size");
@@ -79,6 +80,9 @@ struct SeqDev {
     MbMotion *motion;       // nmb
     unsigned long long *qmv; // nmb * 4 tagged quadrant words (phase B wavefront): epoch << 32 | mvy << 16 | (mvx & 0xffff)
     PartSpec *spec;         // nparts: speculative finalists of the 8x8 search (phase S, read by phase B)
+    MbSpec *mbspec;         // nmb: precomputed P_Skip trials (phase S, read by phase B)
+    uint32_t *prev_gen16;   // nmb: 16x16 predictor >> 2 of the macroblock's P_Skip trial in the previous P picture
+    uint32_t *proxy;        // nparts: best stage-3 vector by SAD (mvx & 0xffff | mvy << 16; SPEC_PREV_NONE: none) — stands in for the final MV when phase S guesses predictors
     uint32_t *prev_gen;     // nparts: mvp >> 2 phase B used for the partition in the previous P picture (genx & 0xffff | geny << 16)
     fh264_mb_result *results;
     uint32_t *status;       // ST_WORDS
@@ -94,6 +98,21 @@ __device__ __forceinline__ int clip255_(int v) { return min(max(v, 0), 255); }
 // mocomp.cpp:39-40,47
 __device__ __forceinline__ int tap6_(int a, int b, int c, int d, int e, int f) { return clip255_((a - 5 * b + 20 * c + 20 * d - 5 * e + f + 16) >> 5); }
 __device__ __forceinline__ int mid_(int a, int b) { return (a + b + 1) >> 1; }
+
+__device__ __forceinline__ int median3_(int a, int b, int c) { return max(min(a, b), min(c, max(a, b))); }
+
+// Median prediction from three neighbour candidates with availability flags (mode_pred.cpp:299-332; every available
+// neighbour of a P picture is inter with refIdx 0, so "same reference" == available, except the A := 0 substitutions).
+__device__ __forceinline__ void median_pred(int aA, int ax, int ay, int aB, int bx, int by, int aC, int cx, int cy, int &ox, int &oy)
+{
+    int sa = aA, sb = aB, sc = aC;
+    if (!aA && !aB) { ax = ay = 0; sa = 1; }
+    else if (!aA) { ax = ay = 0; sa = 0; }
+    if (!aB) { bx = ax; by = ay; sb = sa; }
+    if (!aC) { cx = ax; cy = ay; sc = sa; }
+    if (sa + sb + sc == 1) { ox = sa ? ax : (sb ? bx : cx); oy = sa ? ay : (sb ? by : cy); return; }
+    ox = median3_(ax, bx, cx); oy = median3_(ay, by, cy);
+}
 
 // 8 consecutive bytes starting at an arbitrary address, as two little-endian words: two aligned 8-byte loads (two LSU
 // wavefronts per lane instead of three 4-byte ones) and a funnel shift; reads up to 7 bytes past the block (the plane

@@ -61,7 +61,7 @@ struct fh264_session {
     cudaEvent_t ev_spec;            // after stage 2, before phase S
     int use_spec;                   // phase S + fast path in phase B (FH264_SPEC=0 turns it off: every partition takes the full search)
     // TMA descriptors of the 16 interpolated planes of every sequence (qwin.cuh): box 16 bytes x tmap_rows rows x 16 planes
-    CUtensorMap *d_tmaps;
+    CUtensorMap *d_tmaps, *d_tmaps16;   // d_tmaps16: box of 16 rows (P_Skip trials of phase S)
     int tmap_rows;
     int use_tma;                    // FH264_TMA=0: fill the pixel windows with ordinary loads (development knob)
     bool timed;
@@ -207,7 +207,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->ev_spec = nullptr;
     { const char *e = getenv("FH264_SPEC"); s->use_spec = !(e && atoi(e) == 0); }
     { const char *e = getenv("FH264_TMA"); s->use_tma = !(e && atoi(e) == 0); }
-    s->d_tmaps = nullptr; s->tmap_rows = 0;
+    s->d_tmaps = nullptr; s->d_tmaps16 = nullptr; s->tmap_rows = 0;
     for (int i = 0; i < 3; i++) s->d_scr[i] = nullptr;
     s->d_scr16[0] = s->d_scr16[1] = nullptr;
     Geo &g = s->g;
@@ -260,6 +260,11 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         OPEN_CK(dalloc(s, &S.s2redo, (size_t)S2_REDO_MAX));
         OPEN_CK(dalloc(s, &S.motion, (size_t)g.nmb));
         OPEN_CK(dalloc(s, &S.spec, (size_t)g.nparts));
+        OPEN_CK(dalloc(s, &S.mbspec, (size_t)g.nmb));
+        OPEN_CK(dalloc(s, &S.prev_gen16, (size_t)g.nmb));
+        OPEN_CK(cudaMemset(S.prev_gen16, 0x7f, sizeof(uint32_t) * (size_t)g.nmb));
+        OPEN_CK(dalloc(s, &S.proxy, (size_t)g.nparts));
+        OPEN_CK(cudaMemset(S.proxy, 0x7f, sizeof(uint32_t) * (size_t)g.nparts));
         OPEN_CK(dalloc(s, &S.prev_gen, (size_t)g.nparts));
         OPEN_CK(cudaMemset(S.prev_gen, 0x7f, sizeof(uint32_t) * (size_t)g.nparts));       // SPEC_PREV_NONE: no previous P picture
         OPEN_CK(dalloc(s, &S.qmv, (size_t)g.nmb * 4));
@@ -282,10 +287,12 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     OPEN_CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.nmb, cudaMemcpyHostToDevice));
     OPEN_CK(dalloc(s, &s->d_ticket, (size_t)4));
     OPEN_CK(dalloc(s, &s->d_tmaps, (size_t)batch));
+    OPEN_CK(dalloc(s, &s->d_tmaps16, (size_t)batch));
     OPEN_CK(dalloc(s, &s->d_sync, (size_t)FH_MAX_WORLD));
     OPEN_CK(cudaFuncSetAttribute(k_tile_index, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_CELLS * 4));
     OPEN_CK(cudaFuncSetAttribute(k_stage3, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     OPEN_CK(cudaFuncSetAttribute(k_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OPEN_CK(cudaFuncSetAttribute(k_skipspec, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SKIPWIN_BYTES + 64));
     OPEN_CK(cudaDeviceSynchronize());
     *out = s;
     return FH264_OK;
@@ -430,16 +437,19 @@ static int ensure_tmaps(fh264_session *s, int rows)
     }
     const Geo &g = s->g;
     std::vector<CUtensorMap> maps(s->batch);
-    for (int b = 0; b < s->batch; b++) {
-        const cuuint64_t dims[3] = { (cuuint64_t)g.W, (cuuint64_t)g.H, 16 };
-        const cuuint64_t strides[2] = { (cuuint64_t)g.W, (cuuint64_t)g.WH };
-        const cuuint32_t box[3] = { QW_ROWB, (cuuint32_t)rows, 16 }, estr[3] = { 1, 1, 1 };
-        const CUresult r = enc(&maps[b], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s->h[b].planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(FH264_E_CUDA, "cuTensorMapEncodeTiled failed");
+    for (int pass = s->tmap_rows == 0 ? 0 : 1; pass < 2; pass++) {          // first call: the 16-row maps too
+        const int brows = pass == 0 ? 16 : rows;
+        for (int b = 0; b < s->batch; b++) {
+            const cuuint64_t dims[3] = { (cuuint64_t)g.W, (cuuint64_t)g.H, 16 };
+            const cuuint64_t strides[2] = { (cuuint64_t)g.W, (cuuint64_t)g.WH };
+            const cuuint32_t box[3] = { QW_ROWB, (cuuint32_t)brows, 16 }, estr[3] = { 1, 1, 1 };
+            const CUresult r = enc(&maps[b], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s->h[b].planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(FH264_E_CUDA, "cuTensorMapEncodeTiled failed");
+        }
+        CK(cudaMemcpyAsync(pass == 0 ? s->d_tmaps16 : s->d_tmaps, maps.data(), sizeof(CUtensorMap) * s->batch, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));          // `maps` is a local
     }
-    CK(cudaMemcpyAsync(s->d_tmaps, maps.data(), sizeof(CUtensorMap) * s->batch, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaStreamSynchronize(s->stream));          // `maps` is a local
     s->tmap_rows = rows;
     return FH264_OK;
 }
@@ -527,6 +537,8 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         const int g1 = prm.window / 16, n1 = (2 * g1 + 1) * (2 * g1 + 1) * 16, npad1 = (n1 + 31) & ~31;
         const size_t smems = 4 * (size_t)qwin_bytes(g1) + 4 * sizeof(SpecWarp) + (size_t)4 * npad1 * sizeof(uint32_t) + 16;
         k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, npad1, 1, s->use_tma ? s->d_tmaps : nullptr);
+        k_skipspec<<<dim3((g.band_nmb + 3) / 4, nseq), 128, 4 * SKIPWIN_BYTES + 64, st>>>(s->d_seqs, seq0, g, prm, s->use_tma ? s->d_tmaps16 : nullptr);
+        CKL();
     }
     CK(cudaEventRecord(s->ev[1], st));
     // persistent wavefront CTAs: two anti-diagonals' worth per sequence — one set working, one set that has already

@@ -287,6 +287,21 @@ __global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ se
         e.mvx = (int16_t)((dx << 2) | (f & 3)); e.mvy = (int16_t)((dy << 2) | (f >> 2)); e.sad = sw->msad[m]; e.pad = 0;
         S.s3[(size_t)part * FH_S3_MAX + m] = e;
     }
+    // the list's best vector by SAD (first in list order): phase S guesses the neighbours' final vectors with it (spec.cuh)
+    {
+        uint32_t k = 0xffffffffu;
+        for (int m = lane; m < nm; m += 32) k = min(k, ((uint32_t)sw->msad[m] << 8) | (uint32_t)m);
+        k = __reduce_min_sync(0xffffffffu, k);
+        if (lane == 0) {
+            uint32_t px = 0x7f7f7f7fu;
+            if (nm > 0) {
+                int dx, dy, f;
+                s3_decode((int)sw->members[k & 255u], n3a, w3, g3, i3, w1, g1, i1, dx, dy, f);
+                px = ((uint32_t)((dx << 2) | (f & 3)) & 0xffffu) | ((uint32_t)((dy << 2) | (f >> 2)) << 16);
+            }
+            S.proxy[part] = px;
+        }
+    }
     if (lane == 0) {
         PartA *pa = &S.parta[part];
 #pragma unroll

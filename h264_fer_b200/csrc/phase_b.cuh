@@ -89,7 +89,6 @@ __device__ __forceinline__ Nb neighbour_mv(const NbCache &nc, int xN, int yN, co
     return n;
 }
 
-__device__ __forceinline__ int median3_(int a, int b, int c) { return max(min(a, b), min(c, max(a, b))); }
 
 // PredictMV_Luma (mode_pred.cpp:252-332). Every available neighbour of a P picture is inter with refIdx 0.
 // dir: 0 median, 1 prefer B (16x8 top), 2 prefer A (16x8 bottom / 8x16 left), 3 prefer C (8x16 right).
@@ -125,6 +124,7 @@ struct PBShared {
     u64 best[2][4];                      // per-warp minima, double-buffered across partitions
     u64 sel_min[4]; int sel_cnt[4];      // lazy stage-2 verification
     __align__(16) PartSpec spec[4];      // phase-S finalists of the four partitions (spec.cuh)
+    __align__(16) MbSpec ms;             // phase-S P_Skip trials of the macroblock
     PartA pa[4];                         // phase-A products of the four partitions, fetched BEFORE the dependency wait
     S3Entry s3[4][FH_S3_MAX + 1];
     uint2 pool[4][PB_POOL_PREF];
@@ -263,19 +263,6 @@ __device__ __forceinline__ int block_select_smallest_u32(const uint32_t *keys, i
     }
     __syncthreads();
     return K;
-}
-
-// Median prediction from three neighbour candidates with availability flags (mode_pred.cpp:299-332; every available
-// neighbour of a P picture is inter with refIdx 0, so "same reference" == available, except the A := 0 substitutions).
-__device__ __forceinline__ void median_pred(int aA, int ax, int ay, int aB, int bx, int by, int aC, int cx, int cy, int &ox, int &oy)
-{
-    int sa = aA, sb = aB, sc = aC;
-    if (!aA && !aB) { ax = ay = 0; sa = 1; }
-    else if (!aA) { ax = ay = 0; sa = 0; }
-    if (!aB) { bx = ax; by = ay; sb = sa; }
-    if (!aC) { cx = ax; cy = ay; sc = sa; }
-    if (sa + sb + sc == 1) { ox = sa ? ax : (sb ? bx : cx); oy = sa ? ay : (sb ? by : cy); return; }
-    ox = median3_(ax, bx, cx); oy = median3_(ay, by, cy);
 }
 
 // Stage 2 for a partition whose candidate set did not fit the phase-A buffers (PartA.n2 & S2_SLOW): flat or low-contrast
@@ -420,15 +407,18 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
     //      long before its turn, so these round trips are off the wavefront's critical path
     if (tid < 16) *(uint4 *)&sh.cur[tid][0] = *(const uint4 *)(S.cur[0] + (size_t)(mby * 16 + tid) * W + mbx * 16);
     if (use_spec && tid >= 96) ((uint4 *)sh.spec)[tid - 96] = ((const uint4 *)&S.spec[(size_t)mb * 4])[tid - 96];       // 4 x 128 bytes
-    if (!prm.basic) {
-        if (tid >= 32 && tid < 36) sh.pa[tid - 32] = S.parta[mb * 4 + tid - 32];
-        for (int i = tid; i < 4 * FH_S3_MAX; i += PB_NT) { const int pi = i / FH_S3_MAX, k = i - pi * FH_S3_MAX; sh.s3[pi][k] = S.s3[(size_t)(mb * 4 + pi) * FH_S3_MAX + k]; }
-        // each partition's candidates live in a fixed pool slice: fetch the first PB_POOL_PREF of every slice right away
-        // (entries beyond the partition's count are never looked at)
-        for (int i = tid; i < 4 * PB_POOL_PREF; i += PB_NT) { const int pi = i / PB_POOL_PREF, k = i - pi * PB_POOL_PREF; sh.pool[pi][k] = __ldg(&S.s2pool[(size_t)(mb * 4 + pi) * 1024u + k]); }
-    } else if (tid < 4) {
-        sh.pa[tid].n2 = 0; sh.pa[tid].n3 = 0; sh.pa[tid].s2_off = 0;
-    }
+    if (use_spec && tid == 64) *(uint4 *)&sh.ms = *(const uint4 *)&S.mbspec[mb];
+    // (the phase-A products — lists, candidate pool — are only needed by a partition that misses the fast path: fetched there)
+    auto fetch_phase_a = [&](int pi) {
+        if (!prm.basic) {
+            if (tid == 32) sh.pa[pi] = S.parta[mb * 4 + pi];
+            for (int k = tid; k < FH_S3_MAX; k += PB_NT) sh.s3[pi][k] = S.s3[(size_t)(mb * 4 + pi) * FH_S3_MAX + k];
+            for (int k = tid; k < PB_POOL_PREF; k += PB_NT) sh.pool[pi][k] = __ldg(&S.s2pool[(size_t)(mb * 4 + pi) * 1024u + k]);
+        } else if (tid == 0) {
+            sh.pa[pi].n2 = 0; sh.pa[pi].n3 = 0; sh.pa[pi].s2_off = 0;
+        }
+        __syncthreads();
+    };
     PB_STAMP(1);
     // ---- dependencies. Every final quadrant MV is published as a tagged word (qmv_word). The row ABOVE is waited for here:
     //      exactly the quadrants the predictors can address (up q2/q3, up-right q2, up-left q3). The LEFT neighbour is only
@@ -474,7 +464,8 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
     const int py = tid >> 3, px = (tid & 7) * 2;                          // this thread's two luma samples
     const int c0 = sh.cur[py][px], c1 = sh.cur[py][px + 1];
     int maxdiff = prm.maxdiff_set;
-    if (prm.maxdiff_set == -1) {                                          // moestimation.cpp:407-419
+    if (use_spec) maxdiff = sh.ms.maxdiff;                                // computed by phase S (same arithmetic)
+    else if (prm.maxdiff_set == -1) {                                     // moestimation.cpp:407-419
         int v = __reduce_add_sync(0xffffffffu, c0 + c1);
         if (lane == 0) sh.red[warp] = v;
         __syncthreads();
@@ -489,20 +480,29 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
         luma_pred_block<2, 1>(S, g, mbx * 16 + px + (vx >> 2), mby * 16 + py + (vy >> 2), vx & 3, vy & 3, p2);
     };
     auto skip_bad = [&](const int (&p2)[2]) -> int { return __syncthreads_count(iabs_(c0 - p2[0]) > maxdiff || iabs_(c1 - p2[1]) > maxdiff); };
+    // number of samples outside MAXDIFF for skip vector (vx, vy) — only zero / non-zero matters. Looked up in the phase-S masks
+    // when the vector lies in a guessed cell, else measured here. Block-uniform.
+    auto skip_nbad = [&](int vx, int vy) -> int {
+        if (use_spec) {
+            if (vx == 0 && vy == 0) return sh.ms.zero_ok ? 0 : 1;
+            const int cxx = vx >> 2, cyy = vy >> 2, f = (vy & 3) * 4 + (vx & 3);
+            if (sh.ms.cx[0] == cxx && sh.ms.cy[0] == cyy) return ((sh.ms.mask[0] >> f) & 1) ? 0 : 1;
+            if (sh.ms.cx[1] == cxx && sh.ms.cy[1] == cyy) return ((sh.ms.mask[1] >> f) & 1) ? 0 : 1;
+        }
+        int p2[2];
+        skip_pred(vx, vy, p2);
+        return skip_bad(p2);
+    };
     int smx = 0, smy = 0, nbad;
     if (!leftA || mby == 0 || (u2x == 0 && u2y == 0)) {                  // the skip MV is zero whatever the left MB holds
-        int p2[2];
-        skip_pred(0, 0, p2);
-        nbad = skip_bad(p2);
+        nbad = skip_nbad(0, 0);
     } else {
         // 16x16 predictor: A = left q1, B = up q2, C = up-right q2 else up-left q3 (all available here)
         const int cx16 = aUR ? r2x : d3x, cy16 = aUR ? r2y : d3y;
         if (u2x == cx16 && u2y == cy16) {
             // B == C: the skip MV is B, or zero if the left quadrant turns out to be zero — try both without waiting
-            int pB[2], p0[2];
-            skip_pred(u2x, u2y, pB);
-            skip_pred(0, 0, p0);
-            const int nbB = skip_bad(pB), nb0 = skip_bad(p0);
+            const int nbB = skip_nbad(u2x, u2y), nb0 = skip_nbad(0, 0);
+            if (tid == 0) S.prev_gen16[mb] = ((uint32_t)(u2x >> 2) & 0xffffu) | ((uint32_t)(u2y >> 2) << 16);
             if (nbB != 0 && nb0 != 0) nbad = 1;
             else {
                 fetch_left(1, 0); left1 = true;
@@ -511,10 +511,11 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
             }
         } else {
             fetch_left(1, 1); left1 = true;
-            if (!(nc.mvx[0][1] == 0 && nc.mvy[0][1] == 0)) predict_mv_(nc, 0, 0, 16, 0, zero4, smx, smy);
-            int p2[2];
-            skip_pred(smx, smy, p2);
-            nbad = skip_bad(p2);
+            if (!(nc.mvx[0][1] == 0 && nc.mvy[0][1] == 0)) {
+                predict_mv_(nc, 0, 0, 16, 0, zero4, smx, smy);
+                if (tid == 0) S.prev_gen16[mb] = ((uint32_t)(smx >> 2) & 0xffffu) | ((uint32_t)(smy >> 2) << 16);
+            }
+            nbad = skip_nbad(smx, smy);
         }
     }
     MbMotion mo;
@@ -591,6 +592,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
             }
         }
         if (!hit) {
+        fetch_phase_a(pi);
         const PartA pa = sh.pa[pi];
         u64 *best = sh.best[pi & 1];
         u64 mine = KEY_NONE;

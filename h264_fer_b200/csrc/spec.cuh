@@ -217,8 +217,45 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
     __syncwarp();
 }
 
-// One warp per partition, four per CTA (one macroblock). Guesses: the integer part of the partition's best stage-3 vector by
-// SAD, and the gen phase B used for this partition in the previous P picture (use_prev).
+// Proxy of a quadrant's final vector: the best stage-3 vector by SAD of that 8x8 partition (k_stage3); zero if it has none.
+__device__ __forceinline__ void proxy_mv(const SeqDev &S, int mb, int q, int &x, int &y)
+{
+    const uint32_t v = __ldg(&S.proxy[(size_t)mb * 4 + q]);
+    x = v == SPEC_PREV_NONE ? 0 : (int)(int16_t)(v & 0xffffu);
+    y = v == SPEC_PREV_NONE ? 0 : (int)(int16_t)(v >> 16);
+}
+// The predictor of 8x8 partition pi of macroblock mb (mode_pred.cpp:113-161,252-332) evaluated on the proxies
+// instead of the final vectors: the neighbours are partitions of the same picture, whose best stage-3 vector is the final
+// vector for ~96 % of them, and the median absorbs a single wrong one.
+__device__ __forceinline__ void proxy_predictor(const SeqDev &S, const Geo &g, int mb, int pi, int &ox, int &oy)
+{
+    const int mbx = mb % g.Wmb, mby = mb / g.Wmb;
+    const int aL = mbx > 0, aU = mby > 0, aUR = mby > 0 && mbx < g.Wmb - 1, aUL = mby > 0 && mbx > 0;
+    int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0, aA = 1, aB = 1, aC = 1;
+    if (pi == 0) {
+        aA = aL; aB = aU; aC = aU ? 1 : aUL;
+        if (aL) proxy_mv(S, mb - 1, 1, ax, ay);
+        if (aU) { proxy_mv(S, mb - g.Wmb, 2, bx, by); proxy_mv(S, mb - g.Wmb, 3, cx, cy); }
+        else if (aUL) proxy_mv(S, mb - g.Wmb - 1, 3, cx, cy);
+    } else if (pi == 1) {
+        aB = aU; aC = aUR ? 1 : aU;
+        proxy_mv(S, mb, 0, ax, ay);
+        if (aU) proxy_mv(S, mb - g.Wmb, 3, bx, by);
+        if (aUR) proxy_mv(S, mb - g.Wmb + 1, 2, cx, cy);
+        else if (aU) proxy_mv(S, mb - g.Wmb, 2, cx, cy);
+    } else if (pi == 2) {
+        aA = aL;
+        if (aL) proxy_mv(S, mb - 1, 3, ax, ay);
+        proxy_mv(S, mb, 0, bx, by); proxy_mv(S, mb, 1, cx, cy);
+    } else {
+        proxy_mv(S, mb, 2, ax, ay); proxy_mv(S, mb, 1, bx, by); proxy_mv(S, mb, 0, cx, cy);
+    }
+    median_pred(aA, ax, ay, aB, bx, by, aC, cx, cy, ox, oy);
+}
+
+// One warp per partition, four per CTA (one macroblock). Guesses of gen = mvp >> 2: the predictor rule applied to the
+// neighbours' proxies (98.5 % right on the bench content), then the partition's own proxy (together 99.7 %); without stage-3
+// lists (BasicInterEncoding) the gen phase B used for this partition in the previous P picture, else zero.
 __global__ void __launch_bounds__(128, 4) k_spec(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad1, int use_prev,
                                                  const CUtensorMap *__restrict__ tmaps)
 {
@@ -249,14 +286,17 @@ __global__ void __launch_bounds__(128, 4) k_spec(const SeqDev *__restrict__ seqs
     __syncwarp();
     // guesses
     int g0x = 0, g0y = 0, g1x = 0, g1y = 0, ng = 0;
-    if (n3 > 0) {
-        uint32_t k = 0xffffffffu;
-        for (int i = lane; i < n3; i += 32) k = min(k, ((uint32_t)sw->s3[i].sad << 8) | (uint32_t)i);
-        k = __reduce_min_sync(0xffffffffu, k);
-        const S3Entry e = sw->s3[k & 255u];
-        g0x = e.mvx >> 2; g0y = e.mvy >> 2; ng = 1;
+    if (!prm.basic) {
+        int dx, dy;
+        proxy_predictor(S, g, part >> 2, part & 3, dx, dy);
+        g0x = dx >> 2; g0y = dy >> 2; ng = 1;
+        const uint32_t own = __ldg(&S.proxy[part]);
+        if (own != SPEC_PREV_NONE) {
+            const int ox = (int)(int16_t)(own & 0xffffu) >> 2, oy = (int)(int16_t)(own >> 16) >> 2;
+            if (ox != g0x || oy != g0y) { g1x = ox; g1y = oy; ng = 2; }
+        }
     }
-    if (use_prev) {
+    if (use_prev && ng == 0) {
         const uint32_t pg = S.prev_gen[part];
         if (pg != SPEC_PREV_NONE) {
             const int px = (int16_t)(pg & 0xffffu), py = (int16_t)(pg >> 16);
@@ -268,4 +308,99 @@ __global__ void __launch_bounds__(128, 4) k_spec(const SeqDev *__restrict__ seqs
     for (int slot = 0; slot < ng; slot++)
         spec_slot(S, g, prm, part, xP, yP, rows, fq, n3, n2w, s2_off, slot ? g1x : g0x, slot ? g1y : g0y, slot, sw, win, cost, out, tmap, phase);
     if (ng == 1 && lane == 0) { out->gx[1] = SPEC_NOGUESS; out->gy[1] = SPEC_NOGUESS; out->nf[1] = SPEC_INVALID; }
+}
+
+// ---- P_Skip trial, precomputed (moestimation.cpp:402-425; mode_pred.cpp:383-401) -------------------------------------------
+// The skip vector is either zero or the 16x16 median predictor, known only inside the wavefront; whether the macroblock skips
+// is "all 256 luma samples within MAXDIFF of the prediction at that vector" (:228-244). Per macroblock this kernel evaluates the
+// test for the zero vector and for all 16 quarter-pel vectors of up to two guessed integer cells (the cell of partition 0's
+// first guess, and the cell of the predictor the macroblock had one picture earlier): a 16-bit mask per cell. Phase B looks the
+// answer up and only runs the test itself when the predictor falls outside the guessed cells. MAXDIFF (fixed, or the mean
+// absolute deviation of the macroblock, :407-419) is a function of the source alone and is computed here as well.
+struct __align__(16) MbSpec {
+    int16_t cx[2], cy[2];        // guessed integer cell of the skip vector per slot (SPEC_NOGUESS: none / not evaluable from the planes)
+    uint16_t mask[2];            // bit fy*4+fx: the macroblock skips with vector (4*cx+fx, 4*cy+fy)
+    int16_t maxdiff;
+    uint8_t zero_ok, pad;
+};
+static_assert(sizeof(MbSpec) == 16, "MbSpec size");
+#define SKIPWIN_BYTES (16 * 16 * QW_ROWB)
+
+// One warp per macroblock, four per CTA. tmaps16: tensor maps of the planes with a box of 32 bytes x 16 rows x 16 planes.
+__global__ void __launch_bounds__(128) k_skipspec(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, const CUtensorMap *__restrict__ tmaps16)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];      // 4 windows (128-byte aligned for the TMA) | 4 mbarriers
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *win = smem_raw + (size_t)warp * SKIPWIN_BYTES;
+    uint64_t *bar = (uint64_t *)(smem_raw + 4 * SKIPWIN_BYTES) + warp;
+    const SeqDev &S = seqs[seq0 + blockIdx.y];
+    const int mb = g.band_mb0 + blockIdx.x * 4 + warp;
+    if (mb >= g.band_mb0 + g.band_nmb) return;
+    const CUtensorMap *tmap = tmaps16 ? tmaps16 + seq0 + blockIdx.y : nullptr;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    uint32_t phase = 0;
+    const int mbx = mb % g.Wmb, mby = mb / g.Wmb, W = g.W, H = g.H;
+    const int r = lane >> 1, hf = lane & 1;                       // this lane's 8 samples: row r, columns 8*hf ..
+    const size_t own = (size_t)(mby * 16 + r) * W + mbx * 16 + 8 * hf;
+    const uint2 c = __ldg((const uint2 *)(S.cur[0] + own));
+    int maxdiff = prm.maxdiff_set;
+    if (prm.maxdiff_set == -1) {                                   // :407-419
+        const int sum = (int)__reduce_add_sync(0xffffffffu, __vsadu4(c.x, 0u) + __vsadu4(c.y, 0u));
+        const uint32_t mean4 = (uint32_t)(sum / 256) * 0x01010101u;
+        const int dev = (int)__reduce_add_sync(0xffffffffu, __vsadu4(c.x, mean4) + __vsadu4(c.y, mean4));
+        maxdiff = max(3, dev / 256);
+    }
+    const uint32_t md4 = (uint32_t)min(max(maxdiff, 0), 255) * 0x01010101u;
+    auto within = [&](uint2 p) -> bool {                            // every |cur - pred| <= MAXDIFF, warp-wide (:228-244)
+        const uint32_t bad = __vcmpgtu4(__vabsdiffu4(c.x, p.x), md4) | __vcmpgtu4(__vabsdiffu4(c.y, p.y), md4);
+        return !__any_sync(0xffffffffu, bad != 0u);
+    };
+    MbSpec ms;
+    ms.maxdiff = (int16_t)maxdiff; ms.pad = 0;
+    ms.zero_ok = maxdiff < 0 ? 0 : (uint8_t)within(__ldg((const uint2 *)(S.planes + own)));        // plane 0 == the reference picture
+    // guessed cells
+    int gx[2] = { SPEC_NOGUESS, SPEC_NOGUESS }, gy[2] = { SPEC_NOGUESS, SPEC_NOGUESS };
+    {
+        int n = 0;
+        if (!prm.basic) {
+            // 16x16 predictor (A = left q1, B = up q2, C = up-right q2 else up-left q3) on the proxies
+            const int aL = mbx > 0, aU = mby > 0, aUR = mby > 0 && mbx < g.Wmb - 1, aUL = mby > 0 && mbx > 0;
+            int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0, px, py;
+            if (aL) proxy_mv(S, mb - 1, 1, ax, ay);
+            if (aU) proxy_mv(S, mb - g.Wmb, 2, bx, by);
+            if (aUR) proxy_mv(S, mb - g.Wmb + 1, 2, cx, cy);
+            else if (aUL) proxy_mv(S, mb - g.Wmb - 1, 3, cx, cy);
+            median_pred(aL, ax, ay, aU, bx, by, aUR ? 1 : aUL, cx, cy, px, py);
+            gx[0] = px >> 2; gy[0] = py >> 2; n = 1;
+        }
+        const uint32_t pg = S.prev_gen16[mb];
+        if (pg != SPEC_PREV_NONE) {
+            const int px = (int16_t)(pg & 0xffffu), py = (int16_t)(pg >> 16);
+            if (n == 0) { gx[0] = px; gy[0] = py; }
+            else if (px != gx[0] || py != gy[0]) { gx[1] = px; gy[1] = py; }
+        }
+    }
+#pragma unroll
+    for (int sl = 0; sl < 2; sl++) {
+        ms.cx[sl] = SPEC_NOGUESS; ms.cy[sl] = SPEC_NOGUESS; ms.mask[sl] = 0;
+        if (gx[sl] == SPEC_NOGUESS || maxdiff < 0) continue;
+        const int X = mbx * 16 + gx[sl], Y = mby * 16 + gy[sl], xa = X & ~15, off = X - xa;
+        // the prediction equals the interpolated planes only where every sample position lies inside the picture (phase_c.cuh)
+        if (!tmap || X < 0 || xa + QW_ROWB > W || Y < 0 || Y + 16 > H) continue;
+        __syncwarp();
+        if (lane == 0) { mbar_expect_tx(bar, (uint32_t)SKIPWIN_BYTES); tma_load_window(tmap, win, bar, xa, Y); }
+        mbar_wait(bar, phase); phase ^= 1u;
+        uint32_t mask = 0;
+        const uint32_t *wp = (const uint32_t *)(win + (size_t)r * QW_ROWB) + ((off + 8 * hf) >> 2);
+        const uint32_t sh = (uint32_t)((off + 8 * hf) & 3) * 8;
+#pragma unroll 4
+        for (int f = 0; f < 16; f++) {
+            const uint32_t *w = wp + (size_t)f * (16 * QW_ROWB / 4);
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            if (within(make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh)))) mask |= 1u << f;
+        }
+        ms.cx[sl] = (int16_t)gx[sl]; ms.cy[sl] = (int16_t)gy[sl]; ms.mask[sl] = (uint16_t)mask;
+    }
+    if (lane == 0) *(uint4 *)&S.mbspec[mb] = *(const uint4 *)&ms;
 }

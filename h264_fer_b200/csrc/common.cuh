@@ -69,14 +69,13 @@ struct SeqDev {
     uint8_t *ref[3];        // `dpb`: previous reconstruction
     uint8_t *rec[3];        // reconstruction of the picture being coded (swapped with ref afterwards)
     uint8_t *planes;        // refFrameInterpolated[f].L, f-major, WH each (+16 bytes slack at the end)
+    uint16_t *k0p;          // 8x8 sums K0 of plane 0 per position (the first word of the feature distance: lower bound for stage 3's sweep)
     uint4 *kar;             // refFrameKar[0..4][f] per position: [f][y][x] = {F1|F2<<16, F3|F4<<16, K0, 0}, Fk = K0 - 2*Kk (int16)
     TileEntry *tent;        // ntiles * 4096 entries
     uint16_t *tstart;       // ntiles * FH_TSTART_PITCH
     PartA *parta;           // nparts
     S3Entry *s3;            // nparts * 33
-    uint2 *s2pool;          // stage-2 candidates in arrival order: {dx | dy<<16, feat | sad<<18}
-    uint32_t s2pool_size;
-    uint32_t *s2redo;       // partitions whose gated survivors overflowed the fast stage-2 launch (count in status[ST_S2REDO])
+    uint4 *s2pool;          // stage-2 candidates, a slice of S2_SLICE entries per partition, unordered: {dx | dy<<16, feature distance, lower bound of the SAD, arrival key}
     MbMotion *motion;       // nmb
     unsigned long long *qmv; // nmb * 4 tagged quadrant words (phase B wavefront): epoch << 32 | mvy << 16 | (mvx & 0xffff)
     PartSpec *spec;         // nparts: speculative finalists of the 8x8 search (phase S, read by phase B)

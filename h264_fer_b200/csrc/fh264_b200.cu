@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "phase_r.cuh"
 #include "phase_a.cuh"
+#include "stage3.cuh"
 #include "phase_b.cuh"
 #include "phase_c.cuh"
 #include "cavlc.cuh"
@@ -61,7 +62,7 @@ struct fh264_session {
     cudaEvent_t ev_spec;            // after stage 2, before phase S
     int use_spec;                   // phase S + fast path in phase B (FH264_SPEC=0 turns it off: every partition takes the full search)
     // TMA descriptors of the 16 interpolated planes of every sequence (qwin.cuh): box 16 bytes x tmap_rows rows x 16 planes
-    CUtensorMap *d_tmaps, *d_tmaps16;   // d_tmaps16: box of 16 rows (P_Skip trials of phase S)
+    CUtensorMap *d_tmaps, *d_tmaps16, *d_tmaps48;   // d_tmaps16: box of 16 rows (P_Skip trials of phase S); d_tmaps48: 48-byte rows (stage 3)
     int tmap_rows;
     int use_tma;                    // FH264_TMA=0: fill the pixel windows with ordinary loads (development knob)
     bool timed;
@@ -207,7 +208,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->ev_spec = nullptr;
     { const char *e = getenv("FH264_SPEC"); s->use_spec = !(e && atoi(e) == 0); }
     { const char *e = getenv("FH264_TMA"); s->use_tma = !(e && atoi(e) == 0); }
-    s->d_tmaps = nullptr; s->d_tmaps16 = nullptr; s->tmap_rows = 0;
+    s->d_tmaps = nullptr; s->d_tmaps16 = nullptr; s->d_tmaps48 = nullptr; s->tmap_rows = 0;
     for (int i = 0; i < 3; i++) s->d_scr[i] = nullptr;
     s->d_scr16[0] = s->d_scr16[1] = nullptr;
     Geo &g = s->g;
@@ -251,13 +252,12 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         }
         OPEN_CK(dalloc(s, &S.planes, 16 * WH));
         OPEN_CK(dalloc(s, &S.kar, WH));                  // plane 0 only (16 B per position)
+        OPEN_CK(dalloc(s, &S.k0p, WH + 64));
         OPEN_CK(dalloc(s, &S.tent, (size_t)g.ntiles * FH_TILE * FH_TILE));
         OPEN_CK(dalloc(s, &S.tstart, (size_t)g.ntiles * FH_TSTART_PITCH));
         OPEN_CK(dalloc(s, &S.parta, (size_t)g.nparts));
         OPEN_CK(dalloc(s, &S.s3, (size_t)g.nparts * FH_S3_MAX));
-        S.s2pool_size = (uint32_t)std::min<size_t>((size_t)g.nparts * 1024, 0x7fffffffu);   // worst case: 1023 candidates per partition
-        OPEN_CK(dalloc(s, &S.s2pool, (size_t)S.s2pool_size));
-        OPEN_CK(dalloc(s, &S.s2redo, (size_t)S2_REDO_MAX));
+        OPEN_CK(dalloc(s, &S.s2pool, (size_t)g.nparts * S2_SLICE));
         OPEN_CK(dalloc(s, &S.motion, (size_t)g.nmb));
         OPEN_CK(dalloc(s, &S.spec, (size_t)g.nparts));
         OPEN_CK(dalloc(s, &S.mbspec, (size_t)g.nmb));
@@ -288,6 +288,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     OPEN_CK(dalloc(s, &s->d_ticket, (size_t)4));
     OPEN_CK(dalloc(s, &s->d_tmaps, (size_t)batch));
     OPEN_CK(dalloc(s, &s->d_tmaps16, (size_t)batch));
+    OPEN_CK(dalloc(s, &s->d_tmaps48, (size_t)batch));
     OPEN_CK(dalloc(s, &s->d_sync, (size_t)FH_MAX_WORLD));
     OPEN_CK(cudaFuncSetAttribute(k_tile_index, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_CELLS * 4));
     OPEN_CK(cudaFuncSetAttribute(k_stage3, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -437,17 +438,18 @@ static int ensure_tmaps(fh264_session *s, int rows)
     }
     const Geo &g = s->g;
     std::vector<CUtensorMap> maps(s->batch);
-    for (int pass = s->tmap_rows == 0 ? 0 : 1; pass < 2; pass++) {          // first call: the 16-row maps too
-        const int brows = pass == 0 ? 16 : rows;
+    const int g1w = (rows - 9) / 2;
+    for (int pass = s->tmap_rows == 0 ? 0 : 1; pass < 3; pass++) {          // first call: the 16-row maps too
+        const int brows = pass == 0 ? 16 : (pass == 1 ? rows : s3_win_rows(g1w));
         for (int b = 0; b < s->batch; b++) {
             const cuuint64_t dims[3] = { (cuuint64_t)g.W, (cuuint64_t)g.H, 16 };
             const cuuint64_t strides[2] = { (cuuint64_t)g.W, (cuuint64_t)g.WH };
-            const cuuint32_t box[3] = { QW_ROWB, (cuuint32_t)brows, 16 }, estr[3] = { 1, 1, 1 };
+            const cuuint32_t box[3] = { (cuuint32_t)(pass == 2 ? S3_ROWB : QW_ROWB), (cuuint32_t)brows, 16 }, estr[3] = { 1, 1, 1 };
             const CUresult r = enc(&maps[b], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s->h[b].planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(FH264_E_CUDA, "cuTensorMapEncodeTiled failed");
         }
-        CK(cudaMemcpyAsync(pass == 0 ? s->d_tmaps16 : s->d_tmaps, maps.data(), sizeof(CUtensorMap) * s->batch, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(pass == 0 ? s->d_tmaps16 : (pass == 1 ? s->d_tmaps : s->d_tmaps48), maps.data(), sizeof(CUtensorMap) * s->batch, cudaMemcpyHostToDevice, s->stream));
         CK(cudaStreamSynchronize(s->stream));          // `maps` is a local
     }
     s->tmap_rows = rows;
@@ -519,24 +521,19 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
     k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, s->d_ticket);
     if (prm.basic) CK(cudaEventRecord(s->evk[0], st));
     if (!prm.basic) {
-        const int g3 = prm.window / 2, g1 = prm.window / 16;
-        const int n3 = (2 * g3 + 1) * (2 * g3 + 1) + (2 * g1 + 1) * (2 * g1 + 1) * 16;
-        const int npad = (n3 + 31) & ~31;
-        const size_t smem3 = 4 * sizeof(S3Warp) + (size_t)4 * npad * sizeof(uint32_t);
+        const int g1 = prm.window / 16;
+        const size_t smem3 = (size_t)s3_win_bytes(g1) + 16 + 4 * sizeof(S3WarpV2);
         dim3 g3d(g.band_nmb, nseq), g2d(g.band_nmb * 2, nseq);          // 4 / 2 partitions per CTA
-        k_stage3<<<g3d, 128, smem3, st>>>(s->d_seqs, seq0, g, prm, npad);
+        k_stage3<<<g3d, 128, smem3, st>>>(s->d_seqs, seq0, g, prm, s->use_tma ? s->d_tmaps48 : nullptr);
         CK(cudaEventRecord(s->evk[0], st));
-        k_stage2<S2_CAP_FAST, 2, false><<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
-        // partitions with more than S2_CAP_FAST gated survivors (marked) are redone with the large buffers; every other warp exits at once
-        dim3 g2r(S2_REDO_MAX, nseq);
-        k_stage2<S2_CAP_BIG, 1, true><<<g2r, 32, 0, st>>>(s->d_seqs, seq0, g, prm);
+        k_stage2<2><<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
     CK(cudaEventRecord(s->ev_spec, st));
     if (s->use_spec) {
         // phase S: the search completed for the guessed integer predictors (spec.cuh)
-        const int g1 = prm.window / 16, n1 = (2 * g1 + 1) * (2 * g1 + 1) * 16, npad1 = (n1 + 31) & ~31;
-        const size_t smems = 4 * (size_t)qwin_bytes(g1) + 4 * sizeof(SpecWarp) + (size_t)4 * npad1 * sizeof(uint32_t) + 16;
-        k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, npad1, 1, s->use_tma ? s->d_tmaps : nullptr);
+        const int g1 = prm.window / 16;
+        const size_t smems = 4 * (size_t)qwin_bytes(g1) + 4 * sizeof(SpecWarp) + 16;
+        k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, 1, s->use_tma ? s->d_tmaps : nullptr);
         k_skipspec<<<dim3((g.band_nmb + 3) / 4, nseq), 128, 4 * SKIPWIN_BYTES + 64, st>>>(s->d_seqs, seq0, g, prm, s->use_tma ? s->d_tmaps16 : nullptr);
         CKL();
     }

@@ -148,205 +148,42 @@ __device__ __forceinline__ int warp_select_costs(const uint32_t *cost, int n, in
     return K;
 }
 
-__global__ void __launch_bounds__(128, 6) k_stage3(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    S3Warp *sw = (S3Warp *)smem_raw + warp;
-    uint32_t *cost = (uint32_t *)(smem_raw + 4 * sizeof(S3Warp)) + (size_t)warp * npad;
-    const SeqDev &S = seqs[seq0 + blockIdx.y];
-    const int part = g.band_mb0 * 4 + blockIdx.x * 4 + warp;
-    int xP, yP;
-    part_origin(g, part, xP, yP);
-    uint2 rows[8];
-    load_cur8x8(S.cur[0], g, xP, yP, rows);
-    int s[5];
-    block_sums(rows, s);
-    const FeatQ fq = feat_query(s);
-    const int W = g.W, H = g.H;
-    const int g3 = prm.window / 2, g1 = prm.window / 16;
-    const int w3 = 2 * g3 + 1, w1 = 2 * g1 + 1;
-    const int n3a = w3 * w3, n3b = w1 * w1 * 16, N = n3a + n3b;
-    const uint32_t i3 = udiv_magic((uint32_t)w3), i1 = udiv_magic((uint32_t)w1);
-    const uint4 *__restrict__ K0p = S.kar;
-    uint32_t m1 = COST_INVALID, m2 = COST_INVALID;     // this lane's two smallest costs so far (selection bound)
-    // first call: MEstimation(g = window/2, frac 0); arrival index = (dx + g3) * w3 + (dy + g3).
-    // lane = column (coalesced 16-byte loads), 4 rows in flight; rows [rlo, rhi) lie inside the picture.
-    const int rlo = max(0, g3 - yP), rhi = min(w3, H - yP + g3);
-    const int ncf = w3 & ~31;
-    for (int cb = 0; cb < ncf; cb += 32) {
-        const int c = cb + lane, dx = c - g3, rx = xP + dx;
-        const bool xok = rx >= 0 && rx < W;
-        const int adx = iabs_(dx) + 4;
-        uint32_t *cc = cost + c * w3;
-        for (int r = 0; r < rlo; r++) cc[r] = COST_INVALID;
-        for (int r = rhi; r < w3; r++) cc[r] = COST_INVALID;
-        const uint4 *kp = K0p + (size_t)(yP - g3 + rlo) * W + rx;
-        auto ld4 = [&](const uint4 *q, int r0, uint4 (&v)[FH_S3_UNR]) {
-#pragma unroll
-            for (int u = 0; u < FH_S3_UNR; u++) { v[u] = make_uint4(0, 0, 0, 0); if (xok && r0 + u < rhi) v[u] = __ldg(q + (size_t)u * W); }
-        };
-        auto ev4 = [&](const uint4 (&v)[FH_S3_UNR], int r0) {
-#pragma unroll
-            for (int u = 0; u < FH_S3_UNR; u++) {
-                const int r = r0 + u;
-                if (r < rhi) {
-                    const uint32_t cst = xok ? (uint32_t)((adx + iabs_(r - g3)) * feat_of(fq, v[u])) : COST_INVALID;
-                    cc[r] = cst;
-                    m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
-                }
-            }
-        };
-        uint4 va[FH_S3_UNR];
-        for (int r0 = rlo; r0 < rhi; r0 += FH_S3_UNR) { ld4(kp, r0, va); ev4(va, r0); kp += (size_t)FH_S3_UNR * W; }
-    }
-    // leftover columns: lane = row
-    for (int c = ncf; c < w3; c++) {
-        const int dx = c - g3, rx = xP + dx;
-        const bool xok = rx >= 0 && rx < W;
-        for (int r = lane; r < w3; r += 32) {
-            uint32_t cst = COST_INVALID;
-            if (xok && r >= rlo && r < rhi) cst = (uint32_t)((iabs_(dx) + iabs_(r - g3) + 4) * feat_of(fq, __ldg(K0p + (size_t)(yP + r - g3) * W + rx)));
-            cost[c * w3 + r] = cst;
-            m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
-        }
-    }
-    // second call: MEstimation(g = window/16, all 16 fractions); arrival = ((dx+g1)*w1 + (dy+g1))*16 + frac.
-    // The features of the quarter-pel planes are computed from the planes themselves (qfeat.cuh), a few planes per batch,
-    // in the selection scratch (free until the selection below).
-    {
-        const int npos = w1 * w1, R = 8 + w1 - 1, ps = R * w1, pb = w1 <= 5 ? 4 : 1;
-        uint32_t *X = (uint32_t *)sw->ws.skey;
-        uint16_t *RC = sw->ws.sidx;
-        const uint32_t iR = udiv_magic((uint32_t)R), iN = udiv_magic((uint32_t)npos);
-        for (int f0 = 0; f0 < 16; f0 += pb) {
-            // step A: two rows per lane in flight
-            for (int sg0 = 0; sg0 < pb * R; sg0 += 64) {
-                uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;
-                const int sa = sg0 + lane, sb = sg0 + 32 + lane;
-                const int fa = udiv_by(sa, iR), ra = sa - fa * R, fb = udiv_by(sb, iR), rb = sb - fb * R;
-                if (sa < pb * R) wa = qf_load16(S.planes + (size_t)(f0 + fa) * g.WH, W, H, xP - g1, yP - g1 + ra);
-                if (sb < pb * R) wb = qf_load16(S.planes + (size_t)(f0 + fb) * g.WH, W, H, xP - g1, yP - g1 + rb);
-                if (sa < pb * R) qf_row_sums(wa, w1, X + fa * ps + ra * w1, RC + fa * ps + ra * w1);
-                if (sb < pb * R) qf_row_sums(wb, w1, X + fb * ps + rb * w1, RC + fb * ps + rb * w1);
-            }
-            __syncwarp();
-            // step B: one (plane, position) per lane and round
-            // (the lane -> element map is rotated from batch to batch: every lane should meet many different window
-            // positions, or the per-lane minima that bound the selection below stay loose)
-            const int rot = (f0 * 13) % (pb * npos);
-            for (int o0 = lane; o0 < pb * npos; o0 += 32) {
-                const int o = o0 + rot < pb * npos ? o0 + rot : o0 + rot - pb * npos;
-                const int fl = udiv_by(o, iN), pos = o - fl * npos, cx = udiv_by(pos, i1), cy = pos - cx * w1;
-                const int rx = xP + cx - g1, ry = yP + cy - g1;
-                uint32_t cst = COST_INVALID;
-                if (rx >= 0 && rx < W && ry >= 0 && ry < H)
-                    cst = (uint32_t)((iabs_(cx - g1) + iabs_(cy - g1) + 4) * feat_of(fq, qf_record(X, RC, fl, ps, w1, cx, cy)));
-                cost[n3a + pos * 16 + f0 + fl] = cst;
-                m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
-            }
-            __syncwarp();
-        }
-    }
-    __syncwarp();
-    // candidates = positions whose block origin lies inside the picture (:263-266)
-    const int nva = max(0, min(W - 1, xP + g3) - max(0, xP - g3) + 1) * max(0, rhi - rlo);
-    const int nvb = max(0, min(W - 1, xP + g1) - max(0, xP - g1) + 1) * max(0, min(H - 1, yP + g1) - max(0, yP - g1) + 1) * 16;
-    // the 33 smallest by (cost, arrival index), in list order
-    const int nm = warp_select_costs(cost, N, FH_S3_MAX, nva + nvb, m1, m2, &sw->ws, sw->members);
-    // SADs of the members (satdLuma8x8MVs): 8 lanes per member, one row each; 3 rounds of loads in flight
-    const int r = lane & 7;
-    const uint2 cr = pick_row(rows, r);
-    for (int base = 0; base < nm; base += 4 * FH_S3_SADR) {
-        uint2 rr[FH_S3_SADR];                           // 33 members x 8 rows = 264 row loads
-#pragma unroll
-        for (int u = 0; u < FH_S3_SADR; u++) {
-            const int m = base + u * 4 + (lane >> 3);
-            rr[u] = make_uint2(0, 0);
-            if (m < nm) {
-                int dx, dy, f;
-                s3_decode((int)sw->members[m], n3a, w3, g3, i3, w1, g1, i1, dx, dy, f);
-                rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, xP + dx, yP + dy + r);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < FH_S3_SADR; u++) {
-            const int m = base + u * 4 + (lane >> 3);
-            int sad = m < nm ? sad8(cr, rr[u]) : 0;
-            sad += __shfl_xor_sync(0xffffffffu, sad, 1);
-            sad += __shfl_xor_sync(0xffffffffu, sad, 2);
-            sad += __shfl_xor_sync(0xffffffffu, sad, 4);
-            if (m < nm && r == 0) sw->msad[m] = (uint16_t)sad;
-        }
-    }
-    __syncwarp();
-    for (int m = lane; m < nm; m += 32) {
-        int dx, dy, f;
-        s3_decode((int)sw->members[m], n3a, w3, g3, i3, w1, g1, i1, dx, dy, f);
-        S3Entry e;
-        e.mvx = (int16_t)((dx << 2) | (f & 3)); e.mvy = (int16_t)((dy << 2) | (f >> 2)); e.sad = sw->msad[m]; e.pad = 0;
-        S.s3[(size_t)part * FH_S3_MAX + m] = e;
-    }
-    // the list's best vector by SAD (first in list order): phase S guesses the neighbours' final vectors with it (spec.cuh)
-    {
-        uint32_t k = 0xffffffffu;
-        for (int m = lane; m < nm; m += 32) k = min(k, ((uint32_t)sw->msad[m] << 8) | (uint32_t)m);
-        k = __reduce_min_sync(0xffffffffu, k);
-        if (lane == 0) {
-            uint32_t px = 0x7f7f7f7fu;
-            if (nm > 0) {
-                int dx, dy, f;
-                s3_decode((int)sw->members[k & 255u], n3a, w3, g3, i3, w1, g1, i1, dx, dy, f);
-                px = ((uint32_t)((dx << 2) | (f & 3)) & 0xffffu) | ((uint32_t)((dy << 2) | (f >> 2)) << 16);
-            }
-            S.proxy[part] = px;
-        }
-    }
-    if (lane == 0) {
-        PartA *pa = &S.parta[part];
-#pragma unroll
-        for (int k = 0; k < 5; k++) pa->suma[k] = (uint16_t)s[k];
-        pa->n3 = (uint16_t)nm;
-    }
-}
-
 #define S2_BINS 384           // (j, side) bins: 2*j + side, j <= 180
 #define S2_CHUNK_CAP 512      // a round of 32 short ranges (<= 64 entries each) adds at most 256 chunks
-#define S2_CAP_FAST 512       // gated survivors per partition held by the main launch
-#define S2_CAP_BIG 4096       // ... and by the fallback launch (beyond: FH264_E_CAPACITY)
-#define S2_REDO_MAX 1024      // partitions per picture the fallback launch can take over
+#define S2_CAP 512            // gated entries up to the running j_stop bound held per partition
+#define S2_SLICE 512          // pool entries per partition (16 bytes each); more candidates than that: S2_SLOW
 
-template <int CAP>
 struct S2Warp {
-    uint32_t akey[CAP];              // arrival key: j<<21 | side<<20 | (dx+279)<<10 | (dy+279)
-    uint32_t aval[CAP];              // index entry number, later feature distance (18 bits) | SAD << 18
-    uint16_t order[CAP];             // survivor index by output slot
-    uint32_t bins[S2_BINS];          // counts, then exclusive starts, then scatter cursors
+    uint32_t akey[S2_CAP];           // arrival key: j<<21 | side<<20 | (dx+279)<<10 | (dy+279)
+    uint32_t aval[S2_CAP];           // index entry number
+    uint32_t bins[S2_BINS];          // per (j, side) counts of the kept entries (recounted when the bound is tightened)
     uint32_t chunk[S2_CHUNK_CAP];    // chunks of <= 8 consecutive index entries still to be visited
-    int n_surv;
 };
 
-// CAP = survivor capacity per warp, NW = warps (= partitions) per CTA. The main launch (CAP = 512) keeps shared memory
-// small for occupancy; partitions with more gated survivors are marked and redone by a second launch with CAP = 4096.
-template <int CAP, int NW, bool REDO>
-__global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
+// Stage-2 candidate SET of every partition (moestimation.cpp:470-497), one warp per partition: positions whose 8x8 sum is within
+// +-j_stop of the block's, gated by Manhattan distance and the two half-sums. Output: pool entries {dx | dy << 16, feature
+// distance, lower bound of the SAD, arrival key} in no particular order (bucket s0 twice, :476,486) — ranking by cost needs the
+// multiplier of the (guessed or true) predictor and happens in phase S / phase B, and so do the SADs of the few candidates that
+// can matter (the lower bound — the largest of the feature distance's box-pair terms, each a sum of |differences| over
+// complementary boxes — rules the others out).
+// The walk keeps gated entries only while j <= jb, a running upper bound of j_stop: the first j whose gated count (bucket s0
+// twice) exceeds 128 can only move down as more entries are seen. Entries are appended by ballot compaction; jb is recomputed
+// from the kept entries whenever the buffer fills. Content where thousands of positions share one sum (flat) overflows the
+// buffer: the walk then only counts, records the exact j_stop, and phase B enumerates the set itself (S2_SLOW).
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, FH_S2_MINB) k_stage2(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
 {
-    __shared__ S2Warp<CAP> sm[NW];
+    __shared__ S2Warp sm[NW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    S2Warp<CAP> *w = &sm[warp];
+    S2Warp *w = &sm[warp];
     const SeqDev &S = seqs[seq0 + blockIdx.y];
-    // REDO launch: CTA b takes the b-th partition the main launch listed as overflowing (usually none: exit at once)
-    if (REDO && blockIdx.x >= min(S.status[ST_S2REDO], (uint32_t)S2_REDO_MAX)) return;
-    const int part = REDO ? (int)S.s2redo[blockIdx.x] : g.band_mb0 * 4 + blockIdx.x * NW + warp;
+    const int part = g.band_mb0 * 4 + blockIdx.x * NW + warp;
     int xP, yP;
     part_origin(g, part, xP, yP);
     uint2 rows[8];
     load_cur8x8(S.cur[0], g, xP, yP, rows);
     int s[5];
     block_sums(rows, s);
-    for (int i = lane; i < S2_BINS; i += 32) w->bins[i] = 0;
-    if (lane == 0) w->n_surv = 0;
-    __syncwarp();
     // tiles intersecting the bounding box of the diamond |dx|+|dy| < 280 (moestimation.cpp:481)
     const int tx0 = max(0, xP - 279) >> FH_TILE_SHIFT, tx1 = min(g.W - 1, xP + 279) >> FH_TILE_SHIFT;
     const int ty0 = max(0, yP - 279) >> FH_TILE_SHIFT, ty1 = min(g.H - 1, yP + 279) >> FH_TILE_SHIFT;
@@ -359,30 +196,32 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
     const int inv_nq = 65536 / nq + 1;
     const int ntiles = ntx * nty, inv_ntx = 65536 / ntx + 1;
     const uint4 *__restrict__ tent = (const uint4 *)S.tent;
-    // gate of one index entry (:481). Gated entries are counted per (j, side); they are KEPT only while j <= jb, a running
-    // upper bound of j_stop (counts only grow, so the first j whose running total exceeds 128 can only move down). The
-    // feature distance is computed afterwards in a dense pass over the kept entries.
-    int jb = 180;
+    int jb = 180;                     // running upper bound of j_stop
+    int ns = 0;                       // kept entries (warp-uniform)
+    bool countonly = false;           // the buffer overflowed for good: only the (j, side) counts go on
     // the four gates in 16-bit lanes: (|dx|, |dy|) and (j, |dK1|) by max(a - b, b - a), the Manhattan sum by a dot product
-    const uint32_t Pxy = (uint32_t)xP | ((uint32_t)yP << 16), S01 = (uint32_t)s[0] | ((uint32_t)s[1] << 16), LIM01 = 180u | (99u << 16);
+    const uint32_t Pxy = (uint32_t)xP | ((uint32_t)yP << 16), S01 = (uint32_t)s[0] | ((uint32_t)s[1] << 16);
+    uint32_t LIM01 = (uint32_t)jb | (99u << 16);
     const int s2m = s[2] - 99;
     auto visit = [&](const uint4 v, uint32_t eidx) {
         const uint32_t ad = __vmaxs2(__vsub2(v.x, Pxy), __vsub2(Pxy, v.x)), ae = __vmaxs2(__vsub2(v.y, S01), __vsub2(S01, v.y));
         const bool ok = __vmaxu2(ae, LIM01) == LIM01 && __dp2a_lo(ad, 0x0101u, 0u) < 280u && (uint32_t)((int)(v.z & 0xffffu) - s2m) < 199u;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m == 0u) return;
         if (ok) {
             const int j = (int)(ae & 0xffffu), side = (int)(v.y & 0xffffu) > s[0];
-            atomicAdd(&w->bins[2 * j + side], 1u);
-            if (j <= jb) {
-                const int pos = atomicAdd(&w->n_surv, 1);
-                if (pos < CAP) {
-                    const int dx = (int)(v.x & 0xffffu) - xP, dy = (int)(v.x >> 16) - yP;
-                    w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
-                    w->aval[pos] = eidx;
-                }
+            if (countonly) atomicAdd(&w->bins[2 * j + side], 1u);
+            else {
+                const int pos = ns + __popc(m & ((1u << lane) - 1u));
+                const int dx = (int)(v.x & 0xffffu) - xP, dy = (int)(v.x >> 16) - yP;
+                w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
+                w->aval[pos] = eidx;
             }
         }
+        if (!countonly) ns += __popc(m);
     };
-    // j_stop bound from the counts so far: first j whose running gated count (bucket s0 twice) exceeds 128 (:496)
+    // first j whose running gated count (bucket s0 twice) exceeds 128 (:496), else 180, from the (j, side) counts. Lane l owns
+    // j = 6l .. 6l+5 (bins 12l .. 12l+11).
     auto bound_from_bins = [&]() -> int {
         uint32_t local = 0, c6[6];
 #pragma unroll
@@ -395,27 +234,36 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
         for (int i = 0; i < 6; i++) { run += c6[i]; if (run > 128 && first == 180) first = min(180, lane * 6 + i); }
         return __reduce_min_sync(0xffffffffu, first);
     };
-    // keep the kept-entry buffer from overflowing: tighten jb and drop entries beyond it (called at warp-uniform points)
-    auto tighten = [&]() {
+    auto recount = [&]() -> int {     // (j, side) counts of the kept entries -> bound
         __syncwarp();
-        if (w->n_surv <= CAP - 256) return;
-        const int nb = bound_from_bins();
-        const int n = min(w->n_surv, CAP);
+        for (int i = lane; i < S2_BINS; i += 32) w->bins[i] = 0;
+        __syncwarp();
+        for (int i = lane; i < ns; i += 32) atomicAdd(&w->bins[w->akey[i] >> 20], 1u);
+        __syncwarp();
+        return bound_from_bins();
+    };
+    // room for `need` more entries: tighten jb from the kept entries and drop those beyond it (warp-uniform call sites)
+    auto make_room = [&](int need) {
+        if (countonly || ns + need <= S2_CAP) return;
+        const int nb = recount();
         int outn = 0;
-        for (int base = 0; base < n; base += 32) {
+        for (int base = 0; base < ns; base += 32) {
             const int i = base + lane;
-            const uint32_t k = i < n ? w->akey[i] : 0xffffffffu, e = i < n ? w->aval[i] : 0u;
-            const bool keep = i < n && (int)(k >> 21) <= nb;
+            const uint32_t k = i < ns ? w->akey[i] : 0xffffffffu, e = i < ns ? w->aval[i] : 0u;
+            const bool keep = i < ns && (int)(k >> 21) <= nb;
             const unsigned b = __ballot_sync(0xffffffffu, keep);
             __syncwarp();
             if (keep) { const int p = outn + __popc(b & ((1u << lane) - 1u)); w->akey[p] = k; w->aval[p] = e; }
             outn += __popc(b);
+            __syncwarp();
         }
-        __syncwarp();
-        // entries lost to an overflow since the last call cannot be recovered: poison the count so the partition is redone
-        if (lane == 0) w->n_surv = (w->n_surv > CAP) ? 0x40000000 : outn;
-        jb = nb;
-        __syncwarp();
+        ns = outn; jb = nb;
+        LIM01 = (uint32_t)jb | (99u << 16);
+        if (ns + need > S2_CAP) {
+            // more entries at or below the bound than the buffer holds (thousands of positions share one sum): count only from here on
+            countonly = true;
+            recount();                // bins = counts of what is kept (all with j <= jb); later entries add to them
+        }
     };
     int nchunk = 0;
     const int nitems = ntiles * nq;
@@ -440,8 +288,10 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
             longm &= longm - 1;
             const uint32_t gb = __shfl_sync(0xffffffffu, gbase, src);
             const int ln = __shfl_sync(0xffffffffu, len, src);
-            for (int e0 = 0; e0 < ln; e0 += 32) { if (e0 + lane < ln) visit(__ldg(tent + gb + e0 + lane), gb + e0 + lane); if ((e0 & 255) == 224) tighten(); }
-            tighten();
+            for (int e0 = 0; e0 < ln; e0 += 32) {
+                make_room(32);
+                visit(e0 + lane < ln ? __ldg(tent + gb + e0 + lane) : make_uint4(0, 0xffffu, 0x7fffu, 0), gb + e0 + lane);
+            }
             if (lane == src) len = 0;
         }
         // short ranges: chunks of <= 8 consecutive entries (one 128-byte line): first entry | (count - 1) << 28
@@ -466,166 +316,54 @@ __global__ void __launch_bounds__(32 * NW, REDO ? 1 : FH_S2_MINB) k_stage2(const
                     eid[u] = (cw & 0x0fffffffu) + (uint32_t)(lane & 7);
                     v[u] = (lane & 7) < cnt ? __ldg(tent + eid[u]) : make_uint4(0, 0xffffu, 0x7fffu, 0);
                 }
+                make_room(32 * FH_S2_UNR);
 #pragma unroll
                 for (int u = 0; u < FH_S2_UNR; u++) visit(v[u], eid[u]);
-                tighten();                                  // at most 256 entries were added since the last check
             }
             nchunk = 0;
             __syncwarp();
         }
     }
     __syncwarp();
-    const int ns = w->n_surv;
-    if (ns > CAP) {
-        // too many gated survivors for this launch's buffers: the fallback launch takes the partition over; when that cannot
-        // hold it either (or its list is full) phase B enumerates the set itself. j_stop is final here (the counts saw every entry).
+    PartA *pa = &S.parta[part];
+    if (countonly) {
+        // j_stop is exact: the counts saw every gated entry at or below the bound that was current when it arrived
         const int jsb = bound_from_bins();
-        // candidates up to j_stop (bucket s0 twice): more than a pool slice holds -> no point in the fallback launch either
-        uint32_t upto = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            uint32_t c = w->bins[lane * 12 + 2 * i] + w->bins[lane * 12 + 2 * i + 1];
-            if (lane == 0 && i == 0) c *= 2;
-            if (lane * 6 + i <= jsb) upto += c;
-        }
-        const bool fits = __reduce_add_sync(0xffffffffu, upto) <= 1023u;
-        if (lane == 0) {
-            PartA *pa = &S.parta[part];
-            pa->s2_off = 0;
-            bool listed = false;
-            if (!REDO && fits) { const uint32_t k = atomicAdd(&S.status[ST_S2REDO], 1u); if (k < S2_REDO_MAX) { S.s2redo[k] = (uint32_t)part; listed = true; } }
-            pa->n2 = listed ? 0u : (S2_SLOW | (uint32_t)jsb);
-        }
+        if (lane == 0) { pa->s2_off = 0; pa->n2 = S2_SLOW | (uint32_t)jsb; }
         return;
     }
-    // dense pass over the kept entries: feature distance (:267-276)
-    for (int i = lane; i < ns; i += 32) {
-        const uint4 v = __ldg(tent + w->aval[i]);
-        w->aval[i] = (uint32_t)feat_dist(s, (int)(v.y & 0xffff), (int)(v.y >> 16), (int)(v.z & 0xffff), (int)(v.z >> 16), (int)(v.w & 0xffff));
+    const int js = recount();         // every gated entry with j <= jb is kept and jb >= j_stop: the exact j_stop
+    // candidates: kept entries with j <= j_stop, bucket s0 listed twice (the second visit gets side 1, :476,486)
+    uint4 *pool = S.s2pool + (size_t)part * S2_SLICE;
+    int n2 = 0;
+    bool fits = true;
+    for (int base = 0; base < ns; base += 32) {
+        const int i = base + lane;
+        const uint32_t k = i < ns ? w->akey[i] : 0xffffffffu;
+        const bool in = i < ns && (int)(k >> 21) <= js;
+        const int cnt = in ? ((k >> 21) == 0u ? 2 : 1) : 0;
+        int incl = cnt;
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (n2 + tot > S2_SLICE - 1) { fits = false; break; }
+        if (in) {
+            const uint4 v = __ldg(tent + w->aval[i]);
+            const int k0 = (int)(v.y & 0xffff), k1 = (int)(v.y >> 16), k2 = (int)(v.z & 0xffff), k3 = (int)(v.z >> 16), k4 = (int)(v.w & 0xffff);
+            // feature distance (:267-276) and its largest box-pair term (a lower bound of the SAD)
+            const int d0 = s[0] - k0, ad = iabs_(d0);
+            const int p1 = max(ad, iabs_(2 * (s[1] - k1) - d0)), p2 = max(ad, iabs_(2 * (s[2] - k2) - d0));
+            const int p3 = max(ad, iabs_(2 * (s[3] - k3) - d0)), p4 = max(ad, iabs_(2 * (s[4] - k4) - d0));
+            const uint32_t feat = (uint32_t)(ad + p1 + p2 + p3 + p4), lb = (uint32_t)max(max(p1, p2), max(p3, p4));
+            const int dx = (int)((k >> 10) & 1023) - 279, dy = (int)(k & 1023) - 279;
+            const uint32_t xy = ((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16);
+            const int o = n2 + incl - cnt;
+            pool[o] = make_uint4(xy, feat, lb, k);
+            if (cnt == 2) pool[o + 1] = make_uint4(xy, feat, lb, k | (1u << 20));
+        }
+        n2 += tot;
     }
-    __syncwarp();
-    // j_stop: first j at which the running gated count exceeds 128 (:496), else 180. Bucket s0 is visited by both
-    // sides (:476,486), so its entries count twice. Lane l owns j = 6l .. 6l+5 (bins 12l .. 12l+11).
-    uint32_t cb[12], cj[6], local = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) cb[i] = w->bins[lane * 12 + i];
-#pragma unroll
-    for (int i = 0; i < 6; i++) { cj[i] = cb[2 * i] + cb[2 * i + 1]; if (lane == 0 && i == 0) cj[i] *= 2; local += cj[i]; }
-    uint32_t incl = local;
-    for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-    const uint32_t excl = incl - local;
-    uint32_t run = excl;
-    int first = 1 << 20;
-#pragma unroll
-    for (int i = 0; i < 6; i++) { run += cj[i]; if (run > 128 && first == (1 << 20)) first = lane * 6 + i; }
-    first = __reduce_min_sync(0xffffffffu, first);
-    const int js = min(first, 180);
-    uint32_t upto = 0;
-#pragma unroll
-    for (int i = 0; i < 6; i++) if (lane * 6 + i <= js) upto += cj[i];
-    int n2 = (int)__reduce_add_sync(0xffffffffu, upto);
-    const int cnt0 = (int)__shfl_sync(0xffffffffu, cb[0], 0);
-    // every partition owns a fixed 1024-entry slice of the candidate pool (no allocation, and phase B can prefetch it
-    // without first reading the partition header)
-    uint32_t off = (uint32_t)part * 1024u;
     if (lane == 0) {
-        PartA *pa = &S.parta[part];
-        pa->s2_off = off;
-        if (n2 > 1023) { pa->n2 = S2_SLOW | (uint32_t)js; n2 = 0; }      // more candidates than a pool slice: phase B's own enumeration
-        else if (!REDO && n2 > CAP) {
-            // the kept entries fit, but with bucket s0 listed twice the output slots would run past order[CAP] (half-flat content:
-            // hundreds of positions share the block's exact sum): the fallback launch, whose buffers hold any pool slice, redoes it
-            const uint32_t k = atomicAdd(&S.status[ST_S2REDO], 1u);
-            const bool listed = k < S2_REDO_MAX;
-            if (listed) S.s2redo[k] = (uint32_t)part;
-            pa->s2_off = 0;
-            pa->n2 = listed ? 0u : (S2_SLOW | (uint32_t)js);
-            n2 = 0;
-        }
-        else pa->n2 = (uint32_t)n2;
-    }
-    n2 = __shfl_sync(0xffffffffu, n2, 0);
-    if (n2 == 0) return;
-    // Arrival order (:474-495): j ascending; minus side before plus side; x then y inside a bucket; bucket s0 twice.
-    // Output slot of bin (j, side): start = (entries of smaller j, bucket s0 counted twice) + (side ? count of side 0 : 0);
-    // the second visit of bucket s0 is a copy at cnt0. Starts replace the counts in w->bins.
-    {
-        uint32_t st = excl;
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            w->bins[lane * 12 + 2 * i] = st;
-            w->bins[lane * 12 + 2 * i + 1] = st + cb[2 * i];
-            st += cj[i];
-        }
-    }
-    __syncwarp();
-    for (int i = lane; i < ns; i += 32) {
-        const uint32_t k = w->akey[i];
-        const int bin = (int)(k >> 20);
-        if ((bin >> 1) > js) continue;
-        w->order[atomicAdd(&w->bins[bin], 1u)] = (uint16_t)i;    // arbitrary order inside a bin, fixed below
-    }
-    __syncwarp();
-    {
-        // order inside each (j, side) bin by (x, y): insertion sort by the owning lane (bins hold 0-2 entries on textured content)
-        uint32_t st = excl;
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-#pragma unroll
-            for (int sd = 0; sd < 2; sd++) {
-                const int j = lane * 6 + i;
-                const int b0 = (int)(sd ? st + cb[2 * i] : st), cnt = (int)cb[2 * i + sd];
-                if (j <= js && cnt > 1) {
-                    for (int a = 1; a < cnt; a++) {
-                        const uint16_t ia = w->order[b0 + a];
-                        const uint32_t ka = w->akey[ia];
-                        int p = a - 1;
-                        while (p >= 0 && w->akey[w->order[b0 + p]] > ka) { w->order[b0 + p + 1] = w->order[b0 + p]; p--; }
-                        w->order[b0 + p + 1] = ia;
-                    }
-                }
-            }
-            st += cj[i];
-        }
-    }
-    __syncwarp();
-    // SAD at integer displacement (fraction 0 => plane 0) for the kept candidates: 8 lanes per candidate, one row
-    // each, 8 rounds of loads in flight. Slots of the second visit of bucket s0 are copies.
-    const uint8_t *pl = S.planes;
-    const int r = lane & 7;
-    const uint2 cr = pick_row(rows, r);
-    const int nuniq = n2 - cnt0;          // distinct candidates: slots [0, cnt0) and [2*cnt0, n2)
-    for (int base = 0; base < nuniq; base += 4 * FH_S2_SADR) {
-        uint2 rr[FH_S2_SADR];
-        int idx[FH_S2_SADR];
-#pragma unroll
-        for (int u = 0; u < FH_S2_SADR; u++) {
-            const int m = base + u * 4 + (lane >> 3);
-            rr[u] = make_uint2(0, 0); idx[u] = -1;
-            if (m < nuniq) {
-                const int slot = m < cnt0 ? m : m + cnt0;
-                idx[u] = w->order[slot];
-                const uint32_t k = w->akey[idx[u]];
-                rr[u] = load_row8(pl, g.W, g.H, xP + (int)((k >> 10) & 1023) - 279, yP + (int)(k & 1023) - 279 + r);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < FH_S2_SADR; u++) {
-            int sad = idx[u] >= 0 ? sad8(cr, rr[u]) : 0;
-            sad += __shfl_xor_sync(0xffffffffu, sad, 1);
-            sad += __shfl_xor_sync(0xffffffffu, sad, 2);
-            sad += __shfl_xor_sync(0xffffffffu, sad, 4);
-            if (idx[u] >= 0 && r == 0) w->aval[idx[u]] |= (uint32_t)sad << 18;
-        }
-    }
-    __syncwarp();
-    uint2 *pool = S.s2pool + off;
-    for (int m = lane; m < nuniq; m += 32) {
-        const int slot = m < cnt0 ? m : m + cnt0, i = w->order[slot];
-        const uint32_t k = w->akey[i];
-        const int dx = (int)((k >> 10) & 1023) - 279, dy = (int)(k & 1023) - 279;
-        const uint2 v = make_uint2(((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16), w->aval[i]);
-        pool[slot] = v;
-        if (m < cnt0) pool[cnt0 + m] = v;
+        pa->s2_off = (uint32_t)part * S2_SLICE;
+        pa->n2 = fits ? (uint32_t)n2 : (S2_SLOW | (uint32_t)js);
     }
 }

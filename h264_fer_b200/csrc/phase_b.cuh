@@ -127,7 +127,6 @@ struct PBShared {
     __align__(16) MbSpec ms;             // phase-S P_Skip trials of the macroblock
     PartA pa[4];                         // phase-A products of the four partitions, fetched BEFORE the dependency wait
     S3Entry s3[4][FH_S3_MAX + 1];
-    uint2 pool[4][PB_POOL_PREF];
     uint32_t qx[16 * 61];                // qfeat.cuh step A: row sums of the stage-1 window (16 planes x 12 rows x 5 positions at WindowSize 32)
     uint16_t qrc[16 * 61];
     uint32_t my_ticket;
@@ -413,7 +412,6 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
         if (!prm.basic) {
             if (tid == 32) sh.pa[pi] = S.parta[mb * 4 + pi];
             for (int k = tid; k < FH_S3_MAX; k += PB_NT) sh.s3[pi][k] = S.s3[(size_t)(mb * 4 + pi) * FH_S3_MAX + k];
-            for (int k = tid; k < PB_POOL_PREF; k += PB_NT) sh.pool[pi][k] = __ldg(&S.s2pool[(size_t)(mb * 4 + pi) * 1024u + k]);
         } else if (tid == 0) {
             sh.pa[pi].n2 = 0; sh.pa[pi].n3 = 0; sh.pa[pi].s2_off = 0;
         }
@@ -604,18 +602,15 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
         uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;
         if (sa < qseg) wa = qf_load16(S.planes + (size_t)(warp * qpw + fa) * g.WH, W, H, x0, y0 + ra);
         if (sb < qseg) wb = qf_load16(S.planes + (size_t)(warp * qpw + fb) * g.WH, W, H, x0, y0 + rb);
-        // stage 2 (:470-507) keys while those loads fly: cost << 10 | arrival rank; SADs were measured in phase A
+        // stage 2 (:470-507) keys while those loads fly: cost << 32 | arrival key (the pool is unordered; phase A left no SADs)
         const bool slow2 = (pa.n2 & S2_SLOW) != 0;                     // candidate set too large for phase A: enumerated below
         const int n2 = slow2 ? 0 : (int)pa.n2;
-        const uint2 *pool = S.s2pool + pa.s2_off;
-        u64 t2 = KEY_NONE;               // this thread's best stage-2 (total, key) among candidates not yet rejected
+        const uint4 *pool = S.s2pool + pa.s2_off;
         for (int i = tid; i < n2; i += PB_NT) {
-            const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
+            const uint4 v = __ldg(&pool[i]);
             const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16);
-            const uint32_t cost = (uint32_t)(iabs_(dx - genx) + iabs_(dy - geny) + 4) * (v.y & 0x3ffffu);
-            const u64 key = ((u64)cost << 10) | (u64)i;
-            sh.keys2[i] = key;
-            if (cost < (uint32_t)FH_COST_EMPTY) t2 = min(t2, ((u64)((int)(v.y >> 18) + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
+            const uint32_t cost = (uint32_t)(iabs_(dx - genx) + iabs_(dy - geny) + 4) * v.y;
+            sh.keys2[i] = ((u64)cost << 32) | (u64)v.w;
         }
         // stage 3 (:508-520): phase-A list, already in list order
         if (tid >= 64 && tid - 64 < (int)pa.n3) {
@@ -663,24 +658,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
                 }
             }
         }
-        // stage 2, lazily: the block's best stage-2 candidate by (total, list order) is THE stage-2 contribution iff it is one of
-        // the 33 smallest keys. Its verification shares the barriers of the stage-1 selection: per-warp minima before the key
-        // barrier, count of the keys below it before the selection's first barrier, verdict after the selection.
-        if (n2 > 0) { const u64 wmin = warp_min_u64(t2); if (lane == 0) sh.sel_min[warp] = wmin; }
-        __syncthreads();                                               // keys1, keys2 and the stage-2 minima complete
-        u64 cand = KEY_NONE;
-        bool need_count = false;
-        if (n2 > 0) {
-            cand = min(min(sh.sel_min[0], sh.sel_min[1]), min(sh.sel_min[2], sh.sel_min[3]));
-            need_count = cand != KEY_NONE && n2 > FH_S3_MAX;            // n2 <= 33: every candidate is on the list
-            if (need_count) {
-                const u64 ckey = cand & ((1ull << 42) - 1);
-                int below = 0;
-                for (int i = tid; i < n2; i += PB_NT) below += sh.keys2[i] < ckey;
-                below = __reduce_add_sync(0xffffffffu, below);
-                if (lane == 0) sh.sel_cnt[warp] = below;
-            }
-        }
+        __syncthreads();                                               // keys1 and keys2 complete
         PB_SUB(14);
         const int K1 = block_select_smallest_u32(sh.keys1, n1, FH_S1_MAX, &sh.bs, sh.mem1, callno++);
         PB_SUB(15);
@@ -699,53 +677,25 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
                 rr[u] = load_row8(S.planes + (size_t)f * g.WH, W, H, clampi_(xP + dx, 0, W - 1), clampi_(yP + dy, 0, H - 1) + r);
             }
         }
-        // stage 2 verdict; on failure the owner rejects the candidate and the block retries (twice), then falls back to the exact selection
+        // stage 2 (:498-507): the 33 smallest keys are the list; their SADs are measured here (8 threads per member), and a member
+        // with cost below the "empty" mark competes with its list position as tie-break
         if (n2 > 0) {
-            bool settled = !need_count;
-            if (need_count) {
-                const int rank0 = sh.sel_cnt[0] + sh.sel_cnt[1] + sh.sel_cnt[2] + sh.sel_cnt[3];
-                settled = rank0 < FH_S3_MAX;
-            }
-            for (int attempt = 1; attempt < 3 && !settled; attempt++) {
-                if (t2 == cand) {
-                    // the owner rejects it and recomputes its local best without it
-                    const int rej = (int)(cand & 1023);
-                    t2 = KEY_NONE;
-                    for (int i = tid; i < n2; i += PB_NT) {
-                        const u64 key = sh.keys2[i];
-                        if (i == rej || (key >> 10) >= (u64)FH_COST_EMPTY) continue;
-                        const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
-                        const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16);
-                        const u64 fk = ((u64)((int)(v.y >> 18) + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key;
-                        if (fk > cand) t2 = min(t2, fk);       // candidates rejected earlier compare below `cand`
-                    }
+            const int K2 = block_select_smallest(n2, FH_S3_MAX, [&](int i) -> u64 { return sh.keys2[i]; }, &sh.bs, sh.mem2, callno++);
+            for (int m0 = 0; m0 < K2; m0 += PB_NT / 8) {
+                const int m = m0 + (tid >> 3);
+                int sad = 0, dx = 0, dy = 0;
+                bool live = false;
+                if (m < K2) {
+                    const int i = (int)sh.mem2[m];
+                    const uint4 v = __ldg(&pool[i]);
+                    dx = (int16_t)(v.x & 0xffff); dy = (int16_t)(v.x >> 16);
+                    live = (uint32_t)(sh.keys2[i] >> 32) < (uint32_t)FH_COST_EMPTY;
+                    sad = sad8(cr, load_row8(S.planes, W, H, xP + dx, yP + dy + r));
                 }
-                __syncthreads();                               // everybody has read sel_min / sel_cnt of the previous attempt
-                const u64 wmin = warp_min_u64(t2);
-                if (lane == 0) sh.sel_min[warp] = wmin;
-                __syncthreads();
-                cand = min(min(sh.sel_min[0], sh.sel_min[1]), min(sh.sel_min[2], sh.sel_min[3]));
-                if (cand == KEY_NONE) { settled = true; break; }
-                const u64 ckey = cand & ((1ull << 42) - 1);
-                int below = 0;
-                for (int i = tid; i < n2; i += PB_NT) below += sh.keys2[i] < ckey;
-                below = __reduce_add_sync(0xffffffffu, below);
-                if (lane == 0) sh.sel_cnt[warp] = below;
-                __syncthreads();
-                settled = sh.sel_cnt[0] + sh.sel_cnt[1] + sh.sel_cnt[2] + sh.sel_cnt[3] < FH_S3_MAX;
-            }
-            if (settled) { if (tid == 0) mine = min(mine, cand); }
-            else {
-                const int K2 = block_select_smallest(n2, FH_S3_MAX, [&](int i) -> u64 { return sh.keys2[i]; }, &sh.bs, sh.mem2, callno++);
-                if (tid < K2) {
-                    const int i = (int)sh.mem2[tid];
-                    const u64 key = sh.keys2[i];
-                    if ((key >> 10) < (u64)FH_COST_EMPTY) {
-                        const uint2 v = i < PB_POOL_PREF ? sh.pool[pi][i] : __ldg(&pool[i]);
-                        const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16), sad = (int)(v.y >> 18);
-                        mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | key);
-                    }
-                }
+                sad += __shfl_xor_sync(0xffffffffu, sad, 1);
+                sad += __shfl_xor_sync(0xffffffffu, sad, 2);
+                sad += __shfl_xor_sync(0xffffffffu, sad, 4);
+                if (live && r == 0) mine = min(mine, ((u64)(sad + mv_cost(dx << 2, dy << 2, mvpx, mvpy)) << 44) | (1ull << 42) | (u64)m);
             }
         }
         // stage 1 SADs
@@ -776,7 +726,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
                 const int wi = (int)(b & 1023);
                 if (slow2) { const uint32_t pos = sh.slow_pos[wi]; bx = ((int)(pos & 0xffff) - 512) << 2; by = ((int)(pos >> 16) - 512) << 2; }
                 else {
-                    const uint2 v = wi < PB_POOL_PREF ? sh.pool[pi][wi] : __ldg(&S.s2pool[pa.s2_off + (uint32_t)wi]);
+                    const uint4 v = __ldg(&S.s2pool[pa.s2_off + (uint32_t)sh.mem2[wi]]);
                     bx = ((int)(int16_t)(v.x & 0xffff)) << 2; by = ((int)(int16_t)(v.x >> 16)) << 2;
                 }
             } else {

@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seq
         const int k1 = a[q & 7] + a[(q + 1) & 7] + a[(q + 2) & 7] + a[(q + 3) & 7];
         const int k3 = a[q & 7] + a[(q + 1) & 7] + a[(q + 4) & 7] + a[(q + 5) & 7];
         // K0: 8x8 (:137) | K1: rows 0-3 (:136) ; K2: columns 0-3 (:135) | K3: rows 0,1,4,5 (:133-134) ; K4: columns 0,1,4,5 (:131-132)
-        if (y < H) K[(size_t)y * W + x] = feat_record(k0, k1, k2, k3, k4);
+        if (y < H) {
+            K[(size_t)y * W + x] = feat_record(k0, k1, k2, k3, k4);
+            if (!out) S.k0p[(size_t)y * W + x] = (uint16_t)k0;
+        }
         if (q + 1 < FT_H / 4) {
             const int na = r8[rs + q + 8][tx], n4 = r4[rs + q + 8][tx], nc = rc[rs + q + 8][tx];
             k0 += na - a[q & 7]; k2 += n4 - q4[q & 7]; k4 += nc - qc[q & 7];

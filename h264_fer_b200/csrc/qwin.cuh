@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include "common.cuh"
 #include "qfeat.cuh"
+#include "topk.cuh"
 
 #define QW_ROWB 32                          // bytes per staged row
 #define QW_MAX_ROWS 17                      // R + 1 box rows at WindowSize 64 (R = 8 + 2*4)
@@ -79,28 +80,35 @@ __device__ __forceinline__ void qwin_wait(bool tma, uint64_t *bar, uint32_t &pha
     if (tma) { mbar_wait(bar, phase); phase ^= 1u; }
 }
 
-// Costs of the w1 x w1 x 16 candidates of the window centred at (xP + Gx, yP + Gy): cost[((cx*w1) + cy)*16 + f] =
-// (|cx-g1| + |cy-g1| + 4) * feature distance (:267-276), COST_NONE where the block origin leaves the picture (:265).
+// A staged window as one partition sees it: p = byte 0 of its first row in plane 0, rowb / planeb = row / plane stride in bytes,
+// off = byte offset of the partition's first pixel column inside a row.
+struct QWinView { const uint8_t *p; int rowb, planeb, off; };
+
+// Costs of the w1 x w1 x 16 candidates of the window centred at (xP + Gx, yP + Gy): candidate ((cx*w1) + cy)*16 + f has cost
+// (|cx-g1| + |cy-g1| + 4) * feature distance (:267-276); none where the block origin leaves the picture (:265). Every candidate
+// is handed to emit(cost, index) — called by all 32 lanes together, cost QW_COST_NONE for "nothing".
 // A lane owns (plane f, column cx): horizontal sums of its 8 pixels for every row (all 8 | columns 0-3 packed in one word,
 // columns {0,1,4,5} in another), pair sums down the column, then the five box sums of each of its w1 positions by one or two
 // adds each: rows 0-3 = Q[cy], all = Q[cy] + Q[cy+4], rows {0,1,4,5} = P[cy] + P[cy+4] with P[j] = row j + row j+1, Q[j] = P[j] + P[j+2].
-// m1 <= m2 collect the lane's two smallest costs (selection bound of warp_select_costs). W1 = w1 (template: the column fits registers).
 #define QW_COST_NONE 0xffffffffu
-template <int W1>
-__device__ __forceinline__ void qwin_costs(const Geo &g, const QWinGeo &q, const uint8_t *win, int off, int xP, int yP, int Gx, int Gy, const FeatQ &fq,
-                                           uint32_t *cost, uint32_t &m1, uint32_t &m2)
+template <int W1, typename Emit>
+__device__ __forceinline__ void qwin_costs(const Geo &g, const QWinView &v, int xP, int yP, int Gx, int Gy, const FeatQ &fq, Emit emit)
 {
     constexpr int R = 8 + W1 - 1, G1 = (W1 - 1) / 2;
     const int lane = threadIdx.x & 31;
     const int x0 = xP + Gx - G1, y0 = yP + Gy - G1;
-    for (int u = lane; u < 16 * W1; u += 32) {
+    const int rw = v.rowb >> 2;
+#pragma unroll 1
+    for (int u0 = 0; u0 < 16 * W1; u0 += 32) {
+        const bool active = u0 + lane < 16 * W1;
+        const int u = active ? u0 + lane : 0;
         const int f = u / W1, cx = u - f * W1;
-        const uint32_t *wrow = (const uint32_t *)(win + (size_t)f * q.rows * QW_ROWB) + ((cx + off) >> 2);
-        const uint32_t sh = (uint32_t)((cx + off) & 3) * 8;
+        const uint32_t *wrow = (const uint32_t *)(v.p + (size_t)f * v.planeb) + ((cx + v.off) >> 2);
+        const uint32_t sh = (uint32_t)((cx + v.off) & 3) * 8;
         uint32_t A[R], B[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const uint32_t w0 = wrow[r * (QW_ROWB / 4)], w1 = wrow[r * (QW_ROWB / 4) + 1], w2 = wrow[r * (QW_ROWB / 4) + 2];
+            const uint32_t w0 = wrow[r * rw], w1 = wrow[r * rw + 1], w2 = wrow[r * rw + 2];
             const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
             const uint32_t s4 = __vsadu4(lo, 0u), s8 = __vsadu4(hi, 0u) + s4;
             A[r] = s8 | (s4 << 16);
@@ -112,7 +120,7 @@ __device__ __forceinline__ void qwin_costs(const Geo &g, const QWinGeo &q, const
 #pragma unroll
         for (int r = 0; r < R - 3; r++) { Q[r] = P[r] + P[r + 2]; QB[r] = PB[r] + PB[r + 2]; }
         const int rx = x0 + cx;
-        const bool xok = rx >= 0 && rx < g.W;
+        const bool xok = active && rx >= 0 && rx < g.W;
         const int adx = iabs_(cx - G1) + 4;
 #pragma unroll
         for (int cy = 0; cy < W1; cy++) {
@@ -122,17 +130,69 @@ __device__ __forceinline__ void qwin_costs(const Geo &g, const QWinGeo &q, const
             const int ry = y0 + cy;
             uint32_t cst = QW_COST_NONE;
             if (xok && ry >= 0 && ry < g.H) cst = (uint32_t)((adx + iabs_(cy - G1)) * feat_of(fq, feat_record(k0, k1, k2, k3, k4)));
-            cost[(cx * W1 + cy) * 16 + f] = cst;
-            m2 = min(m2, max(m1, cst)); m1 = min(m1, cst);
+            emit(cst, (uint32_t)((cx * W1 + cy) * 16 + f));
         }
+    }
+}
+template <typename Emit>
+__device__ __forceinline__ void qwin_costs_w(int w1, const Geo &g, const QWinView &v, int xP, int yP, int Gx, int Gy, const FeatQ &fq, Emit emit)
+{
+    switch (w1) {
+    case 1: qwin_costs<1>(g, v, xP, yP, Gx, Gy, fq, emit); break;
+    case 3: qwin_costs<3>(g, v, xP, yP, Gx, Gy, fq, emit); break;
+    case 5: qwin_costs<5>(g, v, xP, yP, Gx, Gy, fq, emit); break;
+    case 7: qwin_costs<7>(g, v, xP, yP, Gx, Gy, fq, emit); break;
+    default: qwin_costs<9>(g, v, xP, yP, Gx, Gy, fq, emit); break;
     }
 }
 
 // One row (8 pixels) of the candidate block (plane f, window column cx, window row wr) from the staged window.
-__device__ __forceinline__ uint2 qwin_row8(const QWinGeo &q, const uint8_t *win, int off, int f, int cx, int wr)
+__device__ __forceinline__ uint2 qwin_row8(const QWinView &v, int f, int cx, int wr)
 {
-    const uint32_t *w = (const uint32_t *)(win + (size_t)(f * q.rows + wr) * QW_ROWB) + ((cx + off) >> 2);
-    const uint32_t sh = (uint32_t)((cx + off) & 3) * 8;
+    const uint32_t *w = (const uint32_t *)(v.p + (size_t)f * v.planeb + (size_t)wr * v.rowb) + ((cx + v.off) >> 2);
+    const uint32_t sh = (uint32_t)((cx + v.off) & 3) * 8;
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+
+// The same candidates with selection (topk.cuh). Small windows (w1 <= 5: at most 15 candidates per lane): every cost is tracked
+// and parked in `stage` (a [15][32] word array per warp, one wavefront per access); the bound is tightened ONCE over all of them
+// and only the candidates at or below it are appended to the selection buffer, with arrival index base + ((cx*w1) + cy)*16 + f.
+// Larger windows stream through tk_offer. The loops stay rolled: the unrolled window code is already 6 KB of instructions.
+#define QW_STAGE_WORDS (15 * 32)
+template <int W1>
+__device__ __forceinline__ void qwin_select(const Geo &g, const QWinView &v, int xP, int yP, int Gx, int Gy, const FeatQ &fq, TopKBuf *buf, TopK &tk,
+                                            uint32_t *stage, uint32_t base)
+{
+    const int lane = threadIdx.x & 31;
+    if constexpr (W1 <= 5) {
+        constexpr int NP = (16 * W1 + 31) / 32;
+        int n = 0;
+        qwin_costs<W1>(g, v, xP, yP, Gx, Gy, fq, [&](uint32_t cst, uint32_t) { stage[n * 32 + lane] = cst; n++; tk_track(tk, cst); });
+        tk_tighten_exact_minima(tk);
+        __syncwarp();
+#pragma unroll 1
+        for (int p = 0; p < NP; p++) {
+            const int u = p * 32 + lane, f = u / W1, cx = u - f * W1;
+            const uint32_t ib = base + (uint32_t)(cx * W1 * 16 + f);
+#pragma unroll 1
+            for (int cy = 0; cy < W1; cy++) tk_append(buf, tk, stage[(p * W1 + cy) * 32 + lane], ib + (uint32_t)(cy * 16));
+        }
+    } else {
+        qwin_costs<W1>(g, v, xP, yP, Gx, Gy, fq, [&](uint32_t cst, uint32_t idx) { tk_offer(buf, tk, cst, base + idx); });
+        tk_tighten_exact_minima(tk);
+        tk_filter(buf, tk, tk.bound);
+    }
+}
+template <typename = void>
+__device__ __forceinline__ void qwin_select_w(int w1, const Geo &g, const QWinView &v, int xP, int yP, int Gx, int Gy, const FeatQ &fq, TopKBuf *buf, TopK &tk,
+                                              uint32_t *stage, uint32_t base)
+{
+    switch (w1) {
+    case 1: qwin_select<1>(g, v, xP, yP, Gx, Gy, fq, buf, tk, stage, base); break;
+    case 3: qwin_select<3>(g, v, xP, yP, Gx, Gy, fq, buf, tk, stage, base); break;
+    case 5: qwin_select<5>(g, v, xP, yP, Gx, Gy, fq, buf, tk, stage, base); break;
+    case 7: qwin_select<7>(g, v, xP, yP, Gx, Gy, fq, buf, tk, stage, base); break;
+    default: qwin_select<9>(g, v, xP, yP, Gx, Gy, fq, buf, tk, stage, base); break;
+    }
 }

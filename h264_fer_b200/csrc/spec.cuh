@@ -22,6 +22,7 @@
 #include "qfeat.cuh"
 #include "phase_a.cuh"
 #include "qwin.cuh"
+#include "topk.cuh"
 
 #define SPEC_NF 7
 #define SPEC_INVALID 0xffu
@@ -44,7 +45,8 @@ __device__ __forceinline__ int cell_max_(int a) { return max(iabs_(a), iabs_(a -
 
 struct __align__(128) SpecWarp {
     uint64_t bar;                            // mbarrier of the TMA-staged pixel window (qwin.cuh)
-    WarpSelScratch ws;                       // selection scratch
+    TopKBuf tk;                              // selection of the 17 stage-1 candidates (topk.cuh)
+    uint32_t stage[QW_STAGE_WORDS];          // the window's costs until the bound is known (qwin_select)
     uint16_t members[FH_S1_MAX + 3];
     uint16_t msad[FH_S1_MAX + 3];
     S3Entry s3[FH_S3_MAX + 1];
@@ -66,7 +68,7 @@ __device__ __forceinline__ void pf_emit(bool have, int mvx, int mvy, int sad, in
 // The finalists of one partition for one guessed gen = (Gx, Gy) into out->f[slot]. Warp-uniform call.
 __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const fh264_params &prm, int part, int xP, int yP, const uint2 (&rows)[8],
                                           const FeatQ &fq, int n3, uint32_t n2w, uint32_t s2_off, int Gx, int Gy, int slot,
-                                          SpecWarp *sw, uint8_t *win, uint32_t *cost, PartSpec *out, const CUtensorMap *tmap, uint32_t &phase)
+                                          SpecWarp *sw, uint8_t *win, PartSpec *out, const CUtensorMap *tmap, uint32_t &phase)
 {
     const int lane = threadIdx.x & 31, W = g.W, H = g.H;
     const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16;
@@ -95,54 +97,60 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
         }
         pf_emit(have, mvx, mvy, sad, (2 << 14) | i, sw, npf);
     }
-    // ---- stage 2 (:470-507): candidates of phase A in arrival order with feature distance and SAD. List membership = one of
-    //      the 33 smallest keys (cost << 10 | arrival); only candidates that can still win have their rank counted.
+    // ---- stage 2 (:470-507): candidates of phase A with feature distance, a lower bound of the SAD and the arrival key. List
+    //      membership = one of the 33 smallest keys (cost, arrival). Only candidates whose lower bound leaves them a chance have
+    //      their rank counted, and only those on the list their SAD measured (8 lanes, one row each).
     if (usable) {
         const int n2 = (int)n2w;
-        const uint2 *__restrict__ pool = S.s2pool + s2_off;
+        const uint4 *__restrict__ pool = S.s2pool + s2_off;
+        const uint2 cr8 = pick_row(rows, lane & 7);
         for (int i0 = 0; i0 < n2; i0 += 32) {
             const int i = i0 + lane;
-            bool pot = false; int dx = 0, dy = 0, sad = 0; uint32_t cst = 0;
+            bool pot = false; int dx = 0, dy = 0; uint32_t cst = 0, ak = 0;
             if (i < n2) {
-                const uint2 v = __ldg(&pool[i]);
-                dx = (int16_t)(v.x & 0xffff); dy = (int16_t)(v.x >> 16); sad = (int)(v.y >> 18);
-                cst = (uint32_t)(iabs_(dx - Gx) + iabs_(dy - Gy) + 4) * (v.y & 0x3ffffu);
-                pot = cst < (uint32_t)FH_COST_EMPTY && sad + cell_min_(4 * dx - cxq) + cell_min_(4 * dy - cyq) <= U;
+                const uint4 v = __ldg(&pool[i]);
+                dx = (int16_t)(v.x & 0xffff); dy = (int16_t)(v.x >> 16); ak = v.w;
+                cst = (uint32_t)(iabs_(dx - Gx) + iabs_(dy - Gy) + 4) * v.y;
+                // (the second listing of a bucket-s0 entry has the same vector and a later arrival: only the first can win)
+                pot = cst < (uint32_t)FH_COST_EMPTY && !((ak >> 21) == 0u && (ak & (1u << 20))) &&
+                      (int)v.z + cell_min_(4 * dx - cxq) + cell_min_(4 * dy - cyq) <= U;
             }
             unsigned pm = __ballot_sync(0xffffffffu, pot);
-            bool member = false; int myrank = 0;
             while (pm) {
                 const int src = __ffs(pm) - 1;
                 pm &= pm - 1;
-                const uint32_t ci = __shfl_sync(0xffffffffu, cst, src);
-                const int ii = i0 + src;
+                const uint32_t ci = __shfl_sync(0xffffffffu, cst, src), ai = __shfl_sync(0xffffffffu, ak, src);
                 int c = 0;
                 for (int j = lane; j < n2; j += 32) {
-                    const uint2 w = __ldg(&pool[j]);
+                    const uint4 w = __ldg(&pool[j]);
                     const int jx = (int16_t)(w.x & 0xffff), jy = (int16_t)(w.x >> 16);
-                    const uint32_t cj = (uint32_t)(iabs_(jx - Gx) + iabs_(jy - Gy) + 4) * (w.y & 0x3ffffu);
-                    c += (cj < ci) || (cj == ci && j < ii);
+                    const uint32_t cj = (uint32_t)(iabs_(jx - Gx) + iabs_(jy - Gy) + 4) * w.y;
+                    c += (cj < ci) || (cj == ci && w.w < ai);
                 }
                 c = __reduce_add_sync(0xffffffffu, c);
-                if (lane == src) { member = c < FH_S3_MAX; myrank = c; }
+                bool have = false; int sad = 0;
+                const int sx = __shfl_sync(0xffffffffu, dx, src), sy = __shfl_sync(0xffffffffu, dy, src);
+                if (c < FH_S3_MAX) {                                   // on the list: measure it
+                    sad = lane < 8 ? sad8(cr8, load_row8(S.planes, W, H, xP + sx, yP + sy + lane)) : 0;
+                    sad += __shfl_xor_sync(0xffffffffu, sad, 1);
+                    sad += __shfl_xor_sync(0xffffffffu, sad, 2);
+                    sad += __shfl_xor_sync(0xffffffffu, sad, 4);
+                    sad = __shfl_sync(0xffffffffu, sad, 0);
+                    have = lane == 0 && sad + cell_min_(4 * sx - cxq) + cell_min_(4 * sy - cyq) <= U;
+                }
+                pf_emit(have, sx * 4, sy * 4, sad, (1 << 14) | c, sw, npf);
             }
-            pf_emit(member, dx * 4, dy * 4, sad, (1 << 14) | myrank, sw, npf);
         }
     }
     // ---- stage 1 (:458-469): feature window around the guess, 17 best by (cost, arrival), their SADs
     {
-        uint32_t m1 = COST_INVALID, m2 = COST_INVALID;
         qwin_wait(tma, &sw->bar, phase);
-        switch (w1) {
-        case 1: qwin_costs<1>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
-        case 3: qwin_costs<3>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
-        case 5: qwin_costs<5>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
-        case 7: qwin_costs<7>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
-        default: qwin_costs<9>(g, qg, win, woff, xP, yP, Gx, Gy, fq, cost, m1, m2); break;
-        }
-        __syncwarp();
+        const QWinView qv = { win, QW_ROWB, qg.rows * QW_ROWB, woff };
         const int nvalid = max(0, min(W - 1, xP + Gx + g1) - max(0, xP + Gx - g1) + 1) * max(0, min(H - 1, yP + Gy + g1) - max(0, yP + Gy - g1) + 1) * 16;
-        const int nm = warp_select_costs(cost, n1, FH_S1_MAX, nvalid, m1, m2, &sw->ws, sw->members);
+        TopK tk;
+        tk_init(tk, min(FH_S1_MAX, nvalid));
+        qwin_select_w(w1, g, qv, xP, yP, Gx, Gy, fq, &sw->tk, tk, sw->stage, 0u);
+        const int nm = tk_finish(&sw->tk, tk, nvalid, sw->members, true);
         const int r = lane & 7;
         const uint2 cr = pick_row(rows, r);
         for (int base = 0; base < nm; base += 4 * 5) {
@@ -154,7 +162,7 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
                 if (m < nm) {
                     // the candidate's block lies inside the staged window (same clamping as satdLuma8x8MVs for an origin inside the picture)
                     const int i = (int)sw->members[m], f = i & 15, pos = i >> 4, cx = udiv_by(pos, i1), cy = pos - cx * w1;
-                    rr[u] = qwin_row8(qg, win, woff, f, cx, cy + r);
+                    rr[u] = qwin_row8(qv, f, cx, cy + r);
                 }
             }
 #pragma unroll
@@ -256,16 +264,15 @@ __device__ __forceinline__ void proxy_predictor(const SeqDev &S, const Geo &g, i
 // One warp per partition, four per CTA (one macroblock). Guesses of gen = mvp >> 2: the predictor rule applied to the
 // neighbours' proxies (98.5 % right on the bench content), then the partition's own proxy (together 99.7 %); without stage-3
 // lists (BasicInterEncoding) the gen phase B used for this partition in the previous P picture, else zero.
-__global__ void __launch_bounds__(128, 4) k_spec(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int npad1, int use_prev,
+__global__ void __launch_bounds__(128, 5) k_spec(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int use_prev,
                                                  const CUtensorMap *__restrict__ tmaps)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // dynamic shared memory: 4 windows (128-byte aligned, qwin_bytes each) | 4 SpecWarp | 4 cost arrays
+    // dynamic shared memory: 4 windows (128-byte aligned, qwin_bytes each) | 4 SpecWarp
     const int wbytes = qwin_bytes(prm.window / 16);
     uint8_t *win = smem_raw + (size_t)warp * wbytes;
     SpecWarp *sw = (SpecWarp *)(smem_raw + 4 * (size_t)wbytes) + warp;
-    uint32_t *cost = (uint32_t *)(smem_raw + 4 * (size_t)wbytes + 4 * sizeof(SpecWarp)) + (size_t)warp * npad1;
     const SeqDev &S = seqs[seq0 + blockIdx.y];
     const CUtensorMap *tmap = tmaps ? tmaps + seq0 + blockIdx.y : nullptr;
     uint32_t phase = 0;
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(128, 4) k_spec(const SeqDev *__restrict__ seqs
     }
     if (ng == 0) ng = 1;                                   // no list and no history: guess gen = (0, 0)
     for (int slot = 0; slot < ng; slot++)
-        spec_slot(S, g, prm, part, xP, yP, rows, fq, n3, n2w, s2_off, slot ? g1x : g0x, slot ? g1y : g0y, slot, sw, win, cost, out, tmap, phase);
+        spec_slot(S, g, prm, part, xP, yP, rows, fq, n3, n2w, s2_off, slot ? g1x : g0x, slot ? g1y : g0y, slot, sw, win, out, tmap, phase);
     if (ng == 1 && lane == 0) { out->gx[1] = SPEC_NOGUESS; out->gy[1] = SPEC_NOGUESS; out->nf[1] = SPEC_INVALID; }
 }
 

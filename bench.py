@@ -33,9 +33,17 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT = 1920, 1080            # input size; coded 1920x1072 after the reference's crop (fileIO.cpp:242-243)
 QP, WINDOW, MAXDIFF = 28, 32, 3
-CLIP_LEN = 6                          # distinct pictures per sequence, played ping-pong so motion stays continuous
+CLIP_LEN = 6                          # distinct pictures per sequence (set per run: warm-up + steps + 3, at most CLIP_MAX); past the end the clip plays back
+CLIP_MAX = 40
 ALG_BYTES_PER_MB = 1984               # 384 src + 384 ref + 384 recon + 768 levels + 64 metadata
 ALG_INTOPS_PER_MB = 0.43e6
+LAUNCHES_PER_STEP = 16                # own kernels per step and group: scene SAD 3 + swap 1, begin, stage 3, stage 2, phase S 2, B, C, dpb swap, phase R 4
+# The same 0.43 M lane-ops per macroblock split over the kernels that do them (SURVEY.md §8d's per-stage counts; 4 partitions
+# per macroblock, 40 ops per feature-cost evaluation, 32 packed-byte ops per 8x8 SAD):
+#   stage 3: 1,475 evaluations + 33 SADs; stage 1 (phase S): 400 evaluations + 17 SADs; stage 2: ~100 evaluations + 32 SADs;
+#   phase C: two motion compensations + 48 4x4 transforms with quant/dequant; phase R: 16-plane interpolation + box sums.
+ALG_INTOPS_BY_KERNEL = {"k_stage3": 4 * (1475 * 40 + 33 * 32), "k_spec": 4 * (400 * 40 + 17 * 32), "k_stage2": 4 * (100 * 40 + 32 * 32),
+                        "k_phase_b": 1000, "k_phase_c": 24000, "k_interp": 110 * 256, "k_features": 190 * 256, "k_tile_index": 0}
 
 
 def ncu_traffic(dom, seqs_per_launch):
@@ -66,15 +74,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def measured_int_peak():
-    """Sustained integer-pipe rate measured on a B200 of this pool by profiles/tools/int_peak.cu (profiles/r01_int_peak.json):
-    the instructions the ME kernels are made of (VABSDIFF4.U8.ACC, VIADDMNMX[.S16x2], IMAD, LOP3, SHF) issue at 64 lanes per SM
-    per clock; only plain adds (VIADD / IADD3) have the second 64 lanes. Returns T lane-ops/s of that 64-lane pipe, or None."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_int_peak.json")))
-        return float(min(d["imad (1 instr)"], d["viaddmnmx (1 instr)"], d["viaddmnmx.s16x2 (1 instr)"]))
-    except Exception:
-        return None
+def measured_int_peak(device):
+    """Sustained integer-pipe rate of THIS GPU, measured now by the library's micro-benchmark (csrc/intpeak.cuh: 2048 threads
+    per SM, 8 independent chains, 128 statements per iteration): the instructions the ME kernels are made of (VABSDIFF4.U8.ACC,
+    VIADDMNMX[.S16x2], IMAD) issue at 64 lanes per SM per clock; only plain adds have the second 64 lanes. Returns
+    (T lane-ops/s of that 64-lane pipe, the per-instruction figures)."""
+    from h264_fer_b200 import native
+    d = native.measure_int_peak(device)
+    return float(min(d["imad"], d["viaddmnmx"], d["viaddmnmx_s16x2"])), d
 
 
 class ClockSampler:
@@ -125,24 +132,34 @@ class ClockSampler:
         return out
 
 
+def set_clip_len(args):
+    global CLIP_LEN
+    CLIP_LEN = max(6, min(CLIP_MAX, max(args.warmup, 3) + args.steps + 3))
+
+
 def pingpong(t, n):
-    """0,1,..,n-1,n-2,..,1,0,1,.. : consecutive pictures always differ by exactly one pan step."""
+    """0,1,..,n-1,n-2,..,1,0,1,.. : consecutive pictures always differ by exactly one pan step. (The clip is made long enough
+    for warm-up + steps, so a default run only ever plays forward.)"""
     period = 2 * (n - 1)
     k = t % period
     return k if k < n else period - k
 
 
-def make_clips(nseq, first_seed):
+def make_clips(nseq, first_seed, length=None):
+    from concurrent.futures import ThreadPoolExecutor
     from h264_fer_b200 import synth
-    clips = []
-    for i in range(nseq):
+    n = CLIP_LEN if length is None else length
+
+    def one(i):
         c = synth.SynthClip(WIDTH, HEIGHT, first_seed + i)
         frames = []
-        for t in range(CLIP_LEN):
+        for t in range(n):
             y, cb, cr = c.frame(t)
             frames.append((synth.crop16(y), synth.crop16(cb, chroma=True), synth.crop16(cr, chroma=True)))
-        clips.append(frames)
-    return clips
+        return frames
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, nseq))) as ex:
+        return list(ex.map(one, range(nseq)))
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -222,7 +239,8 @@ def reference_arm(args):
 def workload_config(args, nseq_total):
     return {"workload": "BASELINE.json config 5 sharding: %d independent synthetic 1080p sequences per GPU (%d total), coded 1920x1072, "
                         "IPPP, 1 step = 1 P picture of every sequence" % (args.seqs, nseq_total),
-            "qp": QP, "window": WINDOW, "maxdiff_set": MAXDIFF, "basic": 0, "seqs_per_gpu": args.seqs, "groups_per_gpu": getattr(args, "groups", 1), "clip": "%d-picture ping-pong" % CLIP_LEN,
+            "qp": QP, "window": WINDOW, "maxdiff_set": MAXDIFF, "basic": 0, "seqs_per_gpu": args.seqs, "groups_per_gpu": getattr(args, "groups", 1),
+            "clip": "%d distinct pictures per sequence played forward (pan 2x1 px per picture, moving square, noise); every timed region starts at picture 1" % CLIP_LEN,
             "first_picture": "source picture 0 uploaded as the reconstruction (I pictures are host work, out of scope)",
             "l2": "per-step working set (>330 MB of reference planes/features per sequence) exceeds the 126 MB L2; no explicit flush"}
 
@@ -242,7 +260,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cavlc", action="store_true", help="skip the device-CAVLC line item (SURVEY.md §8(f) rank 1)")
     ap.add_argument("--no-intra", action="store_true", help="skip the device I-picture line item (SURVEY.md §8(f) rank 2)")
+    ap.add_argument("--no-bands", action="store_true", help="at N > 1: skip the MB-row band measurement that follows the replica measurement")
     args = ap.parse_args()
+    set_clip_len(args)
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -259,14 +279,15 @@ def main():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (the image prints the NCCL version banner)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))       # (NCCL may print its banner; the JSON line is the LAST line)
     if args.mode == "bands":
         return band_mode(args, rank, world, local)
     B, K, Wu = args.seqs, args.steps, max(args.warmup, 3)
     G = max(1, min(args.groups, B))                      # sequence groups: one session + stream + host thread each
     my_seqs = sharding.sequences_for_rank(B * world, rank, world)       # global sequence ids of this GPU (seed = 100 + id)
-    clips = [make_clips(1, 100 + sid)[0] for sid in my_seqs]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        clips = list(ex.map(lambda sid: make_clips(1, 100 + sid)[0], my_seqs))
     H = clips[0][0][0].shape[0]
     nmb = (WIDTH // 16) * (H // 16)
     ysz, csz = WIDTH * H, WIDTH * H // 4
@@ -396,7 +417,7 @@ def main():
 
     ms_dev, clocks = timed(host=False)
     ms_e2e, clocks_e2e = timed(host=True)
-    idr_decisions = sum(gr.idr for gr in groups)
+    idr_decisions = sum(sum(v) for v in sharding.gather_counts([gr.idr for gr in groups]))      # scene-change IDR decisions of all ranks
 
     # device CAVLC line item: the same end-to-end step, but what comes back per picture is the coded
     # slice data + 32 B/MB of side information instead of the 832-byte records. Reported beside the headline, not in it.
@@ -474,16 +495,28 @@ def main():
     counts = [g0.s.mode_counts(0)]
     Bk = g0.n                                             # pictures per kernel launch in the instrumented run
 
+    # BASELINE config 4 at N > 1: ONE 1080p sequence split into MB-row bands over the GPUs of the node (strong scaling), measured
+    # after the replica measurement so that the driver's scaling record carries both partitions the north star names.
+    for gr in groups:
+        gr.s.close()
+    groups = []
+    band = None
+    if not args.no_bands:
+        band = band_measure(args, rank, world, local)          # N = 1: the single-sequence latency the band split is measured against
+
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()
         frames_per_step = B * world
         value = frames_per_step * K / (ms_dev / 1000.0)
         e2e_value = frames_per_step * K / (ms_e2e / 1000.0)
-        kernels = {"k_stage3": tm["k_stage3_ms"], "k_stage2": tm["k_stage2_ms"], "k_phase_b": tm["phase_b_ms"], "k_phase_c": tm["phase_c_ms"],
-                   "k_interp": tm["k_interp_ms"], "k_features": tm["k_features_ms"], "k_tile_index": tm["k_tile_index_ms"]}
+        kernels = {"k_stage3": tm["k_stage3_ms"], "k_stage2": tm["k_stage2_ms"], "k_spec": tm["k_spec_ms"], "k_phase_b": tm["phase_b_ms"],
+                   "k_phase_c": tm["phase_c_ms"], "k_interp": tm["k_interp_ms"], "k_features": tm["k_features_ms"], "k_tile_index": tm["k_tile_index_ms"]}
         dom = max(kernels, key=kernels.get)
         alg_bytes = ALG_BYTES_PER_MB * nmb * Bk           # one launch processes the group's pictures
         achieved = alg_bytes / (kernels[dom] / 1000.0) / 1e9
+        ipk, ipk_detail = measured_int_peak(local)        # T lane-ops/s of the 64-lane integer pipe, measured on this GPU in this run
+        dom_ops = ALG_INTOPS_BY_KERNEL[dom] * nmb * Bk    # algorithmic lane-ops of one launch of the dominant kernel
+        dom_tops = dom_ops / (kernels[dom] / 1000.0) / 1e12
         # phase C alone is the HBM-bound kernel of the path: report it too
         c_achieved = alg_bytes / (tm["phase_c_ms"] / 1000.0) / 1e9
         int_ops = ALG_INTOPS_PER_MB * nmb * B * world * K          # whole timed job
@@ -496,51 +529,70 @@ def main():
             "macroblocks_per_s": value * nmb,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * (ysz + 2 * csz), "d2h_bytes_per_step": B * nmb * 832 + B * 8,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": 13 * K * G,
+            "gpu_launches": LAUNCHES_PER_STEP * K * G,
             "clocks": clocks, "clocks_e2e": clocks_e2e,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "note": "algorithmic bytes = 1984 B/MB x %d MB x %d pictures per launch / live CUDA-event duration of the dominant kernel "
-                                 "(one sequence group running alone); the ME kernels are integer-pipe bound, see int_roofline" % (nmb, Bk)},
+            "roofline": {"bound": "int", "kernel": dom, "achieved": dom_tops, "peak": ipk, "unit": "T int-lane-op/s", "frac": dom_tops / ipk,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": "measured in this run on this GPU (fh264_measure_int_peak: IMAD / VIADDMNMX / VIADDMNMX.S16x2 issue rate = 64 lanes per SM per clock)",
+                         "peak_detail_tops": ipk_detail,
+                         "note": "the motion-search kernels are bound by the integer pipe, not by HBM (SURVEY.md 8d): achieved = algorithmic lane-ops of the dominant "
+                                 "kernel (%d per MB, the reference's own evaluation counts) x %d MB x %d pictures per launch / its live CUDA-event duration; "
+                                 "whole step: int_roofline; the HBM-shaped kernel: roofline_phase_c; HBM fraction of the dominant kernel: roofline_hbm"
+                                 % (ALG_INTOPS_BY_KERNEL[dom], nmb, Bk)},
+            "roofline_hbm": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src},
             "roofline_phase_c": {"bound": "hbm", "kernel": "k_phase_c", "achieved": c_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": c_achieved / hbm_peak},
+            "int_roofline_by_kernel": {k_: {"ops_per_mb": ALG_INTOPS_BY_KERNEL[k_], "ms": kernels[k_],
+                                            "frac": (ALG_INTOPS_BY_KERNEL[k_] * nmb * Bk / (kernels[k_] / 1000.0) / 1e12) / ipk if kernels[k_] > 0 else None}
+                                       for k_ in kernels},
             "int_roofline": {"ops_per_mb": ALG_INTOPS_PER_MB, "achieved_tops": int_ops / (step_ms / 1000.0) / 1e12 / world,
                              "peak_tops_nominal": 148 * 128 * sm_max * 1e6 / 1e12,
                              "frac": (int_ops / (step_ms / 1000.0) / 1e12 / world) / (148 * 128 * sm_max * 1e6 / 1e12),
                              "note": "SURVEY.md §8d: 0.43 M int32-lane ops per MB over the whole timed job, per GPU; peak = 148 SMs x 128 lanes x max SM clock; "
-                                     "peak_tops_measured = sustained rate of the 64-lane integer pipe the ME instructions issue on (profiles/r01_int_peak.json)"},
+                                     "peak_tops_measured = sustained rate of the 64-lane integer pipe the ME instructions issue on, measured in this run"},
             "dram_traffic_bytes_per_launch": traffic_by_kernel,
             "kernel_ms_per_step": kernels, "phase_ms_per_step": {k_: tm[k_] for k_ in ("phase_a_ms", "phase_b_ms", "phase_c_ms", "copy_phase_r_ms", "total_ms")},
             "idr_decisions": idr_decisions, "mode_counts_last_picture_seq0": counts[0],
         }
-        ipk = measured_int_peak()
-        if ipk:
-            line["int_roofline"]["peak_tops_measured"] = ipk
-            line["int_roofline"]["frac_measured"] = line["int_roofline"]["achieved_tops"] / ipk
+        line["int_roofline"]["peak_tops_measured"] = ipk
+        line["int_roofline"]["frac_measured"] = line["int_roofline"]["achieved_tops"] / ipk
+        if band is not None:
+            line["band_mode"] = band
         if cavlc is not None:
             line["device_cavlc"] = cavlc
         if intra is not None:
             line["device_intra"] = intra
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
+        sys.stdout.flush()
         print(json.dumps(line))
-    for gr in groups:
-        gr.s.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def band_mode(args, rank, world, local):
-    """BASELINE config 4: one 1080p sequence, every P picture split into MB-row bands over the GPUs of the node."""
+    """--mode bands: only the band measurement, as its own JSON line."""
+    import torch.distributed as dist
+    r = band_measure(args, rank, world, local)
+    if rank == 0:
+        print(json.dumps({"metric": "1080p P-picture frames/s, ME + transform/quant/reconstruction hot path (ONE sequence, MB-row bands)",
+                          "value": r["frames_s"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_picture"],
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+                          "config": {"workload": r["workload"], "qp": QP, "window": WINDOW, "maxdiff_set": MAXDIFF}, "rank0_phase_ms": r["rank0_phase_ms"]}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def band_measure(args, rank, world, local):
+    """BASELINE config 4: one 1080p sequence, every P picture split into MB-row bands over the GPUs of the node. Returns a dict
+    (same on every rank)."""
     import torch
     import torch.distributed as dist
     import h264_fer_b200 as fh
     from h264_fer_b200 import sharding
     from h264_fer_b200.bands import BandSession
     from h264_fer_b200.native import PinnedArray
-    if world == 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29677")
-        dist.init_process_group("gloo", rank=0, world_size=1)
     K, Wu = args.steps, max(args.warmup, 3)
     clip = make_clips(1, 100)[0]
     H = clip[0][0].shape[0]
@@ -564,7 +616,8 @@ def band_mode(args, rank, world, local):
     for _ in range(Wu):
         step()
     bs.s.sync()
-    dist.barrier()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -575,17 +628,11 @@ def band_mode(args, rank, world, local):
     ms = sharding.reduce_max(e0.elapsed_time(e1))
     bs.s.picture_status(0)
     tm = bs.s.last_timings()
-    if rank == 0:
-        print(json.dumps({"metric": "1080p P-picture frames/s, ME + transform/quant/reconstruction hot path (ONE sequence, MB-row bands)",
-                          "value": K / (ms / 1000.0), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wu, "ms_per_step": ms / K,
-                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-                          "config": {"workload": "BASELINE.json config 4: one synthetic 1080p sequence, MB-row bands %s over %d GPUs, NVLink peer-memory "
-                                                 "wavefront hand-off and reconstruction exchange" % ([b - a for a, b in bs.bands], world),
-                                     "qp": QP, "window": WINDOW, "maxdiff_set": MAXDIFF},
-                          "rank0_phase_ms": tm}))
+    out = {"ms_per_picture": ms / K, "frames_s": K / (ms / 1000.0), "bands_mb_rows": [b - a for a, b in bs.bands], "rank0_phase_ms": tm,
+           "workload": "BASELINE.json config 4: one synthetic 1080p sequence, MB-row bands %s over %d GPUs, NVLink peer-memory wavefront hand-off and "
+                       "reconstruction exchange fused into the kernels (no NCCL call on the data path)" % ([b - a for a, b in bs.bands], world)}
     bs.close()
-    dist.destroy_process_group()
-    return 0
+    return out
 
 
 def cpu_baseline():
@@ -598,7 +645,7 @@ def cpu_baseline():
             sec = hot_seconds(o, 1)
             return {"value": 1.0 / sec, "unit": "frames/s", "cores": 1, "kind": "reference",
                     "sample": "unmodified reference, 1 thread: 1 I + 1 P 1080p picture (seed 100), timed = hot-path calls of the P picture "
-                              "(%.2f s; whole picture %.2f s)" % (sec, o["t_picture"][1])}
+                              "(%.2f s; whole picture %.2f s); 1 sample" % (sec, o["t_picture"][1])}
         from oracle import port
         clips = make_clips(1, 100)
         o = port.Oracle(WIDTH, clips[0][0][0].shape[0])

@@ -16,8 +16,8 @@ from .native import MB_RESULT_DTYPE, Session
 class BandSession:
     def __init__(self, width, height, device, rank=None, world=None):
         import torch.distributed as dist
-        self.rank = dist.get_rank() if rank is None else rank
-        self.world = dist.get_world_size() if world is None else world
+        self.rank = (dist.get_rank() if dist.is_initialized() else 0) if rank is None else rank
+        self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else world
         self.s = Session(width, height, batch=1, device=device)
         self.bands = sharding.mb_row_bands(height >> 4, self.world)
         self.row0, self.row1 = self.bands[self.rank]
@@ -25,12 +25,13 @@ class BandSession:
             raise ValueError("more ranks than macroblock rows")
         self.wmb = width >> 4
         self.s.band_config(self.rank, self.world, self.row0, self.row1)
-        blobs = [None] * self.world
-        dist.all_gather_object(blobs, self.s.ipc_export(0))
-        for r, blob in enumerate(blobs):
-            if r != self.rank:
-                self.s.ipc_import(0, r, blob)
-        dist.barrier()
+        if self.world > 1:
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, self.s.ipc_export(0))
+            for r, blob in enumerate(blobs):
+                if r != self.rank:
+                    self.s.ipc_import(0, r, blob)
+            dist.barrier()
 
     @property
     def mb_slice(self):
@@ -60,8 +61,9 @@ class BandSession:
     def close(self):
         import torch.distributed as dist
         self.s.sync()
-        try:
-            dist.barrier()          # nobody unmaps buffers a peer may still write
-        except Exception:
-            pass
+        if self.world > 1:
+            try:
+                dist.barrier()          # nobody unmaps buffers a peer may still write
+            except Exception:
+                pass
         self.s.close()

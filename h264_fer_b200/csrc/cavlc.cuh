@@ -43,8 +43,10 @@ __global__ void __launch_bounds__(128) k_cavlc_code(const SeqDev *__restrict__ s
     if (mb > nmb) return;
     const CvSeq &cv = cvs[seq0 + blockIdx.y];
     // mb_skip_run: the skipped macroblocks right before this one (rbsp_encoding.cpp:181-188); slot nmb = the run that ends the slice (:310)
+    // (only a macroblock that writes something walks back, so every skipped macroblock is visited once per picture)
     int run = 0;
-    for (int m = mb - 1; m >= 0 && cv.info[m].skip; m--) run++;
+    if (mb == nmb || !cv.info[mb].skip)
+        for (int m = mb - 1; m >= 0 && cv.info[m].skip; m--) run++;
     CvBits b;
     cv_init(b, cv.buf + (size_t)mb * CV_MB_WORDS, CV_MB_WORDS);
     int bad = 0;

@@ -129,14 +129,19 @@ __device__ __forceinline__ uint2 load8_unaligned(const uint8_t *p)
 
 // satdLuma8x8MVs (moestimation.cpp:175-195), one row of the reference block with the reference's clamping rule
 // (block origin clamped to the picture as a whole, then each index clamped at the right/bottom edge only).
+// (the right-edge case is kept out of line: it sits in unrolled SAD loops whose instruction-cache footprint matters)
+__device__ __noinline__ uint2 load_row8_edge(const uint8_t *row, int W, int x0)
+{
+    uint32_t b[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = row[min(x0 + i, W - 1)];
+    return make_uint2(b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24), b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
+}
 __device__ __forceinline__ uint2 load_row8(const uint8_t *plane, int W, int H, int x0, int y)
 {
     y = min(y, H - 1);
     if (x0 + 8 <= W) return load8_unaligned(plane + (size_t)y * W + x0);
-    uint32_t b[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) b[i] = plane[(size_t)y * W + min(x0 + i, W - 1)];
-    return make_uint2(b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24), b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
+    return load_row8_edge(plane + (size_t)y * W, W, x0);
 }
 __device__ __forceinline__ int sad8(uint2 a, uint2 b) { return __vsadu4(a.x, b.x) + __vsadu4(a.y, b.y); }
 __device__ __forceinline__ int sad_row8(uint2 cur, const uint8_t *plane, int W, int H, int x0, int y) { return sad8(cur, load_row8(plane, W, H, x0, y)); }

@@ -16,6 +16,7 @@
 #include "phase_c.cuh"
 #include "cavlc.cuh"
 #include "intra.cuh"
+#include "intpeak.cuh"
 static_assert(sizeof(CvInfo) == sizeof(fh264_cavlc_mb_info) && sizeof(CvInfo) == 32, "CvInfo is the public fh264_cavlc_mb_info");
 
 static thread_local std::string g_err;
@@ -113,13 +114,16 @@ __global__ void k_swap_ref(SeqDev *seqs, int seq0)
 
 // Band mode: all ranks' reconstructed bands must have landed in this rank's picture before phase R reads it.
 // One thread: announce "my phase C of picture `epoch` is complete" in every rank's sync area, then wait (bounded) for all.
-__global__ void k_band_barrier(PeerSync ps, uint32_t *status, uint32_t epoch, int rank, int world)
+// A timeout (a peer is missing or far behind: this rank's reference picture lacks that peer's band) is raised in ST_FLAGS_NEXT of
+// EVERY sequence of the call — the word phase R leaves alone after k_begin_ref, which therefore runs BEFORE this kernel — and
+// becomes the status of the next picture coded from that reference (FH264_E_STATE).
+__global__ void k_band_barrier(PeerSync ps, SeqDev *seqs, int seq0, int nseq, uint32_t epoch, int rank, int world)
 {
     __threadfence_system();
     for (int r = 0; r < world; r++) st_release_sys_u32(&ps.p[r][rank], epoch);
     bool ok = true;
     for (int r = 0; r < world; r++) ok &= wait_progress(&ps.p[rank][r], epoch, true);
-    if (!ok) atomicOr(&status[ST_FLAGS_NEXT], FLAG_TIMEOUT);
+    if (!ok) for (int b = 0; b < nseq; b++) atomicOr(&seqs[seq0 + b].status[ST_FLAGS_NEXT], FLAG_TIMEOUT);
 }
 
 static cudaError_t sync_streams(fh264_session *s)
@@ -404,17 +408,17 @@ extern "C" int fh264_upload_source(fh264_session *s, int seq, const uint8_t *y, 
 }
 
 // Phase R on the current dpb of sequences [seq0, seq0+nseq).
-static int launch_phase_r(fh264_session *s, int seq0, int nseq)
+static int launch_phase_r(fh264_session *s, int seq0, int nseq, bool begin = true)
 {
     const Geo &g = s->g;
-    k_begin_ref<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0);
+    if (begin) k_begin_ref<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0);
     dim3 gi((g.W + IT_W - 1) / IT_W, (g.H + IT_H - 1) / IT_H, nseq);
-    cudaEventRecord(s->evk[1], s->stream);
+    CK(cudaEventRecord(s->evk[1], s->stream));
     k_interp<<<gi, 256, 0, s->stream>>>(s->d_seqs, seq0, g);
-    cudaEventRecord(s->evk[2], s->stream);
+    CK(cudaEventRecord(s->evk[2], s->stream));
     dim3 gf((g.W + FT_W - 1) / FT_W, (g.H + FT_H - 1) / FT_H, nseq);
     k_features<<<gf, 256, 0, s->stream>>>(s->d_seqs, seq0, g, 0, nullptr);
-    cudaEventRecord(s->evk[3], s->stream);
+    CK(cudaEventRecord(s->evk[3], s->stream));
     dim3 gt(g.ntiles, nseq);
     k_tile_index<<<gt, 256, FH_CELLS * 4, s->stream>>>(s->d_seqs, seq0, g);
     CKL();
@@ -564,14 +568,15 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         s->copy_pending = true;
     }
     // dpb := reconstruction (frameDeepCopy, ref_frames.cpp:17-35) by pointer swap, then phase R for the next picture
-    if (g.world > 1) k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->h[seq0].status, s->epoch, g.rank, g.world);
+    k_begin_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);          // before the barrier: a barrier timeout must survive into the next picture's status
+    if (g.world > 1) k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->epoch, g.rank, g.world);
     k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
     for (int b = seq0; b < seq0 + nseq; b++)
         {
             for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
             for (int r = 0; r < FH_MAX_WORLD; r++) for (int c = 0; c < 3; c++) std::swap(s->h[b].peer_ref[r][c], s->h[b].peer_rec[r][c]);
         }
-    rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
+    rc = launch_phase_r(s, seq0, nseq, false); if (rc) return rc;
     CK(cudaEventRecord(s->ev[4], st));
     s->timed = true;
     if (!s->prev_p.empty()) for (int b = seq0; b < seq0 + nseq; b++) { s->prev_p[b] = 1; s->last_i[b] = 0; }
@@ -663,7 +668,7 @@ extern "C" int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh26
     if (s->copy_pending) { CK(cudaStreamWaitEvent(st, s->ev_copy_done, 0)); s->copy_pending = false; }   // the I records reuse the result buffer
     s->epoch++;
     CK(cudaMemcpyAsync(s->d_prev_p + seq0, s->prev_p.data() + seq0, sizeof(int) * nseq, cudaMemcpyHostToDevice, st));
-    k_begin_intra<<<1, 1, 0, st>>>(s->d_ticket + 1);
+    k_begin_intra<<<1, nseq, 0, st>>>(s->d_ticket + 1, s->d_seqs, seq0);
     int nl = 32;
     { const char *e = getenv("FH264_INTRA_LANES"); if (e && atoi(e) == 1) nl = 1; }   // development knob (read per call): everything on lane 0
     const unsigned ctas = (unsigned)std::min<long long>((long long)g.nmb * nseq, (long long)nseq * (g.Wmb + 16));
@@ -742,11 +747,14 @@ static int cavlc_finish(fh264_session *s, int seq0, int nseq, int first_bit, uin
     CKL();
     for (int b = seq0; b < seq0 + nseq; b++) CK(cudaMemcpyAsync(s->h_cvstat + 2 * b, s->cvh[b].stat, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (int b = seq0; b < seq0 + nseq; b++) {
+    for (int b = seq0; b < seq0 + nseq; b++) {            // every sequence is validated before any copy into the caller's buffers is queued
         const uint32_t fl = s->h_cvstat[2 * b], total = s->h_cvstat[2 * b + 1];
         if (fl & CV_FLAG_LEVEL_RANGE) return fail(FH264_E_UNSUPPORTED, "a level is outside the reference's level table (level_prefix > 15, residual_tables.cpp:940-1008)");
         if (fl & (CV_FLAG_MB_OVERFLOW | CV_FLAG_STREAM_OVERFLOW)) return fail(FH264_E_CAPACITY, "slice data exceeds the 500000-byte RBSP buffer of the reference (fer_h264.cpp:93)");
         if (((size_t)total + 7) / 8 > out_stride) return fail(FH264_E_ARG, "out_stride smaller than the slice data");
+    }
+    for (int b = seq0; b < seq0 + nseq; b++) {
+        const uint32_t total = s->h_cvstat[2 * b + 1];
         nbits[b - seq0] = total;
         CK(cudaMemcpyAsync(out + (size_t)(b - seq0) * out_stride, s->cvh[b].stream, ((size_t)total + 7) / 8, cudaMemcpyDeviceToHost, st));
         if (mb_info) CK(cudaMemcpyAsync(mb_info + (size_t)(b - seq0) * nmb, s->cvh[b].info, sizeof(CvInfo) * (size_t)nmb, cudaMemcpyDeviceToHost, st));
@@ -762,6 +770,8 @@ extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit
     if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
     if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
     if (s->epoch == 0) return fail(FH264_E_STATE, "cavlc_p before any encode_p");
+    for (int b = seq0; b < seq0 + nseq; b++)
+        if (!s->prev_p[b] || s->last_i[b]) return fail(FH264_E_STATE, "cavlc_p: the last picture of the sequence was not coded by encode_p (its records are not P records)");
     CK(cudaSetDevice(s->device));
     rc = ensure_cavlc(s); if (rc) return rc;
     const int nmb = s->g.nmb, wmb = s->g.Wmb;
@@ -841,6 +851,28 @@ extern "C" int fh264_last_spec_ms(fh264_session *s, float *ms)
     CK(cudaSetDevice(s->device));
     CK(cudaEventSynchronize(s->ev[4]));
     CK(cudaEventElapsedTime(ms, s->ev_spec, s->ev[1]));
+    return FH264_OK;
+}
+
+// Sustained integer-pipe rate of this GPU, T lane-statements per second: [0] IMAD, [1] VIADDMNMX.S16x2, [2] VIADDMNMX,
+// [3] VABSDIFF4.U8.ACC + VIADD pairs (two instructions per statement). About 40 ms of GPU time.
+extern "C" int fh264_measure_int_peak(int device, double tops[4])
+{
+    if (!tops) return fail(FH264_E_ARG, "null output");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(FH264_E_NO_DEVICE, "no such CUDA device");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    CK(cudaSetDevice(device));
+    unsigned *d = nullptr;
+    CK(cudaMalloc(&d, 64));
+    const int sms = prop.multiProcessorCount, iters = 512;
+    tops[0] = int_peak_run<0>(d, sms, iters, 0);
+    tops[1] = int_peak_run<1>(d, sms, iters, 0);
+    tops[2] = int_peak_run<2>(d, sms, iters, 0);
+    tops[3] = int_peak_run<3>(d, sms, iters, 0);
+    CK(cudaDeviceSynchronize());
+    cudaFree(d);
     return FH264_OK;
 }
 

@@ -17,7 +17,12 @@ struct IntraSeq {
 static_assert(sizeof(fh264_mb_result_i) == sizeof(fh264_mb_result), "I records share the result buffer");
 static_assert(sizeof(IcInfo) == 48, "IcInfo size");
 
-__global__ void k_begin_intra(uint32_t *ticket) { *ticket = 0; }
+// (also clears a wavefront timeout left by an earlier picture: intra_wait gives up early while it is set)
+__global__ void k_begin_intra(uint32_t *ticket, SeqDev *seqs, int seq0)
+{
+    seqs[seq0 + threadIdx.x].status[ST_FLAGS] &= ~FLAG_TIMEOUT;
+    if (threadIdx.x == 0) *ticket = 0;
+}
 
 // Bounded wait for a neighbour's completion flag; gives up at once when another wait of this picture has already timed out
 // (the picture is lost anyway and must drain quickly).

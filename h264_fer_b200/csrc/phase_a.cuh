@@ -13,7 +13,7 @@
 #define COST_INVALID 0xffffffffu
 // tuning constants (each one the winner of an A/B build on the B200, profiles/tools/ab_variants.sh)
 #ifndef FH_S3_SADR
-#define FH_S3_SADR 9      // stage-3 SAD: member rows in flight per lane (all 33 members in one round)
+#define FH_S3_SADR 3      // stage-3 SAD: member rows in flight per lane
 #endif
 #ifndef FH_S2_UNR
 #define FH_S2_UNR 4        // index entries in flight per lane in the stage-2 visit loop

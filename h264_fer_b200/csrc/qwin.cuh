@@ -161,7 +161,7 @@ __device__ __forceinline__ uint2 qwin_row8(const QWinView &v, int f, int cx, int
 // Larger windows stream through tk_offer. The loops stay rolled: the unrolled window code is already 6 KB of instructions.
 #define QW_STAGE_WORDS (15 * 32)
 template <int W1>
-__device__ __forceinline__ void qwin_select(const Geo &g, const QWinView &v, int xP, int yP, int Gx, int Gy, const FeatQ &fq, TopKBuf *buf, TopK &tk,
+__device__ __forceinline__ void qwin_select(const Geo &g, const QWinView &v, int xP, int yP, int Gx, int Gy, const FeatQ &fq, u64 *buf, TopK &tk,
                                             uint32_t *stage, uint32_t base)
 {
     const int lane = threadIdx.x & 31;
@@ -185,7 +185,7 @@ __device__ __forceinline__ void qwin_select(const Geo &g, const QWinView &v, int
     }
 }
 template <typename = void>
-__device__ __forceinline__ void qwin_select_w(int w1, const Geo &g, const QWinView &v, int xP, int yP, int Gx, int Gy, const FeatQ &fq, TopKBuf *buf, TopK &tk,
+__device__ __forceinline__ void qwin_select_w(int w1, const Geo &g, const QWinView &v, int xP, int yP, int Gx, int Gy, const FeatQ &fq, u64 *buf, TopK &tk,
                                               uint32_t *stage, uint32_t base)
 {
     switch (w1) {

@@ -45,7 +45,7 @@ __device__ __forceinline__ int cell_max_(int a) { return max(iabs_(a), iabs_(a -
 
 struct __align__(128) SpecWarp {
     uint64_t bar;                            // mbarrier of the TMA-staged pixel window (qwin.cuh)
-    TopKBuf tk;                              // selection of the 17 stage-1 candidates (topk.cuh)
+    TopKBufT<128> tk;                        // selection of the 17 stage-1 candidates (topk.cuh; appended after the bound is tight)
     uint32_t stage[QW_STAGE_WORDS];          // the window's costs until the bound is known (qwin_select)
     uint16_t members[FH_S1_MAX + 3];
     uint16_t msad[FH_S1_MAX + 3];
@@ -148,9 +148,9 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
         const QWinView qv = { win, QW_ROWB, qg.rows * QW_ROWB, woff };
         const int nvalid = max(0, min(W - 1, xP + Gx + g1) - max(0, xP + Gx - g1) + 1) * max(0, min(H - 1, yP + Gy + g1) - max(0, yP + Gy - g1) + 1) * 16;
         TopK tk;
-        tk_init(tk, min(FH_S1_MAX, nvalid));
-        qwin_select_w(w1, g, qv, xP, yP, Gx, Gy, fq, &sw->tk, tk, sw->stage, 0u);
-        const int nm = tk_finish(&sw->tk, tk, nvalid, sw->members, true);
+        tk_init(tk, min(FH_S1_MAX, nvalid), 128);
+        qwin_select_w(w1, g, qv, xP, yP, Gx, Gy, fq, sw->tk.key, tk, sw->stage, 0u);
+        const int nm = tk_finish(sw->tk.key, tk, nvalid, sw->members, true);
         const int r = lane & 7;
         const uint2 cr = pick_row(rows, r);
         for (int base = 0; base < nm; base += 4 * 5) {

@@ -24,7 +24,7 @@ __host__ __device__ __forceinline__ int s3_win_rows(int g1) { return 8 + 2 * g1 
 __host__ __device__ __forceinline__ int s3_win_bytes(int g1) { return 16 * s3_win_rows(g1) * S3_ROWB; }
 
 struct __align__(16) S3WarpV2 {
-    TopKBuf tk;
+    TopKBufT<320> tk;
     uint32_t stage[QW_STAGE_WORDS];      // the quarter-pel window's costs until the bound is known (qwin_select)
     uint16_t members[FH_S3_MAX + 3];
     uint16_t msad[FH_S3_MAX + 3];
@@ -80,11 +80,11 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
     const int nva = max(0, chi - clo) * max(0, rhi - rlo);
     const int nvb = max(0, min(W - 1, xP + g1) - max(0, xP - g1) + 1) * max(0, min(H - 1, yP + g1) - max(0, yP - g1) + 1) * 16;
     TopK tk;
-    tk_init(tk, min(FH_S3_MAX, nva + nvb));
+    tk_init(tk, min(FH_S3_MAX, nva + nvb), 320);
     // ---- second call first (its costs bound the first call's): MEstimation(window/16, 16 fractions, centre 0); arrival n3a + ...
     const QWinView qv = { win + (size_t)(warp >> 1) * 8 * S3_ROWB, S3_ROWB, rows * S3_ROWB, woff + (warp & 1) * 8 };
     if (interior) mbar_wait(bar, 0);
-    qwin_select_w(w1, g, qv, xP, yP, 0, 0, fq, &sw->tk, tk, sw->stage, (uint32_t)n3a);
+    qwin_select_w(w1, g, qv, xP, yP, 0, 0, fq, sw->tk.key, tk, sw->stage, (uint32_t)n3a);
     // ---- first call: MEstimation(window/2, fraction 0, centre 0); arrival (dx + g3) * w3 + (dy + g3). Rows [rlo, rhi) and columns
     //      [clo, chi) of the window have their block origin inside the picture (:265).
     const uint16_t *__restrict__ k0p = S.k0p;
@@ -116,11 +116,10 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
             while (mask) { const int b = __ffs(mask) - 1; mask &= mask - 1; sw->surv[pos++] = (uint16_t)(c * w3 + rb + b); }
             nsv += __shfl_sync(0xffffffffu, incl, 31);
         }
-        for (int e0 = 0; e0 < (chi - ncf) * (re - rb); e0 += 32) {      // leftover columns: element = (column, row)
-            const int e = e0 + lane, nr = re - rb;
-            bool pass = false; int c = 0, r = 0;
-            if (e < (chi - ncf) * nr) {
-                c = ncf + e / nr; r = rb + e % nr;
+        for (int c = ncf; c < chi; c++) {                            // leftover columns (one at WindowSize 32): lane = row of the block
+            const int r = rb + lane;
+            bool pass = false;
+            if (r < re) {
                 const uint32_t lb = (uint32_t)((iabs_(c - g3) + iabs_(r - g3) + 4) * iabs_(s[0] - (int)__ldg(k0p + (size_t)(yP - g3 + r) * W + (xP - g3 + c))));
                 pass = lb <= tcost;
             }
@@ -138,12 +137,12 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
                 const uint4 rec = __ldg(kar + (size_t)(yP - g3 + r) * W + (xP - g3 + c));
                 cst = (uint32_t)((iabs_(c - g3) + iabs_(r - g3) + 4) * feat_of(fq, rec));
             }
-            tk_offer(&sw->tk, tk, cst, idx);
+            tk_offer(sw->tk.key, tk, cst, idx);
         }
         tk_tighten(tk);
         __syncwarp();
     }
-    const int nm = tk_finish(&sw->tk, tk, nva + nvb, sw->members);
+    const int nm = tk_finish(sw->tk.key, tk, nva + nvb, sw->members);
     // ---- SADs of the members (satdLuma8x8MVs, :175-195): 8 lanes per member, one row each. Quarter-pel window members read the
     //      staged window (their block lies inside it; same clamping as the reference for an origin inside the picture).
     const int r8 = lane & 7;

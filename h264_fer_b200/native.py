@@ -31,7 +31,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_frame", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
-           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_cavlc_i", "fh264_last_timings", "fh264_last_spec_ms", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
+           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_cavlc_i", "fh264_last_timings", "fh264_last_spec_ms", "fh264_measure_int_peak", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
 
 
 class Fh264Error(RuntimeError):
@@ -88,6 +88,7 @@ def load_library():
     L.fh264_debug_feature.argtypes = [vp, i32, i32, i32, vp]
     L.fh264_last_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.fh264_last_spec_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.fh264_measure_int_peak.argtypes = [i32, C.POINTER(C.c_double)]
     L.fh264_debug_timeline.argtypes = [vp, i32, vp]
     L.fh264_cavlc_p.argtypes = [vp, i32, i32, i32, vp, C.c_size_t, vp, vp]
     L.fh264_decode_p.argtypes = [vp, i32, i32, i32, vp]
@@ -110,6 +111,16 @@ def _ptr(a: np.ndarray):
 
 def _u8(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def measure_int_peak(device=0):
+    """Sustained integer-pipe rate of the GPU in T lane-statements/s: dict of IMAD, VIADDMNMX.S16x2, VIADDMNMX, VABSDIFF4+VIADD."""
+    L = load_library()
+    t = (C.c_double * 4)()
+    rc = L.fh264_measure_int_peak(int(device), t)
+    if rc:
+        raise Fh264Error(rc, (L.fh264_last_error() or b"").decode())
+    return {"imad": t[0], "viaddmnmx_s16x2": t[1], "viaddmnmx": t[2], "vabsdiff4_acc_plus_viadd": t[3]}
 
 
 class PinnedArray:

@@ -2,9 +2,11 @@
 
 * Independent sequences (BASELINE config 5) shard with NO data-path collective: sequence s -> rank s % world.
 * Macroblock-row bands of one picture (BASELINE config 4): contiguous bands, remainder rows to the first ranks (1080p:
-  67 MB rows -> 9,9,9,8,8,8,8,8 on 8 GPUs). Phases R/A/C shard by band; the phase-B wavefront does not (the first MB row of
-  a band needs the MVs of the band above), so band mode exchanges the reconstruction (all-gather) and the band's last MB
-  row of motion records. Only the partitioning arithmetic lives here; it is what the gloo CPU tests exercise.
+  67 MB rows -> 9,9,9,8,8,8,8,8 on 8 GPUs). Phases A/S/C shard by band; the phase-B wavefront crosses the bands (the first MB
+  row of a band needs the vectors of the band above). The exchange itself is not here: the kernels store the reconstruction and
+  the last MB row's vectors straight into the peers' memory (bands.py, csrc/phase_b.cuh, phase_c.cuh); stage 2 reaches +-291
+  luma rows, more than a band, so every rank keeps the whole reference picture. Only the partitioning arithmetic and the small
+  host-side reductions live here; they are what the gloo CPU tests exercise.
 """
 from __future__ import annotations
 
@@ -28,13 +30,6 @@ def mb_row_bands(mb_rows: int, world: int) -> List[Tuple[int, int]]:
         out.append((r, r + n))
         r += n
     return out
-
-
-def halo_rows(band: Tuple[int, int], mb_rows: int, reach_px: int = 291) -> Tuple[int, int]:
-    """Reference luma rows [lo, hi) a band needs: stage 2 reaches Manhattan 279 px + 8 (block) + 3 (6-tap), moestimation.cpp:481."""
-    lo = max(0, band[0] * 16 - reach_px)
-    hi = min(mb_rows * 16, band[1] * 16 + reach_px)
-    return lo, hi
 
 
 def reduce_max(value: float) -> float:

@@ -167,6 +167,10 @@ int fh264_last_timings(fh264_session *s, float ms[10]);
 /* Phase S of the last fh264_encode_p (k_spec: the search completed in parallel for the guessed integer predictors, so that the
  * wavefront only evaluates a handful of finalists per 8x8 partition), milliseconds; it is part of [0] above. */
 int fh264_last_spec_ms(fh264_session *s, float *ms);
+/* Measurement aid: sustained rate of the integer pipe the motion-search instructions issue on, measured on
+ * `device` now (about 40 ms), in T lane-statements per second: [0] IMAD, [1] VIADDMNMX.S16x2, [2] VIADDMNMX,
+ * [3] VABSDIFF4.U8.ACC + VIADD pairs. bench.py divides by it in the same run that it times the kernels. */
+int fh264_measure_int_peak(int device, double tops[4]);
 
 /* ---- device entropy coding of a P slice ---------------------------------------------------------
  * slice_data() of the P picture last coded by fh264_encode_p for sequences [seq0, seq0 + nseq): what the P-slice macroblock

@@ -42,14 +42,11 @@ def test_two_rank_gloo_sharding_and_timing():
         assert tmax == 11.0                                     # max over ranks, identical on every rank
 
 
-def test_mb_row_bands_and_halo():
+def test_mb_row_bands():
     assert [b - a for a, b in sharding.mb_row_bands(67, 8)] == [9, 9, 9, 8, 8, 8, 8, 8]
     bands = sharding.mb_row_bands(67, 8)
     assert bands[0][0] == 0 and bands[-1][1] == 67 and all(bands[i][1] == bands[i + 1][0] for i in range(7))
     assert sharding.mb_row_bands(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
-    lo, hi = sharding.halo_rows(bands[3], 67)
-    assert lo == bands[3][0] * 16 - 291 and hi == bands[3][1] * 16 + 291
-    assert sharding.halo_rows(bands[0], 67)[0] == 0 and sharding.halo_rows(bands[7], 67)[1] == 67 * 16
     with pytest.raises(ValueError):
         sharding.sequences_for_rank(4, 2, 2)
 

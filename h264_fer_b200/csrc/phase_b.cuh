@@ -28,14 +28,17 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) { uint32_t
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 // Bounded wait until *p >= target (flags written by another CTA, or in band mode by another GPU). Returns false on timeout.
+#define FH_WAIT_NS 2000000000ll          // every cross-CTA / cross-GPU wait gives up after 2 s of %globaltimer
+__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ bool wait_progress(const uint32_t *p, uint32_t target, bool sys)
 {
-    for (unsigned it = 0; it < (1u << 25); it++) {
+    long long t0 = 0;
+    for (unsigned it = 0;; it++) {
         const uint32_t v = sys ? ld_acquire_sys_u32(p) : ld_acquire_u32(p);
         if (v >= target) return true;
+        if ((it & 1023u) == 1023u) { const long long t = gtime_ns(); if (t0 == 0) t0 = t; else if (t - t0 > FH_WAIT_NS) return false; }
         __nanosleep(20);
     }
-    return false;
 }
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
@@ -58,9 +61,11 @@ __device__ __forceinline__ unsigned long long qmv_word(uint32_t epoch, int mvx, 
 // Bounded wait for a quadrant word of this picture (written by another CTA, or in band mode by another GPU).
 __device__ __forceinline__ bool wait_qmv(const unsigned long long *p, uint32_t epoch, bool sys, int &mvx, int &mvy)
 {
-    for (unsigned it = 0; it < (1u << 25); it++) {
+    long long t0 = 0;
+    for (unsigned it = 0;; it++) {
         const unsigned long long v = ld_relaxed_u64(p, sys);
         if ((uint32_t)(v >> 32) == epoch) { mvx = (int)(int16_t)(v & 0xffffu); mvy = (int)(int16_t)((v >> 16) & 0xffffu); return true; }
+        if ((it & 1023u) == 1023u) { const long long t = gtime_ns(); if (t0 == 0) t0 = t; else if (t - t0 > FH_WAIT_NS) break; }
         __nanosleep(20);
     }
     mvx = mvy = 0;
@@ -110,7 +115,39 @@ __device__ __forceinline__ void predict_mv_(const NbCache &nc, int px, int py, i
 
 __device__ __forceinline__ int mv_cost(int mvx, int mvy, int px, int py) { return iabs_(mvx - px) + iabs_(mvy - py); }
 
-__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+// ---- the whole macroblock from the phase-S products, by ONE warp, in registers (no block barrier, no shared-memory state) -------
+// Every decision interEncoding makes for a macroblock (:402-564) once the predictors are known is a lookup: the P_Skip trial in
+// the phase-S masks, each partition's winner among its finalists, merge and mvd from the four winners. The left macroblock's
+// quadrants are polled by lane 0 exactly where a predictor really depends on them (same rules as the block-level path below).
+// Returns false — without having published anything that the block-level path would not publish identically — as soon as a
+// lookup cannot answer (predictor outside the guessed cells, oversized finalist set); the caller then runs the full search.
+struct FastNb { int aL, aU, aUR, aUL, u2x, u2y, u3x, u3y, r2x, r2y, d3x, d3y; };
+__device__ __forceinline__ int spec_lookup(const PartSpec &sp, int genx, int geny, int mvpx, int mvpy, int &bx, int &by, int &bs)
+{
+    int slot = -1;
+    if (sp.nf[0] != SPEC_INVALID && sp.gx[0] == genx && sp.gy[0] == geny) slot = 0;
+    else if (sp.nf[1] != SPEC_INVALID && sp.gx[1] == genx && sp.gy[1] == geny) slot = 1;
+    if (slot < 0) return 0;
+    const int nf = sp.nf[slot];
+    u64 bk = KEY_NONE;
+    for (int k = 0; k < nf; k++) {
+        const SpecFinal f = sp.f[slot][k];
+        const u64 key = ((u64)((int)f.sad + mv_cost(f.mvx, f.mvy, mvpx, mvpy)) << 32) | ((u64)f.order << 16) | (u64)k;
+        bk = min(bk, key);
+    }
+    const SpecFinal f = sp.f[slot][(int)(bk & 15)];
+    bx = f.mvx; by = f.mvy; bs = f.sad;
+    return 1;
+}
+__device__ __forceinline__ int skip_lookup(const MbSpec &ms, int vx, int vy)       // 0: skips, 1: does not, -1: not precomputed
+{
+    if (vx == 0 && vy == 0) return ms.zero_ok ? 0 : 1;
+    const int cxx = vx >> 2, cyy = vy >> 2, f = (vy & 3) * 4 + (vx & 3);
+    if (ms.cx[0] == cxx && ms.cy[0] == cyy) return ((ms.mask[0] >> f) & 1) ? 0 : 1;
+    if (ms.cx[1] == cxx && ms.cy[1] == cyy) return ((ms.mask[1] >> f) & 1) ? 0 : 1;
+    return -1;
+}
 
 struct BlockSel { u64 skey[256]; uint16_t sidx[256]; int ns[2]; int phase; };
 
@@ -130,6 +167,7 @@ struct PBShared {
     uint32_t qx[16 * 61];                // qfeat.cuh step A: row sums of the stage-1 window (16 planes x 12 rows x 5 positions at WindowSize 32)
     uint16_t qrc[16 * 61];
     uint32_t my_ticket;
+    int fast_done;                       // the warp-level fast path decided the whole macroblock
     int red[4];
     // stage2_slow
     int slow_ns, slow_total, slow_arg[12];
@@ -457,6 +495,144 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
     const int r2x = nc.mvx[2][2], r2y = nc.mvy[2][2], d3x = nc.mvx[3][3], d3y = nc.mvy[3][3];
 
     PB_STAMP(3);
+    // ---- fast path: the whole macroblock by warp 0 from the phase-S products (see spec_lookup / skip_lookup above). On any
+    //      lookup that cannot answer, the block-level search below redoes the macroblock from the start (same published values).
+    if (use_spec) {
+        if (warp == 0) {
+            bool ok = true, done = false;
+            int l1x = 0, l1y = 0, l3x = 0, l3y = 0;
+            bool have1 = !leftA, have3 = !leftA;
+            auto poll_left = [&](int q, int &vx, int &vy) {
+                int x = 0, y = 0;
+                if (lane == 0 && !wait_qmv(&S.qmv[(size_t)(mb - 1) * 4 + q], epoch, false, x, y)) atomicOr(&S.status[ST_FLAGS], FLAG_TIMEOUT);
+                vx = __shfl_sync(0xffffffffu, x, 0); vy = __shfl_sync(0xffffffffu, y, 0);
+            };
+            auto publish = [&](int q, int vx, int vy) {
+                if (lane == 0) {
+                    const unsigned long long wq = qmv_word(epoch, vx, vy);
+                    st_relaxed_u64(&S.qmv[(size_t)mb * 4 + q], wq, false);
+                    if (mirror) st_relaxed_u64(&S.peer_qmv_next[(size_t)mb * 4 + q], wq, true);
+                }
+            };
+            const MbSpec &ms = sh.ms;
+            int smx = 0, smy = 0, nbad = 1;
+            if (!leftA || mby == 0 || (u2x == 0 && u2y == 0)) nbad = skip_lookup(ms, 0, 0);
+            else {
+                const int cx16 = aUR ? r2x : d3x, cy16 = aUR ? r2y : d3y;
+                if (u2x == cx16 && u2y == cy16) {
+                    const int nbB = skip_lookup(ms, u2x, u2y), nb0 = skip_lookup(ms, 0, 0);
+                    if (lane == 0) S.prev_gen16[mb] = ((uint32_t)(u2x >> 2) & 0xffffu) | ((uint32_t)(u2y >> 2) << 16);
+                    if (nbB < 0) ok = false;
+                    else if (nbB != 0 && nb0 != 0) nbad = 1;
+                    else {
+                        poll_left(1, l1x, l1y); have1 = true;
+                        const bool lz = l1x == 0 && l1y == 0;
+                        smx = lz ? 0 : u2x; smy = lz ? 0 : u2y; nbad = lz ? nb0 : nbB;
+                    }
+                } else {
+                    poll_left(1, l1x, l1y); have1 = true;
+                    if (!(l1x == 0 && l1y == 0)) {
+                        median_pred(1, l1x, l1y, 1, u2x, u2y, 1, cx16, cy16, smx, smy);      // A = left q1, B = up q2, C = up-right q2 else up-left q3: all available here
+                        if (lane == 0) S.prev_gen16[mb] = ((uint32_t)(smx >> 2) & 0xffffu) | ((uint32_t)(smy >> 2) << 16);
+                    }
+                    nbad = skip_lookup(ms, smx, smy);
+                    if (nbad < 0) ok = false;
+                }
+            }
+            if (dbg && lane == 0) dbg[4] = gtime_ns();
+            if (ok && nbad == 0) {
+                for (int q = 0; q < 4; q++) publish(q, smx, smy);
+                if (lane == 0) {
+                    MbMotion mo;
+                    mo.maxdiff = (int16_t)ms.maxdiff; mo.pad = 0; mo.mb_type = FH264_P_SKIP; mo.num_parts = 0;
+                    for (int i = 0; i < 4; i++) { mo.mv[i][0] = (int16_t)smx; mo.mv[i][1] = (int16_t)smy; mo.mvd[i][0] = mo.mvd[i][1] = 0; mo.sad[i] = 0; }
+                    uint4 *d = (uint4 *)&S.motion[mb];
+                    const uint4 *s4 = (const uint4 *)&mo;
+                    d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
+                    atomicAdd(&S.status[ST_COUNTS + 0], 1u);
+                }
+                done = true;
+            } else if (ok) {
+                int q0x = 0, q0y = 0, q1x = 0, q1y = 0, q2x = 0, q2y = 0, q3x = 0, q3y = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                int p0x, p0y, p1x, p1y, p2x, p2y, p3x, p3y;
+                // partition 0 predicts from left q1 unless up q2 == up q3; partition 2 from left q3 unless own q0 == q1
+                if (!have1 && !(aU && u2x == u3x && u2y == u3y)) { poll_left(1, l1x, l1y); have1 = true; }
+                median_pred(aL, l1x, l1y, aU, u2x, u2y, aU ? 1 : aUL, aU ? u3x : d3x, aU ? u3y : d3y, p0x, p0y);
+                ok = spec_lookup(sh.spec[0], p0x >> 2, p0y >> 2, p0x, p0y, q0x, q0y, s0);
+                if (ok) {
+                    publish(0, q0x, q0y);
+                    if (dbg && lane == 0) dbg[5] = gtime_ns();
+                    median_pred(1, q0x, q0y, aU, u3x, u3y, aUR ? 1 : aU, aUR ? r2x : u2x, aUR ? r2y : u2y, p1x, p1y);
+                    ok = spec_lookup(sh.spec[1], p1x >> 2, p1y >> 2, p1x, p1y, q1x, q1y, s1);
+                }
+                if (ok) {
+                    publish(1, q1x, q1y);
+                    if (dbg && lane == 0) dbg[6] = gtime_ns();
+                    if (!have3 && !(q0x == q1x && q0y == q1y)) { poll_left(3, l3x, l3y); have3 = true; }
+                    median_pred(aL, l3x, l3y, 1, q0x, q0y, 1, q1x, q1y, p2x, p2y);
+                    ok = spec_lookup(sh.spec[2], p2x >> 2, p2y >> 2, p2x, p2y, q2x, q2y, s2);
+                }
+                if (ok) {
+                    publish(2, q2x, q2y);
+                    if (dbg && lane == 0) dbg[7] = gtime_ns();
+                    median_pred(1, q2x, q2y, 1, q1x, q1y, 1, q0x, q0y, p3x, p3y);
+                    ok = spec_lookup(sh.spec[3], p3x >> 2, p3y >> 2, p3x, p3y, q3x, q3y, s3);
+                }
+                if (ok) {
+                    publish(3, q3x, q3y);
+                    if (dbg && lane == 0) dbg[8] = gtime_ns();
+                    // merge (:529-551) and final mvd with the merged type's predictors (:552-564)
+                    const bool eq01 = q0x == q1x && q0y == q1y, eq23 = q2x == q3x && q2y == q3y;
+                    const bool eq02 = q0x == q2x && q0y == q2y, eq13 = q1x == q3x && q1y == q3y;
+                    if ((eq01 && eq23) || (eq02 && eq13)) {               // 16x16 / 16x8 / 8x16: the predictors read the left macroblock
+                        if (!have1) { poll_left(1, l1x, l1y); have1 = true; }
+                        if (!have3) { poll_left(3, l3x, l3y); have3 = true; }
+                    }
+                    if (lane == 0) {
+                        nc.mvx[0][1] = l1x; nc.mvy[0][1] = l1y; nc.mvx[0][3] = l3x; nc.mvy[0][3] = l3y;
+                        const int mv[4][2] = { { q0x, q0y }, { q1x, q1y }, { q2x, q2y }, { q3x, q3y } };
+                        const int mvps[4][2] = { { p0x, p0y }, { p1x, p1y }, { p2x, p2y }, { p3x, p3y } };
+                        const int sadq[4] = { s0, s1, s2, s3 };
+                        int type = FH264_P_8x8ref0, nparts = 4, cnt = 4;
+                        if (eq01 && eq23 && eq02) { type = FH264_P_L0_16x16; nparts = 1; cnt = 1; }
+                        else if (eq01 && eq23) { type = FH264_P_L0_L0_16x8; nparts = 2; cnt = 2; }
+                        else if (eq02 && eq13) { type = FH264_P_L0_L0_8x16; nparts = 2; cnt = 3; }
+                        MbMotion mo;
+                        mo.maxdiff = (int16_t)ms.maxdiff; mo.pad = 0;
+                        int fin[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+                        for (int i = 0; i < 4; i++) { mo.mvd[i][0] = mo.mvd[i][1] = 0; }
+                        for (int i = 0; i < nparts; i++) {
+                            int ppx = 0, ppy = 0, pw = 16, dir = 0, qsel = i, ox, oy;
+                            if (type == FH264_P_L0_L0_16x8) { ppy = i * 8; dir = i == 0 ? 1 : 2; qsel = i * 2; }
+                            else if (type == FH264_P_L0_L0_8x16) { ppx = i * 8; pw = 8; dir = i == 0 ? 2 : 3; }
+                            else if (type == FH264_P_8x8ref0) { ppx = (i & 1) * 8; ppy = (i >> 1) * 8; pw = 8; }
+                            if (type == FH264_P_8x8ref0) { ox = mvps[i][0]; oy = mvps[i][1]; }
+                            else predict_mv_(nc, ppx, ppy, pw, dir, fin, ox, oy);
+                            mo.mvd[i][0] = (int16_t)(mv[qsel][0] - ox); mo.mvd[i][1] = (int16_t)(mv[qsel][1] - oy);
+                            for (int q = 0; q < 4; q++) {
+                                const bool in = type == FH264_P_L0_16x16 || (type == FH264_P_L0_L0_16x8 && (q >> 1) == i) ||
+                                                (type == FH264_P_L0_L0_8x16 && (q & 1) == i) || (type == FH264_P_8x8ref0 && q == i);
+                                if (in) { fin[q][0] = mv[qsel][0]; fin[q][1] = mv[qsel][1]; }
+                            }
+                        }
+                        mo.mb_type = (int16_t)type; mo.num_parts = (int16_t)nparts;
+                        for (int q = 0; q < 4; q++) { mo.mv[q][0] = (int16_t)fin[q][0]; mo.mv[q][1] = (int16_t)fin[q][1]; mo.sad[q] = (uint16_t)sadq[q]; }
+                        uint4 *d = (uint4 *)&S.motion[mb];
+                        const uint4 *s4 = (const uint4 *)&mo;
+                        d[0] = s4[0]; d[1] = s4[1]; d[2] = s4[2];
+                        for (int i = 0; i < 4; i++) S.prev_gen[(size_t)mb * 4 + i] = ((uint32_t)(mvps[i][0] >> 2) & 0xffffu) | ((uint32_t)(mvps[i][1] >> 2) << 16);
+                        if (dbg) dbg[9] = gtime_ns();
+                        atomicAdd(&S.status[ST_COUNTS + cnt], 1u);
+                        atomicAdd(&S.status[ST_SPEC_HIT], 4u);
+                    }
+                    done = true;
+                }
+            }
+            if (lane == 0) sh.fast_done = done ? 1 : 0;
+        }
+        __syncthreads();
+        if (sh.fast_done) continue;
+    }
     // ---- P_Skip trial (mode_pred.cpp:383-401, moestimation.cpp:402-425) -----------------------------------------
     int zero4[4][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
     const int py = tid >> 3, px = (tid & 7) * 2;                          // this thread's two luma samples

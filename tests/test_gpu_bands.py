@@ -72,3 +72,51 @@ def test_band_mode_matches_oracle(world, w, h, window, maxdiff):
             assert np.array_equal(got, want), "rank %d picture %d: %s" % (r, t, np.argwhere(got != want)[:6].tolist())
             assert all(np.array_equal(a, b) for a, b in zip(recon, want_recon)), "rank %d picture %d recon" % (r, t)
         ref = want_recon
+
+
+def _worker_missing_peer(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import h264_fer_b200 as fh
+    from h264_fer_b200 import synth
+    from h264_fer_b200.bands import BandSession
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w, h = 352, 288
+    clip = synth.SynthClip(w, h, 9)
+    bs = BandSession(w, h, device=rank)
+    bs.upload_recon(*clip.frame(0))
+    bs.upload_source(*clip.frame(1))
+    bs.encode_p(28, 32, 3)                                    # picture 1: every rank takes part
+    outcome = "ok"
+    if rank == 0:
+        bs.upload_source(*clip.frame(2))
+        bs.encode_p(28, 32, 3)                                # picture 2: rank 1 is missing; its band never arrives, the picture barrier times out
+        bs.upload_source(*clip.frame(3))
+        try:
+            bs.encode_p(28, 32, 3)                            # picture 3 would predict from an incomplete reference picture
+            outcome = "no error"
+        except fh.Fh264Error as e:
+            outcome = "error %d" % e.code
+    q.put((rank, outcome))
+    bs.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="band mode needs at least 2 GPUs")
+def test_band_mode_reports_a_missing_peer_instead_of_coding_from_an_incomplete_reference():
+    """A rank that skips a picture leaves the others' reference picture without its band: the picture barrier's bounded wait
+    must surface as FH264_E_STATE on the next picture (it used to be cleared by phase R before anybody read it)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_missing_peer, args=(r, 2, 29643, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert res[0] == "error -4", res

@@ -8,6 +8,8 @@
 //   transformDecodingP_Skip(...)                    inttransform.h:5     -> no-op (the GPU reconstructed the picture)
 //   FillInterpolatedRefFrame()                      moestimation.h:8     -> keeps host `frame`/`dpb` and the device in step
 //   selectNALUnitType()                             ref_frames.h:20      -> same rule, scene SAD from the device
+//   InitCL / AllocateFrameBuffersCL / CloseCL        openCL_functions.h:4-19 -> the accelerator lifecycle seam the reference already
+//                                                    has (fer_h264.cpp:90,74,129; rbsp_encoding.cpp:129): session open / close
 //
 // following the pattern the reference itself uses for its OpenCL offload: launch whole-picture work when
 // CurrMbAddr == 0 and consume it per macroblock (IntraCL() at rbsp_encoding.cpp:144, WaitIntraCL at intra.cpp:963-966).
@@ -51,13 +53,46 @@ static void die(const char *what, int rc)
     exit(3);                       // fail loudly: there is no CPU fallback behind this shim
 }
 
-static void ensure_session()
+static void open_session()
 {
     if (g_sess) return;
     const char *dev = getenv("FH264_DEVICE");
     int rc = fh264_open(frame.Lwidth, frame.Lheight, 1, dev ? atoi(dev) : 0, &g_sess);
     if (rc) die("fh264_open", rc);
     g_res.resize((size_t)(frame.Lwidth >> 4) * (frame.Lheight >> 4));
+}
+// (a host that never calls AllocateFrameBuffersCL — none in the reference — still gets a session on first use)
+static void ensure_session() { open_session(); }
+
+// ---- the reference's accelerator lifecycle seam (openCL_functions.h:4-19), taken over as it stands -------------------------
+// OpenCLEnabled stays false: the reference's own OpenCL intra path yields different bitstreams (intra.cpp:961-977 vs :978-1049),
+// and the symbols its host code references must exist. InitCL() runs before the picture size is known (fer_h264.cpp:90), so the
+// session opens in AllocateFrameBuffersCL(), which RBSP_encode() calls right after the SPS fixed the size (rbsp_encoding.cpp:129)
+// — the same place the reference allocates its device frame buffers — and closes in CloseCL() (fer_h264.cpp:74,129).
+#include <CL/cl.h>
+bool OpenCLEnabled = false;
+int *predModes16x16 = 0, *predModes4x4 = 0;
+cl_mem frame_mem, dpb_mem, ans_mem;
+cl_command_queue cmd_queue;
+cl_context context;
+cl_kernel kernel[2];
+void InitCL() {}
+void AllocateFrameBuffersCL() { open_session(); }
+void CloseCL()
+{
+    if (!g_sess) return;
+    int rc = fh264_close(g_sess);
+    g_sess = 0;
+    if (rc) die("fh264_close", rc);
+}
+void IntraCL() {}                               // (only reached with OpenCLEnabled)
+void WaitIntraCL(int) {}
+void subtractFramesCL(unsigned char *, unsigned char *)
+{
+    // the reference's selectNALUnitType() would take this path with OpenCLEnabled (ref_frames.cpp:196-208); the shim replaces
+    // selectNALUnitType() itself (below: fh264_scene_sad returns the 64-bit sum instead of W*H differences), so nobody calls it
+    fprintf(stderr, "fh264 shim: subtractFramesCL is not part of the binding (selectNALUnitType uses fh264_scene_sad)\n");
+    exit(3);
 }
 
 int selectNALUnitType()

@@ -30,6 +30,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
+LIB_BOUNDS = os.path.join(HERE, "libfh264_b200_bounds.so")
+
+
+def build_bounds() -> str:
+    """Debug build with -DFH_BOUNDS (index checks on the shared-memory work arrays of the search kernels); load it with
+    FH264_B200_LIB=<path> to run the parity suite on it."""
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DFH_BOUNDS", "-o", LIB_BOUNDS, SRC]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout.decode()[-4000:])
+    return LIB_BOUNDS
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or needs_build():
         cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB, SRC]
@@ -45,4 +58,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    print(build_bounds() if "--bounds" in sys.argv else build(force=True, verbose=True))

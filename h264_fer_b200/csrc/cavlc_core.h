@@ -98,30 +98,42 @@ FH_HD int cv_ilog2(uint32_t v) { int n = 0; while (v >>= 1) n++; return n; }
 FH_HD void cv_ue(CvBits &b, uint32_t v) { const int k = cv_ilog2(v + 1); cv_put(b, k, 0); cv_put(b, k + 1, v + 1); }       // expgolomb.cpp:80-92
 FH_HD void cv_se(CvBits &b, int v) { cv_ue(b, v <= 0 ? (uint32_t)(-v) * 2u : (uint32_t)v * 2u - 1u); }                    // :94-106
 
-// ---- one residual block (residual.cpp:374-666). coef[0 .. maxc-1] in scan order; returns TotalCoeff; *bad set when a level
-//      is outside what the reference's level table can code (level_prefix <= 15, residual_tables.cpp:940-1008) ---------------
+// ---- one residual block (what residual_block_cavlc_write emits, residual.cpp:374-666). coef[0 .. maxc-1] in scan order; returns
+//      TotalCoeff; *bad set when a level is outside what the reference's level table can code (level_prefix <= 15,
+//      residual_tables.cpp:940-1008).
+// The block is described by its NON-ZERO MASK (bit i = coef[i] != 0): TotalCoeff is its population count, the coefficients come
+// in coding order (highest frequency first) by peeling the top set bit, TrailingOnes are the leading +-1 among the first three
+// peeled, total_zeros = zeros below the top set bit, and run_before is the gap between consecutive set bits — no level / run
+// arrays, no backward scans.
+#if defined(__CUDA_ARCH__)
+#define CV_POPC(x) __popc(x)
+#define CV_TOPBIT(x) (31 - __clz((int)(x)))
+#else
+#define CV_POPC(x) __builtin_popcount(x)
+#define CV_TOPBIT(x) (31 - __builtin_clz(x))
+#endif
 FH_HD int cv_block(CvBits &b, const int16_t *coef, int maxc, int nC, int *bad)
 {
-    int level[16], run[16];
-    int tc = 0, t1 = 0, tz = 0;
-    bool only_ones = true;
-    for (int i = maxc - 1; i >= 0; i--) {
-        const int c = coef[i];
-        if (c != 0) {
-            int r = 0;
-            for (int j = i - 1; j >= 0 && coef[j] == 0; j--) r++;
-            run[tc] = r;
-            if ((c == 1 || c == -1) && t1 < 3 && only_ones) t1++; else only_ones = false;
-            level[tc++] = c;
-        } else if (tc > 0) tz++;
-    }
+    uint32_t nz = 0;
+    for (int i = 0; i < maxc; i++) nz |= (uint32_t)(coef[i] != 0) << i;
+    const int tc = CV_POPC(nz);
     const int tab = nC < 0 ? 4 : (nC < 2 ? 0 : (nC < 4 ? 1 : (nC < 8 ? 2 : 3)));
+    if (tc == 0) { cv_put(b, cv_ct_len[tab][0][0], cv_ct_code[tab][0][0]); return 0; }
+    int t1 = 0;
+    for (uint32_t m = nz; m && t1 < 3; t1++) {
+        const int p = CV_TOPBIT(m);
+        if (coef[p] != 1 && coef[p] != -1) break;
+        m &= ~(1u << p);
+    }
     cv_put(b, cv_ct_len[tab][tc][t1], cv_ct_code[tab][tc][t1]);
-    if (tc == 0) return 0;
     int sl = (tc > 10 && t1 < 3) ? 1 : 0;
+    uint32_t m = nz;
     for (int i = 0; i < tc; i++) {
-        if (i < t1) { cv_put(b, 1, (uint32_t)((1 - level[i]) >> 1)); continue; }
-        int lc = level[i] < 0 ? -(level[i] << 1) - 1 : (level[i] << 1) - 2;
+        const int p = CV_TOPBIT(m);
+        m &= ~(1u << p);
+        const int lv = coef[p];
+        if (i < t1) { cv_put(b, 1, (uint32_t)((1 - lv) >> 1)); continue; }
+        int lc = lv < 0 ? -(lv << 1) - 1 : (lv << 1) - 2;
         if (i == t1 && t1 < 3) lc -= 2;
         // level_prefix / level_suffix (9.2.2.1 inverted): escape at prefix 14 (suffixLength 0) and 15
         int prefix, ssize;
@@ -137,20 +149,25 @@ FH_HD int cv_block(CvBits &b, const int16_t *coef, int maxc, int nC, int *bad)
         cv_put(b, 1, 1);
         cv_put(b, ssize, suffix);
         if (sl == 0) sl = 1;
-        const int al = level[i] < 0 ? -level[i] : level[i];
+        const int al = lv < 0 ? -lv : lv;
         if (al > (3 << (sl - 1)) && sl < 6) sl++;
     }
+    int zl = CV_TOPBIT(nz) + 1 - tc;                       // total_zeros
     if (tc < maxc) {
-        if (nC >= 0) cv_put(b, cv_tz_len[tc - 1][tz], cv_tz_code[tc - 1][tz]);
-        else cv_put(b, cv_tzc_len[tc - 1][tz], cv_tzc_code[tc - 1][tz]);
-    } else tz = 0;
-    int zl = tz;
-    for (int j = 0; j < tc - 1; j++) {
-        if (zl > 0) {
-            if (zl > 6) { if (run[j] < 7) cv_put(b, 3, (uint32_t)(7 - run[j])); else { cv_put(b, run[j] - 4, 0); cv_put(b, 1, 1); } }   // residual.cpp:73-84
-            else cv_put(b, cv_rb_len[zl - 1][run[j]], cv_rb_code[zl - 1][run[j]]);
-        }
-        zl -= run[j];
+        if (nC >= 0) cv_put(b, cv_tz_len[tc - 1][zl], cv_tz_code[tc - 1][zl]);
+        else cv_put(b, cv_tzc_len[tc - 1][zl], cv_tzc_code[tc - 1][zl]);
+    } else zl = 0;
+    m = nz;
+    int p = CV_TOPBIT(m);
+    m &= ~(1u << p);
+    while (m && zl > 0) {                                  // run_before of every coefficient but the last, while zeros are left
+        const int q = CV_TOPBIT(m);
+        m &= ~(1u << q);
+        const int run = p - q - 1;
+        if (zl > 6) { if (run < 7) cv_put(b, 3, (uint32_t)(7 - run)); else { cv_put(b, run - 4, 0); cv_put(b, 1, 1); } }   // residual.cpp:73-84
+        else cv_put(b, cv_rb_len[zl - 1][run], cv_rb_code[zl - 1][run]);
+        zl -= run;
+        p = q;
     }
     return tc;
 }

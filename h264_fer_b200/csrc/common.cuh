@@ -5,7 +5,17 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 #include "../../include/fh264_b200.h"
+
+// -DFH_BOUNDS (debug build, `python -m h264_fer_b200.build --bounds`): every index into a shared-memory work array of the search
+// kernels is checked and traps (compute-sanitizer is closed on this pool; the parity suite is run on this build once per round).
+#ifdef FH_BOUNDS
+__device__ __forceinline__ int fh_idx_(int i, int n, int line) { if ((unsigned)i >= (unsigned)n) { printf("FH_BOUNDS: index %d outside [0, %d) at line %d\n", i, n, line); __trap(); } return i; }
+#define FH_IDX(i, n) fh_idx_((int)(i), (int)(n), __LINE__)
+#else
+#define FH_IDX(i, n) (i)
+#endif
 
 #define FH_TILE 64              // spatial tile of the stage-2 index
 #define FH_TILE_SHIFT 6

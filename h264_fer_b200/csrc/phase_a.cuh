@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(32 * NW, FH_S2_MINB) k_stage2(const SeqDev *__
         if (m == 0u) return;
         if (ok) {
             const int j = (int)(ae & 0xffffu), side = (int)(v.y & 0xffffu) > s[0];
-            if (countonly) atomicAdd(&w->bins[2 * j + side], 1u);
+            if (countonly) atomicAdd(&w->bins[FH_IDX(2 * j + side, S2_BINS)], 1u);
             else {
                 const int pos = ns + __popc(m & ((1u << lane) - 1u));
                 const int dx = (int)(v.x & 0xffffu) - xP, dy = (int)(v.x >> 16) - yP;
-                w->akey[pos] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
+                w->akey[FH_IDX(pos, S2_CAP)] = ((uint32_t)j << 21) | ((uint32_t)side << 20) | ((uint32_t)(dx + 279) << 10) | (uint32_t)(dy + 279);
                 w->aval[pos] = eidx;
             }
         }
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(32 * NW, FH_S2_MINB) k_stage2(const SeqDev *__
         __syncwarp();
         for (int i = lane; i < S2_BINS; i += 32) w->bins[i] = 0;
         __syncwarp();
-        for (int i = lane; i < ns; i += 32) atomicAdd(&w->bins[w->akey[i] >> 20], 1u);
+        for (int i = lane; i < ns; i += 32) atomicAdd(&w->bins[FH_IDX(w->akey[i] >> 20, S2_BINS)], 1u);
         __syncwarp();
         return bound_from_bins();
     };
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(32 * NW, FH_S2_MINB) k_stage2(const SeqDev *__
         int incl = nc;
         for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
         const int pos = nchunk + incl - nc;
-        for (int c = 0; c < nc; c++) w->chunk[pos + c] = (gbase + 8u * c) | ((uint32_t)(min(8, len - 8 * c) - 1) << 28);
+        for (int c = 0; c < nc; c++) w->chunk[FH_IDX(pos + c, S2_CHUNK_CAP)] = (gbase + 8u * c) | ((uint32_t)(min(8, len - 8 * c) - 1) << 28);
         nchunk += __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
         if (nchunk > S2_CHUNK_CAP - 256 || it0 + 32 >= nitems) {
@@ -357,8 +357,8 @@ __global__ void __launch_bounds__(32 * NW, FH_S2_MINB) k_stage2(const SeqDev *__
             const int dx = (int)((k >> 10) & 1023) - 279, dy = (int)(k & 1023) - 279;
             const uint32_t xy = ((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16);
             const int o = n2 + incl - cnt;
-            pool[o] = make_uint4(xy, feat, lb, k);
-            if (cnt == 2) pool[o + 1] = make_uint4(xy, feat, lb, k | (1u << 20));
+            pool[FH_IDX(o, S2_SLICE)] = make_uint4(xy, feat, lb, k);
+            if (cnt == 2) pool[FH_IDX(o + 1, S2_SLICE)] = make_uint4(xy, feat, lb, k | (1u << 20));
         }
         n2 += tot;
     }

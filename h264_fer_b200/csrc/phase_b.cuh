@@ -207,7 +207,7 @@ __device__ __forceinline__ int block_select_smallest(int n, int k, KeyFn keyfn, 
         const u64 key = keyfn(i);
         if (key <= thr) {
             const int pos = atomicAdd(nsp, 1);
-            if (pos < 256) { bs->skey[pos] = key; bs->sidx[pos] = (uint16_t)i; }
+            if (pos < 256) { bs->skey[FH_IDX(pos, 256)] = key; bs->sidx[pos] = (uint16_t)i; }
         }
     }
     __syncthreads();
@@ -786,7 +786,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
             const uint4 v = __ldg(&pool[i]);
             const int dx = (int16_t)(v.x & 0xffff), dy = (int16_t)(v.x >> 16);
             const uint32_t cost = (uint32_t)(iabs_(dx - genx) + iabs_(dy - geny) + 4) * v.y;
-            sh.keys2[i] = ((u64)cost << 32) | (u64)v.w;
+            sh.keys2[FH_IDX(i, 1024)] = ((u64)cost << 32) | (u64)v.w;
         }
         // stage 3 (:508-520): phase-A list, already in list order
         if (tid >= 64 && tid - 64 < (int)pa.n3) {
@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
                     uint32_t key = COST_INVALID;
                     if (rx >= 0 && rx < W && ry >= 0 && ry < H)
                         key = ((uint32_t)((iabs_(ox) + iabs_(oy) + 4) * feat_of(fq, qf_record(qx, qrc, fl, qps, w1, cx, cy))) << 11) | (uint32_t)i;
-                    sh.keys1[i] = key;
+                    sh.keys1[FH_IDX(i, S1_KEY_CAP)] = key;
                 }
             }
         }

@@ -168,7 +168,7 @@ __device__ __forceinline__ void qwin_select(const Geo &g, const QWinView &v, int
     if constexpr (W1 <= 5) {
         constexpr int NP = (16 * W1 + 31) / 32;
         int n = 0;
-        qwin_costs<W1>(g, v, xP, yP, Gx, Gy, fq, [&](uint32_t cst, uint32_t) { stage[n * 32 + lane] = cst; n++; tk_track(tk, cst); });
+        qwin_costs<W1>(g, v, xP, yP, Gx, Gy, fq, [&](uint32_t cst, uint32_t) { stage[FH_IDX(n * 32 + lane, QW_STAGE_WORDS)] = cst; n++; tk_track(tk, cst); });
         tk_tighten_exact_minima(tk);
         __syncwarp();
 #pragma unroll 1

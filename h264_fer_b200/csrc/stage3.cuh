@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t2; }
             int pos = nsv + incl - cnt;
-            while (mask) { const int b = __ffs(mask) - 1; mask &= mask - 1; sw->surv[pos++] = (uint16_t)(c * w3 + rb + b); }
+            while (mask) { const int b = __ffs(mask) - 1; mask &= mask - 1; sw->surv[FH_IDX(pos, S3_SURV_CAP)] = (uint16_t)(c * w3 + rb + b); pos++; }
             nsv += __shfl_sync(0xffffffffu, incl, 31);
         }
         for (int c = ncf; c < chi; c++) {                            // leftover columns (one at WindowSize 32): lane = row of the block
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
                 pass = lb <= tcost;
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (pass) sw->surv[nsv + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(c * w3 + r);
+            if (pass) sw->surv[FH_IDX(nsv + __popc(m & ((1u << lane) - 1u)), S3_SURV_CAP)] = (uint16_t)(c * w3 + r);
             nsv += __popc(m);
         }
         __syncwarp();

@@ -121,7 +121,7 @@ __device__ __forceinline__ void tk_append(u64 *b, TopK &t, uint32_t cost, uint32
     const bool sv = cost != TK_NONE && key <= t.bound;
     const unsigned m = __ballot_sync(0xffffffffu, sv);
     if (m) {
-        if (sv) b[t.ns + __popc(m & ((1u << lane) - 1u))] = key;
+        if (sv) b[FH_IDX(t.ns + __popc(m & ((1u << lane) - 1u)), t.cap)] = key;
         t.ns += __popc(m);
     }
 }
@@ -150,8 +150,8 @@ __device__ __forceinline__ int tk_finish(u64 *b, TopK &t, int nvalid, uint16_t *
         const u64 kb = hb ? b[s + 32] : 0ull;
         int ra = 0, rb = 0;
         for (int j = 0; j < ns; j++) { const u64 kj = b[j]; ra += kj < ka; rb += kj < kb; }
-        if (ra < K) members[ra] = (uint16_t)(ka & 0xffffu);
-        if (hb && rb < K) members[rb] = (uint16_t)(kb & 0xffffu);
+        if (ra < K) members[FH_IDX(ra, FH_S3_MAX + 1)] = (uint16_t)(ka & 0xffffu);
+        if (hb && rb < K) members[FH_IDX(rb, FH_S3_MAX + 1)] = (uint16_t)(kb & 0xffffu);
     }
     __syncwarp();
     return K;

@@ -48,6 +48,7 @@ struct Geo {
     int WH;
     // macroblock-row band of this rank (band mode): MBs [band_mb0, band_mb0 + band_nmb); whole picture otherwise
     int band_mb0, band_nmb, rank, world;
+    uint32_t wmb_magic;             // udiv_magic(Wmb): macroblock address -> (x, y) without a division routine in the kernels
 };
 #define FH_MAX_WORLD 8
 
@@ -159,6 +160,8 @@ __device__ __forceinline__ int sad_row8(uint2 cur, const uint8_t *plane, int W, 
 // Exact n / d by one IMAD.HI for n * d < 2^32: magic = 2^32 / d + 1; d == 1 has no 32-bit magic and is marked by 0.
 __host__ __device__ __forceinline__ uint32_t udiv_magic(uint32_t d) { return d > 1u ? 0xffffffffu / d + 1u : 0u; }
 __device__ __forceinline__ int udiv_by(int n, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)n, magic) : n; }
+
+__device__ __forceinline__ void mb_xy(const Geo &g, int mb, int &mbx, int &mby) { mby = udiv_by(mb, g.wmb_magic); mbx = mb - mby * g.Wmb; }
 
 // n / d for 0 <= n < 65536 / d with inv = 65536 / d + 1 (window geometry: d <= 129)
 __device__ __forceinline__ int fdiv_(int n, int inv) { return (int)(((unsigned)n * (unsigned)inv) >> 16); }

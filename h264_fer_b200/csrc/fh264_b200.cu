@@ -220,6 +220,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     g.tilesx = (width + FH_TILE - 1) / FH_TILE; g.tilesy = (height + FH_TILE - 1) / FH_TILE; g.ntiles = g.tilesx * g.tilesy;
     g.WH = width * height;
     g.band_mb0 = 0; g.band_nmb = g.nmb; g.rank = 0; g.world = 1;
+    g.wmb_magic = udiv_magic((uint32_t)g.Wmb);
     s->has_ref.assign(batch, 0);
     s->prev_p.assign(batch, 0);
     s->last_i.assign(batch, 0);
@@ -528,7 +529,8 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         const int g1 = prm.window / 16;
         const size_t smem3 = (size_t)s3_win_bytes(g1) + 16 + 4 * sizeof(S3WarpV2);
         dim3 g3d(g.band_nmb, nseq), g2d(g.band_nmb * 2, nseq);          // 4 / 2 partitions per CTA
-        k_stage3<<<g3d, 128, smem3, st>>>(s->d_seqs, seq0, g, prm, s->use_tma ? s->d_tmaps48 : nullptr);
+        const WinMagic wm = { udiv_magic((uint32_t)(2 * (prm.window / 2) + 1)), udiv_magic((uint32_t)(2 * g1 + 1)) };
+        k_stage3<<<g3d, 128, smem3, st>>>(s->d_seqs, seq0, g, prm, wm, s->use_tma ? s->d_tmaps48 : nullptr);
         CK(cudaEventRecord(s->evk[0], st));
         k_stage2<2><<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
@@ -537,7 +539,8 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
         // phase S: the search completed for the guessed integer predictors (spec.cuh)
         const int g1 = prm.window / 16;
         const size_t smems = 4 * (size_t)qwin_bytes(g1) + 4 * sizeof(SpecWarp) + 16;
-        k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, 1, s->use_tma ? s->d_tmaps : nullptr);
+        const WinMagic wm = { udiv_magic((uint32_t)(2 * (prm.window / 2) + 1)), udiv_magic((uint32_t)(2 * g1 + 1)) };
+        k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, 1, wm, s->use_tma ? s->d_tmaps : nullptr);
         k_skipspec<<<dim3((g.band_nmb + 3) / 4, nseq), 128, 4 * SKIPWIN_BYTES + 64, st>>>(s->d_seqs, seq0, g, prm, s->use_tma ? s->d_tmaps16 : nullptr);
         CKL();
     }

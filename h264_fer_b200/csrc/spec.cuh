@@ -23,7 +23,11 @@
 #include "phase_a.cuh"
 #include "qwin.cuh"
 #include "topk.cuh"
+#include "stage3.cuh"
 
+#ifndef FH_SPEC_MINB
+#define FH_SPEC_MINB 5
+#endif
 #define SPEC_NF 7
 #define SPEC_INVALID 0xffu
 #define SPEC_NOGUESS 0x7fff
@@ -68,11 +72,11 @@ __device__ __forceinline__ void pf_emit(bool have, int mvx, int mvy, int sad, in
 // The finalists of one partition for one guessed gen = (Gx, Gy) into out->f[slot]. Warp-uniform call.
 __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const fh264_params &prm, int part, int xP, int yP, const uint2 (&rows)[8],
                                           const FeatQ &fq, int n3, uint32_t n2w, uint32_t s2_off, int Gx, int Gy, int slot,
-                                          SpecWarp *sw, uint8_t *win, PartSpec *out, const CUtensorMap *tmap, uint32_t &phase)
+                                          SpecWarp *sw, uint8_t *win, PartSpec *out, const CUtensorMap *tmap, uint32_t &phase, const WinMagic &wm)
 {
     const int lane = threadIdx.x & 31, W = g.W, H = g.H;
     const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16;
-    const uint32_t i1 = udiv_magic((uint32_t)w1);
+    const uint32_t i1 = wm.i1;
     const int cxq = 4 * Gx, cyq = 4 * Gy;
     int npf = 0;
     bool usable = !(n2w & S2_SLOW);                        // oversized stage-2 set: phase B enumerates it itself
@@ -104,6 +108,7 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
         const int n2 = (int)n2w;
         const uint4 *__restrict__ pool = S.s2pool + s2_off;
         const uint2 cr8 = pick_row(rows, lane & 7);
+#pragma unroll 1
         for (int i0 = 0; i0 < n2; i0 += 32) {
             const int i = i0 + lane;
             bool pot = false; int dx = 0, dy = 0; uint32_t cst = 0, ak = 0;
@@ -121,6 +126,7 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
                 pm &= pm - 1;
                 const uint32_t ci = __shfl_sync(0xffffffffu, cst, src), ai = __shfl_sync(0xffffffffu, ak, src);
                 int c = 0;
+#pragma unroll 2
                 for (int j = lane; j < n2; j += 32) {
                     const uint4 w = __ldg(&pool[j]);
                     const int jx = (int16_t)(w.x & 0xffff), jy = (int16_t)(w.x >> 16);
@@ -237,7 +243,8 @@ __device__ __forceinline__ void proxy_mv(const SeqDev &S, int mb, int q, int &x,
 // vector for ~96 % of them, and the median absorbs a single wrong one.
 __device__ __forceinline__ void proxy_predictor(const SeqDev &S, const Geo &g, int mb, int pi, int &ox, int &oy)
 {
-    const int mbx = mb % g.Wmb, mby = mb / g.Wmb;
+    int mbx, mby;
+    mb_xy(g, mb, mbx, mby);
     const int aL = mbx > 0, aU = mby > 0, aUR = mby > 0 && mbx < g.Wmb - 1, aUL = mby > 0 && mbx > 0;
     int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0, aA = 1, aB = 1, aC = 1;
     if (pi == 0) {
@@ -264,7 +271,7 @@ __device__ __forceinline__ void proxy_predictor(const SeqDev &S, const Geo &g, i
 // One warp per partition, four per CTA (one macroblock). Guesses of gen = mvp >> 2: the predictor rule applied to the
 // neighbours' proxies (98.5 % right on the bench content), then the partition's own proxy (together 99.7 %); without stage-3
 // lists (BasicInterEncoding) the gen phase B used for this partition in the previous P picture, else zero.
-__global__ void __launch_bounds__(128, 5) k_spec(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int use_prev,
+__global__ void __launch_bounds__(128, FH_SPEC_MINB) k_spec(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, int use_prev, WinMagic wm,
                                                  const CUtensorMap *__restrict__ tmaps)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(128, 5) k_spec(const SeqDev *__restrict__ seqs
     }
     if (ng == 0) ng = 1;                                   // no list and no history: guess gen = (0, 0)
     for (int slot = 0; slot < ng; slot++)
-        spec_slot(S, g, prm, part, xP, yP, rows, fq, n3, n2w, s2_off, slot ? g1x : g0x, slot ? g1y : g0y, slot, sw, win, out, tmap, phase);
+        spec_slot(S, g, prm, part, xP, yP, rows, fq, n3, n2w, s2_off, slot ? g1x : g0x, slot ? g1y : g0y, slot, sw, win, out, tmap, phase, wm);
     if (ng == 1 && lane == 0) { out->gx[1] = SPEC_NOGUESS; out->gy[1] = SPEC_NOGUESS; out->nf[1] = SPEC_INVALID; }
 }
 
@@ -347,7 +354,9 @@ __global__ void __launch_bounds__(128) k_skipspec(const SeqDev *__restrict__ seq
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
     uint32_t phase = 0;
-    const int mbx = mb % g.Wmb, mby = mb / g.Wmb, W = g.W, H = g.H;
+    int mbx, mby;
+    mb_xy(g, mb, mbx, mby);
+    const int W = g.W, H = g.H;
     const int r = lane >> 1, hf = lane & 1;                       // this lane's 8 samples: row r, columns 8*hf ..
     const size_t own = (size_t)(mby * 16 + r) * W + mbx * 16 + 8 * hf;
     const uint2 c = __ldg((const uint2 *)(S.cur[0] + own));

@@ -18,11 +18,15 @@
 #include "qwin.cuh"
 #include "topk.cuh"
 
+#ifndef FH_S3_MINB
+#define FH_S3_MINB 5
+#endif
 #define S3_ROWB 48                       // bytes per staged row of the macroblock's window
 #define S3_SURV_CAP 288                  // first-call survivors of one block of rows (8 rows x 33 columns at WindowSize 32)
 __host__ __device__ __forceinline__ int s3_win_rows(int g1) { return 8 + 2 * g1 + 8 + 1; }          // R + 8, + 1: odd
 __host__ __device__ __forceinline__ int s3_win_bytes(int g1) { return 16 * s3_win_rows(g1) * S3_ROWB; }
 
+struct WinMagic { uint32_t i3, i1; };     // udiv_magic(2*(window/2)+1), udiv_magic(2*(window/16)+1), computed by the host
 struct __align__(16) S3WarpV2 {
     TopKBufT<320> tk;
     uint32_t stage[QW_STAGE_WORDS];      // the quarter-pel window's costs until the bound is known (qwin_select)
@@ -31,7 +35,7 @@ struct __align__(16) S3WarpV2 {
     uint16_t surv[S3_SURV_CAP];          // arrival indices of the first-call candidates that passed the sum bound
 };
 
-__global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, const CUtensorMap *__restrict__ tmaps48)
+__global__ void __launch_bounds__(128, FH_S3_MINB) k_stage3(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, WinMagic wm, const CUtensorMap *__restrict__ tmaps48)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];       // window (128-byte aligned) | mbarrier | 4 x S3WarpV2
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -45,7 +49,9 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
     const int mb = g.band_mb0 + blockIdx.x;
     const int part = mb * 4 + warp;
     const int W = g.W, H = g.H;
-    const int xM = (mb % g.Wmb) * 16, yM = (mb / g.Wmb) * 16;
+    int mbxM, mbyM;
+    mb_xy(g, mb, mbxM, mbyM);
+    const int xM = mbxM * 16, yM = mbyM * 16;
     // ---- the macroblock's quarter-pel window: pixels [xM - g1, xM - g1 + R + 8) x [yM - g1, yM - g1 + R + 8) of the 16 planes
     const int R = 8 + w1 - 1, rows = s3_win_rows(g1);
     const int wx0 = xM - g1, wy0 = yM - g1, wxa = wx0 & ~15;
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
     block_sums(crow, s);
     const FeatQ fq = feat_query(s);
     const int n3a = w3 * w3;
-    const uint32_t i3 = udiv_magic((uint32_t)w3), i1 = udiv_magic((uint32_t)w1);
+    const uint32_t i3 = wm.i3, i1 = wm.i1;
     const int rlo = max(0, g3 - yP), rhi = min(w3, H - yP + g3), clo = max(0, g3 - xP), chi = min(w3, W - xP + g3);
     const int nva = max(0, chi - clo) * max(0, rhi - rlo);
     const int nvb = max(0, min(W - 1, xP + g1) - max(0, xP - g1) + 1) * max(0, min(H - 1, yP + g1) - max(0, yP - g1) + 1) * 16;
@@ -94,6 +100,7 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
     // the bound tightens for the next block.
     const int RB = max(1, min(8, S3_SURV_CAP / w3));
     const int ncf = clo + ((chi - clo) & ~31);                    // columns [clo, ncf) in full groups of 32
+#pragma unroll 1
     for (int rb = rlo; rb < rhi; rb += RB) {
         const int re = min(rhi, rb + RB);
         const uint32_t tcost = (uint32_t)min(tk.bound >> 16, (u64)0xfffffffeu);
@@ -102,7 +109,7 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
             const int c = cb + lane, mx = iabs_(c - g3) + 4;
             const uint16_t *kp = k0p + (size_t)(yP - g3 + rb) * W + (xP - g3 + c);
             uint32_t mask = 0;
-#pragma unroll 8
+#pragma unroll 4
             for (int r = rb; r < re; r++, kp += W) {
                 const uint32_t lb = (uint32_t)((mx + iabs_(r - g3)) * iabs_(s[0] - (int)__ldg(kp)));
                 mask |= (uint32_t)(lb <= tcost) << (r - rb);
@@ -128,6 +135,7 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
             nsv += __popc(m);
         }
         __syncwarp();
+#pragma unroll 1
         for (int i0 = 0; i0 < nsv; i0 += 32) {
             const int i = i0 + lane;
             uint32_t cst = TK_NONE, idx = 0;
@@ -147,6 +155,7 @@ __global__ void __launch_bounds__(128, 5) k_stage3(const SeqDev *__restrict__ se
     //      staged window (their block lies inside it; same clamping as the reference for an origin inside the picture).
     const int r8 = lane & 7;
     const uint2 cr = pick_row(crow, r8);
+#pragma unroll 1
     for (int base = 0; base < nm; base += 4 * FH_S3_SADR) {
         uint2 rr[FH_S3_SADR];
 #pragma unroll

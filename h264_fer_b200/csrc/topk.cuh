@@ -31,6 +31,7 @@ __device__ __forceinline__ int tk_count_le(const u64 *b, int ns, u64 x)
 {
     const int lane = threadIdx.x & 31;
     int c = 0;
+#pragma unroll 1
     for (int i = lane; i < ns; i += 32) c += b[i] <= x;
     return __reduce_add_sync(0xffffffffu, c);
 }
@@ -39,6 +40,7 @@ __device__ __noinline__ int tk_filter_ni(u64 *b, int ns, u64 x)
 {
     const int lane = threadIdx.x & 31;
     int outn = 0;
+#pragma unroll 1
     for (int base = 0; base < ns; base += 32) {
         const int i = base + lane;
         const u64 kv = i < ns ? b[i] : ~0ull;
@@ -149,6 +151,7 @@ __device__ __forceinline__ int tk_finish(u64 *b, TopK &t, int nvalid, uint16_t *
         const bool hb = s + 32 < ns;
         const u64 kb = hb ? b[s + 32] : 0ull;
         int ra = 0, rb = 0;
+#pragma unroll 2
         for (int j = 0; j < ns; j++) { const u64 kj = b[j]; ra += kj < ka; rb += kj < kb; }
         if (ra < K) members[FH_IDX(ra, FH_S3_MAX + 1)] = (uint16_t)(ka & 0xffffu);
         if (hb && rb < K) members[FH_IDX(rb, FH_S3_MAX + 1)] = (uint16_t)(kb & 0xffffu);

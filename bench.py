@@ -37,7 +37,8 @@ CLIP_LEN = 6                          # distinct pictures per sequence (set per 
 CLIP_MAX = 40
 ALG_BYTES_PER_MB = 1984               # 384 src + 384 ref + 384 recon + 768 levels + 64 metadata
 ALG_INTOPS_PER_MB = 0.43e6
-LAUNCHES_PER_STEP = 16                # own kernels per step and group: scene SAD 3 + swap 1, begin, stage 3, stage 2, phase S 2, B, C, dpb swap, phase R 4
+LAUNCHES_PER_STEP = 15                # own kernels per step and group: source swap, begin, scene SAD, scene gate, stage 3, stage 2, phase S 2, B, C,
+                                      # begin-ref, dpb swap, phase R 3 (the e2e step adds the 4 entropy-coding kernels; --pipeline: two halves of 16)
 # The same 0.43 M lane-ops per macroblock split over the kernels that do them (SURVEY.md §8d's per-stage counts; 4 partitions
 # per macroblock, 40 ops per feature-cost evaluation, 32 packed-byte ops per 8x8 SAD):
 #   stage 3: 1,475 evaluations + 33 SADs; stage 1 (phase S): 400 evaluations + 17 SADs; stage 2: ~100 evaluations + 32 SADs;
@@ -255,6 +256,7 @@ def main():
     ap.add_argument("--seqs", type=int, default=8, help="independent sequences per GPU")
     ap.add_argument("--groups", type=int, default=1, help="sequence groups per GPU (session + stream + host thread each)")
     ap.add_argument("--threaded", action="store_true", help="drive even a single group from a worker thread")
+    ap.add_argument("--pipeline", action="store_true", help="software-pipeline the two halves of every step (fh264_set_pipeline; measured: no gain, profiles/r02_pipeline.md)")
     ap.add_argument("--mode", default="sequences", choices=["sequences", "bands"],
                     help="sequences: independent sequences per GPU (weak scaling, the headline); bands: ONE 1080p sequence split into MB-row bands over all GPUs (BASELINE config 4, strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -270,7 +272,7 @@ def main():
     import torch.distributed as dist
     import h264_fer_b200 as fh
     from h264_fer_b200 import sharding
-    from h264_fer_b200.native import PinnedArray
+    from h264_fer_b200.native import PinnedArray, StreamOut, ST_GATED_TOTAL
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -293,59 +295,68 @@ def main():
     ysz, csz = WIDTH * H, WIDTH * H // 4
     master = torch.cuda.current_stream()
 
+    SLICE_COPY = 65536        # bytes of slice data per sequence and step that come home (a 1080p P slice at QP 28 is ~21 KB)
+    pic = ysz + 2 * csz
+
     class Group:
-        """A slice of the GPU's sequences driven like one reference process: its own session, CUDA stream and host thread
-        (the reference is one sequence per process; here a group advances its sequences in lockstep)."""
+        """A slice of the GPU's sequences driven through one session (the reference is one sequence per process; here a group
+        advances its sequences in lockstep). One step = fh264_upload_source_batch + fh264_encode_p_stream: no host round trip."""
 
         def __init__(self, seq_ids):
             self.ids = seq_ids
             self.n = len(seq_ids)
-            self.pinned = [[PinnedArray((ysz + 2 * csz,), np.uint8) for _ in range(CLIP_LEN)] for _ in seq_ids]
-            for j, b in enumerate(seq_ids):
-                for t in range(CLIP_LEN):
-                    a = self.pinned[j][t].array
-                    a[:ysz] = clips[b][t][0].ravel(); a[ysz:ysz + csz] = clips[b][t][1].ravel(); a[ysz + csz:] = clips[b][t][2].ravel()
-            self.dev = [[torch.from_numpy(self.pinned[j][t].array.copy()).cuda() for t in range(CLIP_LEN)] for j in range(self.n)]
+            self.pinned = [PinnedArray((self.n, pic), np.uint8) for _ in range(CLIP_LEN)]      # picture t of every sequence: one block
+            for t in range(CLIP_LEN):
+                a = self.pinned[t].array
+                for j, b in enumerate(seq_ids):
+                    a[j, :ysz] = clips[b][t][0].ravel(); a[j, ysz:ysz + csz] = clips[b][t][1].ravel(); a[j, ysz + csz:] = clips[b][t][2].ravel()
+            self.dev = [torch.from_numpy(self.pinned[t].array.copy()).cuda() for t in range(CLIP_LEN)]
             self.results = PinnedArray((self.n, nmb), fh.MB_RESULT_DTYPE)
             self.s = fh.Session(WIDTH, H, batch=self.n, device=local)
             self.stream = torch.cuda.Stream()
             self.s.set_stream(self.stream.cuda_stream)
-            self.idr = 0
+            # what a step sends home: "dev" the status words only; "host" the entropy-coded slice data + 32 B/MB side information
+            # (what the reference's host code needs to write the NAL unit); "records" the 832-byte macroblock records instead
+            self.outs = {"dev": StreamOut(self.n, nmb), "host": StreamOut(self.n, nmb, slice_bytes=SLICE_COPY, mb_info=True),
+                         "records": StreamOut(self.n, nmb, records=True)}
             self.t = 1
 
-        def reset(self, host=False):
+        def reset(self, mode="dev"):
+            self.s.set_pipeline(1 if args.pipeline else 0)
             for j, b in enumerate(self.ids):
                 self.s.upload_recon(j, *clips[b][0])
             self.s.sync()
             self.t = 1
-            self.upload(host)                                    # prime: the first picture to code
+            self.upload(mode)                                    # prime: the first picture to code
             self.s.sync()
 
-        def upload(self, host):
-            """Hands the next picture of every sequence to the library (pinned H2D when host, else D2D): the copy runs on the
-            library's upload stream into the source buffer that is not being coded."""
+        def upload(self, mode):
+            """Hands the next picture of every sequence to the library in one call (pinned H2D, or D2D for "dev"): the copies run on
+            the library's upload stream into the source buffers that are not being coded."""
             k = pingpong(self.t, CLIP_LEN)
             self.t += 1
-            for j in range(self.n):
-                p = self.pinned[j][k].ptr if host else self.dev[j][k].data_ptr()
-                self.s.upload_source_ptrs(j, p, p + ysz, p + ysz + csz, device=not host)
+            if mode == "dev":
+                self.s.upload_source_batch(self.dev[k].data_ptr(), pic, device=True)
+            else:
+                self.s.upload_source_batch(self.pinned[k].ptr, pic)
 
-        def code(self, host):
-            sads = self.s.scene_sad_batch()                      # selectNALUnitType's measure (ref_frames.cpp:210-224)
-            self.idr += sum(1 for v in sads if v > (nmb << 12))
-            self.s.encode_p(QP, WINDOW, MAXDIFF, 0, out=self.results.array, sync=False, download=host)
+        def step(self, mode):
+            """One step = code the picture uploaded last — IDR decision on the device (selectNALUnitType's scene-change rule,
+            ref_frames.cpp:210-224), phases A / B / C, entropy coding when the slice data goes home, dpb swap, phase R — then
+            upload the next one (its H2D overlaps this picture's coding)."""
+            self.s.encode_p_stream(QP, WINDOW, MAXDIFF, 0, scene_gate=True, out=self.outs[mode])
+            self.upload(mode)
 
-        def step(self, host):
-            """One step = code the picture uploaded last, then upload the next one (its H2D overlaps this picture's coding;
-            every step still moves one picture per sequence in and one set of records out)."""
-            self.code(host)
-            self.upload(host)
+        def gated_total(self):
+            st = self.outs["dev"].status.array
+            return int(sum(int(st[j, ST_GATED_TOTAL]) for j in range(self.n)))
 
     groups = [Group(list(range(B))[i::G]) for i in range(G)]
 
-    def timed(host):
+    def timed(mode):
+        host = mode != "dev"
         for gr in groups:
-            gr.reset(host)
+            gr.reset(mode)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ends = [torch.cuda.Event() for _ in groups]
         bar_warm, bar_go = threading.Barrier(G + 1), threading.Barrier(G + 1)
@@ -355,15 +366,14 @@ def main():
             try:
                 torch.cuda.set_device(local)
                 for _ in range(Wu):
-                    gr.step(host)
+                    gr.step(mode)
                 gr.s.sync()
                 bar_warm.wait()
                 bar_go.wait()
                 gr.stream.wait_event(e0)                         # the timed region starts at e0 on every group stream
                 for _ in range(K):
-                    gr.step(host)
-                if host:
-                    gr.s.sync()                                  # the last records' D2H (library copy stream) is inside the timed region
+                    gr.step(mode)
+                gr.s.sync()                                      # everything of the last step is done / home inside the timed region
                 ev.record(gr.stream)
             except Exception as ex:       # surfaced by the main thread
                 errors.append(ex)
@@ -378,7 +388,7 @@ def main():
             th.start()
         if inline:
             for _ in range(Wu):
-                groups[0].step(host)
+                groups[0].step(mode)
             groups[0].s.sync()
         else:
             bar_warm.wait()
@@ -392,9 +402,8 @@ def main():
         if inline:
             groups[0].stream.wait_event(e0)
             for _ in range(K):
-                groups[0].step(host)
-            if host:
-                groups[0].s.sync()                               # the last records' D2H (library copy stream) is inside the timed region
+                groups[0].step(mode)
+            groups[0].s.sync()                                   # the pipeline lanes and the last copies home are inside the timed region
             ends[0].record(groups[0].stream)
         else:
             bar_go.wait()
@@ -415,46 +424,22 @@ def main():
                 gr.s.picture_status(j)
         return ms, clocks
 
-    ms_dev, clocks = timed(host=False)
-    ms_e2e, clocks_e2e = timed(host=True)
-    idr_decisions = sum(sum(v) for v in sharding.gather_counts([gr.idr for gr in groups]))      # scene-change IDR decisions of all ranks
-
-    # device CAVLC line item: the same end-to-end step, but what comes back per picture is the coded
-    # slice data + 32 B/MB of side information instead of the 832-byte records. Reported beside the headline, not in it.
-    cavlc = None
-    if not args.no_cavlc and G == 1:
-        g0 = groups[0]
-        g0.reset(True)
-        slice_out = PinnedArray((g0.n, 500064), np.uint8)
-        info_out = PinnedArray((g0.n, nmb), fh.CAVLC_MB_INFO_DTYPE)
-        nbits = np.zeros(g0.n, np.uint32)
-
-        def cavlc_step():
-            g0.s.scene_sad_batch()
-            g0.s.encode_p(QP, WINDOW, MAXDIFF, 0, out=g0.results.array, sync=False, download=False)
-            g0.upload(True)
-            t0 = time.perf_counter()
-            g0.s._ck(g0.s.L.fh264_cavlc_p(g0.s.handle, 0, g0.n, 0, slice_out.ptr, 500064, nbits.ctypes.data, info_out.ptr))
-            return time.perf_counter() - t0
-
-        for _ in range(Wu):
-            cavlc_step()
-        torch.cuda.synchronize()
-        ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ec0.record(g0.stream)
-        calls = [cavlc_step() for _ in range(K)]
-        ec1.record(g0.stream)
-        torch.cuda.synchronize()
-        ms_c = ec0.elapsed_time(ec1)
-        t0 = time.perf_counter()                            # the picture is finished: this call is the entropy coding alone
-        g0.s._ck(g0.s.L.fh264_cavlc_p(g0.s.handle, 0, g0.n, 0, slice_out.ptr, 500064, nbits.ctypes.data, info_out.ptr))
-        cavlc_alone_ms = 1000.0 * (time.perf_counter() - t0)
-        cavlc = {"e2e_value": g0.n * K / (ms_c / 1000.0), "unit": "frames/s (this GPU)", "ms_per_step": ms_c / K,
-                 "cavlc_call_ms": 1000.0 * sum(calls) / len(calls), "cavlc_alone_ms": cavlc_alone_ms,
-                 "slice_bytes_per_step": int(sum((int(b) + 7) // 8 for b in nbits)), "d2h_bytes_per_step": int(sum((int(b) + 7) // 8 for b in nbits)) + g0.n * nmb * 32,
-                 "note": "fh264_cavlc_p after every encode_p: 4 kernels (prep, code, scan, pack) + D2H of the slice data and 32 B/MB side information; "
-                         "the call waits for the picture (no record D2H); cavlc_call_ms includes that wait, cavlc_alone_ms is a repeat call on the finished "
-                         "pictures (kernels + copies + two stream syncs, host wall clock)"}
+    ms_dev, clocks = timed("dev")
+    idr_decisions = sum(sum(v) for v in sharding.gather_counts([gr.gated_total() for gr in groups]))      # pictures the device-side scene gate stopped, all ranks
+    ms_e2e, clocks_e2e = timed("host")
+    g0 = groups[0]
+    slice_bits = [int(g0.outs["host"].slice_stat.array[j, 1]) for j in range(g0.n)]
+    slice_flags = [int(g0.outs["host"].slice_stat.array[j, 0]) for j in range(g0.n)]
+    if any(slice_flags) or max(slice_bits) > 8 * SLICE_COPY or min(slice_bits) <= 0:
+        raise SystemExit("device CAVLC: flags %s, bits %s (copy bound %d bytes)" % (slice_flags, slice_bits, SLICE_COPY))
+    # the record path (832 B per macroblock home instead of the slice data): line item beside the headline
+    ms_rec, _ = timed("records") if not args.no_cavlc else (None, None)
+    cavlc = {"slice_bytes_last_step_group0": int(sum((b + 7) // 8 for b in slice_bits)),
+             "note": "e2e returns what the reference's host code needs to write the slice NAL unit: the entropy-coded slice data (device CAVLC, "
+                     "cavlc.cuh; %d bytes per sequence copied home) + 32 B/MB side information + the status words; e2e_records returns the 832-byte "
+                     "macroblock records instead (host-side entropy coding)" % SLICE_COPY}
+    if ms_rec is not None:
+        cavlc["e2e_records"] = {"value": B * world * K / (ms_rec / 1000.0), "unit": "frames/s", "ms_per_step": ms_rec / K, "d2h_bytes_per_step": B * nmb * 832 + B * 96}
 
     # device I-picture line item: every sequence of group 0 codes its current source picture as an IDR
     # picture on the device (fh264_encode_i: intra mode searches, both CAVLC bit-cost trials, TQ, reconstruction, then phase R),
@@ -468,7 +453,7 @@ def main():
             g0.t = 1 + it
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            g0.upload(True)
+            g0.upload("host")
             g0.s._ck(g0.s.L.fh264_encode_i(g0.s.handle, 0, g0.n, QP, i_out.ptr))
             if it:
                 call_ms.append(1000.0 * (time.perf_counter() - t0))
@@ -483,9 +468,11 @@ def main():
     # per-kernel device times (CUDA events inside the library, on the launching stream): group 0 alone, a few steps
     g0 = groups[0]
     g0.reset()
+    g0.s.set_pipeline(0)              # the per-kernel split is measured unpipelined: every kernel alone on the GPU, all sequences per launch
     acc, nsamp = {}, 0
     for i in range(3 + 4):
-        g0.step(False)
+        g0.s.encode_p(QP, WINDOW, MAXDIFF, 0, sync=False, download=False)
+        g0.upload("dev")
         tm = g0.s.last_timings()
         if i >= 3:
             for k_, v in tm.items():
@@ -527,8 +514,9 @@ def main():
             "n_gpus": world, "steps": K, "warmup": Wu, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic", "config": workload_config(args, B * world),
             "macroblocks_per_s": value * nmb,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * (ysz + 2 * csz), "d2h_bytes_per_step": B * nmb * 832 + B * 8,
-                    "ms_per_step": ms_e2e / K},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * (ysz + 2 * csz), "d2h_bytes_per_step": B * (SLICE_COPY + nmb * 32 + 8 + 96),
+                    "ms_per_step": ms_e2e / K,
+                    "returns": "device-CAVLC slice data + 32 B/MB side information + status words (see device_cavlc)"},
             "gpu_launches": LAUNCHES_PER_STEP * K * G,
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "roofline": {"bound": "int", "kernel": dom, "achieved": dom_tops, "peak": ipk, "unit": "T int-lane-op/s", "frac": dom_tops / ipk,

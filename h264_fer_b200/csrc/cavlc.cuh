@@ -30,6 +30,10 @@ __global__ void __launch_bounds__(128) k_cavlc_prep(const SeqDev *__restrict__ s
 {
     const int mb = blockIdx.x * 128 + threadIdx.x;
     if (mb >= nmb) return;
+    if (seqs[seq0 + blockIdx.y].status[ST_GATE_DONE]) {            // scene cut: no P picture was coded (empty slice data)
+        if (mb == 0) { cvs[seq0 + blockIdx.y].stat[0] = 0; cvs[seq0 + blockIdx.y].stat[1] = 0; }
+        return;
+    }
     const fh264_mb_result &r = seqs[seq0 + blockIdx.y].results[mb];
     CvInfo o;
     cv_prepare(r.mb_type, r.luma, r.chroma_dc, r.chroma_ac, FH264_P_SKIP, o);
@@ -42,6 +46,7 @@ __global__ void __launch_bounds__(128) k_cavlc_code(const SeqDev *__restrict__ s
     const int mb = blockIdx.x * 128 + threadIdx.x;
     if (mb > nmb) return;
     const CvSeq &cv = cvs[seq0 + blockIdx.y];
+    if (seqs[seq0 + blockIdx.y].status[ST_GATE_DONE]) { cv.bits[mb] = 0; return; }
     // mb_skip_run: the skipped macroblocks right before this one (rbsp_encoding.cpp:181-188); slot nmb = the run that ends the slice (:310)
     // (only a macroblock that writes something walks back, so every skipped macroblock is visited once per picture)
     int run = 0;

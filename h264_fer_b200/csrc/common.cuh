@@ -38,7 +38,12 @@ __device__ __forceinline__ int fh_idx_(int i, int n, int line) { if ((unsigned)i
 #define ST_S2REDO 12       // number of partitions that overflowed the fast stage-2 launch
 #define ST_SPEC_HIT 13     // partitions decided from the speculative finalists (spec.cuh)
 #define ST_SPEC_MISS 14    // partitions that took the full search inside the wavefront
-#define ST_WORDS 16
+#define ST_GATE 16         // scene-change gate of the picture being coded (fh264_encode_p_stream): 1 = sum |cur - dpb| above the IDR threshold
+                           // (ref_frames.cpp:210-224) -> every P kernel leaves this sequence alone; 0 otherwise
+#define ST_GATE_DONE 17    // the gate as phase C saw it (read by the entropy coder and the status snapshot; the next picture's phase C rewrites it)
+#define ST_GATED_TOTAL 18  // pictures of this sequence the gate has stopped since the session was opened
+#define ST_NSLOW 19        // partitions of the picture whose stage-2 set phase A could not store (S2_SLOW): the picture takes the block-level phase B
+#define ST_WORDS 24
 #define FLAG_UB_INPUT 1u
 #define FLAG_CAPACITY 2u
 #define FLAG_TIMEOUT 4u      // a bounded wavefront / cross-GPU wait gave up (peer rank missing or far behind)

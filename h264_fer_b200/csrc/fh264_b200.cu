@@ -13,6 +13,7 @@
 #include "phase_a.cuh"
 #include "stage3.cuh"
 #include "phase_b.cuh"
+#include "phase_bw.cuh"
 #include "phase_c.cuh"
 #include "cavlc.cuh"
 #include "intra.cuh"
@@ -35,6 +36,25 @@ struct PeerSync { uint32_t *p[FH_MAX_WORLD]; };
 
 struct fh264_session;
 static cudaError_t sync_streams(fh264_session *s);
+static int enter_main(fh264_session *s);
+
+// A coding lane: the streams and events one half of a call's sequences is enqueued on. Lane 2 (`main`) is the session stream
+// itself and codes a whole call the plain way. Lanes 0 / 1 are the software pipeline of fh264_encode_p_stream and of
+// fh264_encode_p_async with FH264_PIPE=1: the call's sequences are split into two halves, each half on its own stream, phase B
+// (a latency-bound wavefront that leaves most of the SMs idle) on a high-priority side stream, and the second half's phase A is
+// held back until the first half's is through — so one half's wavefront always runs under the other half's search kernels, within
+// a call and across consecutive calls (nothing on a lane waits for the other lane's picture to finish).
+struct Lane {
+    cudaStream_t st, hi, cp;        // coding stream; phase B stream (null: phase B on st); copies home
+    cudaEvent_t ev_a, ev_b;         // phase A (+ S) enqueued work done; phase B done
+    cudaEvent_t ev_c_done, ev_copy_done, ev_done;
+    bool copy_pending;              // records / slice data of the lane's last picture still travelling (phase C of the next must wait)
+    bool busy;                      // work enqueued since the last join with the session stream
+    uint32_t *d_ticket;             // phase B ticket counter
+    bool timing;                    // records the per-phase timing events (fh264_last_timings)
+    cudaEvent_t tr[8][5];           // FH264_TRACE=1: timing events of the last 8 pictures (phase A start / end, phase B end, phase C end, phase R end)
+    int tr_n;
+};
 
 struct fh264_session {
     Geo g;
@@ -42,8 +62,10 @@ struct fh264_session {
     cudaStream_t stream;
     bool own_stream;
     cudaStream_t copy_stream;       // result records go home on their own stream, overlapping phase R and the next picture
-    cudaEvent_t ev_c_done, ev_copy_done;
-    bool copy_pending;
+    Lane lane[3];                   // [2] = the session stream (plain calls); [0], [1] = pipeline halves
+    int pipeline;                   // 1: fh264_encode_p_async splits its sequences over lanes 0 / 1 (FH264_PIPE, fh264_set_pipeline)
+    cudaEvent_t ev_fork;
+    bool main_dirty;                // work enqueued on the session stream since the lanes last forked from it
     // double-buffered source pictures: uploads run on their own stream into the buffer that is not being coded
     cudaStream_t up_stream;
     std::vector<cudaEvent_t> ev_up;                 // per sequence: upload complete
@@ -66,6 +88,9 @@ struct fh264_session {
     CUtensorMap *d_tmaps, *d_tmaps16, *d_tmaps48;   // d_tmaps16: box of 16 rows (P_Skip trials of phase S); d_tmaps48: 48-byte rows (stage 3)
     int tmap_rows;
     int use_tma;                    // FH264_TMA=0: fill the pixel windows with ordinary loads (development knob)
+    int use_bw;                     // phase B kernel: 1 warp-level (phase_bw.cuh), 0 block-level, -1 (default) warp-level on the pipeline lanes only (FH264_PBW)
+    int trace;                      // FH264_TRACE=1: per-lane timing events (fh264_debug_trace)
+    int force_miss;                 // FH264_PBW_FORCE_MISS=1: the warp-level phase B treats every phase-S lookup as a miss (test knob)
     bool timed;
     std::vector<void *> allocs;
     // scratch for the stand-alone entry points
@@ -87,15 +112,23 @@ struct fh264_session {
     int *d_prev_p;                  // per sequence: the previous picture was a P picture whose records are in `results`
     std::vector<int> prev_p;
     std::vector<char> last_i;       // per sequence: `results` holds the I records of the picture coded last
+    // scene gate (fh264_encode_p_stream): whether a gated call really coded a P picture is known only once its status is home.
+    // Until then: the state before the first unresolved gated call, how many such calls were issued, and the sequence's
+    // ST_GATED_TOTAL at that point (resolved in sync_streams).
+    std::vector<int> gate_calls, saved_prev_p;
+    std::vector<char> saved_last_i;
+    std::vector<uint32_t> gated_seen;
 };
 
 __global__ void k_begin_picture(SeqDev *seqs, int seq0, uint32_t *ticket)
 {
     uint32_t *st = seqs[seq0 + threadIdx.x].status;
     st[ST_FLAGS] = st[ST_FLAGS_NEXT];
+    st[ST_GATE] = 0; st[ST_SAD_LO] = 0; st[ST_SAD_HI] = 0;             // (the scene gate of fh264_encode_p_stream accumulates and decides after this)
     for (int i = 0; i < 5; i++) st[ST_COUNTS + i] = 0;
     st[ST_S2REDO] = 0; st[ST_SPEC_HIT] = 0; st[ST_SPEC_MISS] = 0;
-    if (threadIdx.x == 0) *ticket = 0;
+    st[ST_NSLOW] = 0;
+    if (threadIdx.x == 0) { ticket[0] = 0; ticket[1] = 0; }
 }
 __global__ void k_begin_ref(SeqDev *seqs, int seq0) { seqs[seq0 + threadIdx.x].status[ST_FLAGS_NEXT] = 0; }
 __global__ void k_zero_sad(SeqDev *seqs, int seq0) { uint32_t *st = seqs[seq0 + threadIdx.x].status; st[ST_SAD_LO] = 0; st[ST_SAD_HI] = 0; }
@@ -129,8 +162,25 @@ __global__ void k_band_barrier(PeerSync ps, SeqDev *seqs, int seq0, int nseq, ui
 static cudaError_t sync_streams(fh264_session *s)
 {
     cudaError_t e = cudaStreamSynchronize(s->stream);
+    for (int l = 0; l < 2 && e == cudaSuccess; l++) {
+        Lane &L = s->lane[l];
+        if (L.st) e = cudaStreamSynchronize(L.st);
+        if (e == cudaSuccess && L.hi) e = cudaStreamSynchronize(L.hi);
+        if (e == cudaSuccess && L.cp) e = cudaStreamSynchronize(L.cp);
+        L.busy = false; L.copy_pending = false;
+    }
     if (e == cudaSuccess && s->copy_stream) e = cudaStreamSynchronize(s->copy_stream);
     if (e == cudaSuccess && s->up_stream) e = cudaStreamSynchronize(s->up_stream);
+    if (e == cudaSuccess) s->lane[2].copy_pending = false;
+    if (e == cudaSuccess)
+        for (int b = 0; b < s->batch; b++) {
+            if (!s->gate_calls[b]) continue;
+            const uint32_t *st = s->h_status + (size_t)b * ST_WORDS;
+            // the records are P records unless every call since the last resolve was stopped by the gate
+            if (st[ST_GATE_DONE] && st[ST_GATED_TOTAL] - s->gated_seen[b] == (uint32_t)s->gate_calls[b]) { s->prev_p[b] = s->saved_prev_p[b]; s->last_i[b] = s->saved_last_i[b]; }
+            s->gated_seen[b] = st[ST_GATED_TOTAL];
+            s->gate_calls[b] = 0;
+        }
     return e;
 }
 
@@ -177,8 +227,13 @@ extern "C" int fh264_close(fh264_session *s)
     if (s->up_stream) cudaStreamDestroy(s->up_stream);
     for (auto e : s->ev_up) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) for (auto e : s->ev_free[k]) cudaEventDestroy(e);
-    if (s->ev_c_done) cudaEventDestroy(s->ev_c_done);
-    if (s->ev_copy_done) cudaEventDestroy(s->ev_copy_done);
+    for (int l = 0; l < 3; l++) {
+        Lane &L = s->lane[l];
+        if (l < 2) { if (L.st) cudaStreamDestroy(L.st); if (L.hi) cudaStreamDestroy(L.hi); if (L.cp) cudaStreamDestroy(L.cp); }
+        cudaEvent_t *evs[5] = { &L.ev_a, &L.ev_b, &L.ev_c_done, &L.ev_copy_done, &L.ev_done };
+        for (auto e : evs) if (*e) cudaEventDestroy(*e);
+    }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     delete s;
     return FH264_OK;
 }
@@ -203,7 +258,10 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->batch = batch; s->device = device; s->epoch = 0; s->timed = false; s->own_stream = true;
     s->d_sync = nullptr; memset(&s->peer_sync, 0, sizeof s->peer_sync);
     s->up_stream = nullptr;
-    s->copy_stream = nullptr; s->ev_c_done = nullptr; s->ev_copy_done = nullptr; s->copy_pending = false;
+    s->copy_stream = nullptr;
+    memset(s->lane, 0, sizeof s->lane);
+    s->ev_fork = nullptr; s->main_dirty = true;
+    { const char *e = getenv("FH264_PIPE"); s->pipeline = (e && atoi(e) == 1) ? 1 : 0; }
     s->d_cvs = nullptr; s->h_cvstat = nullptr;
     s->d_is = nullptr; s->d_prev_p = nullptr; s->d_iwf_order = nullptr; s->ev_i[0] = s->ev_i[1] = nullptr; s->intra_timed = false;
     s->d_seqs = nullptr; s->h_status = nullptr; s->h_sad = nullptr; s->d_sadout = nullptr; s->scr_mbs = 0;
@@ -212,6 +270,9 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->ev_spec = nullptr;
     { const char *e = getenv("FH264_SPEC"); s->use_spec = !(e && atoi(e) == 0); }
     { const char *e = getenv("FH264_TMA"); s->use_tma = !(e && atoi(e) == 0); }
+    { const char *e = getenv("FH264_PBW"); s->use_bw = e ? atoi(e) : -1; }       // -1: warp-level phase B on the pipeline lanes only
+    { const char *e = getenv("FH264_TRACE"); s->trace = (e && atoi(e) == 1) ? 1 : 0; }
+    { const char *e = getenv("FH264_PBW_FORCE_MISS"); s->force_miss = (e && atoi(e) == 1) ? 1 : 0; }
     s->d_tmaps = nullptr; s->d_tmaps16 = nullptr; s->d_tmaps48 = nullptr; s->tmap_rows = 0;
     for (int i = 0; i < 3; i++) s->d_scr[i] = nullptr;
     s->d_scr16[0] = s->d_scr16[1] = nullptr;
@@ -224,6 +285,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     s->has_ref.assign(batch, 0);
     s->prev_p.assign(batch, 0);
     s->last_i.assign(batch, 0);
+    s->gate_calls.assign(batch, 0); s->saved_prev_p.assign(batch, 0); s->saved_last_i.assign(batch, 0); s->gated_seen.assign(batch, 0);
     s->h.resize(batch);
 #define OPEN_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(FH264_E_CUDA, #call, e_); fh264_close(s); return FH264_E_CUDA; } } while (0)
     OPEN_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -235,8 +297,24 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         OPEN_CK(cudaEventCreateWithFlags(&s->ev_up[b], cudaEventDisableTiming));
         for (int k = 0; k < 2; k++) OPEN_CK(cudaEventCreateWithFlags(&s->ev_free[k][b], cudaEventDisableTiming));
     }
-    OPEN_CK(cudaEventCreateWithFlags(&s->ev_c_done, cudaEventDisableTiming));
-    OPEN_CK(cudaEventCreateWithFlags(&s->ev_copy_done, cudaEventDisableTiming));
+    {
+        int prio_lo = 0, prio_hi = 0;
+        OPEN_CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));           // (numerically lower = higher priority)
+        for (int l = 0; l < 3; l++) {
+            Lane &L = s->lane[l];
+            if (l < 2) {
+                OPEN_CK(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, prio_lo));
+                OPEN_CK(cudaStreamCreateWithPriority(&L.hi, cudaStreamNonBlocking, prio_hi));
+                OPEN_CK(cudaStreamCreateWithFlags(&L.cp, cudaStreamNonBlocking));
+            } else { L.st = s->stream; L.hi = nullptr; L.cp = s->copy_stream; }
+            cudaEvent_t *evs[5] = { &L.ev_a, &L.ev_b, &L.ev_c_done, &L.ev_copy_done, &L.ev_done };
+            for (auto e : evs) OPEN_CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+            L.copy_pending = false; L.busy = false; L.timing = l == 2;
+            L.tr_n = 0;
+            if (s->trace) for (int i = 0; i < 8; i++) for (int k = 0; k < 5; k++) OPEN_CK(cudaEventCreate(&L.tr[i][k]));
+        }
+        OPEN_CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    }
     for (int i = 0; i < 5; i++) OPEN_CK(cudaEventCreate(&s->ev[i]));
     for (int i = 0; i < 4; i++) OPEN_CK(cudaEventCreate(&s->evk[i]));
     OPEN_CK(cudaEventCreate(&s->ev_spec));
@@ -247,11 +325,16 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     const size_t WH = (size_t)g.WH, CWH = WH / 4;
     fh264_mb_result *results = nullptr;
     OPEN_CK(dalloc(s, &results, (size_t)batch * g.nmb));
+    uint32_t *status_block = nullptr;
+    OPEN_CK(dalloc(s, &status_block, (size_t)batch * ST_WORDS));
     for (int b = 0; b < batch; b++) {
         SeqDev &S = s->h[b];
+        // source pictures: Y | Cb | Cr in one block each (a picture arrives by one copy, fh264_upload_source_batch)
+        OPEN_CK(dalloc(s, &S.cur[0], WH + 2 * CWH));
+        OPEN_CK(dalloc(s, &S.cur_alt[0], WH + 2 * CWH));
+        S.cur[1] = S.cur[0] + WH; S.cur[2] = S.cur[1] + CWH;
+        S.cur_alt[1] = S.cur_alt[0] + WH; S.cur_alt[2] = S.cur_alt[1] + CWH;
         for (int c = 0; c < 3; c++) {
-            OPEN_CK(dalloc(s, &S.cur[c], c ? CWH : WH));
-            OPEN_CK(dalloc(s, &S.cur_alt[c], c ? CWH : WH));
             OPEN_CK(dalloc(s, &S.ref[c], c ? CWH : WH));
             OPEN_CK(dalloc(s, &S.rec[c], c ? CWH : WH));
         }
@@ -273,7 +356,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         OPEN_CK(dalloc(s, &S.prev_gen, (size_t)g.nparts));
         OPEN_CK(cudaMemset(S.prev_gen, 0x7f, sizeof(uint32_t) * (size_t)g.nparts));       // SPEC_PREV_NONE: no previous P picture
         OPEN_CK(dalloc(s, &S.qmv, (size_t)g.nmb * 4));
-        OPEN_CK(dalloc(s, &S.status, (size_t)ST_WORDS));
+        S.status = status_block + (size_t)b * ST_WORDS;     // one block: a range of sequences is snapshot by one copy
         S.results = results + (size_t)b * g.nmb;
         S.dbg = nullptr;
         memset(S.peer_ref, 0, sizeof S.peer_ref); memset(S.peer_rec, 0, sizeof S.peer_rec);
@@ -290,7 +373,8 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     std::stable_sort(order.begin(), order.end(), [Wmb, sn, sd](int a, int b) { return sd * (a % Wmb) + sn * (a / Wmb) < sd * (b % Wmb) + sn * (b / Wmb); });
     OPEN_CK(dalloc(s, &s->d_wf_order, (size_t)g.nmb));
     OPEN_CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.nmb, cudaMemcpyHostToDevice));
-    OPEN_CK(dalloc(s, &s->d_ticket, (size_t)4));
+    OPEN_CK(dalloc(s, &s->d_ticket, (size_t)8));               // [0..1] session stream, [2..3], [4..5] pipeline lanes, [6] I pictures
+    s->lane[2].d_ticket = s->d_ticket; s->lane[0].d_ticket = s->d_ticket + 2; s->lane[1].d_ticket = s->d_ticket + 4;   // pairs: warp-level, block-level kernel
     OPEN_CK(dalloc(s, &s->d_tmaps, (size_t)batch));
     OPEN_CK(dalloc(s, &s->d_tmaps16, (size_t)batch));
     OPEN_CK(dalloc(s, &s->d_tmaps48, (size_t)batch));
@@ -312,6 +396,8 @@ extern "C" int fh264_set_stream(fh264_session *s, void *cuda_stream)
     if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
     if (cuda_stream) s->stream = (cudaStream_t)cuda_stream;
     else { CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
+    s->lane[2].st = s->stream;
+    s->main_dirty = true;
     return FH264_OK;
 }
 
@@ -358,7 +444,7 @@ __global__ void k_swap_cur(SeqDev *seqs, int seq0, unsigned long long mask)
 }
 
 // Makes the pictures uploaded since the last use current for sequences [seq0, seq0+nseq) (called by everything that reads `cur`).
-static int adopt_uploads(fh264_session *s, int seq0, int nseq)
+static int adopt_uploads(fh264_session *s, cudaStream_t st, int seq0, int nseq)
 {
     for (int b0 = seq0; b0 < seq0 + nseq; b0 += 64) {
         const int n = std::min(64, seq0 + nseq - b0);
@@ -366,13 +452,13 @@ static int adopt_uploads(fh264_session *s, int seq0, int nseq)
         for (int i = 0; i < n; i++) {
             const int b = b0 + i;
             if (!s->up_pending[b]) continue;
-            CK(cudaStreamWaitEvent(s->stream, s->ev_up[b], 0));
+            CK(cudaStreamWaitEvent(st, s->ev_up[b], 0));
             mask |= 1ull << i;
             for (int c = 0; c < 3; c++) std::swap(s->h[b].cur[c], s->h[b].cur_alt[c]);
             s->cur_set[b] ^= 1;
             s->up_pending[b] = 0;
         }
-        if (mask) k_swap_cur<<<1, n, 0, s->stream>>>(s->d_seqs, b0, mask);
+        if (mask) k_swap_cur<<<1, n, 0, st>>>(s->d_seqs, b0, mask);
     }
     return FH264_OK;
 }
@@ -408,20 +494,38 @@ extern "C" int fh264_upload_source(fh264_session *s, int seq, const uint8_t *y, 
     return upload_planes(s, seq, y, cb, cr, cudaMemcpyHostToDevice);
 }
 
+extern "C" int fh264_upload_source_batch(fh264_session *s, int seq0, int nseq, const void *block, size_t stride, int device)
+{
+    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
+    const size_t pic = (size_t)s->g.WH + (size_t)s->g.WH / 2;
+    if (!block || stride < pic) return fail(FH264_E_ARG, "null block or stride smaller than one 4:2:0 picture");
+    CK(cudaSetDevice(s->device));
+    for (int b = seq0; b < seq0 + nseq; b++) {
+        const int target = 1 - s->cur_set[b];
+        if (s->free_valid[target][b]) CK(cudaStreamWaitEvent(s->up_stream, s->ev_free[target][b], 0));
+    }
+    for (int b = seq0; b < seq0 + nseq; b++) {               // Y | Cb | Cr are contiguous on both sides: one copy per picture
+        CK(cudaMemcpyAsync(s->h[b].cur_alt[0], (const uint8_t *)block + (size_t)(b - seq0) * stride, pic, device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->up_stream));
+        CK(cudaEventRecord(s->ev_up[b], s->up_stream));
+        s->up_pending[b] = 1;
+    }
+    return FH264_OK;
+}
+
 // Phase R on the current dpb of sequences [seq0, seq0+nseq).
-static int launch_phase_r(fh264_session *s, int seq0, int nseq, bool begin = true)
+static int launch_phase_r(fh264_session *s, cudaStream_t st, bool timing, int seq0, int nseq, bool begin = true)
 {
     const Geo &g = s->g;
-    if (begin) k_begin_ref<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0);
+    if (begin) k_begin_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
     dim3 gi((g.W + IT_W - 1) / IT_W, (g.H + IT_H - 1) / IT_H, nseq);
-    CK(cudaEventRecord(s->evk[1], s->stream));
-    k_interp<<<gi, 256, 0, s->stream>>>(s->d_seqs, seq0, g);
-    CK(cudaEventRecord(s->evk[2], s->stream));
+    if (timing) CK(cudaEventRecord(s->evk[1], st));
+    k_interp<<<gi, 256, 0, st>>>(s->d_seqs, seq0, g);
+    if (timing) CK(cudaEventRecord(s->evk[2], st));
     dim3 gf((g.W + FT_W - 1) / FT_W, (g.H + FT_H - 1) / FT_H, nseq);
-    k_features<<<gf, 256, 0, s->stream>>>(s->d_seqs, seq0, g, 0, nullptr);
-    CK(cudaEventRecord(s->evk[3], s->stream));
+    k_features<<<gf, 256, 0, st>>>(s->d_seqs, seq0, g, 0, nullptr);
+    if (timing) CK(cudaEventRecord(s->evk[3], st));
     dim3 gt(g.ntiles, nseq);
-    k_tile_index<<<gt, 256, FH_CELLS * 4, s->stream>>>(s->d_seqs, seq0, g);
+    k_tile_index<<<gt, 256, FH_CELLS * 4, st>>>(s->d_seqs, seq0, g);
     CKL();
     return FH264_OK;
 }
@@ -442,6 +546,8 @@ static int ensure_tmaps(fh264_session *s, int rows)
         enc = (EncodeTiledFn)fn;
     }
     const Geo &g = s->g;
+    CK(sync_streams(s));                                // window geometry changed: nothing in flight may still read the old maps
+    s->main_dirty = true;
     std::vector<CUtensorMap> maps(s->batch);
     const int g1w = (rows - 9) / 2;
     for (int pass = s->tmap_rows == 0 ? 0 : 1; pass < 3; pass++) {          // first call: the 16-row maps too
@@ -466,11 +572,12 @@ extern "C" int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, c
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     if (!y || !cb || !cr) return fail(FH264_E_ARG, "null plane");
     CK(cudaSetDevice(s->device));
+    rc = enter_main(s); if (rc) return rc;
     const size_t WH = (size_t)s->g.WH;
     CK(cudaMemcpyAsync(s->h[seq].ref[0], y, WH, cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->h[seq].ref[1], cb, WH / 4, cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->h[seq].ref[2], cr, WH / 4, cudaMemcpyHostToDevice, s->stream));
-    rc = launch_phase_r(s, seq, 1); if (rc) return rc;
+    rc = launch_phase_r(s, s->stream, true, seq, 1); if (rc) return rc;
     s->has_ref[seq] = 1;
     if (!s->prev_p.empty()) { s->prev_p[seq] = 0; s->last_i[seq] = 0; }     // a picture coded elsewhere: no P_Skip entries in mb_type_array
     return FH264_OK;
@@ -483,7 +590,8 @@ extern "C" int fh264_scene_sad_batch(fh264_session *s, int seq0, int nseq, uint6
     for (int b = seq0; b < seq0 + nseq; b++)
         if (!s->has_ref[b]) return fail(FH264_E_STATE, "scene_sad before any reference picture (dpb.L == NULL => IDR, ref_frames.cpp:191)");
     CK(cudaSetDevice(s->device));
-    rc = adopt_uploads(s, seq0, nseq); if (rc) return rc;
+    rc = enter_main(s); if (rc) return rc;
+    rc = adopt_uploads(s, s->stream, seq0, nseq); if (rc) return rc;
     k_zero_sad<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0);
     dim3 gs(nseq >= 8 ? 74 : 296, nseq);
     k_scene_sad<<<gs, 256, 0, s->stream>>>(s->d_seqs, seq0, s->g);
@@ -505,70 +613,139 @@ extern "C" int fh264_upload_source_device(fh264_session *s, int seq, const void 
     return upload_planes(s, seq, dy, dcb, dcr, cudaMemcpyDeviceToDevice);
 }
 
-extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const fh264_params *p, fh264_mb_result *results)
+// ---- lanes --------------------------------------------------------------------------------------------------------------------
+// Everything but the pipelined encode works on the session stream: it first waits for whatever the lanes still have in flight.
+static int enter_main(fh264_session *s)
 {
-    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
-    if (!p) return fail(FH264_E_ARG, "null params");
-    if (p->qp < 0 || p->qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
-    if (p->window < 0 || p->window > FH_MAX_WINDOW) return fail(FH264_E_UNSUPPORTED, "WindowSize above 64 is not supported");
-    if (p->maxdiff_set < -1) return fail(FH264_E_ARG, "maxdiff_set below -1");
-    for (int b = seq0; b < seq0 + nseq; b++)
-        if (!s->has_ref[b]) return fail(FH264_E_STATE, "encode_p before any reference picture (upload_recon first)");
-    CK(cudaSetDevice(s->device));
+    for (int l = 0; l < 2; l++) {
+        Lane &L = s->lane[l];
+        if (!L.busy) continue;
+        CK(cudaStreamWaitEvent(s->stream, L.ev_done, 0));
+        if (L.copy_pending) { CK(cudaStreamWaitEvent(s->stream, L.ev_copy_done, 0)); L.copy_pending = false; }
+        L.busy = false;
+    }
+    s->main_dirty = true;
+    return FH264_OK;
+}
+// The lanes start from the state the session stream has reached (once per batch of work enqueued there).
+static int fork_lanes(fh264_session *s)
+{
+    if (!s->main_dirty) return FH264_OK;
+    CK(cudaEventRecord(s->ev_fork, s->stream));
+    for (int l = 0; l < 2; l++) CK(cudaStreamWaitEvent(s->lane[l].st, s->ev_fork, 0));
+    if (s->lane[2].copy_pending) for (int l = 0; l < 2; l++) CK(cudaStreamWaitEvent(s->lane[l].st, s->lane[2].ev_copy_done, 0));
+    s->main_dirty = false;
+    return FH264_OK;
+}
+
+// selectNALUnitType's scene-change rule on the device (ref_frames.cpp:210-224): sum |cur Y - dpb Y| > MBs << 12 -> the picture
+// must be an IDR picture; the P kernels of the call then leave the sequence alone (ST_GATE).
+__global__ void k_scene_gate(SeqDev *seqs, int seq0, unsigned long long thr)
+{
+    uint32_t *st = seqs[seq0 + threadIdx.x].status;
+    const unsigned long long sad = (unsigned long long)st[ST_SAD_LO] | ((unsigned long long)st[ST_SAD_HI] << 32);
+    st[ST_GATE] = sad > thr ? 1u : 0u;
+}
+
+struct StreamOut {                  // what one lane sends home after phase C (all optional, pinned host memory)
+    fh264_mb_result *records;       // nseq * nmb
+    int cavlc;                      // entropy-code the slice data on the device
+    int first_bit;
+    uint8_t *slice; size_t slice_stride, slice_copy;
+    uint32_t *slice_stat;           // 2 words per sequence: flags (CV_FLAG_*), total bits
+    fh264_cavlc_mb_info *mb_info;   // nseq * nmb
+    uint32_t *status;               // ST_WORDS per sequence (scene SAD, gate, mode counts, flags)
+};
+
+static int ensure_cavlc(fh264_session *s);
+
+// One P picture of sequences [seq0, seq0 + nseq) on lane L. gate: scene-change rule decided on the device first.
+// hold: event the lane's phase A waits for (the pipeline's stagger), or null.
+static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh264_params &prm, int gate, cudaEvent_t hold, const StreamOut &o)
+{
     const Geo &g = s->g;
-    fh264_params prm = *p;
-    prm.basic = prm.basic ? 1 : 0;
-    s->epoch++;
-    cudaStream_t st = s->stream;
-    rc = ensure_tmaps(s, 8 + 2 * (prm.window / 16) + 1); if (rc) return rc;
-    rc = adopt_uploads(s, seq0, nseq); if (rc) return rc;
-    CK(cudaEventRecord(s->ev[0], st));
-    k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, s->d_ticket);
-    if (prm.basic) CK(cudaEventRecord(s->evk[0], st));
+    cudaStream_t st = L.st;
+    int rc = adopt_uploads(s, st, seq0, nseq); if (rc) return rc;
+    if (L.timing) CK(cudaEventRecord(s->ev[0], st));
+    k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, L.d_ticket);
+    if (gate) {
+        k_scene_sad<<<dim3(nseq >= 8 ? 74 : 296, nseq), 256, 0, st>>>(s->d_seqs, seq0, g);
+        k_scene_gate<<<1, nseq, 0, st>>>(s->d_seqs, seq0, (unsigned long long)g.nmb << 12);
+    }
+    if (hold) CK(cudaStreamWaitEvent(st, hold, 0));
+    cudaEvent_t *tr = s->trace ? L.tr[L.tr_n++ & 7] : nullptr;
+    if (tr) CK(cudaEventRecord(tr[0], st));
+    if (prm.basic && L.timing) CK(cudaEventRecord(s->evk[0], st));
+    const int g1 = prm.window / 16;
+    const WinMagic wm = { udiv_magic((uint32_t)(2 * (prm.window / 2) + 1)), udiv_magic((uint32_t)(2 * g1 + 1)) };
     if (!prm.basic) {
-        const int g1 = prm.window / 16;
         const size_t smem3 = (size_t)s3_win_bytes(g1) + 16 + 4 * sizeof(S3WarpV2);
         dim3 g3d(g.band_nmb, nseq), g2d(g.band_nmb * 2, nseq);          // 4 / 2 partitions per CTA
-        const WinMagic wm = { udiv_magic((uint32_t)(2 * (prm.window / 2) + 1)), udiv_magic((uint32_t)(2 * g1 + 1)) };
         k_stage3<<<g3d, 128, smem3, st>>>(s->d_seqs, seq0, g, prm, wm, s->use_tma ? s->d_tmaps48 : nullptr);
-        CK(cudaEventRecord(s->evk[0], st));
+        if (L.timing) CK(cudaEventRecord(s->evk[0], st));
         k_stage2<2><<<g2d, 64, 0, st>>>(s->d_seqs, seq0, g, prm);
     }
-    CK(cudaEventRecord(s->ev_spec, st));
+    if (L.timing) CK(cudaEventRecord(s->ev_spec, st));
     if (s->use_spec) {
         // phase S: the search completed for the guessed integer predictors (spec.cuh)
-        const int g1 = prm.window / 16;
         const size_t smems = 4 * (size_t)qwin_bytes(g1) + 4 * sizeof(SpecWarp) + 16;
-        const WinMagic wm = { udiv_magic((uint32_t)(2 * (prm.window / 2) + 1)), udiv_magic((uint32_t)(2 * g1 + 1)) };
         k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, 1, wm, s->use_tma ? s->d_tmaps : nullptr);
         k_skipspec<<<dim3((g.band_nmb + 3) / 4, nseq), 128, 4 * SKIPWIN_BYTES + 64, st>>>(s->d_seqs, seq0, g, prm, s->use_tma ? s->d_tmaps16 : nullptr);
         CKL();
     }
-    CK(cudaEventRecord(s->ev[1], st));
+    if (L.timing) CK(cudaEventRecord(s->ev[1], st));
+    CK(cudaEventRecord(L.ev_a, st));
+    if (tr) CK(cudaEventRecord(tr[1], st));
     // persistent wavefront CTAs: two anti-diagonals' worth per sequence — one set working, one set that has already
     // drawn its ticket and prefetched (otherwise ticket + prefetch latency sits on the wavefront's critical path)
     unsigned pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, (long long)nseq * (g.Wmb + 16));
     { static const char *e = getenv("FH264_PB_CTAS"); if (e && atoi(e) > 0) pb_ctas = (unsigned)std::min<long long>((long long)g.band_nmb * nseq, atoll(e)); }   // development knob
-    k_phase_b<<<pb_ctas, PB_NT, 0, st>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, s->d_ticket, s->use_spec);
-    CK(cudaEventRecord(s->ev[2], st));
+    cudaStream_t sb = L.hi ? L.hi : st;
+    if (L.hi) CK(cudaStreamWaitEvent(sb, L.ev_a, 0));
+    // the warp-level kernel (phase_bw.cuh) codes every picture phase S prepared; k_phase_b only those that need the block-level search
+    const int bw = s->use_spec && (s->use_bw < 0 ? L.hi != nullptr : s->use_bw != 0);
+    if (bw) k_phase_b_warp<<<pb_ctas, 32, pbw_smem_bytes(g1), sb>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, L.d_ticket, wm, s->use_tma ? s->d_tmaps : nullptr, s->force_miss);
+    k_phase_b<<<pb_ctas, PB_NT, 0, sb>>>(s->d_seqs, seq0, nseq, g, prm, s->epoch, s->d_wf_order, L.d_ticket + 1, s->use_spec, bw);
+    if (tr) CK(cudaEventRecord(tr[2], sb));
+    if (L.hi) { CK(cudaEventRecord(L.ev_b, sb)); CK(cudaStreamWaitEvent(st, L.ev_b, 0)); }
+    if (L.timing) CK(cudaEventRecord(s->ev[2], st));
     dim3 gc((g.band_nmb + 3) / 4, nseq);
-    if (s->copy_pending) { CK(cudaStreamWaitEvent(st, s->ev_copy_done, 0)); s->copy_pending = false; }   // records of the previous picture are home
+    if (L.copy_pending) { CK(cudaStreamWaitEvent(st, L.ev_copy_done, 0)); L.copy_pending = false; }   // records of the previous picture are home
     k_phase_c<<<gc, 128, 0, st>>>(s->d_seqs, seq0, g, prm);
     CKL();
+    if (tr) CK(cudaEventRecord(tr[3], st));
     for (int b = seq0; b < seq0 + nseq; b++) { CK(cudaEventRecord(s->ev_free[(int)s->cur_set[b]][b], st)); s->free_valid[(int)s->cur_set[b]][b] = 1; }   // `cur` is free for the upload after next
-    CK(cudaEventRecord(s->ev[3], st));
-    for (int b = seq0; b < seq0 + nseq; b++)
-        CK(cudaMemcpyAsync(s->h_status + (size_t)b * ST_WORDS, s->h[b].status, sizeof(uint32_t) * ST_WORDS, cudaMemcpyDeviceToHost, st));
-    if (results)
+    if (L.timing) CK(cudaEventRecord(s->ev[3], st));
+    CK(cudaMemcpyAsync(s->h_status + (size_t)seq0 * ST_WORDS, s->h[seq0].status, sizeof(uint32_t) * ST_WORDS * nseq, cudaMemcpyDeviceToHost, st));
+    // (the caller's snapshot too is taken in stream order: the next picture's k_begin_picture resets the counters)
+    if (o.status) CK(cudaMemcpyAsync(o.status, s->h[seq0].status, sizeof(uint32_t) * ST_WORDS * nseq, cudaMemcpyDeviceToHost, st));
+    if (o.records || o.cavlc)
     {
-        // the records travel on the copy stream while this stream goes on with the dpb swap, phase R and the next picture
-        CK(cudaEventRecord(s->ev_c_done, st));
-        CK(cudaStreamWaitEvent(s->copy_stream, s->ev_c_done, 0));
-        if (g.world == 1) CK(cudaMemcpyAsync(results, s->h[seq0].results, sizeof(fh264_mb_result) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, s->copy_stream));
-        else for (int b = 0; b < nseq; b++)      // band mode: only this rank's band of every sequence is valid
-            CK(cudaMemcpyAsync(results + (size_t)b * g.nmb + g.band_mb0, s->h[seq0 + b].results + g.band_mb0, sizeof(fh264_mb_result) * (size_t)g.band_nmb, cudaMemcpyDeviceToHost, s->copy_stream));
-        CK(cudaEventRecord(s->ev_copy_done, s->copy_stream));
-        s->copy_pending = true;
+        // everything that goes home travels on the lane's copy stream while the coding stream goes on with the dpb swap, phase R
+        // and the next picture; the entropy coder (cavlc.cuh) reads the records phase C left, so it runs there too
+        CK(cudaEventRecord(L.ev_c_done, st));
+        CK(cudaStreamWaitEvent(L.cp, L.ev_c_done, 0));
+        if (o.records) {
+            if (g.world == 1) CK(cudaMemcpyAsync(o.records, s->h[seq0].results, sizeof(fh264_mb_result) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, L.cp));
+            else for (int b = 0; b < nseq; b++)      // band mode: only this rank's band of every sequence is valid
+                CK(cudaMemcpyAsync(o.records + (size_t)b * g.nmb + g.band_mb0, s->h[seq0 + b].results + g.band_mb0, sizeof(fh264_mb_result) * (size_t)g.band_nmb, cudaMemcpyDeviceToHost, L.cp));
+        }
+        if (o.cavlc) {
+            const int nmb = g.nmb, wmb = g.Wmb;
+            for (int b = seq0; b < seq0 + nseq; b++) CK(cudaMemsetAsync(s->cvh[b].stream, 0, (size_t)CV_STREAM_BYTES + 64, L.cp));
+            k_cavlc_prep<<<dim3((nmb + 127) / 128, nseq), 128, 0, L.cp>>>(s->d_seqs, s->d_cvs, seq0, nmb);
+            k_cavlc_code<<<dim3((nmb + 1 + 127) / 128, nseq), 128, 0, L.cp>>>(s->d_seqs, s->d_cvs, seq0, nmb, wmb);
+            k_cavlc_scan<<<nseq, 1024, 0, L.cp>>>(s->d_cvs, seq0, nmb, o.first_bit);
+            k_cavlc_pack<<<dim3((nmb + 1 + 3) / 4, nseq), 128, 0, L.cp>>>(s->d_cvs, seq0, nmb, o.first_bit);
+            CKL();
+            for (int b = 0; b < nseq; b++) {
+                CK(cudaMemcpyAsync(o.slice_stat + 2 * b, s->cvh[seq0 + b].stat, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, L.cp));
+                CK(cudaMemcpyAsync(o.slice + (size_t)b * o.slice_stride, s->cvh[seq0 + b].stream, o.slice_copy, cudaMemcpyDeviceToHost, L.cp));
+                if (o.mb_info) CK(cudaMemcpyAsync(o.mb_info + (size_t)b * nmb, s->cvh[seq0 + b].info, sizeof(CvInfo) * (size_t)nmb, cudaMemcpyDeviceToHost, L.cp));
+            }
+        }
+        CK(cudaEventRecord(L.ev_copy_done, L.cp));
+        L.copy_pending = true;
     }
     // dpb := reconstruction (frameDeepCopy, ref_frames.cpp:17-35) by pointer swap, then phase R for the next picture
     k_begin_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);          // before the barrier: a barrier timeout must survive into the next picture's status
@@ -579,11 +756,63 @@ extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const 
             for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
             for (int r = 0; r < FH_MAX_WORLD; r++) for (int c = 0; c < 3; c++) std::swap(s->h[b].peer_ref[r][c], s->h[b].peer_rec[r][c]);
         }
-    rc = launch_phase_r(s, seq0, nseq, false); if (rc) return rc;
-    CK(cudaEventRecord(s->ev[4], st));
-    s->timed = true;
-    if (!s->prev_p.empty()) for (int b = seq0; b < seq0 + nseq; b++) { s->prev_p[b] = 1; s->last_i[b] = 0; }
+    rc = launch_phase_r(s, st, L.timing, seq0, nseq, false); if (rc) return rc;
+    if (L.timing) { CK(cudaEventRecord(s->ev[4], st)); s->timed = true; }
+    if (tr) CK(cudaEventRecord(tr[4], st));
+    CK(cudaEventRecord(L.ev_done, st));
+    L.busy = true;
+    for (int b = seq0; b < seq0 + nseq; b++) {
+        if (gate) { if (!s->gate_calls[b]) { s->saved_prev_p[b] = s->prev_p[b]; s->saved_last_i[b] = s->last_i[b]; } s->gate_calls[b]++; }
+        else s->gate_calls[b] = 0;
+        s->prev_p[b] = 1; s->last_i[b] = 0;
+    }
     return FH264_OK;
+}
+
+static int check_encode_p(fh264_session *s, int seq0, int nseq, const fh264_params *p)
+{
+    int rc = check_seq(s, seq0, nseq); if (rc) return rc;
+    if (!p) return fail(FH264_E_ARG, "null params");
+    if (p->qp < 0 || p->qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
+    if (p->window < 0 || p->window > FH_MAX_WINDOW) return fail(FH264_E_UNSUPPORTED, "WindowSize above 64 is not supported");
+    if (p->maxdiff_set < -1) return fail(FH264_E_ARG, "maxdiff_set below -1");
+    for (int b = seq0; b < seq0 + nseq; b++)
+        if (!s->has_ref[b]) return fail(FH264_E_STATE, "encode_p before any reference picture (upload_recon first)");
+    return FH264_OK;
+}
+
+// The call's sequences on the session stream (plain) or split over the two pipeline lanes.
+static int encode_dispatch(fh264_session *s, int seq0, int nseq, const fh264_params *p, int gate, bool piped, const StreamOut &o)
+{
+    CK(cudaSetDevice(s->device));
+    fh264_params prm = *p;
+    prm.basic = prm.basic ? 1 : 0;
+    s->epoch++;
+    int rc = ensure_tmaps(s, 8 + 2 * (prm.window / 16) + 1); if (rc) return rc;
+    if (o.cavlc) { rc = ensure_cavlc(s); if (rc) return rc; }
+    if (!piped || nseq < 2 || s->g.world > 1) {
+        rc = enter_main(s); if (rc) return rc;
+        return encode_lane(s, s->lane[2], seq0, nseq, prm, gate, nullptr, o);
+    }
+    rc = fork_lanes(s); if (rc) return rc;
+    const int n0 = (nseq + 1) / 2, n1 = nseq - n0, nmb = s->g.nmb;
+    StreamOut o1 = o;
+    if (o.records) o1.records = o.records + (size_t)n0 * nmb;
+    if (o.slice) o1.slice = o.slice + (size_t)n0 * o.slice_stride;
+    if (o.slice_stat) o1.slice_stat = o.slice_stat + 2 * n0;
+    if (o.mb_info) o1.mb_info = o.mb_info + (size_t)n0 * nmb;
+    if (o.status) o1.status = o.status + (size_t)n0 * ST_WORDS;
+    rc = encode_lane(s, s->lane[0], seq0, n0, prm, gate, nullptr, o); if (rc) return rc;
+    return encode_lane(s, s->lane[1], seq0 + n0, n1, prm, gate, s->lane[0].ev_a, o1);
+}
+
+extern "C" int fh264_encode_p_async(fh264_session *s, int seq0, int nseq, const fh264_params *p, fh264_mb_result *results)
+{
+    int rc = check_encode_p(s, seq0, nseq, p); if (rc) return rc;
+    StreamOut o;
+    memset(&o, 0, sizeof o);
+    o.records = results;
+    return encode_dispatch(s, seq0, nseq, p, 0, s->pipeline != 0, o);
 }
 
 extern "C" int fh264_encode_p(fh264_session *s, int seq0, int nseq, const fh264_params *p, fh264_mb_result *results)
@@ -592,6 +821,54 @@ extern "C" int fh264_encode_p(fh264_session *s, int seq0, int nseq, const fh264_
     CK(sync_streams(s));
     for (int b = seq0; b < seq0 + nseq; b++) { rc = fh264_picture_status(s, b); if (rc) return rc; }
     return FH264_OK;
+}
+
+// Development tap (FH264_TRACE=1): out[lane][picture][5] = ms since the oldest traced phase-A start of lane 0, for the last 8
+// pictures of the three lanes (0, 1: pipeline halves; 2: session stream); -1 where nothing was recorded. Synchronises.
+extern "C" int fh264_debug_trace(fh264_session *s, float *out)
+{
+    if (!s || !out) return fail(FH264_E_ARG, "null argument");
+    if (!s->trace) return fail(FH264_E_STATE, "FH264_TRACE=1 was not set when the session was opened");
+    CK(cudaSetDevice(s->device));
+    CK(sync_streams(s));
+    for (int i = 0; i < 3 * 8 * 5; i++) out[i] = -1.0f;
+    cudaEvent_t base = nullptr;
+    for (int l = 0; l < 3 && !base; l++) { const Lane &L = s->lane[l]; if (L.tr_n > 0) base = L.tr[(L.tr_n >= 8 ? L.tr_n : 0) & 7][0]; }
+    if (!base) return FH264_OK;
+    for (int l = 0; l < 3; l++) {
+        const Lane &L = s->lane[l];
+        const int n = std::min(L.tr_n, 8), first = L.tr_n - n;
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < 5; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, base, L.tr[(first + i) & 7][k]) == cudaSuccess) out[(l * 8 + i) * 5 + k] = ms; else cudaGetLastError(); }
+    }
+    return FH264_OK;
+}
+
+extern "C" int fh264_set_pipeline(fh264_session *s, int on)
+{
+    if (!s) return fail(FH264_E_ARG, "null session");
+    s->pipeline = on ? 1 : 0;
+    return FH264_OK;
+}
+
+// One step of a batch of sequences without a host round trip. See the header.
+extern "C" int fh264_encode_p_stream(fh264_session *s, int seq0, int nseq, const fh264_params *p, int scene_gate, const fh264_stream_out *out)
+{
+    int rc = check_encode_p(s, seq0, nseq, p); if (rc) return rc;
+    if (scene_gate && s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "the device-side scene gate is not available in band mode");
+    StreamOut o;
+    memset(&o, 0, sizeof o);
+    if (out) {
+        o.records = out->records; o.status = out->status;
+        if (out->slice) {
+            if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
+            if (!out->slice_stat || out->first_bit < 0 || out->first_bit > 7 || out->slice_copy_bytes > out->slice_stride || out->slice_copy_bytes > (size_t)CV_STREAM_BYTES)
+                return fail(FH264_E_ARG, "slice output: slice_stat missing, first_bit outside 0..7 or copy size above the stride / 500000");
+            o.cavlc = 1; o.first_bit = out->first_bit; o.slice = out->slice; o.slice_stride = out->slice_stride; o.slice_copy = out->slice_copy_bytes;
+            o.slice_stat = out->slice_stat; o.mb_info = out->mb_info;
+        }
+    }
+    return encode_dispatch(s, seq0, nseq, p, scene_gate ? 1 : 0, s->pipeline != 0, o);
 }
 
 // Decoder inverse path: reconstructs the P picture described by `records` (quadrant MVs, mb_type,
@@ -606,16 +883,17 @@ extern "C" int fh264_decode_p(fh264_session *s, int seq0, int nseq, int qp, cons
     for (int b = seq0; b < seq0 + nseq; b++)
         if (!s->has_ref[b]) return fail(FH264_E_STATE, "decode_p before any reference picture (upload_recon first)");
     CK(cudaSetDevice(s->device));
+    rc = enter_main(s); if (rc) return rc;
     const Geo &g = s->g;
     cudaStream_t st = s->stream;
-    if (s->copy_pending) { CK(cudaStreamWaitEvent(st, s->ev_copy_done, 0)); s->copy_pending = false; }
+    if (s->lane[2].copy_pending) { CK(cudaStreamWaitEvent(st, s->lane[2].ev_copy_done, 0)); s->lane[2].copy_pending = false; }
     CK(cudaMemcpyAsync(s->h[seq0].results, records, sizeof(fh264_mb_result) * (size_t)g.nmb * nseq, cudaMemcpyHostToDevice, st));
     k_decode_p<<<dim3((g.nmb + 3) / 4, nseq), 128, 0, st>>>(s->d_seqs, seq0, g, qp);
     CKL();
     k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
     for (int b = seq0; b < seq0 + nseq; b++)
         for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
-    rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
+    rc = launch_phase_r(s, st, true, seq0, nseq); if (rc) return rc;
     CK(sync_streams(s));
     if (!s->prev_p.empty()) for (int b = seq0; b < seq0 + nseq; b++) { s->prev_p[b] = 1; s->last_i[b] = 0; }
     return FH264_OK;
@@ -664,31 +942,32 @@ extern "C" int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh26
     if (qp < 0 || qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
     if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "encode_i is not available in band mode");
     CK(cudaSetDevice(s->device));
+    for (int b = seq0; b < seq0 + nseq; b++) if (s->gate_calls[b]) { CK(sync_streams(s)); break; }      // prev_p of a gated call is known once its status is home
+    rc = enter_main(s); if (rc) return rc;
     rc = ensure_intra(s); if (rc) return rc;
     const Geo &g = s->g;
     cudaStream_t st = s->stream;
-    rc = adopt_uploads(s, seq0, nseq); if (rc) return rc;
-    if (s->copy_pending) { CK(cudaStreamWaitEvent(st, s->ev_copy_done, 0)); s->copy_pending = false; }   // the I records reuse the result buffer
+    rc = adopt_uploads(s, st, seq0, nseq); if (rc) return rc;
+    if (s->lane[2].copy_pending) { CK(cudaStreamWaitEvent(st, s->lane[2].ev_copy_done, 0)); s->lane[2].copy_pending = false; }   // the I records reuse the result buffer
     s->epoch++;
     CK(cudaMemcpyAsync(s->d_prev_p + seq0, s->prev_p.data() + seq0, sizeof(int) * nseq, cudaMemcpyHostToDevice, st));
-    k_begin_intra<<<1, nseq, 0, st>>>(s->d_ticket + 1, s->d_seqs, seq0);
+    k_begin_intra<<<1, nseq, 0, st>>>(s->d_ticket + 6, s->d_seqs, seq0);
     int nl = 32;
     { const char *e = getenv("FH264_INTRA_LANES"); if (e && atoi(e) == 1) nl = 1; }   // development knob (read per call): everything on lane 0
     const unsigned ctas = (unsigned)std::min<long long>((long long)g.nmb * nseq, (long long)nseq * (g.Wmb + 16));
     CK(cudaEventRecord(s->ev_i[0], st));
-    k_intra<<<ctas, 32, 0, st>>>(s->d_seqs, s->d_is, s->d_prev_p, seq0, nseq, g, qp, s->epoch, s->d_iwf_order, s->d_ticket + 1, nl);
+    k_intra<<<ctas, 32, 0, st>>>(s->d_seqs, s->d_is, s->d_prev_p, seq0, nseq, g, qp, s->epoch, s->d_iwf_order, s->d_ticket + 6, nl);
     CKL();
     CK(cudaEventRecord(s->ev_i[1], st));
     s->intra_timed = true;
     for (int b = seq0; b < seq0 + nseq; b++) { CK(cudaEventRecord(s->ev_free[(int)s->cur_set[b]][b], st)); s->free_valid[(int)s->cur_set[b]][b] = 1; }
-    for (int b = seq0; b < seq0 + nseq; b++)
-        CK(cudaMemcpyAsync(s->h_status + (size_t)b * ST_WORDS, s->h[b].status, sizeof(uint32_t) * ST_WORDS, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s->h_status + (size_t)seq0 * ST_WORDS, s->h[seq0].status, sizeof(uint32_t) * ST_WORDS * nseq, cudaMemcpyDeviceToHost, st));
     if (results) CK(cudaMemcpyAsync(results, s->h[seq0].results, sizeof(fh264_mb_result_i) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, st));
     // dpb := reconstruction, then phase R for the next picture (rbsp_encoding.cpp:317-322)
     k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
     for (int b = seq0; b < seq0 + nseq; b++)
         for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
-    rc = launch_phase_r(s, seq0, nseq); if (rc) return rc;
+    rc = launch_phase_r(s, st, true, seq0, nseq); if (rc) return rc;
     for (int b = seq0; b < seq0 + nseq; b++) { s->has_ref[b] = 1; s->prev_p[b] = 0; s->last_i[b] = 1; }
     CK(sync_streams(s));
     for (int b = seq0; b < seq0 + nseq; b++)
@@ -773,9 +1052,11 @@ extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit
     if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
     if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
     if (s->epoch == 0) return fail(FH264_E_STATE, "cavlc_p before any encode_p");
+    for (int b = seq0; b < seq0 + nseq; b++) if (s->gate_calls[b]) { CK(cudaSetDevice(s->device)); CK(sync_streams(s)); break; }
     for (int b = seq0; b < seq0 + nseq; b++)
         if (!s->prev_p[b] || s->last_i[b]) return fail(FH264_E_STATE, "cavlc_p: the last picture of the sequence was not coded by encode_p (its records are not P records)");
     CK(cudaSetDevice(s->device));
+    rc = enter_main(s); if (rc) return rc;
     rc = ensure_cavlc(s); if (rc) return rc;
     const int nmb = s->g.nmb, wmb = s->g.Wmb;
     cudaStream_t st = s->stream;
@@ -791,8 +1072,10 @@ extern "C" int fh264_cavlc_i(fh264_session *s, int seq0, int nseq, int first_bit
     int rc = check_seq(s, seq0, nseq); if (rc) return rc;
     if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
     if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
+    for (int b = seq0; b < seq0 + nseq; b++) if (s->gate_calls[b]) { CK(cudaSetDevice(s->device)); CK(sync_streams(s)); break; }
     for (int b = seq0; b < seq0 + nseq; b++) if (!s->last_i[b]) return fail(FH264_E_STATE, "cavlc_i: the last picture of the sequence was not coded by encode_i");
     CK(cudaSetDevice(s->device));
+    rc = enter_main(s); if (rc) return rc;
     rc = ensure_cavlc(s); if (rc) return rc;
     const int nmb = s->g.nmb, wmb = s->g.Wmb;
     cudaStream_t st = s->stream;
@@ -812,7 +1095,7 @@ extern "C" int fh264_debug_status(fh264_session *s, int seq, uint32_t out[16])
     if (!out) return fail(FH264_E_ARG, "null output");
     CK(cudaSetDevice(s->device));
     CK(sync_streams(s));
-    memcpy(out, s->h_status + (size_t)seq * ST_WORDS, sizeof(uint32_t) * ST_WORDS);
+    memcpy(out, s->h_status + (size_t)seq * ST_WORDS, sizeof(uint32_t) * 16);
     return FH264_OK;
 }
 
@@ -822,6 +1105,7 @@ extern "C" int fh264_download_recon(fh264_session *s, int seq, uint8_t *y, uint8
     if (!y || !cb || !cr) return fail(FH264_E_ARG, "null plane");
     if (!s->has_ref[seq]) return fail(FH264_E_STATE, "no reference picture yet");
     CK(cudaSetDevice(s->device));
+    rc = enter_main(s); if (rc) return rc;
     const size_t WH = (size_t)s->g.WH;
     CK(cudaMemcpyAsync(y, s->h[seq].ref[0], WH, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(cb, s->h[seq].ref[1], WH / 4, cudaMemcpyDeviceToHost, s->stream));
@@ -932,6 +1216,7 @@ extern "C" int fh264_motion_compensate(fh264_session *s, int seq, const int16_t 
     if (!qmv || !pred384) return fail(FH264_E_ARG, "null argument");
     if (!s->has_ref[seq]) return fail(FH264_E_STATE, "no reference picture yet");
     CK(cudaSetDevice(s->device));
+    rc = enter_main(s); if (rc) return rc;
     const int n = s->g.nmb;
     rc = ensure_scratch(s, (size_t)n); if (rc) return rc;
     cudaStream_t st = s->stream;
@@ -948,6 +1233,7 @@ extern "C" int fh264_debug_plane(fh264_session *s, int seq, int f, uint8_t *out)
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     if (!out || f < 0 || f > 15) return fail(FH264_E_ARG, "bad argument");
     CK(cudaSetDevice(s->device));
+    rc = enter_main(s); if (rc) return rc;
     CK(cudaMemcpyAsync(out, s->h[seq].planes + (size_t)f * s->g.WH, (size_t)s->g.WH, cudaMemcpyDeviceToHost, s->stream));
     CK(sync_streams(s));
     return FH264_OK;
@@ -966,6 +1252,7 @@ extern "C" int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint
     int rc = check_seq(s, seq, 1); if (rc) return rc;
     if (!out || f < 0 || f > 15 || k < 0 || k > 4) return fail(FH264_E_ARG, "bad argument");
     CK(cudaSetDevice(s->device));
+    rc = enter_main(s); if (rc) return rc;
     const int n = s->g.WH;
     rc = ensure_scratch(s, (size_t)(n * 2 + 767) / 768); if (rc) return rc;
     // the path keeps plane 0 only; the tap evaluates the same kernel for plane f into a temporary

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(32 * NW, FH_S2_MINB) k_stage2(const SeqDev *__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     S2Warp *w = &sm[warp];
     const SeqDev &S = seqs[seq0 + blockIdx.y];
+    if (S.status[ST_GATE]) return;
     const int part = g.band_mb0 * 4 + blockIdx.x * NW + warp;
     int xP, yP;
     part_origin(g, part, xP, yP);
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(32 * NW, FH_S2_MINB) k_stage2(const SeqDev *__
     if (countonly) {
         // j_stop is exact: the counts saw every gated entry at or below the bound that was current when it arrived
         const int jsb = bound_from_bins();
-        if (lane == 0) { pa->s2_off = 0; pa->n2 = S2_SLOW | (uint32_t)jsb; }
+        if (lane == 0) { pa->s2_off = 0; pa->n2 = S2_SLOW | (uint32_t)jsb; atomicAdd(&S.status[ST_NSLOW], 1u); }
         return;
     }
     const int js = recount();         // every gated entry with j <= jb is kept and jb >= j_stop: the exact j_stop
@@ -367,5 +368,6 @@ __global__ void __launch_bounds__(32 * NW, FH_S2_MINB) k_stage2(const SeqDev *__
     if (lane == 0) {
         pa->s2_off = (uint32_t)part * S2_SLICE;
         pa->n2 = fits ? (uint32_t)n2 : (S2_SLOW | (uint32_t)js);
+        if (!fits) atomicAdd(&S.status[ST_NSLOW], 1u);
     }
 }

@@ -115,6 +115,11 @@ __device__ __forceinline__ void predict_mv_(const NbCache &nc, int px, int py, i
 
 __device__ __forceinline__ int mv_cost(int mvx, int mvy, int px, int py) { return iabs_(mvx - px) + iabs_(mvy - py); }
 
+// Which phase-B kernel codes the current picture of a sequence: the block-level one (this file) when a partition's stage-2 set
+// has to be enumerated here (S2_SLOW) or the timeline tap is on, the warp-level one (phase_bw.cuh) otherwise. Both kernels are
+// launched for every call and evaluate this the same way.
+__device__ __forceinline__ bool seq_is_heavy(const SeqDev &S) { return S.status[ST_NSLOW] != 0u || S.dbg != nullptr; }
+
 
 // ---- the whole macroblock from the phase-S products, by ONE warp, in registers (no block barrier, no shared-memory state) -------
 // Every decision interEncoding makes for a macroblock (:402-564) once the predictors are known is a lookup: the P_Skip trial in
@@ -416,10 +421,15 @@ __device__ __noinline__ u64 stage2_slow(const SeqDev &S, const Geo &g, PBShared 
 }
 
 __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__restrict__ seqs, int seq0, int nseq, Geo g, fh264_params prm,
-                                                   uint32_t epoch, const int *__restrict__ wf_order, uint32_t *__restrict__ ticket, int use_spec)
+                                                   uint32_t epoch, const int *__restrict__ wf_order, uint32_t *__restrict__ ticket, int use_spec, int heavy_only)
 {
     __shared__ PBShared sh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (heavy_only) {                                      // k_phase_b_warp codes the other sequences (usually all of them)
+        bool any = false;
+        for (int b = 0; b < nseq; b++) any |= seq_is_heavy(seqs[seq0 + b]) && !seqs[seq0 + b].status[ST_GATE];
+        if (!any) return;
+    }
     // Persistent CTAs: the grid holds about one wavefront's worth of CTAs per sequence (more would only spin and keep
     // other streams' kernels off the SMs); each CTA keeps drawing tickets until the picture is done.
     const uint32_t total = (uint32_t)g.band_nmb * (uint32_t)nseq;
@@ -430,6 +440,7 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
     const uint32_t t = sh.my_ticket;
     if (t >= total) return;
     const SeqDev &S = seqs[seq0 + (int)(t % (uint32_t)nseq)];
+    if (S.status[ST_GATE] || (heavy_only && !seq_is_heavy(S))) continue;   // scene cut / not ours: the ticket is dropped (block-uniform)
     const int mb = wf_order[t / (uint32_t)nseq];
     const int mbx = mb % g.Wmb, mby = mb / g.Wmb;
     const int W = g.W, H = g.H;

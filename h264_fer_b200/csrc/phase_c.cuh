@@ -190,7 +190,23 @@ __global__ void __launch_bounds__(128) k_phase_c(const SeqDev *__restrict__ seqs
     const SeqDev &S = seqs[seq0 + blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb = g.band_mb0 + blockIdx.x * 4 + warp;
+    const uint32_t gated = S.status[ST_GATE];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { S.status[ST_GATE_DONE] = gated; if (gated) S.status[ST_GATED_TOTAL] += 1u; }
     if (mb >= g.band_mb0 + g.band_nmb) return;
+    if (gated) {
+        // Scene cut (fh264_encode_p_stream): the picture is not coded as P. The reconstruction buffer takes a copy of the reference so
+        // that the dpb swap and phase R that follow on the stream leave the sequence exactly where it was; records stay untouched.
+        const int mbx = mb % g.Wmb, mby = mb / g.Wmb, CW = g.W >> 1;
+        if (lane < 16) {
+            const size_t o = (size_t)(mby * 16 + lane) * g.W + mbx * 16;
+            *(uint4 *)(S.rec[0] + o) = *(const uint4 *)(S.ref[0] + o);
+        } else {
+            const int c = (lane - 16) >> 3, r = (lane - 16) & 7;
+            const size_t o = (size_t)(mby * 8 + r) * CW + mbx * 8;
+            *(uint2 *)(S.rec[1 + c] + o) = *(const uint2 *)(S.ref[1 + c] + o);
+        }
+        return;
+    }
     fh264_mb_result *rec = &recs[warp];
     {   // zero the record (52 x 16 bytes)
         uint4 z = make_uint4(0, 0, 0, 0);

@@ -69,17 +69,20 @@ __device__ __forceinline__ void pf_emit(bool have, int mvx, int mvy, int sad, in
     npf += __popc(b);
 }
 
-// The finalists of one partition for one guessed gen = (Gx, Gy) into out->f[slot]. Warp-uniform call.
-__device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const fh264_params &prm, int part, int xP, int yP, const uint2 (&rows)[8],
-                                          const FeatQ &fq, int n3, uint32_t n2w, uint32_t s2_off, int Gx, int Gy, int slot,
-                                          SpecWarp *sw, uint8_t *win, PartSpec *out, const CUtensorMap *tmap, uint32_t &phase, const WinMagic &wm)
+// The complete search of one partition for gen = (Gx, Gy) (stage 3 list of phase A, stage 2 ranked with the multiplier of this
+// gen and measured, stage 1 window around it): every evaluated candidate that can be the strict first minimum of
+// SAD + |mv - mvp|_1 for SOME mvp of the cell [4*gen, 4*gen+3]^2 is left in sw->pf_mv / sw->pf_so (vector; SAD | order << 16).
+// Returns their number; usable = false when the stage-2 set is not in the pool (S2_SLOW). Warp-uniform call.
+__device__ __forceinline__ int spec_collect(const SeqDev &S, const Geo &g, const fh264_params &prm, int xP, int yP, const uint2 (&rows)[8],
+                                            const FeatQ &fq, int n3, uint32_t n2w, uint32_t s2_off, int Gx, int Gy,
+                                            SpecWarp *sw, uint8_t *win, const CUtensorMap *tmap, uint32_t &phase, const WinMagic &wm, bool &usable)
 {
     const int lane = threadIdx.x & 31, W = g.W, H = g.H;
-    const int g1 = prm.window / 16, w1 = 2 * g1 + 1, n1 = w1 * w1 * 16;
+    const int g1 = prm.window / 16, w1 = 2 * g1 + 1;
     const uint32_t i1 = wm.i1;
     const int cxq = 4 * Gx, cyq = 4 * Gy;
     int npf = 0;
-    bool usable = !(n2w & S2_SLOW);                        // oversized stage-2 set: phase B enumerates it itself
+    usable = !(n2w & S2_SLOW);                             // oversized stage-2 set: phase B enumerates it itself
     // the pixel window of stage 1 starts to arrive now (TMA) and is consumed after stages 3 and 2
     const QWinGeo qg = qwin_geo(g1);
     int woff;
@@ -194,9 +197,20 @@ __device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const f
         }
     }
     __syncwarp();
-    // ---- finalists: bound over everything still in the race, duplicates of one MV dropped (the first in list order stays)
     if (npf > SPEC_PF_CAP) usable = false;                 // cannot happen (17 + 33 + 33 candidates at most)
-    const int n = min(npf, SPEC_PF_CAP);
+    return min(npf, SPEC_PF_CAP);
+}
+
+// The finalists of one partition for one guessed gen = (Gx, Gy) into out->f[slot]. Warp-uniform call.
+__device__ __forceinline__ void spec_slot(const SeqDev &S, const Geo &g, const fh264_params &prm, int part, int xP, int yP, const uint2 (&rows)[8],
+                                          const FeatQ &fq, int n3, uint32_t n2w, uint32_t s2_off, int Gx, int Gy, int slot,
+                                          SpecWarp *sw, uint8_t *win, PartSpec *out, const CUtensorMap *tmap, uint32_t &phase, const WinMagic &wm)
+{
+    const int lane = threadIdx.x & 31;
+    const int cxq = 4 * Gx, cyq = 4 * Gy;
+    bool usable;
+    const int n = spec_collect(S, g, prm, xP, yP, rows, fq, n3, n2w, s2_off, Gx, Gy, sw, win, tmap, phase, wm, usable);
+    // ---- finalists: bound over everything still in the race, duplicates of one MV dropped (the first in list order stays)
     int Uf = 0x7fffffff;
     for (int i = lane; i < n; i += 32) {
         const uint32_t mv = sw->pf_mv[i], so = sw->pf_so[i];
@@ -281,6 +295,7 @@ __global__ void __launch_bounds__(128, FH_SPEC_MINB) k_spec(const SeqDev *__rest
     uint8_t *win = smem_raw + (size_t)warp * wbytes;
     SpecWarp *sw = (SpecWarp *)(smem_raw + 4 * (size_t)wbytes) + warp;
     const SeqDev &S = seqs[seq0 + blockIdx.y];
+    if (S.status[ST_GATE]) return;
     const CUtensorMap *tmap = tmaps ? tmaps + seq0 + blockIdx.y : nullptr;
     uint32_t phase = 0;
     if (lane == 0) mbar_init(&sw->bar, 1);
@@ -348,6 +363,7 @@ __global__ void __launch_bounds__(128) k_skipspec(const SeqDev *__restrict__ seq
     uint8_t *win = smem_raw + (size_t)warp * SKIPWIN_BYTES;
     uint64_t *bar = (uint64_t *)(smem_raw + 4 * SKIPWIN_BYTES) + warp;
     const SeqDev &S = seqs[seq0 + blockIdx.y];
+    if (S.status[ST_GATE]) return;
     const int mb = g.band_mb0 + blockIdx.x * 4 + warp;
     if (mb >= g.band_mb0 + g.band_nmb) return;
     const CUtensorMap *tmap = tmaps16 ? tmaps16 + seq0 + blockIdx.y : nullptr;

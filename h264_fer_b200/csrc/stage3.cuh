@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(128, FH_S3_MINB) k_stage3(const SeqDev *__rest
     uint64_t *bar = (uint64_t *)(smem_raw + wbytes);
     S3WarpV2 *sw = (S3WarpV2 *)(smem_raw + wbytes + 16) + warp;
     const SeqDev &S = seqs[seq0 + blockIdx.y];
+    if (S.status[ST_GATE]) return;                                   // scene cut: this picture is not coded as P (CTA-uniform)
     const int mb = g.band_mb0 + blockIdx.x;
     const int part = mb * 4 + warp;
     const int W = g.W, H = g.H;

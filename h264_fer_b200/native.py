@@ -31,7 +31,9 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_host_alloc", "fh264_host_free", "fh264_upload_source", "fh264_upload_source_frame", "fh264_upload_source_device", "fh264_upload_recon", "fh264_scene_sad", "fh264_scene_sad_batch",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
-           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_cavlc_i", "fh264_last_timings", "fh264_last_spec_ms", "fh264_measure_int_peak", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import"]
+           "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_cavlc_i", "fh264_last_timings", "fh264_last_spec_ms", "fh264_measure_int_peak", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import",
+           "fh264_encode_p_stream", "fh264_set_pipeline", "fh264_upload_source_batch", "fh264_debug_trace"]
+STATUS_WORDS, ST_SAD_LO, ST_SAD_HI, ST_GATE, ST_GATED_TOTAL = 24, 8, 9, 17, 18
 
 
 class Fh264Error(RuntimeError):
@@ -42,6 +44,11 @@ class Fh264Error(RuntimeError):
 
 class Params(C.Structure):
     _fields_ = [("qp", C.c_int32), ("window", C.c_int32), ("maxdiff_set", C.c_int32), ("basic", C.c_int32)]
+
+
+class StreamOutStruct(C.Structure):        # struct fh264_stream_out
+    _fields_ = [("records", C.c_void_p), ("slice", C.c_void_p), ("slice_stride", C.c_size_t), ("slice_copy_bytes", C.c_size_t),
+                ("first_bit", C.c_int), ("slice_stat", C.c_void_p), ("mb_info", C.c_void_p), ("status", C.c_void_p)]
 
 
 def lib_path() -> str:
@@ -99,6 +106,10 @@ def load_library():
     L.fh264_band_config.argtypes = [vp, i32, i32, i32, i32]
     L.fh264_ipc_export.argtypes = [vp, i32, vp]
     L.fh264_ipc_import.argtypes = [vp, i32, i32, vp]
+    L.fh264_encode_p_stream.argtypes = [vp, i32, i32, C.POINTER(Params), i32, C.POINTER(StreamOutStruct)]
+    L.fh264_set_pipeline.argtypes = [vp, i32]
+    L.fh264_debug_trace.argtypes = [vp, vp]
+    L.fh264_upload_source_batch.argtypes = [vp, i32, i32, vp, C.c_size_t, i32]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
@@ -146,6 +157,36 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+class StreamOut:
+    """Pinned host buffers one fh264_encode_p_stream step writes (records / device-CAVLC slice data / side information / status)."""
+
+    def __init__(self, nseq, nmb, records=False, slice_bytes=0, mb_info=False, status=True, first_bit=0):
+        self.nseq, self.nmb = nseq, nmb
+        self.records = PinnedArray((nseq, nmb), MB_RESULT_DTYPE) if records else None
+        self.slice = PinnedArray((nseq, slice_bytes), np.uint8) if slice_bytes else None
+        self.slice_stat = PinnedArray((nseq, 2), np.uint32) if slice_bytes else None
+        self.mb_info = PinnedArray((nseq, nmb), CAVLC_MB_INFO_DTYPE) if (slice_bytes and mb_info) else None
+        self.status = PinnedArray((nseq, STATUS_WORDS), np.uint32) if status else None
+        g = lambda a: a.ptr if a is not None else None
+        self.struct = StreamOutStruct(g(self.records), g(self.slice), slice_bytes, slice_bytes, first_bit, g(self.slice_stat), g(self.mb_info), g(self.status))
+
+    def coded(self):
+        """Per sequence: True = coded as a P picture, False = stopped by the scene gate (code it with encode_i)."""
+        return [int(self.status.array[b, ST_GATE]) == 0 for b in range(self.nseq)]
+
+    def scene_sad(self):
+        st = self.status.array
+        return [int(st[b, ST_SAD_LO]) | (int(st[b, ST_SAD_HI]) << 32) for b in range(self.nseq)]
+
+    def slices(self):
+        """[(bytes, nbits)] per sequence (only what slice_copy_bytes brought home)."""
+        res = []
+        for b in range(self.nseq):
+            nb = int(self.slice_stat.array[b, 1])
+            res.append((self.slice.array[b, :min((nb + 7) // 8, self.slice.array.shape[1])].copy(), nb))
+        return res
 
 
 class Session:
@@ -233,6 +274,22 @@ class Session:
         fn = self.L.fh264_encode_p if sync else self.L.fh264_encode_p_async
         self._ck(fn(self.handle, seq0, nseq, C.byref(prm), _ptr(out) if download else None))
         return out if download else None
+
+    def set_pipeline(self, on):
+        self._ck(self.L.fh264_set_pipeline(self.handle, 1 if on else 0))
+
+    def upload_source_batch(self, ptr, stride, seq0=0, nseq=None, device=False):
+        """Source pictures of sequences [seq0, seq0 + nseq) from one block (Y | Cb | Cr per sequence, `stride` bytes apart): raw
+        pointer to pinned host memory, or to device memory with device=True; asynchronous."""
+        nseq = self.batch - seq0 if nseq is None else nseq
+        self._ck(self.L.fh264_upload_source_batch(self.handle, seq0, nseq, C.c_void_p(ptr), stride, 1 if device else 0))
+
+    def encode_p_stream(self, qp, window, maxdiff_set, basic=0, seq0=0, nseq=None, scene_gate=True, out=None):
+        """One step without a host round trip (fh264_encode_p_stream). `out`: a StreamOut (pinned buffers) or None; everything it
+        receives is valid after sync()."""
+        nseq = self.batch - seq0 if nseq is None else nseq
+        prm = Params(int(qp), int(window), int(maxdiff_set), int(basic))
+        self._ck(self.L.fh264_encode_p_stream(self.handle, seq0, nseq, C.byref(prm), 1 if scene_gate else 0, C.byref(out.struct) if out is not None else None))
 
     def picture_status(self, seq):
         self._ck(self.L.fh264_picture_status(self.handle, seq))
@@ -347,6 +404,11 @@ class Session:
         buf = np.frombuffer(blob, np.uint8).copy()
         assert buf.size == 9 * 64
         self._ck(self.L.fh264_ipc_import(self.handle, seq, peer_rank, _ptr(buf)))
+
+    def debug_trace(self):
+        out = np.zeros((3, 8, 5), np.float32)
+        self._ck(self.L.fh264_debug_trace(self.handle, _ptr(out)))
+        return out
 
     def debug_status(self, seq):
         out = np.zeros(16, np.uint32)

@@ -196,6 +196,50 @@ typedef struct fh264_cavlc_mb_info {   /* per macroblock, 32 bytes: what the ref
 int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits,
                   fh264_cavlc_mb_info *mb_info);
 
+/* ---- streaming step (no host round trip per picture) ------------------------------------------------------------------------
+ * The reference decides P vs IDR on the host before every picture (selectNALUnitType, ref_frames.cpp:185-234) and then walks the
+ * slice (RBSP_encode, rbsp_encoding.cpp:139-323); a caller that mirrors that with fh264_scene_sad + fh264_encode_p + fh264_cavlc_p
+ * synchronises with the GPU three times per picture. fh264_encode_p_stream enqueues the whole step and returns:
+ *   - scene_gate != 0: sum |frame.L - dpb.L| is measured on the device and compared with MBs << 12 (:210-224). A sequence above the
+ *     threshold is NOT coded: its reference picture, records and entropy-coder state stay as they were, status word
+ *     FH264_ST_GATE of its snapshot is 1, and the caller codes that picture with fh264_encode_i (the source picture is still
+ *     current). The first-picture and IntraEvery rules (:191) need no pixels and stay with the caller.
+ *   - records / slice data / side information / status go home on a copy stream, overlapping the dpb swap, phase R and the next
+ *     step. All output pointers are optional and must be pinned host memory (fh264_host_alloc); they are valid after fh264_sync().
+ *   - slice (device CAVLC, as fh264_cavlc_p): sequence b's bytes start at slice + b * slice_stride; only the first
+ *     slice_copy_bytes of every sequence are copied home (bound chosen by the caller: a 1080p P slice at QP 28 is ~20 KB; the
+ *     reference's own limit is 500000). slice_stat[2b] = error flags (1: a macroblock's private buffer overflowed, 2: level outside
+ *     the reference's table, 4: slice above 500000 bytes), slice_stat[2b+1] = slice_data bits (first_bit included). A slice longer
+ *     than slice_copy_bytes is complete on the device: fetch it with fh264_cavlc_p.
+ *   - status: FH264_STATUS_WORDS uint32 per sequence, the snapshot after phase C: [0] flags, [2..6] mode counts (brojTipova order),
+ *     [8],[9] scene SAD low / high word (when scene_gate), [FH264_ST_GATE] the gate, [FH264_ST_GATED_TOTAL] pictures stopped so far.
+ * fh264_set_pipeline(s, 1) (or FH264_PIPE=1 in the environment at fh264_open) software-pipelines calls with two or more sequences:
+ * the sequences are split into two halves on two streams and the latency-bound mode-decision wavefront of one half (warp-level
+ * kernel, high-priority stream) runs under the search kernels of the other half, within a call and across consecutive calls.
+ * Results are identical. Off by default: on the B200 the search kernels lose as much to the resident wavefront as the overlap
+ * gains (profiles/r02_pipeline.md), and the per-kernel timings (fh264_last_timings) are only meaningful unpipelined. */
+#define FH264_STATUS_WORDS 24
+#define FH264_ST_SAD_LO 8
+#define FH264_ST_SAD_HI 9
+#define FH264_ST_GATE 17
+#define FH264_ST_GATED_TOTAL 18
+typedef struct fh264_stream_out {
+    fh264_mb_result *records;          /* nseq * MBs, or NULL */
+    uint8_t *slice;                    /* or NULL: no entropy coding */
+    size_t slice_stride, slice_copy_bytes;
+    int first_bit;                     /* 0..7, as fh264_cavlc_p */
+    uint32_t *slice_stat;              /* 2 * nseq (required with slice) */
+    fh264_cavlc_mb_info *mb_info;      /* nseq * MBs, or NULL */
+    uint32_t *status;                  /* FH264_STATUS_WORDS * nseq, or NULL */
+} fh264_stream_out;
+int fh264_encode_p_stream(fh264_session *s, int seq0, int nseq, const fh264_params *p, int scene_gate, const fh264_stream_out *out);
+int fh264_set_pipeline(fh264_session *s, int on);
+
+/* `frame` := the source pictures of sequences [seq0, seq0 + nseq) from ONE host block (sequence b's Y, Cb, Cr planes contiguous at
+ * block + b * stride): one call per step instead of one per sequence (ReadFromY4M per process, fileIO.cpp:286-337). Asynchronous,
+ * double buffered like fh264_upload_source. device != 0: the block is device memory (device-to-device copies). */
+int fh264_upload_source_batch(fh264_session *s, int seq0, int nseq, const void *block, size_t stride, int device);
+
 /* ---- decoder inverse path ------------------------------------------------------------------------
  * Reconstructs the P picture described by `records` ([nseq][MBs]: mb_type, quadrant MVs and levels, i.e. what RBSP_decode holds
  * per macroblock after entropy decoding, rbsp_decoding.cpp:98-109,330-346) from the current reference picture with the same
@@ -253,6 +297,9 @@ int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const uint8_t *ha
 /* Snapshot of the 16 status words of sequence seq after phase C of its last encode_p: [0] flags, [1] stage-2 pool
  * entries used, [2..6] mode counts, [12] partitions redone by the large-buffer stage-2 launch. */
 int fh264_debug_status(fh264_session *s, int seq, uint32_t out[16]);
+/* FH264_TRACE=1 (environment, read by fh264_open): out[3][8][5] = ms of phase A start / end, phase B end, phase C end, phase R end of the
+ * last 8 pictures of the two pipeline lanes and the session stream, relative to the oldest of them; -1 where nothing was recorded. */
+int fh264_debug_trace(fh264_session *s, float *out);
 
 /* Debug: clock64() samples of the phase-B wavefront, 12 int64 per macroblock of sequence seq ([0] CTA start,
  * [1] prefetch issued, [2] dependencies satisfied, [3] neighbour MVs loaded, [4] P_Skip decided, [5..8] partitions

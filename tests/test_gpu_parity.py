@@ -374,11 +374,15 @@ def test_other_window_sizes_against_oracle(window):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("force_miss", ["0", "1"])
 @pytest.mark.parametrize("w,h", [(16, 16), (48, 16), (16, 64), (32, 32)])
-def test_tiny_pictures_against_oracle(w, h):
+def test_tiny_pictures_against_oracle(w, h, force_miss, monkeypatch):
     """One macroblock, one macroblock row, one macroblock column: every neighbour-availability corner of the wavefront, search
-    windows and the 64x64 index tiles larger than the picture."""
+    windows and the 64x64 index tiles larger than the picture. force_miss: the warp-level phase B searches every partition itself
+    (windows that leave the picture, P_Skip trials whose prediction crosses the picture edge)."""
     from oracle import port
+    monkeypatch.setenv("FH264_PBW", force_miss)
+    monkeypatch.setenv("FH264_PBW_FORCE_MISS", force_miss)
     qp, window, maxdiff = 30, 32, 3
     clip = synth.SynthClip(w, h, 50 + w + h, square=False)
     for t in (1, 2):
@@ -399,13 +403,24 @@ def test_tiny_pictures_against_oracle(w, h):
         assert bits > 0
 
 
-@pytest.mark.parametrize("spec", ["1", "0"])
+@pytest.mark.parametrize("spec", ["1", "0", "block", "miss", "miss-adaptive", "miss-basic"])
 def test_speculative_fast_path_and_full_search_agree_with_the_oracle(spec, monkeypatch):
     """Phase S (spec.cuh) guesses the integer predictor and leaves finalists; phase B falls back to the full search on a wrong
-    guess. Both paths against the oracle over chained pictures (the second picture also has the temporal guess), with the
-    fast path switched off (FH264_SPEC=0: every partition takes the full search) and on (most partitions must hit)."""
-    monkeypatch.setenv("FH264_SPEC", spec)
+    guess. All paths against the oracle over chained pictures (the second picture also has the temporal guess): the fast path
+    switched off (FH264_SPEC=0: every partition takes the block-level full search) and on (most partitions must hit; "block":
+    with the block-level kernel k_phase_b instead of the warp-level k_phase_b_warp), and the warp-level kernel with every lookup
+    treated as a miss (FH264_PBW_FORCE_MISS=1: every partition reruns the warp-level search for its true predictor and every
+    P_Skip trial is measured in the wavefront; also with adaptive MAXDIFF and with BasicInterEncoding)."""
+    monkeypatch.setenv("FH264_SPEC", "0" if spec == "0" else "1")
+    monkeypatch.setenv("FH264_PBW", "0" if spec == "block" else "1")
+    if spec.startswith("miss"):
+        monkeypatch.setenv("FH264_PBW_FORCE_MISS", "1")
     w, h, qp, window, maxdiff = 320, 208, 27, 32, 3
+    basic = 0
+    if spec == "miss-adaptive":
+        maxdiff = -1
+    if spec == "miss-basic":
+        basic = 1
     clip = synth.SynthClip(w, h, 57)
     o = port.Oracle(w, h)
     ref = clip.frame(0)
@@ -414,16 +429,16 @@ def test_speculative_fast_path_and_full_search_agree_with_the_oracle(spec, monke
         for t in range(1, 4):
             cur = clip.frame(t)
             assert not o.phase_r(ref[0])
-            erec, erecon = o.encode_p(cur, ref, qp, window, maxdiff)
+            erec, erecon = o.encode_p(cur, ref, qp, window, maxdiff, basic)
             s.upload_source(0, *cur)
-            got = fh.records_to_ints(s.encode_p(qp, window, maxdiff)[0])
+            got = fh.records_to_ints(s.encode_p(qp, window, maxdiff, basic)[0])
             assert np.array_equal(got, erec), np.argwhere(got != erec)[:6]
             assert all(np.array_equal(a, b) for a, b in zip(s.download_recon(0), erecon))
             st = s.debug_status(0)
             hits, misses = int(st[13]), int(st[14])
             coded = int((erec[:, 0] != 31).sum())
             assert hits + misses == 4 * coded, (hits, misses, coded)
-            if spec == "0":
+            if spec == "0" or spec.startswith("miss"):
                 assert hits == 0
             else:
                 assert hits > 2 * misses, (hits, misses)

@@ -594,12 +594,16 @@ def band_measure(args, rank, world, local):
     bs.upload_recon(*clip[0])
     t = 1
 
+    from h264_fer_b200.native import StreamOut
+    sout = StreamOut(1, nmb)
+
     def step():
+        # one picture: scene SAD measured on the device (every rank holds the whole picture: same value everywhere), phases A / B / C
+        # on this rank's band, reconstruction exchange, picture barrier, phase R — no host round trip
         nonlocal t
         p = dev[pingpong(t, CLIP_LEN)].data_ptr(); t += 1
-        bs.s.upload_source_ptrs(0, p, p + ysz, p + ysz + csz, device=True)
-        bs.s.scene_sad_batch()
-        bs.s.encode_p(QP, WINDOW, MAXDIFF, 0, out=results.array, sync=False, download=False)
+        bs.s.upload_source_batch(p, ysz + 2 * csz, device=True)
+        bs.s.encode_p_stream(QP, WINDOW, MAXDIFF, 0, scene_gate=2, out=sout)
 
     for _ in range(Wu):
         step()

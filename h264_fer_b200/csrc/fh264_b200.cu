@@ -670,7 +670,7 @@ static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh26
     k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, L.d_ticket);
     if (gate) {
         k_scene_sad<<<dim3(nseq >= 8 ? 74 : 296, nseq), 256, 0, st>>>(s->d_seqs, seq0, g);
-        k_scene_gate<<<1, nseq, 0, st>>>(s->d_seqs, seq0, (unsigned long long)g.nmb << 12);
+        if (gate == 1) k_scene_gate<<<1, nseq, 0, st>>>(s->d_seqs, seq0, (unsigned long long)g.nmb << 12);
     }
     if (hold) CK(cudaStreamWaitEvent(st, hold, 0));
     cudaEvent_t *tr = s->trace ? L.tr[L.tr_n++ & 7] : nullptr;
@@ -762,7 +762,7 @@ static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh26
     CK(cudaEventRecord(L.ev_done, st));
     L.busy = true;
     for (int b = seq0; b < seq0 + nseq; b++) {
-        if (gate) { if (!s->gate_calls[b]) { s->saved_prev_p[b] = s->prev_p[b]; s->saved_last_i[b] = s->last_i[b]; } s->gate_calls[b]++; }
+        if (gate == 1) { if (!s->gate_calls[b]) { s->saved_prev_p[b] = s->prev_p[b]; s->saved_last_i[b] = s->last_i[b]; } s->gate_calls[b]++; }
         else s->gate_calls[b] = 0;
         s->prev_p[b] = 1; s->last_i[b] = 0;
     }
@@ -855,7 +855,8 @@ extern "C" int fh264_set_pipeline(fh264_session *s, int on)
 extern "C" int fh264_encode_p_stream(fh264_session *s, int seq0, int nseq, const fh264_params *p, int scene_gate, const fh264_stream_out *out)
 {
     int rc = check_encode_p(s, seq0, nseq, p); if (rc) return rc;
-    if (scene_gate && s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "the device-side scene gate is not available in band mode");
+    if (scene_gate == 1 && s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "the device-side scene gate is not available in band mode (scene_gate = 2 measures only)");
+    if (scene_gate < 0 || scene_gate > 2) return fail(FH264_E_ARG, "scene_gate must be 0, 1 or 2");
     StreamOut o;
     memset(&o, 0, sizeof o);
     if (out) {
@@ -868,7 +869,7 @@ extern "C" int fh264_encode_p_stream(fh264_session *s, int seq0, int nseq, const
             o.slice_stat = out->slice_stat; o.mb_info = out->mb_info;
         }
     }
-    return encode_dispatch(s, seq0, nseq, p, scene_gate ? 1 : 0, s->pipeline != 0, o);
+    return encode_dispatch(s, seq0, nseq, p, scene_gate, s->pipeline != 0, o);
 }
 
 // Decoder inverse path: reconstructs the P picture described by `records` (quadrant MVs, mb_type,

@@ -289,7 +289,7 @@ class Session:
         receives is valid after sync()."""
         nseq = self.batch - seq0 if nseq is None else nseq
         prm = Params(int(qp), int(window), int(maxdiff_set), int(basic))
-        self._ck(self.L.fh264_encode_p_stream(self.handle, seq0, nseq, C.byref(prm), 1 if scene_gate else 0, C.byref(out.struct) if out is not None else None))
+        self._ck(self.L.fh264_encode_p_stream(self.handle, seq0, nseq, C.byref(prm), int(scene_gate), C.byref(out.struct) if out is not None else None))
 
     def picture_status(self, seq):
         self._ck(self.L.fh264_picture_status(self.handle, seq))

@@ -200,7 +200,9 @@ int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *
  * The reference decides P vs IDR on the host before every picture (selectNALUnitType, ref_frames.cpp:185-234) and then walks the
  * slice (RBSP_encode, rbsp_encoding.cpp:139-323); a caller that mirrors that with fh264_scene_sad + fh264_encode_p + fh264_cavlc_p
  * synchronises with the GPU three times per picture. fh264_encode_p_stream enqueues the whole step and returns:
- *   - scene_gate != 0: sum |frame.L - dpb.L| is measured on the device and compared with MBs << 12 (:210-224). A sequence above the
+ *   - scene_gate == 2: sum |frame.L - dpb.L| is measured on the device and reported in the status words, nothing else changes
+ *     (the only form available in band mode, where every rank holds the whole picture and measures the same value).
+ *   - scene_gate == 1: the sum is also compared with MBs << 12 (:210-224). A sequence above the
  *     threshold is NOT coded: its reference picture, records and entropy-coder state stay as they were, status word
  *     FH264_ST_GATE of its snapshot is 1, and the caller codes that picture with fh264_encode_i (the source picture is still
  *     current). The first-picture and IntraEvery rules (:191) need no pixels and stay with the caller.

@@ -17,7 +17,7 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, w, h, seed, npics, qp, window, maxdiff, q):
+def _worker(rank, world, port, w, h, seed, npics, qp, window, maxdiff, q, stream=False):
     import torch
     import torch.distributed as dist
     import h264_fer_b200 as fh
@@ -30,12 +30,31 @@ def _worker(rank, world, port, w, h, seed, npics, qp, window, maxdiff, q):
     clip = synth.SynthClip(w, h, seed)
     bs = BandSession(w, h, device=rank)
     bs.upload_recon(*clip.frame(0))
+    prev_recon_y = clip.frame(0)[0]
     out = []
     for t in range(1, npics):
-        bs.upload_source(*clip.frame(t))
-        band = bs.encode_p(qp, window, maxdiff)
+        if stream:
+            # the streaming step (fh264_encode_p_stream) in band mode: one upload call, scene SAD measured on the device, records home
+            # on the copy stream; every rank holds the whole picture, so every rank must report the same scene SAD
+            from h264_fer_b200 import native
+            from oracle import port as oport
+            y, cb, cr = clip.frame(t)
+            blk = native.PinnedArray((1, w * h * 3 // 2), np.uint8)
+            blk.array[0] = np.concatenate([y.ravel(), cb.ravel(), cr.ravel()])
+            so = native.StreamOut(1, bs.s.nmb, records=True)
+            bs.s.upload_source_batch(blk.ptr, w * h * 3 // 2)
+            bs.s.encode_p_stream(qp, window, maxdiff, scene_gate=2, out=so)
+            bs.s.sync()
+            bs.s.picture_status(0)
+            assert so.coded() == [True]
+            assert so.scene_sad()[0] == oport.scene_sad(y, prev_recon_y), "scene SAD of picture %d on rank %d" % (t, rank)
+            band = so.records.array[0][bs.mb_slice].copy()
+        else:
+            bs.upload_source(*clip.frame(t))
+            band = bs.encode_p(qp, window, maxdiff)
         rec = bs.gather_records(band)
         recon = bs.download_recon()
+        prev_recon_y = recon[0]
         out.append((fh.records_to_ints(rec), recon))
     q.put((rank, out))
     bs.close()
@@ -43,8 +62,9 @@ def _worker(rank, world, port, w, h, seed, npics, qp, window, maxdiff, q):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="band mode needs at least 2 GPUs")
-@pytest.mark.parametrize("world,w,h,window,maxdiff", [(2, 352, 288, 32, 3), (2, 640, 480, 32, -1), (4, 352, 288, 32, 3), (8, 640, 480, 32, 3)])
-def test_band_mode_matches_oracle(world, w, h, window, maxdiff):
+@pytest.mark.parametrize("world,w,h,window,maxdiff,stream", [(2, 352, 288, 32, 3, False), (2, 640, 480, 32, -1, False), (4, 352, 288, 32, 3, False),
+                                                             (8, 640, 480, 32, 3, False), (2, 352, 288, 32, 3, True), (8, 640, 480, 32, 3, True)])
+def test_band_mode_matches_oracle(world, w, h, window, maxdiff, stream):
     if world > 2 and _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
@@ -54,7 +74,7 @@ def test_band_mode_matches_oracle(world, w, h, window, maxdiff):
     seed, npics, qp = 9, 4, 28
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, 29641, w, h, seed, npics, qp, window, maxdiff, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, 29641, w, h, seed, npics, qp, window, maxdiff, q, stream)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in range(world))

@@ -145,6 +145,32 @@ __device__ __forceinline__ int spec_lookup(const PartSpec &sp, int genx, int gen
     bx = f.mvx; by = f.mvy; bs = f.sad;
     return 1;
 }
+// The same lookup by a whole warp (all 32 lanes call it with the same arguments): lane k weighs finalist k, the winner is one
+// 32-bit warp minimum of total << 11 | stage << 9 | list position << 3 | k (total < 2^15: SAD <= 16320 plus two vector distances;
+// list positions < 64) — the order of (total, order, k). The wavefront's critical path is a chain of these lookups: as scalar
+// code by one lane it cost 0.3-0.7 us per partition (profiles/tools/phase_b_waits.py).
+__device__ __forceinline__ int spec_lookup_w(const PartSpec &sp, int genx, int geny, int mvpx, int mvpy, int &bx, int &by, int &bs)
+{
+    const int lane = threadIdx.x & 31;
+    const uint4 h = *(const uint4 *)&sp;                   // gx[2] | gy[2] | nf[2] | pad
+    const int gx0 = (int)(int16_t)(h.x & 0xffffu), gx1 = (int)(int16_t)(h.x >> 16), gy0 = (int)(int16_t)(h.y & 0xffffu), gy1 = (int)(int16_t)(h.y >> 16);
+    const int nf0 = (int)(h.z & 0xffu), nf1 = (int)((h.z >> 8) & 0xffu);
+    int slot = -1;
+    if (nf0 != SPEC_INVALID && gx0 == genx && gy0 == geny) slot = 0;
+    else if (nf1 != SPEC_INVALID && gx1 == genx && gy1 == geny) slot = 1;
+    if (slot < 0) return 0;
+    const int nf = slot ? nf1 : nf0;
+    uint32_t key = 0xffffffffu;
+    if (lane < nf) {
+        const SpecFinal f = sp.f[slot][lane];
+        const uint32_t total = (uint32_t)((int)f.sad + mv_cost(f.mvx, f.mvy, mvpx, mvpy));
+        key = (total << 11) | ((uint32_t)(f.order >> 14) << 9) | ((uint32_t)(f.order & 63u) << 3) | (uint32_t)lane;
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    const SpecFinal f = sp.f[slot][(int)(key & 7u)];
+    bx = f.mvx; by = f.mvy; bs = f.sad;
+    return 1;
+}
 __device__ __forceinline__ int skip_lookup(const MbSpec &ms, int vx, int vy)       // 0: skips, 1: does not, -1: not precomputed
 {
     if (vx == 0 && vy == 0) return ms.zero_ok ? 0 : 1;
@@ -569,25 +595,25 @@ __global__ void __launch_bounds__(PB_NT, PB_MINB) k_phase_b(const SeqDev *__rest
                 // partition 0 predicts from left q1 unless up q2 == up q3; partition 2 from left q3 unless own q0 == q1
                 if (!have1 && !(aU && u2x == u3x && u2y == u3y)) { poll_left(1, l1x, l1y); have1 = true; }
                 median_pred(aL, l1x, l1y, aU, u2x, u2y, aU ? 1 : aUL, aU ? u3x : d3x, aU ? u3y : d3y, p0x, p0y);
-                ok = spec_lookup(sh.spec[0], p0x >> 2, p0y >> 2, p0x, p0y, q0x, q0y, s0);
+                ok = spec_lookup_w(sh.spec[0], p0x >> 2, p0y >> 2, p0x, p0y, q0x, q0y, s0);
                 if (ok) {
                     publish(0, q0x, q0y);
                     if (dbg && lane == 0) dbg[5] = gtime_ns();
                     median_pred(1, q0x, q0y, aU, u3x, u3y, aUR ? 1 : aU, aUR ? r2x : u2x, aUR ? r2y : u2y, p1x, p1y);
-                    ok = spec_lookup(sh.spec[1], p1x >> 2, p1y >> 2, p1x, p1y, q1x, q1y, s1);
+                    ok = spec_lookup_w(sh.spec[1], p1x >> 2, p1y >> 2, p1x, p1y, q1x, q1y, s1);
                 }
                 if (ok) {
                     publish(1, q1x, q1y);
                     if (dbg && lane == 0) dbg[6] = gtime_ns();
                     if (!have3 && !(q0x == q1x && q0y == q1y)) { poll_left(3, l3x, l3y); have3 = true; }
                     median_pred(aL, l3x, l3y, 1, q0x, q0y, 1, q1x, q1y, p2x, p2y);
-                    ok = spec_lookup(sh.spec[2], p2x >> 2, p2y >> 2, p2x, p2y, q2x, q2y, s2);
+                    ok = spec_lookup_w(sh.spec[2], p2x >> 2, p2y >> 2, p2x, p2y, q2x, q2y, s2);
                 }
                 if (ok) {
                     publish(2, q2x, q2y);
                     if (dbg && lane == 0) dbg[7] = gtime_ns();
                     median_pred(1, q2x, q2y, 1, q1x, q1y, 1, q0x, q0y, p3x, p3y);
-                    ok = spec_lookup(sh.spec[3], p3x >> 2, p3y >> 2, p3x, p3y, q3x, q3y, s3);
+                    ok = spec_lookup_w(sh.spec[3], p3x >> 2, p3y >> 2, p3x, p3y, q3x, q3y, s3);
                 }
                 if (ok) {
                     publish(3, q3x, q3y);

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32, PBW_MINB) k_phase_b_warp(const SeqDev *__r
             } else median_pred(1, q2x, q2y, 1, q1x, q1y, 1, q0x, q0y, px, py);
             // the winner for predictor (px, py): lookup among the phase-S finalists, else the full search for the true gen
             const int genx = px >> 2, geny = py >> 2;
-            if (!force_miss && spec_lookup(sh.spec[pi], genx, geny, px, py, bx, by, bs)) nhit++;
+            if (!force_miss && spec_lookup_w(sh.spec[pi], genx, geny, px, py, bx, by, bs)) nhit++;
             else {
                 const int part = mb * 4 + pi, xP = mbx * 16 + (pi & 1) * 8, yP = mby * 16 + (pi >> 1) * 8;
                 uint2 rows[8];

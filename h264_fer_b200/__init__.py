@@ -8,7 +8,7 @@ is missing, every call raises.
 """
 from .native import (Fh264Error, Session, MB_RESULT_DTYPE, CAVLC_MB_INFO_DTYPE, P_SKIP, P_8x8ref0, P_L0_16x16, P_L0_L0_16x8, P_L0_L0_8x16,
                      lib_path, load_library, records_to_ints, MB_RESULT_I_DTYPE, i_records_to_ints)
-from .encoder import SequenceEncoder, NAL_IDR, NAL_NON_IDR
+from .encoder import SequenceEncoder, BatchEncoder, NAL_IDR, NAL_NON_IDR
 
-__all__ = ["Fh264Error", "Session", "SequenceEncoder", "MB_RESULT_DTYPE", "CAVLC_MB_INFO_DTYPE", "lib_path", "load_library", "records_to_ints", "MB_RESULT_I_DTYPE", "i_records_to_ints",
+__all__ = ["Fh264Error", "Session", "SequenceEncoder", "BatchEncoder", "MB_RESULT_DTYPE", "CAVLC_MB_INFO_DTYPE", "lib_path", "load_library", "records_to_ints", "MB_RESULT_I_DTYPE", "i_records_to_ints",
            "P_SKIP", "P_8x8ref0", "P_L0_16x16", "P_L0_L0_16x8", "P_L0_L0_8x16", "NAL_IDR", "NAL_NON_IDR"]

@@ -689,7 +689,8 @@ static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh26
     if (s->use_spec) {
         // phase S: the search completed for the guessed integer predictors (spec.cuh)
         const size_t smems = 4 * (size_t)qwin_bytes(g1) + 4 * sizeof(SpecWarp) + 16;
-        k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, 1, wm, s->use_tma ? s->d_tmaps : nullptr);
+        static const int spec_flags = 1 | ((getenv("FH264_SPEC_NG") && atoi(getenv("FH264_SPEC_NG")) == 1) ? 2 : 0);   // development knob
+        k_spec<<<dim3(g.band_nmb, nseq), 128, smems, st>>>(s->d_seqs, seq0, g, prm, spec_flags, wm, s->use_tma ? s->d_tmaps : nullptr);
         k_skipspec<<<dim3((g.band_nmb + 3) / 4, nseq), 128, 4 * SKIPWIN_BYTES + 64, st>>>(s->d_seqs, seq0, g, prm, s->use_tma ? s->d_tmaps16 : nullptr);
         CKL();
     }

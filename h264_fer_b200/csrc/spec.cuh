@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(128, FH_SPEC_MINB) k_spec(const SeqDev *__rest
             if (ox != g0x || oy != g0y) { g1x = ox; g1y = oy; ng = 2; }
         }
     }
-    if (use_prev && ng == 0) {
+    if ((use_prev & 1) && ng == 0) {
         const uint32_t pg = S.prev_gen[part];
         if (pg != SPEC_PREV_NONE) {
             const int px = (int16_t)(pg & 0xffffu), py = (int16_t)(pg >> 16);
@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(128, FH_SPEC_MINB) k_spec(const SeqDev *__rest
         }
     }
     if (ng == 0) ng = 1;                                   // no list and no history: guess gen = (0, 0)
+    if (use_prev & 2) ng = 1;                              // (development knob FH264_SPEC_NG=1: first guess only)
     for (int slot = 0; slot < ng; slot++)
         spec_slot(S, g, prm, part, xP, yP, rows, fq, n3, n2w, s2_off, slot ? g1x : g0x, slot ? g1y : g0y, slot, sw, win, out, tmap, phase, wm);
     if (ng == 1 && lane == 0) { out->gx[1] = SPEC_NOGUESS; out->gy[1] = SPEC_NOGUESS; out->nf[1] = SPEC_INVALID; }

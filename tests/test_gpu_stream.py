@@ -194,3 +194,32 @@ def test_stream_error_paths():
         with pytest.raises(fh.Fh264Error) as e:
             s.upload_source_batch(0, 10)
         assert e.value.code == -1
+
+
+def test_batch_encoder_follows_the_reference_picture_type_rules():
+    """BatchEncoder (host mirror of selectNALUnitType + RBSP_encode for a batch, h264_fer_b200/encoder.py) against one
+    SequenceEncoder per sequence driven the reference's way: first picture and every IntraEvery-th picture IDR (ref_frames.cpp:191),
+    scene cut IDR (:210-224), everything else P — same picture types and the same slice data, picture by picture."""
+    nseq, npic, intra_every = 3, 7, 5
+    clips = _clips(nseq, npic, seed0=80)
+    other = synth.SynthClip(W, H, 555, pan=(0, 0))
+    for t in range(3, npic):                                 # sequence 2 cuts at picture 3
+        clips[2][t] = other.frame(t)
+    want = []
+    with fh.Session(W, H, batch=nseq) as s:
+        encs = [fh.SequenceEncoder(s, b, qp=QP, window=WINDOW, maxdiff_set=MAXDIFF, intra_every=intra_every) for b in range(nseq)]
+        for t in range(npic):
+            row = []
+            for b in range(nseq):
+                nal, _ = encs[b].encode_picture(*clips[b][t])
+                sl = s.cavlc_i(first_bit=5, seq0=b, nseq=1)[0] if nal == fh.NAL_IDR else s.cavlc_p(first_bit=5, seq0=b, nseq=1)[0]
+                row.append((nal,) + sl)
+            want.append(row)
+    assert [r[2][0] for r in want] == [5, 1, 1, 5, 1, 5, 1], "sequence 2 must see the cut at picture 3 besides the periodic IDRs"
+    with fh.Session(W, H, batch=nseq) as s:
+        be = fh.BatchEncoder(s, qp=QP, window=WINDOW, maxdiff_set=MAXDIFF, intra_every=intra_every, first_bit=5)
+        for t in range(npic):
+            got = be.encode_pictures([clips[b][t] for b in range(nseq)])
+            for b in range(nseq):
+                assert got[b][0] == want[t][b][0], "picture %d sequence %d: nal_unit_type" % (t, b)
+                assert got[b][2] == want[t][b][2] and np.array_equal(got[b][1], want[t][b][1]), "picture %d sequence %d: slice data" % (t, b)

@@ -23,7 +23,6 @@ __device__ __forceinline__ int fh_idx_(int i, int n, int line) { if ((unsigned)i
 #define FH_TSTART_PITCH 16386   // uint16 per tile: 16384 cell starts + total + pad
 #define FH_S3_MAX 33            // list slots evaluated in stages 2/3 (moestimation.cpp:498,511)
 #define FH_S1_MAX 17            // list slots evaluated in stage 1 (moestimation.cpp:460)
-#define FH_S2_SMEM_CAP 2048     // stage-2 survivors held in shared memory per partition
 #define FH_MAX_WINDOW 64
 #define FH_COST_EMPTY 100000000 // stages 2/3 ignore list slots with cost >= 1e8 (moestimation.cpp:499,512)
 

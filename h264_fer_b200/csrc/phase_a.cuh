@@ -18,12 +18,6 @@
 #ifndef FH_S2_UNR
 #define FH_S2_UNR 4        // index entries in flight per lane in the stage-2 visit loop
 #endif
-#ifndef FH_S2_SADR
-#define FH_S2_SADR 8       // stage-2 SAD: candidate rows in flight per lane
-#endif
-#ifndef FH_S3_UNR
-#define FH_S3_UNR 4        // stage-3 first call: feature records in flight per lane
-#endif
 #ifndef FH_S2_MINB
 #define FH_S2_MINB 16     // 64 registers, 16 CTAs of two warps per SM (A/B on the B200: 2.81 -> 2.60 ms against 12)
 #endif
@@ -58,96 +52,6 @@ __device__ __forceinline__ void s3_decode(int i, int n3a, int w3, int g3, uint32
     const int t = a ? i : (i - n3a) >> 4, w = a ? w3 : w1, gg = a ? g3 : g1;
     const int c = udiv_by(t, a ? i3 : i1);
     dx = c - gg; dy = t - c * w - gg; f = a ? 0 : (i - n3a) & 15;
-}
-
-struct S3Warp { WarpSelScratch ws; uint16_t members[FH_S3_MAX + 1]; uint16_t msad[FH_S3_MAX + 1]; };
-
-// Selection of the K = min(k, nvalid) smallest (cost, arrival index) pairs of cost[0..n-1] (0xffffffff = no candidate) when
-// every lane already holds the two smallest COSTS (m1 <= m2) of the elements it produced. The bound on the K-th cost
-// is the one of warp_select_smallest; survivors are the elements with cost <= bound (ties included), ranked exactly by
-// the 64-bit (cost, index) key. Same contract as warp_select_smallest.
-__device__ __forceinline__ int warp_select_costs(const uint32_t *cost, int n, int k, int nvalid, uint32_t m1, uint32_t m2, WarpSelScratch *ws, uint16_t *members)
-{
-    const int lane = threadIdx.x & 31;
-    const int K = min(k, nvalid);
-    if (K == 0) return 0;
-    const int L1 = __popc(__ballot_sync(0xffffffffu, m1 != COST_INVALID));
-    const int L2 = __popc(__ballot_sync(0xffffffffu, m2 != COST_INVALID));
-    uint32_t thr = COST_INVALID - 1;
-    if (L1 >= K) thr = __reduce_max_sync(0xffffffffu, m1 != COST_INVALID ? m1 : 0u);
-    else if (L1 + 1 >= K && L2 >= 1) thr = max(__reduce_max_sync(0xffffffffu, m1 != COST_INVALID ? m1 : 0u), __reduce_min_sync(0xffffffffu, m2));
-    else if (2 * L2 >= K) thr = __reduce_max_sync(0xffffffffu, m2 != COST_INVALID ? m2 : 0u);
-    if (L1 + L2 >= K) {
-        // tighter: the K-th smallest of the (up to 64) per-lane minima themselves — K distinct candidates lie at or below it.
-        // Bisection on the value with two ballots per step (about 20 steps); it typically halves the survivors to rank.
-        uint32_t lo = __reduce_min_sync(0xffffffffu, m1), hi = thr;
-        while (lo < hi) {
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            const int c = __popc(__ballot_sync(0xffffffffu, m1 <= mid)) + __popc(__ballot_sync(0xffffffffu, m2 <= mid));
-            if (c >= K) hi = mid; else lo = mid + 1;
-        }
-        thr = lo;
-    }
-    int ns = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const uint32_t c = i < n ? cost[i] : COST_INVALID;
-        const bool sv = c <= thr;                              // COST_INVALID > thr always
-        const unsigned b = __ballot_sync(0xffffffffu, sv);
-        if (sv) {
-            const int pos = ns + __popc(b & ((1u << lane) - 1u));
-            if (pos < WSEL_CAP) { ws->skey[pos] = ((u64)c << 16) | (u64)i; ws->sidx[pos] = (uint16_t)i; }
-        }
-        ns += __popc(b);
-    }
-    __syncwarp();
-    if (ns > WSEL_CAP) {
-        // the bound was loose (the good candidates sat in few lanes): bisect the exact K-th smallest cost, then compact again
-        uint32_t lo = 0, hi = thr;
-        while (lo < hi) {
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            int c = 0;
-            for (int i = lane; i < n; i += 32) c += cost[i] <= mid;
-            if (__reduce_add_sync(0xffffffffu, c) >= K) hi = mid; else lo = mid + 1;
-        }
-        thr = lo;
-        ns = 0;
-        for (int base = 0; base < n; base += 32) {
-            const int i = base + lane;
-            const uint32_t c = i < n ? cost[i] : COST_INVALID;
-            const bool sv = c <= thr;
-            const unsigned b = __ballot_sync(0xffffffffu, sv);
-            if (sv) {
-                const int pos = ns + __popc(b & ((1u << lane) - 1u));
-                if (pos < WSEL_CAP) { ws->skey[pos] = ((u64)c << 16) | (u64)i; ws->sidx[pos] = (uint16_t)i; }
-            }
-            ns += __popc(b);
-        }
-        __syncwarp();
-    }
-    if (ns <= WSEL_CAP) {
-        for (int s = lane; s < ns; s += 64) {
-            const u64 ka = ws->skey[s];
-            const bool hb = s + 32 < ns;
-            const u64 kb = hb ? ws->skey[s + 32] : 0ull;
-            int ra = 0, rb = 0;
-            for (int j = 0; j < ns; j++) { const u64 kj = ws->skey[j]; ra += kj < ka; rb += kj < kb; }
-            if (ra < K) members[ra] = ws->sidx[s];
-            if (hb && rb < K) members[rb] = ws->sidx[s + 32];
-        }
-    } else {
-        // degenerate (flat content: hundreds of candidates tie at the K-th cost): rank against every candidate
-        for (int i = lane; i < n; i += 32) {
-            const uint32_t c = cost[i];
-            if (c > thr) continue;
-            const u64 key = ((u64)c << 16) | (u64)i;
-            int rank = 0;
-            for (int j = 0; j < n && rank < K; j++) rank += (((u64)cost[j] << 16) | (u64)j) < key;
-            if (rank < K) members[rank] = (uint16_t)i;
-        }
-    }
-    __syncwarp();
-    return K;
 }
 
 #define S2_BINS 384           // (j, side) bins: 2*j + side, j <= 180

@@ -207,7 +207,7 @@ struct PBShared {
     uint32_t slow_pos[FH_S3_MAX + 1];        // (dx + 512) | (dy + 512) << 16 of the selected candidates, list order
 };
 
-// Block-cooperative version of warp_select_smallest (warp_select.cuh): the K = min(k, #valid) smallest of
+// Block-cooperative selection: the K = min(k, #valid) smallest of
 // keyfn(0..n-1) in ascending order into members[]. EVERY warp scans all keys (n/32 per lane), so all warps derive the
 // same tight upper bound on the k-th key without exchanging anything; the survivors are then compacted and ranked by
 // all PB_NT threads. `call` alternates the survivor counter so that no reset barrier is needed. Ends with a barrier.

@@ -2,10 +2,10 @@
 //
 // The reference keeps insertion-sorted lists (moestimation.cpp:277-291); downstream only list MEMBERSHIP (the k smallest by
 // (cost, arrival)) and the order among members matter. Round 1 stored every cost in shared memory and selected afterwards
-// (warp_select_costs: ~1500 warp instructions and 6 KB per partition in stage 3). Here candidates are offered as they are
+// (~1500 warp instructions and 6 KB per partition in stage 3). Here candidates are offered as they are
 // produced: a candidate is kept only if its key (cost << 16 | arrival index) is at or below a running bound, kept candidates go
 // to a small buffer by a ballot-compacted append, and the bound tightens from the two smallest costs every lane has produced
-// (the same bound argument as warp_select.cuh: the k-th smallest of the per-lane minima bounds the k-th smallest cost).
+// (the k-th smallest of the per-lane minima bounds the k-th smallest cost).
 // Exact for any arrival order and any number of ties: when the buffer would overflow it is reduced to exactly its k smallest
 // keys (bisection on the key), which makes the k-th of them the new bound.
 #pragma once

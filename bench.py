@@ -6,9 +6,13 @@ GPU codes `--seqs` independent synthetic 1080p sequences (coded 1920x1072, IPPP,
 MAXDIFF 3) in lockstep; one STEP = one P picture of every sequence on the GPU: scene-change SAD (a12), phases A/B/C
 (a3-a10), dpb swap (a11), phase R (a2). Weak scaling: per-GPU work fixed, no data-path collective.
 
+One step = fh264_upload_source_batch + fh264_encode_p_stream (include/fh264_b200.h): no host round trip per picture; the
+scene-change IDR rule is decided on the device.
+
   value  : pictures/s with the source pictures already resident in HBM (device-to-device into `frame`)
-  e2e    : the same through the C ABI with HOST buffers: pinned H2D of every source picture and D2H of every
-           macroblock record (832 B/MB) inside the timed region
+  e2e    : the same through the C ABI with HOST buffers: pinned H2D of every source picture and, inside the timed region, D2H
+           of what the reference's host code needs to write the slice NAL unit (entropy-coded slice data, 32 B/MB side
+           information, status words); `device_cavlc.e2e_records`: the 832-byte macroblock records instead
   --impl reference : the unmodified reference encoder (oracle/_ref/ref_encoder, compiled from /root/reference in the
            build container) on the box's host cores, one single-threaded process per sequence.
 

@@ -185,11 +185,14 @@ static cudaError_t sync_streams(fh264_session *s)
 }
 
 // Wavefront visiting order x + slope * y. Any slope >= 2 keeps every dependency (left, up, up-right, up-left) on a smaller
-// ticket. 3 is the measured optimum (a macroblock needs THREE quadrants of its up-right neighbour, so with slope 2 it is drawn
-// before they can be ready and its CTA idles: 1080p alone 4.07 -> 3.51 ms, 8 sequences 5.60 -> 5.24 ms); FH264_WF_SLOPE overrides.
-static void wf_slope(int &num, int &den)      // order key = den * x + num * y, slope = num / den ("3" or "5/2")
+// ticket. With phase S in front a macroblock is ~1.2 us of lookups and what bounds the wavefront is the serial chain along the first
+// macroblock row (every macroblock there predicts from its left neighbour alone) followed by the chain down the right picture edge:
+// the rows below can only trail the first one, so the best order is close to raster order — tickets are not spent on macroblocks
+// that wait for the row above. Measured, 8 sequences: slope 2 / 3 / 4 / 6 / 8 / 12 -> phase B 1.27 / 1.14 / 1.09 / 1.04 / 1.02 / 1.03 ms
+// (round 1's block-level search had its optimum at 3). FH264_WF_SLOPE overrides.
+static void wf_slope(int &num, int &den)      // order key = den * x + num * y, slope = num / den ("8" or "5/2")
 {
-    num = 3; den = 1;
+    num = 8; den = 1;
     if (const char *e = getenv("FH264_WF_SLOPE")) { int a = 0, b = 1; if (sscanf(e, "%d/%d", &a, &b) >= 1 && b >= 1 && a >= 2 * b) { num = a; den = b; } }
 }
 

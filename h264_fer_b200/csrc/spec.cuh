@@ -303,23 +303,35 @@ __global__ void __launch_bounds__(128, FH_SPEC_MINB) k_spec(const SeqDev *__rest
     const int part = g.band_mb0 * 4 + blockIdx.x * 4 + warp;
     int xP, yP;
     part_origin(g, part, xP, yP);
+    // every global load of the prologue is issued before anything waits for one (the warp is latency bound here: they used to be
+    // four dependent round trips — source rows, partition record, its list, the neighbours' proxies)
     uint2 rows[8];
     load_cur8x8(S.cur[0], g, xP, yP, rows);
+    PartSpec *out = &S.spec[part];
+    int n3 = 0; uint32_t n2w = 0, s2_off = 0;
+    PartA pa;
+    S3Entry e0, e1;
+    uint32_t own = SPEC_PREV_NONE;
+    int pdx = 0, pdy = 0;
+    if (!prm.basic) {
+        pa = S.parta[part];
+        e0 = S.s3[(size_t)part * FH_S3_MAX + lane];                                   // the list is read whole (33 slots); n3 says how much of it counts
+        if (lane == 0) e1 = S.s3[(size_t)part * FH_S3_MAX + 32];
+        own = __ldg(&S.proxy[part]);
+        proxy_predictor(S, g, part >> 2, part & 3, pdx, pdy);
+        n3 = pa.n3; n2w = pa.n2; s2_off = pa.s2_off;
+        sw->s3[lane] = e0;
+        if (lane == 0) sw->s3[32] = e1;
+    }
     int s[5];
     block_sums(rows, s);
     const FeatQ fq = feat_query(s);
-    PartSpec *out = &S.spec[part];
-    int n3 = 0; uint32_t n2w = 0, s2_off = 0;
-    if (!prm.basic) { const PartA pa = S.parta[part]; n3 = pa.n3; n2w = pa.n2; s2_off = pa.s2_off; }
-    for (int i = lane; i < n3; i += 32) sw->s3[i] = S.s3[(size_t)part * FH_S3_MAX + i];
     __syncwarp();
     // guesses
     int g0x = 0, g0y = 0, g1x = 0, g1y = 0, ng = 0;
     if (!prm.basic) {
-        int dx, dy;
-        proxy_predictor(S, g, part >> 2, part & 3, dx, dy);
+        const int dx = pdx, dy = pdy;
         g0x = dx >> 2; g0y = dy >> 2; ng = 1;
-        const uint32_t own = __ldg(&S.proxy[part]);
         if (own != SPEC_PREV_NONE) {
             const int ox = (int)(int16_t)(own & 0xffffu) >> 2, oy = (int)(int16_t)(own >> 16) >> 2;
             if (ox != g0x || oy != g0y) { g1x = ox; g1y = oy; ng = 2; }

@@ -83,3 +83,59 @@ def test_1080p_picture_against_oracle_over_the_qp_sweep(qp):
         recon = s.download_recon(0)
     assert np.array_equal(got, want), np.argwhere(got != want)[:6]
     assert all(np.array_equal(a, b) for a, b in zip(recon, want_recon))
+
+
+@pytest.mark.parametrize("piped", [0, 1])
+def test_streaming_step_soak_against_the_plain_call_sequence(piped):
+    """The asynchronous step (fh264_upload_source_batch + fh264_encode_p_stream, nothing synchronised between pictures) over a long
+    chain with periodic scene cuts, against the host-driven sequence fh264_scene_sad + fh264_encode_p / fh264_encode_i picture by
+    picture: any ordering bug between the coding stream, the copy stream and the upload stream shows as a drifting reconstruction."""
+    from h264_fer_b200 import native
+    w, h, nseq, npic, qp, window, maxdiff = 352, 288, 4, 48, 28, 32, 3
+    clips = [[synth.SynthClip(w, h, 300 + b + 17 * (t // 16 if b == 1 else 0)).frame(t) for t in range(npic)] for b in range(nseq)]   # sequence 1 cuts every 16 pictures
+    pic = w * h * 3 // 2
+    want_rec, want_recon, want_idr = [], None, 0
+    with fh.Session(w, h, batch=nseq) as s:
+        for b in range(nseq):
+            s.upload_recon(b, *clips[b][0])
+        for t in range(1, npic):
+            for b in range(nseq):
+                s.upload_source(b, *clips[b][t])
+            sads = s.scene_sad_batch()
+            row = []
+            for b in range(nseq):
+                if sads[b] > (s.nmb << 12):
+                    s.encode_i(qp, seq0=b, nseq=1); row.append(None); want_idr += 1
+                else:
+                    row.append(s.encode_p(qp, window, maxdiff, seq0=b, nseq=1)[0].copy())
+            want_rec.append(row)
+        want_recon = [s.download_recon(b) for b in range(nseq)]
+    assert want_idr == 2
+    with fh.Session(w, h, batch=nseq) as s:
+        s.set_pipeline(piped)
+        for b in range(nseq):
+            s.upload_recon(b, *clips[b][0])
+        blocks, outs = [], []
+        for t in range(1, npic):
+            blk = native.PinnedArray((nseq, pic), np.uint8)
+            for b in range(nseq):
+                blk.array[b] = np.concatenate([p.ravel() for p in clips[b][t]])
+            so = native.StreamOut(nseq, s.nmb, records=True)
+            blocks.append(blk); outs.append(so)
+            s.upload_source_batch(blk.ptr, pic)
+            s.encode_p_stream(qp, window, maxdiff, scene_gate=1, out=so)
+            if any(r is None for r in want_rec[t - 1]):          # the host of a real encoder learns about a cut by looking: sync, then the IDR picture
+                s.sync()
+                coded = so.coded()
+                assert coded == [r is not None for r in want_rec[t - 1]], "picture %d" % t
+                for b in range(nseq):
+                    if not coded[b]:
+                        s.encode_i(qp, seq0=b, nseq=1)
+        s.sync()
+        for t, so in enumerate(outs):
+            for b in range(nseq):
+                if want_rec[t][b] is not None:
+                    assert np.array_equal(so.records.array[b], want_rec[t][b]), "picture %d sequence %d" % (t + 1, b)
+        for b in range(nseq):
+            s.picture_status(b)
+            assert all(np.array_equal(a, c) for a, c in zip(s.download_recon(b), want_recon[b])), "final reconstruction of sequence %d" % b

@@ -14,7 +14,7 @@ from .native import MB_RESULT_DTYPE, Session
 
 
 class BandSession:
-    def __init__(self, width, height, device, rank=None, world=None):
+    def __init__(self, width, height, device, rank=None, world=None, pipelined=True):
         import torch.distributed as dist
         self.rank = (dist.get_rank() if dist.is_initialized() else 0) if rank is None else rank
         self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else world
@@ -31,6 +31,9 @@ class BandSession:
             for r, blob in enumerate(blobs):
                 if r != self.rank:
                     self.s.ipc_import(0, r, blob)
+            if pipelined:
+                # every rank knows every band: the picture barrier becomes a wait for the ranks within the halo (fh264_band_peers)
+                self.s.band_peers(self.bands)
             dist.barrier()
 
     @property

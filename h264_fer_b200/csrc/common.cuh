@@ -53,6 +53,11 @@ struct Geo {
     // macroblock-row band of this rank (band mode): MBs [band_mb0, band_mb0 + band_nmb); whole picture otherwise
     int band_mb0, band_nmb, rank, world;
     uint32_t wmb_magic;             // udiv_magic(Wmb): macroblock address -> (x, y) without a division routine in the kernels
+    // band mode with the peers' bands known (fh264_band_peers): luma rows [halo_y0, halo_y1) (multiples of 64, or H) are everything
+    // this rank's phases A / S / B / C read of the reference picture (stage 2 reaches 279 rows); phase R is restricted to them and the
+    // picture barrier only waits for the ranks in wait_mask, whose bands they touch. Whole picture / all ranks otherwise.
+    int halo_y0, halo_y1;
+    uint32_t wait_mask;
 };
 #define FH_MAX_WORLD 8
 

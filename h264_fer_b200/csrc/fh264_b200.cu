@@ -89,6 +89,7 @@ struct fh264_session {
     int tmap_rows;
     int use_tma;                    // FH264_TMA=0: fill the pixel windows with ordinary loads (development knob)
     int use_bw;                     // phase B kernel: 1 warp-level (phase_bw.cuh), 0 block-level, -1 (default) warp-level on the pipeline lanes only (FH264_PBW)
+    int sad_y0, sad_y1;             // luma rows the scene SAD covers: the picture, or this rank's band once the peers' bands are known
     int trace;                      // FH264_TRACE=1: per-lane timing events (fh264_debug_trace)
     int force_miss;                 // FH264_PBW_FORCE_MISS=1: the warp-level phase B treats every phase-S lookup as a miss (test knob)
     bool timed;
@@ -150,12 +151,14 @@ __global__ void k_swap_ref(SeqDev *seqs, int seq0)
 // A timeout (a peer is missing or far behind: this rank's reference picture lacks that peer's band) is raised in ST_FLAGS_NEXT of
 // EVERY sequence of the call — the word phase R leaves alone after k_begin_ref, which therefore runs BEFORE this kernel — and
 // becomes the status of the next picture coded from that reference (FH264_E_STATE).
-__global__ void k_band_barrier(PeerSync ps, SeqDev *seqs, int seq0, int nseq, uint32_t epoch, int rank, int world)
+// With the peers' bands known (fh264_band_peers) only the ranks whose bands touch this rank's halo are waited for (wait_mask): a rank
+// whose halo is complete goes on with phase R and the next picture while the wavefront of this one is still running further down.
+__global__ void k_band_barrier(PeerSync ps, SeqDev *seqs, int seq0, int nseq, uint32_t epoch, int rank, int world, uint32_t wait_mask)
 {
     __threadfence_system();
     for (int r = 0; r < world; r++) st_release_sys_u32(&ps.p[r][rank], epoch);
     bool ok = true;
-    for (int r = 0; r < world; r++) ok &= wait_progress(&ps.p[rank][r], epoch, true);
+    for (int r = 0; r < world; r++) if ((wait_mask >> r) & 1u) ok &= wait_progress(&ps.p[rank][r], epoch, true);
     if (!ok) for (int b = 0; b < nseq; b++) atomicOr(&seqs[seq0 + b].status[ST_FLAGS_NEXT], FLAG_TIMEOUT);
 }
 
@@ -285,6 +288,8 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     g.WH = width * height;
     g.band_mb0 = 0; g.band_nmb = g.nmb; g.rank = 0; g.world = 1;
     g.wmb_magic = udiv_magic((uint32_t)g.Wmb);
+    g.halo_y0 = 0; g.halo_y1 = height; g.wait_mask = 0xffffffffu;
+    s->sad_y0 = 0; s->sad_y1 = height;
     s->has_ref.assign(batch, 0);
     s->prev_p.assign(batch, 0);
     s->last_i.assign(batch, 0);
@@ -520,15 +525,19 @@ static int launch_phase_r(fh264_session *s, cudaStream_t st, bool timing, int se
 {
     const Geo &g = s->g;
     if (begin) k_begin_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
-    dim3 gi((g.W + IT_W - 1) / IT_W, (g.H + IT_H - 1) / IT_H, nseq);
+    // rows [y0, y1) of the reference picture (everything, or in band mode the band's halo); the planes reach 16 rows further down
+    // (the features of the last rows sum 8 rows below them, SADs read 8 rows from a candidate's origin)
+    const int y0 = g.halo_y0, y1 = g.halo_y1, yi1 = std::min(g.H, y1 + 16);
+    dim3 gi((g.W + IT_W - 1) / IT_W, (yi1 - y0 + IT_H - 1) / IT_H, nseq);
     if (timing) CK(cudaEventRecord(s->evk[1], st));
-    k_interp<<<gi, 256, 0, st>>>(s->d_seqs, seq0, g);
+    k_interp<<<gi, 256, 0, st>>>(s->d_seqs, seq0, g, y0);
     if (timing) CK(cudaEventRecord(s->evk[2], st));
-    dim3 gf((g.W + FT_W - 1) / FT_W, (g.H + FT_H - 1) / FT_H, nseq);
-    k_features<<<gf, 256, 0, st>>>(s->d_seqs, seq0, g, 0, nullptr);
+    dim3 gf((g.W + FT_W - 1) / FT_W, (y1 - y0 + FT_H - 1) / FT_H, nseq);
+    k_features<<<gf, 256, 0, st>>>(s->d_seqs, seq0, g, 0, nullptr, y0);
     if (timing) CK(cudaEventRecord(s->evk[3], st));
-    dim3 gt(g.ntiles, nseq);
-    k_tile_index<<<gt, 256, FH_CELLS * 4, st>>>(s->d_seqs, seq0, g);
+    const int ty0 = y0 / FH_TILE, ty1 = (y1 + FH_TILE - 1) / FH_TILE;
+    dim3 gt((ty1 - ty0) * g.tilesx, nseq);
+    k_tile_index<<<gt, 256, FH_CELLS * 4, st>>>(s->d_seqs, seq0, g, ty0 * g.tilesx);
     CKL();
     return FH264_OK;
 }
@@ -597,7 +606,7 @@ extern "C" int fh264_scene_sad_batch(fh264_session *s, int seq0, int nseq, uint6
     rc = adopt_uploads(s, s->stream, seq0, nseq); if (rc) return rc;
     k_zero_sad<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0);
     dim3 gs(nseq >= 8 ? 74 : 296, nseq);
-    k_scene_sad<<<gs, 256, 0, s->stream>>>(s->d_seqs, seq0, s->g);
+    k_scene_sad<<<gs, 256, 0, s->stream>>>(s->d_seqs, seq0, s->g, s->sad_y0, s->sad_y1);
     k_gather_sad<<<1, nseq, 0, s->stream>>>(s->d_seqs, seq0, s->d_sadout);
     CKL();
     CK(cudaMemcpyAsync(s->h_sad, s->d_sadout, sizeof(uint64_t) * nseq, cudaMemcpyDeviceToHost, s->stream));
@@ -672,7 +681,7 @@ static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh26
     if (L.timing) CK(cudaEventRecord(s->ev[0], st));
     k_begin_picture<<<1, nseq, 0, st>>>(s->d_seqs, seq0, L.d_ticket);
     if (gate) {
-        k_scene_sad<<<dim3(nseq >= 8 ? 74 : 296, nseq), 256, 0, st>>>(s->d_seqs, seq0, g);
+        k_scene_sad<<<dim3(nseq >= 8 ? 74 : 296, nseq), 256, 0, st>>>(s->d_seqs, seq0, g, s->sad_y0, s->sad_y1);
         if (gate == 1) k_scene_gate<<<1, nseq, 0, st>>>(s->d_seqs, seq0, (unsigned long long)g.nmb << 12);
     }
     if (hold) CK(cudaStreamWaitEvent(st, hold, 0));
@@ -753,7 +762,7 @@ static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh26
     }
     // dpb := reconstruction (frameDeepCopy, ref_frames.cpp:17-35) by pointer swap, then phase R for the next picture
     k_begin_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);          // before the barrier: a barrier timeout must survive into the next picture's status
-    if (g.world > 1) k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->epoch, g.rank, g.world);
+    if (g.world > 1) k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->epoch, g.rank, g.world, g.wait_mask);
     k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
     for (int b = seq0; b < seq0 + nseq; b++)
         {
@@ -1265,7 +1274,7 @@ extern "C" int fh264_debug_feature(fh264_session *s, int seq, int k, int f, uint
     CK(cudaMalloc(&tmp, (size_t)n * sizeof(uint4)));
     const Geo &g = s->g;
     dim3 gf((g.W + FT_W - 1) / FT_W, (g.H + FT_H - 1) / FT_H, 1);
-    k_features<<<gf, 256, 0, s->stream>>>(s->d_seqs, seq, g, f, tmp);
+    k_features<<<gf, 256, 0, s->stream>>>(s->d_seqs, seq, g, f, tmp, 0);
     k_unpack_feature<<<(n + 255) / 256, 256, 0, s->stream>>>(tmp, n, k, (uint16_t *)s->d_scr16[0]);
     CKL();
     CK(cudaMemcpyAsync(out, s->d_scr16[0], (size_t)n * 2, cudaMemcpyDeviceToHost, s->stream));
@@ -1308,6 +1317,8 @@ extern "C" int fh264_band_config(fh264_session *s, int rank, int world, int mb_r
     CK(sync_streams(s));
     Geo &g = s->g;
     g.rank = rank; g.world = world; g.band_mb0 = mb_row0 * g.Wmb; g.band_nmb = (mb_row1 - mb_row0) * g.Wmb;
+    g.halo_y0 = 0; g.halo_y1 = g.H; g.wait_mask = 0xffffffffu;       // until fh264_band_peers says where the other bands are
+    s->sad_y0 = 0; s->sad_y1 = g.H;
     // wavefront order restricted to the band
     std::vector<int> order(g.band_nmb);
     for (int i = 0; i < g.band_nmb; i++) order[i] = g.band_mb0 + i;
@@ -1320,6 +1331,46 @@ extern "C" int fh264_band_config(fh264_session *s, int rank, int world, int mb_r
     for (int b = 0; b < s->batch; b++)
         for (int c = 0; c < 3; c++) { s->h[b].peer_ref[rank][c] = s->h[b].ref[c]; s->h[b].peer_rec[rank][c] = s->h[b].rec[c]; }
     CK(cudaMemcpy(s->d_seqs, s->h.data(), sizeof(SeqDev) * s->batch, cudaMemcpyHostToDevice));
+    return FH264_OK;
+}
+
+// The bands of ALL ranks (mb_rows[2r], mb_rows[2r+1] = first / end macroblock row of rank r). With them the picture barrier stops
+// being global: this rank's phases A / S / B / C read the reference picture only within FH_BAND_HALO luma rows of its band (stage 2:
+// |dx| + |dy| < 280, moestimation.cpp:481; + the 8x8 block, the 8-row box sums below a position and the 6-tap's 3 rows), so phase R
+// covers only those rows (rounded to the 64-row index tiles) and the barrier waits only for the ranks whose bands they touch — rank r
+// starts picture t+1 while the wavefront of picture t is still running through the bands further down. From here on the scene SAD of
+// a rank covers its own band (the bands' sums add up to the picture's), and fh264_download_recon returns the whole picture only
+// after every rank has finished it (synchronise the ranks on the host first).
+#define FH_BAND_HALO 304
+extern "C" int fh264_band_peers(fh264_session *s, int world, const int *mb_rows)
+{
+    if (!s || !mb_rows) return fail(FH264_E_ARG, "null argument");
+    Geo &g = s->g;
+    if (world != g.world || g.world < 2) return fail(FH264_E_STATE, "fh264_band_config first (same world size)");
+    if (mb_rows[2 * g.rank] * g.Wmb != g.band_mb0 || (mb_rows[2 * g.rank + 1] - mb_rows[2 * g.rank]) * g.Wmb != g.band_nmb)
+        return fail(FH264_E_ARG, "this rank's entry differs from its fh264_band_config");
+    CK(cudaSetDevice(s->device));
+    CK(sync_streams(s));
+    // reads[a] = ranks whose bands rank a reads (its halo rows, 16 more for the planes below them, 3 for the 6-tap). Rank a must not
+    // start picture t+1 before they have delivered picture t — and must not OVERWRITE (its phase C of picture t+1 stores into the
+    // buffer that held picture t-1) what a rank that reads a's band may still be reading: the relation is made symmetric.
+    uint32_t reads[FH_MAX_WORLD] = { 0 };
+    int hy0[FH_MAX_WORLD], hy1[FH_MAX_WORLD];
+    for (int a = 0; a < world; a++) {
+        const int top = mb_rows[2 * a] * 16, bottom = mb_rows[2 * a + 1] * 16;
+        hy0[a] = std::max(0, top - FH_BAND_HALO) / FH_TILE * FH_TILE;
+        hy1[a] = std::min(g.H, (bottom + FH_BAND_HALO + FH_TILE - 1) / FH_TILE * FH_TILE);
+        const int need0 = hy0[a] - 3, need1 = std::min(g.H, hy1[a] + 16) + 3;
+        for (int r = 0; r < world; r++)
+            if (mb_rows[2 * r] * 16 < need1 && mb_rows[2 * r + 1] * 16 > need0) reads[a] |= 1u << r;
+        reads[a] |= 1u << a;
+        if (a + 1 < world) reads[a] |= 1u << (a + 1);        // the rank below reads this band's last row of vectors (qmv mirror): never more than a picture apart
+        if (a > 0) reads[a] |= 1u << (a - 1);
+    }
+    g.halo_y0 = hy0[g.rank]; g.halo_y1 = hy1[g.rank];
+    g.wait_mask = reads[g.rank];
+    for (int a = 0; a < world; a++) if ((reads[a] >> g.rank) & 1u) g.wait_mask |= 1u << a;
+    s->sad_y0 = mb_rows[2 * g.rank] * 16; s->sad_y1 = mb_rows[2 * g.rank + 1] * 16;
     return FH264_OK;
 }
 

@@ -11,14 +11,14 @@
 #define IT_H 16
 #define IT_PW (IT_W + 6)   // 70 columns: x0-2 .. x0+IT_W+3
 
-__global__ void __launch_bounds__(256) k_interp(const SeqDev *__restrict__ seqs, int seq0, Geo g)
+__global__ void __launch_bounds__(256) k_interp(const SeqDev *__restrict__ seqs, int seq0, Geo g, int yoff)
 {
     const SeqDev &S = seqs[seq0 + blockIdx.z];
     const uint8_t *__restrict__ ref = S.ref[0];
     __shared__ uint8_t pix[IT_H + 6][IT_PW + 2];   // E(x0-2+c, y0-2+r): edge-extended reference (mocomp.cpp:11-23)
     __shared__ uint8_t hv[IT_H][IT_PW + 2];        // column half-pel at (x0-2+c, y0+r)
     __shared__ uint8_t bh[IT_H + 1][IT_W];         // row half-pel at (x0+c, y0+r)
-    const int x0 = blockIdx.x * IT_W, y0 = blockIdx.y * IT_H, tid = threadIdx.x;
+    const int x0 = blockIdx.x * IT_W, y0 = yoff + blockIdx.y * IT_H, tid = threadIdx.x;       // yoff: first row of the band's halo (band mode)
     const int W = g.W, H = g.H;
 
     for (int i = tid; i < (IT_H + 6) * IT_PW; i += 256) {
@@ -71,13 +71,13 @@ __global__ void __launch_bounds__(256) k_interp(const SeqDev *__restrict__ seqs,
 // ~140 of a direct evaluation, so the kernel is bound by its 16-byte-per-position HBM writes.
 // Only plane `f` is materialised (phase R: f = 0 into S.kar, read by stage 3's integer window and the stage-2 index; the
 // quarter-pel planes' features are computed where they are needed, qfeat.cuh). `out` overrides the destination (debug tap).
-__global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seqs, int seq0, Geo g, int f, uint4 *__restrict__ out)
+__global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seqs, int seq0, Geo g, int f, uint4 *__restrict__ out, int yoff)
 {
     const SeqDev &S = seqs[seq0 + blockIdx.z];
     const uint8_t *__restrict__ pl = S.planes + (size_t)f * g.WH;
     __shared__ __align__(16) uint32_t t[FT_H + 8][(FT_W + 8) / 4];      // padded plane rows as words
     __shared__ uint16_t r8[FT_H + 8][FT_W + 2], r4[FT_H + 8][FT_W + 2], rc[FT_H + 8][FT_W + 2];
-    const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H, tid = threadIdx.x;
+    const int x0 = blockIdx.x * FT_W, y0 = yoff + blockIdx.y * FT_H, tid = threadIdx.x;
     const int W = g.W, H = g.H;
     // padded plane: replicate the last column / row (moestimation.cpp:107-115). W is a multiple of 16, so a word is either
     // entirely inside the picture or entirely in the padding.
@@ -140,12 +140,12 @@ __global__ void __launch_bounds__(256) k_features(const SeqDev *__restrict__ seq
 
 // One CTA per 64x64 tile of plane-0 positions. Cell = (K1>>6)*128 + (K2>>6) (the two half-sum gates of stage 2). Order inside a cell is arbitrary:
 // stage 2 re-derives the reference's arrival order (sum bucket, side, x, y) from the entry itself.
-__global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ seqs, int seq0, Geo g)
+__global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ seqs, int seq0, Geo g, int tile0)
 {
     extern __shared__ uint32_t hist[];   // FH_CELLS counters
     __shared__ uint32_t wsum[8];
     const SeqDev &S = seqs[seq0 + blockIdx.y];
-    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int tile = tile0 + blockIdx.x, tid = threadIdx.x;
     const int tx0 = (tile % g.tilesx) * FH_TILE, ty0 = (tile / g.tilesx) * FH_TILE;
     const int tw = min(FH_TILE, g.W - tx0), th = min(FH_TILE, g.H - ty0);
     const uint4 *__restrict__ K = S.kar;      // plane 0 (f = 0) feature records
@@ -201,12 +201,13 @@ __global__ void __launch_bounds__(256) k_tile_index(const SeqDev *__restrict__ s
 }
 
 // Scene-change measure. grid.x blocks per sequence, grid.y = sequence. Result: 64-bit sum in status[ST_SAD_LO/HI].
-__global__ void __launch_bounds__(256) k_scene_sad(const SeqDev *__restrict__ seqs, int seq0, Geo g)
+// (band mode: rows [y0, y1) = this rank's band — the bands' sums add up to the picture's)
+__global__ void __launch_bounds__(256) k_scene_sad(const SeqDev *__restrict__ seqs, int seq0, Geo g, int y0, int y1)
 {
     const SeqDev &S = seqs[seq0 + blockIdx.y];
-    const uint4 *__restrict__ a = (const uint4 *)S.cur[0];
-    const uint4 *__restrict__ b = (const uint4 *)S.ref[0];
-    const int n16 = g.WH >> 4;   // W is a multiple of 16
+    const uint4 *__restrict__ a = (const uint4 *)(S.cur[0] + (size_t)y0 * g.W);
+    const uint4 *__restrict__ b = (const uint4 *)(S.ref[0] + (size_t)y0 * g.W);
+    const int n16 = ((y1 - y0) * g.W) >> 4;   // W is a multiple of 16
     uint32_t acc = 0;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n16; i += gridDim.x * 256) {
         uint4 p = a[i], q = b[i];

@@ -294,6 +294,13 @@ int fh264_last_intra_ms(fh264_session *s, float *ms);
 #define FH264_IPC_HANDLES 9
 int fh264_band_config(fh264_session *s, int rank, int world, int mb_row0, int mb_row1);
 int fh264_ipc_export(fh264_session *s, int seq, uint8_t *handles /* FH264_IPC_HANDLES * FH264_IPC_HANDLE_BYTES */);
+/* Optional, after fh264_band_config on every rank: the bands of ALL ranks (mb_rows[2r], mb_rows[2r+1] = first / end MB row of rank r).
+ * The picture barrier then only waits for the ranks whose bands lie within this rank's halo (304 luma rows: stage 2 reaches 279,
+ * moestimation.cpp:481) and phase R only covers those rows, so a rank starts the next picture while the wavefront of the current one
+ * is still running through the bands further down (pictures are pipelined across the GPUs). From then on the scene SAD of a rank
+ * covers its own band (the ranks' sums add up to the picture's, ref_frames.cpp:210-224) and fh264_download_recon returns the whole
+ * picture only once every rank has finished it: synchronise the ranks on the host first. */
+int fh264_band_peers(fh264_session *s, int world, const int *mb_rows);
 int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const uint8_t *handles);
 
 /* Snapshot of the 16 status words of sequence seq after phase C of its last encode_p: [0] flags, [1] stage-2 pool

@@ -47,7 +47,10 @@ def _worker(rank, world, port, w, h, seed, npics, qp, window, maxdiff, q, stream
             bs.s.sync()
             bs.s.picture_status(0)
             assert so.coded() == [True]
-            assert so.scene_sad()[0] == oport.scene_sad(y, prev_recon_y), "scene SAD of picture %d on rank %d" % (t, rank)
+            # with the peers' bands known a rank measures its own band: the ranks' sums add up to the picture's (ref_frames.cpp:210-224)
+            parts = [None] * world
+            dist.all_gather_object(parts, int(so.scene_sad()[0]))
+            assert sum(parts) == oport.scene_sad(y, prev_recon_y), "scene SAD of picture %d" % t
             band = so.records.array[0][bs.mb_slice].copy()
         else:
             bs.upload_source(*clip.frame(t))
@@ -140,3 +143,79 @@ def test_band_mode_reports_a_missing_peer_instead_of_coding_from_an_incomplete_r
         p.join(120)
         assert p.exitcode == 0
     assert res[0] == "error -4", res
+
+
+def _worker_async(rank, world, port, w, h, seed, npics, qp, window, maxdiff, q):
+    """All pictures enqueued without any host synchronisation between them (fh264_upload_source_batch + fh264_encode_p_stream): with
+    the peers' bands known (fh264_band_peers) a rank whose halo is complete runs ahead of the ranks further down."""
+    import torch
+    import torch.distributed as dist
+    import h264_fer_b200 as fh
+    from h264_fer_b200 import native, synth
+    from h264_fer_b200.bands import BandSession
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    clip = synth.SynthClip(w, h, seed)
+    bs = BandSession(w, h, device=rank)
+    bs.upload_recon(*clip.frame(0))
+    bs.s.sync()
+    dist.barrier()
+    pic = w * h * 3 // 2
+    blocks, outs = [], []
+    for t in range(1, npics):
+        blk = native.PinnedArray((1, pic), np.uint8)
+        blk.array[0] = np.concatenate([p.ravel() for p in clip.frame(t)])
+        so = native.StreamOut(1, bs.s.nmb, records=True)
+        blocks.append(blk); outs.append(so)
+        bs.s.upload_source_batch(blk.ptr, pic)
+        bs.s.encode_p_stream(qp, window, maxdiff, scene_gate=2, out=so)
+    bs.s.sync()
+    bs.s.picture_status(0)
+    dist.barrier()                                            # every rank has finished every picture: the whole reconstruction is everywhere
+    recs = [fh.records_to_ints(bs.gather_records(so.records.array[0][bs.mb_slice].copy())) for so in outs]
+    sads = []
+    for so in outs:
+        parts = [None] * world
+        dist.all_gather_object(parts, int(so.scene_sad()[0]))
+        sads.append(sum(parts))
+    q.put((rank, (recs, sads, bs.download_recon())))
+    bs.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="band mode needs at least 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_band_mode_pipelined_pictures_match_oracle(world):
+    """A tall picture (68 macroblock rows, more than two halos) coded by 2 / 4 / 8 ranks with nothing synchronised between pictures:
+    the upper ranks start the next picture while the wavefront of the current one is still in the lower bands. Records of every
+    picture, the scene SADs (sum of the ranks' band sums) and the final reconstruction against the oracle."""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    from h264_fer_b200 import synth
+    from oracle import port
+    w, h, seed, npics, qp, window, maxdiff = 352, 1088, 21, 6, 28, 32, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_async, args=(r, world, 29647, w, h, seed, npics, qp, window, maxdiff, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    clip = synth.SynthClip(w, h, seed)
+    o = port.Oracle(w, h)
+    ref = clip.frame(0)
+    for t in range(1, npics):
+        assert not o.phase_r(ref[0])
+        want_sad = port.scene_sad(clip.frame(t)[0], ref[0])
+        want, ref = o.encode_p(clip.frame(t), ref, qp, window, maxdiff)
+        for r in range(world):
+            recs, sads, _ = res[r]
+            assert np.array_equal(recs[t - 1], want), "rank %d picture %d: %s" % (r, t, np.argwhere(recs[t - 1] != want)[:6].tolist())
+            assert sads[t - 1] == want_sad, "picture %d scene SAD" % t
+    for r in range(world):
+        assert all(np.array_equal(a, b) for a, b in zip(res[r][2], ref)), "rank %d final reconstruction" % r

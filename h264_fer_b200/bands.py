@@ -3,7 +3,9 @@
 One process per GPU (``torch.distributed`` only carries the setup: the CUDA-IPC handles of each rank's buffers). After
 setup the data path is entirely on the devices: the phase-B wavefront crosses GPUs through progress flags that each rank
 mirrors into the next rank's memory, the reconstructed bands travel as NVLink peer stores issued by phase C itself, and a
-device-side barrier separates pictures. Every rank must encode the same pictures in the same order.
+device-side barrier separates pictures — per halo: a rank only waits for the ranks whose bands its search can reach (304 luma rows),
+so pictures are pipelined across the GPUs. Every rank must encode the same pictures in the same order; the whole reconstruction
+is on every rank once ALL ranks have finished the picture (synchronise them on the host before ``download_recon``).
 """
 from __future__ import annotations
 

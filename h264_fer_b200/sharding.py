@@ -4,9 +4,10 @@
 * Macroblock-row bands of one picture (BASELINE config 4): contiguous bands, remainder rows to the first ranks (1080p:
   67 MB rows -> 9,9,9,8,8,8,8,8 on 8 GPUs). Phases A/S/C shard by band; the phase-B wavefront crosses the bands (the first MB
   row of a band needs the vectors of the band above). The exchange itself is not here: the kernels store the reconstruction and
-  the last MB row's vectors straight into the peers' memory (bands.py, csrc/phase_b.cuh, phase_c.cuh); stage 2 reaches +-291
-  luma rows, more than a band, so every rank keeps the whole reference picture. Only the partitioning arithmetic and the small
-  host-side reductions live here; they are what the gloo CPU tests exercise.
+  the last MB row's vectors straight into the peers' memory (bands.py, csrc/phase_b.cuh, phase_c.cuh); stage 2 reaches 279
+  luma rows, more than a band, so every rank keeps the whole reference picture but waits, per picture, only for the bands within
+  that halo (fh264_band_peers). Only the partitioning arithmetic and the small host-side reductions live here; they are what the
+  gloo CPU tests exercise.
 """
 from __future__ import annotations
 

@@ -33,6 +33,27 @@ def mb_row_bands(mb_rows: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+BAND_HALO = 304      # luma rows a band's search can reach (csrc/fh264_b200.cu FH_BAND_HALO: stage 2's 279 + block + box sums + 6-tap)
+INDEX_TILE = 64
+
+
+def band_wait_sets(bands: List[Tuple[int, int]], height: int) -> List[List[int]]:
+    """For every rank the ranks it waits for at the picture barrier (host mirror of fh264_band_peers): those whose bands lie within
+    its halo rows (rounded to the 64-row index tiles, + 16 rows of planes below and the 6-tap's 3), its direct neighbours (the rank
+    below reads the band's last row of vectors), and — the relation is symmetric — every rank that waits for it."""
+    n = len(bands)
+    reads = []
+    for a, (r0, r1) in enumerate(bands):
+        top, bottom = r0 * 16, r1 * 16
+        y0 = max(0, top - BAND_HALO) // INDEX_TILE * INDEX_TILE
+        y1 = min(height, (bottom + BAND_HALO + INDEX_TILE - 1) // INDEX_TILE * INDEX_TILE)
+        need0, need1 = y0 - 3, min(height, y1 + 16) + 3
+        s = {r for r, (q0, q1) in enumerate(bands) if q0 * 16 < need1 and q1 * 16 > need0}
+        s |= {a} | ({a + 1} if a + 1 < n else set()) | ({a - 1} if a > 0 else set())
+        reads.append(s)
+    return [sorted(reads[a] | {b for b in range(n) if a in reads[b]}) for a in range(n)]
+
+
 def reduce_max(value: float) -> float:
     """Max over ranks of a per-rank device time (ms); identity without an initialised process group."""
     import torch

@@ -105,3 +105,24 @@ def test_host_mirror_routes_idr_pictures():
     assert e.encode_picture(None, None, None) == (NAL_IDR, None)
     assert e.encode_picture(None, None, None)[0] == NAL_NON_IDR
     assert f.calls == ["src", "upload_recon", "src", "encode_p"]
+
+
+def test_band_wait_sets_are_symmetric_and_cover_the_halo():
+    """Host mirror of fh264_band_peers: at 1080p on 8 GPUs the first rank waits for four bands, not eight; every pair is mutual; the
+    neighbours are always in; with two ranks (or a small picture) everybody waits for everybody."""
+    from h264_fer_b200 import sharding
+    bands = sharding.mb_row_bands(67, 8)
+    ws = sharding.band_wait_sets(bands, 1072)
+    assert ws[0] == [0, 1, 2, 3] and ws[7] == [4, 5, 6, 7]
+    for a in range(8):
+        assert a in ws[a]
+        for b in ws[a]:
+            assert a in ws[b]
+        if a + 1 < 8:
+            assert a + 1 in ws[a]
+        lo, hi = bands[a][0] * 16 - 304, bands[a][1] * 16 + 304
+        for b, (q0, q1) in enumerate(bands):
+            if q0 * 16 < hi and q1 * 16 > lo:
+                assert b in ws[a], "rank %d reads rows of band %d" % (a, b)
+    assert sharding.band_wait_sets(sharding.mb_row_bands(67, 2), 1072) == [[0, 1], [0, 1]]
+    assert sharding.band_wait_sets(sharding.mb_row_bands(18, 4), 288) == [[0, 1, 2, 3]] * 4

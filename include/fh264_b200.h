@@ -299,7 +299,8 @@ int fh264_ipc_export(fh264_session *s, int seq, uint8_t *handles /* FH264_IPC_HA
  * moestimation.cpp:481) and phase R only covers those rows, so a rank starts the next picture while the wavefront of the current one
  * is still running through the bands further down (pictures are pipelined across the GPUs). From then on the scene SAD of a rank
  * covers its own band (the ranks' sums add up to the picture's, ref_frames.cpp:210-224) and fh264_download_recon returns the whole
- * picture only once every rank has finished it: synchronise the ranks on the host first. */
+ * picture only once every rank has finished it: synchronise the ranks on the host first. FH264_E_UB_INPUT is raised by the ranks
+ * whose halo contains the offending window: treat any rank's status as the picture's. */
 int fh264_band_peers(fh264_session *s, int world, const int *mb_rows);
 int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const uint8_t *handles);
 

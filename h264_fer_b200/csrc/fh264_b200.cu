@@ -89,6 +89,7 @@ struct fh264_session {
     int tmap_rows;
     int use_tma;                    // FH264_TMA=0: fill the pixel windows with ordinary loads (development knob)
     int use_bw;                     // phase B kernel: 1 warp-level (phase_bw.cuh), 0 block-level, -1 (default) warp-level on the pipeline lanes only (FH264_PBW)
+    uint32_t band_epoch;            // band mode: epoch of the last picture announced at the picture barrier
     int sad_y0, sad_y1;             // luma rows the scene SAD covers: the picture, or this rank's band once the peers' bands are known
     int trace;                      // FH264_TRACE=1: per-lane timing events (fh264_debug_trace)
     int force_miss;                 // FH264_PBW_FORCE_MISS=1: the warp-level phase B treats every phase-S lookup as a miss (test knob)
@@ -151,6 +152,15 @@ __global__ void k_swap_ref(SeqDev *seqs, int seq0)
 // A timeout (a peer is missing or far behind: this rank's reference picture lacks that peer's band) is raised in ST_FLAGS_NEXT of
 // EVERY sequence of the call — the word phase R leaves alone after k_begin_ref, which therefore runs BEFORE this kernel — and
 // becomes the status of the next picture coded from that reference (FH264_E_STATE).
+// Waits (bounded) until every rank has announced picture `epoch` (band mode, before an I picture: it is coded whole by every rank and
+// reads what ALL bands of the previous P picture left — the per-halo barrier of that picture only waited for the neighbours).
+__global__ void k_band_wait_all(PeerSync ps, SeqDev *seqs, int seq0, int nseq, uint32_t epoch, int rank, int world)
+{
+    bool ok = true;
+    for (int r = 0; r < world; r++) ok &= wait_progress(&ps.p[rank][r], epoch, true);
+    if (!ok) for (int b = 0; b < nseq; b++) atomicOr(&seqs[seq0 + b].status[ST_FLAGS], FLAG_TIMEOUT);
+}
+
 // With the peers' bands known (fh264_band_peers) only the ranks whose bands touch this rank's halo are waited for (wait_mask): a rank
 // whose halo is complete goes on with phase R and the next picture while the wavefront of this one is still running further down.
 __global__ void k_band_barrier(PeerSync ps, SeqDev *seqs, int seq0, int nseq, uint32_t epoch, int rank, int world, uint32_t wait_mask)
@@ -289,7 +299,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     g.band_mb0 = 0; g.band_nmb = g.nmb; g.rank = 0; g.world = 1;
     g.wmb_magic = udiv_magic((uint32_t)g.Wmb);
     g.halo_y0 = 0; g.halo_y1 = height; g.wait_mask = 0xffffffffu;
-    s->sad_y0 = 0; s->sad_y1 = height;
+    s->sad_y0 = 0; s->sad_y1 = height; s->band_epoch = 0;
     s->has_ref.assign(batch, 0);
     s->prev_p.assign(batch, 0);
     s->last_i.assign(batch, 0);
@@ -367,7 +377,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         S.status = status_block + (size_t)b * ST_WORDS;     // one block: a range of sequences is snapshot by one copy
         S.results = results + (size_t)b * g.nmb;
         S.dbg = nullptr;
-        memset(S.peer_ref, 0, sizeof S.peer_ref); memset(S.peer_rec, 0, sizeof S.peer_rec);
+        memset(S.peer_ref, 0, sizeof S.peer_ref); memset(S.peer_rec, 0, sizeof S.peer_rec); memset(S.peer_motion, 0, sizeof S.peer_motion);
         S.peer_qmv_next = nullptr;
     }
     OPEN_CK(dalloc(s, &s->d_seqs, (size_t)batch));
@@ -762,7 +772,7 @@ static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh26
     }
     // dpb := reconstruction (frameDeepCopy, ref_frames.cpp:17-35) by pointer swap, then phase R for the next picture
     k_begin_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);          // before the barrier: a barrier timeout must survive into the next picture's status
-    if (g.world > 1) k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->epoch, g.rank, g.world, g.wait_mask);
+    if (g.world > 1) { k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->epoch, g.rank, g.world, g.wait_mask); s->band_epoch = s->epoch; }
     k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
     for (int b = seq0; b < seq0 + nseq; b++)
         {
@@ -954,7 +964,6 @@ extern "C" int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh26
 {
     int rc = check_seq(s, seq0, nseq); if (rc) return rc;
     if (qp < 0 || qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
-    if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "encode_i is not available in band mode");
     CK(cudaSetDevice(s->device));
     for (int b = seq0; b < seq0 + nseq; b++) if (s->gate_calls[b]) { CK(sync_streams(s)); break; }      // prev_p of a gated call is known once its status is home
     rc = enter_main(s); if (rc) return rc;
@@ -964,8 +973,11 @@ extern "C" int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh26
     rc = adopt_uploads(s, st, seq0, nseq); if (rc) return rc;
     if (s->lane[2].copy_pending) { CK(cudaStreamWaitEvent(st, s->lane[2].ev_copy_done, 0)); s->lane[2].copy_pending = false; }   // the I records reuse the result buffer
     s->epoch++;
+    // band mode: an I picture is not split — every rank codes the whole picture (it holds the whole source and, once all ranks have
+    // delivered the previous picture, everything an I picture reads across pictures); no exchange, identical results everywhere
     CK(cudaMemcpyAsync(s->d_prev_p + seq0, s->prev_p.data() + seq0, sizeof(int) * nseq, cudaMemcpyHostToDevice, st));
     k_begin_intra<<<1, nseq, 0, st>>>(s->d_ticket + 6, s->d_seqs, seq0);
+    if (g.world > 1) k_band_wait_all<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->band_epoch, g.rank, g.world);   // (a timeout fails this picture)
     int nl = 32;
     { const char *e = getenv("FH264_INTRA_LANES"); if (e && atoi(e) == 1) nl = 1; }   // development knob (read per call): everything on lane 0
     const unsigned ctas = (unsigned)std::min<long long>((long long)g.nmb * nseq, (long long)nseq * (g.Wmb + 16));
@@ -978,10 +990,18 @@ extern "C" int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh26
     CK(cudaMemcpyAsync(s->h_status + (size_t)seq0 * ST_WORDS, s->h[seq0].status, sizeof(uint32_t) * ST_WORDS * nseq, cudaMemcpyDeviceToHost, st));
     if (results) CK(cudaMemcpyAsync(results, s->h[seq0].results, sizeof(fh264_mb_result_i) * (size_t)g.nmb * nseq, cudaMemcpyDeviceToHost, st));
     // dpb := reconstruction, then phase R for the next picture (rbsp_encoding.cpp:317-322)
+    if (g.world > 1) {
+        // nobody may start the next P picture (whose phase C mirrors macroblock types into every rank) before every rank is through this one
+        k_begin_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);          // (before the barrier: its timeout must survive into the next picture's status)
+        k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->epoch, g.rank, g.world, 0xffffffffu);
+        s->band_epoch = s->epoch;
+    }
     k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
-    for (int b = seq0; b < seq0 + nseq; b++)
+    for (int b = seq0; b < seq0 + nseq; b++) {
         for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);
-    rc = launch_phase_r(s, st, true, seq0, nseq); if (rc) return rc;
+        for (int r = 0; r < FH_MAX_WORLD; r++) for (int c = 0; c < 3; c++) std::swap(s->h[b].peer_ref[r][c], s->h[b].peer_rec[r][c]);
+    }
+    rc = launch_phase_r(s, st, true, seq0, nseq, g.world == 1); if (rc) return rc;
     for (int b = seq0; b < seq0 + nseq; b++) { s->has_ref[b] = 1; s->prev_p[b] = 0; s->last_i[b] = 1; }
     CK(sync_streams(s));
     for (int b = seq0; b < seq0 + nseq; b++)
@@ -1085,7 +1105,6 @@ extern "C" int fh264_cavlc_i(fh264_session *s, int seq0, int nseq, int first_bit
 {
     int rc = check_seq(s, seq0, nseq); if (rc) return rc;
     if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
-    if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
     for (int b = seq0; b < seq0 + nseq; b++) if (s->gate_calls[b]) { CK(cudaSetDevice(s->device)); CK(sync_streams(s)); break; }
     for (int b = seq0; b < seq0 + nseq; b++) if (!s->last_i[b]) return fail(FH264_E_STATE, "cavlc_i: the last picture of the sequence was not coded by encode_i");
     CK(cudaSetDevice(s->device));
@@ -1329,7 +1348,7 @@ extern "C" int fh264_band_config(fh264_session *s, int rank, int world, int mb_r
     CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.band_nmb, cudaMemcpyHostToDevice));
     s->peer_sync.p[rank] = s->d_sync;
     for (int b = 0; b < s->batch; b++)
-        for (int c = 0; c < 3; c++) { s->h[b].peer_ref[rank][c] = s->h[b].ref[c]; s->h[b].peer_rec[rank][c] = s->h[b].rec[c]; }
+        { for (int c = 0; c < 3; c++) { s->h[b].peer_ref[rank][c] = s->h[b].ref[c]; s->h[b].peer_rec[rank][c] = s->h[b].rec[c]; } s->h[b].peer_motion[rank] = s->h[b].motion; }
     CK(cudaMemcpy(s->d_seqs, s->h.data(), sizeof(SeqDev) * s->batch, cudaMemcpyHostToDevice));
     return FH264_OK;
 }
@@ -1407,6 +1426,7 @@ extern "C" int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const 
     }
     SeqDev &S = s->h[seq];
     for (int c = 0; c < 3; c++) { S.peer_ref[peer_rank][c] = (uint8_t *)ptrs[c]; S.peer_rec[peer_rank][c] = (uint8_t *)ptrs[3 + c]; }
+    S.peer_motion[peer_rank] = (MbMotion *)ptrs[6];
     if (peer_rank == s->g.rank + 1) S.peer_qmv_next = (unsigned long long *)ptrs[7];
     s->peer_sync.p[peer_rank] = (uint32_t *)ptrs[8];
     CK(cudaMemcpy(&s->d_seqs[seq], &S, sizeof(SeqDev), cudaMemcpyHostToDevice));

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(32) k_intra(const SeqDev *__restrict__ seqs, c
         const int mb = wf_order[t / (uint32_t)nseq];
         const int mbx = mb % g.Wmb, mby = mb / g.Wmb;
         // mb_type_array[CurrMbAddr] of the previous picture (read before this macroblock's record replaces it)
-        const bool prev_skip = prev_p[b] && S.results[mb].mb_type == FH264_P_SKIP;
+        // (band mode: the records of the other bands live on other GPUs; phase C mirrored every macroblock's type into `motion`)
+        const bool prev_skip = prev_p[b] && (g.world > 1 ? S.motion[mb].mb_type : S.results[mb].mb_type) == FH264_P_SKIP;
         if (lane == 0) {
             for (int k = 0; k < 3; k++) { c.src[k] = S.cur[k]; c.rec[k] = S.rec[k]; }
             c.W = g.W; c.H = g.H; c.xP = mbx * 16; c.yP = mby * 16; c.qp = qp;

@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(128) k_phase_c(const SeqDev *__restrict__ seqs
             uint8_t *pp = S.peer_rec[pr][plane] + off;
 #pragma unroll
             for (int r = 0; r < 4; r++) *(uint32_t *)(pp + (size_t)r * pitch) = rw[r];
+            if (lane == 0) S.peer_motion[pr][mb].mb_type = mo.mb_type;
         }
     }
     __syncwarp();

@@ -273,7 +273,8 @@ typedef struct fh264_mb_result_i {
  * (intraPredictionEncoding + quantizationTransform, rbsp_encoding.cpp:196-215); then dpb := reconstruction and phase R, as after
  * fh264_encode_p. The bit-cost trial of a macroblock reads whether the SAME macroblock was P_Skip in the previous picture
  * (mb_type_array is only cleared after the first trial, intra.cpp:1008-1012); the session remembers that from its last
- * fh264_encode_p / fh264_decode_p. results: nseq * MBs records (host) or NULL. Synchronous. Not available in band mode. */
+ * fh264_encode_p / fh264_decode_p. results: nseq * MBs records (host) or NULL. Synchronous. Band mode: the picture is not split —
+ * every rank codes the whole picture (every rank must make the call; all ranks are waited for before and after it). */
 int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh264_mb_result_i *results);
 /* slice_data() of the I picture last coded by fh264_encode_i for sequences [seq0, seq0 + nseq): what the I-slice macroblock loop of
  * RBSP_encode writes between shd_write() and RBSP_trailing_bits() (rbsp_encoding.cpp:221-305: mb_type, prev_intra4x4_pred_mode_flag /

@@ -219,3 +219,60 @@ def test_band_mode_pipelined_pictures_match_oracle(world):
             assert sads[t - 1] == want_sad, "picture %d scene SAD" % t
     for r in range(world):
         assert all(np.array_equal(a, b) for a, b in zip(res[r][2], ref)), "rank %d final reconstruction" % r
+
+
+def _worker_ipi(rank, world, port, name, q):
+    """I -> P -> I in band mode on a committed fixture of the compiled reference: the I pictures are coded whole by every rank
+    (fh264_encode_i; the second one reads which macroblocks of the P picture were P_Skip — types mirrored by phase C from every band),
+    the P picture is split into bands."""
+    import torch
+    import torch.distributed as dist
+    import h264_fer_b200 as fh
+    from h264_fer_b200.bands import BandSession
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_intra_host import compare_i_records, golden_pictures
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params, pics = golden_pictures(name)
+    qp, window, maxdiff = int(params[4]), int(params[5]), int(params[6])
+    h, w = pics[0]["SRCY"].shape
+    bs = BandSession(w, h, device=rank)
+    outcome = "ok"
+    try:
+        for n, p in enumerate(pics):
+            bs.upload_source(p["SRCY"], p["SRCU"], p["SRCV"])
+            if "imbrec" in p:
+                rec = bs.s.encode_i(qp)[0]
+                compare_i_records(fh.i_records_to_ints(rec), p["imbrec"], "%s picture %d (I) on rank %d" % (name, n, rank))
+            else:
+                band = bs.encode_p(qp, window, maxdiff)
+                mine, ref = fh.records_to_ints(bs.gather_records(band)), p["mbrec"]
+                assert np.array_equal(mine[:, :17], ref[:, :17]) and np.array_equal(mine[:, 21:], ref[:, 21:]), "picture %d (P)" % n
+            dist.barrier()
+            for got, t in zip(bs.download_recon(), ("RECY", "RECU", "RECV")):
+                assert np.array_equal(got, p[t]), "picture %d: %s differs on rank %d" % (n, t, rank)
+    except AssertionError as e:
+        outcome = "FAILED: %s" % e
+    q.put((rank, outcome))
+    bs.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="band mode needs at least 2 GPUs")
+@pytest.mark.parametrize("name", ["intra_static_qp12_ipi", "intra_qcif_qp28_ipi"])
+def test_band_mode_codes_i_pictures_whole_on_every_rank(name):
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_ipi, args=(r, world, 29651, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert res == {0: "ok", 1: "ok"}, res

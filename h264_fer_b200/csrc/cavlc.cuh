@@ -26,7 +26,10 @@ struct CvSeq {                          // per sequence, allocated on the first 
     uint32_t *stat;                     // [0] flags, [1] total bits (first_bit included)
 };
 
-__global__ void __launch_bounds__(128) k_cavlc_prep(const SeqDev *__restrict__ seqs, const CvSeq *__restrict__ cvs, int seq0, int nmb)
+// par >= 0 (band mode, rank 0): the records are the gathered ones of that epoch parity instead of the sequence's own result buffer
+__device__ __forceinline__ const fh264_mb_result *cv_records(const SeqDev &S, int par) { return par >= 0 ? S.gather[par] : S.results; }
+
+__global__ void __launch_bounds__(128) k_cavlc_prep(const SeqDev *__restrict__ seqs, const CvSeq *__restrict__ cvs, int seq0, int nmb, int par)
 {
     const int mb = blockIdx.x * 128 + threadIdx.x;
     if (mb >= nmb) return;
@@ -34,14 +37,14 @@ __global__ void __launch_bounds__(128) k_cavlc_prep(const SeqDev *__restrict__ s
         if (mb == 0) { cvs[seq0 + blockIdx.y].stat[0] = 0; cvs[seq0 + blockIdx.y].stat[1] = 0; }
         return;
     }
-    const fh264_mb_result &r = seqs[seq0 + blockIdx.y].results[mb];
+    const fh264_mb_result &r = cv_records(seqs[seq0 + blockIdx.y], par)[mb];
     CvInfo o;
     cv_prepare(r.mb_type, r.luma, r.chroma_dc, r.chroma_ac, FH264_P_SKIP, o);
     cvs[seq0 + blockIdx.y].info[mb] = o;
     if (mb == 0) { cvs[seq0 + blockIdx.y].stat[0] = 0; cvs[seq0 + blockIdx.y].stat[1] = 0; }
 }
 
-__global__ void __launch_bounds__(128) k_cavlc_code(const SeqDev *__restrict__ seqs, const CvSeq *__restrict__ cvs, int seq0, int nmb, int wmb)
+__global__ void __launch_bounds__(128) k_cavlc_code(const SeqDev *__restrict__ seqs, const CvSeq *__restrict__ cvs, int seq0, int nmb, int wmb, int par)
 {
     const int mb = blockIdx.x * 128 + threadIdx.x;
     if (mb > nmb) return;
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(128) k_cavlc_code(const SeqDev *__restrict__ s
     int bad = 0;
     if (mb == nmb) { if (run > 0) cv_ue(b, (uint32_t)run); }
     else if (!cv.info[mb].skip) {
-        const fh264_mb_result &r = seqs[seq0 + blockIdx.y].results[mb];
+        const fh264_mb_result &r = cv_records(seqs[seq0 + blockIdx.y], par)[mb];
         const CvInfo me = cv.info[mb];
         CvInfo left, up;
         const bool hl = (mb % wmb) != 0, hu = mb >= wmb;

@@ -108,6 +108,8 @@ struct SeqDev {
     // band mode: the same buffers of the other ranks, mapped through CUDA IPC (NVLink peer access)
     uint8_t *peer_ref[FH_MAX_WORLD][3], *peer_rec[FH_MAX_WORLD][3];
     unsigned long long *peer_qmv_next;   // rank + 1: mirror of the band's last MB row (tagged quadrant words)
+    fh264_mb_result *gather[2];          // band mode: rank 0's copy of the WHOLE picture's records, one buffer per epoch parity — phase C of
+                                         // every rank stores its macroblocks' records there over NVLink, so rank 0 can entropy-code the slice
     MbMotion *peer_motion[FH_MAX_WORLD]; // every rank's motion records: phase C mirrors each macroblock's mb_type there (an I picture, coded
                                          // whole by every rank, needs to know which macroblocks of the previous P picture were P_Skip)
     long long *dbg;         // optional: nmb * 12 clock samples of phase B (fh264_debug_timeline), else null

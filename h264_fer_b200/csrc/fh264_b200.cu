@@ -378,6 +378,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
         S.results = results + (size_t)b * g.nmb;
         S.dbg = nullptr;
         memset(S.peer_ref, 0, sizeof S.peer_ref); memset(S.peer_rec, 0, sizeof S.peer_rec); memset(S.peer_motion, 0, sizeof S.peer_motion);
+        S.gather[0] = S.gather[1] = nullptr;
         S.peer_qmv_next = nullptr;
     }
     OPEN_CK(dalloc(s, &s->d_seqs, (size_t)batch));
@@ -734,7 +735,7 @@ static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh26
     if (L.timing) CK(cudaEventRecord(s->ev[2], st));
     dim3 gc((g.band_nmb + 3) / 4, nseq);
     if (L.copy_pending) { CK(cudaStreamWaitEvent(st, L.ev_copy_done, 0)); L.copy_pending = false; }   // records of the previous picture are home
-    k_phase_c<<<gc, 128, 0, st>>>(s->d_seqs, seq0, g, prm);
+    k_phase_c<<<gc, 128, 0, st>>>(s->d_seqs, seq0, g, prm, s->epoch);
     CKL();
     if (tr) CK(cudaEventRecord(tr[3], st));
     for (int b = seq0; b < seq0 + nseq; b++) { CK(cudaEventRecord(s->ev_free[(int)s->cur_set[b]][b], st)); s->free_valid[(int)s->cur_set[b]][b] = 1; }   // `cur` is free for the upload after next
@@ -756,8 +757,11 @@ static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh26
         if (o.cavlc) {
             const int nmb = g.nmb, wmb = g.Wmb;
             for (int b = seq0; b < seq0 + nseq; b++) CK(cudaMemsetAsync(s->cvh[b].stream, 0, (size_t)CV_STREAM_BYTES + 64, L.cp));
-            k_cavlc_prep<<<dim3((nmb + 127) / 128, nseq), 128, 0, L.cp>>>(s->d_seqs, s->d_cvs, seq0, nmb);
-            k_cavlc_code<<<dim3((nmb + 1 + 127) / 128, nseq), 128, 0, L.cp>>>(s->d_seqs, s->d_cvs, seq0, nmb, wmb);
+            // band mode (rank 0): the slice is coded from the records every rank's phase C gathered here — once all of them are through
+            const int par = g.world > 1 ? (int)(s->epoch & 1u) : -1;
+            if (g.world > 1) k_band_wait_all<<<1, 1, 0, L.cp>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->epoch, g.rank, g.world);
+            k_cavlc_prep<<<dim3((nmb + 127) / 128, nseq), 128, 0, L.cp>>>(s->d_seqs, s->d_cvs, seq0, nmb, par);
+            k_cavlc_code<<<dim3((nmb + 1 + 127) / 128, nseq), 128, 0, L.cp>>>(s->d_seqs, s->d_cvs, seq0, nmb, wmb, par);
             k_cavlc_scan<<<nseq, 1024, 0, L.cp>>>(s->d_cvs, seq0, nmb, o.first_bit);
             k_cavlc_pack<<<dim3((nmb + 1 + 3) / 4, nseq), 128, 0, L.cp>>>(s->d_cvs, seq0, nmb, o.first_bit);
             CKL();
@@ -885,7 +889,7 @@ extern "C" int fh264_encode_p_stream(fh264_session *s, int seq0, int nseq, const
     if (out) {
         o.records = out->records; o.status = out->status;
         if (out->slice) {
-            if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
+            if (s->g.world > 1 && s->g.rank != 0) return fail(FH264_E_UNSUPPORTED, "band mode: the slice is entropy-coded on rank 0, where the picture's records are gathered");
             if (!out->slice_stat || out->first_bit < 0 || out->first_bit > 7 || out->slice_copy_bytes > out->slice_stride || out->slice_copy_bytes > (size_t)CV_STREAM_BYTES)
                 return fail(FH264_E_ARG, "slice output: slice_stat missing, first_bit outside 0..7 or copy size above the stride / 500000");
             o.cavlc = 1; o.first_bit = out->first_bit; o.slice = out->slice; o.slice_stride = out->slice_stride; o.slice_copy = out->slice_copy_bytes;
@@ -1084,7 +1088,8 @@ extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit
 {
     int rc = check_seq(s, seq0, nseq); if (rc) return rc;
     if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
-    if (s->g.world > 1) return fail(FH264_E_UNSUPPORTED, "device CAVLC needs the whole picture on one GPU (not available in band mode)");
+    if (s->g.world > 1 && (s->g.rank != 0 || !s->h[seq0].gather[0]))
+        return fail(FH264_E_UNSUPPORTED, "band mode: the picture's records are gathered on rank 0 — the slice is entropy-coded there (after fh264_ipc_import of every peer)");
     if (s->epoch == 0) return fail(FH264_E_STATE, "cavlc_p before any encode_p");
     for (int b = seq0; b < seq0 + nseq; b++) if (s->gate_calls[b]) { CK(cudaSetDevice(s->device)); CK(sync_streams(s)); break; }
     for (int b = seq0; b < seq0 + nseq; b++)
@@ -1095,8 +1100,10 @@ extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit
     const int nmb = s->g.nmb, wmb = s->g.Wmb;
     cudaStream_t st = s->stream;
     for (int b = seq0; b < seq0 + nseq; b++) CK(cudaMemsetAsync(s->cvh[b].stream, 0, (size_t)CV_STREAM_BYTES + 64, st));
-    k_cavlc_prep<<<dim3((nmb + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb);
-    k_cavlc_code<<<dim3((nmb + 1 + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb, wmb);
+    const int par = s->g.world > 1 ? (int)(s->epoch & 1u) : -1;          // band mode (rank 0): the gathered records of this picture
+    if (s->g.world > 1) k_band_wait_all<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->band_epoch, s->g.rank, s->g.world);
+    k_cavlc_prep<<<dim3((nmb + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb, par);
+    k_cavlc_code<<<dim3((nmb + 1 + 127) / 128, nseq), 128, 0, st>>>(s->d_seqs, s->d_cvs, seq0, nmb, wmb, par);
     return cavlc_finish(s, seq0, nseq, first_bit, out, out_stride, nbits, mb_info);
 }
 
@@ -1348,6 +1355,9 @@ extern "C" int fh264_band_config(fh264_session *s, int rank, int world, int mb_r
     CK(cudaMemcpy(s->d_wf_order, order.data(), sizeof(int) * g.band_nmb, cudaMemcpyHostToDevice));
     s->peer_sync.p[rank] = s->d_sync;
     for (int b = 0; b < s->batch; b++)
+        for (int k = 0; k < 2; k++)
+            if (!s->h[b].gather[k]) CK(dalloc(s, &s->h[b].gather[k], (size_t)g.nmb));      // (used on rank 0; every rank exports one so that the handle blob is uniform)
+    for (int b = 0; b < s->batch; b++)
         { for (int c = 0; c < 3; c++) { s->h[b].peer_ref[rank][c] = s->h[b].ref[c]; s->h[b].peer_rec[rank][c] = s->h[b].rec[c]; } s->h[b].peer_motion[rank] = s->h[b].motion; }
     CK(cudaMemcpy(s->d_seqs, s->h.data(), sizeof(SeqDev) * s->batch, cudaMemcpyHostToDevice));
     return FH264_OK;
@@ -1393,7 +1403,7 @@ extern "C" int fh264_band_peers(fh264_session *s, int world, const int *mb_rows)
     return FH264_OK;
 }
 
-// handles: FH264_IPC_HANDLES x 64 bytes = ref[3], rec[3], motion, done, sync
+// handles: FH264_IPC_HANDLES x 64 bytes = ref[3], rec[3], motion, qmv, sync, gather[2]
 extern "C" int fh264_ipc_export(fh264_session *s, int seq, uint8_t *handles)
 {
     int rc = check_seq(s, seq, 1); if (rc) return rc;
@@ -1401,7 +1411,8 @@ extern "C" int fh264_ipc_export(fh264_session *s, int seq, uint8_t *handles)
     CK(cudaSetDevice(s->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == FH264_IPC_HANDLE_BYTES, "IPC handle size");
     const SeqDev &S = s->h[seq];
-    void *ptrs[FH264_IPC_HANDLES] = { S.ref[0], S.ref[1], S.ref[2], S.rec[0], S.rec[1], S.rec[2], S.motion, S.qmv, s->d_sync };
+    if (!S.gather[0]) return fail(FH264_E_STATE, "fh264_band_config first");
+    void *ptrs[FH264_IPC_HANDLES] = { S.ref[0], S.ref[1], S.ref[2], S.rec[0], S.rec[1], S.rec[2], S.motion, S.qmv, s->d_sync, S.gather[0], S.gather[1] };
     for (int i = 0; i < FH264_IPC_HANDLES; i++) {
         cudaIpcMemHandle_t h;
         CK(cudaIpcGetMemHandle(&h, ptrs[i]));
@@ -1420,13 +1431,16 @@ extern "C" int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const 
     for (int i = 0; i < FH264_IPC_HANDLES; i++) {
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + (size_t)i * FH264_IPC_HANDLE_BYTES, FH264_IPC_HANDLE_BYTES);
-        if (i == FH264_IPC_HANDLES - 1 && s->peer_sync.p[peer_rank]) { ptrs[i] = s->peer_sync.p[peer_rank]; continue; }   // sync area: once per peer
+        ptrs[i] = nullptr;
+        if (i == 8 && s->peer_sync.p[peer_rank]) { ptrs[i] = s->peer_sync.p[peer_rank]; continue; }   // sync area: once per peer
+        if (i >= 9 && peer_rank != 0) continue;                                                     // only rank 0 gathers the records
         CK(cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
         s->ipc_opened.push_back(ptrs[i]);
     }
     SeqDev &S = s->h[seq];
     for (int c = 0; c < 3; c++) { S.peer_ref[peer_rank][c] = (uint8_t *)ptrs[c]; S.peer_rec[peer_rank][c] = (uint8_t *)ptrs[3 + c]; }
     S.peer_motion[peer_rank] = (MbMotion *)ptrs[6];
+    if (peer_rank == 0) { S.gather[0] = (fh264_mb_result *)ptrs[9]; S.gather[1] = (fh264_mb_result *)ptrs[10]; }
     if (peer_rank == s->g.rank + 1) S.peer_qmv_next = (unsigned long long *)ptrs[7];
     s->peer_sync.p[peer_rank] = (uint32_t *)ptrs[8];
     CK(cudaMemcpy(&s->d_seqs[seq], &S, sizeof(SeqDev), cudaMemcpyHostToDevice));

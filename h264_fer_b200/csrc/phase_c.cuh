@@ -184,7 +184,7 @@ __device__ __forceinline__ void tq_lane(int lane, int qp, const int src[16], con
     for (int i = 0; i < 16; i++) recon[i] = clip255_(pred[i] + rr[i]);
 }
 
-__global__ void __launch_bounds__(128) k_phase_c(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm)
+__global__ void __launch_bounds__(128) k_phase_c(const SeqDev *__restrict__ seqs, int seq0, Geo g, fh264_params prm, uint32_t epoch)
 {
     __shared__ __align__(16) fh264_mb_result recs[4];
     const SeqDev &S = seqs[seq0 + blockIdx.y];
@@ -298,6 +298,10 @@ __global__ void __launch_bounds__(128) k_phase_c(const SeqDev *__restrict__ seqs
     __syncwarp();
     uint4 *dst = (uint4 *)&S.results[mb];
     for (int i = lane; i < (int)(sizeof(fh264_mb_result) / 16); i += 32) dst[i] = ((const uint4 *)rec)[i];
+    if (g.world > 1 && S.gather[0]) {                          // band mode: rank 0 collects the picture's records (device CAVLC of the slice)
+        uint4 *gd = (uint4 *)&S.gather[epoch & 1u][mb];
+        for (int i = lane; i < (int)(sizeof(fh264_mb_result) / 16); i += 32) gd[i] = ((const uint4 *)rec)[i];
+    }
 }
 
 // Stand-alone fused TQ over n macroblocks given source and prediction (unit tests; I-picture helper).

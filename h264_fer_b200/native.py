@@ -33,6 +33,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
            "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_cavlc_i", "fh264_last_timings", "fh264_last_spec_ms", "fh264_measure_int_peak", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import",
            "fh264_encode_p_stream", "fh264_set_pipeline", "fh264_upload_source_batch", "fh264_debug_trace", "fh264_band_peers"]
+IPC_BLOB_BYTES = 11 * 64        # FH264_IPC_HANDLES * FH264_IPC_HANDLE_BYTES
 STATUS_WORDS, ST_SAD_LO, ST_SAD_HI, ST_GATE, ST_GATED_TOTAL = 24, 8, 9, 17, 18
 
 
@@ -402,13 +403,13 @@ class Session:
         self._ck(self.L.fh264_band_peers(self.handle, len(bands), flat))
 
     def ipc_export(self, seq=0) -> bytes:
-        buf = np.zeros(9 * 64, np.uint8)
+        buf = np.zeros(IPC_BLOB_BYTES, np.uint8)
         self._ck(self.L.fh264_ipc_export(self.handle, seq, _ptr(buf)))
         return buf.tobytes()
 
     def ipc_import(self, seq, peer_rank, blob: bytes):
         buf = np.frombuffer(blob, np.uint8).copy()
-        assert buf.size == 9 * 64
+        assert buf.size == IPC_BLOB_BYTES
         self._ck(self.L.fh264_ipc_import(self.handle, seq, peer_rank, _ptr(buf)))
 
     def debug_trace(self):

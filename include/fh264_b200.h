@@ -181,7 +181,7 @@ int fh264_measure_int_peak(int device, double tops[4]);
  * its last, partially filled byte, so the returned bytes can be OR-ed / appended without shifting: sequence b's bytes start at
  * out + b * out_stride, bits [0, first_bit) are zero, slice data occupies bits [first_bit, nbits[b]), the rest of the last
  * byte is zero (RBSP_trailing_bits stays with the caller). Errors: FH264_E_UNSUPPORTED if a level needs level_prefix > 15
- * (outside the reference's level table, residual_tables.cpp:940-1008) or in band mode; FH264_E_CAPACITY if the slice data
+ * (outside the reference's level table, residual_tables.cpp:940-1008); FH264_E_CAPACITY if the slice data
  * exceeds the reference's 500000-byte RBSP buffer (fer_h264.cpp:93). */
 typedef struct fh264_cavlc_mb_info {   /* per macroblock, 32 bytes: what the reference's macroblock loop leaves in its host arrays */
     uint8_t skip;                      /* mb_type == P_Skip */
@@ -193,6 +193,9 @@ typedef struct fh264_cavlc_mb_info {   /* per macroblock, 32 bytes: what the ref
 } fh264_cavlc_mb_info;
 /* mb_info (nullable, nseq * MBs entries): side information a host that keeps coding I pictures with the reference's own code
  * needs to keep those arrays as the reference would (its intra bit-cost trials read them across pictures). */
+/* Band mode: phase C of every rank also stores its macroblocks' records into rank 0's memory (NVLink peer stores, one buffer per
+ * picture parity), so the slice — whose contexts cross the bands — is entropy-coded on rank 0 once all ranks have delivered the
+ * picture; the other ranks get FH264_E_UNSUPPORTED. */
 int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits,
                   fh264_cavlc_mb_info *mb_info);
 
@@ -292,7 +295,7 @@ int fh264_last_intra_ms(fh264_session *s, float *ms);
  * device-side barrier separates pictures. Setup: band_config on every rank, then exchange the export blobs (e.g. with
  * torch.distributed all_gather_object) and import every other rank's blob. */
 #define FH264_IPC_HANDLE_BYTES 64
-#define FH264_IPC_HANDLES 9
+#define FH264_IPC_HANDLES 11
 int fh264_band_config(fh264_session *s, int rank, int world, int mb_row0, int mb_row1);
 int fh264_ipc_export(fh264_session *s, int seq, uint8_t *handles /* FH264_IPC_HANDLES * FH264_IPC_HANDLE_BYTES */);
 /* Optional, after fh264_band_config on every rank: the bands of ALL ranks (mb_rows[2r], mb_rows[2r+1] = first / end MB row of rank r).

@@ -276,3 +276,71 @@ def test_band_mode_codes_i_pictures_whole_on_every_rank(name):
         p.join(120)
         assert p.exitcode == 0
     assert res == {0: "ok", 1: "ok"}, res
+
+
+def _worker_cavlc(rank, world, port, golden_path, q):
+    """P slices of a committed clip of the compiled reference coded in band mode; rank 0, where phase C of every rank gathers the
+    picture's records over NVLink, entropy-codes the slice on the device (fh264_cavlc_p): slice data against the reference's RBSP."""
+    import sys
+    import torch
+    import torch.distributed as dist
+    import h264_fer_b200 as fh
+    from h264_fer_b200.bands import BandSession
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import Golden
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = Golden(golden_path)
+    bs = BandSession(g.w, g.h, device=rank)
+    outcome, checked = "ok", 0
+    try:
+        for n, t in enumerate(g.types):
+            if t == 5:
+                bs.upload_recon(*g.rec(n))
+                bs.s.sync()
+                dist.barrier()
+                continue
+            bs.upload_source(*g.src(n))
+            bs.encode_p(g.qp, g.window, g.maxdiff, g.basic)
+            if rank == 0:
+                rbsp, bit0 = g.slice_rbsp(n)
+                data, nbits = bs.s.cavlc_p(first_bit=bit0 % 8)[0]
+                nd = nbits - bit0 % 8
+                ref, mine = np.unpackbits(np.asarray(rbsp, np.uint8)), np.unpackbits(np.asarray(data, np.uint8))
+                assert np.array_equal(mine[bit0 % 8:nbits], ref[bit0:bit0 + nd]), "picture %d: slice data differs" % n
+                tail = ref[bit0 + nd:]
+                assert tail[0] == 1 and not tail[1:].any() and len(tail) <= 8
+                checked += 1
+            else:
+                try:
+                    bs.s.cavlc_p()
+                    outcome = "FAILED: cavlc_p on rank %d did not refuse" % rank
+                except fh.Fh264Error as e:
+                    assert e.code == -7
+            dist.barrier()
+        if rank == 0:
+            assert checked == len(g.p_pictures())
+    except AssertionError as e:
+        outcome = "FAILED: %s" % e
+    q.put((rank, outcome))
+    bs.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="band mode needs at least 2 GPUs")
+def test_band_mode_slice_data_is_entropy_coded_on_rank_0():
+    import torch.multiprocessing as mp
+    world = 2
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qcif_w16_qp28.npz")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_cavlc, args=(r, world, 29653, path, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert res == {0: "ok", 1: "ok"}, res

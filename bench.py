@@ -41,8 +41,8 @@ CLIP_LEN = 6                          # distinct pictures per sequence (set per 
 CLIP_MAX = 40
 ALG_BYTES_PER_MB = 1984               # 384 src + 384 ref + 384 recon + 768 levels + 64 metadata
 ALG_INTOPS_PER_MB = 0.43e6
-LAUNCHES_PER_STEP = 15                # own kernels per step and group: source swap, begin, scene SAD, scene gate, stage 3, stage 2, phase S 2, B, C,
-                                      # begin-ref, dpb swap, phase R 3 (the e2e step adds the 4 entropy-coding kernels; --pipeline: two halves of 16)
+LAUNCHES_PER_STEP = 14                # own kernels per step and group: source swap, begin, scene SAD, scene gate, stage 3, stage 2, phase S 2, B, C,
+                                      # dpb swap, phase R 3 (the e2e step adds the 4 entropy-coding kernels; --pipeline: two halves of 15)
 # The same 0.43 M lane-ops per macroblock split over the kernels that do them (SURVEY.md §8d's per-stage counts; 4 partitions
 # per macroblock, 40 ops per feature-cost evaluation, 32 packed-byte ops per 8x8 SAD):
 #   stage 3: 1,475 evaluations + 33 SADs; stage 1 (phase S): 400 evaluations + 17 SADs; stage 2: ~100 evaluations + 32 SADs;

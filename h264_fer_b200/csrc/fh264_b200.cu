@@ -139,9 +139,11 @@ __global__ void k_gather_sad(SeqDev *seqs, int seq0, unsigned long long *out)
     const uint32_t *st = seqs[seq0 + threadIdx.x].status;
     out[threadIdx.x] = (unsigned long long)st[ST_SAD_LO] | ((unsigned long long)st[ST_SAD_HI] << 32);
 }
-__global__ void k_swap_ref(SeqDev *seqs, int seq0)
+// begin_ref: 1 = also what k_begin_ref does (one launch instead of two where no picture barrier sits between them)
+__global__ void k_swap_ref(SeqDev *seqs, int seq0, int begin_ref = 0)
 {
     SeqDev &S = seqs[seq0 + threadIdx.x];
+    if (begin_ref) S.status[ST_FLAGS_NEXT] = 0;
     for (int c = 0; c < 3; c++) { uint8_t *t = S.ref[c]; S.ref[c] = S.rec[c]; S.rec[c] = t; }
     for (int r = 0; r < FH_MAX_WORLD; r++)
         for (int c = 0; c < 3; c++) { uint8_t *t = S.peer_ref[r][c]; S.peer_ref[r][c] = S.peer_rec[r][c]; S.peer_rec[r][c] = t; }
@@ -775,9 +777,12 @@ static int encode_lane(fh264_session *s, Lane &L, int seq0, int nseq, const fh26
         L.copy_pending = true;
     }
     // dpb := reconstruction (frameDeepCopy, ref_frames.cpp:17-35) by pointer swap, then phase R for the next picture
-    k_begin_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);          // before the barrier: a barrier timeout must survive into the next picture's status
-    if (g.world > 1) { k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->epoch, g.rank, g.world, g.wait_mask); s->band_epoch = s->epoch; }
-    k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);
+    if (g.world > 1) {
+        k_begin_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0);      // before the barrier: a barrier timeout must survive into the next picture's status
+        k_band_barrier<<<1, 1, 0, st>>>(s->peer_sync, s->d_seqs, seq0, nseq, s->epoch, g.rank, g.world, g.wait_mask);
+        s->band_epoch = s->epoch;
+    }
+    k_swap_ref<<<1, nseq, 0, st>>>(s->d_seqs, seq0, g.world == 1);
     for (int b = seq0; b < seq0 + nseq; b++)
         {
             for (int c = 0; c < 3; c++) std::swap(s->h[b].ref[c], s->h[b].rec[c]);

@@ -433,6 +433,14 @@ extern "C" int fh264_sync(fh264_session *s)
 extern "C" void *fh264_host_alloc(size_t bytes) { void *p = nullptr; return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
 extern "C" void fh264_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+// band mode and every peer's sync area mapped (fh264_ipc_import done for all of them)
+static bool band_linked(const fh264_session *s)
+{
+    if (s->g.world < 2) return false;
+    for (int r = 0; r < s->g.world; r++) if (!s->peer_sync.p[r]) return false;
+    return true;
+}
+
 static int check_seq(fh264_session *s, int seq0, int nseq)
 {
     if (!s) return fail(FH264_E_ARG, "null session");
@@ -599,6 +607,9 @@ extern "C" int fh264_upload_recon(fh264_session *s, int seq, const uint8_t *y, c
     CK(cudaSetDevice(s->device));
     rc = enter_main(s); if (rc) return rc;
     const size_t WH = (size_t)s->g.WH;
+    // band mode: the per-halo picture barrier lets this rank run ahead of ranks that are still storing their band of the previous
+    // picture into the very buffer the upload replaces — all of them are waited for first
+    if (band_linked(s)) k_band_wait_all<<<1, 1, 0, s->stream>>>(s->peer_sync, s->d_seqs, seq, 1, s->band_epoch, s->g.rank, s->g.world);
     CK(cudaMemcpyAsync(s->h[seq].ref[0], y, WH, cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->h[seq].ref[1], cb, WH / 4, cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->h[seq].ref[2], cr, WH / 4, cudaMemcpyHostToDevice, s->stream));

@@ -828,6 +828,7 @@ static int check_encode_p(fh264_session *s, int seq0, int nseq, const fh264_para
 static int encode_dispatch(fh264_session *s, int seq0, int nseq, const fh264_params *p, int gate, bool piped, const StreamOut &o)
 {
     CK(cudaSetDevice(s->device));
+    if (s->g.world > 1 && !band_linked(s)) return fail(FH264_E_STATE, "band mode: fh264_ipc_import every peer before coding");
     fh264_params prm = *p;
     prm.basic = prm.basic ? 1 : 0;
     s->epoch++;
@@ -985,6 +986,7 @@ extern "C" int fh264_encode_i(fh264_session *s, int seq0, int nseq, int qp, fh26
     int rc = check_seq(s, seq0, nseq); if (rc) return rc;
     if (qp < 0 || qp > 51) return fail(FH264_E_ARG, "qp outside 0..51");
     CK(cudaSetDevice(s->device));
+    if (s->g.world > 1 && !band_linked(s)) return fail(FH264_E_STATE, "band mode: fh264_ipc_import every peer before coding");
     for (int b = seq0; b < seq0 + nseq; b++) if (s->gate_calls[b]) { CK(sync_streams(s)); break; }      // prev_p of a gated call is known once its status is home
     rc = enter_main(s); if (rc) return rc;
     rc = ensure_intra(s); if (rc) return rc;

@@ -493,7 +493,10 @@ def main():
     groups = []
     band = None
     if not args.no_bands:
-        band = band_measure(args, rank, world, local)          # N = 1: the single-sequence latency the band split is measured against
+        try:
+            band = band_measure(args, rank, world, local)      # N = 1: the single-sequence latency the band split is measured against
+        except Exception as ex:                                # (the replica measurement above stands on its own)
+            band = {"error": repr(ex)}
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()

@@ -16,7 +16,7 @@ from .native import MB_RESULT_DTYPE, Session
 
 
 class BandSession:
-    def __init__(self, width, height, device, rank=None, world=None, pipelined=True):
+    def __init__(self, width, height, device, rank=None, world=None, pipelined=True, gather=False):
         import torch.distributed as dist
         self.rank = (dist.get_rank() if dist.is_initialized() else 0) if rank is None else rank
         self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else world
@@ -36,6 +36,9 @@ class BandSession:
             if pipelined:
                 # every rank knows every band: the picture barrier becomes a wait for the ranks within the halo (fh264_band_peers)
                 self.s.band_peers(self.bands)
+            if gather:
+                # rank 0 collects the whole picture's records (phase C of every rank stores them there): device CAVLC of the slice
+                self.s.band_gather(True)
             dist.barrier()
 
     @property

@@ -58,6 +58,7 @@ struct Geo {
     // picture barrier only waits for the ranks in wait_mask, whose bands they touch. Whole picture / all ranks otherwise.
     int halo_y0, halo_y1;
     uint32_t wait_mask;
+    int gather_on;                  // band mode: phase C also stores every record into rank 0's gather buffer (fh264_band_gather)
 };
 #define FH_MAX_WORLD 8
 

@@ -300,7 +300,7 @@ extern "C" int fh264_open(int width, int height, int batch, int device, fh264_se
     g.WH = width * height;
     g.band_mb0 = 0; g.band_nmb = g.nmb; g.rank = 0; g.world = 1;
     g.wmb_magic = udiv_magic((uint32_t)g.Wmb);
-    g.halo_y0 = 0; g.halo_y1 = height; g.wait_mask = 0xffffffffu;
+    g.halo_y0 = 0; g.halo_y1 = height; g.wait_mask = 0xffffffffu; g.gather_on = 0;
     s->sad_y0 = 0; s->sad_y1 = height; s->band_epoch = 0;
     s->has_ref.assign(batch, 0);
     s->prev_p.assign(batch, 0);
@@ -906,7 +906,7 @@ extern "C" int fh264_encode_p_stream(fh264_session *s, int seq0, int nseq, const
     if (out) {
         o.records = out->records; o.status = out->status;
         if (out->slice) {
-            if (s->g.world > 1 && s->g.rank != 0) return fail(FH264_E_UNSUPPORTED, "band mode: the slice is entropy-coded on rank 0, where the picture's records are gathered");
+            if (s->g.world > 1 && (s->g.rank != 0 || !s->g.gather_on)) return fail(FH264_E_UNSUPPORTED, "band mode: the slice is entropy-coded on rank 0, and only with the record gather on (fh264_band_gather)");
             if (!out->slice_stat || out->first_bit < 0 || out->first_bit > 7 || out->slice_copy_bytes > out->slice_stride || out->slice_copy_bytes > (size_t)CV_STREAM_BYTES)
                 return fail(FH264_E_ARG, "slice output: slice_stat missing, first_bit outside 0..7 or copy size above the stride / 500000");
             o.cavlc = 1; o.first_bit = out->first_bit; o.slice = out->slice; o.slice_stride = out->slice_stride; o.slice_copy = out->slice_copy_bytes;
@@ -1106,8 +1106,8 @@ extern "C" int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit
 {
     int rc = check_seq(s, seq0, nseq); if (rc) return rc;
     if (!out || !nbits || first_bit < 0 || first_bit > 7) return fail(FH264_E_ARG, "bad argument");
-    if (s->g.world > 1 && (s->g.rank != 0 || !s->h[seq0].gather[0]))
-        return fail(FH264_E_UNSUPPORTED, "band mode: the picture's records are gathered on rank 0 — the slice is entropy-coded there (after fh264_ipc_import of every peer)");
+    if (s->g.world > 1 && (s->g.rank != 0 || !s->g.gather_on || !s->h[seq0].gather[0]))
+        return fail(FH264_E_UNSUPPORTED, "band mode: the slice is entropy-coded on rank 0, and only with the record gather on (fh264_band_gather on every rank, after fh264_ipc_import)");
     if (s->epoch == 0) return fail(FH264_E_STATE, "cavlc_p before any encode_p");
     for (int b = seq0; b < seq0 + nseq; b++) if (s->gate_calls[b]) { CK(cudaSetDevice(s->device)); CK(sync_streams(s)); break; }
     for (int b = seq0; b < seq0 + nseq; b++)
@@ -1418,6 +1418,18 @@ extern "C" int fh264_band_peers(fh264_session *s, int world, const int *mb_rows)
     g.wait_mask = reads[g.rank];
     for (int a = 0; a < world; a++) if ((reads[a] >> g.rank) & 1u) g.wait_mask |= 1u << a;
     s->sad_y0 = mb_rows[2 * g.rank] * 16; s->sad_y1 = mb_rows[2 * g.rank + 1] * 16;
+    return FH264_OK;
+}
+
+// Band mode: from the next picture on, phase C of this rank also stores every macroblock's record into rank 0's gather buffer (6.7 MB per
+// 1080p picture over NVLink in total), so that rank 0 can entropy-code the slice (fh264_cavlc_p). Every rank must make the same call.
+extern "C" int fh264_band_gather(fh264_session *s, int on)
+{
+    if (!s) return fail(FH264_E_ARG, "null session");
+    if (s->g.world < 2) return fail(FH264_E_STATE, "fh264_band_config first");
+    CK(cudaSetDevice(s->device));
+    CK(sync_streams(s));
+    s->g.gather_on = on ? 1 : 0;
     return FH264_OK;
 }
 

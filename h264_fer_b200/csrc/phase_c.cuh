@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(128) k_phase_c(const SeqDev *__restrict__ seqs
     __syncwarp();
     uint4 *dst = (uint4 *)&S.results[mb];
     for (int i = lane; i < (int)(sizeof(fh264_mb_result) / 16); i += 32) dst[i] = ((const uint4 *)rec)[i];
-    if (g.world > 1 && S.gather[0]) {                          // band mode: rank 0 collects the picture's records (device CAVLC of the slice)
+    if (g.world > 1 && g.gather_on && S.gather[0]) {                          // band mode: rank 0 collects the picture's records (device CAVLC of the slice)
         uint4 *gd = (uint4 *)&S.gather[epoch & 1u][mb];
         for (int i = lane; i < (int)(sizeof(fh264_mb_result) / 16); i += 32) gd[i] = ((const uint4 *)rec)[i];
     }

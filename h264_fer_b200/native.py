@@ -32,7 +32,7 @@ EXPORTS = ["fh264_open", "fh264_close", "fh264_last_error", "fh264_abi_version",
            "fh264_encode_p", "fh264_encode_p_async", "fh264_picture_status", "fh264_download_recon", "fh264_mode_counts",
            "fh264_tq_macroblocks", "fh264_tq_luma_intra16", "fh264_motion_compensate", "fh264_debug_plane",
            "fh264_debug_feature", "fh264_cavlc_p", "fh264_decode_p", "fh264_encode_i", "fh264_last_intra_ms", "fh264_cavlc_i", "fh264_last_timings", "fh264_last_spec_ms", "fh264_measure_int_peak", "fh264_debug_timeline", "fh264_debug_status", "fh264_band_config", "fh264_ipc_export", "fh264_ipc_import",
-           "fh264_encode_p_stream", "fh264_set_pipeline", "fh264_upload_source_batch", "fh264_debug_trace", "fh264_band_peers"]
+           "fh264_encode_p_stream", "fh264_set_pipeline", "fh264_upload_source_batch", "fh264_debug_trace", "fh264_band_peers", "fh264_band_gather"]
 IPC_BLOB_BYTES = 11 * 64        # FH264_IPC_HANDLES * FH264_IPC_HANDLE_BYTES
 STATUS_WORDS, ST_SAD_LO, ST_SAD_HI, ST_GATE, ST_GATED_TOTAL = 24, 8, 9, 17, 18
 
@@ -111,6 +111,7 @@ def load_library():
     L.fh264_set_pipeline.argtypes = [vp, i32]
     L.fh264_debug_trace.argtypes = [vp, vp]
     L.fh264_band_peers.argtypes = [vp, i32, C.POINTER(C.c_int)]
+    L.fh264_band_gather.argtypes = [vp, i32]
     L.fh264_upload_source_batch.argtypes = [vp, i32, i32, vp, C.c_size_t, i32]
     for name in EXPORTS:
         getattr(L, name)
@@ -401,6 +402,9 @@ class Session:
         """bands: [(first_mb_row, end_mb_row)] of every rank (fh264_band_peers): halo-restricted phase R and picture barrier."""
         flat = (C.c_int * (2 * len(bands)))(*[v for b in bands for v in b])
         self._ck(self.L.fh264_band_peers(self.handle, len(bands), flat))
+
+    def band_gather(self, on=True):
+        self._ck(self.L.fh264_band_gather(self.handle, 1 if on else 0))
 
     def ipc_export(self, seq=0) -> bytes:
         buf = np.zeros(IPC_BLOB_BYTES, np.uint8)

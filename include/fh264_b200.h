@@ -193,9 +193,9 @@ typedef struct fh264_cavlc_mb_info {   /* per macroblock, 32 bytes: what the ref
 } fh264_cavlc_mb_info;
 /* mb_info (nullable, nseq * MBs entries): side information a host that keeps coding I pictures with the reference's own code
  * needs to keep those arrays as the reference would (its intra bit-cost trials read them across pictures). */
-/* Band mode: phase C of every rank also stores its macroblocks' records into rank 0's memory (NVLink peer stores, one buffer per
- * picture parity), so the slice — whose contexts cross the bands — is entropy-coded on rank 0 once all ranks have delivered the
- * picture; the other ranks get FH264_E_UNSUPPORTED. */
+/* Band mode: after fh264_band_gather(s, 1) on every rank, phase C of every rank also stores its macroblocks' records into rank 0's
+ * memory (NVLink peer stores, one buffer per picture parity), so the slice — whose contexts cross the bands — is entropy-coded on
+ * rank 0 once all ranks have delivered the picture; the other ranks (and rank 0 without the gather) get FH264_E_UNSUPPORTED. */
 int fh264_cavlc_p(fh264_session *s, int seq0, int nseq, int first_bit, uint8_t *out, size_t out_stride, uint32_t *nbits,
                   fh264_cavlc_mb_info *mb_info);
 
@@ -306,6 +306,8 @@ int fh264_ipc_export(fh264_session *s, int seq, uint8_t *handles /* FH264_IPC_HA
  * picture only once every rank has finished it: synchronise the ranks on the host first. FH264_E_UB_INPUT is raised by the ranks
  * whose halo contains the offending window: treat any rank's status as the picture's. */
 int fh264_band_peers(fh264_session *s, int world, const int *mb_rows);
+/* Band mode, optional: gather every rank's macroblock records on rank 0 (see fh264_cavlc_p). Same call on every rank. */
+int fh264_band_gather(fh264_session *s, int on);
 int fh264_ipc_import(fh264_session *s, int seq, int peer_rank, const uint8_t *handles);
 
 /* Snapshot of the 16 status words of sequence seq after phase C of its last encode_p: [0] flags, [1] stage-2 pool

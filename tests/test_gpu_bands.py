@@ -293,7 +293,7 @@ def _worker_cavlc(rank, world, port, golden_path, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = Golden(golden_path)
-    bs = BandSession(g.w, g.h, device=rank)
+    bs = BandSession(g.w, g.h, device=rank, gather=True)
     outcome, checked = "ok", 0
     try:
         for n, t in enumerate(g.types):

@@ -65,16 +65,21 @@ class BatchEncoder:
     step, whose scene gate (Σ|frame − dpb| > MBs << 12, :210-224) may still stop it: such a sequence is then coded as an IDR picture
     too, exactly as the reference would have. Returns per sequence (nal_unit_type, slice data bytes, bits)."""
 
-    def __init__(self, session: Session, qp=28, window=16, maxdiff_set=3, basic=0, intra_every=1000, first_bit=0, slice_bytes=500000):
-        from .native import PinnedArray, StreamOut
+    def __init__(self, session: Session, qp=28, window=16, maxdiff_set=3, basic=0, intra_every=1000, first_bit=0, slice_bytes=500000,
+                 buffers=None):
+        """buffers: (block, out) to use instead of pinned host memory of the CUDA library (CPU tests of the host logic)."""
         self.s = session
         self.n = session.batch
         self.qp, self.window, self.maxdiff_set, self.basic, self.intra_every, self.first_bit = qp, window, maxdiff_set, basic, intra_every, first_bit
         self.curr_frame_count = 0
         self.have_dpb = False
         self.pic_bytes = session.w * session.h * 3 // 2
-        self.block = PinnedArray((self.n, self.pic_bytes), np.uint8)
-        self.out = StreamOut(self.n, session.nmb, slice_bytes=slice_bytes, mb_info=True, first_bit=first_bit)
+        if buffers is None:
+            from .native import PinnedArray, StreamOut
+            self.block = PinnedArray((self.n, self.pic_bytes), np.uint8)
+            self.out = StreamOut(self.n, session.nmb, slice_bytes=slice_bytes, mb_info=True, first_bit=first_bit)
+        else:
+            self.block, self.out = buffers
 
     def encode_pictures(self, pictures):
         """pictures: one (Y, Cb, Cr) per sequence. Returns [(nal_unit_type, bytes, nbits)] per sequence."""

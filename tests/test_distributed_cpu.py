@@ -126,3 +126,47 @@ def test_band_wait_sets_are_symmetric_and_cover_the_halo():
                 assert b in ws[a], "rank %d reads rows of band %d" % (a, b)
     assert sharding.band_wait_sets(sharding.mb_row_bands(67, 2), 1072) == [[0, 1], [0, 1]]
     assert sharding.band_wait_sets(sharding.mb_row_bands(18, 4), 288) == [[0, 1, 2, 3]] * 4
+
+
+def test_batch_host_mirror_routes_pictures_by_the_reference_rules():
+    """BatchEncoder (encoder.py) on a fake session: first picture and every IntraEvery-th picture are IDR pictures for the whole batch
+    decided on the host (ref_frames.cpp:191); in between the batch goes through ONE streaming step, and a sequence the device-side
+    scene gate stopped (:210-224) is coded as an IDR picture right after, its source picture still current."""
+    import numpy as np
+    from h264_fer_b200.encoder import BatchEncoder, NAL_IDR, NAL_NON_IDR
+
+    class Block:
+        def __init__(self, n, nbytes): self.array = np.zeros((n, nbytes), np.uint8); self.ptr = 1234
+
+    class Out:
+        def __init__(self, n): self.n = n; self.gated = set()
+        def coded(self): return [b not in self.gated for b in range(self.n)]
+        def slices(self): return [(np.array([b], np.uint8), 8) for b in range(self.n)]
+
+    class Fake:
+        w, h, batch, nmb = 32, 16, 3, 2
+        def __init__(self): self.calls = []
+        def upload_source_batch(self, ptr, stride): self.calls.append(("upload", ptr, stride))
+        def encode_p_stream(self, qp, window, maxdiff, basic, scene_gate, out): self.calls.append(("stream", scene_gate))
+        def sync(self): self.calls.append(("sync",))
+        def picture_status(self, b): pass
+        def encode_i(self, qp, seq0=0, nseq=None): self.calls.append(("encode_i", seq0))
+        def cavlc_i(self, first_bit=0, seq0=0, nseq=None): return [(np.array([100 + seq0], np.uint8), 16)]
+
+    f, out = Fake(), Out(3)
+    be = BatchEncoder(f, intra_every=3, buffers=(Block(3, 32 * 16 * 3 // 2), out))
+    pics = [(np.full((16, 32), 10 * b, np.uint8), np.zeros((8, 16), np.uint8), np.zeros((8, 16), np.uint8)) for b in range(3)]
+    r0 = be.encode_pictures(pics)
+    assert [t for t, _, _ in r0] == [NAL_IDR] * 3 and [c[0] for c in f.calls] == ["upload", "encode_i", "encode_i", "encode_i"]
+    assert be.block.array[1, 0] == 10 and be.block.array[2, 32 * 16 - 1] == 20 and f.calls[0][1:] == (1234, 32 * 16 * 3 // 2)
+    f.calls.clear()
+    out.gated = {1}                                           # picture 1: the gate stops sequence 1
+    r1 = be.encode_pictures(pics)
+    assert [t for t, _, _ in r1] == [NAL_NON_IDR, NAL_IDR, NAL_NON_IDR]
+    assert [c[0] for c in f.calls] == ["upload", "stream", "sync", "encode_i"] and f.calls[1] == ("stream", 1) and f.calls[3] == ("encode_i", 1)
+    assert int(r1[1][1][0]) == 101 and r1[1][2] == 16 and int(r1[2][1][0]) == 2
+    f.calls.clear(); out.gated = set()
+    assert [t for t, _, _ in be.encode_pictures(pics)] == [NAL_NON_IDR] * 3
+    f.calls.clear()
+    assert [t for t, _, _ in be.encode_pictures(pics)] == [NAL_IDR] * 3          # currFrameCount 3 % IntraEvery 3 == 0
+    assert "stream" not in [c[0] for c in f.calls]

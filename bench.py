@@ -532,8 +532,12 @@ def main():
                          "peak_detail_tops": ipk_detail,
                          "note": "the motion-search kernels are bound by the integer pipe, not by HBM (SURVEY.md 8d): achieved = algorithmic lane-ops of the dominant "
                                  "kernel (%d per MB, the reference's own evaluation counts) x %d MB x %d pictures per launch / its live CUDA-event duration; "
-                                 "whole step: int_roofline; the HBM-shaped kernel: roofline_phase_c; HBM fraction of the dominant kernel: roofline_hbm"
-                                 % (ALG_INTOPS_BY_KERNEL[dom], nmb, Bk)},
+                                 "whole step: int_roofline; every kernel: int_roofline_by_kernel; the HBM-shaped kernel: roofline_phase_c; HBM fraction of "
+                                 "the dominant kernel: roofline_hbm"
+                                 % (ALG_INTOPS_BY_KERNEL[dom], nmb, Bk)
+                                 + ("; k_stage2's algorithmic count is the ~100 candidate evaluations + 32 SADs per partition only - SURVEY.md 8d deliberately does "
+                                    "not count the SEARCH for the candidates (the reference scans ~83 k bucket entries per partition, this kernel ~2.1 k index "
+                                    "entries), which is what the kernel spends its time on" if dom == "k_stage2" else "")},
             "roofline_hbm": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src},
             "roofline_phase_c": {"bound": "hbm", "kernel": "k_phase_c", "achieved": c_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": c_achieved / hbm_peak},
             "int_roofline_by_kernel": {k_: {"ops_per_mb": ALG_INTOPS_BY_KERNEL[k_], "ms": kernels[k_],
